@@ -1,0 +1,118 @@
+"""ctypes binding of oracle/liboracle.so (corr_oracle.c).  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+DMATCH = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"),
+                   ("distance", "<f4")])
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "corr_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def set_threads(n):
+    return lib().oracle_set_threads(int(n))
+
+
+def l2_knn2(Q, T):
+    Q = np.ascontiguousarray(Q, np.float32).reshape(-1, 128) if Q.size else np.zeros((0, 128), np.float32)
+    T = np.ascontiguousarray(T, np.float32).reshape(-1, 128) if T.size else np.zeros((0, 128), np.float32)
+    idx = np.full((Q.shape[0], 2), -1, np.int32)
+    dist = np.zeros((Q.shape[0], 2), np.float32)
+    rc = lib().oracle_l2_knn2(_p(Q), Q.shape[0], _p(T), T.shape[0], 128, _p(idx), _p(dist))
+    assert rc == 0
+    return idx, dist
+
+
+def hamming_knn2(Q, T):
+    Q = np.ascontiguousarray(Q, np.uint8).reshape(-1, 32) if Q.size else np.zeros((0, 32), np.uint8)
+    T = np.ascontiguousarray(T, np.uint8).reshape(-1, 32) if T.size else np.zeros((0, 32), np.uint8)
+    idx = np.full((Q.shape[0], 2), -1, np.int32)
+    dist = np.zeros((Q.shape[0], 2), np.float32)
+    rc = lib().oracle_hamming_knn2(_p(Q), Q.shape[0], _p(T), T.shape[0], 32, _p(idx), _p(dist))
+    assert rc == 0
+    return idx, dist
+
+
+def ratio_test(idx, dist, ratio):
+    idx = np.ascontiguousarray(idx, np.int32)
+    dist = np.ascontiguousarray(dist, np.float32)
+    nq = idx.shape[0]
+    out = np.zeros(max(nq, 1), DMATCH)
+    n = ctypes.c_int(0)
+    rc = lib().oracle_ratio_test(_p(idx), _p(dist), nq, ctypes.c_double(ratio), _p(out),
+                                 ctypes.byref(n))
+    assert rc == 0
+    return out[: n.value].copy()
+
+
+def match_features(matcher, Q, T, ratio):
+    """matchFeatures restatement: returns the good matches as a DMATCH structured array."""
+    if matcher in (0, 1):
+        idx, dist = l2_knn2(Q, T)
+    elif matcher == 2:
+        idx, dist = hamming_knn2(Q, T)
+    else:
+        raise ValueError("bad matcher type")  # reference: throw std::exception()
+    return ratio_test(idx, dist, ratio)
+
+
+def gather_points(prev_xy, next_xy, matches):
+    prev_xy = np.ascontiguousarray(prev_xy, np.float32)
+    next_xy = np.ascontiguousarray(next_xy, np.float32)
+    m = np.ascontiguousarray(matches, DMATCH)
+    p1 = np.zeros((len(m), 2), np.float32)
+    p2 = np.zeros((len(m), 2), np.float32)
+    lib().oracle_gather_points(_p(prev_xy), _p(next_xy), _p(m), len(m), _p(p1), _p(p2))
+    return p1, p2
+
+
+def score_essential(pts1, pts2, K4, E, threshold_px, want_all_masks=False):
+    pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+    pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    E = np.ascontiguousarray(E, np.float64).reshape(-1, 9)
+    M, H = pts1.shape[0], E.shape[0]
+    counts = np.zeros(H, np.int32)
+    best = ctypes.c_int32(-1)
+    best_mask = np.zeros(M, np.uint8)
+    allm = np.zeros((H, M), np.uint8) if want_all_masks else None
+    rc = lib().oracle_score_essential(_p(pts1), _p(pts2), M, _p(K4), _p(E), H,
+                                      ctypes.c_double(threshold_px), _p(counts),
+                                      ctypes.byref(best), _p(best_mask),
+                                      _p(allm) if allm is not None else None)
+    assert rc == 0
+    return counts, int(best.value), best_mask, allm
+
+
+def sampson_errors(pts1, pts2, K4, E):
+    pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+    pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    E = np.ascontiguousarray(E, np.float64).reshape(-1, 9)
+    err = np.zeros((E.shape[0], pts1.shape[0]), np.float32)
+    rc = lib().oracle_sampson_errors(_p(pts1), _p(pts2), pts1.shape[0], _p(K4), _p(E),
+                                     E.shape[0], _p(err))
+    assert rc == 0
+    return err

@@ -1,0 +1,318 @@
+/*
+ * corr_oracle.c -- CPU restatement of the reference's correspondence hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * file's shared object, and there only as the checker or the timed CPU arm.  The product path
+ * (libslamb200.so) never links, loads or calls it and has no CPU fallback.
+ *
+ * What is restated (reference file:line are relative to /root/reference):
+ *   - matchFeatures            src/mainModule/featureMatching/featureMatchingCPU.cpp:17-43
+ *       DescriptorMatcher BRUTEFORCE (NORM_L2) / BRUTEFORCE_HAMMING, knnMatch(query=prev,
+ *       train=cur, k=2).  The arithmetic lives in OpenCV 4.8.0 (README.md:16, un-vendored):
+ *       cv::batchDistance -> hal::normL2Sqr_ / normHamming, then the strict-'<' top-K insert.
+ *   - getGoodMatches           src/mainModule/featureMatching/featureMatchingCommon.cpp:37-50
+ *   - getKeyPointCoordsFromFramePair  featureMatchingCommon.cpp:23-33
+ *   - findEssentialMat(RANSAC) scoring as called at
+ *                              src/mainModule/translation/cameraTranslation.cpp:41-46
+ *       (OpenCV calib3d five-point.cpp EMEstimatorCallback::computeError +
+ *        ptsetreg.cpp RANSACPointSetRegistrator::findInliers / run()).
+ *
+ * Parity pin: the reference ships no tests or golden vectors, so this
+ * oracle is pinned against the reference's own arithmetic owner, OpenCV, through the cv2 wheel
+ * (tests/test_oracle_vs_cv2.py, and the committed cv2-generated fixtures in tests/golden/ made by
+ * oracle/gen_golden.py).
+ *
+ * Build: see oracle/Makefile (-O2 -ffp-contract=off: no FMA contraction anywhere in here).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#include <limits.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    int32_t queryIdx;
+    int32_t trainIdx;
+    int32_t imgIdx;
+    float distance;
+} oracle_dmatch; /* bit-compatible with cv::DMatch */
+
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
+/* ---- L2: hal::normL2Sqr_ of the SSE-baseline OpenCV build -------------------------------
+ * Four 4-lane accumulators; element j = 16*i + 4*a + l is added to acc[a][l] with the multiply
+ * and the add rounded separately (v_muladd has no FMA on the SSE3 baseline); the accumulators are
+ * combined as ((acc0+acc1)+acc2)+acc3 lane-wise and the lanes as (S0+S2)+(S1+S3)
+ * (v_reduce_sum); a scalar left-to-right tail handles n % 16. */
+static float l2sqr_cv(const float* a, const float* b, int n) {
+    float acc[4][4];
+    int j = 0;
+    float d = 0.f;
+    memset(acc, 0, sizeof(acc));
+    for (; j <= n - 16; j += 16) {
+        for (int v = 0; v < 4; v++)
+            for (int l = 0; l < 4; l++) {
+                float t = a[j + 4 * v + l] - b[j + 4 * v + l];
+                float p = t * t;
+                acc[v][l] = acc[v][l] + p;
+            }
+    }
+    {
+        float S[4];
+        for (int l = 0; l < 4; l++) S[l] = ((acc[0][l] + acc[1][l]) + acc[2][l]) + acc[3][l];
+        d = (S[0] + S[2]) + (S[1] + S[3]);
+    }
+    for (; j < n; j++) {
+        float t = a[j] - b[j];
+        d += t * t;
+    }
+    return d;
+}
+
+static inline int32_t f2i(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
+static inline float i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
+
+/* BatchDistInvoker's top-K insert for K=2 on int-compared keys (positive floats compare like
+ * ints): strict '<' against the current K-th, shift while strictly greater -> equal distances
+ * keep the lower train index first. */
+static inline void top2_insert(int32_t d, int32_t j, int32_t* dk, int32_t* ik) {
+    if (d < dk[1]) {
+        if (dk[0] > d) {
+            dk[1] = dk[0]; ik[1] = ik[0];
+            dk[0] = d;     ik[0] = j;
+        } else {
+            dk[1] = d;     ik[1] = j;
+        }
+    }
+}
+
+/* BFMatcher(NORM_L2).knnMatch(Q, T, 2) raw result: idx[q][k] = -1 when absent, dist as float. */
+int oracle_l2_knn2(const float* Q, int nq, const float* T, int nt, int dim,
+                   int32_t* idx /* nq*2 */, float* dist /* nq*2 */) {
+    if (nq < 0 || nt < 0 || dim <= 0) return -1;
+#pragma omp parallel for schedule(static)
+    for (int q = 0; q < nq; q++) {
+        int32_t dk[2] = {f2i(FLT_MAX), f2i(FLT_MAX)};
+        int32_t ik[2] = {-1, -1};
+        const float* a = Q + (size_t)q * dim;
+        for (int t = 0; t < nt; t++) {
+            float d = sqrtf(l2sqr_cv(a, T + (size_t)t * dim, dim));
+            top2_insert(f2i(d), t, dk, ik);
+        }
+        idx[2 * q] = ik[0]; idx[2 * q + 1] = ik[1];
+        dist[2 * q] = i2f(dk[0]); dist[2 * q + 1] = i2f(dk[1]);
+    }
+    return 0;
+}
+
+/* BFMatcher(NORM_HAMMING).knnMatch: int distances = popcount(a ^ b), converted to float in the
+ * DMatch. */
+int oracle_hamming_knn2(const uint8_t* Q, int nq, const uint8_t* T, int nt, int nbytes,
+                        int32_t* idx, float* dist) {
+    if (nq < 0 || nt < 0 || nbytes <= 0) return -1;
+#pragma omp parallel for schedule(static)
+    for (int q = 0; q < nq; q++) {
+        int32_t dk[2] = {INT_MAX, INT_MAX};
+        int32_t ik[2] = {-1, -1};
+        const uint8_t* a = Q + (size_t)q * nbytes;
+        for (int t = 0; t < nt; t++) {
+            const uint8_t* b = T + (size_t)t * nbytes;
+            int32_t d = 0;
+            int j = 0;
+            for (; j + 8 <= nbytes; j += 8) {
+                uint64_t x, y;
+                memcpy(&x, a + j, 8); memcpy(&y, b + j, 8);
+                d += __builtin_popcountll(x ^ y);
+            }
+            for (; j < nbytes; j++) d += __builtin_popcount((unsigned)(a[j] ^ b[j]));
+            top2_insert(d, t, dk, ik);
+        }
+        idx[2 * q] = ik[0]; idx[2 * q + 1] = ik[1];
+        dist[2 * q] = ik[0] >= 0 ? (float)dk[0] : FLT_MAX;
+        dist[2 * q + 1] = ik[1] >= 0 ? (float)dk[1] : FLT_MAX;
+    }
+    return 0;
+}
+
+/* getGoodMatches (featureMatchingCommon.cpp:37-50): rows in ascending queryIdx, skip empty lists,
+ * keep [0] iff (double)d0 < ratio * (double)d1 (strict, in double).  The reference reads [1]
+ * unchecked when the list has one element (T == 1): undefined behaviour there; defined here as
+ * "reject the row" (SURVEY.md appendix A.5). */
+int oracle_ratio_test(const int32_t* idx, const float* dist, int nq, double ratio,
+                      oracle_dmatch* out, int* n_out) {
+    int n = 0;
+    for (int q = 0; q < nq; q++) {
+        if (idx[2 * q] < 0) continue;      /* empty list */
+        if (idx[2 * q + 1] < 0) continue;  /* single-element list: reference UB, defined reject */
+        if ((double)dist[2 * q] < ratio * (double)dist[2 * q + 1]) {
+            out[n].queryIdx = q;
+            out[n].trainIdx = idx[2 * q];
+            out[n].imgIdx = 0;
+            out[n].distance = dist[2 * q];
+            n++;
+        }
+    }
+    *n_out = n;
+    return 0;
+}
+
+/* getKeyPointCoordsFromFramePair (featureMatchingCommon.cpp:23-33): gather pt of the matched
+ * keypoints; kps are (x, y) float pairs. */
+int oracle_gather_points(const float* prev_xy, const float* next_xy, const oracle_dmatch* m,
+                         int n, float* pts1, float* pts2) {
+    for (int i = 0; i < n; i++) {
+        pts1[2 * i] = prev_xy[2 * m[i].queryIdx];
+        pts1[2 * i + 1] = prev_xy[2 * m[i].queryIdx + 1];
+        pts2[2 * i] = next_xy[2 * m[i].trainIdx];
+        pts2[2 * i + 1] = next_xy[2 * m[i].trainIdx + 1];
+    }
+    return 0;
+}
+
+/* findEssentialMat's point normalisation (five-point.cpp): points converted to double, then the
+ * Mat expression (col - c) / f, which OpenCV's MatExpr algebra folds into one scaled convert:
+ * x = u * (1/f) + (-c * (1/f)), every operation rounded separately in double. */
+void oracle_normalize_points(const float* pts, int n, double f_x, double f_y, double c_x,
+                             double c_y, double* out) {
+    double ax = 1.0 / f_x, ay = 1.0 / f_y;
+    double bx = -c_x * ax, by = -c_y * ay;
+    for (int i = 0; i < n; i++) {
+        double u = (double)pts[2 * i], v = (double)pts[2 * i + 1];
+        double pu = u * ax, pv = v * ay;
+        out[2 * i] = pu + bx;
+        out[2 * i + 1] = pv + by;
+    }
+}
+
+/* EMEstimatorCallback::computeError for one (model, match): Matx33d * Vec3d and Vec3d::dot are
+ * "s = 0; s += a*b" left-to-right sums; the error is rounded to float. */
+static inline float sampson_cv(const double* E, double x1, double y1, double x2, double y2) {
+    double Ex1[3], Etx2[3];
+    for (int r = 0; r < 3; r++) {
+        double s = 0;
+        s += E[3 * r + 0] * x1;
+        s += E[3 * r + 1] * y1;
+        s += E[3 * r + 2] * 1.0;
+        Ex1[r] = s;
+    }
+    for (int r = 0; r < 3; r++) {
+        double s = 0;
+        s += E[0 + r] * x2;
+        s += E[3 + r] * y2;
+        s += E[6 + r] * 1.0;
+        Etx2[r] = s;
+    }
+    double x2tEx1;
+    {
+        double s = 0;
+        s += x2 * Ex1[0];
+        s += y2 * Ex1[1];
+        s += 1.0 * Ex1[2];
+        x2tEx1 = s;
+    }
+    double a = Ex1[0] * Ex1[0];
+    double b = Ex1[1] * Ex1[1];
+    double c = Etx2[0] * Etx2[0];
+    double d = Etx2[1] * Etx2[1];
+    return (float)(x2tEx1 * x2tEx1 / (a + b + c + d));
+}
+
+/* Scores H fixed essential-matrix hypotheses against M matches the way the RANSAC loop of
+ * findEssentialMat does (cameraTranslation.cpp:41-46 -> ptsetreg.cpp): threshold_px is
+ * RPRANSACThreshold, divided by (fx+fy)/2; inlier iff err <= (float)(thr*thr); a model replaces
+ * the best iff count > max(best, 4) (strict: the first best wins).  best = -1 when no model has
+ * more than 4 inliers.  all_masks (H*M) is optional. */
+int oracle_score_essential(const float* pts1, const float* pts2, int M, const double* K4,
+                           const double* E, int H, double threshold_px, int32_t* counts,
+                           int32_t* best, uint8_t* best_mask, uint8_t* all_masks) {
+    if (M < 0 || H < 0) return -1;
+    double fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+    double* n1 = (double*)malloc(sizeof(double) * 2 * (size_t)(M > 0 ? M : 1));
+    double* n2 = (double*)malloc(sizeof(double) * 2 * (size_t)(M > 0 ? M : 1));
+    if (!n1 || !n2) { free(n1); free(n2); return -2; }
+    oracle_normalize_points(pts1, M, fx, fy, cx, cy, n1);
+    oracle_normalize_points(pts2, M, fx, fy, cx, cy, n2);
+    double thr = threshold_px / ((fx + fy) / 2);
+    float t = (float)(thr * thr);
+#pragma omp parallel for schedule(static)
+    for (int h = 0; h < H; h++) {
+        const double* Eh = E + 9 * (size_t)h;
+        int32_t nz = 0;
+        for (int i = 0; i < M; i++) {
+            float err = sampson_cv(Eh, n1[2 * i], n1[2 * i + 1], n2[2 * i], n2[2 * i + 1]);
+            int f = err <= t;
+            if (all_masks) all_masks[(size_t)h * M + i] = (uint8_t)f;
+            nz += f;
+        }
+        counts[h] = nz;
+    }
+    int32_t bi = -1, bc = 0;
+    for (int h = 0; h < H; h++) {
+        int32_t lim = bc > 4 ? bc : 4;
+        if (counts[h] > lim) { bc = counts[h]; bi = h; }
+    }
+    *best = bi;
+    if (best_mask) {
+        if (bi >= 0) {
+            const double* Eh = E + 9 * (size_t)bi;
+            for (int i = 0; i < M; i++) {
+                float err = sampson_cv(Eh, n1[2 * i], n1[2 * i + 1], n2[2 * i], n2[2 * i + 1]);
+                best_mask[i] = (uint8_t)(err <= t);
+            }
+        } else {
+            memset(best_mask, 0, (size_t)M);
+        }
+    }
+    free(n1); free(n2);
+    return 0;
+}
+
+/* Raw per-(hypothesis, match) float errors, for tests that want to look at the margin to the
+ * threshold. */
+int oracle_sampson_errors(const float* pts1, const float* pts2, int M, const double* K4,
+                          const double* E, int H, float* err /* H*M */) {
+    double* n1 = (double*)malloc(sizeof(double) * 2 * (size_t)(M > 0 ? M : 1));
+    double* n2 = (double*)malloc(sizeof(double) * 2 * (size_t)(M > 0 ? M : 1));
+    if (!n1 || !n2) { free(n1); free(n2); return -2; }
+    oracle_normalize_points(pts1, M, K4[0], K4[1], K4[2], K4[3], n1);
+    oracle_normalize_points(pts2, M, K4[0], K4[1], K4[2], K4[3], n2);
+    for (int h = 0; h < H; h++)
+        for (int i = 0; i < M; i++)
+            err[(size_t)h * M + i] =
+                sampson_cv(E + 9 * (size_t)h, n1[2 * i], n1[2 * i + 1], n2[2 * i], n2[2 * i + 1]);
+    free(n1); free(n2);
+    return 0;
+}
+
+/* matchFeatures end to end (featureMatchingCPU.cpp:17-43): matcher 0 SIFT_BF and 1 SIFT_FLANN
+ * -> exact L2 (FLANN is approximate in the reference; its ground truth is BF), 2 ORB_BF ->
+ * Hamming.  Returns the good-match count through n_out. */
+int oracle_match_features(int matcher, const void* q, int nq, const void* t, int nt, double ratio,
+                          oracle_dmatch* out, int* n_out) {
+    int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)(nq > 0 ? nq : 1));
+    float* dist = (float*)malloc(sizeof(float) * 2 * (size_t)(nq > 0 ? nq : 1));
+    int rc;
+    if (!idx || !dist) { free(idx); free(dist); return -2; }
+    if (matcher == 0 || matcher == 1)
+        rc = oracle_l2_knn2((const float*)q, nq, (const float*)t, nt, 128, idx, dist);
+    else if (matcher == 2)
+        rc = oracle_hamming_knn2((const uint8_t*)q, nq, (const uint8_t*)t, nt, 32, idx, dist);
+    else
+        rc = -3; /* reference: throw std::exception() (featureMatchingCPU.cpp:37) */
+    if (rc == 0) rc = oracle_ratio_test(idx, dist, nq, ratio, out, n_out);
+    free(idx); free(dist);
+    return rc;
+}
