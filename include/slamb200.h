@@ -1,0 +1,173 @@
+/*
+ * slamb200.h -- C ABI of libslamb200.so, the B200-native (sm_100a) correspondence hot path of
+ * FIT-2023-SLAM-indoor/slam-indoor-code.
+ *
+ * This is the drop-in boundary.  Everything the reference computes between
+ *     matchFramesPairFeatures(...)   src/mainModule/featureMatching/featureMatching.h:29-53
+ *     findEssentialMat(..., RANSAC)  src/mainModule/translation/cameraTranslation.cpp:41-46
+ * and their outputs (std::vector<cv::DMatch>, the uchar inlier mask) is reachable through the
+ * plain-C entry points below: plain pointers and sizes, no C++ / OpenCV / torch types, integer
+ * status codes, no exceptions.  The reference-side binding (featureMatchingB200.cpp, the third
+ * translation unit behind featureMatching.h next to featureMatchingCPU.cpp /
+ * featureMatchingCUDA.cpp) is shown in INTEGRATION.md and shipped in
+ * slam_indoor_code_b200/host/.
+ *
+ * There is no CPU fallback: every compute entry point runs hand-written CUDA kernels on the
+ * context's device and fails with SLAMB200_ERR_CUDA when no sm_100 device is present.
+ *
+ * Thread safety: a context may be used from several host threads at once (the reference calls
+ * matchFramesPairFeatures from `threadsCount` std::threads sharing one read-only query
+ * descriptor, batch.cpp:181-201).  Descriptor handles are immutable after upload and may be
+ * shared between threads; each call borrows one of the context's internal lanes (stream +
+ * scratch).
+ */
+#ifndef SLAMB200_H
+#define SLAMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLAMB200_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ---------------------------------------------------------------------- */
+#define SLAMB200_OK 0
+#define SLAMB200_ERR_INVALID (-1)  /* null pointer, negative size, capacity too small ...     */
+#define SLAMB200_ERR_CUDA (-2)     /* CUDA runtime error or no sm_100 device                  */
+#define SLAMB200_ERR_NOMEM (-3)    /* device or host allocation failed                        */
+#define SLAMB200_ERR_MATCHER (-4)  /* matcher type not 0/1/2: the reference throws
+                                      std::exception() there (featureMatchingCPU.cpp:37)      */
+#define SLAMB200_ERR_KIND (-5)     /* descriptor kind does not fit the matcher (OpenCV asserts
+                                      on a type mismatch in batchDistance)                    */
+#define SLAMB200_ERR_INTERNAL (-6) /* a device-side self check failed (never expected)        */
+
+/* ---- matcher types: enum MatcherType, featureMatchingCommon.h:8-12 --------------------- */
+#define SLAMB200_SIFT_BF 0    /* useFM-SIFT-BF    -> BFMatcher NORM_L2 (featureMatchingCPU.cpp:27) */
+#define SLAMB200_SIFT_FLANN 1 /* useFM-SIFT-FLANN -> exact L2 as well: the reference's FLANN
+                                 (featureMatchingCPU.cpp:30) is approximate, its ground truth is
+                                 the BF result, so recall vs BF is 1.0 by construction        */
+#define SLAMB200_ORB_BF 2     /* useFM-ORB        -> BFMatcher NORM_HAMMING (:33)              */
+
+/* ---- descriptor kinds: what extractDescriptor emits (featureMatchingCPU.cpp:45-66) ------ */
+#define SLAMB200_DESC_F32X128 0 /* cv::SIFT: CV_32F, 128 columns */
+#define SLAMB200_DESC_U8X32 1   /* cv::ORB:  CV_8U,  32 columns  */
+
+typedef struct slamb200_ctx slamb200_ctx;
+typedef struct slamb200_desc slamb200_desc; /* one frame's descriptor set, resident in HBM */
+typedef struct slamb200_pts slamb200_pts;   /* one frame's keypoint coordinates (x,y) in HBM */
+
+/* Bit-compatible with cv::DMatch {int queryIdx; int trainIdx; int imgIdx; float distance;}. */
+typedef struct slamb200_dmatch {
+  int32_t queryIdx;
+  int32_t trainIdx;
+  int32_t imgIdx;
+  float distance;
+} slamb200_dmatch;
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* Binds a context to CUDA device `device` (main.cpp:30-38 only checks that a device exists). */
+int slamb200_init(int device, slamb200_ctx** out);
+int slamb200_shutdown(slamb200_ctx* ctx);
+int slamb200_version(void);
+/* Last error text of the calling thread (never NULL). */
+const char* slamb200_last_error(void);
+/* Kernels this library has launched on the context since init (the bench's gpu_launches). */
+int64_t slamb200_launch_count(const slamb200_ctx* ctx);
+/* Blocks until all work queued by the context has finished. */
+int slamb200_synchronize(slamb200_ctx* ctx);
+
+/* ---- descriptor sets: replaces the per-call cuda::GpuMat uploads of
+ *      featureMatchingCUDA.cpp:98-99 with "upload once per frame" ----------------------- */
+/* rows: host pointer to n rows of the kind's type, row_stride bytes apart (cv::Mat::step). */
+int slamb200_upload_desc(slamb200_ctx* ctx, int kind, const void* rows, int n, size_t row_stride,
+                         slamb200_desc** out);
+/* Same, but `rows` is a device pointer on the context's device (bytes already in HBM);
+ * `stream` (a cudaStream_t, may be NULL) is the stream the bytes were produced on. */
+int slamb200_upload_desc_device(slamb200_ctx* ctx, int kind, const void* rows, int n,
+                                size_t row_stride, void* stream, slamb200_desc** out);
+int slamb200_free_desc(slamb200_ctx* ctx, slamb200_desc* d);
+int slamb200_desc_rows(const slamb200_desc* d);
+int slamb200_desc_kind(const slamb200_desc* d);
+/* 1 when the set is integer-valued in [0,255] with small norms (what cv::SIFT emits) and so
+ * takes the tcgen05 candidate path; 0 for general floats (exact fp32 path); -1 for ORB. */
+int slamb200_desc_exact_mode(const slamb200_desc* d);
+
+/* ---- hot path A: matchFeatures (featureMatchingCPU.cpp:17-43) --------------------------- */
+/* knnMatch(query, train, k=2) raw result, the shape cv::BFMatcher returns before the ratio test:
+ * idx[2*q+k] = train index of the k-th neighbour of query row q or -1 when the train set has
+ * fewer than k+1 rows; dist likewise (sqrt-L2 as float, or the Hamming count as float). */
+int slamb200_knn2(slamb200_ctx* ctx, int matcher, const slamb200_desc* query,
+                  const slamb200_desc* train, int32_t* idx, float* dist);
+
+/* knnMatch + getGoodMatches (featureMatchingCommon.cpp:37-50): out receives the accepted
+ * matches in ascending queryIdx, *n_out their count; cap must be >= rows(query).  ratio is
+ * the knnMatcherDistance config value; the comparison is (double)d0 < ratio * (double)d1. */
+int slamb200_match_pair(slamb200_ctx* ctx, int matcher, const slamb200_desc* query,
+                        const slamb200_desc* train, double ratio, slamb200_dmatch* out, int cap,
+                        int* n_out);
+
+/* The batch window of batch.cpp:120-148 / :181-201 in one call: one query frame against
+ * n_pairs train frames.  out is n_pairs slabs of `cap` matches, n_out[p] the count of pair p. */
+int slamb200_match_batch(slamb200_ctx* ctx, int matcher, const slamb200_desc* query,
+                         const slamb200_desc* const* trains, int n_pairs, double ratio,
+                         slamb200_dmatch* out, int cap, int* n_out);
+
+/* All i<j pairs of a frame window (BAMaxFramesCnt window, config 4): pair order is
+ * (0,1),(0,2)...(0,n-1),(1,2)...; frame i is the query, frame j the train. */
+int slamb200_match_window(slamb200_ctx* ctx, int matcher, const slamb200_desc* const* frames,
+                          int n_frames, double ratio, slamb200_dmatch* out, int cap, int* n_out);
+
+/* Device-resident variants: enqueue the batch on `stream` (cudaStream_t; NULL = the lane's own
+ * stream), keep the results in HBM inside the context, return without synchronising.
+ * slamb200_batch_fetch copies the results of the last enqueue to the host. */
+int slamb200_match_batch_enqueue(slamb200_ctx* ctx, int matcher, const slamb200_desc* query,
+                                 const slamb200_desc* const* trains, int n_pairs, double ratio,
+                                 void* stream);
+int slamb200_batch_fetch(slamb200_ctx* ctx, slamb200_dmatch* out, int cap, int* n_out,
+                         void* stream);
+
+/* ---- hot path B: RANSAC essential-matrix inlier scoring (cameraTranslation.cpp:41-46) --- */
+/* Scores H candidate essential matrices (row-major 3x3 doubles, in normalised coordinates, as
+ * the 5-point solver returns them) against M matches exactly as cv::findEssentialMat's RANSAC
+ * loop does: points normalised with K = {fx, fy, cx, cy}, threshold_px (RPRANSACThreshold)
+ * divided by (fx+fy)/2, Sampson error in fp64 rounded to float, inlier iff err <= (float)thr^2,
+ * a model replaces the best iff count > max(best_count, 4).  counts[H]; *best = winning index or
+ * -1; best_mask[M] = 0/1 (the N x 1 uchar mask the reference logs, cameraTranslation.cpp:53);
+ * all_masks (H*M bytes) may be NULL. */
+int slamb200_score_essential(slamb200_ctx* ctx, const float* pts1, const float* pts2, int M,
+                             const double K[4], const double* E, int H, double threshold_px,
+                             int32_t* counts, int32_t* best, uint8_t* best_mask,
+                             uint8_t* all_masks);
+
+/* P independent pairs in one launch sequence.  Matches are ragged: pair p owns
+ * pts[m_off[p] .. m_off[p+1]) (m_off has P+1 entries); E is P*H*9 doubles; counts P*H;
+ * best P; best_mask m_off[P] bytes. */
+int slamb200_score_essential_batch(slamb200_ctx* ctx, int P, const float* pts1,
+                                   const float* pts2, const int32_t* m_off, const double K[4],
+                                   const double* E, int H, double threshold_px, int32_t* counts,
+                                   int32_t* best, uint8_t* best_mask);
+
+/* Keypoint coordinates of a frame (cv::KeyPoint::pt as x,y float pairs, `stride` bytes apart)
+ * kept in HBM so that getKeyPointCoordsFromFramePair (featureMatchingCommon.cpp:23-33) can run
+ * on the device between matching and scoring. */
+int slamb200_upload_pts(slamb200_ctx* ctx, const float* xy, int n, size_t stride,
+                        slamb200_pts** out);
+int slamb200_free_pts(slamb200_ctx* ctx, slamb200_pts* p);
+
+/* Chained batch: score, for every pair of the last slamb200_match_batch_enqueue, H hypotheses
+ * (E: n_pairs*H*9 host doubles) against that pair's accepted matches, gathering the coordinates
+ * on the device (query_pts / train_pts[p]).  Results stay in HBM until
+ * slamb200_batch_scores_fetch.  Enqueue-only. */
+int slamb200_score_batch_enqueue(slamb200_ctx* ctx, const slamb200_pts* query_pts,
+                                 const slamb200_pts* const* train_pts, const double K[4],
+                                 const double* E, int H, double threshold_px, void* stream);
+int slamb200_batch_scores_fetch(slamb200_ctx* ctx, int32_t* counts, int32_t* best,
+                                uint8_t* best_mask, int mask_cap, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMB200_H */

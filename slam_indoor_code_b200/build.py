@@ -1,0 +1,75 @@
+"""Builds libslamb200.so (hand-written sm_100a CUDA + the C ABI) in-tree with nvcc.
+
+    python -m slam_indoor_code_b200.build [--force]
+
+The shared object lands in slam_indoor_code_b200/lib/ (git-ignored, but it travels to the GPU box
+with the repo snapshot).  cudart is linked statically and the driver API is reached through
+cudaGetDriverEntryPoint, so the library loads on a machine without libcuda (the symbol-export
+test runs without a GPU).
+"""
+import concurrent.futures
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIBDIR, "libslamb200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
+          "-ccbin", "/usr/bin/g++", "-DSLAMB200_BUILD"]
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJDIR, src[:-3] + ".o")
+    headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "slamb200.h"))
+    if _stale(obj, [os.path.join(CSRC, src)] + headers):
+        cmd = [NVCC] + ARCH + CFLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+    return obj
+
+
+def build(force=False, verbose=False, defines=()):
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJDIR):
+            os.remove(os.path.join(OBJDIR, f))
+    global CFLAGS
+    if defines:
+        CFLAGS = CFLAGS + [f"-D{d}" for d in defines]
+    srcs = sources()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
+    if _stale(LIB, objs):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static", "-ccbin",
+                                                                "/usr/bin/g++", "-lpthread", "-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

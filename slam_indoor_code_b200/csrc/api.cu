@@ -1,0 +1,732 @@
+// api.cu -- the C ABI of libslamb200 (include/slamb200.h): context, lanes, HBM-resident
+// descriptor sets, batch orchestration.  All arithmetic is in the kernels; this file only moves
+// bytes and sequences launches.  No CPU fallback exists anywhere in this library.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <condition_variable>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int64_t g_launches = 0;
+int64_t* launch_counter() { return &g_launches; }
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess)                                                            \
+      return fail(e__ == cudaErrorMemoryAllocation ? SLAMB200_ERR_NOMEM                \
+                                                   : SLAMB200_ERR_CUDA,                \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,   \
+                  __LINE__);                                                           \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+#define N_LANES 4
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  bool busy = false;
+  // matching scratch (device)
+  DevBuf pairs, tcpairs, part, cand, knn_idx, knn_dist, flags, chunk_cnt, out, n_out, err_flag;
+  // scoring scratch (device)
+  DevBuf npts, E, counts, best, mask, m_off, p1, p2, txy, all_masks;
+  // pinned staging
+  void* h_stage = nullptr;
+  size_t h_stage_cap = 0;
+  cudaEvent_t stage_free = nullptr;  // recorded after the last async copy out of h_stage
+  int32_t* h_small = nullptr;        // pinned, N_SMALL ints (counts read-back)
+  // state of the last enqueued batch
+  int b_matcher = -1, b_nq = 0, b_pairs = 0, b_cap = 0;
+  int s_H = 0, s_pairs = 0;
+};
+#define N_SMALL 65536
+
+struct slamb200_ctx {
+  int device = 0;
+  cudaMemPool_t pool = nullptr;
+  std::mutex mu;
+  std::condition_variable cv;
+  Lane lanes[N_LANES];  // lane 0 is the batch (enqueue/fetch) lane
+  std::mutex batch_mu;
+};
+
+static int dev_alloc(slamb200_ctx* c, void** p, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) bytes = 16;
+  CU(cudaMallocFromPoolAsync(p, bytes, c->pool, s));
+  return SLAMB200_OK;
+}
+
+static int buf_reserve(slamb200_ctx* c, DevBuf& b, size_t bytes, cudaStream_t s) {
+  if (bytes <= b.cap && b.p) return SLAMB200_OK;
+  if (b.p) CU(cudaFreeAsync(b.p, s));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  int rc = dev_alloc(c, &b.p, want, s);
+  if (rc) return rc;
+  b.cap = want;
+  return SLAMB200_OK;
+}
+
+static int stage_reserve(Lane& L, size_t bytes) {
+  // the previous async copy out of the staging area must have been consumed
+  if (L.stage_free) CU(cudaEventSynchronize(L.stage_free));
+  if (bytes <= L.h_stage_cap) return SLAMB200_OK;
+  if (L.h_stage) CU(cudaFreeHost(L.h_stage));
+  L.h_stage = nullptr;
+  L.h_stage_cap = 0;
+  size_t want = bytes * 2 + 4096;
+  CU(cudaMallocHost(&L.h_stage, want));
+  L.h_stage_cap = want;
+  return SLAMB200_OK;
+}
+
+struct LaneGuard {
+  slamb200_ctx* c;
+  int idx;
+  LaneGuard(slamb200_ctx* c_) : c(c_), idx(-1) {
+    std::unique_lock<std::mutex> lk(c->mu);
+    for (;;) {
+      for (int i = 1; i < N_LANES; i++)
+        if (!c->lanes[i].busy) { idx = i; break; }
+      if (idx >= 0) break;
+      c->cv.wait(lk);
+    }
+    c->lanes[idx].busy = true;
+  }
+  ~LaneGuard() {
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      c->lanes[idx].busy = false;
+    }
+    c->cv.notify_one();
+  }
+  Lane& lane() { return c->lanes[idx]; }
+};
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int slamb200_version(void) { return SLAMB200_VERSION; }
+extern "C" const char* slamb200_last_error(void) { return g_err; }
+extern "C" int64_t slamb200_launch_count(const slamb200_ctx*) { return g_launches; }
+
+extern "C" int slamb200_init(int device, slamb200_ctx** out) {
+  if (!out) return fail(SLAMB200_ERR_INVALID, "slamb200_init: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(SLAMB200_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= n)
+    return fail(SLAMB200_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SLAMB200_ERR_CUDA, "device %d is sm_%d%d; libslamb200 is built for sm_100a only",
+                device, prop.major, prop.minor);
+  CU(cudaSetDevice(device));
+  slamb200_ctx* c = new (std::nothrow) slamb200_ctx();
+  if (!c) return fail(SLAMB200_ERR_NOMEM, "host allocation failed");
+  c->device = device;
+  cudaMemPoolProps pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.allocType = cudaMemAllocationTypePinned;
+  pp.handleTypes = cudaMemHandleTypeNone;
+  pp.location.type = cudaMemLocationTypeDevice;
+  pp.location.id = device;
+  CU(cudaMemPoolCreate(&c->pool, &pp));
+  uint64_t thr = UINT64_MAX;
+  CU(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  for (int i = 0; i < N_LANES; i++) {
+    CU(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->lanes[i].stage_free, cudaEventDisableTiming));
+    CU(cudaMallocHost((void**)&c->lanes[i].h_small, sizeof(int32_t) * N_SMALL));
+  }
+  *out = c;
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_synchronize(slamb200_ctx* c) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  for (int i = 0; i < N_LANES; i++) CU(cudaStreamSynchronize(c->lanes[i].stream));
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_shutdown(slamb200_ctx* c) {
+  if (!c) return SLAMB200_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < N_LANES; i++) {
+    Lane& L = c->lanes[i];
+    DevBuf* bufs[] = {&L.pairs, &L.tcpairs, &L.part, &L.cand, &L.knn_idx, &L.knn_dist, &L.flags,
+                      &L.chunk_cnt, &L.out, &L.n_out, &L.err_flag, &L.npts, &L.E, &L.counts,
+                      &L.best, &L.mask, &L.m_off, &L.p1, &L.p2, &L.txy, &L.all_masks};
+    for (DevBuf* b : bufs)
+      if (b->p) cudaFreeAsync(b->p, L.stream);
+    cudaStreamSynchronize(L.stream);
+    if (L.h_stage) cudaFreeHost(L.h_stage);
+    if (L.h_small) cudaFreeHost(L.h_small);
+    if (L.stage_free) cudaEventDestroy(L.stage_free);
+    cudaStreamDestroy(L.stream);
+  }
+  if (c->pool) cudaMemPoolDestroy(c->pool);
+  delete c;
+  return SLAMB200_OK;
+}
+
+// ---- descriptor sets ------------------------------------------------------------------------
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_t row_stride,
+                       bool src_on_device, cudaStream_t producer, slamb200_desc** out) {
+  if (!c || !out) return fail(SLAMB200_ERR_INVALID, "upload_desc: NULL argument");
+  *out = nullptr;
+  if (kind != SLAMB200_DESC_F32X128 && kind != SLAMB200_DESC_U8X32)
+    return fail(SLAMB200_ERR_KIND, "upload_desc: unknown descriptor kind %d", kind);
+  if (n < 0 || (n > 0 && !rows)) return fail(SLAMB200_ERR_INVALID, "upload_desc: bad rows/n");
+  const size_t row_bytes = kind == SLAMB200_DESC_F32X128 ? 512 : 32;
+  if (row_stride == 0) row_stride = row_bytes;
+  if (row_stride < row_bytes || (kind == SLAMB200_DESC_F32X128 && (row_stride % 16)))
+    return fail(SLAMB200_ERR_INVALID, "upload_desc: row_stride %zu unsupported", row_stride);
+  CU(cudaSetDevice(c->device));
+  slamb200_desc* d = (slamb200_desc*)calloc(1, sizeof(slamb200_desc));
+  if (!d) return fail(SLAMB200_ERR_NOMEM, "host allocation failed");
+  d->kind = kind;
+  d->n = n;
+  d->n_pad = round_up(n > 0 ? n : 1, SLAMB200_TILE_PAD);
+  d->host_exact = -2;
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  cudaStream_t s = L.stream;
+  int rc = SLAMB200_OK;
+  cudaEvent_t ev = nullptr;
+#define DCU(call)                                                                   \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      rc = fail(SLAMB200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+      goto done;                                                                    \
+    }                                                                               \
+  } while (0)
+  if (producer && src_on_device) {
+    DCU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    DCU(cudaEventRecord(ev, producer));
+    DCU(cudaStreamWaitEvent(s, ev, 0));
+  }
+  DCU(cudaEventCreateWithFlags(&d->ready, cudaEventDisableTiming));
+  if (kind == SLAMB200_DESC_U8X32) {
+    if ((rc = dev_alloc(c, (void**)&d->u8, (size_t)d->n_pad * 32, s))) goto done;
+    DCU(cudaMemsetAsync(d->u8, 0, (size_t)d->n_pad * 32, s));
+    if (n > 0)
+      DCU(cudaMemcpy2DAsync(d->u8, 32, rows, row_stride, 32, n,
+                            src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  } else {
+    const size_t np = d->n_pad;
+    float* raw = nullptr;
+    if ((rc = dev_alloc(c, (void**)&d->f32, np * 512, s))) goto done;
+    if ((rc = dev_alloc(c, (void**)&d->bf16, np * 256, s))) goto done;
+    if ((rc = dev_alloc(c, (void**)&d->augq, np * 32, s))) goto done;
+    if ((rc = dev_alloc(c, (void**)&d->augt, np * 32, s))) goto done;
+    if ((rc = dev_alloc(c, (void**)&d->u8, np * 128, s))) goto done;
+    if ((rc = dev_alloc(c, (void**)&d->nrm2, np * 4, s))) goto done;
+    if ((rc = dev_alloc(c, (void**)&d->flags, 16, s))) goto done;
+    DCU(cudaMemsetAsync(d->flags, 0, 16, s));
+    const float* src = (const float*)rows;
+    size_t src_stride = row_stride / 4;
+    if (!src_on_device && n > 0) {
+      // stage the caller's rows in HBM once; the prep kernel removes the pitch
+      if ((rc = dev_alloc(c, (void**)&raw, (size_t)n * 512, s))) goto done;
+      DCU(cudaMemcpy2DAsync(raw, 512, rows, row_stride, 512, n, cudaMemcpyHostToDevice, s));
+      src = raw;
+      src_stride = 128;
+    }
+    launch_sift_prep(src, src_stride, n, d->n_pad, d->f32, d->bf16, d->augq, d->augt, d->u8,
+                     d->nrm2, d->flags, s);
+    DCU(cudaGetLastError());
+    if (raw) DCU(cudaFreeAsync(raw, s));
+  }
+  DCU(cudaEventRecord(d->ready, s));
+  if (!src_on_device) DCU(cudaStreamSynchronize(s));  // the caller may reuse `rows` on return
+done:
+  if (ev) cudaEventDestroy(ev);
+  if (rc != SLAMB200_OK) {
+    slamb200_free_desc(c, d);
+    return rc;
+  }
+  *out = d;
+  return SLAMB200_OK;
+#undef DCU
+}
+
+extern "C" int slamb200_upload_desc(slamb200_ctx* c, int kind, const void* rows, int n,
+                                    size_t row_stride, slamb200_desc** out) {
+  return desc_create(c, kind, rows, n, row_stride, false, nullptr, out);
+}
+
+extern "C" int slamb200_upload_desc_device(slamb200_ctx* c, int kind, const void* rows, int n,
+                                           size_t row_stride, void* stream, slamb200_desc** out) {
+  return desc_create(c, kind, rows, n, row_stride, true, (cudaStream_t)stream, out);
+}
+
+extern "C" int slamb200_free_desc(slamb200_ctx* c, slamb200_desc* d) {
+  if (!d) return SLAMB200_OK;
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  cudaSetDevice(c->device);
+  // work queued by this context that may still read the set must drain first
+  for (int i = 0; i < N_LANES; i++) cudaStreamSynchronize(c->lanes[i].stream);
+  cudaStream_t s = c->lanes[1].stream;
+  void* ptrs[] = {d->f32, d->bf16, d->augq, d->augt, d->u8, d->nrm2, d->flags};
+  for (void* p : ptrs)
+    if (p) cudaFreeAsync(p, s);
+  if (d->ready) cudaEventDestroy(d->ready);
+  free(d->tmap_main);
+  free(d);
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_desc_rows(const slamb200_desc* d) { return d ? d->n : -1; }
+extern "C" int slamb200_desc_kind(const slamb200_desc* d) { return d ? d->kind : -1; }
+extern "C" int slamb200_desc_exact_mode(const slamb200_desc* d) {
+  if (!d) return -1;
+  if (d->kind != SLAMB200_DESC_F32X128) return -1;
+  slamb200_desc* m = const_cast<slamb200_desc*>(d);
+  if (m->host_exact == -2) {
+    int32_t f = 1;
+    if (cudaEventSynchronize(d->ready) != cudaSuccess) return -1;
+    if (cudaMemcpy(&f, d->flags, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    m->host_exact = f == 0 ? 1 : 0;
+  }
+  return m->host_exact;
+}
+
+// ---- matching ---------------------------------------------------------------------------------
+static int pick_splits(int q_blocks, int n_pairs, int t_max, int min_chunk) {
+  // enough (q-block, split, pair) work items for ~4 waves of 148 SMs
+  long long items = (long long)q_blocks * n_pairs;
+  int want = (int)((148LL * 4 + items - 1) / (items > 0 ? items : 1));
+  int max_split = t_max / min_chunk;
+  if (max_split < 1) max_split = 1;
+  if (want > max_split) want = max_split;
+  if (want < 1) want = 1;
+  return want;
+}
+
+static int check_matcher(int matcher, const slamb200_desc* q, const slamb200_desc* const* t,
+                         int n_pairs) {
+  if (matcher != SLAMB200_SIFT_BF && matcher != SLAMB200_SIFT_FLANN && matcher != SLAMB200_ORB_BF)
+    return fail(SLAMB200_ERR_MATCHER, "matcher type %d is not 0 (SIFT_BF), 1 (SIFT_FLANN) or 2 (ORB_BF)",
+                matcher);
+  const int kind = matcher == SLAMB200_ORB_BF ? SLAMB200_DESC_U8X32 : SLAMB200_DESC_F32X128;
+  if (!q) return fail(SLAMB200_ERR_INVALID, "query descriptor set is NULL");
+  if (q->kind != kind) return fail(SLAMB200_ERR_KIND, "query descriptor kind does not fit the matcher");
+  for (int p = 0; p < n_pairs; p++) {
+    if (!t || !t[p]) return fail(SLAMB200_ERR_INVALID, "train descriptor set %d is NULL", p);
+    if (t[p]->kind != kind)
+      return fail(SLAMB200_ERR_KIND, "train descriptor kind of pair %d does not fit the matcher", p);
+  }
+  return SLAMB200_OK;
+}
+
+// Queues one (query x n_pairs trains) batch on stream s using lane L's scratch.  Results:
+// L.knn_idx / L.knn_dist [P][nq][2], L.out [P][cap] dmatch, L.n_out [P].
+static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
+                         const slamb200_desc* q, const slamb200_desc* const* trains, int n_pairs,
+                         double ratio) {
+  const int nq = q->n;
+  const int cap = nq > 0 ? nq : 1;
+  L.b_matcher = matcher; L.b_nq = nq; L.b_pairs = n_pairs; L.b_cap = cap;
+  if (n_pairs == 0) return SLAMB200_OK;
+  int rc;
+  const bool orb = matcher == SLAMB200_ORB_BF;
+  int t_max = 0;
+  for (int p = 0; p < n_pairs; p++) t_max = trains[p]->n > t_max ? trains[p]->n : t_max;
+  const int q_blocks = orb ? (nq + 255) / 256 : (nq + 15) / 16;
+  const int n_split = pick_splits(q_blocks > 0 ? q_blocks : 1, n_pairs, t_max, orb ? 1024 : 512);
+
+  // pair table -> device
+  if ((rc = stage_reserve(L, sizeof(PairArgs) * (size_t)n_pairs))) return rc;
+  PairArgs* hp = (PairArgs*)L.h_stage;
+  for (int p = 0; p < n_pairs; p++) {
+    hp[p].t_rows = orb ? (const void*)trains[p]->u8 : (const void*)trains[p]->f32;
+    hp[p].t_flags = orb ? nullptr : trains[p]->flags;
+    hp[p].t_n = trains[p]->n;
+    hp[p].t_pad = trains[p]->n_pad;
+  }
+  if ((rc = buf_reserve(c, L.pairs, sizeof(PairArgs) * (size_t)n_pairs, s))) return rc;
+  CU(cudaMemcpyAsync(L.pairs.p, hp, sizeof(PairArgs) * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
+  CU(cudaEventRecord(L.stage_free, s));
+
+  const size_t rows = (size_t)n_pairs * cap;
+  if ((rc = buf_reserve(c, L.part, sizeof(uint4) * rows * n_split, s))) return rc;
+  if ((rc = buf_reserve(c, L.knn_idx, sizeof(int32_t) * rows * 2, s))) return rc;
+  if ((rc = buf_reserve(c, L.knn_dist, sizeof(float) * rows * 2, s))) return rc;
+  if ((rc = buf_reserve(c, L.flags, rows, s))) return rc;
+  if ((rc = buf_reserve(c, L.chunk_cnt, sizeof(int32_t) * (size_t)n_pairs * (finalize_chunks(cap) + 1), s))) return rc;
+  if ((rc = buf_reserve(c, L.out, sizeof(slamb200_dmatch) * rows, s))) return rc;
+  if ((rc = buf_reserve(c, L.n_out, sizeof(int32_t) * (size_t)n_pairs, s))) return rc;
+
+  // the descriptor sets must have finished their prep kernels
+  CU(cudaStreamWaitEvent(s, q->ready, 0));
+  for (int p = 0; p < n_pairs; p++) CU(cudaStreamWaitEvent(s, trains[p]->ready, 0));
+
+  if (orb) {
+    launch_orb_knn2(q->u8, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split, (uint4*)L.part.p, s);
+  } else {
+    // general-float pairs: exact fp32 kernel.  Exact-mode pairs (integer-valued descriptors)
+    // are skipped inside that kernel once the tcgen05 path is present and take it instead.
+#ifdef SLAMB200_HAVE_TC
+    const int force = 0;
+#else
+    const int force = 1;
+#endif
+    launch_sift_exact_knn2(q->f32, q->flags, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split,
+                           (uint4*)L.part.p, force, s);
+  }
+  CU(cudaGetLastError());
+  launch_finalize((const uint4*)L.part.p, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split,
+                  orb ? 1 : 0, ratio, (int32_t*)L.knn_idx.p, (float*)L.knn_dist.p,
+                  (uint8_t*)L.flags.p, (int32_t*)L.chunk_cnt.p, (slamb200_dmatch*)L.out.p, cap,
+                  (int32_t*)L.n_out.p, s);
+  CU(cudaGetLastError());
+  return SLAMB200_OK;
+}
+
+// Copies the last batch of lane L to the host: out = P slabs of out_cap matches, n_out[P].
+static int fetch_batch(Lane& L, cudaStream_t s, slamb200_dmatch* out, int out_cap, int* n_out) {
+  const int P = L.b_pairs;
+  if (P == 0) return SLAMB200_OK;
+  if (!n_out) return fail(SLAMB200_ERR_INVALID, "n_out is NULL");
+  if (L.b_nq == 0) {
+    for (int p = 0; p < P; p++) n_out[p] = 0;
+    return SLAMB200_OK;
+  }
+  if (out_cap < L.b_nq) return fail(SLAMB200_ERR_INVALID, "cap %d < query rows %d", out_cap, L.b_nq);
+  if (!out) return fail(SLAMB200_ERR_INVALID, "out is NULL");
+  CU(cudaMemcpyAsync(n_out, L.n_out.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  int mx = 0;
+  for (int p = 0; p < P; p++) mx = n_out[p] > mx ? n_out[p] : mx;
+  if (mx > 0) {
+    CU(cudaMemcpy2DAsync(out, sizeof(slamb200_dmatch) * (size_t)out_cap, L.out.p,
+                         sizeof(slamb200_dmatch) * (size_t)L.b_cap, sizeof(slamb200_dmatch) * (size_t)mx,
+                         P, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_match_batch(slamb200_ctx* c, int matcher, const slamb200_desc* q,
+                                    const slamb200_desc* const* trains, int n_pairs, double ratio,
+                                    slamb200_dmatch* out, int cap, int* n_out) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  if (n_pairs < 0) return fail(SLAMB200_ERR_INVALID, "n_pairs < 0");
+  int rc = check_matcher(matcher, q, trains, n_pairs);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  if ((rc = enqueue_batch(c, L, L.stream, matcher, q, trains, n_pairs, ratio))) return rc;
+  return fetch_batch(L, L.stream, out, cap, n_out);
+}
+
+extern "C" int slamb200_match_pair(slamb200_ctx* c, int matcher, const slamb200_desc* q,
+                                   const slamb200_desc* t, double ratio, slamb200_dmatch* out,
+                                   int cap, int* n_out) {
+  const slamb200_desc* tt[1] = {t};
+  return slamb200_match_batch(c, matcher, q, tt, 1, ratio, out, cap, n_out);
+}
+
+extern "C" int slamb200_knn2(slamb200_ctx* c, int matcher, const slamb200_desc* q,
+                             const slamb200_desc* t, int32_t* idx, float* dist) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  const slamb200_desc* tt[1] = {t};
+  int rc = check_matcher(matcher, q, tt, 1);
+  if (rc) return rc;
+  if (q->n > 0 && (!idx || !dist)) return fail(SLAMB200_ERR_INVALID, "idx/dist is NULL");
+  CU(cudaSetDevice(c->device));
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  if ((rc = enqueue_batch(c, L, L.stream, matcher, q, tt, 1, 0.0))) return rc;
+  if (q->n > 0) {
+    CU(cudaMemcpyAsync(idx, L.knn_idx.p, sizeof(int32_t) * 2 * (size_t)q->n, cudaMemcpyDeviceToHost, L.stream));
+    CU(cudaMemcpyAsync(dist, L.knn_dist.p, sizeof(float) * 2 * (size_t)q->n, cudaMemcpyDeviceToHost, L.stream));
+  }
+  CU(cudaStreamSynchronize(L.stream));
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_match_window(slamb200_ctx* c, int matcher,
+                                     const slamb200_desc* const* frames, int n_frames,
+                                     double ratio, slamb200_dmatch* out, int cap, int* n_out) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  if (n_frames < 0 || (n_frames > 0 && !frames)) return fail(SLAMB200_ERR_INVALID, "bad frames");
+  int pair0 = 0;
+  for (int i = 0; i + 1 < n_frames; i++) {
+    const int np = n_frames - 1 - i;
+    if (frames[i] && cap < frames[i]->n) return fail(SLAMB200_ERR_INVALID, "cap too small");
+    int rc = slamb200_match_batch(c, matcher, frames[i], frames + i + 1, np, ratio,
+                                  out ? out + (size_t)pair0 * cap : nullptr, cap, n_out + pair0);
+    if (rc) return rc;
+    pair0 += np;
+  }
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_match_batch_enqueue(slamb200_ctx* c, int matcher, const slamb200_desc* q,
+                                            const slamb200_desc* const* trains, int n_pairs,
+                                            double ratio, void* stream) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  if (n_pairs < 0) return fail(SLAMB200_ERR_INVALID, "n_pairs < 0");
+  int rc = check_matcher(matcher, q, trains, n_pairs);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> lk(c->batch_mu);
+  Lane& L = c->lanes[0];
+  cudaStream_t s = stream ? (cudaStream_t)stream : L.stream;
+  return enqueue_batch(c, L, s, matcher, q, trains, n_pairs, ratio);
+}
+
+extern "C" int slamb200_batch_fetch(slamb200_ctx* c, slamb200_dmatch* out, int cap, int* n_out,
+                                    void* stream) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> lk(c->batch_mu);
+  Lane& L = c->lanes[0];
+  cudaStream_t s = stream ? (cudaStream_t)stream : L.stream;
+  return fetch_batch(L, s, out, cap, n_out);
+}
+
+// ---- RANSAC essential scoring -----------------------------------------------------------------
+static int make_score_params(const double K[4], double threshold_px, ScoreParams* sp) {
+  if (!K) return fail(SLAMB200_ERR_INVALID, "K is NULL");
+  const double fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+  sp->ax = 1.0 / fx;
+  sp->ay = 1.0 / fy;
+  sp->bx = -cx * sp->ax;
+  sp->by = -cy * sp->ay;
+  const double thr = threshold_px / ((fx + fy) / 2);
+  const float t = (float)(thr * thr);
+  const float u = nextafterf(t, INFINITY);
+  const double mid = ((double)t + (double)u) * 0.5;
+  sp->t = t;
+  sp->mid_lo = mid * (1.0 - ldexp(1.0, -49));
+  sp->mid_hi = mid * (1.0 + ldexp(1.0, -49));
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_score_essential_batch(slamb200_ctx* c, int P, const float* pts1,
+                                              const float* pts2, const int32_t* m_off,
+                                              const double K[4], const double* E, int H,
+                                              double threshold_px, int32_t* counts, int32_t* best,
+                                              uint8_t* best_mask) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  if (P < 0 || H < 0) return fail(SLAMB200_ERR_INVALID, "P or H negative");
+  if (P == 0) return SLAMB200_OK;
+  if (!m_off) return fail(SLAMB200_ERR_INVALID, "m_off is NULL");
+  for (int p = 0; p < P; p++)
+    if (m_off[p + 1] < m_off[p]) return fail(SLAMB200_ERR_INVALID, "m_off not monotone");
+  const int total = m_off[P] - m_off[0];
+  if (m_off[0] != 0) return fail(SLAMB200_ERR_INVALID, "m_off[0] must be 0");
+  if ((total > 0 && (!pts1 || !pts2)) || (H > 0 && !E)) return fail(SLAMB200_ERR_INVALID, "NULL input");
+  if ((H > 0 && !counts) || !best) return fail(SLAMB200_ERR_INVALID, "NULL output");
+  ScoreParams sp;
+  int rc = make_score_params(K, threshold_px, &sp);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  cudaStream_t s = L.stream;
+  const size_t tot = total > 0 ? total : 1;
+  if ((rc = buf_reserve(c, L.p1, tot * 8, s))) return rc;
+  if ((rc = buf_reserve(c, L.p2, tot * 8, s))) return rc;
+  if ((rc = buf_reserve(c, L.npts, tot * 32, s))) return rc;
+  if ((rc = buf_reserve(c, L.m_off, sizeof(int32_t) * (size_t)(P + 1), s))) return rc;
+  if ((rc = buf_reserve(c, L.E, sizeof(double) * 9 * (size_t)P * (H > 0 ? H : 1), s))) return rc;
+  if ((rc = buf_reserve(c, L.counts, sizeof(int32_t) * (size_t)P * (H > 0 ? H : 1), s))) return rc;
+  if ((rc = buf_reserve(c, L.best, sizeof(int32_t) * (size_t)P, s))) return rc;
+  if ((rc = buf_reserve(c, L.mask, tot, s))) return rc;
+  if (total > 0) {
+    CU(cudaMemcpyAsync(L.p1.p, pts1, (size_t)total * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(L.p2.p, pts2, (size_t)total * 8, cudaMemcpyHostToDevice, s));
+  }
+  CU(cudaMemcpyAsync(L.m_off.p, m_off, sizeof(int32_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, s));
+  if (H > 0) CU(cudaMemcpyAsync(L.E.p, E, sizeof(double) * 9 * (size_t)P * H, cudaMemcpyHostToDevice, s));
+  launch_normalize_points((const float2*)L.p1.p, (const float2*)L.p2.p, total, sp, (double4*)L.npts.p, s);
+  launch_score_counts((const double4*)L.npts.p, (const int32_t*)L.m_off.p, nullptr, 0,
+                      (const double*)L.E.p, H, P, sp, (int32_t*)L.counts.p, s);
+  launch_score_best((const int32_t*)L.counts.p, H, P, (int32_t*)L.best.p, s);
+  if (best_mask)
+    launch_score_mask((const double4*)L.npts.p, (const int32_t*)L.m_off.p, nullptr, 0,
+                      (const double*)L.E.p, H, P, (const int32_t*)L.best.p, sp, (uint8_t*)L.mask.p, s);
+  CU(cudaGetLastError());
+  if (H > 0) CU(cudaMemcpyAsync(counts, L.counts.p, sizeof(int32_t) * (size_t)P * H, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(best, L.best.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
+  if (best_mask && total > 0) CU(cudaMemcpyAsync(best_mask, L.mask.p, (size_t)total, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_score_essential(slamb200_ctx* c, const float* pts1, const float* pts2,
+                                        int M, const double K[4], const double* E, int H,
+                                        double threshold_px, int32_t* counts, int32_t* best,
+                                        uint8_t* best_mask, uint8_t* all_masks) {
+  if (M < 0) return fail(SLAMB200_ERR_INVALID, "M negative");
+  int32_t off[2] = {0, M};
+  int rc = slamb200_score_essential_batch(c, 1, pts1, pts2, off, K, E, H, threshold_px, counts,
+                                          best, best_mask);
+  if (rc || !all_masks || M == 0 || H == 0) return rc;
+  // parity aid: every (hypothesis, match) flag
+  ScoreParams sp;
+  if ((rc = make_score_params(K, threshold_px, &sp))) return rc;
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  cudaStream_t s = L.stream;
+  if ((rc = buf_reserve(c, L.p1, (size_t)M * 8, s))) return rc;
+  if ((rc = buf_reserve(c, L.p2, (size_t)M * 8, s))) return rc;
+  if ((rc = buf_reserve(c, L.npts, (size_t)M * 32, s))) return rc;
+  if ((rc = buf_reserve(c, L.E, sizeof(double) * 9 * (size_t)H, s))) return rc;
+  if ((rc = buf_reserve(c, L.all_masks, (size_t)H * M, s))) return rc;
+  CU(cudaMemcpyAsync(L.p1.p, pts1, (size_t)M * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(L.p2.p, pts2, (size_t)M * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(L.E.p, E, sizeof(double) * 9 * (size_t)H, cudaMemcpyHostToDevice, s));
+  launch_normalize_points((const float2*)L.p1.p, (const float2*)L.p2.p, M, sp, (double4*)L.npts.p, s);
+  launch_score_all_masks((const double4*)L.npts.p, M, (const double*)L.E.p, H, sp, (uint8_t*)L.all_masks.p, s);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(all_masks, L.all_masks.p, (size_t)H * M, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SLAMB200_OK;
+}
+
+// ---- keypoint coordinates + chained batch scoring ---------------------------------------------
+extern "C" int slamb200_upload_pts(slamb200_ctx* c, const float* xy, int n, size_t stride,
+                                   slamb200_pts** out) {
+  if (!c || !out) return fail(SLAMB200_ERR_INVALID, "upload_pts: NULL argument");
+  *out = nullptr;
+  if (n < 0 || (n > 0 && !xy)) return fail(SLAMB200_ERR_INVALID, "upload_pts: bad xy/n");
+  if (stride == 0) stride = 8;
+  if (stride < 8) return fail(SLAMB200_ERR_INVALID, "upload_pts: stride < 8");
+  CU(cudaSetDevice(c->device));
+  slamb200_pts* p = (slamb200_pts*)calloc(1, sizeof(slamb200_pts));
+  if (!p) return fail(SLAMB200_ERR_NOMEM, "host allocation failed");
+  p->n = n;
+  LaneGuard g(c);
+  cudaStream_t s = g.lane().stream;
+  int rc = dev_alloc(c, (void**)&p->xy, (size_t)(n > 0 ? n : 1) * 8, s);
+  if (rc) { free(p); return rc; }
+  cudaError_t e = cudaSuccess;
+  if (n > 0) e = cudaMemcpy2DAsync(p->xy, 8, xy, stride, 8, n, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(p->ready, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(p->xy, s);
+    free(p);
+    return fail(SLAMB200_ERR_CUDA, "upload_pts: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_free_pts(slamb200_ctx* c, slamb200_pts* p) {
+  if (!p) return SLAMB200_OK;
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  cudaSetDevice(c->device);
+  for (int i = 0; i < N_LANES; i++) cudaStreamSynchronize(c->lanes[i].stream);
+  if (p->xy) cudaFreeAsync(p->xy, c->lanes[1].stream);
+  if (p->ready) cudaEventDestroy(p->ready);
+  free(p);
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_score_batch_enqueue(slamb200_ctx* c, const slamb200_pts* query_pts,
+                                            const slamb200_pts* const* train_pts,
+                                            const double K[4], const double* E, int H,
+                                            double threshold_px, void* stream) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  if (H <= 0 || !E) return fail(SLAMB200_ERR_INVALID, "H <= 0 or E is NULL");
+  ScoreParams sp;
+  int rc = make_score_params(K, threshold_px, &sp);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> lk(c->batch_mu);
+  Lane& L = c->lanes[0];
+  cudaStream_t s = stream ? (cudaStream_t)stream : L.stream;
+  const int P = L.b_pairs, cap = L.b_cap;
+  if (P <= 0) return fail(SLAMB200_ERR_INVALID, "no batch has been enqueued on this context");
+  if (!query_pts || !train_pts) return fail(SLAMB200_ERR_INVALID, "NULL keypoint sets");
+  if (query_pts->n < L.b_nq) return fail(SLAMB200_ERR_INVALID, "query keypoints < query rows");
+  // E and the train keypoint pointer table go through the pinned staging area
+  const size_t e_bytes = sizeof(double) * 9 * (size_t)P * H;
+  const size_t tab_bytes = sizeof(void*) * (size_t)P;
+  if ((rc = stage_reserve(L, e_bytes + tab_bytes))) return rc;
+  memcpy(L.h_stage, E, e_bytes);
+  const float2** tab = (const float2**)((char*)L.h_stage + e_bytes);
+  for (int p = 0; p < P; p++) {
+    if (!train_pts[p]) return fail(SLAMB200_ERR_INVALID, "train keypoint set %d is NULL", p);
+    tab[p] = train_pts[p]->xy;
+  }
+  if ((rc = buf_reserve(c, L.E, e_bytes, s))) return rc;
+  if ((rc = buf_reserve(c, L.txy, tab_bytes, s))) return rc;
+  if ((rc = buf_reserve(c, L.npts, (size_t)P * cap * 32, s))) return rc;
+  if ((rc = buf_reserve(c, L.counts, sizeof(int32_t) * (size_t)P * H, s))) return rc;
+  if ((rc = buf_reserve(c, L.best, sizeof(int32_t) * (size_t)P, s))) return rc;
+  if ((rc = buf_reserve(c, L.mask, (size_t)P * cap, s))) return rc;
+  CU(cudaMemcpyAsync(L.E.p, L.h_stage, e_bytes, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(L.txy.p, tab, tab_bytes, cudaMemcpyHostToDevice, s));
+  CU(cudaEventRecord(L.stage_free, s));
+  CU(cudaStreamWaitEvent(s, query_pts->ready, 0));
+  for (int p = 0; p < P; p++) CU(cudaStreamWaitEvent(s, train_pts[p]->ready, 0));
+  launch_gather_normalize(query_pts->xy, (const float2* const*)L.txy.p,
+                          (const slamb200_dmatch*)L.out.p, cap, (const int32_t*)L.n_out.p, P, sp,
+                          (double4*)L.npts.p, s);
+  launch_score_counts((const double4*)L.npts.p, nullptr, (const int32_t*)L.n_out.p, cap,
+                      (const double*)L.E.p, H, P, sp, (int32_t*)L.counts.p, s);
+  launch_score_best((const int32_t*)L.counts.p, H, P, (int32_t*)L.best.p, s);
+  launch_score_mask((const double4*)L.npts.p, nullptr, (const int32_t*)L.n_out.p, cap,
+                    (const double*)L.E.p, H, P, (const int32_t*)L.best.p, sp, (uint8_t*)L.mask.p, s);
+  CU(cudaGetLastError());
+  L.s_H = H;
+  L.s_pairs = P;
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_batch_scores_fetch(slamb200_ctx* c, int32_t* counts, int32_t* best,
+                                           uint8_t* best_mask, int mask_cap, void* stream) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> lk(c->batch_mu);
+  Lane& L = c->lanes[0];
+  cudaStream_t s = stream ? (cudaStream_t)stream : L.stream;
+  const int P = L.s_pairs, H = L.s_H;
+  if (P <= 0) return fail(SLAMB200_ERR_INVALID, "no scores have been enqueued on this context");
+  if (counts) CU(cudaMemcpyAsync(counts, L.counts.p, sizeof(int32_t) * (size_t)P * H, cudaMemcpyDeviceToHost, s));
+  if (best) CU(cudaMemcpyAsync(best, L.best.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
+  if (best_mask) {
+    if (mask_cap < L.b_cap) return fail(SLAMB200_ERR_INVALID, "mask_cap %d < %d", mask_cap, L.b_cap);
+    CU(cudaMemcpy2DAsync(best_mask, mask_cap, L.mask.p, L.b_cap, L.b_cap, P, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  return SLAMB200_OK;
+}

@@ -1,0 +1,116 @@
+// common.cuh -- internal declarations shared by the kernels and the C ABI of libslamb200.
+//
+// Data layout in HBM (DESIGN.md "Layout"):
+//   SIFT frame (n rows, padded to n_pad = multiple of 256 rows):
+//     f32   [n_pad][128] fp32   the caller's rows (exact path, fp32 rerank)
+//     bf16  [n_pad][128] bf16   tcgen05 operand, same buffer for the query and the train role
+//     augq  [n_pad][16]  bf16   K-augmentation block when the frame is the query  (A operand)
+//     augt  [n_pad][16]  bf16   K-augmentation block when the frame is the train  (B operand)
+//     u8    [n_pad][128] u8     integer copy for the dp4a rerank (exact mode only)
+//     nrm2  [n_pad]      int32  squared norms (exact mode)
+//     flags [4]          int32  [0] = 0 iff every value is an integer in [0,255] and every
+//                               squared norm < 2^20 ("exact mode"); non-zero = general floats
+//   ORB frame: u8 [n_pad][32].
+//   Partial top-2 records: uint4 {key0, idx0, key1, idx1} per (pair, split, query row); key is the
+//   fp32 bit pattern of the distance (L2) or the integer Hamming distance; absent = {~0u, -1}.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/slamb200.h"
+
+#define SLAMB200_TILE_PAD 256
+
+struct slamb200_desc {
+  int kind;
+  int n;
+  int n_pad;
+  float* f32;
+  __nv_bfloat16* bf16;
+  __nv_bfloat16* augq;
+  __nv_bfloat16* augt;
+  uint8_t* u8;
+  int32_t* nrm2;
+  int32_t* flags;      // device
+  int host_exact;      // -2 unknown, else 1 when flags[0] == 0
+  cudaEvent_t ready;   // recorded after the prep kernels
+  void* tmap_main;     // CUtensorMap (128 B) for bf16 as [n_pad][128], box 64 x rows
+  void* tmap_augq;
+  void* tmap_augt;
+};
+
+struct slamb200_pts {
+  int n;
+  float2* xy;  // device
+  cudaEvent_t ready;
+};
+
+// One pair of a batch as the kernels see it (device array of these).
+struct PairArgs {
+  const void* t_rows;      // train rows: float* (SIFT exact) or uint8_t* (ORB)
+  const int32_t* t_flags;  // train exact-mode flag (SIFT) or nullptr
+  int t_n;                 // train row count
+  int t_pad;
+};
+
+#define ABSENT_KEY 0xFFFFFFFFu
+
+// ---- kernel launchers (each in its own .cu) ------------------------------------------------
+// ORB: partial top-2 per (pair, split, query).
+void launch_orb_knn2(const uint8_t* q, int nq, const PairArgs* pairs, int n_pairs, int n_split,
+                     uint4* part, cudaStream_t s);
+// SIFT exact fp32 (cv2 summation order); skips pairs whose query and train are both in exact
+// mode (flags[0] == 0; the tcgen05 path owns those) unless force != 0.
+void launch_sift_exact_knn2(const float* q, const int32_t* q_flags, int nq, const PairArgs* pairs,
+                            int n_pairs, int n_split, uint4* part, int force, cudaStream_t s);
+// merge partials -> raw knn + ratio flags + per-chunk counts, then ordered compaction.
+void launch_finalize(const uint4* part, int nq, const PairArgs* pairs, int n_pairs, int n_split,
+                     int hamming, double ratio, int32_t* knn_idx, float* knn_dist,
+                     uint8_t* flags, int32_t* chunk_cnt, slamb200_dmatch* out, int cap,
+                     int32_t* n_out, cudaStream_t s);
+int finalize_chunks(int nq);
+
+// RANSAC essential scoring.
+struct ScoreParams {
+  double ax, ay, bx, by;  // normalisation: x = u*ax + bx
+  double mid_lo, mid_hi;  // fast accept / reject bounds on num/den
+  float t;                // (float)(thr*thr)
+};
+void launch_normalize_points(const float2* p1, const float2* p2, int total, ScoreParams sp,
+                             double4* out, cudaStream_t s);
+void launch_gather_normalize(const float2* q_xy, const float2* const* t_xy,
+                             const slamb200_dmatch* matches, int cap, const int32_t* n_match,
+                             int n_pairs, ScoreParams sp, double4* out, cudaStream_t s);
+void launch_score_counts(const double4* npts, const int32_t* m_off, const int32_t* m_cnt,
+                         int m_stride, const double* E, int H, int P, ScoreParams sp,
+                         int32_t* counts, cudaStream_t s);
+void launch_score_best(const int32_t* counts, int H, int P, int32_t* best, cudaStream_t s);
+void launch_score_mask(const double4* npts, const int32_t* m_off, const int32_t* m_cnt,
+                       int m_stride, const double* E, int H, int P, const int32_t* best,
+                       ScoreParams sp, uint8_t* mask, cudaStream_t s);
+void launch_score_all_masks(const double4* npts, int M, const double* E, int H, ScoreParams sp,
+                            uint8_t* masks, cudaStream_t s);
+
+// SIFT prep: fp32 rows -> bf16 / aug / u8 / norms / exact flag.  n_pad rows are written
+// (padding rows get an "infinitely far" augmentation so they never become candidates).
+void launch_sift_prep(const float* src, size_t src_stride_floats, int n, int n_pad, float* f32,
+                      __nv_bfloat16* bf16, __nv_bfloat16* augq, __nv_bfloat16* augt, uint8_t* u8,
+                      int32_t* nrm2, int32_t* flags, cudaStream_t s);
+
+// SIFT tcgen05 candidate kernel + dp4a rerank (sift_tc.cu).
+struct TcPair {
+  const void* tmap_main;  // device copy of the train frame's tensor maps (3 x 128 B)
+  const uint8_t* t_u8;
+  const int32_t* t_nrm2;
+  const int32_t* t_flags;
+  int t_n;
+  int t_pad;
+};
+size_t tc_candidate_bytes(int nq_pad, int n_pairs, int max_t_pad);
+int launch_sift_tc(const slamb200_desc* q, const void* q_tmaps_dev, const TcPair* pairs_dev,
+                   const TcPair* pairs_host, int n_pairs, void* cand, uint4* part,
+                   int32_t* err_flag, cudaStream_t s);
+int tc_encode_tmaps(const slamb200_desc* d, void* host_out_3x128);
+
+int64_t* launch_counter();
+#define COUNT_LAUNCH() (++(*launch_counter()))

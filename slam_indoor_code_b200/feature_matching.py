@@ -1,0 +1,249 @@
+"""Host-side mirror of the reference's matching interface over the libslamb200 C ABI.
+
+Names, argument meaning and error behaviour follow
+  src/mainModule/featureMatching/featureMatching.h:12-53        (matchFramesPairFeatures)
+  src/mainModule/featureMatching/featureMatchingCPU.cpp:17-43   (matchFeatures)
+  src/mainModule/featureMatching/featureMatchingCommon.{h,cpp}  (MatcherType, getGoodMatches,
+                                                                 getKeyPointCoordsFromFramePair)
+so that the parity tests read like the reference's call sites (batch.cpp:113-130).  Descriptors are
+NumPy arrays in cv::Mat layout (N x 128 float32 for SIFT, N x 32 uint8 for ORB); matches come
+back as a structured array bit-compatible with cv::DMatch.  The compiled-host twin of this file
+is host/featureMatchingB200.cpp.
+"""
+import ctypes
+import enum
+
+import numpy as np
+
+from . import _capi
+from ._capi import DMATCH, check, ptr
+
+
+class MatcherType(enum.IntEnum):
+    """featureMatchingCommon.h:8-12"""
+    SIFT_BF = 0
+    SIFT_FLANN = 1
+    ORB_BF = 2
+
+
+def getMatcherTypeIndex(config):
+    """featureMatchingCommon.cpp:13-21: flag priority useFM-SIFT-BF > useFM-SIFT-FLANN > useFM-ORB;
+    none set -> the reference throws."""
+    if config.get("useFM-SIFT-BF"):
+        return MatcherType.SIFT_BF
+    if config.get("useFM-SIFT-FLANN"):
+        return MatcherType.SIFT_FLANN
+    if config.get("useFM-ORB"):
+        return MatcherType.ORB_BF
+    raise RuntimeError("no matcher flag set (useFM-SIFT-BF / useFM-SIFT-FLANN / useFM-ORB)")
+
+
+def _kind_of(matcher_type):
+    if matcher_type in (MatcherType.SIFT_BF, MatcherType.SIFT_FLANN):
+        return _capi.DESC_F32X128
+    if matcher_type == MatcherType.ORB_BF:
+        return _capi.DESC_U8X32
+    # featureMatchingCPU.cpp:36-37 / :62-63: default -> throw std::exception()
+    raise RuntimeError(f"bad matcher type {matcher_type!r}")
+
+
+class Context:
+    """One libslamb200 context bound to one CUDA device."""
+
+    def __init__(self, device=0):
+        self._lib = _capi.load()
+        h = ctypes.c_void_p()
+        check(self._lib.slamb200_init(int(device), ctypes.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.slamb200_shutdown(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(self._lib.slamb200_synchronize(self._h))
+
+    def launch_count(self):
+        return int(self._lib.slamb200_launch_count(self._h))
+
+    # -- descriptor sets ("upload once per frame") --------------------------------------------
+    def upload(self, desc, kind=None):
+        """Host descriptor Mat (N x 128 float32 or N x 32 uint8, row pitch honoured) -> HBM."""
+        desc = np.asarray(desc)
+        if kind is None:
+            kind = _capi.DESC_U8X32 if desc.dtype == np.uint8 else _capi.DESC_F32X128
+        width = 128 if kind == _capi.DESC_F32X128 else 32
+        want = np.float32 if kind == _capi.DESC_F32X128 else np.uint8
+        if desc.dtype != want:
+            raise TypeError(f"descriptor dtype {desc.dtype} does not fit kind {kind}")
+        if desc.size == 0:
+            desc = np.zeros((0, width), want)
+        if desc.ndim != 2 or desc.shape[1] != width:
+            raise ValueError(f"descriptor shape {desc.shape}, expected (N, {width})")
+        if desc.strides[1] != desc.itemsize:
+            desc = np.ascontiguousarray(desc)
+        stride = desc.strides[0] if desc.shape[0] > 1 else width * desc.itemsize
+        h = ctypes.c_void_p()
+        check(self._lib.slamb200_upload_desc(self._h, kind, ptr(desc), desc.shape[0], stride,
+                                             ctypes.byref(h)))
+        return DescriptorSet(self, h, desc.shape[0], kind)
+
+    def upload_device(self, dev_ptr, n, kind, row_stride=0, stream=None):
+        """Rows already resident on this device (raw pointer, e.g. torch.Tensor.data_ptr())."""
+        h = ctypes.c_void_p()
+        check(self._lib.slamb200_upload_desc_device(self._h, kind, ctypes.c_void_p(dev_ptr), n,
+                                                    row_stride, ctypes.c_void_p(stream or 0),
+                                                    ctypes.byref(h)))
+        return DescriptorSet(self, h, n, kind)
+
+    def upload_keypoints(self, xy):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        h = ctypes.c_void_p()
+        check(self._lib.slamb200_upload_pts(self._h, ptr(xy), xy.shape[0], 8, ctypes.byref(h)))
+        return KeypointSet(self, h, xy.shape[0])
+
+    # -- hot path A ------------------------------------------------------------------------------
+    def knnMatch(self, matcher_type, query, train):
+        """DescriptorMatcher::knnMatch(query, train, k=2) raw: idx[nq,2] (-1 absent), dist[nq,2]."""
+        _kind_of(matcher_type)
+        idx = np.full((query.n, 2), -1, np.int32)
+        dist = np.zeros((query.n, 2), np.float32)
+        check(self._lib.slamb200_knn2(self._h, int(matcher_type), query._h, train._h, ptr(idx),
+                                      ptr(dist)))
+        return idx, dist
+
+    def matchFeatures(self, prevDesc, curDesc, matcherType, knnMatcherDistance=0.7):
+        """featureMatchingCPU.cpp:17-43 on resident descriptor sets: knnMatch(prev, cur, 2) then
+        getGoodMatches.  Returns the good matches (DMATCH structured array, ascending queryIdx)."""
+        _kind_of(matcherType)
+        cap = max(prevDesc.n, 1)
+        out = np.zeros(cap, DMATCH)
+        n = ctypes.c_int(0)
+        check(self._lib.slamb200_match_pair(self._h, int(matcherType), prevDesc._h, curDesc._h,
+                                            float(knnMatcherDistance), ptr(out), cap,
+                                            ctypes.byref(n)))
+        return out[: n.value].copy()
+
+    def matchBatch(self, prevDesc, trainDescs, matcherType, knnMatcherDistance=0.7):
+        """The batch window of batch.cpp:120-148 in one call: list of good-match arrays."""
+        _kind_of(matcherType)
+        P = len(trainDescs)
+        cap = max(prevDesc.n, 1)
+        out = np.zeros((max(P, 1), cap), DMATCH)
+        n_out = np.zeros(max(P, 1), np.int32)
+        arr = (ctypes.c_void_p * max(P, 1))(*[t._h for t in trainDescs])
+        check(self._lib.slamb200_match_batch(self._h, int(matcherType), prevDesc._h, arr, P,
+                                             float(knnMatcherDistance), ptr(out), cap, ptr(n_out)))
+        return [out[p, : n_out[p]].copy() for p in range(P)]
+
+    def matchWindow(self, frames, matcherType, knnMatcherDistance=0.7):
+        """All i<j pairs of a frame window: dict {(i, j): matches}."""
+        _kind_of(matcherType)
+        F = len(frames)
+        P = F * (F - 1) // 2
+        cap = max([f.n for f in frames] + [1])
+        out = np.zeros((max(P, 1), cap), DMATCH)
+        n_out = np.zeros(max(P, 1), np.int32)
+        arr = (ctypes.c_void_p * max(F, 1))(*[f._h for f in frames])
+        check(self._lib.slamb200_match_window(self._h, int(matcherType), arr, F,
+                                              float(knnMatcherDistance), ptr(out), cap, ptr(n_out)))
+        res, p = {}, 0
+        for i in range(F):
+            for j in range(i + 1, F):
+                res[(i, j)] = out[p, : n_out[p]].copy()
+                p += 1
+        return res
+
+    # device-resident batch (bench / pipelines): enqueue on a stream, fetch later
+    def matchBatchEnqueue(self, prevDesc, trainDescs, matcherType, knnMatcherDistance=0.7,
+                          stream=None):
+        _kind_of(matcherType)
+        P = len(trainDescs)
+        arr = (ctypes.c_void_p * max(P, 1))(*[t._h for t in trainDescs])
+        check(self._lib.slamb200_match_batch_enqueue(self._h, int(matcherType), prevDesc._h, arr,
+                                                     P, float(knnMatcherDistance),
+                                                     ctypes.c_void_p(stream or 0)))
+        self._last = (P, max(prevDesc.n, 1))
+
+    def batchFetch(self, stream=None):
+        P, cap = self._last
+        out = np.zeros((max(P, 1), cap), DMATCH)
+        n_out = np.zeros(max(P, 1), np.int32)
+        check(self._lib.slamb200_batch_fetch(self._h, ptr(out), cap, ptr(n_out),
+                                             ctypes.c_void_p(stream or 0)))
+        return [out[p, : n_out[p]] for p in range(P)], n_out[:P]
+
+
+class DescriptorSet:
+    """One frame's descriptors resident in HBM (slamb200_desc)."""
+
+    def __init__(self, ctx, h, n, kind):
+        self._ctx, self._h, self.n, self.kind = ctx, h, n, kind
+
+    @property
+    def exact_mode(self):
+        return int(self._ctx._lib.slamb200_desc_exact_mode(self._h))
+
+    def free(self):
+        if self._h and self._ctx._h:
+            self._ctx._lib.slamb200_free_desc(self._ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class KeypointSet:
+    def __init__(self, ctx, h, n):
+        self._ctx, self._h, self.n = ctx, h, n
+
+    def free(self):
+        if self._h and self._ctx._h:
+            self._ctx._lib.slamb200_free_pts(self._ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def matchFramesPairFeatures(ctx, firstFrameDescriptor, secondDescriptor, matcherType,
+                            knnMatcherDistance=0.7):
+    """featureMatching.h:47-53 with the descriptor of the second frame already extracted
+    (extractDescriptor stays OpenCV-CPU; it only produces this function's input): uploads both
+    Mats, matches, returns the good matches."""
+    kind = _kind_of(matcherType)
+    a = ctx.upload(firstFrameDescriptor, kind)
+    b = ctx.upload(secondDescriptor, kind)
+    try:
+        return ctx.matchFeatures(a, b, matcherType, knnMatcherDistance)
+    finally:
+        a.free()
+        b.free()
+
+
+def getKeyPointCoordsFromFramePair(prevFrameFeatures, nextFrameFeatures, matches):
+    """featureMatchingCommon.cpp:23-33 (host gather; the device twin runs inside
+    slamb200_score_batch_enqueue)."""
+    prev = np.asarray(prevFrameFeatures, np.float32).reshape(-1, 2)
+    nxt = np.asarray(nextFrameFeatures, np.float32).reshape(-1, 2)
+    return prev[matches["queryIdx"]].copy(), nxt[matches["trainIdx"]].copy()

@@ -1,0 +1,310 @@
+"""GPU parity tests for hot path A (kNN-2 + Lowe ratio) -- all through the C ABI.
+
+Checker: the CPU oracle (oracle/, pinned to cv2) and the committed cv2 fixtures.  Bit-exact:
+train indices, accept/reject, float distance bit patterns.  Mirrors the reference's call shape
+matchFeatures(prevDesc, curDesc, matches, type) (featureMatchingCPU.cpp:17-43).
+"""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle, synth
+from slam_indoor_code_b200 import _capi
+from slam_indoor_code_b200.feature_matching import (MatcherType, getMatcherTypeIndex,
+                                                    matchFramesPairFeatures)
+
+SIFT_GOLD = ["sift_int", "sift_float", "sift_ties", "sift_t1", "sift_t2", "sift_q1"]
+
+
+def _f32(a):
+    return a if a.dtype == np.float32 else a.astype(np.float32)
+
+
+def _check_knn(idx, dist, ridx, rdist):
+    assert np.array_equal(idx, ridx)
+    valid = ridx >= 0
+    assert np.array_equal(dist[valid].view(np.int32), rdist[valid].view(np.int32))
+
+
+def _knn_and_matches(ctx, matcher, q, t, ratio=0.7):
+    Q, T = ctx.upload(q), ctx.upload(t)
+    idx, dist = ctx.knnMatch(matcher, Q, T)
+    good = ctx.matchFeatures(Q, T, matcher, ratio)
+    Q.free(); T.free()
+    return idx, dist, good
+
+
+@pytest.mark.parametrize("name", SIFT_GOLD)
+@pytest.mark.parametrize("matcher", [MatcherType.SIFT_BF, MatcherType.SIFT_FLANN])
+def test_sift_golden(ctx, golden_dir, name, matcher):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    q, t = _f32(g["q"]), _f32(g["t"])
+    idx, dist, good = _knn_and_matches(ctx, matcher, q, t)
+    _check_knn(idx, dist, g["idx"], g["dist"])
+    assert np.array_equal(good, c_oracle.ratio_test(g["idx"], g["dist"], 0.7))
+
+
+@pytest.mark.parametrize("name", ["orb", "orb_t1"])
+def test_orb_golden(ctx, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.ORB_BF, g["q"], g["t"])
+    _check_knn(idx, dist, g["idx"], g["dist"])
+    assert np.array_equal(good, c_oracle.ratio_test(g["idx"], g["dist"], 0.7))
+
+
+@pytest.mark.parametrize("nq,nt,seed", [(1000, 1500, 101), (2049, 777, 102), (130, 4100, 103)])
+def test_sift_int_seeded(ctx, nq, nt, seed):
+    q, t = synth.sift_pair(nq, nt, seed)
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.SIFT_BF, q, t)
+    ridx, rdist = c_oracle.l2_knn2(q, t)
+    _check_knn(idx, dist, ridx, rdist)
+    ref = c_oracle.ratio_test(ridx, rdist, 0.7)
+    assert np.array_equal(good, ref) and len(ref) > 0.2 * min(nq, nt)
+
+
+@pytest.mark.parametrize("nq,nt,seed", [(700, 900, 201), (257, 2300, 202)])
+def test_sift_float_seeded(ctx, nq, nt, seed):
+    """General floats: the low bits of the distances depend on cv2's summation order."""
+    q, t = synth.float_pair(nq, nt, seed)
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.SIFT_BF, q, t, ratio=0.95)
+    ridx, rdist = c_oracle.l2_knn2(q, t)
+    _check_knn(idx, dist, ridx, rdist)
+    assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.95))
+
+
+def test_sift_mixed_exactness(ctx):
+    """An integer-valued query against a float train set (and the reverse) takes the exact path."""
+    qi, ti = synth.sift_pair(300, 400, 301)
+    qf, tf = synth.float_pair(300, 400, 302)
+    for q, t in ((qi, tf), (qf, ti)):
+        idx, dist, _ = _knn_and_matches(ctx, MatcherType.SIFT_BF, q, t)
+        _check_knn(idx, dist, *c_oracle.l2_knn2(q, t))
+
+
+def test_sift_large_norm_integers(ctx):
+    """Integer rows whose squared norm exceeds 2^20 are not 'exact mode' but must still match."""
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 256, (300, 128)).astype(np.float32)
+    t = rng.integers(0, 256, (500, 128)).astype(np.float32)
+    t[17] = q[3]
+    Q, T = ctx.upload(q), ctx.upload(t)
+    assert Q.exact_mode == 0
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, Q, T)
+    _check_knn(idx, dist, *c_oracle.l2_knn2(q, t))
+    assert ctx.upload(synth.sift_like(64, 1)).exact_mode == 1
+
+
+@pytest.mark.parametrize("nq,nt,seed", [(1500, 2500, 401), (4097, 300, 402), (100, 5000, 403)])
+def test_orb_seeded(ctx, nq, nt, seed):
+    q, t = synth.orb_pair(nq, nt, seed)
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.ORB_BF, q, t)
+    ridx, rdist = c_oracle.hamming_knn2(q, t)
+    _check_knn(idx, dist, ridx, rdist)
+    assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.7))
+
+
+def test_orb_many_ties(ctx):
+    """Few distinct descriptors -> masses of equal distances: lowest train index must win."""
+    rng = np.random.default_rng(6)
+    base = rng.integers(0, 256, (5, 32), dtype=np.uint8)
+    q = base[rng.integers(0, 5, 400)]
+    t = base[rng.integers(0, 5, 3000)]
+    idx, dist, _ = _knn_and_matches(ctx, MatcherType.ORB_BF, q, t)
+    _check_knn(idx, dist, *c_oracle.hamming_knn2(q, t))
+
+
+def test_sift_many_ties(ctx):
+    rng = np.random.default_rng(7)
+    base = synth.sift_like(6, 8)
+    q = base[rng.integers(0, 6, 300)]
+    t = base[rng.integers(0, 6, 2600)]
+    idx, dist, _ = _knn_and_matches(ctx, MatcherType.SIFT_BF, q, t)
+    _check_knn(idx, dist, *c_oracle.l2_knn2(q, t))
+
+
+@pytest.mark.parametrize("matcher", [MatcherType.SIFT_BF, MatcherType.ORB_BF])
+def test_empty_and_single_row_sets(ctx, matcher):
+    if matcher == MatcherType.ORB_BF:
+        q, t = synth.orb_pair(9, 5, 501, planted=0)
+        e = np.zeros((0, 32), np.uint8)
+    else:
+        q, t = synth.sift_pair(9, 5, 501, planted=0)
+        e = np.zeros((0, 128), np.float32)
+    Q, T, E = ctx.upload(q), ctx.upload(t), ctx.upload(e)
+    # empty query -> no rows, no matches (cv2: empty result)
+    idx, dist = ctx.knnMatch(matcher, E, T)
+    assert idx.shape == (0, 2)
+    assert len(ctx.matchFeatures(E, T, matcher)) == 0
+    # empty train -> Q empty lists
+    idx, dist = ctx.knnMatch(matcher, Q, E)
+    assert np.all(idx == -1)
+    assert len(ctx.matchFeatures(Q, E, matcher)) == 0
+    # one train row -> one-element lists; getGoodMatches' read of [1] is UB: defined as reject
+    T1 = ctx.upload(t[:1])
+    idx, dist = ctx.knnMatch(matcher, Q, T1)
+    assert np.all(idx[:, 0] == 0) and np.all(idx[:, 1] == -1)
+    assert len(ctx.matchFeatures(Q, T1, matcher)) == 0
+
+
+def test_row_pitch_is_honoured(ctx):
+    """cv::Mat::step: rows 640 B apart (SIFT) / 48 B apart (ORB)."""
+    q, t = synth.sift_pair(200, 300, 601)
+    wide = np.zeros((300, 160), np.float32)
+    wide[:, :128] = t
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, ctx.upload(q), ctx.upload(wide[:, :128]))
+    _check_knn(idx, dist, *c_oracle.l2_knn2(q, t))
+    q, t = synth.orb_pair(200, 300, 602)
+    wide = np.zeros((300, 48), np.uint8)
+    wide[:, :32] = t
+    idx, dist = ctx.knnMatch(MatcherType.ORB_BF, ctx.upload(q), ctx.upload(wide[:, :32]))
+    _check_knn(idx, dist, *c_oracle.hamming_knn2(q, t))
+
+
+def test_ratio_values(ctx):
+    q, t = synth.sift_pair(600, 700, 701)
+    ridx, rdist = c_oracle.l2_knn2(q, t)
+    Q, T = ctx.upload(q), ctx.upload(t)
+    for r in (0.0, 0.5, 0.7, 0.8, 1.0, 1.5):
+        assert np.array_equal(ctx.matchFeatures(Q, T, MatcherType.SIFT_BF, r),
+                              c_oracle.ratio_test(ridx, rdist, r))
+
+
+def test_bad_matcher_type_and_kind_mismatch(ctx):
+    """featureMatchingCPU.cpp:36-37 throws on an unknown type; a Mat of the wrong type asserts."""
+    q, t = synth.sift_pair(10, 10, 801)
+    Q, T = ctx.upload(q), ctx.upload(t)
+    with pytest.raises(RuntimeError):
+        ctx.matchFeatures(Q, T, 7)
+    out = np.zeros(16, _capi.DMATCH)
+    n = np.zeros(1, np.int32)
+    rc = ctx._lib.slamb200_match_pair(ctx._h, 7, Q._h, T._h, 0.7, _capi.ptr(out), 16, _capi.ptr(n))
+    assert rc == _capi.ERR_MATCHER
+    rc = ctx._lib.slamb200_match_pair(ctx._h, 2, Q._h, T._h, 0.7, _capi.ptr(out), 16, _capi.ptr(n))
+    assert rc == _capi.ERR_KIND
+    rc = ctx._lib.slamb200_match_pair(ctx._h, 0, Q._h, T._h, 0.7, _capi.ptr(out), 4, _capi.ptr(n))
+    assert rc == _capi.ERR_INVALID                       # capacity below rows(query)
+    assert getMatcherTypeIndex({"useFM-SIFT-BF": True, "useFM-ORB": True}) == MatcherType.SIFT_BF
+    assert getMatcherTypeIndex({"useFM-SIFT-FLANN": True, "useFM-ORB": True}) == MatcherType.SIFT_FLANN
+    with pytest.raises(RuntimeError):
+        getMatcherTypeIndex({})
+
+
+@pytest.mark.parametrize("matcher", [MatcherType.SIFT_BF, MatcherType.ORB_BF])
+def test_batch_window_equals_pairs(ctx, matcher):
+    """batch.cpp:120-148: one query frame against a ragged batch of train frames."""
+    sizes = [700, 1, 0, 1300, 256, 2]
+    if matcher == MatcherType.ORB_BF:
+        q = synth.orb_pair(900, 8, 900)[0]
+        trains = [synth.orb_pair(8, n, 901 + i)[1] if n else np.zeros((0, 32), np.uint8)
+                  for i, n in enumerate(sizes)]
+    else:
+        q = synth.sift_like(900, 900)
+        trains = [synth.sift_train_from_query(q, n, 901 + i) if n else np.zeros((0, 128), np.float32)
+                  for i, n in enumerate(sizes)]
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(t) for t in trains]
+    got = ctx.matchBatch(Q, Ts, matcher, 0.7)
+    for t, g in zip(trains, got):
+        assert np.array_equal(g, c_oracle.match_features(int(matcher), q, t, 0.7))
+    ctx.matchBatchEnqueue(Q, Ts, matcher, 0.7)
+    got2, n_out = ctx.batchFetch()
+    for a, b in zip(got, got2):
+        assert np.array_equal(a, b)
+    assert len(ctx.matchBatch(Q, [], matcher, 0.7)) == 0
+
+
+def test_frame_window_all_pairs(ctx):
+    frames = [synth.sift_like(300 + 50 * i, 1000 + i) for i in range(4)]
+    for i in range(1, 4):                                   # plant overlap with frame 0
+        frames[i][:100] = frames[0][:100]
+    sets = [ctx.upload(f) for f in frames]
+    res = ctx.matchWindow(sets, MatcherType.SIFT_BF, 0.7)
+    assert sorted(res) == [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+    for (i, j), m in res.items():
+        assert np.array_equal(m, c_oracle.match_features(0, frames[i], frames[j], 0.7))
+
+
+def test_concurrent_host_threads_share_query(ctx):
+    """batch.cpp:181-201: threadsCount std::threads, one shared read-only query descriptor."""
+    q = synth.sift_like(800, 1100)
+    trains = [synth.sift_train_from_query(q, 900 + 10 * i, 1101 + i) for i in range(8)]
+    Q = ctx.upload(q)
+    res, errs = [None] * 8, []
+
+    def work(i):
+        try:
+            T = ctx.upload(trains[i])
+            res[i] = ctx.matchFeatures(Q, T, MatcherType.SIFT_BF, 0.7)
+            T.free()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for i in range(8):
+        assert np.array_equal(res[i], c_oracle.match_features(0, q, trains[i], 0.7))
+
+
+def test_match_frames_pair_features_entry_point(ctx):
+    """featureMatching.h:47-53 shape: descriptors in, good matches out."""
+    q, t = synth.sift_pair(500, 600, 1201)
+    got = matchFramesPairFeatures(ctx, q, t, MatcherType.SIFT_FLANN, 0.7)
+    assert np.array_equal(got, c_oracle.match_features(1, q, t, 0.7))
+    q, t = synth.orb_pair(500, 600, 1202)
+    got = matchFramesPairFeatures(ctx, q, t, MatcherType.ORB_BF, 0.7)
+    assert np.array_equal(got, c_oracle.match_features(2, q, t, 0.7))
+
+
+# ---- BASELINE.json full sizes: size-independent properties --------------------------------------
+def _properties(ctx, matcher, q, t):
+    Q, T = ctx.upload(q), ctx.upload(t)
+    idx, dist = ctx.knnMatch(matcher, Q, T)
+    good = ctx.matchFeatures(Q, T, matcher, 0.7)
+    n = q.shape[0]
+    assert idx.shape == (n, 2) and idx.min() >= 0 and idx.max() < t.shape[0]
+    assert np.all(dist[:, 0] <= dist[:, 1]) and np.all(idx[:, 0] != idx[:, 1])
+    assert np.all(np.diff(good["queryIdx"]) > 0)                       # ascending queryIdx
+    keep = dist[:, 0].astype(np.float64) < 0.7 * dist[:, 1].astype(np.float64)
+    assert np.array_equal(good["queryIdx"], np.nonzero(keep)[0])
+    assert np.array_equal(good["trainIdx"], idx[keep, 0])
+    # spot-check 64 rows against the oracle (full rows, all 10k trains)
+    rows = np.random.default_rng(1).choice(n, 64, replace=False)
+    ridx, rdist = (c_oracle.hamming_knn2 if matcher == MatcherType.ORB_BF else c_oracle.l2_knn2)(q[rows], t)
+    _check_knn(idx[rows], dist[rows], ridx, rdist)
+    # train-set permutation: distances invariant, indices mapped
+    perm = np.random.default_rng(2).permutation(t.shape[0])
+    Tp = ctx.upload(np.ascontiguousarray(t[perm]))
+    idx2, dist2 = ctx.knnMatch(matcher, Q, Tp)
+    assert np.array_equal(dist2.view(np.int32), dist.view(np.int32))
+    untied = dist[:, 0] != dist[:, 1]
+    assert np.array_equal(perm[idx2[untied, 0]], idx[untied, 0])
+    # self match: every row finds itself at distance 0 (lowest index among duplicates)
+    idx3, dist3 = ctx.knnMatch(matcher, T, T)
+    assert np.all(dist3[:, 0] == 0) and np.all(idx3[:, 0] <= np.arange(t.shape[0]))
+    return good
+
+
+def test_cfg1_sift_10k_properties(ctx):
+    q, t = synth.sift_pair(10000, 10000, 1001)
+    good = _properties(ctx, MatcherType.SIFT_BF, q, t)
+    assert 2500 < len(good) < 4000                                     # ~30 % planted
+
+
+def test_cfg2_orb_10k_properties(ctx):
+    q, t = synth.orb_pair(10000, 10000, 2001)
+    good = _properties(ctx, MatcherType.ORB_BF, q, t)
+    assert len(good) > 2000
+
+
+def test_cfg1_float_10k_spot(ctx):
+    q, t = synth.float_pair(10000, 10000, 1002)
+    Q, T = ctx.upload(q), ctx.upload(t)
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, Q, T)
+    rows = np.random.default_rng(3).choice(10000, 48, replace=False)
+    _check_knn(idx[rows], dist[rows], *c_oracle.l2_knn2(q[rows], t))

@@ -1,0 +1,143 @@
+"""CPU: the oracle (C and NumPy restatements) against the committed cv2-generated fixtures.
+
+tests/golden/*.npz hold the outputs of the reference's own arithmetic owner (OpenCV, through the
+cv2 wheel; oracle/gen_golden.py) for the calls the reference makes at
+featureMatchingCPU.cpp:26-40 and cameraTranslation.cpp:41-46.  Bit-exact everywhere: indices,
+float distances (bit patterns), masks.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, np_oracle
+
+L2_CASES = ["sift_int", "sift_float", "sift_ties", "sift_t1", "sift_t2", "sift_q1"]
+
+
+def _load(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    return g, g["q"].astype(np.float32) if g["q"].dtype != np.float32 else g["q"], \
+        g["t"].astype(np.float32) if g["t"].dtype != np.float32 else g["t"]
+
+
+def _same_knn(idx, dist, g):
+    assert np.array_equal(idx, g["idx"])
+    valid = g["idx"] >= 0
+    assert np.array_equal(dist[valid].view(np.int32), g["dist"][valid].view(np.int32))
+
+
+@pytest.mark.parametrize("name", L2_CASES)
+def test_c_oracle_l2_matches_cv2(golden_dir, name):
+    g, q, t = _load(golden_dir, name)
+    idx, dist = c_oracle.l2_knn2(q, t)
+    _same_knn(idx, dist, g)
+
+
+@pytest.mark.parametrize("name", L2_CASES)
+def test_np_oracle_l2_matches_cv2(golden_dir, name):
+    g, q, t = _load(golden_dir, name)
+    idx, dist = np_oracle.knn2_from_matrix(np_oracle.l2_dist_matrix(q, t))
+    _same_knn(idx, dist, g)
+
+
+@pytest.mark.parametrize("name", ["orb", "orb_t1"])
+def test_oracles_hamming_match_cv2(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    idx, dist = c_oracle.hamming_knn2(g["q"], g["t"])
+    _same_knn(idx, dist, g)
+    idx, dist = np_oracle.knn2_from_matrix(np_oracle.hamming_dist_matrix(g["q"], g["t"]))
+    _same_knn(idx, dist, g)
+
+
+def test_ties_keep_lowest_train_index(golden_dir):
+    g, q, t = _load(golden_dir, "sift_ties")
+    idx, dist = c_oracle.l2_knn2(q, t)
+    # query 5 has two exact copies in the train set at rows 7 and 20: both distance 0, 7 first
+    assert list(idx[5]) == [7, 20] and dist[5, 0] == 0 and dist[5, 1] == 0
+    # query 9 has one exact copy at row 60
+    assert idx[9, 0] == 60 and dist[9, 0] == 0
+    # identical queries get identical rows
+    assert np.array_equal(idx[11], idx[12])
+
+
+def test_short_train_sets(golden_dir):
+    g, q, t = _load(golden_dir, "sift_t1")
+    assert list(g["lens"]) == [1] * q.shape[0]          # cv2: one-element lists when T == 1
+    idx, _ = c_oracle.l2_knn2(q, t)
+    assert np.all(idx[:, 0] == 0) and np.all(idx[:, 1] == -1)
+    # getGoodMatches would read [1] out of bounds there (reference UB): defined as "reject"
+    assert len(c_oracle.match_features(0, q, t, 0.7)) == 0
+    # empty sets
+    e = np.zeros((0, 128), np.float32)
+    assert c_oracle.l2_knn2(e, t)[0].shape == (0, 2)
+    idx, _ = c_oracle.l2_knn2(q, e)
+    assert np.all(idx == -1)
+    assert len(c_oracle.match_features(0, q, e, 0.7)) == 0
+
+
+def test_ratio_test_is_strict_and_in_double():
+    idx = np.array([[3, 4], [5, 6], [7, 8], [1, -1], [-1, -1]], np.int32)
+    d1 = np.float32(10.0)
+    on = np.float32(np.float64(0.7) * np.float64(d1))        # (float) of the double product
+    dist = np.array([[on, d1], [np.nextafter(on, np.float32(0)), d1], [0, 0], [1, 0], [0, 0]],
+                    np.float32)
+    got = c_oracle.ratio_test(idx, dist, 0.7)
+    ref = np_oracle.ratio_test(idx, dist, 0.7)
+    assert np.array_equal(got, ref)
+    exp = [q for q in range(3) if float(dist[q, 0]) < 0.7 * float(dist[q, 1])]
+    assert list(got["queryIdx"]) == exp
+    assert 2 not in got["queryIdx"]                           # 0 < 0.7*0 is false
+    assert np.all(got["imgIdx"] == 0)
+
+
+def test_c_and_np_oracles_agree_on_seeded_inputs():
+    from oracle import synth
+    q, t = synth.sift_pair(150, 170, 77)
+    a = c_oracle.match_features(0, q, t, 0.7)
+    idx, dist = np_oracle.knn2_from_matrix(np_oracle.l2_dist_matrix(q, t))
+    b = np_oracle.ratio_test(idx, dist, 0.7)
+    assert np.array_equal(a, b) and len(a) > 10
+    q, t = synth.orb_pair(120, 140, 78)
+    a = c_oracle.match_features(2, q, t, 0.7)
+    idx, dist = np_oracle.knn2_from_matrix(np_oracle.hamming_dist_matrix(q, t))
+    assert np.array_equal(a, np_oracle.ratio_test(idx, dist, 0.7)) and len(a) > 10
+    with pytest.raises(ValueError):
+        c_oracle.match_features(3, q, t, 0.7)
+
+
+def test_ransac_masks_match_cv2(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ransac.npz"))
+    for c in range(4):
+        p1, p2 = g[f"p1_{c}"], g[f"p2_{c}"]
+        for orc in (c_oracle, np_oracle):
+            counts, best, mask, _ = orc.score_essential(p1, p2, g["K4"], g[f"E_cv_{c}"],
+                                                        float(g["threshold_px"]))[:4]
+            assert best == 0
+            assert np.array_equal(mask, g[f"mask_cv_{c}"])
+            assert counts[0] == int(g[f"mask_cv_{c}"].sum())
+
+
+def test_ransac_c_vs_np_on_hypothesis_lists(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ransac.npz"))
+    for c in range(4):
+        p1, p2, hyp = g[f"p1_{c}"], g[f"p2_{c}"], g[f"hyp_{c}"]
+        ca, ba, ma, alla = c_oracle.score_essential(p1, p2, g["K4"], hyp, 5.0, want_all_masks=True)
+        cb, bb, mb, allb = np_oracle.score_essential(p1, p2, g["K4"], hyp, 5.0)
+        assert np.array_equal(ca, cb) and ba == bb and np.array_equal(ma, mb)
+        assert np.array_equal(alla, allb)
+        # first-best-wins, and only above 4 inliers
+        if ba >= 0:
+            assert ca[ba] == ca.max() and ca[ba] > 4 and np.argmax(ca) == ba
+
+
+def test_ransac_first_best_and_min_count():
+    from oracle import synth
+    p1, p2, R, t = synth.two_view(200, 42)
+    E = synth.pose_hypotheses(8, R, t, 43)
+    E2 = np.concatenate([E, E])                               # duplicates: the first must win
+    c, b, m, _ = c_oracle.score_essential(p1, p2, synth.SAMSUNG_HV_4K, E2, 5.0)
+    assert b == int(np.argmax(c)) and b < 8
+    # three matches can never exceed the "> 4" floor
+    c, b, m, _ = c_oracle.score_essential(p1[:3], p2[:3], synth.SAMSUNG_HV_4K, E, 5.0)
+    assert b == -1 and not m.any()
