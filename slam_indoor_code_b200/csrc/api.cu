@@ -48,7 +48,7 @@ struct Lane {
   cudaStream_t stream = nullptr;
   bool busy = false;
   // matching scratch (device)
-  DevBuf pairs, tcpairs, part, cand, knn_idx, knn_dist, flags, chunk_cnt, out, n_out, err_flag;
+  DevBuf pairs, tcpairs, tile_prefix, part, cand, knn_idx, knn_dist, flags, chunk_cnt, out, n_out, err_flag;
   // scoring scratch (device)
   DevBuf npts, E, counts, best, mask, m_off, p1, p2, txy, all_masks;
   // pinned staging
@@ -59,6 +59,7 @@ struct Lane {
   // state of the last enqueued batch
   int b_matcher = -1, b_nq = 0, b_pairs = 0, b_cap = 0;
   int s_H = 0, s_pairs = 0;
+  float* dbg = nullptr;  // debug: raw accumulator dump target of the next tcgen05 launch
 };
 #define N_SMALL 65536
 
@@ -69,6 +70,8 @@ struct slamb200_ctx {
   std::condition_variable cv;
   Lane lanes[N_LANES];  // lane 0 is the batch (enqueue/fetch) lane
   std::mutex batch_mu;
+  int n_sm = 148;
+  int use_tc = 1;  // debug switch (slamb200_dbg_set_tc): 0 routes exact-mode pairs to the fp32 kernel
 };
 
 static int dev_alloc(slamb200_ctx* c, void** p, size_t bytes, cudaStream_t s) {
@@ -149,6 +152,7 @@ extern "C" int slamb200_init(int device, slamb200_ctx** out) {
   slamb200_ctx* c = new (std::nothrow) slamb200_ctx();
   if (!c) return fail(SLAMB200_ERR_NOMEM, "host allocation failed");
   c->device = device;
+  c->n_sm = prop.multiProcessorCount;
   cudaMemPoolProps pp;
   memset(&pp, 0, sizeof(pp));
   pp.allocType = cudaMemAllocationTypePinned;
@@ -180,7 +184,7 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
   cudaDeviceSynchronize();
   for (int i = 0; i < N_LANES; i++) {
     Lane& L = c->lanes[i];
-    DevBuf* bufs[] = {&L.pairs, &L.tcpairs, &L.part, &L.cand, &L.knn_idx, &L.knn_dist, &L.flags,
+    DevBuf* bufs[] = {&L.pairs, &L.tcpairs, &L.tile_prefix, &L.part, &L.cand, &L.knn_idx, &L.knn_dist, &L.flags,
                       &L.chunk_cnt, &L.out, &L.n_out, &L.err_flag, &L.npts, &L.E, &L.counts,
                       &L.best, &L.mask, &L.m_off, &L.p1, &L.p2, &L.txy, &L.all_masks};
     for (DevBuf* b : bufs)
@@ -266,6 +270,15 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
                      d->nrm2, d->flags, s);
     DCU(cudaGetLastError());
     if (raw) DCU(cudaFreeAsync(raw, s));
+    {
+      alignas(64) unsigned char tm[128];
+      if (tc_encode_tmap(d->bf16, d->n_pad, tm) != 0) {
+        rc = fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        goto done;
+      }
+      if ((rc = dev_alloc(c, &d->d_tmap, 128, s))) goto done;
+      DCU(cudaMemcpyAsync(d->d_tmap, tm, 128, cudaMemcpyHostToDevice, s));
+    }
   }
   DCU(cudaEventRecord(d->ready, s));
   if (!src_on_device) DCU(cudaStreamSynchronize(s));  // the caller may reuse `rows` on return
@@ -297,11 +310,10 @@ extern "C" int slamb200_free_desc(slamb200_ctx* c, slamb200_desc* d) {
   // work queued by this context that may still read the set must drain first
   for (int i = 0; i < N_LANES; i++) cudaStreamSynchronize(c->lanes[i].stream);
   cudaStream_t s = c->lanes[1].stream;
-  void* ptrs[] = {d->f32, d->bf16, d->augq, d->augt, d->u8, d->nrm2, d->flags};
+  void* ptrs[] = {d->f32, d->bf16, d->augq, d->augt, d->u8, d->nrm2, d->flags, d->d_tmap};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, s);
   if (d->ready) cudaEventDestroy(d->ready);
-  free(d->tmap_main);
   free(d);
   return SLAMB200_OK;
 }
@@ -386,6 +398,8 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   if ((rc = buf_reserve(c, L.chunk_cnt, sizeof(int32_t) * (size_t)n_pairs * (finalize_chunks(cap) + 1), s))) return rc;
   if ((rc = buf_reserve(c, L.out, sizeof(slamb200_dmatch) * rows, s))) return rc;
   if ((rc = buf_reserve(c, L.n_out, sizeof(int32_t) * (size_t)n_pairs, s))) return rc;
+  if ((rc = buf_reserve(c, L.err_flag, 16, s))) return rc;
+  CU(cudaMemsetAsync(L.err_flag.p, 0, 16, s));
 
   // the descriptor sets must have finished their prep kernels
   CU(cudaStreamWaitEvent(s, q->ready, 0));
@@ -394,15 +408,50 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   if (orb) {
     launch_orb_knn2(q->u8, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split, (uint4*)L.part.p, s);
   } else {
-    // general-float pairs: exact fp32 kernel.  Exact-mode pairs (integer-valued descriptors)
-    // are skipped inside that kernel once the tcgen05 path is present and take it instead.
-#ifdef SLAMB200_HAVE_TC
-    const int force = 0;
-#else
-    const int force = 1;
-#endif
+    // General-float pairs: exact fp32 kernel (it skips exact-mode pairs unless force).  Exact-mode
+    // pairs (integer-valued descriptors, what cv::SIFT emits): tcgen05 candidates + dp4a rerank
+    // (those kernels skip the general-float pairs).  Both read the flags on the device, so no
+    // host synchronisation is needed to pick the path.
     launch_sift_exact_knn2(q->f32, q->flags, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split,
-                           (uint4*)L.part.p, force, s);
+                           (uint4*)L.part.p, c->use_tc ? 0 : 1, s);
+    if (c->use_tc && nq > 0) {
+      const int n_rb = (nq + 127) / 128;
+      if ((rc = stage_reserve(L, (sizeof(TcPair) + sizeof(int32_t)) * (size_t)(n_pairs + 1)))) return rc;
+      TcPair* tp = (TcPair*)L.h_stage;
+      int32_t* pre = (int32_t*)(tp + n_pairs);
+      int n_cb_max = 1;
+      long long total = 0;
+      for (int p = 0; p < n_pairs; p++) {
+        tp[p].tmap_main = trains[p]->d_tmap;
+        tp[p].t_aug = (const uint8_t*)trains[p]->augt;
+        tp[p].t_u8 = trains[p]->u8;
+        tp[p].t_nrm2 = trains[p]->nrm2;
+        tp[p].t_flags = trains[p]->flags;
+        tp[p].t_n = trains[p]->n;
+        tp[p].t_pad = trains[p]->n_pad;
+        const int n_cb = (trains[p]->n + 255) / 256;
+        n_cb_max = n_cb > n_cb_max ? n_cb : n_cb_max;
+        pre[p] = (int32_t)total;
+        total += (long long)n_cb * n_rb;
+      }
+      pre[n_pairs] = (int32_t)total;
+      if (total > 0x7fffffffLL) return fail(SLAMB200_ERR_INVALID, "batch too large (tile count)");
+      const int n_cta = total < c->n_sm ? (int)total : c->n_sm;
+      const int n_slots = tc_slots(n_cb_max, (int)total, n_cta > 0 ? n_cta : 1);
+      const size_t cand_bytes = sizeof(uint4) * (size_t)n_pairs * n_slots * (size_t)n_rb * 128;
+      if ((rc = buf_reserve(c, L.tcpairs, sizeof(TcPair) * (size_t)n_pairs, s))) return rc;
+      if ((rc = buf_reserve(c, L.tile_prefix, sizeof(int32_t) * (size_t)(n_pairs + 1), s))) return rc;
+      if ((rc = buf_reserve(c, L.cand, cand_bytes, s))) return rc;
+      CU(cudaMemcpyAsync(L.tcpairs.p, tp, sizeof(TcPair) * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(L.tile_prefix.p, pre, sizeof(int32_t) * (size_t)(n_pairs + 1), cudaMemcpyHostToDevice, s));
+      CU(cudaEventRecord(L.stage_free, s));
+      CU(cudaMemsetAsync(L.cand.p, 0xFF, cand_bytes, s));
+      if (launch_sift_tc(q->d_tmap, (const uint8_t*)q->augq, q->flags, q->u8, q->nrm2, nq,
+                         (const TcPair*)L.tcpairs.p, (const int32_t*)L.tile_prefix.p, n_pairs,
+                         (int)total, n_cta, n_slots, n_split, (uint4*)L.cand.p, (uint4*)L.part.p,
+                         (int32_t*)L.err_flag.p, L.dbg, s) != 0)
+        return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
+    }
   }
   CU(cudaGetLastError());
   launch_finalize((const uint4*)L.part.p, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split,
@@ -425,7 +474,11 @@ static int fetch_batch(Lane& L, cudaStream_t s, slamb200_dmatch* out, int out_ca
   if (out_cap < L.b_nq) return fail(SLAMB200_ERR_INVALID, "cap %d < query rows %d", out_cap, L.b_nq);
   if (!out) return fail(SLAMB200_ERR_INVALID, "out is NULL");
   CU(cudaMemcpyAsync(n_out, L.n_out.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(L.h_small, L.err_flag.p, 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  if (L.h_small[0] != 0)
+    return fail(SLAMB200_ERR_INTERNAL, "device self-check failed (flag %d): tensor-core candidates "
+                "disagree with the exact rerank", L.h_small[0]);
   int mx = 0;
   for (int p = 0; p < P; p++) mx = n_out[p] > mx ? n_out[p] : mx;
   if (mx > 0) {
@@ -473,7 +526,10 @@ extern "C" int slamb200_knn2(slamb200_ctx* c, int matcher, const slamb200_desc* 
     CU(cudaMemcpyAsync(idx, L.knn_idx.p, sizeof(int32_t) * 2 * (size_t)q->n, cudaMemcpyDeviceToHost, L.stream));
     CU(cudaMemcpyAsync(dist, L.knn_dist.p, sizeof(float) * 2 * (size_t)q->n, cudaMemcpyDeviceToHost, L.stream));
   }
+  CU(cudaMemcpyAsync(L.h_small, L.err_flag.p, 4, cudaMemcpyDeviceToHost, L.stream));
   CU(cudaStreamSynchronize(L.stream));
+  if (L.h_small[0] != 0)
+    return fail(SLAMB200_ERR_INTERNAL, "device self-check failed (flag %d)", L.h_small[0]);
   return SLAMB200_OK;
 }
 
@@ -729,4 +785,35 @@ extern "C" int slamb200_batch_scores_fetch(slamb200_ctx* c, int32_t* counts, int
   }
   CU(cudaStreamSynchronize(s));
   return SLAMB200_OK;
+}
+
+// ---- debug hooks (not part of the public header) ----------------------------------------------
+extern "C" int slamb200_dbg_set_tc(slamb200_ctx* c, int on) {
+  if (!c) return SLAMB200_ERR_INVALID;
+  c->use_tc = on ? 1 : 0;
+  return SLAMB200_OK;
+}
+
+// Raw fp32 accumulators (d^2/2) of the first 128 x 256 tile of (query, train): out[128*256].
+extern "C" int slamb200_dbg_tc_tile(slamb200_ctx* c, const slamb200_desc* q, const slamb200_desc* t,
+                                    float* out) {
+  if (!c || !q || !t || !out) return SLAMB200_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  float* d = nullptr;
+  int rc = dev_alloc(c, (void**)&d, 128 * 256 * 4, L.stream);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(d, 0, 128 * 256 * 4, L.stream));
+  L.dbg = d;
+  const slamb200_desc* tt[1] = {t};
+  rc = enqueue_batch(c, L, L.stream, SLAMB200_SIFT_BF, q, tt, 1, 0.7);
+  L.dbg = nullptr;
+  if (rc == SLAMB200_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, d, 128 * 256 * 4, cudaMemcpyDeviceToHost, L.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
+    if (e != cudaSuccess) rc = fail(SLAMB200_ERR_CUDA, "dbg_tc_tile: %s", cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d, L.stream);
+  return rc;
 }

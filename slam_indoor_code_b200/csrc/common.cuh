@@ -6,6 +6,8 @@
 //     bf16  [n_pad][128] bf16   tcgen05 operand, same buffer for the query and the train role
 //     augq  [n_pad][16]  bf16   K-augmentation block when the frame is the query  (A operand)
 //     augt  [n_pad][16]  bf16   K-augmentation block when the frame is the train  (B operand)
+//                               both stored in UMMA's no-swizzle core-matrix order: per 8-row
+//                               group 256 B = [8 rows x k 0..7][8 rows x k 8..15]
 //     u8    [n_pad][128] u8     integer copy for the dp4a rerank (exact mode only)
 //     nrm2  [n_pad]      int32  squared norms (exact mode)
 //     flags [4]          int32  [0] = 0 iff every value is an integer in [0,255] and every
@@ -34,9 +36,7 @@ struct slamb200_desc {
   int32_t* flags;      // device
   int host_exact;      // -2 unknown, else 1 when flags[0] == 0
   cudaEvent_t ready;   // recorded after the prep kernels
-  void* tmap_main;     // CUtensorMap (128 B) for bf16 as [n_pad][128], box 64 x rows
-  void* tmap_augq;
-  void* tmap_augt;
+  void* d_tmap;        // device copy of the CUtensorMap (128 B) over bf16: box 64 x 128, SW128
 };
 
 struct slamb200_pts {
@@ -99,18 +99,22 @@ void launch_sift_prep(const float* src, size_t src_stride_floats, int n, int n_p
 
 // SIFT tcgen05 candidate kernel + dp4a rerank (sift_tc.cu).
 struct TcPair {
-  const void* tmap_main;  // device copy of the train frame's tensor maps (3 x 128 B)
+  const void* tmap_main;   // the train frame's CUtensorMap, resident in device memory
+  const uint8_t* t_aug;    // train-role K-augmentation block (interleaved core-matrix layout)
   const uint8_t* t_u8;
   const int32_t* t_nrm2;
   const int32_t* t_flags;
   int t_n;
   int t_pad;
 };
-size_t tc_candidate_bytes(int nq_pad, int n_pairs, int max_t_pad);
-int launch_sift_tc(const slamb200_desc* q, const void* q_tmaps_dev, const TcPair* pairs_dev,
-                   const TcPair* pairs_host, int n_pairs, void* cand, uint4* part,
-                   int32_t* err_flag, cudaStream_t s);
-int tc_encode_tmaps(const slamb200_desc* d, void* host_out_3x128);
+int tc_encode_tmap(const void* bf16_dev, int n_pad, void* host_out_128B);
+size_t tc_smem_bytes();
+int tc_slots(int n_cb_max, int total_tiles, int n_cta);
+int launch_sift_tc(const void* q_tmap_dev, const uint8_t* q_aug, const int32_t* q_flags,
+                   const uint8_t* q_u8, const int32_t* q_nrm2, int nq, const TcPair* pairs_dev,
+                   const int32_t* tile_prefix_dev, int n_pairs, int total_tiles, int n_cta,
+                   int n_slots, int n_split, uint4* cand, uint4* part, int32_t* err_flag,
+                   float* dbg, cudaStream_t s);
 
 int64_t* launch_counter();
 #define COUNT_LAUNCH() (++(*launch_counter()))

@@ -47,7 +47,6 @@ sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ 
   extern __shared__ __align__(16) float smem[];
   float* sq = smem;                      // [SE_QT][SE_PITCH]
   float* st = smem + SE_QT * SE_PITCH;   // [SE_TT][SE_PITCH]
-  uint4* smerge = reinterpret_cast<uint4*>(st);  // reused after the main loop: [SE_QT][32]
 
   const int pair = blockIdx.z;
   const int split = blockIdx.y;
@@ -147,7 +146,6 @@ sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ 
     if (lane == 0 && qrow < nq)
       part[((size_t)pair * n_split + split) * nq + qrow] = best[a];
   }
-  (void)smerge;
 }
 
 void launch_sift_exact_knn2(const float* q, const int32_t* q_flags, int nq, const PairArgs* pairs,

@@ -73,8 +73,10 @@ sift_prep_kernel(const float* __restrict__ src, size_t src_stride, int n, int n_
     if (lane == 3) { aq = one; at = h; }
     if (lane == 4) { aq = one; at = m; }
     if (lane == 5) { aq = one; at = l; }
-    augq[(size_t)row * 16 + lane] = __float2bfloat16_rn(aq);
-    augt[(size_t)row * 16 + lane] = __float2bfloat16_rn(at);
+    // UMMA no-swizzle K-major core-matrix order: 8-row group -> [k 0..7 of 8 rows][k 8..15 ...]
+    const size_t o = (size_t)(row >> 3) * 128 + (size_t)(lane >> 3) * 64 + (row & 7) * 8 + (lane & 7);
+    augq[o] = __float2bfloat16_rn(aq);
+    augt[o] = __float2bfloat16_rn(at);
   }
 }
 
