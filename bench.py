@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/s of the SIFT kNN-2 + ratio hot path on the framesBatchSize window.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path: OpenCV)
+
+Workload (BASELINE.json configs[2], the one its metric is quoted on): one query frame against a
+batch of 210 train frames, 10,000 SIFT descriptors (128-d) per frame, BF L2 kNN k=2 + Lowe ratio
+0.7 -- the window findGoodFramesFromBatch walks (batch.cpp:120-148).  A step is one pass over the
+whole 210-pair batch.  With N GPUs the 210 pairs are split contiguously over the ranks (strong
+scaling, no data-path collective); NCCL only gathers the per-pair match counts after the timed
+region.
+
+  value  = pairs/s with every descriptor set already resident in HBM, CUDA-event timed.
+  e2e    = pairs/s through the C ABI with HOST buffers: every step uploads the query and the 210
+           train descriptor Mats from pinned host memory, matches, and copies the match lists back.
+  roofline = the tcgen05 candidate kernel: 2*Q*T*128 FLOP per pair / its CUDA-event duration,
+           against the measured cuBLAS bf16 peak in MEASURED_PEAKS.json.
+  cpu_baseline = the same OpenCV calls the reference makes (cv2.BFMatcher.knnMatch + the
+           getGoodMatches loop) on the box's host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PAIRS = 210
+N_ROWS = 10000
+RATIO = 0.7
+FLOP_PER_PAIR = 2.0 * N_ROWS * N_ROWS * 128
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def my_pairs(rank, world, n=N_PAIRS):
+    lo = n * rank // world
+    hi = n * (rank + 1) // world
+    return list(range(lo, hi))
+
+
+def make_inputs(pairs, pinned):
+    """Query frame + the owned train frames (seeds of SURVEY.md 8d cfg3), as float32 N x 128."""
+    import torch
+    from oracle import synth  # input generator only (shared with the tests)
+    q = synth.sift_like(N_ROWS, 3000)
+
+    def hold(a):
+        if not pinned:
+            return a
+        t = torch.empty(a.shape, dtype=torch.float32).pin_memory()
+        v = t.numpy()
+        v[...] = a
+        return v
+
+    keep = [hold(q)]
+    trains = []
+    for p in pairs:
+        t = hold(synth.sift_train_from_query(q, N_ROWS, 3001 + p))
+        trains.append(t)
+    return keep[0], trains
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15] or self.rows
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return d, "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, \
+        "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the OpenCV calls the reference makes (featureMatchingCPU.cpp:27-42)
+# ------------------------------------------------------------------------------------------------
+def cpu_match_pair(q, t):
+    """Returns the number of good matches.  cv2 when importable (the reference's own arithmetic
+    owner), else the C oracle port."""
+    try:
+        import cv2
+    except Exception:
+        cv2 = None
+    if cv2 is not None:
+        res = cv2.BFMatcher(cv2.NORM_L2).knnMatch(q, t, 2)
+        n = 0
+        for r in res:           # getGoodMatches, featureMatchingCommon.cpp:43-49
+            if len(r) >= 2 and r[0].distance < RATIO * r[1].distance:
+                n += 1
+        return n
+    from oracle import c_oracle
+    return len(c_oracle.match_features(0, q, t, RATIO))
+
+
+def cpu_threads():
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count() or 1)
+        return int(cv2.getNumThreads()), "reference", \
+            f"cv2 {cv2.__version__} BFMatcher(NORM_L2).knnMatch k=2 + getGoodMatches loop"
+    except Exception:
+        from oracle import c_oracle
+        return int(c_oracle.set_threads(os.cpu_count() or 1)), "port", \
+            "oracle/corr_oracle.c (OpenMP) knn2 + ratio"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: rank 0 times the CPU path on a bounded sample of the same batch."""
+    if rank != 0:
+        return
+    cores, kind, what = cpu_threads()
+    n_sample = max(1, args.ref_pairs)
+    q, trains = make_inputs(list(range(n_sample)), pinned=False)
+    for _ in range(args.warmup):
+        cpu_match_pair(q, trains[0])
+    t0 = time.perf_counter()
+    good = 0
+    for _ in range(args.steps):
+        for t in trains:
+            good += cpu_match_pair(q, t)
+    dt = time.perf_counter() - t0
+    value = n_sample * args.steps / dt
+    sample = (f"{n_sample} of the {N_PAIRS} pairs per step ({what}); the reference binary itself "
+              "cannot be built here (no OpenCV C++ dev files), these are the calls it makes")
+    line = {
+        "impl": "reference", "metric": "SIFT 10k x 10k kNN+ratio frame-pairs/s", "value": value,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world, n_sample_note=f"CPU arm: {n_sample} pairs per step"),
+        "tflops": value * FLOP_PER_PAIR / 1e12,
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world, n_sample_note=None):
+    cfg = {"workload": "cfg3: framesBatchSize=210 window, 1 query frame x 210 train frames, "
+                       "10000 SIFT 128-d descriptors per frame, BF L2 kNN k=2 + ratio 0.7",
+           "pairs": N_PAIRS, "rows_per_frame": N_ROWS, "ratio": RATIO,
+           "sharding": f"{N_PAIRS} pairs split contiguously over {world} rank(s); no data-path collective",
+           "l2": "inputs larger than L2 (211 resident descriptor sets, 0.6 GB of bf16 operands per step)"}
+    if n_sample_note:
+        cfg["note"] = n_sample_note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from slam_indoor_code_b200.feature_matching import Context, MatcherType
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.zeros(1, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    pairs = my_pairs(rank, world)
+    t_gen = time.perf_counter()
+    q, trains = make_inputs(pairs, pinned=True)
+    log(f"[rank {rank}] generated {len(trains)} train frames in {time.perf_counter() - t_gen:.1f}s")
+
+    ctx = Context(local)
+    stream = torch.cuda.current_stream().cuda_stream
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(t) for t in trains]
+    assert Q.exact_mode == 1 and all(t.exact_mode == 1 for t in Ts[:2]), \
+        "synthetic SIFT rows must take the tcgen05 path"
+
+    def step():
+        ctx.matchBatchEnqueue(Q, Ts, MatcherType.SIFT_BF, RATIO, stream)
+
+    # ---- device-resident throughput (the headline `value`) ------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    launches = torch.tensor([ctx.launch_count() - launches0], device=dev, dtype=torch.float64)
+    clocks = sampler.stop(t0, t1)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    value = N_PAIRS * args.steps / (ms_total / 1e3)
+
+    matches, n_out = ctx.batchFetch(stream)
+    n_good = torch.zeros(N_PAIRS, device=dev, dtype=torch.int32)
+    if pairs:
+        n_good[pairs[0]: pairs[-1] + 1] = torch.from_numpy(np.ascontiguousarray(n_out)).to(dev)
+    if world > 1:
+        dist.all_reduce(n_good, op=dist.ReduceOp.SUM)   # NCCL: gather the per-pair results
+    n_good = n_good.cpu().numpy()
+
+    # ---- roofline of the dominant kernel (tcgen05 candidates), this rank ------------------------
+    peaks, peak_src = measured_peaks()
+    tc_ms, tc_n = prof["sift_tc"]
+    roof = None
+    if tc_n > 0:
+        per_launch_flop = FLOP_PER_PAIR * len(pairs)
+        achieved = per_launch_flop / (tc_ms / tc_n / 1e3) / 1e12
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        roof = {"bound": "tensor", "kernel": "sift_tc_kernel (tcgen05 bf16 candidates)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
+                "frac_of_burst": achieved / float(peaks.get("bf16_tflops", peak)),
+                "kernel_ms_per_launch": tc_ms / tc_n, "kernel_share_of_step": tc_ms / ms_total
+                if world == 1 else None,
+                "traffic": TRAFFIC_BYTES_PER_LAUNCH}
+
+    # ---- e2e through the C ABI with host buffers -------------------------------------------------
+    for t in Ts:
+        t.free()
+    Q.free()
+    e2e_steps = max(0, min(args.steps, args.e2e_steps))
+    h2d = (len(trains) + 1) * N_ROWS * 512
+    d2h = 0
+
+    def e2e_step():
+        nonlocal d2h
+        Qe = ctx.upload_pinned(q)
+        Te = [ctx.upload_pinned(t) for t in trains]
+        res = ctx.matchBatch(Qe, Te, MatcherType.SIFT_BF, RATIO)
+        mx = max([len(r) for r in res] + [0])
+        d2h = len(res) * 4 + len(res) * mx * 16
+        for t in Te:
+            t.free()
+        Qe.free()
+        return res
+
+    res = matches
+    for _ in range(2 if e2e_steps else 0):
+        e2e_step()
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = e2e_step()
+    barrier()
+    te = torch.tensor([max(time.perf_counter() - te0, 1e-9)], device=dev, dtype=torch.float64)
+    io = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    e2e_value = N_PAIRS * e2e_steps / float(te.item()) if e2e_steps else None
+    same = all(np.array_equal(a, b) for a, b in zip(res, matches))
+
+    if rank == 0:
+        line = {
+            "metric": "SIFT 10k x 10k kNN+ratio frame-pairs/s", "value": value, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world),
+            "tflops": value * FLOP_PER_PAIR / 1e12,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(io[0].item()),
+                    "d2h_bytes_per_step": int(io[1].item()), "steps": e2e_steps,
+                    "timing": "host wall clock between device synchronisations, max over ranks",
+                    "results_equal_device_resident_run": bool(same)},
+            "gpu_launches": int(launches.item()),
+            "roofline": roof,
+            "checksum": {"good_matches_total": int(n_good.sum()), "pairs": int((n_good > 0).sum())},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(q, trains, matches, args.cpu_seconds)
+        if world == 1 and not args.no_extras:
+            line["extras"] = extras(ctx, stream)
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram bytes of the tcgen05 kernel per launch from the committed ncu capture (profiles/); null
+# until a capture of this exact kernel version exists.
+TRAFFIC_BYTES_PER_LAUNCH = None
+
+
+def cpu_baseline(q, trains, gpu_matches, seconds):
+    """Rank 0, N=1: the OpenCV CPU path on a bounded sample of the same batch, result-checked."""
+    cores, kind, what = cpu_threads()
+    t0 = time.perf_counter()
+    n0 = cpu_match_pair(q, trains[0])
+    one = time.perf_counter() - t0
+    n = int(max(1, min(len(trains) - 1, seconds / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    agree = n0 == len(gpu_matches[0])
+    for i in range(1, n + 1):
+        agree = agree and (cpu_match_pair(q, trains[i]) == len(gpu_matches[i]))
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "pairs/s", "cores": cores, "kind": kind,
+            "sample": f"pairs 1..{n} of the {N_PAIRS} ({what}); good-match counts equal the GPU's: {agree}",
+            "tflops": n / dt * FLOP_PER_PAIR / 1e12}
+
+
+def extras(ctx, stream):
+    """Short device-resident probes of the other BASELINE.json configs (not the headline)."""
+    import torch
+    from oracle import synth
+    from slam_indoor_code_b200 import camera_translation as ct
+    from slam_indoor_code_b200.feature_matching import MatcherType
+    out = {}
+
+    def ev_time(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    q, t = synth.sift_pair(N_ROWS, N_ROWS, 1001)
+    Q, T = ctx.upload(q), ctx.upload(t)
+    ms = ev_time(lambda: ctx.matchBatchEnqueue(Q, [T], MatcherType.SIFT_BF, RATIO, stream), 50)
+    out["cfg1_sift_single_pair"] = {"us_per_pair": ms * 1e3, "pairs_per_s": 1e3 / ms,
+                                    "tflops": FLOP_PER_PAIR / ms / 1e9}
+    q, t = synth.orb_pair(N_ROWS, N_ROWS, 2001)
+    Q, T = ctx.upload(q), ctx.upload(t)
+    ms = ev_time(lambda: ctx.matchBatchEnqueue(Q, [T] * 16, MatcherType.ORB_BF, RATIO, stream), 10)
+    out["cfg2_orb_16_pairs"] = {"us_per_pair": ms / 16 * 1e3, "pairs_per_s": 16e3 / ms,
+                                "tpopc_per_s": 16 * 8e8 / ms / 1e9}
+    # cfg5: 2048 hypotheses x 5000 matches, 32 pairs per launch, host-call timing incl. copies
+    p1, p2, R, tv = synth.two_view(5000, 5000)
+    E = synth.pose_hypotheses(2048, R, tv, 5001)
+    P = 32
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    for _ in range(3):
+        ct.scoreEssentialBatch(ctx, [p1] * P, [p2] * P, synth.SAMSUNG_HV_4K, np.stack([E] * P), 5.0)
+    kms, kn = ctx.profile_read()["ransac"]
+    ctx.profile_enable(False)
+    out["cfg5_ransac_2048x5000"] = {"kernel_us_per_pair": kms / kn / P * 1e3,
+                                    "fp64_tflops_40flop_convention": P * 2048 * 5000 * 40 / (kms / kn) / 1e9}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the CPU arm")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        log("warmup < 3 requested; the timing rules ask for >= 3")
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        log(f"--gpus {args.gpus} needs torchrun (one rank per GPU); running this process as 1 rank")
+    run_b200(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,11 @@ int slamb200_upload_desc(slamb200_ctx* ctx, int kind, const void* rows, int n, s
  * `stream` (a cudaStream_t, may be NULL) is the stream the bytes were produced on. */
 int slamb200_upload_desc_device(slamb200_ctx* ctx, int kind, const void* rows, int n,
                                 size_t row_stride, void* stream, slamb200_desc** out);
+/* Pipelined upload for callers that keep `rows` in page-locked host memory: returns as soon as
+ * the copy is queued; `rows` must stay valid and unmodified until slamb200_synchronize(ctx) or
+ * until a matching call that uses the set has returned its results. */
+int slamb200_upload_desc_pinned(slamb200_ctx* ctx, int kind, const void* rows, int n,
+                                size_t row_stride, slamb200_desc** out);
 int slamb200_free_desc(slamb200_ctx* ctx, slamb200_desc* d);
 int slamb200_desc_rows(const slamb200_desc* d);
 int slamb200_desc_kind(const slamb200_desc* d);
@@ -158,7 +163,7 @@ int slamb200_upload_pts(slamb200_ctx* ctx, const float* xy, int n, size_t stride
 int slamb200_free_pts(slamb200_ctx* ctx, slamb200_pts* p);
 
 /* Chained batch: score, for every pair of the last slamb200_match_batch_enqueue, H hypotheses
- * (E: n_pairs*H*9 host doubles) against that pair's accepted matches, gathering the coordinates
+ * (E: n_pairs*H*9 doubles, host memory or already resident on the context's device) against that pair's accepted matches, gathering the coordinates
  * on the device (query_pts / train_pts[p]).  Results stay in HBM until
  * slamb200_batch_scores_fetch.  Enqueue-only. */
 int slamb200_score_batch_enqueue(slamb200_ctx* ctx, const slamb200_pts* query_pts,
@@ -166,6 +171,17 @@ int slamb200_score_batch_enqueue(slamb200_ctx* ctx, const slamb200_pts* query_pt
                                  const double* E, int H, double threshold_px, void* stream);
 int slamb200_batch_scores_fetch(slamb200_ctx* ctx, int32_t* counts, int32_t* best,
                                 uint8_t* best_mask, int mask_cap, void* stream);
+
+/* ---- kernel timing (CUDA events recorded around the hot kernels inside the enqueue calls) -- */
+#define SLAMB200_K_SIFT_TC 0    /* tcgen05 candidate kernel          */
+#define SLAMB200_K_SIFT_EXACT 1 /* exact fp32 kernel (general floats) */
+#define SLAMB200_K_ORB 2        /* Hamming kernel                    */
+#define SLAMB200_K_RANSAC 3     /* Sampson counting kernel           */
+#define SLAMB200_K_COUNT 4
+int slamb200_profile_enable(slamb200_ctx* ctx, int on);
+/* Synchronises, then returns the summed device time (ms) and the launch count of each kernel
+ * class since the last read; ms and launches have SLAMB200_K_COUNT entries. */
+int slamb200_profile_read(slamb200_ctx* ctx, double* ms, int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@ SYMBOLS = {
     "slamb200_synchronize": (_i, [_vp]),
     "slamb200_upload_desc": (_i, [_vp, _i, _vp, _i, _sz, _pp]),
     "slamb200_upload_desc_device": (_i, [_vp, _i, _vp, _i, _sz, _vp, _pp]),
+    "slamb200_upload_desc_pinned": (_i, [_vp, _i, _vp, _i, _sz, _pp]),
     "slamb200_free_desc": (_i, [_vp, _vp]),
     "slamb200_desc_rows": (_i, [_vp]),
     "slamb200_desc_kind": (_i, [_vp]),
@@ -42,6 +43,8 @@ SYMBOLS = {
     "slamb200_free_pts": (_i, [_vp, _vp]),
     "slamb200_score_batch_enqueue": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _d, _vp]),
     "slamb200_batch_scores_fetch": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "slamb200_profile_enable": (_i, [_vp, _i]),
+    "slamb200_profile_read": (_i, [_vp, _vp, _vp]),
 }
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_MATCHER, ERR_KIND, ERR_INTERNAL = 0, -1, -2, -3, -4, -5, -6

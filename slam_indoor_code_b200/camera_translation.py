@@ -61,17 +61,24 @@ def scoreEssentialBatch(ctx, points1_list, points2_list, K4, E, RPRANSACThreshol
     return counts[:, :H], best, masks
 
 
-def scoreBatchEnqueue(ctx, query_kps, train_kps, K4, E, RPRANSACThreshold=5.0, stream=None):
+def scoreBatchEnqueue(ctx, query_kps, train_kps, K4, E, RPRANSACThreshold=5.0, stream=None,
+                      E_device_ptr=None, H=None):
     """Chains onto the last matchBatchEnqueue: gathers the matched keypoints on the device
-    (getKeyPointCoordsFromFramePair) and scores H hypotheses per pair.  Enqueue-only."""
+    (getKeyPointCoordsFromFramePair) and scores H hypotheses per pair.  Enqueue-only.  E is a host
+    array [P, H, 9], or (E_device_ptr, H) names P*H*9 doubles already resident on the device."""
     P = len(train_kps)
-    E = np.ascontiguousarray(E, np.float64).reshape(P, -1, 9)
     K4 = np.ascontiguousarray(K4, np.float64)
     arr = (ctypes.c_void_p * max(P, 1))(*[t._h for t in train_kps])
-    check(ctx._lib.slamb200_score_batch_enqueue(ctx._h, query_kps._h, arr, ptr(K4), ptr(E),
-                                                E.shape[1], float(RPRANSACThreshold),
+    if E_device_ptr is not None:
+        e_ptr = ctypes.c_void_p(E_device_ptr)
+    else:
+        E = np.ascontiguousarray(E, np.float64).reshape(P, -1, 9)
+        H = E.shape[1]
+        e_ptr = ptr(E)
+    check(ctx._lib.slamb200_score_batch_enqueue(ctx._h, query_kps._h, arr, ptr(K4), e_ptr, int(H),
+                                                float(RPRANSACThreshold),
                                                 ctypes.c_void_p(stream or 0)))
-    ctx._last_score = (P, E.shape[1])
+    ctx._last_score = (P, int(H))
 
 
 def batchScoresFetch(ctx, stream=None):

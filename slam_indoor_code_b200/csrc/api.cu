@@ -63,8 +63,16 @@ struct Lane {
 };
 #define N_SMALL 65536
 
+struct ProfEvent {
+  cudaEvent_t a, b;
+  int kind;
+};
+
 struct slamb200_ctx {
   int device = 0;
+  int profile = 0;
+  std::mutex prof_mu;
+  std::vector<ProfEvent> prof;
   cudaMemPool_t pool = nullptr;
   std::mutex mu;
   std::condition_variable cv;
@@ -200,11 +208,56 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
   return SLAMB200_OK;
 }
 
+// ---- kernel timing ---------------------------------------------------------------------------
+struct ProfScope {
+  slamb200_ctx* c;
+  cudaStream_t s;
+  ProfEvent ev;
+  bool on;
+  ProfScope(slamb200_ctx* c_, cudaStream_t s_, int kind) : c(c_), s(s_), on(c_->profile != 0) {
+    if (!on) return;
+    ev.kind = kind;
+    if (cudaEventCreate(&ev.a) != cudaSuccess || cudaEventCreate(&ev.b) != cudaSuccess) { on = false; return; }
+    cudaEventRecord(ev.a, s);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(ev.b, s);
+    std::lock_guard<std::mutex> lk(c->prof_mu);
+    c->prof.push_back(ev);
+  }
+};
+
+extern "C" int slamb200_profile_enable(slamb200_ctx* c, int on) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  c->profile = on ? 1 : 0;
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_profile_read(slamb200_ctx* c, double* ms, int64_t* launches) {
+  if (!c || !ms || !launches) return fail(SLAMB200_ERR_INVALID, "profile_read: NULL argument");
+  CU(cudaSetDevice(c->device));
+  for (int k = 0; k < SLAMB200_K_COUNT; k++) { ms[k] = 0; launches[k] = 0; }
+  std::lock_guard<std::mutex> lk(c->prof_mu);
+  for (ProfEvent& e : c->prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) {
+      ms[e.kind] += t;
+      launches[e.kind] += 1;
+    }
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  c->prof.clear();
+  return SLAMB200_OK;
+}
+
 // ---- descriptor sets ------------------------------------------------------------------------
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_t row_stride,
-                       bool src_on_device, cudaStream_t producer, slamb200_desc** out) {
+                       bool src_on_device, cudaStream_t producer, bool no_sync,
+                       slamb200_desc** out) {
   if (!c || !out) return fail(SLAMB200_ERR_INVALID, "upload_desc: NULL argument");
   *out = nullptr;
   if (kind != SLAMB200_DESC_F32X128 && kind != SLAMB200_DESC_U8X32)
@@ -271,17 +324,17 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
     DCU(cudaGetLastError());
     if (raw) DCU(cudaFreeAsync(raw, s));
     {
-      alignas(64) unsigned char tm[128];
-      if (tc_encode_tmap(d->bf16, d->n_pad, tm) != 0) {
+      alignas(64) unsigned char tm[512];
+      if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->n_pad, tm) != 0) {
         rc = fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
         goto done;
       }
-      if ((rc = dev_alloc(c, &d->d_tmap, 128, s))) goto done;
-      DCU(cudaMemcpyAsync(d->d_tmap, tm, 128, cudaMemcpyHostToDevice, s));
+      if ((rc = dev_alloc(c, &d->d_tmap, 512, s))) goto done;
+      DCU(cudaMemcpyAsync(d->d_tmap, tm, 512, cudaMemcpyHostToDevice, s));
     }
   }
   DCU(cudaEventRecord(d->ready, s));
-  if (!src_on_device) DCU(cudaStreamSynchronize(s));  // the caller may reuse `rows` on return
+  if (!src_on_device && !no_sync) DCU(cudaStreamSynchronize(s));  // the caller may reuse `rows` on return
 done:
   if (ev) cudaEventDestroy(ev);
   if (rc != SLAMB200_OK) {
@@ -295,12 +348,17 @@ done:
 
 extern "C" int slamb200_upload_desc(slamb200_ctx* c, int kind, const void* rows, int n,
                                     size_t row_stride, slamb200_desc** out) {
-  return desc_create(c, kind, rows, n, row_stride, false, nullptr, out);
+  return desc_create(c, kind, rows, n, row_stride, false, nullptr, false, out);
+}
+
+extern "C" int slamb200_upload_desc_pinned(slamb200_ctx* c, int kind, const void* rows, int n,
+                                           size_t row_stride, slamb200_desc** out) {
+  return desc_create(c, kind, rows, n, row_stride, false, nullptr, true, out);
 }
 
 extern "C" int slamb200_upload_desc_device(slamb200_ctx* c, int kind, const void* rows, int n,
                                            size_t row_stride, void* stream, slamb200_desc** out) {
-  return desc_create(c, kind, rows, n, row_stride, true, (cudaStream_t)stream, out);
+  return desc_create(c, kind, rows, n, row_stride, true, (cudaStream_t)stream, false, out);
 }
 
 extern "C" int slamb200_free_desc(slamb200_ctx* c, slamb200_desc* d) {
@@ -406,24 +464,27 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   for (int p = 0; p < n_pairs; p++) CU(cudaStreamWaitEvent(s, trains[p]->ready, 0));
 
   if (orb) {
+    ProfScope ps(c, s, SLAMB200_K_ORB);
     launch_orb_knn2(q->u8, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split, (uint4*)L.part.p, s);
   } else {
     // General-float pairs: exact fp32 kernel (it skips exact-mode pairs unless force).  Exact-mode
     // pairs (integer-valued descriptors, what cv::SIFT emits): tcgen05 candidates + dp4a rerank
     // (those kernels skip the general-float pairs).  Both read the flags on the device, so no
     // host synchronisation is needed to pick the path.
-    launch_sift_exact_knn2(q->f32, q->flags, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split,
-                           (uint4*)L.part.p, c->use_tc ? 0 : 1, s);
+    {
+      ProfScope ps(c, s, SLAMB200_K_SIFT_EXACT);
+      launch_sift_exact_knn2(q->f32, q->flags, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split,
+                             (uint4*)L.part.p, c->use_tc ? 0 : 1, s);
+    }
     if (c->use_tc && nq > 0) {
-      const int n_rb = (nq + 127) / 128;
+      const int n_rb = (nq + 255) / 256;  // one query block per CTA pair
       if ((rc = stage_reserve(L, (sizeof(TcPair) + sizeof(int32_t)) * (size_t)(n_pairs + 1)))) return rc;
       TcPair* tp = (TcPair*)L.h_stage;
       int32_t* pre = (int32_t*)(tp + n_pairs);
       int n_cb_max = 1;
       long long total = 0;
       for (int p = 0; p < n_pairs; p++) {
-        tp[p].tmap_main = trains[p]->d_tmap;
-        tp[p].t_aug = (const uint8_t*)trains[p]->augt;
+        tp[p].tmap_main = (const char*)trains[p]->d_tmap + 256;  // {main, aug (train role)}
         tp[p].t_u8 = trains[p]->u8;
         tp[p].t_nrm2 = trains[p]->nrm2;
         tp[p].t_flags = trains[p]->flags;
@@ -436,9 +497,10 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       }
       pre[n_pairs] = (int32_t)total;
       if (total > 0x7fffffffLL) return fail(SLAMB200_ERR_INVALID, "batch too large (tile count)");
-      const int n_cta = total < c->n_sm ? (int)total : c->n_sm;
+      const int max_pairs = c->n_sm / 2;  // one CTA pair per two SMs
+      const int n_cta = total < max_pairs ? (int)total : max_pairs;
       const int n_slots = tc_slots(n_cb_max, (int)total, n_cta > 0 ? n_cta : 1);
-      const size_t cand_bytes = sizeof(uint4) * (size_t)n_pairs * n_slots * (size_t)n_rb * 128;
+      const size_t cand_bytes = sizeof(uint4) * (size_t)n_pairs * n_slots * (size_t)n_rb * 256;
       if ((rc = buf_reserve(c, L.tcpairs, sizeof(TcPair) * (size_t)n_pairs, s))) return rc;
       if ((rc = buf_reserve(c, L.tile_prefix, sizeof(int32_t) * (size_t)(n_pairs + 1), s))) return rc;
       if ((rc = buf_reserve(c, L.cand, cand_bytes, s))) return rc;
@@ -446,11 +508,16 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       CU(cudaMemcpyAsync(L.tile_prefix.p, pre, sizeof(int32_t) * (size_t)(n_pairs + 1), cudaMemcpyHostToDevice, s));
       CU(cudaEventRecord(L.stage_free, s));
       CU(cudaMemsetAsync(L.cand.p, 0xFF, cand_bytes, s));
-      if (launch_sift_tc(q->d_tmap, (const uint8_t*)q->augq, q->flags, q->u8, q->nrm2, nq,
-                         (const TcPair*)L.tcpairs.p, (const int32_t*)L.tile_prefix.p, n_pairs,
-                         (int)total, n_cta, n_slots, n_split, (uint4*)L.cand.p, (uint4*)L.part.p,
-                         (int32_t*)L.err_flag.p, L.dbg, s) != 0)
-        return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
+      int trc;
+      {
+        ProfScope ps(c, s, SLAMB200_K_SIFT_TC);
+        trc = launch_sift_tc_candidates(q->d_tmap, q->flags, nq, (const TcPair*)L.tcpairs.p,
+                                        (const int32_t*)L.tile_prefix.p, n_pairs, (int)total, n_cta,
+                                        n_slots, (uint4*)L.cand.p, (int32_t*)L.err_flag.p, L.dbg, s);
+      }
+      if (trc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
+      launch_sift_rerank(q->flags, q->u8, q->nrm2, nq, (const TcPair*)L.tcpairs.p, n_pairs, n_slots,
+                         n_split, (const uint4*)L.cand.p, (uint4*)L.part.p, (int32_t*)L.err_flag.p, s);
     }
   }
   CU(cudaGetLastError());
@@ -630,8 +697,11 @@ extern "C" int slamb200_score_essential_batch(slamb200_ctx* c, int P, const floa
   CU(cudaMemcpyAsync(L.m_off.p, m_off, sizeof(int32_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, s));
   if (H > 0) CU(cudaMemcpyAsync(L.E.p, E, sizeof(double) * 9 * (size_t)P * H, cudaMemcpyHostToDevice, s));
   launch_normalize_points((const float2*)L.p1.p, (const float2*)L.p2.p, total, sp, (double4*)L.npts.p, s);
-  launch_score_counts((const double4*)L.npts.p, (const int32_t*)L.m_off.p, nullptr, 0,
-                      (const double*)L.E.p, H, P, sp, (int32_t*)L.counts.p, s);
+  {
+    ProfScope ps(c, s, SLAMB200_K_RANSAC);
+    launch_score_counts((const double4*)L.npts.p, (const int32_t*)L.m_off.p, nullptr, 0,
+                        (const double*)L.E.p, H, P, sp, (int32_t*)L.counts.p, s);
+  }
   launch_score_best((const int32_t*)L.counts.p, H, P, (int32_t*)L.best.p, s);
   if (best_mask)
     launch_score_mask((const double4*)L.npts.p, (const int32_t*)L.m_off.p, nullptr, 0,
@@ -733,23 +803,37 @@ extern "C" int slamb200_score_batch_enqueue(slamb200_ctx* c, const slamb200_pts*
   if (P <= 0) return fail(SLAMB200_ERR_INVALID, "no batch has been enqueued on this context");
   if (!query_pts || !train_pts) return fail(SLAMB200_ERR_INVALID, "NULL keypoint sets");
   if (query_pts->n < L.b_nq) return fail(SLAMB200_ERR_INVALID, "query keypoints < query rows");
-  // E and the train keypoint pointer table go through the pinned staging area
+  // E (unless it is already resident on this device) and the train keypoint pointer table go
+  // through the pinned staging area
   const size_t e_bytes = sizeof(double) * 9 * (size_t)P * H;
   const size_t tab_bytes = sizeof(void*) * (size_t)P;
-  if ((rc = stage_reserve(L, e_bytes + tab_bytes))) return rc;
-  memcpy(L.h_stage, E, e_bytes);
-  const float2** tab = (const float2**)((char*)L.h_stage + e_bytes);
+  bool e_on_device = false;
+  {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, E) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
+        pa.device == c->device)
+      e_on_device = true;
+    cudaGetLastError();
+  }
+  if ((rc = stage_reserve(L, (e_on_device ? 0 : e_bytes) + tab_bytes))) return rc;
+  const size_t tab_off = e_on_device ? 0 : e_bytes;
+  if (!e_on_device) memcpy(L.h_stage, E, e_bytes);
+  const float2** tab = (const float2**)((char*)L.h_stage + tab_off);
   for (int p = 0; p < P; p++) {
     if (!train_pts[p]) return fail(SLAMB200_ERR_INVALID, "train keypoint set %d is NULL", p);
     tab[p] = train_pts[p]->xy;
   }
-  if ((rc = buf_reserve(c, L.E, e_bytes, s))) return rc;
+  const double* E_dev = E;
+  if (!e_on_device) {
+    if ((rc = buf_reserve(c, L.E, e_bytes, s))) return rc;
+    E_dev = (const double*)L.E.p;
+  }
   if ((rc = buf_reserve(c, L.txy, tab_bytes, s))) return rc;
   if ((rc = buf_reserve(c, L.npts, (size_t)P * cap * 32, s))) return rc;
   if ((rc = buf_reserve(c, L.counts, sizeof(int32_t) * (size_t)P * H, s))) return rc;
   if ((rc = buf_reserve(c, L.best, sizeof(int32_t) * (size_t)P, s))) return rc;
   if ((rc = buf_reserve(c, L.mask, (size_t)P * cap, s))) return rc;
-  CU(cudaMemcpyAsync(L.E.p, L.h_stage, e_bytes, cudaMemcpyHostToDevice, s));
+  if (!e_on_device) CU(cudaMemcpyAsync(L.E.p, L.h_stage, e_bytes, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(L.txy.p, tab, tab_bytes, cudaMemcpyHostToDevice, s));
   CU(cudaEventRecord(L.stage_free, s));
   CU(cudaStreamWaitEvent(s, query_pts->ready, 0));
@@ -757,11 +841,14 @@ extern "C" int slamb200_score_batch_enqueue(slamb200_ctx* c, const slamb200_pts*
   launch_gather_normalize(query_pts->xy, (const float2* const*)L.txy.p,
                           (const slamb200_dmatch*)L.out.p, cap, (const int32_t*)L.n_out.p, P, sp,
                           (double4*)L.npts.p, s);
-  launch_score_counts((const double4*)L.npts.p, nullptr, (const int32_t*)L.n_out.p, cap,
-                      (const double*)L.E.p, H, P, sp, (int32_t*)L.counts.p, s);
+  {
+    ProfScope ps(c, s, SLAMB200_K_RANSAC);
+    launch_score_counts((const double4*)L.npts.p, nullptr, (const int32_t*)L.n_out.p, cap, E_dev, H,
+                        P, sp, (int32_t*)L.counts.p, s);
+  }
   launch_score_best((const int32_t*)L.counts.p, H, P, (int32_t*)L.best.p, s);
-  launch_score_mask((const double4*)L.npts.p, nullptr, (const int32_t*)L.n_out.p, cap,
-                    (const double*)L.E.p, H, P, (const int32_t*)L.best.p, sp, (uint8_t*)L.mask.p, s);
+  launch_score_mask((const double4*)L.npts.p, nullptr, (const int32_t*)L.n_out.p, cap, E_dev, H, P,
+                    (const int32_t*)L.best.p, sp, (uint8_t*)L.mask.p, s);
   CU(cudaGetLastError());
   L.s_H = H;
   L.s_pairs = P;
@@ -794,7 +881,7 @@ extern "C" int slamb200_dbg_set_tc(slamb200_ctx* c, int on) {
   return SLAMB200_OK;
 }
 
-// Raw fp32 accumulators (d^2/2) of the first 128 x 256 tile of (query, train): out[128*256].
+// Raw fp32 accumulators (d^2/2) of the first 256 x 256 tile of (query, train): out[256*256].
 extern "C" int slamb200_dbg_tc_tile(slamb200_ctx* c, const slamb200_desc* q, const slamb200_desc* t,
                                     float* out) {
   if (!c || !q || !t || !out) return SLAMB200_ERR_INVALID;
@@ -802,15 +889,15 @@ extern "C" int slamb200_dbg_tc_tile(slamb200_ctx* c, const slamb200_desc* q, con
   LaneGuard g(c);
   Lane& L = g.lane();
   float* d = nullptr;
-  int rc = dev_alloc(c, (void**)&d, 128 * 256 * 4, L.stream);
+  int rc = dev_alloc(c, (void**)&d, 256 * 256 * 4, L.stream);
   if (rc) return rc;
-  CU(cudaMemsetAsync(d, 0, 128 * 256 * 4, L.stream));
+  CU(cudaMemsetAsync(d, 0, 256 * 256 * 4, L.stream));
   L.dbg = d;
   const slamb200_desc* tt[1] = {t};
   rc = enqueue_batch(c, L, L.stream, SLAMB200_SIFT_BF, q, tt, 1, 0.7);
   L.dbg = nullptr;
   if (rc == SLAMB200_OK) {
-    cudaError_t e = cudaMemcpyAsync(out, d, 128 * 256 * 4, cudaMemcpyDeviceToHost, L.stream);
+    cudaError_t e = cudaMemcpyAsync(out, d, 256 * 256 * 4, cudaMemcpyDeviceToHost, L.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
     if (e != cudaSuccess) rc = fail(SLAMB200_ERR_CUDA, "dbg_tc_tile: %s", cudaGetErrorString(e));
   }

@@ -36,7 +36,7 @@ struct slamb200_desc {
   int32_t* flags;      // device
   int host_exact;      // -2 unknown, else 1 when flags[0] == 0
   cudaEvent_t ready;   // recorded after the prep kernels
-  void* d_tmap;        // device copy of the CUtensorMap (128 B) over bf16: box 64 x 128, SW128
+  void* d_tmap;        // device copy of 4 CUtensorMaps (512 B): {main, augq, main, augt}
 };
 
 struct slamb200_pts {
@@ -99,22 +99,24 @@ void launch_sift_prep(const float* src, size_t src_stride_floats, int n, int n_p
 
 // SIFT tcgen05 candidate kernel + dp4a rerank (sift_tc.cu).
 struct TcPair {
-  const void* tmap_main;   // the train frame's CUtensorMap, resident in device memory
-  const uint8_t* t_aug;    // train-role K-augmentation block (interleaved core-matrix layout)
+  const void* tmap_main;   // the train frame's CUtensorMaps {main, aug (train role)} in HBM
   const uint8_t* t_u8;
   const int32_t* t_nrm2;
   const int32_t* t_flags;
   int t_n;
   int t_pad;
 };
-int tc_encode_tmap(const void* bf16_dev, int n_pad, void* host_out_128B);
+int tc_encode_tmaps(const void* bf16_dev, const void* augq_dev, const void* augt_dev, int n_pad,
+                    void* host_out_512B);
 size_t tc_smem_bytes();
 int tc_slots(int n_cb_max, int total_tiles, int n_cta);
-int launch_sift_tc(const void* q_tmap_dev, const uint8_t* q_aug, const int32_t* q_flags,
-                   const uint8_t* q_u8, const int32_t* q_nrm2, int nq, const TcPair* pairs_dev,
-                   const int32_t* tile_prefix_dev, int n_pairs, int total_tiles, int n_cta,
-                   int n_slots, int n_split, uint4* cand, uint4* part, int32_t* err_flag,
-                   float* dbg, cudaStream_t s);
+int launch_sift_tc_candidates(const void* q_tmaps_dev, const int32_t* q_flags, int nq,
+                              const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                              int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
+                              int32_t* err_flag, float* dbg, cudaStream_t s);
+void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
+                        const TcPair* pairs_dev, int n_pairs, int n_slots, int n_split,
+                        const uint4* cand, uint4* part, int32_t* err_flag, cudaStream_t s);
 
 int64_t* launch_counter();
 #define COUNT_LAUNCH() (++(*launch_counter()))

@@ -7,13 +7,20 @@
 // holds every value exactly and every partial sum stays below 2^24, so the fp32 accumulators in
 // TMEM are exact and the contraction itself yields d^2/2:
 //
-//     acc(q,t) = -(q . t)                       8 x tcgen05.mma 128x256x16, A negated
+//     acc(q,t) = -(q . t)                       8 x tcgen05.mma 256x256x16, A negated
 //              + (|q|^2/2) * 1 + 1 * (|t|^2/2)  1 x tcgen05.mma on the 16-column K augmentation
 //
-// One persistent CTA per SM walks a contiguous range of 128 x 256 tiles (pair-major, then query
-// block, then train tile).  Warp roles: warp 0 = TMA producer (query block resident per
-// segment, train tiles double-buffered), warp 1 = MMA issuer (one elected thread, accumulators
-// double-buffered in the 512 TMEM columns), warp 2 = TMEM allocator, warps 4..11 = epilogue.
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): a pair owns a 256 x 256 tile -- each CTA holds
+// 128 query rows (its half of M, accumulated in its own TMEM) and loads 128 of the tile's 256
+// train rows (its half of N), so every CTA streams only half of each train tile from L2 and the
+// tensor core reads 64 B/clk of shared memory per SM instead of 96 (a single-CTA 128 x 256 MMA
+// is shared-memory-bandwidth bound at ~66 % of the tensor rate; measured).  One persistent pair
+// per two SMs walks a contiguous range of tiles (pair-major, then query block, then train tile).
+// Warp roles per CTA: warp 0 = TMA producer (query block resident per segment in 2 stages, train
+// half-tiles in a 4-stage ring; both CTAs signal the leader's "full" barriers), warp 1 = MMA
+// issuer (leader CTA only, one elected thread; accumulators double-buffered in the 512 TMEM
+// columns; completion multicast to both CTAs with tcgen05.commit), warp 2 = TMEM allocator,
+// warps 4..11 = epilogue.
 //
 // Epilogue: a thread owns one query row (TMEM lane) and half of the tile's columns.  Per 32-column
 // tcgen05.ld it reduces four groups of 8 columns with 3-input FMNMX trees and only when some
@@ -31,36 +38,36 @@
 
 namespace {
 
-constexpr int BM = 128;             // query rows per tile (TMEM lanes)
+constexpr int BM = 128;             // query rows per CTA (TMEM lanes); the CTA pair covers 256
 constexpr int BN = 256;             // train rows per tile (TMEM columns per accumulator stage)
-constexpr int A_KBLK = BM * 128;    // bytes of one 64-wide bf16 k-block of the query tile
-constexpr int B_KBLK = BN * 128;
-constexpr int A_AUG_OFF = 2 * A_KBLK;
-constexpr int B_AUG_OFF = 2 * B_KBLK;
-constexpr int A_STAGE = 2 * A_KBLK + BM * 32;  // 36864
-constexpr int B_STAGE = 2 * B_KBLK + BN * 32;  // 73728
+constexpr int BNH = 128;            // train rows each CTA of the pair loads
+constexpr int KBLK = 128 * 128;     // bytes of one 64-wide bf16 k-block of 128 rows
+constexpr int AUG_OFF = 2 * KBLK;   // K-augmentation block behind the two k-blocks
+constexpr int STAGE = 2 * KBLK + 128 * 32;  // 36864: one 128-row operand stage (A or B half)
 constexpr int N_ASTAGE = 2;
-constexpr int N_BSTAGE = 2;
+constexpr int N_BSTAGE = 4;
 constexpr int SMEM_BARS = 1024;
-constexpr int SMEM_BYTES = N_ASTAGE * A_STAGE + N_BSTAGE * B_STAGE + SMEM_BARS + 1024;
+constexpr int SMEM_BYTES = (N_ASTAGE + N_BSTAGE) * STAGE + SMEM_BARS + 1024;
 constexpr int TC_THREADS = 384;     // 12 warps
 constexpr int EPI_WARP0 = 4;
+constexpr int N_EPI_WARPS = 8;
 constexpr int GROUP = 8;            // columns per candidate group
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared address
 
 struct TcParams {
-  const CUtensorMap* q_tmap;   // query main map (device memory)
-  const uint8_t* q_aug;        // query aug block, interleaved layout
+  const CUtensorMap* q_tmap;   // query maps (device memory): [0] main, [1] aug (query role)
   const TcPair* pairs;         // per pair: train maps / aug / sizes
   const int32_t* tile_prefix;  // [P+1] tiles before pair p
   const int32_t* q_flags;
   int n_pairs;
-  int n_rb;                    // query row blocks
+  int n_rb;                    // query row blocks of 256 rows (one per CTA pair)
   int total_tiles;
   int n_slots;                 // candidate slots per (pair, row) = 2 * max segments per row block
-  int nq_pad;                  // n_rb * 128
+  int nq_pad;                  // n_rb * 256
   uint4* cand;                 // [pair][slot][nq_pad]
-  float* dbg;                  // optional raw accumulator dump of the CTA-0 first tile
+  float* dbg;                  // optional raw accumulator dump of pair 0's first tile [256][256]
   int32_t* err_flag;
+  int mode;                    // 0 = product; 1..3 = timing experiments (results invalid)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -103,19 +110,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// 2-CTA TMA load: lands in this CTA's shared memory, signals the LEADER CTA's mbarrier.
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes,
-                                             uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(dst), "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -124,8 +140,11 @@ __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
+  // completion of all prior MMAs of this thread -> arrive on `bar` in both CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+          "r"(bar), "h"((uint16_t)3)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                        uint32_t idesc, uint32_t accumulate) {
@@ -133,7 +152,7 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -182,18 +201,27 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_neg) {
 struct TileIter {
   int pair, rb, cb, n_cb;
   int tile, end;
+  // per-pair context, reloaded only when the walk enters a new pair (never per tile)
+  int prefix0;              // tiles before this pair
+  bool skip;                // general-float train set: the exact fp32 kernel owns the pair
+  const CUtensorMap* tmap;  // train maps: [0] main, [1] aug (train role)
+  __device__ void load_pair(const TcParams& P) {
+    const TcPair pr = P.pairs[pair];
+    prefix0 = P.tile_prefix[pair];
+    n_cb = (P.tile_prefix[pair + 1] - prefix0) / P.n_rb;
+    skip = pr.t_flags[0] != 0;
+    tmap = reinterpret_cast<const CUtensorMap*>(pr.tmap_main);
+  }
   __device__ void init(const TcParams& P, int cta, int n_cta) {
     tile = (int)(((long long)P.total_tiles * cta) / n_cta);
     end = (int)(((long long)P.total_tiles * (cta + 1)) / n_cta);
-    pair = 0;
+    pair = 0; n_cb = 1; rb = 0; cb = 0; prefix0 = 0; skip = false; tmap = nullptr;
     if (tile < end) {
       while (P.tile_prefix[pair + 1] <= tile) pair++;
-      n_cb = (P.tile_prefix[pair + 1] - P.tile_prefix[pair]) / P.n_rb;
-      const int local = tile - P.tile_prefix[pair];
+      load_pair(P);
+      const int local = tile - prefix0;
       rb = local / n_cb;
       cb = local - rb * n_cb;
-    } else {
-      n_cb = 1; rb = 0; cb = 0;
     }
   }
   __device__ bool valid() const { return tile < end; }
@@ -206,7 +234,7 @@ struct TileIter {
     if (++rb < P.n_rb) return true;
     rb = 0;
     do { pair++; } while (P.tile_prefix[pair + 1] == P.tile_prefix[pair]);
-    n_cb = (P.tile_prefix[pair + 1] - P.tile_prefix[pair]) / P.n_rb;
+    load_pair(P);
     return true;
   }
 };
@@ -274,104 +302,106 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0,
 }
 
 template <bool DBG>
-__global__ void __launch_bounds__(TC_THREADS, 1) sift_tc_kernel(const TcParams P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+sift_tc_kernel(const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for the SWIZZLE_128B atoms
+  // 1024-byte alignment for the SWIZZLE_128B atoms (same offset in both CTAs of the pair)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + N_ASTAGE * A_STAGE;
-  const uint32_t bar_base = b_base + N_BSTAGE * B_STAGE;
+  const uint32_t b_base = smem_base + N_ASTAGE * STAGE;
+  const uint32_t bar_base = b_base + N_BSTAGE * STAGE;
   // barrier slots (8 B each)
-  const uint32_t a_full = bar_base, a_empty = bar_base + 16;
-  const uint32_t b_full = bar_base + 32, b_empty = bar_base + 48;
-  const uint32_t t_full = bar_base + 64, t_empty = bar_base + 80;
-  const uint32_t tmem_slot = bar_base + 96;
+  const uint32_t a_full = bar_base, a_empty = bar_base + 16;          // 2 + 2
+  const uint32_t b_full = bar_base + 32, b_empty = bar_base + 64;     // 4 + 4
+  const uint32_t t_full = bar_base + 96, t_empty = bar_base + 112;    // 2 + 2
+  const uint32_t tmem_slot = bar_base + 128;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + N_ASTAGE * A_STAGE + N_BSTAGE * B_STAGE + 96);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (N_ASTAGE + N_BSTAGE) * STAGE + 128);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_cta = gridDim.x;
-  const int cta = blockIdx.x;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader (issues the MMAs)
+  const int n_pairs_cta = gridDim.x >> 1;        // CTA pairs in the grid
+  const int pair_id = blockIdx.x >> 1;
 
   if (P.q_flags[0] != 0) return;  // general-float query: the exact fp32 kernel owns this batch
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; s++) {
-      mbar_init(a_full + 8 * s, 1);
-      mbar_init(a_empty + 8 * s, 1);
+    for (int s = 0; s < N_ASTAGE; s++) {
+      mbar_init(a_full + 8 * s, 1);    // leader producer's arrive.expect_tx (bytes of both CTAs)
+      mbar_init(a_empty + 8 * s, 1);   // tcgen05.commit multicast
+    }
+    for (int s = 0; s < N_BSTAGE; s++) {
       mbar_init(b_full + 8 * s, 1);
       mbar_init(b_empty + 8 * s, 1);
-      mbar_init(t_full + 8 * s, 1);
-      mbar_init(t_empty + 8 * s, 8);  // one elected lane of each of the 8 epilogue warps
+    }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(t_full + 8 * s, 1);                  // tcgen05.commit multicast
+      mbar_init(t_empty + 8 * s, 2 * N_EPI_WARPS);   // epilogue warps of both CTAs (leader's copy)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                  "n"(512)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (both CTAs; each loads its own halves) =================
     if (elect_one()) {
       TileIter it;
-      it.init(P, cta, n_cta);
+      it.init(P, pair_id, n_pairs_cta);
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       bool new_seg = true;
       while (it.valid()) {
-        const TcPair pr = P.pairs[it.pair];
-        if (pr.t_flags[0] != 0) {  // general-float train set: skipped here (exact kernel)
+        if (it.skip) {  // general-float train set: skipped here (exact kernel)
           new_seg = it.next(P) || new_seg;
           continue;
         }
         if (new_seg) {
           mbar_wait(a_empty + 8 * a_stage, a_phase ^ 1);
-          const uint32_t dst = a_base + a_stage * A_STAGE;
+          const uint32_t dst = a_base + a_stage * STAGE;
           const uint32_t bar = a_full + 8 * a_stage;
-          mbar_expect_tx(bar, A_STAGE);
-          tma_load_2d(dst, P.q_tmap, bar, 0, it.rb * BM);
-          tma_load_2d(dst + A_KBLK, P.q_tmap, bar, 64, it.rb * BM);
-          bulk_load_1d(dst + A_AUG_OFF, P.q_aug + (size_t)it.rb * BM * 32, BM * 32, bar);
+          const int row0 = it.rb * 2 * BM + (int)rank * BM;
+          if (rank == 0) mbar_expect_tx(bar, 2 * STAGE);
+          tma_load_2d(dst, P.q_tmap, bar, 0, row0);
+          tma_load_2d(dst + KBLK, P.q_tmap, bar, 64, row0);
+          tma_load_2d(dst + AUG_OFF, P.q_tmap + 1, bar, 0, row0 >> 3);
           if (++a_stage == N_ASTAGE) { a_stage = 0; a_phase ^= 1; }
         }
         mbar_wait(b_empty + 8 * b_stage, b_phase ^ 1);
         {
-          const uint32_t dst = b_base + b_stage * B_STAGE;
+          const uint32_t dst = b_base + b_stage * STAGE;
           const uint32_t bar = b_full + 8 * b_stage;
-          const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(pr.tmap_main);
-          const int row0 = it.cb * BN;
-          mbar_expect_tx(bar, B_STAGE);
-          tma_load_2d(dst, tm, bar, 0, row0);
-          tma_load_2d(dst + BM * 128, tm, bar, 0, row0 + 128);
-          tma_load_2d(dst + B_KBLK, tm, bar, 64, row0);
-          tma_load_2d(dst + B_KBLK + BM * 128, tm, bar, 64, row0 + 128);
-          bulk_load_1d(dst + B_AUG_OFF, pr.t_aug + (size_t)row0 * 32, BN * 32, bar);
+          const int row0 = it.cb * BN + (int)rank * BNH;
+          if (rank == 0) mbar_expect_tx(bar, 2 * STAGE);
+          tma_load_2d(dst, it.tmap, bar, 0, row0);
+          tma_load_2d(dst + KBLK, it.tmap, bar, 64, row0);
+          tma_load_2d(dst + AUG_OFF, it.tmap + 1, bar, 0, row0 >> 3);
           if (++b_stage == N_BSTAGE) { b_stage = 0; b_phase ^= 1; }
         }
         new_seg = it.next(P);
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (elect_one()) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0 && elect_one()) {
       TileIter it;
-      it.init(P, cta, n_cta);
+      it.init(P, pair_id, n_pairs_cta);
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, t_stage = 0, t_phase = 0;
       int cur_a = 0;
       bool new_seg = true;
-      constexpr uint32_t IDESC_NEG = idesc_bf16(BM, BN, 1);
-      constexpr uint32_t IDESC_POS = idesc_bf16(BM, BN, 0);
+      constexpr uint32_t IDESC_NEG = idesc_bf16(2 * BM, BN, 1);
+      constexpr uint32_t IDESC_POS = idesc_bf16(2 * BM, BN, 0);
       while (it.valid()) {
-        const TcPair pr = P.pairs[it.pair];
-        if (pr.t_flags[0] != 0) {
+        if (it.skip) {
           new_seg = it.next(P) || new_seg;
           continue;
         }
@@ -383,17 +413,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sift_tc_kernel(const TcParams P
         mbar_wait(b_full + 8 * b_stage, b_phase);
         mbar_wait(t_empty + 8 * t_stage, t_phase ^ 1);
         tc_fence_after();
-        const uint32_t a_addr = a_base + cur_a * A_STAGE;
-        const uint32_t b_addr = b_base + b_stage * B_STAGE;
+        const uint32_t a_addr = a_base + cur_a * STAGE;
+        const uint32_t b_addr = b_base + b_stage * STAGE;
         const uint32_t d_tmem = tmem_base + t_stage * BN;
+        if (P.mode < 3) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const uint64_t ad = desc_sw128(a_addr + (k >> 2) * A_KBLK + (k & 3) * 32);
-          const uint64_t bd = desc_sw128(b_addr + (k >> 2) * B_KBLK + (k & 3) * 32);
-          tc_mma(d_tmem, ad, bd, IDESC_NEG, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 8; k++) {
+            const uint64_t ad = desc_sw128(a_addr + (k >> 2) * KBLK + (k & 3) * 32);
+            const uint64_t bd = desc_sw128(b_addr + (k >> 2) * KBLK + (k & 3) * 32);
+            tc_mma(d_tmem, ad, bd, IDESC_NEG, k > 0 ? 1u : 0u);
+          }
+          tc_mma(d_tmem, desc_interleave(a_addr + AUG_OFF), desc_interleave(b_addr + AUG_OFF),
+                 IDESC_POS, 1u);
         }
-        tc_mma(d_tmem, desc_interleave(a_addr + A_AUG_OFF), desc_interleave(b_addr + B_AUG_OFF),
-               IDESC_POS, 1u);
         tc_commit(b_empty + 8 * b_stage);
         tc_commit(t_full + 8 * t_stage);
         if (++b_stage == N_BSTAGE) { b_stage = 0; b_phase ^= 1; }
@@ -403,28 +435,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sift_tc_kernel(const TcParams P
       }
     }
   } else if (warp >= EPI_WARP0) {
-    // ================= epilogue =================
+    // ================= epilogue (both CTAs; each drains its own TMEM) =================
     const int ew = warp - EPI_WARP0;
     const int quarter = ew & 3;   // TMEM lane quarter this warp may read
     const int half = ew >> 2;     // which 128 columns of the tile
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int row_in_tile = quarter * 32 + lane;
+    const int row_in_tile = (int)rank * BM + quarter * 32 + lane;  // within the pair's 256 rows
     TileIter it;
-    it.init(P, cta, n_cta);
+    it.init(P, pair_id, n_pairs_cta);
     int t_stage = 0, t_phase = 0;
     float m1 = __int_as_float(0x7f800000), m2 = m1;
     int i1 = -1, i2 = -1;
-    int seg_pair = -1, seg_rb = 0, seg_first_tile = 0;
+    int seg_pair = -1, seg_rb = 0;
     bool new_seg = true;
-    bool first_tile_of_cta = true;
+    bool first_tile = true;
+    int seg_prefix0 = 0, seg_ncb = 1;
     while (it.valid()) {
-      const TcPair pr = P.pairs[it.pair];
-      if (pr.t_flags[0] != 0) {
+      if (it.skip) {
         new_seg = it.next(P) || new_seg;
         continue;
       }
       if (new_seg) {
-        seg_pair = it.pair; seg_rb = it.rb; seg_first_tile = it.tile;
+        seg_pair = it.pair; seg_rb = it.rb;
+        seg_prefix0 = it.prefix0; seg_ncb = it.n_cb;
         m1 = m2 = __int_as_float(0x7f800000);
         i1 = i2 = -1;
       }
@@ -432,52 +465,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sift_tc_kernel(const TcParams P
       tc_fence_after();
       const uint32_t t_addr = tmem_base + lane_addr + t_stage * BN + half * 128;
       const int gid_tile = (it.cb * BN + half * 128) / GROUP;
-      uint32_t va[32], vb[32];
-      TMEM_LD32(t_addr, va);
-      TMEM_WAIT32(va);
-      TMEM_LD32(t_addr + 32, vb);
-      if (DBG && first_tile_of_cta && cta == 0) {
+      const bool dump = DBG && first_tile && pair_id == 0;
+      uint32_t va[32] = {}, vb[32] = {};
+      if (P.mode < 2) {
+        TMEM_LD32(t_addr, va);
+        TMEM_WAIT32(va);
+        TMEM_LD32(t_addr + 32, vb);
+      }
+      if (dump) {
 #pragma unroll
         for (int j = 0; j < 32; j++)
           P.dbg[(size_t)row_in_tile * BN + half * 128 + j] = __uint_as_float(va[j]);
       }
-      process_chunk(va, gid_tile + 0, m1, i1, m2, i2);
-      TMEM_WAIT32(vb);
-      TMEM_LD32(t_addr + 64, va);
-      if (DBG && first_tile_of_cta && cta == 0) {
+      if (P.mode < 1) process_chunk(va, gid_tile + 0, m1, i1, m2, i2);
+      if (P.mode < 2) {
+        TMEM_WAIT32(vb);
+        TMEM_LD32(t_addr + 64, va);
+      }
+      if (dump) {
 #pragma unroll
         for (int j = 0; j < 32; j++)
           P.dbg[(size_t)row_in_tile * BN + half * 128 + 32 + j] = __uint_as_float(vb[j]);
       }
-      process_chunk(vb, gid_tile + 4, m1, i1, m2, i2);
-      TMEM_WAIT32(va);
-      TMEM_LD32(t_addr + 96, vb);
-      if (DBG && first_tile_of_cta && cta == 0) {
+      if (P.mode < 1) process_chunk(vb, gid_tile + 4, m1, i1, m2, i2);
+      if (P.mode < 2) {
+        TMEM_WAIT32(va);
+        TMEM_LD32(t_addr + 96, vb);
+      }
+      if (dump) {
 #pragma unroll
         for (int j = 0; j < 32; j++)
           P.dbg[(size_t)row_in_tile * BN + half * 128 + 64 + j] = __uint_as_float(va[j]);
       }
-      process_chunk(va, gid_tile + 8, m1, i1, m2, i2);
-      TMEM_WAIT32(vb);
+      if (P.mode < 1) process_chunk(va, gid_tile + 8, m1, i1, m2, i2);
+      if (P.mode < 2) { TMEM_WAIT32(vb); }
       // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+      // (the leader's barrier counts the epilogue warps of both CTAs)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty + 8 * t_stage);
-      if (DBG && first_tile_of_cta && cta == 0) {
+      if (lane == 0) mbar_arrive_cluster(t_empty + 8 * t_stage, 0);
+      if (dump) {
 #pragma unroll
         for (int j = 0; j < 32; j++)
           P.dbg[(size_t)row_in_tile * BN + half * 128 + 96 + j] = __uint_as_float(vb[j]);
       }
-      process_chunk(vb, gid_tile + 12, m1, i1, m2, i2);
-      first_tile_of_cta = false;
+      if (P.mode < 1) process_chunk(vb, gid_tile + 12, m1, i1, m2, i2);
+      first_tile = false;
       if (++t_stage == 2) { t_stage = 0; t_phase ^= 1; }
       new_seg = it.next(P);
       if (new_seg) {
         // flush this segment's per-row record
-        const int rb_first = P.tile_prefix[seg_pair] +
-                             seg_rb * ((P.tile_prefix[seg_pair + 1] - P.tile_prefix[seg_pair]) / P.n_rb);
-        int ord = cta - owner_cta(P.total_tiles, n_cta, rb_first);
-        (void)seg_first_tile;
+        const int rb_first = seg_prefix0 + seg_rb * seg_ncb;
+        int ord = pair_id - owner_cta(P.total_tiles, n_pairs_cta, rb_first);
         if (ord < 0 || 2 * ord + 1 >= P.n_slots) {
           if (lane == 0) atomicOr(P.err_flag, 2);
           ord = 0;
@@ -486,16 +525,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sift_tc_kernel(const TcParams P
         uint4 rec;
         rec.x = __float_as_uint(m1); rec.y = (uint32_t)i1;
         rec.z = __float_as_uint(m2); rec.w = (uint32_t)i2;
-        P.cand[((size_t)seg_pair * P.n_slots + slot) * P.nq_pad + seg_rb * BM + row_in_tile] = rec;
+        P.cand[((size_t)seg_pair * P.n_slots + slot) * P.nq_pad + seg_rb * 2 * BM + row_in_tile] = rec;
       }
     }
   }
 
+  // both CTAs must be done with each other's shared memory / barriers before either exits;
+  // reconverge each warp first (the elected producer / MMA lanes come back from their loops):
+  // barrier.cluster.*.aligned needs the whole warp
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512)
                  : "memory");
   }
 }
@@ -633,19 +676,43 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-// Encodes the frame's main tensor map: bf16 [n_pad][128] row-major, box 64 x 128, SWIZZLE_128B.
-int tc_encode_tmap(const void* bf16_dev, int n_pad, void* host_out_128B) {
+int g_tc_mode = 0;
+extern "C" int slamb200_dbg_set_tc_mode(int m) { g_tc_mode = m; return 0; }
+
+// Encodes a frame's tensor maps into host_out (4 x 128 B): [0] main, [1] aug (query role),
+// [2] main again, [3] aug (train role), so that `base` serves the query role and `base + 2` the
+// train role with the same {main, aug} indexing.
+//   main: bf16 [n_pad][128] row-major, box 64 x 128, SWIZZLE_128B
+//   aug : the interleaved K-augmentation block viewed as bytes [n_pad/8][256], box 256 x 16
+//         (= 128 rows, a dense 4 KB copy), no swizzle
+int tc_encode_tmaps(const void* bf16_dev, const void* augq_dev, const void* augt_dev, int n_pad,
+                    void* host_out_512B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -1;
-  cuuint64_t dims[2] = {128, (cuuint64_t)n_pad};
-  cuuint64_t strides[1] = {256};
-  cuuint32_t box[2] = {64, 128};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(reinterpret_cast<CUtensorMap*>(host_out_128B), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                  const_cast<void*>(bf16_dev), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -2;
+  CUtensorMap* out = reinterpret_cast<CUtensorMap*>(host_out_512B);
+  {
+    cuuint64_t dims[2] = {128, (cuuint64_t)n_pad};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&out[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(bf16_dev), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -2;
+    out[2] = out[0];
+  }
+  const void* aug[2] = {augq_dev, augt_dev};
+  for (int i = 0; i < 2; i++) {
+    cuuint64_t dims[2] = {256, (cuuint64_t)(n_pad / 8)};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {256, 16};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&out[1 + 2 * i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(aug[i]), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -3;
+  }
+  return 0;
 }
 
 size_t tc_smem_bytes() { return SMEM_BYTES; }
@@ -658,11 +725,10 @@ int tc_slots(int n_cb_max, int total_tiles, int n_cta) {
   return 2 * segs;
 }
 
-int launch_sift_tc(const void* q_tmap_dev, const uint8_t* q_aug, const int32_t* q_flags,
-                   const uint8_t* q_u8, const int32_t* q_nrm2, int nq, const TcPair* pairs_dev,
-                   const int32_t* tile_prefix_dev, int n_pairs, int total_tiles, int n_cta,
-                   int n_slots, int n_split, uint4* cand, uint4* part, int32_t* err_flag,
-                   float* dbg, cudaStream_t s) {
+int launch_sift_tc_candidates(const void* q_tmaps_dev, const int32_t* q_flags, int nq,
+                              const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                              int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
+                              int32_t* err_flag, float* dbg, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(sift_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -672,36 +738,39 @@ int launch_sift_tc(const void* q_tmap_dev, const uint8_t* q_aug, const int32_t* 
       return -1;
     attr_done = true;
   }
-  const int n_rb = (nq + BM - 1) / BM;
-  if (total_tiles > 0 && nq > 0) {
-    TcParams P;
-    P.q_tmap = reinterpret_cast<const CUtensorMap*>(q_tmap_dev);
-    P.q_aug = q_aug;
-    P.pairs = pairs_dev;
-    P.tile_prefix = tile_prefix_dev;
-    P.q_flags = q_flags;
-    P.n_pairs = n_pairs;
-    P.n_rb = n_rb;
-    P.total_tiles = total_tiles;
-    P.n_slots = n_slots;
-    P.nq_pad = n_rb * BM;
-    P.cand = cand;
-    P.dbg = dbg;
-    P.err_flag = err_flag;
-    if (dbg)
-      sift_tc_kernel<true><<<n_cta, TC_THREADS, SMEM_BYTES, s>>>(P);
-    else
-      sift_tc_kernel<false><<<n_cta, TC_THREADS, SMEM_BYTES, s>>>(P);
-    COUNT_LAUNCH();
-  }
-  if (nq > 0 && n_pairs > 0) {
-    RerankParams R;
-    R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
-    R.nq = nq; R.nq_pad = n_rb * BM; R.n_slots = n_slots; R.n_pairs = n_pairs; R.n_split = n_split;
-    R.part = part; R.err_flag = err_flag;
-    dim3 grid((nq + 7) / 8, n_pairs);
-    sift_rerank_kernel<<<grid, 256, 0, s>>>(R);
-    COUNT_LAUNCH();
-  }
+  if (total_tiles <= 0 || nq <= 0) return 0;
+  const int n_rb = (nq + 2 * BM - 1) / (2 * BM);
+  TcParams P;
+  P.q_tmap = reinterpret_cast<const CUtensorMap*>(q_tmaps_dev);
+  P.pairs = pairs_dev;
+  P.tile_prefix = tile_prefix_dev;
+  P.q_flags = q_flags;
+  P.n_pairs = n_pairs;
+  P.n_rb = n_rb;
+  P.total_tiles = total_tiles;
+  P.n_slots = n_slots;
+  P.nq_pad = n_rb * 2 * BM;
+  P.cand = cand;
+  P.dbg = dbg;
+  P.err_flag = err_flag;
+  P.mode = g_tc_mode;
+  if (dbg)
+    sift_tc_kernel<true><<<2 * n_cta_pairs, TC_THREADS, SMEM_BYTES, s>>>(P);
+  else
+    sift_tc_kernel<false><<<2 * n_cta_pairs, TC_THREADS, SMEM_BYTES, s>>>(P);
+  COUNT_LAUNCH();
   return 0;
+}
+
+void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
+                        const TcPair* pairs_dev, int n_pairs, int n_slots, int n_split,
+                        const uint4* cand, uint4* part, int32_t* err_flag, cudaStream_t s) {
+  if (nq <= 0 || n_pairs <= 0) return;
+  RerankParams R;
+  R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
+  R.nq = nq; R.nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM); R.n_slots = n_slots; R.n_pairs = n_pairs;
+  R.n_split = n_split; R.part = part; R.err_flag = err_flag;
+  dim3 grid((nq + 7) / 8, n_pairs);
+  sift_rerank_kernel<<<grid, 256, 0, s>>>(R);
+  COUNT_LAUNCH();
 }

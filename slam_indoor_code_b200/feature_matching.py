@@ -80,8 +80,20 @@ class Context:
     def launch_count(self):
         return int(self._lib.slamb200_launch_count(self._h))
 
+    KERNELS = ("sift_tc", "sift_exact", "orb", "ransac")
+
+    def profile_enable(self, on=True):
+        check(self._lib.slamb200_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel: (summed device ms, launches)} since the last read (synchronises)."""
+        ms = np.zeros(len(self.KERNELS), np.float64)
+        n = np.zeros(len(self.KERNELS), np.int64)
+        check(self._lib.slamb200_profile_read(self._h, ptr(ms), ptr(n)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNELS)}
+
     # -- descriptor sets ("upload once per frame") --------------------------------------------
-    def upload(self, desc, kind=None):
+    def upload(self, desc, kind=None, _pinned=False):
         """Host descriptor Mat (N x 128 float32 or N x 32 uint8, row pitch honoured) -> HBM."""
         desc = np.asarray(desc)
         if kind is None:
@@ -98,9 +110,14 @@ class Context:
             desc = np.ascontiguousarray(desc)
         stride = desc.strides[0] if desc.shape[0] > 1 else width * desc.itemsize
         h = ctypes.c_void_p()
-        check(self._lib.slamb200_upload_desc(self._h, kind, ptr(desc), desc.shape[0], stride,
-                                             ctypes.byref(h)))
+        fn = self._lib.slamb200_upload_desc_pinned if _pinned else self._lib.slamb200_upload_desc
+        check(fn(self._h, kind, ptr(desc), desc.shape[0], stride, ctypes.byref(h)))
         return DescriptorSet(self, h, desc.shape[0], kind)
+
+    def upload_pinned(self, desc, kind=None):
+        """Pipelined upload from page-locked host memory (no synchronisation; the caller keeps
+        `desc` alive and unmodified until synchronize() or until results were fetched)."""
+        return self.upload(desc, kind, _pinned=True)
 
     def upload_device(self, dev_ptr, n, kind, row_stride=0, stream=None):
         """Rows already resident on this device (raw pointer, e.g. torch.Tensor.data_ptr())."""

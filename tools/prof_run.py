@@ -1,0 +1,33 @@
+"""Short driver for ncu captures: 32 SIFT pairs (10k x 10k each) device-resident, 3 passes;
+optionally ORB / RANSAC passes."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from oracle import synth
+from slam_indoor_code_b200.feature_matching import Context, MatcherType
+from slam_indoor_code_b200 import camera_translation as ct
+which = sys.argv[1] if len(sys.argv) > 1 else "sift"
+torch.zeros(1, device="cuda")
+ctx = Context(0)
+st = torch.cuda.current_stream().cuda_stream
+if which == "sift":
+    q = synth.sift_like(10000, 3000)
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(synth.sift_train_from_query(q, 10000, 3001 + i)) for i in range(32)]
+    for _ in range(3):
+        ctx.matchBatchEnqueue(Q, Ts, MatcherType.SIFT_BF, 0.7, st)
+    torch.cuda.synchronize()
+    print("ok", [len(m) for m in ctx.batchFetch(st)[0]][:4])
+elif which == "orb":
+    q, t = synth.orb_pair(10000, 10000, 2001)
+    Q, T = ctx.upload(q), ctx.upload(t)
+    for _ in range(3):
+        ctx.matchBatchEnqueue(Q, [T] * 8, MatcherType.ORB_BF, 0.7, st)
+    torch.cuda.synchronize()
+    print("ok", len(ctx.batchFetch(st)[0][0]))
+elif which == "ransac":
+    p1, p2, R, tv = synth.two_view(5000, 5000)
+    E = synth.pose_hypotheses(2048, R, tv, 5001)
+    for _ in range(3):
+        c, b, m = ct.scoreEssentialBatch(ctx, [p1] * 16, [p2] * 16, synth.SAMSUNG_HV_4K, np.stack([E] * 16), 5.0)
+    print("ok", b[:4])

@@ -13,10 +13,10 @@ lib.slamb200_dbg_tc_tile.restype = ctypes.c_int
 q, t = synth.sift_pair(300, 700, 5)
 Q, T = ctx.upload(q), ctx.upload(t)
 print("exact", Q.exact_mode, T.exact_mode, flush=True)
-out = np.zeros((128, 256), np.float32)
+out = np.zeros((256, 256), np.float32)
 rc = lib.slamb200_dbg_tc_tile(ctx._h, Q._h, T._h, _capi.ptr(out))
 print("rc", rc, lib.slamb200_last_error(), flush=True)
-qq, tt = q[:128].astype(np.float64), t[:256].astype(np.float64)
+qq, tt = q[:256].astype(np.float64), t[:256].astype(np.float64)
 ref = ((qq ** 2).sum(1)[:, None] + (tt ** 2).sum(1)[None, :]) / 2 - qq @ tt.T
 print("max abs diff", np.abs(out - ref).max(), "n mismatched", (out != ref).sum())
 if (out != ref).any():

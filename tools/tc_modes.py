@@ -1,0 +1,21 @@
+"""Timing experiments on the tcgen05 kernel: what each role costs (results invalid for mode>0)."""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from oracle import synth
+from slam_indoor_code_b200.feature_matching import Context, MatcherType
+torch.zeros(1, device="cuda")
+ctx = Context(0); lib = ctx._lib
+st = torch.cuda.current_stream().cuda_stream
+q = synth.sift_like(10000, 3000)
+Q = ctx.upload(q)
+NP = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+Ts = [ctx.upload(synth.sift_train_from_query(q, 10000, 3001 + i)) for i in range(NP)]
+ctx.profile_enable(True)
+for mode in (0, 1, 2, 3, 0):
+    lib.slamb200_dbg_set_tc_mode(mode)
+    for _ in range(2): ctx.matchBatchEnqueue(Q, Ts, MatcherType.SIFT_BF, 0.7, st)
+    torch.cuda.synchronize(); ctx.profile_read()
+    for _ in range(10): ctx.matchBatchEnqueue(Q, Ts, MatcherType.SIFT_BF, 0.7, st)
+    ms, n = ctx.profile_read()["sift_tc"]
+    print(f"mode {mode}: tc kernel {ms/n*1e3/NP:.2f} us/pair  {NP*25.6e9/(ms/n)/1e9:.0f} TFLOP/s", flush=True)
