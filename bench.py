@@ -307,16 +307,35 @@ def run_b200(args, rank, world, local):
     h2d = (len(trains) + 1) * N_ROWS * 512
     d2h = 0
 
+    # The reference walks the window from `threadsCount` host threads that share the query
+    # descriptor (batch.cpp:181-201); the C ABI is re-entrant the same way.  Three host threads
+    # each take chunks of the window: upload the chunk's train Mats (page-locked host memory,
+    # read by the prep kernel straight over PCIe), match the chunk, copy its match lists back --
+    # so one thread's matching overlaps the other threads' uploads.
+    from concurrent.futures import ThreadPoolExecutor
+    from slam_indoor_code_b200._capi import DMATCH
+    n_workers, chunk = 3, 24
+    chunks = [list(range(i, min(i + chunk, len(trains)))) for i in range(0, len(trains), chunk)]
+    out_buf = np.empty((max(len(trains), 1), N_ROWS), DMATCH)      # caller-owned, reused per step
+    n_buf = np.zeros(max(len(trains), 1), np.int32)
+    pool = ThreadPoolExecutor(n_workers)
+
+    def e2e_chunk(Qe, ids):
+        Te = [ctx.upload_pinned(trains[i]) for i in ids]
+        r = ctx.matchBatch(Qe, Te, MatcherType.SIFT_BF, RATIO, out=out_buf[ids[0]: ids[-1] + 1],
+                           n_out=n_buf[ids[0]: ids[-1] + 1])
+        for t in Te:
+            t.free()
+        return r
+
     def e2e_step():
         nonlocal d2h
         Qe = ctx.upload_pinned(q)
-        Te = [ctx.upload_pinned(t) for t in trains]
-        res = ctx.matchBatch(Qe, Te, MatcherType.SIFT_BF, RATIO)
-        mx = max([len(r) for r in res] + [0])
-        d2h = len(res) * 4 + len(res) * mx * 16
-        for t in Te:
-            t.free()
+        res = []
+        for r in pool.map(lambda ids: e2e_chunk(Qe, ids), chunks):
+            res.extend(r)
         Qe.free()
+        d2h = len(res) * 4 + sum(len(r) for r in res) * 16
         return res
 
     res = matches
@@ -325,7 +344,9 @@ def run_b200(args, rank, world, local):
     barrier()
     te0 = time.perf_counter()
     for _ in range(e2e_steps):
+        ts0 = time.perf_counter()
         res = e2e_step()
+        log(f"[rank {rank}] e2e step {1e3 * (time.perf_counter() - ts0):.1f} ms")
     barrier()
     te = torch.tensor([max(time.perf_counter() - te0, 1e-9)], device=dev, dtype=torch.float64)
     io = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)

@@ -55,7 +55,10 @@ struct Lane {
   void* h_stage = nullptr;
   size_t h_stage_cap = 0;
   cudaEvent_t stage_free = nullptr;  // recorded after the last async copy out of h_stage
+  cudaEvent_t done = nullptr;        // recorded after the last work queued through this lane
   int32_t* h_small = nullptr;        // pinned, N_SMALL ints (counts read-back)
+  void* h_out = nullptr;             // pinned staging for the match lists on their way out
+  size_t h_out_cap = 0;
   // state of the last enqueued batch
   int b_matcher = -1, b_nq = 0, b_pairs = 0, b_cap = 0;
   int s_H = 0, s_pairs = 0;
@@ -78,7 +81,10 @@ struct slamb200_ctx {
   std::condition_variable cv;
   Lane lanes[N_LANES];  // lane 0 is the batch (enqueue/fetch) lane
   std::mutex batch_mu;
+  std::mutex free_mu;
   int n_sm = 148;
+  int next_lane = 0;
+  cudaStream_t free_stream = nullptr;  // frees are stream-ordered here behind every lane's work
   int use_tc = 1;  // debug switch (slamb200_dbg_set_tc): 0 routes exact-mode pairs to the fp32 kernel
 };
 
@@ -119,11 +125,15 @@ struct LaneGuard {
   LaneGuard(slamb200_ctx* c_) : c(c_), idx(-1) {
     std::unique_lock<std::mutex> lk(c->mu);
     for (;;) {
-      for (int i = 1; i < N_LANES; i++)
+      // round-robin over the worker lanes so that back-to-back uploads land on different streams
+      for (int k = 1; k < N_LANES; k++) {
+        const int i = 1 + (c->next_lane + k - 1) % (N_LANES - 1);
         if (!c->lanes[i].busy) { idx = i; break; }
+      }
       if (idx >= 0) break;
       c->cv.wait(lk);
     }
+    c->next_lane = idx;
     c->lanes[idx].busy = true;
   }
   ~LaneGuard() {
@@ -173,8 +183,10 @@ extern "C" int slamb200_init(int device, slamb200_ctx** out) {
   for (int i = 0; i < N_LANES; i++) {
     CU(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->lanes[i].stage_free, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->lanes[i].done, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&c->lanes[i].h_small, sizeof(int32_t) * N_SMALL));
   }
+  CU(cudaStreamCreateWithFlags(&c->free_stream, cudaStreamNonBlocking));
   *out = c;
   return SLAMB200_OK;
 }
@@ -183,6 +195,7 @@ extern "C" int slamb200_synchronize(slamb200_ctx* c) {
   if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
   CU(cudaSetDevice(c->device));
   for (int i = 0; i < N_LANES; i++) CU(cudaStreamSynchronize(c->lanes[i].stream));
+  CU(cudaStreamSynchronize(c->free_stream));
   return SLAMB200_OK;
 }
 
@@ -200,9 +213,12 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
     cudaStreamSynchronize(L.stream);
     if (L.h_stage) cudaFreeHost(L.h_stage);
     if (L.h_small) cudaFreeHost(L.h_small);
+    if (L.h_out) cudaFreeHost(L.h_out);
     if (L.stage_free) cudaEventDestroy(L.stage_free);
+    if (L.done) cudaEventDestroy(L.done);
     cudaStreamDestroy(L.stream);
   }
+  if (c->free_stream) cudaStreamDestroy(c->free_stream);
   if (c->pool) cudaMemPoolDestroy(c->pool);
   delete c;
   return SLAMB200_OK;
@@ -268,8 +284,10 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   if (row_stride < row_bytes || (kind == SLAMB200_DESC_F32X128 && (row_stride % 16)))
     return fail(SLAMB200_ERR_INVALID, "upload_desc: row_stride %zu unsupported", row_stride);
   CU(cudaSetDevice(c->device));
-  slamb200_desc* d = (slamb200_desc*)calloc(1, sizeof(slamb200_desc));
+  slamb200_desc* d =
+      (slamb200_desc*)aligned_alloc(64, (sizeof(slamb200_desc) + 63) / 64 * 64);  // CUtensorMap: 64 B
   if (!d) return fail(SLAMB200_ERR_NOMEM, "host allocation failed");
+  memset(d, 0, sizeof(slamb200_desc));
   d->kind = kind;
   d->n = n;
   d->n_pad = round_up(n > 0 ? n : 1, SLAMB200_TILE_PAD);
@@ -294,46 +312,63 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   }
   DCU(cudaEventCreateWithFlags(&d->ready, cudaEventDisableTiming));
   if (kind == SLAMB200_DESC_U8X32) {
-    if ((rc = dev_alloc(c, (void**)&d->u8, (size_t)d->n_pad * 32, s))) goto done;
-    DCU(cudaMemsetAsync(d->u8, 0, (size_t)d->n_pad * 32, s));
-    if (n > 0)
-      DCU(cudaMemcpy2DAsync(d->u8, 32, rows, row_stride, 32, n,
-                            src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-  } else {
-    const size_t np = d->n_pad;
-    float* raw = nullptr;
-    if ((rc = dev_alloc(c, (void**)&d->f32, np * 512, s))) goto done;
-    if ((rc = dev_alloc(c, (void**)&d->bf16, np * 256, s))) goto done;
-    if ((rc = dev_alloc(c, (void**)&d->augq, np * 32, s))) goto done;
-    if ((rc = dev_alloc(c, (void**)&d->augt, np * 32, s))) goto done;
-    if ((rc = dev_alloc(c, (void**)&d->u8, np * 128, s))) goto done;
-    if ((rc = dev_alloc(c, (void**)&d->nrm2, np * 4, s))) goto done;
-    if ((rc = dev_alloc(c, (void**)&d->flags, 16, s))) goto done;
-    DCU(cudaMemsetAsync(d->flags, 0, 16, s));
-    const float* src = (const float*)rows;
-    size_t src_stride = row_stride / 4;
-    if (!src_on_device && n > 0) {
-      // stage the caller's rows in HBM once; the prep kernel removes the pitch
-      if ((rc = dev_alloc(c, (void**)&raw, (size_t)n * 512, s))) goto done;
-      DCU(cudaMemcpy2DAsync(raw, 512, rows, row_stride, 512, n, cudaMemcpyHostToDevice, s));
-      src = raw;
-      src_stride = 128;
+    if ((rc = dev_alloc(c, &d->slab, (size_t)d->n_pad * 32, s))) goto done;
+    d->u8 = (uint8_t*)d->slab;
+    if (d->n_pad > n) DCU(cudaMemsetAsync(d->u8 + (size_t)n * 32, 0, (size_t)(d->n_pad - n) * 32, s));
+    if (n > 0) {
+      const cudaMemcpyKind k = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+      if (row_stride == 32) DCU(cudaMemcpyAsync(d->u8, rows, (size_t)n * 32, k, s));
+      else DCU(cudaMemcpy2DAsync(d->u8, 32, rows, row_stride, 32, n, k, s));
     }
-    launch_sift_prep(src, src_stride, n, d->n_pad, d->f32, d->bf16, d->augq, d->augt, d->u8,
+  } else {
+    // one slab: f32 | bf16 | augq | augt | u8 | nrm2 | flags  (every part 256-byte aligned)
+    const size_t np = d->n_pad;
+    const size_t o_f32 = 0, o_bf16 = o_f32 + np * 512, o_augq = o_bf16 + np * 256,
+                 o_augt = o_augq + np * 32, o_u8 = o_augt + np * 32, o_nrm = o_u8 + np * 128,
+                 o_flags = o_nrm + np * 4, total = o_flags + 256;
+    if ((rc = dev_alloc(c, &d->slab, total, s))) goto done;
+    char* base = (char*)d->slab;
+    d->f32 = (float*)(base + o_f32);
+    d->bf16 = (__nv_bfloat16*)(base + o_bf16);
+    d->augq = (__nv_bfloat16*)(base + o_augq);
+    d->augt = (__nv_bfloat16*)(base + o_augt);
+    d->u8 = (uint8_t*)(base + o_u8);
+    d->nrm2 = (int32_t*)(base + o_nrm);
+    d->flags = (int32_t*)(base + o_flags);
+    DCU(cudaMemsetAsync(d->flags, 0, 16, s));
+    const float* prep_src = d->f32;
+    size_t prep_stride = 128;
+    if (n > 0) {
+      // Page-locked, device-mapped host rows (the pipelined upload): the prep kernel reads them
+      // straight over PCIe -- no staging copy, no per-copy setup cost, one pass over the data.
+      const void* mapped = nullptr;
+      if (!src_on_device && no_sync) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, rows) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+            pa.devicePointer != nullptr)
+          mapped = pa.devicePointer;
+        cudaGetLastError();
+      }
+      if (mapped) {
+        prep_src = (const float*)mapped;
+        prep_stride = row_stride / 4;
+      } else {
+        // the caller's rows land straight in the fp32 part (pitch removed by the copy itself)
+        const cudaMemcpyKind k = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (row_stride == 512) DCU(cudaMemcpyAsync(d->f32, rows, (size_t)n * 512, k, s));
+        else DCU(cudaMemcpy2DAsync(d->f32, 512, rows, row_stride, 512, n, k, s));
+      }
+    }
+    launch_sift_prep(prep_src, prep_stride, n, d->n_pad, d->f32, d->bf16, d->augq, d->augt, d->u8,
                      d->nrm2, d->flags, s);
     DCU(cudaGetLastError());
-    if (raw) DCU(cudaFreeAsync(raw, s));
-    {
-      alignas(64) unsigned char tm[512];
-      if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->n_pad, tm) != 0) {
-        rc = fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-        goto done;
-      }
-      if ((rc = dev_alloc(c, &d->d_tmap, 512, s))) goto done;
-      DCU(cudaMemcpyAsync(d->d_tmap, tm, 512, cudaMemcpyHostToDevice, s));
+    if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->n_pad, d->tmaps) != 0) {
+      rc = fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+      goto done;
     }
   }
   DCU(cudaEventRecord(d->ready, s));
+  DCU(cudaEventRecord(L.done, s));
   if (!src_on_device && !no_sync) DCU(cudaStreamSynchronize(s));  // the caller may reuse `rows` on return
 done:
   if (ev) cudaEventDestroy(ev);
@@ -361,16 +396,23 @@ extern "C" int slamb200_upload_desc_device(slamb200_ctx* c, int kind, const void
   return desc_create(c, kind, rows, n, row_stride, true, (cudaStream_t)stream, false, out);
 }
 
+// Orders a free behind everything the context has queued so far without blocking the host: the
+// free stream waits (on the device) for every lane's latest work, then releases the memory.
+static void free_behind_lanes(slamb200_ctx* c, void* p, cudaEvent_t ready) {
+  std::lock_guard<std::mutex> lk(c->free_mu);
+  if (ready) cudaStreamWaitEvent(c->free_stream, ready, 0);
+  for (int i = 0; i < N_LANES; i++) cudaStreamWaitEvent(c->free_stream, c->lanes[i].done, 0);
+  cudaFreeAsync(p, c->free_stream);
+}
+
 extern "C" int slamb200_free_desc(slamb200_ctx* c, slamb200_desc* d) {
   if (!d) return SLAMB200_OK;
   if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
   cudaSetDevice(c->device);
-  // work queued by this context that may still read the set must drain first
-  for (int i = 0; i < N_LANES; i++) cudaStreamSynchronize(c->lanes[i].stream);
-  cudaStream_t s = c->lanes[1].stream;
-  void* ptrs[] = {d->f32, d->bf16, d->augq, d->augt, d->u8, d->nrm2, d->flags, d->d_tmap};
-  for (void* p : ptrs)
-    if (p) cudaFreeAsync(p, s);
+  // Work this context queued that may still read the set drains first (stream-ordered, the host
+  // does not wait).  Work the caller queued on its own streams through the *_enqueue entry
+  // points must have been recorded by them (it is: every enqueue records the lane's event).
+  if (d->slab) free_behind_lanes(c, d->slab, d->ready);
   if (d->ready) cudaEventDestroy(d->ready);
   free(d);
   return SLAMB200_OK;
@@ -484,7 +526,8 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       int n_cb_max = 1;
       long long total = 0;
       for (int p = 0; p < n_pairs; p++) {
-        tp[p].tmap_main = (const char*)trains[p]->d_tmap + 256;  // {main, aug (train role)}
+        memcpy(tp[p].tmap, trains[p]->tmaps, 128);             // main
+        memcpy(tp[p].tmap + 128, trains[p]->tmaps + 256, 128);  // aug, train role
         tp[p].t_u8 = trains[p]->u8;
         tp[p].t_nrm2 = trains[p]->nrm2;
         tp[p].t_flags = trains[p]->flags;
@@ -511,7 +554,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       int trc;
       {
         ProfScope ps(c, s, SLAMB200_K_SIFT_TC);
-        trc = launch_sift_tc_candidates(q->d_tmap, q->flags, nq, (const TcPair*)L.tcpairs.p,
+        trc = launch_sift_tc_candidates(q->tmaps, q->flags, nq, (const TcPair*)L.tcpairs.p,
                                         (const int32_t*)L.tile_prefix.p, n_pairs, (int)total, n_cta,
                                         n_slots, (uint4*)L.cand.p, (int32_t*)L.err_flag.p, L.dbg, s);
       }
@@ -526,10 +569,13 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
                   (uint8_t*)L.flags.p, (int32_t*)L.chunk_cnt.p, (slamb200_dmatch*)L.out.p, cap,
                   (int32_t*)L.n_out.p, s);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(L.done, s));
   return SLAMB200_OK;
 }
 
 // Copies the last batch of lane L to the host: out = P slabs of out_cap matches, n_out[P].
+// The device->host transfer goes through the lane's page-locked staging area at full PCIe speed
+// (the caller's buffers are usually pageable: std::vector<cv::DMatch>), then a host memcpy.
 static int fetch_batch(Lane& L, cudaStream_t s, slamb200_dmatch* out, int out_cap, int* n_out) {
   const int P = L.b_pairs;
   if (P == 0) return SLAMB200_OK;
@@ -540,19 +586,33 @@ static int fetch_batch(Lane& L, cudaStream_t s, slamb200_dmatch* out, int out_ca
   }
   if (out_cap < L.b_nq) return fail(SLAMB200_ERR_INVALID, "cap %d < query rows %d", out_cap, L.b_nq);
   if (!out) return fail(SLAMB200_ERR_INVALID, "out is NULL");
-  CU(cudaMemcpyAsync(n_out, L.n_out.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
+  if (P + 1 > N_SMALL) return fail(SLAMB200_ERR_INVALID, "too many pairs in one batch");
+  CU(cudaMemcpyAsync(L.h_small + 1, L.n_out.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(L.h_small, L.err_flag.p, 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   if (L.h_small[0] != 0)
     return fail(SLAMB200_ERR_INTERNAL, "device self-check failed (flag %d): tensor-core candidates "
                 "disagree with the exact rerank", L.h_small[0]);
   int mx = 0;
-  for (int p = 0; p < P; p++) mx = n_out[p] > mx ? n_out[p] : mx;
+  for (int p = 0; p < P; p++) {
+    n_out[p] = L.h_small[1 + p];
+    mx = n_out[p] > mx ? n_out[p] : mx;
+  }
   if (mx > 0) {
-    CU(cudaMemcpy2DAsync(out, sizeof(slamb200_dmatch) * (size_t)out_cap, L.out.p,
-                         sizeof(slamb200_dmatch) * (size_t)L.b_cap, sizeof(slamb200_dmatch) * (size_t)mx,
-                         P, cudaMemcpyDeviceToHost, s));
+    const size_t row = sizeof(slamb200_dmatch) * (size_t)mx;
+    if (L.h_out_cap < row * P) {
+      if (L.h_out) CU(cudaFreeHost(L.h_out));
+      L.h_out = nullptr;
+      L.h_out_cap = 0;
+      CU(cudaMallocHost(&L.h_out, row * P * 2));
+      L.h_out_cap = row * P * 2;
+    }
+    CU(cudaMemcpy2DAsync(L.h_out, row, L.out.p, sizeof(slamb200_dmatch) * (size_t)L.b_cap, row, P,
+                         cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    for (int p = 0; p < P; p++)
+      memcpy(out + (size_t)p * out_cap, (const char*)L.h_out + row * p,
+             sizeof(slamb200_dmatch) * (size_t)n_out[p]);
   }
   return SLAMB200_OK;
 }
@@ -779,8 +839,7 @@ extern "C" int slamb200_free_pts(slamb200_ctx* c, slamb200_pts* p) {
   if (!p) return SLAMB200_OK;
   if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
   cudaSetDevice(c->device);
-  for (int i = 0; i < N_LANES; i++) cudaStreamSynchronize(c->lanes[i].stream);
-  if (p->xy) cudaFreeAsync(p->xy, c->lanes[1].stream);
+  if (p->xy) free_behind_lanes(c, p->xy, p->ready);
   if (p->ready) cudaEventDestroy(p->ready);
   free(p);
   return SLAMB200_OK;
@@ -850,6 +909,7 @@ extern "C" int slamb200_score_batch_enqueue(slamb200_ctx* c, const slamb200_pts*
   launch_score_mask((const double4*)L.npts.p, nullptr, (const int32_t*)L.n_out.p, cap, E_dev, H, P,
                     (const int32_t*)L.best.p, sp, (uint8_t*)L.mask.p, s);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(L.done, s));
   L.s_H = H;
   L.s_pairs = P;
   return SLAMB200_OK;

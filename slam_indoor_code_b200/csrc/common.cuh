@@ -36,7 +36,8 @@ struct slamb200_desc {
   int32_t* flags;      // device
   int host_exact;      // -2 unknown, else 1 when flags[0] == 0
   cudaEvent_t ready;   // recorded after the prep kernels
-  void* d_tmap;        // device copy of 4 CUtensorMaps (512 B): {main, augq, main, augt}
+  void* slab;          // the one device allocation all the pointers above live in
+  alignas(64) unsigned char tmaps[384];  // host copies of 3 CUtensorMaps: main, augq, augt
 };
 
 struct slamb200_pts {
@@ -98,8 +99,8 @@ void launch_sift_prep(const float* src, size_t src_stride_floats, int n, int n_p
                       int32_t* nrm2, int32_t* flags, cudaStream_t s);
 
 // SIFT tcgen05 candidate kernel + dp4a rerank (sift_tc.cu).
-struct TcPair {
-  const void* tmap_main;   // the train frame's CUtensorMaps {main, aug (train role)} in HBM
+struct alignas(64) TcPair {
+  unsigned char tmap[256];  // the train frame's CUtensorMaps {main, aug (train role)}, read by TMA
   const uint8_t* t_u8;
   const int32_t* t_nrm2;
   const int32_t* t_flags;
@@ -107,10 +108,10 @@ struct TcPair {
   int t_pad;
 };
 int tc_encode_tmaps(const void* bf16_dev, const void* augq_dev, const void* augt_dev, int n_pad,
-                    void* host_out_512B);
+                    void* host_out_384B);
 size_t tc_smem_bytes();
 int tc_slots(int n_cb_max, int total_tiles, int n_cta);
-int launch_sift_tc_candidates(const void* q_tmaps_dev, const int32_t* q_flags, int nq,
+int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_flags, int nq,
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
                               int32_t* err_flag, float* dbg, cudaStream_t s);

@@ -42,25 +42,32 @@ __device__ __forceinline__ void top2_insert(uint4& r, uint32_t k, uint32_t i) {
 
 __global__ void __launch_bounds__(SE_THREADS)
 sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_flags, int nq,
-                       const PairArgs* __restrict__ pairs, int n_split, uint4* __restrict__ part,
-                       int force) {
+                       const PairArgs* __restrict__ pairs, int n_split, long long n_items,
+                       uint4* __restrict__ part, int force) {
   extern __shared__ __align__(16) float smem[];
   float* sq = smem;                      // [SE_QT][SE_PITCH]
   float* st = smem + SE_QT * SE_PITCH;   // [SE_TT][SE_PITCH]
 
-  const int pair = blockIdx.z;
-  const int split = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;  // 8 warps -> query rows 2*warp, 2*warp+1
+  const int q_blocks = (nq + SE_QT - 1) / SE_QT;
+  const bool q_exact = q_flags[0] == 0;
+
+  // persistent walk over (pair, split, query block) work items: a batch whose pairs all belong
+  // to the tcgen05 path costs a few flag reads per block, not one block launch per item
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int qb = (int)(item % q_blocks);
+  const int split = (int)((item / q_blocks) % n_split);
+  const int pair = (int)(item / ((long long)q_blocks * n_split));
   const PairArgs pa = pairs[pair];
-  if (!force && q_flags[0] == 0 && pa.t_flags != nullptr && pa.t_flags[0] == 0)
-    return;  // exact-mode pair: the tcgen05 path owns it
+  if (!force && q_exact && pa.t_flags != nullptr && pa.t_flags[0] == 0)
+    continue;  // exact-mode pair: the tcgen05 path owns it
   const float* __restrict__ t = reinterpret_cast<const float*>(pa.t_rows);
   const int per = (pa.t_n + n_split - 1) / n_split;
   const int t_begin = split * per;
   const int t_end = min(pa.t_n, t_begin + per);
-  const int q_base = blockIdx.x * SE_QT;
-
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;  // 8 warps -> query rows 2*warp, 2*warp+1
+  const int q_base = qb * SE_QT;
+  __syncthreads();  // the previous item is done with the shared tiles
 
   // query tile
   for (int i = threadIdx.x; i < SE_QT * 32; i += SE_THREADS) {
@@ -146,6 +153,7 @@ sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ 
     if (lane == 0 && qrow < nq)
       part[((size_t)pair * n_split + split) * nq + qrow] = best[a];
   }
+  }  // work items
 }
 
 void launch_sift_exact_knn2(const float* q, const int32_t* q_flags, int nq, const PairArgs* pairs,
@@ -158,8 +166,9 @@ void launch_sift_exact_knn2(const float* q, const int32_t* q_flags, int nq, cons
                          (int)smem);
     attr_done = true;
   }
-  dim3 grid((nq + SE_QT - 1) / SE_QT, n_split, n_pairs);
-  sift_exact_knn2_kernel<<<grid, SE_THREADS, smem, s>>>(q, q_flags, nq, pairs, n_split, part,
-                                                        force);
+  const long long n_items = (long long)((nq + SE_QT - 1) / SE_QT) * n_split * n_pairs;
+  const int grid = (int)(n_items < 148 * 8 ? n_items : 148 * 8);
+  sift_exact_knn2_kernel<<<grid, SE_THREADS, smem, s>>>(q, q_flags, nq, pairs, n_split, n_items,
+                                                        part, force);
   COUNT_LAUNCH();
 }

@@ -24,7 +24,7 @@ sift_prep_kernel(const float* __restrict__ src, size_t src_stride, int n, int n_
   if (row >= n_pad) return;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (row < n) v = reinterpret_cast<const float4*>(src + (size_t)row * src_stride)[lane];
-  reinterpret_cast<float4*>(f32 + (size_t)row * 128)[lane] = v;
+  if (src != f32 || row >= n) reinterpret_cast<float4*>(f32 + (size_t)row * 128)[lane] = v;
   const float x[4] = {v.x, v.y, v.z, v.w};
   int bad = 0, ss = 0;
   uint32_t packed = 0;

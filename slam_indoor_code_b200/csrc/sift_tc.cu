@@ -33,6 +33,7 @@
 // tensor-core value and raises err_flag on any mismatch (never expected).
 #include <cuda.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -54,8 +55,8 @@ constexpr int N_EPI_WARPS = 8;
 constexpr int GROUP = 8;            // columns per candidate group
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared address
 
-struct TcParams {
-  const CUtensorMap* q_tmap;   // query maps (device memory): [0] main, [1] aug (query role)
+struct alignas(64) TcParams {
+  CUtensorMap q_tmap[2];       // query maps: [0] main, [1] aug (query role); __grid_constant__
   const TcPair* pairs;         // per pair: train maps / aug / sizes
   const int32_t* tile_prefix;  // [P+1] tiles before pair p
   const int32_t* q_flags;
@@ -205,12 +206,17 @@ struct TileIter {
   int prefix0;              // tiles before this pair
   bool skip;                // general-float train set: the exact fp32 kernel owns the pair
   const CUtensorMap* tmap;  // train maps: [0] main, [1] aug (train role)
+  // The pair table (and the tensor maps inside it) is rewritten by the host before every launch:
+  // make the TMA unit's descriptor reads observe those generic-proxy writes.
+  __device__ void acquire_maps() const {
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap + 1) : "memory");
+  }
   __device__ void load_pair(const TcParams& P) {
-    const TcPair pr = P.pairs[pair];
     prefix0 = P.tile_prefix[pair];
     n_cb = (P.tile_prefix[pair + 1] - prefix0) / P.n_rb;
-    skip = pr.t_flags[0] != 0;
-    tmap = reinterpret_cast<const CUtensorMap*>(pr.tmap_main);
+    skip = P.pairs[pair].t_flags[0] != 0;
+    tmap = reinterpret_cast<const CUtensorMap*>(P.pairs[pair].tmap);
   }
   __device__ void init(const TcParams& P, int cta, int n_cta) {
     tile = (int)(((long long)P.total_tiles * cta) / n_cta);
@@ -303,7 +309,7 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0,
 
 template <bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-sift_tc_kernel(const TcParams P) {
+sift_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the SWIZZLE_128B atoms (same offset in both CTAs of the pair)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -359,11 +365,16 @@ sift_tc_kernel(const TcParams P) {
       TileIter it;
       it.init(P, pair_id, n_pairs_cta);
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
+      int maps_of_pair = -1;
       bool new_seg = true;
       while (it.valid()) {
         if (it.skip) {  // general-float train set: skipped here (exact kernel)
           new_seg = it.next(P) || new_seg;
           continue;
+        }
+        if (maps_of_pair != it.pair) {
+          it.acquire_maps();
+          maps_of_pair = it.pair;
         }
         if (new_seg) {
           mbar_wait(a_empty + 8 * a_stage, a_phase ^ 1);
@@ -559,19 +570,22 @@ __device__ __forceinline__ bool lt_fi(float va, int ia, float vb, int ib) {
   return va < vb || (va == vb && ia < ib);
 }
 
+// Half a warp per query row (16 candidates = 16 lanes), two rows per warp, 16 rows per block.
 __global__ void __launch_bounds__(256) sift_rerank_kernel(const RerankParams R) {
   const int pair = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (q >= R.nq) return;
-  const TcPair pr = R.pairs[pair];
-  if (R.q_flags[0] != 0 || pr.t_flags[0] != 0) return;  // not an exact-mode pair
+  const int l = threadIdx.x & 15;
+  const int q = blockIdx.x * 16 + (threadIdx.x >> 4);
+  const TcPair* pr = R.pairs + pair;
+  if (R.q_flags[0] != 0 || pr->t_flags[0] != 0) return;  // not an exact-mode pair (block-uniform)
+  const bool row_ok = q < R.nq;
+  const int qc = row_ok ? q : R.nq - 1;
+  const int t_n = pr->t_n;
 
   // 1. best two candidate groups over all slots (each lane reads one slot record)
   float v0 = __int_as_float(0x7f800000), v1 = v0;
   int g0 = 0x7fffffff, g1 = 0x7fffffff;
-  for (int s = lane; s < R.n_slots; s += 32) {
-    const uint4 rec = R.cand[((size_t)pair * R.n_slots + s) * R.nq_pad + q];
+  for (int s = l; s < R.n_slots; s += 16) {
+    const uint4 rec = R.cand[((size_t)pair * R.n_slots + s) * R.nq_pad + qc];
     const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.z);
     const int ia = (int)rec.y, ib = (int)rec.w;
     if (ia >= 0) {
@@ -584,7 +598,7 @@ __global__ void __launch_bounds__(256) sift_rerank_kernel(const RerankParams R) 
     }
   }
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
+  for (int off = 8; off >= 1; off >>= 1) {
     const float ov0 = __shfl_xor_sync(0xffffffffu, v0, off), ov1 = __shfl_xor_sync(0xffffffffu, v1, off);
     const int og0 = __shfl_xor_sync(0xffffffffu, g0, off), og1 = __shfl_xor_sync(0xffffffffu, g1, off);
     if (lt_fi(ov0, og0, v0, g0)) {
@@ -594,19 +608,19 @@ __global__ void __launch_bounds__(256) sift_rerank_kernel(const RerankParams R) 
     } else if (!(ov0 == v0 && og0 == g0)) {
       if (lt_fi(ov0, og0, v1, g1)) { v1 = ov0; g1 = og0; }
     } else {
-      // identical best (same record seen by both): second = min of the seconds
+      // identical best (both sides empty): second = min of the seconds
       if (lt_fi(ov1, og1, v1, g1)) { v1 = ov1; g1 = og1; }
     }
   }
 
   // 2. exact integer d^2 for the 16 candidate columns: lanes 0..7 -> group g0, 8..15 -> group g1
-  const int grp = lane < 8 ? g0 : g1;
-  const bool has_grp = lane < 16 && grp != 0x7fffffff;
-  const int col = has_grp ? grp * GROUP + (lane & 7) : -1;
+  const int grp = l < 8 ? g0 : g1;
+  const bool has_grp = grp != 0x7fffffff;
+  const int col = has_grp ? grp * GROUP + (l & 7) : -1;
   uint32_t d2 = 0xFFFFFFFFu;
-  if (has_grp && col < pr.t_n) {
-    const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)q * 128);
-    const uint4* tp = reinterpret_cast<const uint4*>(pr.t_u8 + (size_t)col * 128);
+  if (has_grp && col < t_n) {
+    const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qc * 128);
+    const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)col * 128);
     uint32_t dot = 0;  // u8 x u8 products: unsigned dp4a
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -616,32 +630,33 @@ __global__ void __launch_bounds__(256) sift_rerank_kernel(const RerankParams R) 
       dot = __dp4a(a.z, b.z, dot);
       dot = __dp4a(a.w, b.w, dot);
     }
-    d2 = (uint32_t)(R.q_nrm2[q] + pr.t_nrm2[col]) - 2u * dot;
+    d2 = (uint32_t)(R.q_nrm2[qc] + pr->t_nrm2[col]) - 2u * dot;
   }
   // self check: the minimum of group g0 must equal twice the tensor-core value
   {
-    uint32_t mn = lane < 8 ? d2 : 0xFFFFFFFFu;
+    uint32_t mn = d2;
 #pragma unroll
     for (int off = 4; off >= 1; off >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-    if (lane == 0 && g0 != 0x7fffffff && mn != 0xFFFFFFFFu) {
+    if (l == 0 && row_ok && g0 != 0x7fffffff && mn != 0xFFFFFFFFu) {
       if ((float)mn != 2.0f * v0) atomicOr(R.err_flag, 1);
     }
   }
   // 3. top-2 by (d2, col) across the 16 lanes
-  unsigned long long key = d2 == 0xFFFFFFFFu ? ~0ull : (((unsigned long long)d2 << 32) | (uint32_t)col);
+  const unsigned long long key =
+      d2 == 0xFFFFFFFFu ? ~0ull : (((unsigned long long)d2 << 32) | (uint32_t)col);
   unsigned long long k0 = key;
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
+  for (int off = 8; off >= 1; off >>= 1) {
     const unsigned long long o = __shfl_xor_sync(0xffffffffu, k0, off);
     k0 = o < k0 ? o : k0;
   }
   unsigned long long k1 = key == k0 ? ~0ull : key;
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
+  for (int off = 8; off >= 1; off >>= 1) {
     const unsigned long long o = __shfl_xor_sync(0xffffffffu, k1, off);
     k1 = o < k1 ? o : k1;
   }
-  if (lane == 0) {
+  if (l == 0 && row_ok) {
     uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
     if (k0 != ~0ull) {
       rec.x = __float_as_uint(sqrtf((float)(uint32_t)(k0 >> 32)));
@@ -679,17 +694,16 @@ EncodeTiledFn get_encode_fn() {
 int g_tc_mode = 0;
 extern "C" int slamb200_dbg_set_tc_mode(int m) { g_tc_mode = m; return 0; }
 
-// Encodes a frame's tensor maps into host_out (4 x 128 B): [0] main, [1] aug (query role),
-// [2] main again, [3] aug (train role), so that `base` serves the query role and `base + 2` the
-// train role with the same {main, aug} indexing.
+// Encodes a frame's tensor maps into host_out (3 x 128 B): [0] main, [1] aug (query role),
+// [2] aug (train role).
 //   main: bf16 [n_pad][128] row-major, box 64 x 128, SWIZZLE_128B
 //   aug : the interleaved K-augmentation block viewed as bytes [n_pad/8][256], box 256 x 16
 //         (= 128 rows, a dense 4 KB copy), no swizzle
 int tc_encode_tmaps(const void* bf16_dev, const void* augq_dev, const void* augt_dev, int n_pad,
-                    void* host_out_512B) {
+                    void* host_out_384B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -1;
-  CUtensorMap* out = reinterpret_cast<CUtensorMap*>(host_out_512B);
+  CUtensorMap* out = reinterpret_cast<CUtensorMap*>(host_out_384B);
   {
     cuuint64_t dims[2] = {128, (cuuint64_t)n_pad};
     cuuint64_t strides[1] = {256};
@@ -699,7 +713,6 @@ int tc_encode_tmaps(const void* bf16_dev, const void* augq_dev, const void* augt
                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -2;
-    out[2] = out[0];
   }
   const void* aug[2] = {augq_dev, augt_dev};
   for (int i = 0; i < 2; i++) {
@@ -707,7 +720,7 @@ int tc_encode_tmaps(const void* bf16_dev, const void* augq_dev, const void* augt
     cuuint64_t strides[1] = {256};
     cuuint32_t box[2] = {256, 16};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(&out[1 + 2 * i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(aug[i]), dims,
+    CUresult r = fn(&out[1 + i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(aug[i]), dims,
                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -3;
@@ -725,7 +738,7 @@ int tc_slots(int n_cb_max, int total_tiles, int n_cta) {
   return 2 * segs;
 }
 
-int launch_sift_tc_candidates(const void* q_tmaps_dev, const int32_t* q_flags, int nq,
+int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_flags, int nq,
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
                               int32_t* err_flag, float* dbg, cudaStream_t s) {
@@ -741,7 +754,7 @@ int launch_sift_tc_candidates(const void* q_tmaps_dev, const int32_t* q_flags, i
   if (total_tiles <= 0 || nq <= 0) return 0;
   const int n_rb = (nq + 2 * BM - 1) / (2 * BM);
   TcParams P;
-  P.q_tmap = reinterpret_cast<const CUtensorMap*>(q_tmaps_dev);
+  memcpy(P.q_tmap, q_tmaps_host_256B, 256);
   P.pairs = pairs_dev;
   P.tile_prefix = tile_prefix_dev;
   P.q_flags = q_flags;
@@ -770,7 +783,7 @@ void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32
   R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
   R.nq = nq; R.nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM); R.n_slots = n_slots; R.n_pairs = n_pairs;
   R.n_split = n_split; R.part = part; R.err_flag = err_flag;
-  dim3 grid((nq + 7) / 8, n_pairs);
+  dim3 grid((nq + 15) / 16, n_pairs);
   sift_rerank_kernel<<<grid, 256, 0, s>>>(R);
   COUNT_LAUNCH();
 }

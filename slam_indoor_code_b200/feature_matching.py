@@ -155,17 +155,24 @@ class Context:
                                             ctypes.byref(n)))
         return out[: n.value].copy()
 
-    def matchBatch(self, prevDesc, trainDescs, matcherType, knnMatcherDistance=0.7):
-        """The batch window of batch.cpp:120-148 in one call: list of good-match arrays."""
+    def matchBatch(self, prevDesc, trainDescs, matcherType, knnMatcherDistance=0.7, out=None,
+                   n_out=None):
+        """The batch window of batch.cpp:120-148 in one call: list of good-match arrays.  `out`
+        ([P, rows(query)] DMATCH) and `n_out` ([P] int32) may be caller-owned buffers that are
+        reused across calls; the returned arrays are then views into `out`."""
         _kind_of(matcherType)
         P = len(trainDescs)
         cap = max(prevDesc.n, 1)
-        out = np.zeros((max(P, 1), cap), DMATCH)
-        n_out = np.zeros(max(P, 1), np.int32)
+        own = out is None
+        if own:
+            out = np.empty((max(P, 1), cap), DMATCH)
+            n_out = np.zeros(max(P, 1), np.int32)
+        assert out.shape[0] >= P and out.shape[1] >= cap and out.dtype == DMATCH
         arr = (ctypes.c_void_p * max(P, 1))(*[t._h for t in trainDescs])
         check(self._lib.slamb200_match_batch(self._h, int(matcherType), prevDesc._h, arr, P,
-                                             float(knnMatcherDistance), ptr(out), cap, ptr(n_out)))
-        return [out[p, : n_out[p]].copy() for p in range(P)]
+                                             float(knnMatcherDistance), ptr(out), out.shape[1],
+                                             ptr(n_out)))
+        return [out[p, : n_out[p]].copy() if own else out[p, : n_out[p]] for p in range(P)]
 
     def matchWindow(self, frames, matcherType, knnMatcherDistance=0.7):
         """All i<j pairs of a frame window: dict {(i, j): matches}."""
@@ -198,7 +205,7 @@ class Context:
 
     def batchFetch(self, stream=None):
         P, cap = self._last
-        out = np.zeros((max(P, 1), cap), DMATCH)
+        out = np.empty((max(P, 1), cap), DMATCH)
         n_out = np.zeros(max(P, 1), np.int32)
         check(self._lib.slamb200_batch_fetch(self._h, ptr(out), cap, ptr(n_out),
                                              ctypes.c_void_p(stream or 0)))

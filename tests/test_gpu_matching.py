@@ -308,3 +308,22 @@ def test_cfg1_float_10k_spot(ctx):
     idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, Q, T)
     rows = np.random.default_rng(3).choice(10000, 48, replace=False)
     _check_knn(idx[rows], dist[rows], *c_oracle.l2_knn2(q[rows], t))
+
+
+def test_pinned_pipelined_upload(ctx):
+    """slamb200_upload_desc_pinned: rows in page-locked host memory are read by the prep kernel
+    directly (no staging copy); results must not change, with and without a row pitch."""
+    import torch
+    q, t = synth.sift_pair(1500, 2100, 1401)
+    hq = torch.empty(q.shape, dtype=torch.float32).pin_memory()
+    hq.numpy()[...] = q
+    wide = torch.zeros((t.shape[0], 160), dtype=torch.float32).pin_memory()
+    wide.numpy()[:, :128] = t
+    Q = ctx.upload_pinned(hq.numpy())
+    T = ctx.upload_pinned(wide.numpy()[:, :128])
+    got = ctx.matchFeatures(Q, T, MatcherType.SIFT_BF, 0.7)
+    assert np.array_equal(got, c_oracle.match_features(0, q, t, 0.7))
+    # pageable memory through the same entry point falls back to a copy
+    Q2 = ctx.upload_pinned(q.copy())
+    ctx.synchronize()
+    assert np.array_equal(ctx.matchFeatures(Q2, T, MatcherType.SIFT_BF, 0.7), got)
