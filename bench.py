@@ -38,8 +38,20 @@ RATIO = 0.7
 FLOP_PER_PAIR = 2.0 * N_ROWS * N_ROWS * 128
 
 
+_REAL_STDOUT = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def dist_env():
@@ -201,7 +213,7 @@ def run_reference(args, rank, world):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(world, n_sample_note=None):
@@ -377,7 +389,7 @@ def run_b200(args, rank, world, local):
             line["cpu_baseline"] = cpu_baseline(q, trains, matches, args.cpu_seconds)
         if world == 1 and not args.no_extras:
             line["extras"] = extras(ctx, stream)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -451,6 +463,13 @@ def extras(ctx, stream):
 
 
 def main():
+    # Exactly one JSON line may reach stdout: route fd 1 to stderr for everything else (NCCL prints
+    # its version banner to stdout when NCCL_DEBUG=VERSION is set on a box) and keep the real
+    # stdout for the final line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -523,8 +523,15 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       if ((rc = stage_reserve(L, (sizeof(TcPair) + sizeof(int32_t)) * (size_t)(n_pairs + 1)))) return rc;
       TcPair* tp = (TcPair*)L.h_stage;
       int32_t* pre = (int32_t*)(tp + n_pairs);
-      int n_cb_max = 1;
       long long total = 0;
+      const int max_pairs = c->n_sm / 2;  // one CTA pair per two SMs
+      int max_tiles = 0;
+      for (int p = 0; p < n_pairs; p++) {
+        const int n_cb = (trains[p]->n + 255) / 256;
+        max_tiles = n_cb * n_rb > max_tiles ? n_cb * n_rb : max_tiles;
+      }
+      const int n_cta = max_tiles < max_pairs ? (max_tiles > 0 ? max_tiles : 1) : max_pairs;
+      int n_slots = 2;
       for (int p = 0; p < n_pairs; p++) {
         memcpy(tp[p].tmap, trains[p]->tmaps, 128);             // main
         memcpy(tp[p].tmap + 128, trains[p]->tmaps + 256, 128);  // aug, train role
@@ -534,15 +541,17 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         tp[p].t_n = trains[p]->n;
         tp[p].t_pad = trains[p]->n_pad;
         const int n_cb = (trains[p]->n + 255) / 256;
-        n_cb_max = n_cb > n_cb_max ? n_cb : n_cb_max;
         pre[p] = (int32_t)total;
         total += (long long)n_cb * n_rb;
+        // every CTA pair takes a contiguous share of this frame pair's tiles: how many shares
+        // can cut one row block of n_cb tiles
+        if (n_cb > 0) {
+          const int slots = tc_slots(n_cb, n_cb * n_rb, n_cta);
+          n_slots = slots > n_slots ? slots : n_slots;
+        }
       }
       pre[n_pairs] = (int32_t)total;
       if (total > 0x7fffffffLL) return fail(SLAMB200_ERR_INVALID, "batch too large (tile count)");
-      const int max_pairs = c->n_sm / 2;  // one CTA pair per two SMs
-      const int n_cta = total < max_pairs ? (int)total : max_pairs;
-      const int n_slots = tc_slots(n_cb_max, (int)total, n_cta > 0 ? n_cta : 1);
       const size_t cand_bytes = sizeof(uint4) * (size_t)n_pairs * n_slots * (size_t)n_rb * 256;
       if ((rc = buf_reserve(c, L.tcpairs, sizeof(TcPair) * (size_t)n_pairs, s))) return rc;
       if ((rc = buf_reserve(c, L.tile_prefix, sizeof(int32_t) * (size_t)(n_pairs + 1), s))) return rc;

@@ -199,11 +199,17 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_neg) {
 }
 
 // ---- tile walk: every role iterates the same sequence -----------------------------------------
+// Tile walk.  Every CTA pair visits every frame pair in order and takes a contiguous share of
+// THAT frame pair's tiles (row-block major): at any moment the whole grid is streaming the same
+// train set, which therefore stays L2-resident (2.9 MB) instead of every CTA pair dragging its own
+// train set through HBM; contiguous shares keep the segments (same query block) long.  The share
+// owner rotates with the frame-pair index so that rounding does not always favour the same CTAs.
 struct TileIter {
   int pair, rb, cb, n_cb;
-  int tile, end;
-  // per-pair context, reloaded only when the walk enters a new pair (never per tile)
-  int prefix0;              // tiles before this pair
+  int tile, end;            // local tile index inside the current frame pair, and the share's end
+  int slot_c;               // this CTA pair's (rotated) position for the current frame pair
+  int n_tiles;              // tiles of the current frame pair
+  int cta, n_cta;
   bool skip;                // general-float train set: the exact fp32 kernel owns the pair
   const CUtensorMap* tmap;  // train maps: [0] main, [1] aug (train role)
   // The pair table (and the tensor maps inside it) is rewritten by the host before every launch:
@@ -212,35 +218,44 @@ struct TileIter {
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap + 1) : "memory");
   }
-  __device__ void load_pair(const TcParams& P) {
-    prefix0 = P.tile_prefix[pair];
-    n_cb = (P.tile_prefix[pair + 1] - prefix0) / P.n_rb;
-    skip = P.pairs[pair].t_flags[0] != 0;
-    tmap = reinterpret_cast<const CUtensorMap*>(P.pairs[pair].tmap);
-  }
-  __device__ void init(const TcParams& P, int cta, int n_cta) {
-    tile = (int)(((long long)P.total_tiles * cta) / n_cta);
-    end = (int)(((long long)P.total_tiles * (cta + 1)) / n_cta);
-    pair = 0; n_cb = 1; rb = 0; cb = 0; prefix0 = 0; skip = false; tmap = nullptr;
-    if (tile < end) {
-      while (P.tile_prefix[pair + 1] <= tile) pair++;
-      load_pair(P);
-      const int local = tile - prefix0;
-      rb = local / n_cb;
-      cb = local - rb * n_cb;
+  // positions on the first non-empty share at or after frame pair `p`; false when none is left
+  __device__ bool seek(const TcParams& P, int p) {
+    for (; p < P.n_pairs; p++) {
+      n_tiles = P.tile_prefix[p + 1] - P.tile_prefix[p];
+      if (n_tiles == 0) continue;
+      if (P.pairs[p].t_flags[0] != 0) continue;  // general-float train set: exact kernel's
+      slot_c = (cta + p) % n_cta;
+      tile = (int)(((long long)n_tiles * slot_c) / n_cta);
+      end = (int)(((long long)n_tiles * (slot_c + 1)) / n_cta);
+      if (tile >= end) continue;
+      pair = p;
+      n_cb = n_tiles / P.n_rb;
+      rb = tile / n_cb;
+      cb = tile - rb * n_cb;
+      skip = false;
+      tmap = reinterpret_cast<const CUtensorMap*>(P.pairs[p].tmap);
+      return true;
     }
+    pair = P.n_pairs;
+    return false;
+  }
+  __device__ void init(const TcParams& P, int cta_, int n_cta_) {
+    cta = cta_; n_cta = n_cta_;
+    pair = 0; n_cb = 1; rb = 0; cb = 0; tile = 0; end = 0; slot_c = 0; n_tiles = 0;
+    skip = false; tmap = nullptr;
+    seek(P, 0);
   }
   __device__ bool valid() const { return tile < end; }
   // returns true when the next tile starts a new (pair, row block) segment
   __device__ bool next(const TcParams& P) {
     tile++;
-    if (tile >= end) return true;
+    if (tile >= end) {
+      if (!seek(P, pair + 1)) { tile = 0; end = 0; }
+      return true;
+    }
     if (++cb < n_cb) return false;
     cb = 0;
-    if (++rb < P.n_rb) return true;
-    rb = 0;
-    do { pair++; } while (P.tile_prefix[pair + 1] == P.tile_prefix[pair]);
-    load_pair(P);
+    ++rb;
     return true;
   }
 };
@@ -460,7 +475,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     int seg_pair = -1, seg_rb = 0;
     bool new_seg = true;
     bool first_tile = true;
-    int seg_prefix0 = 0, seg_ncb = 1;
+    int seg_ntiles = 1, seg_ncb = 1, seg_c = 0;
     while (it.valid()) {
       if (it.skip) {
         new_seg = it.next(P) || new_seg;
@@ -468,7 +483,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       }
       if (new_seg) {
         seg_pair = it.pair; seg_rb = it.rb;
-        seg_prefix0 = it.prefix0; seg_ncb = it.n_cb;
+        seg_ntiles = it.n_tiles; seg_ncb = it.n_cb; seg_c = it.slot_c;
         m1 = m2 = __int_as_float(0x7f800000);
         i1 = i2 = -1;
       }
@@ -526,8 +541,8 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       new_seg = it.next(P);
       if (new_seg) {
         // flush this segment's per-row record
-        const int rb_first = seg_prefix0 + seg_rb * seg_ncb;
-        int ord = pair_id - owner_cta(P.total_tiles, n_pairs_cta, rb_first);
+        // ordinal of this share among the shares that cut the row block (<= n_slots / 2)
+        int ord = seg_c - owner_cta(seg_ntiles, n_pairs_cta, seg_rb * seg_ncb);
         if (ord < 0 || 2 * ord + 1 >= P.n_slots) {
           if (lane == 0) atomicOr(P.err_flag, 2);
           ord = 0;
