@@ -300,14 +300,18 @@ def run_b200(args, rank, world, local):
     tc_ms, tc_n = prof["sift_tc"]
     roof = None
     if tc_n > 0:
-        per_launch_flop = FLOP_PER_PAIR * len(pairs)
-        achieved = per_launch_flop / (tc_ms / tc_n / 1e3) / 1e12
+        # every timed step launches the kernel over this rank's pairs (possibly in sub-batches)
+        achieved = FLOP_PER_PAIR * len(pairs) * args.steps / (tc_ms / 1e3) / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         roof = {"bound": "tensor", "kernel": "sift_tc_kernel (tcgen05 bf16 candidates)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                 "frac_of_burst": achieved / float(peaks.get("bf16_tflops", peak)),
-                "kernel_ms_per_launch": tc_ms / tc_n, "kernel_share_of_step": tc_ms / ms_total
+                "kernel_ms_per_step": tc_ms / args.steps, "kernel_launches_per_step": tc_n / args.steps,
+                "algorithmic_flop_per_step": FLOP_PER_PAIR * len(pairs),
+                "other_kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()
+                                              if k != "sift_tc" and v[1] > 0},
+                "kernel_share_of_step": tc_ms / ms_total
                 if world == 1 else None,
                 "traffic": TRAFFIC_BYTES_PER_LAUNCH}
 

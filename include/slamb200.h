@@ -177,7 +177,9 @@ int slamb200_batch_scores_fetch(slamb200_ctx* ctx, int32_t* counts, int32_t* bes
 #define SLAMB200_K_SIFT_EXACT 1 /* exact fp32 kernel (general floats) */
 #define SLAMB200_K_ORB 2        /* Hamming kernel                    */
 #define SLAMB200_K_RANSAC 3     /* Sampson counting kernel           */
-#define SLAMB200_K_COUNT 4
+#define SLAMB200_K_SIFT_RERANK 4 /* exact dp4a rerank of the candidates */
+#define SLAMB200_K_FINALIZE 5   /* ratio test + ordered compaction    */
+#define SLAMB200_K_COUNT 6
 int slamb200_profile_enable(slamb200_ctx* ctx, int on);
 /* Synchronises, then returns the summed device time (ms) and the launch count of each kernel
  * class since the last read; ms and launches have SLAMB200_K_COUNT entries. */

@@ -46,9 +46,11 @@ struct DevBuf {
 
 struct Lane {
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;      // rerank / finalize side of the sub-batch pipeline
+  std::vector<cudaEvent_t> sub_ev;
   bool busy = false;
   // matching scratch (device)
-  DevBuf pairs, tcpairs, tile_prefix, part, cand, knn_idx, knn_dist, flags, chunk_cnt, out, n_out, err_flag;
+  DevBuf pairs, tcpairs, tile_prefix, part, cand, work, work_v0, knn_idx, knn_dist, flags, chunk_cnt, out, n_out, err_flag;
   // scoring scratch (device)
   DevBuf npts, E, counts, best, mask, m_off, p1, p2, txy, all_masks;
   // pinned staging
@@ -85,6 +87,7 @@ struct slamb200_ctx {
   int n_sm = 148;
   int next_lane = 0;
   cudaStream_t free_stream = nullptr;  // frees are stream-ordered here behind every lane's work
+  int sub_batch = 0;  // debug: pairs per tcgen05 launch when pipelining against the rerank
   int use_tc = 1;  // debug switch (slamb200_dbg_set_tc): 0 routes exact-mode pairs to the fp32 kernel
 };
 
@@ -182,6 +185,7 @@ extern "C" int slamb200_init(int device, slamb200_ctx** out) {
   CU(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
   for (int i = 0; i < N_LANES; i++) {
     CU(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->lanes[i].stream2, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->lanes[i].stage_free, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->lanes[i].done, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&c->lanes[i].h_small, sizeof(int32_t) * N_SMALL));
@@ -205,7 +209,7 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
   cudaDeviceSynchronize();
   for (int i = 0; i < N_LANES; i++) {
     Lane& L = c->lanes[i];
-    DevBuf* bufs[] = {&L.pairs, &L.tcpairs, &L.tile_prefix, &L.part, &L.cand, &L.knn_idx, &L.knn_dist, &L.flags,
+    DevBuf* bufs[] = {&L.pairs, &L.tcpairs, &L.tile_prefix, &L.work, &L.work_v0, &L.part, &L.cand, &L.knn_idx, &L.knn_dist, &L.flags,
                       &L.chunk_cnt, &L.out, &L.n_out, &L.err_flag, &L.npts, &L.E, &L.counts,
                       &L.best, &L.mask, &L.m_off, &L.p1, &L.p2, &L.txy, &L.all_masks};
     for (DevBuf* b : bufs)
@@ -216,6 +220,9 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
     if (L.h_out) cudaFreeHost(L.h_out);
     if (L.stage_free) cudaEventDestroy(L.stage_free);
     if (L.done) cudaEventDestroy(L.done);
+    for (cudaEvent_t e : L.sub_ev)
+      if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(L.stream2);
     cudaStreamDestroy(L.stream);
   }
   if (c->free_stream) cudaStreamDestroy(c->free_stream);
@@ -465,7 +472,7 @@ static int check_matcher(int matcher, const slamb200_desc* q, const slamb200_des
 // L.knn_idx / L.knn_dist [P][nq][2], L.out [P][cap] dmatch, L.n_out [P].
 static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
                          const slamb200_desc* q, const slamb200_desc* const* trains, int n_pairs,
-                         double ratio) {
+                         double ratio, bool want_knn = false) {
   const int nq = q->n;
   const int cap = nq > 0 ? nq : 1;
   L.b_matcher = matcher; L.b_nq = nq; L.b_pairs = n_pairs; L.b_cap = cap;
@@ -498,8 +505,8 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   if ((rc = buf_reserve(c, L.chunk_cnt, sizeof(int32_t) * (size_t)n_pairs * (finalize_chunks(cap) + 1), s))) return rc;
   if ((rc = buf_reserve(c, L.out, sizeof(slamb200_dmatch) * rows, s))) return rc;
   if ((rc = buf_reserve(c, L.n_out, sizeof(int32_t) * (size_t)n_pairs, s))) return rc;
-  if ((rc = buf_reserve(c, L.err_flag, 16, s))) return rc;
-  CU(cudaMemsetAsync(L.err_flag.p, 0, 16, s));
+  if ((rc = buf_reserve(c, L.err_flag, 4096, s))) return rc;  // [0] self-check flag, [1+k] work counts
+  CU(cudaMemsetAsync(L.err_flag.p, 0, 4096, s));
 
   // the descriptor sets must have finished their prep kernels
   CU(cudaStreamWaitEvent(s, q->ready, 0));
@@ -513,6 +520,9 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     // pairs (integer-valued descriptors, what cv::SIFT emits): tcgen05 candidates + dp4a rerank
     // (those kernels skip the general-float pairs).  Both read the flags on the device, so no
     // host synchronisation is needed to pick the path.
+    // every (pair, split, row) record starts "absent"; the exact kernel and the rerank fill in
+    // the ones they own
+    if (c->use_tc) CU(cudaMemsetAsync(L.part.p, 0xFF, sizeof(uint4) * rows * n_split, s));
     {
       ProfScope ps(c, s, SLAMB200_K_SIFT_EXACT);
       launch_sift_exact_knn2(q->f32, q->flags, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split,
@@ -560,16 +570,66 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       CU(cudaMemcpyAsync(L.tile_prefix.p, pre, sizeof(int32_t) * (size_t)(n_pairs + 1), cudaMemcpyHostToDevice, s));
       CU(cudaEventRecord(L.stage_free, s));
       CU(cudaMemsetAsync(L.cand.p, 0xFF, cand_bytes, s));
-      int trc;
-      {
-        ProfScope ps(c, s, SLAMB200_K_SIFT_TC);
-        trc = launch_sift_tc_candidates(q->tmaps, q->flags, nq, (const TcPair*)L.tcpairs.p,
-                                        (const int32_t*)L.tile_prefix.p, n_pairs, (int)total, n_cta,
-                                        n_slots, (uint4*)L.cand.p, (int32_t*)L.err_flag.p, L.dbg, s);
+      if ((rc = buf_reserve(c, L.work, sizeof(uint4) * rows, s))) return rc;
+      if ((rc = buf_reserve(c, L.work_v0, sizeof(float) * rows, s))) return rc;
+      // Sub-batch pipeline: the tcgen05 kernel of sub-batch k+1 runs on `s` while the rerank and
+      // the finalize kernels of sub-batch k run on the lane's second stream.  The tensor-core
+      // kernel leaves registers, threads and issue slots free on every SM, so the L2-bound rerank
+      // co-resides with it instead of extending the step.
+      // (measured: with the 40-candidate rerank the two sides contend for the same SM issue
+      // slots and the step does not get shorter, so the default is one sub-batch; the knob stays
+      // for experiments: slamb200_dbg_set_sub_batch)
+      const int sub = (c->sub_batch > 0 && c->sub_batch < n_pairs) ? c->sub_batch : n_pairs;
+      const int n_sub = (n_pairs + sub - 1) / sub;
+      if ((int)L.sub_ev.size() < n_sub + 1) {
+        const size_t old_n = L.sub_ev.size();
+        L.sub_ev.resize(n_sub + 1, nullptr);
+        for (size_t i = old_n; i < L.sub_ev.size(); i++)
+          CU(cudaEventCreateWithFlags(&L.sub_ev[i], cudaEventDisableTiming));
       }
-      if (trc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
-      launch_sift_rerank(q->flags, q->u8, q->nrm2, nq, (const TcPair*)L.tcpairs.p, n_pairs, n_slots,
-                         n_split, (const uint4*)L.cand.p, (uint4*)L.part.p, (int32_t*)L.err_flag.p, s);
+      cudaStream_t s2 = n_sub > 1 ? L.stream2 : s;
+      const size_t cand_per_pair = (size_t)n_slots * n_rb * 256;
+      const int chunks = finalize_chunks(cap);
+      for (int k = 0; k < n_sub; k++) {
+        const int p0 = k * sub;
+        const int np = n_pairs - p0 < sub ? n_pairs - p0 : sub;
+        const TcPair* tcp = (const TcPair*)L.tcpairs.p + p0;
+        const int32_t* pre_k = (const int32_t*)L.tile_prefix.p + p0;
+        const int tiles_k = pre[p0 + np] - pre[p0];
+        uint4* cand_k = (uint4*)L.cand.p + (size_t)p0 * cand_per_pair;
+        uint4* part_k = (uint4*)L.part.p + (size_t)p0 * n_split * nq;
+        int trc;
+        {
+          ProfScope ps(c, s, SLAMB200_K_SIFT_TC);
+          trc = launch_sift_tc_candidates(q->tmaps, q->flags, nq, tcp, pre_k, np, tiles_k, n_cta,
+                                          n_slots, cand_k, (int32_t*)L.err_flag.p, k == 0 ? L.dbg : nullptr, s);
+        }
+        if (trc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
+        if (s2 != s) {
+          CU(cudaEventRecord(L.sub_ev[k], s));
+          CU(cudaStreamWaitEvent(s2, L.sub_ev[k], 0));
+        }
+        {
+          ProfScope ps(c, s2, SLAMB200_K_SIFT_RERANK);
+          launch_sift_rerank(q->u8, q->nrm2, nq, tcp, np, n_slots, n_split, cand_k, part_k,
+                             (uint4*)L.work.p + (size_t)p0 * nq, (float*)L.work_v0.p + (size_t)p0 * nq,
+                             (int32_t*)L.err_flag.p + 1 + (k < 1000 ? k : 1000), (int32_t*)L.err_flag.p,
+                             want_knn ? 0 : 1, ratio, s2);
+        }
+        ProfScope psf(c, s2, SLAMB200_K_FINALIZE);
+        launch_finalize(part_k, nq, (const PairArgs*)L.pairs.p + p0, np, n_split, 0, ratio,
+                        (int32_t*)L.knn_idx.p + (size_t)p0 * nq * 2,
+                        (float*)L.knn_dist.p + (size_t)p0 * nq * 2, (uint8_t*)L.flags.p + (size_t)p0 * nq,
+                        (int32_t*)L.chunk_cnt.p + (size_t)p0 * chunks,
+                        (slamb200_dmatch*)L.out.p + (size_t)p0 * cap, cap, (int32_t*)L.n_out.p + p0, s2);
+      }
+      CU(cudaGetLastError());
+      if (s2 != s) {
+        CU(cudaEventRecord(L.sub_ev[n_sub], s2));
+        CU(cudaStreamWaitEvent(s, L.sub_ev[n_sub], 0));
+      }
+      CU(cudaEventRecord(L.done, s));
+      return SLAMB200_OK;
     }
   }
   CU(cudaGetLastError());
@@ -657,7 +717,7 @@ extern "C" int slamb200_knn2(slamb200_ctx* c, int matcher, const slamb200_desc* 
   CU(cudaSetDevice(c->device));
   LaneGuard g(c);
   Lane& L = g.lane();
-  if ((rc = enqueue_batch(c, L, L.stream, matcher, q, tt, 1, 0.0))) return rc;
+  if ((rc = enqueue_batch(c, L, L.stream, matcher, q, tt, 1, 0.0, true))) return rc;
   if (q->n > 0) {
     CU(cudaMemcpyAsync(idx, L.knn_idx.p, sizeof(int32_t) * 2 * (size_t)q->n, cudaMemcpyDeviceToHost, L.stream));
     CU(cudaMemcpyAsync(dist, L.knn_dist.p, sizeof(float) * 2 * (size_t)q->n, cudaMemcpyDeviceToHost, L.stream));
@@ -944,6 +1004,12 @@ extern "C" int slamb200_batch_scores_fetch(slamb200_ctx* c, int32_t* counts, int
 }
 
 // ---- debug hooks (not part of the public header) ----------------------------------------------
+extern "C" int slamb200_dbg_set_sub_batch(slamb200_ctx* c, int pairs) {
+  if (!c) return SLAMB200_ERR_INVALID;
+  c->sub_batch = pairs;
+  return SLAMB200_OK;
+}
+
 extern "C" int slamb200_dbg_set_tc(slamb200_ctx* c, int on) {
   if (!c) return SLAMB200_ERR_INVALID;
   c->use_tc = on ? 1 : 0;

@@ -115,9 +115,10 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_fl
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
                               int32_t* err_flag, float* dbg, cudaStream_t s);
-void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
-                        const TcPair* pairs_dev, int n_pairs, int n_slots, int n_split,
-                        const uint4* cand, uint4* part, int32_t* err_flag, cudaStream_t s);
+void launch_sift_rerank(const uint8_t* q_u8, const int32_t* q_nrm2, int nq, const TcPair* pairs_dev,
+                        int n_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
+                        uint4* work, float* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
+                        double ratio, cudaStream_t s);
 
 int64_t* launch_counter();
 #define COUNT_LAUNCH() (++(*launch_counter()))

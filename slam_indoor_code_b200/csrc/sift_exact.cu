@@ -42,7 +42,7 @@ __device__ __forceinline__ void top2_insert(uint4& r, uint32_t k, uint32_t i) {
 
 __global__ void __launch_bounds__(SE_THREADS)
 sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_flags, int nq,
-                       const PairArgs* __restrict__ pairs, int n_split, long long n_items,
+                       const PairArgs* __restrict__ pairs, int n_pairs, int n_split, long long n_items,
                        uint4* __restrict__ part, int force) {
   extern __shared__ __align__(16) float smem[];
   float* sq = smem;                      // [SE_QT][SE_PITCH]
@@ -52,6 +52,16 @@ sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ 
   const int warp = threadIdx.x >> 5;  // 8 warps -> query rows 2*warp, 2*warp+1
   const int q_blocks = (nq + SE_QT - 1) / SE_QT;
   const bool q_exact = q_flags[0] == 0;
+  // one parallel sweep over the pair flags: a batch that belongs entirely to the tcgen05 path
+  // costs a single memory round trip here
+  if (!force) {
+    int mine = 0;
+    if (!q_exact) mine = 1;
+    else
+      for (int p = threadIdx.x; p < n_pairs; p += SE_THREADS)
+        if (pairs[p].t_flags == nullptr || pairs[p].t_flags[0] != 0) mine = 1;
+    if (__syncthreads_or(mine) == 0) return;
+  }
 
   // persistent walk over (pair, split, query block) work items: a batch whose pairs all belong
   // to the tcgen05 path costs a few flag reads per block, not one block launch per item
@@ -168,7 +178,7 @@ void launch_sift_exact_knn2(const float* q, const int32_t* q_flags, int nq, cons
   }
   const long long n_items = (long long)((nq + SE_QT - 1) / SE_QT) * n_split * n_pairs;
   const int grid = (int)(n_items < 148 * 8 ? n_items : 148 * 8);
-  sift_exact_knn2_kernel<<<grid, SE_THREADS, smem, s>>>(q, q_flags, nq, pairs, n_split, n_items,
+  sift_exact_knn2_kernel<<<grid, SE_THREADS, smem, s>>>(q, q_flags, nq, pairs, n_pairs, n_split, n_items,
                                                         part, force);
   COUNT_LAUNCH();
 }

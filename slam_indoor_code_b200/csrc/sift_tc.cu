@@ -23,13 +23,14 @@
 // warps 4..11 = epilogue.
 //
 // Epilogue: a thread owns one query row (TMEM lane) and half of the tile's columns.  Per 32-column
-// tcgen05.ld it reduces four groups of 8 columns with 3-input FMNMX trees and only when some
-// lane of the warp sees a group minimum below its running second-best does the warp fall into the
-// insert path, which keeps the best two *groups* (value, group index) per row.  The true top-2
-// columns of a row always lie inside its top-2 groups (ties resolve to the lowest index at every
-// level), so the rerank evaluates 16 candidates per row exactly -- integer dp4a on the u8 copies --
-// and emits (sqrtf(d^2), index) records that the shared finalize kernels turn into the ratio-
-// tested, ordered match list.  A device-side self check compares each rerank minimum with the
+// tcgen05.ld ("chunk") it reduces four groups of 8 columns with 3-input FMNMX trees, takes the
+// chunk minimum together with the group that holds it, and pushes (value, group) through a
+// branch-free running top-2 over chunks (~0.9 ALU instructions per accumulator, no divergence,
+// data-independent timing).  The best element of a row is the minimum of its best chunk; the
+// second best is either in that same chunk or is the minimum of the second-best chunk (ties
+// resolve to the lowest index at every level).  So the rerank evaluates 32 + 8 = 40 candidates per
+// row exactly -- integer dp4a on the u8 copies -- and emits (sqrtf(d^2), index) records that the
+// shared finalize kernels turn into the ratio-tested, ordered match list.  A device-side self check compares each rerank minimum with the
 // tensor-core value and raises err_flag on any mismatch (never expected).
 #include <cuda.h>
 #include <stdio.h>
@@ -304,6 +305,9 @@ __device__ __forceinline__ void top2_group_insert(float g, int gid, float& m1, i
                  "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),  \
                  "+r"(v[30]), "+r"(v[31])::"memory")
 
+// One 32-column chunk of a row: the chunk minimum and the 8-column group that holds it (lowest
+// group on ties) go through a branch-free running top-2 over *chunks*.  gid = column / 8 of the
+// minimum's group, so chunk = gid >> 2.  Strict '<' keeps the earlier chunk on equal values.
 __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0, float& m1, int& i1,
                                               float& m2, int& i2) {
   float g[4];
@@ -315,11 +319,12 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0,
                           __uint_as_float(v[8 * j + 5]));
     g[j] = fmin3(a, b, fminf(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
   }
-  const float cmin = fmin3(g[0], g[1], fminf(g[2], g[3]));
-  if (__any_sync(0xffffffffu, cmin < m2)) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) top2_group_insert(g[j], gid0 + j, m1, i1, m2, i2);
-  }
+  const float m01 = fminf(g[0], g[1]), m23 = fminf(g[2], g[3]);
+  const int j01 = g[1] < g[0] ? gid0 + 1 : gid0;
+  const int j23 = g[3] < g[2] ? gid0 + 3 : gid0 + 2;
+  const float cm = fminf(m01, m23);
+  const int gid = m23 < m01 ? j23 : j01;
+  top2_group_insert(cm, gid, m1, i1, m2, i2);
 }
 
 template <bool DBG>
@@ -569,15 +574,19 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
   }
 }
 
-// ---- rerank: exact integer distances of the 16 candidates of every row ------------------------
+// ---- rerank: merge the slot records, prune by the ratio test, evaluate the survivors exactly ---
 struct RerankParams {
   const uint8_t* q_u8;
   const int32_t* q_nrm2;
-  const int32_t* q_flags;
   const TcPair* pairs;
   const uint4* cand;
   int nq, nq_pad, n_slots, n_pairs, n_split;
-  uint4* part;       // [pair][n_split][nq]: split 0 gets the record, the others "absent"
+  int prune;         // 1: rows that cannot pass the ratio test skip the exact evaluation
+  double ratio;
+  uint4* part;       // [pair][n_split][nq]: split 0 gets the record (pre-set to "absent")
+  uint4* work;       // survivors: {pair, row, gid of the best chunk, gid of the second chunk}
+  float* work_v0;    // their tensor-core minimum (self check)
+  int32_t* work_n;   // number of survivors
   int32_t* err_flag;
 };
 
@@ -585,105 +594,138 @@ __device__ __forceinline__ bool lt_fi(float va, int ia, float vb, int ib) {
   return va < vb || (va == vb && ia < ib);
 }
 
-// Half a warp per query row (16 candidates = 16 lanes), two rows per warp, 16 rows per block.
-__global__ void __launch_bounds__(256) sift_rerank_kernel(const RerankParams R) {
+// Pass 1, one thread per (pair, row): merges the row's slot records into its best two chunks.
+// Lanes run along the rows, so every slot read is a coalesced 512 B per warp.
+//
+// Ratio-test pruning (exact, not a heuristic): v0 is the row's exact best d^2/2, and the second
+// best element is no farther than the second chunk's minimum v1.  sqrtf, float->double and the
+// multiplication by a non-negative ratio are monotone, so if even the upper bound
+// D1 = sqrtf(2*v1) fails  d0 < ratio * D1  (getGoodMatches' own comparison,
+// featureMatchingCommon.cpp:47), the true second distance fails it too: the row is rejected
+// without touching its candidates, and its record carries (d0, D1) so that the finalize kernel
+// reaches the same verdict with the same arithmetic.  Rows that survive go to the work list.
+// General-float pairs have no slot records (the tcgen05 kernel skipped them) and are left alone.
+__global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
   const int pair = blockIdx.y;
-  const int l = threadIdx.x & 15;
-  const int q = blockIdx.x * 16 + (threadIdx.x >> 4);
-  const TcPair* pr = R.pairs + pair;
-  if (R.q_flags[0] != 0 || pr->t_flags[0] != 0) return;  // not an exact-mode pair (block-uniform)
-  const bool row_ok = q < R.nq;
-  const int qc = row_ok ? q : R.nq - 1;
-  const int t_n = pr->t_n;
-
-  // 1. best two candidate groups over all slots (each lane reads one slot record)
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  bool survive = false;
   float v0 = __int_as_float(0x7f800000), v1 = v0;
   int g0 = 0x7fffffff, g1 = 0x7fffffff;
-  for (int s = l; s < R.n_slots; s += 16) {
-    const uint4 rec = R.cand[((size_t)pair * R.n_slots + s) * R.nq_pad + qc];
-    const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.z);
-    const int ia = (int)rec.y, ib = (int)rec.w;
-    if (ia >= 0) {
-      if (lt_fi(a, ia, v0, g0)) { v1 = v0; g1 = g0; v0 = a; g0 = ia; }
-      else if (lt_fi(a, ia, v1, g1)) { v1 = a; g1 = ia; }
+  if (q < R.nq) {
+    for (int s = 0; s < R.n_slots; s++) {
+      const uint4 rec = R.cand[((size_t)pair * R.n_slots + s) * R.nq_pad + q];
+      const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.z);
+      const int ia = (int)rec.y, ib = (int)rec.w;
+      if (ia >= 0) {
+        if (lt_fi(a, ia, v0, g0)) { v1 = v0; g1 = g0; v0 = a; g0 = ia; }
+        else if (lt_fi(a, ia, v1, g1)) { v1 = a; g1 = ia; }
+      }
+      if (ib >= 0) {
+        if (lt_fi(b, ib, v0, g0)) { v1 = v0; g1 = g0; v0 = b; g0 = ib; }
+        else if (lt_fi(b, ib, v1, g1)) { v1 = b; g1 = ib; }
+      }
     }
-    if (ib >= 0) {
-      if (lt_fi(b, ib, v0, g0)) { v1 = v0; g1 = g0; v0 = b; g0 = ib; }
-      else if (lt_fi(b, ib, v1, g1)) { v1 = b; g1 = ib; }
-    }
-  }
-#pragma unroll
-  for (int off = 8; off >= 1; off >>= 1) {
-    const float ov0 = __shfl_xor_sync(0xffffffffu, v0, off), ov1 = __shfl_xor_sync(0xffffffffu, v1, off);
-    const int og0 = __shfl_xor_sync(0xffffffffu, g0, off), og1 = __shfl_xor_sync(0xffffffffu, g1, off);
-    if (lt_fi(ov0, og0, v0, g0)) {
-      // other's best wins: second = min(mine best, other's second)
-      if (lt_fi(v0, g0, ov1, og1)) { v1 = v0; g1 = g0; } else { v1 = ov1; g1 = og1; }
-      v0 = ov0; g0 = og0;
-    } else if (!(ov0 == v0 && og0 == g0)) {
-      if (lt_fi(ov0, og0, v1, g1)) { v1 = ov0; g1 = og0; }
-    } else {
-      // identical best (both sides empty): second = min of the seconds
-      if (lt_fi(ov1, og1, v1, g1)) { v1 = ov1; g1 = og1; }
+    const bool has0 = g0 != 0x7fffffff, has1 = g1 != 0x7fffffff;
+    survive = has0;
+    if (R.prune && has0 && has1) {
+      const float d0 = sqrtf(2.0f * v0), D1 = sqrtf(2.0f * v1);
+      if (!((double)d0 < __dmul_rn(R.ratio, (double)D1))) {
+        R.part[((size_t)pair * R.n_split) * R.nq + q] =
+            make_uint4(__float_as_uint(d0), 0u, __float_as_uint(D1), 0u);
+        survive = false;
+      }
     }
   }
+  // warp-aggregated append to the work list
+  const unsigned bal = __ballot_sync(0xffffffffu, survive);
+  if (bal) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(R.work_n, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (survive) {
+      const int at = base + __popc(bal & ((1u << lane) - 1));
+      R.work[at] = make_uint4((uint32_t)pair, (uint32_t)q, (uint32_t)g0, (uint32_t)g1);
+      R.work_v0[at] = v0;
+    }
+  }
+}
 
-  // 2. exact integer d^2 for the 16 candidate columns: lanes 0..7 -> group g0, 8..15 -> group g1
-  const int grp = l < 8 ? g0 : g1;
-  const bool has_grp = grp != 0x7fffffff;
-  const int col = has_grp ? grp * GROUP + (l & 7) : -1;
-  uint32_t d2 = 0xFFFFFFFFu;
-  if (has_grp && col < t_n) {
-    const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qc * 128);
-    const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)col * 128);
-    uint32_t dot = 0;  // u8 x u8 products: unsigned dp4a
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const uint4 a = qp[k], b = tp[k];
-      dot = __dp4a(a.x, b.x, dot);
-      dot = __dp4a(a.y, b.y, dot);
-      dot = __dp4a(a.z, b.z, dot);
-      dot = __dp4a(a.w, b.w, dot);
+// Pass 2, persistent warps over the work list, one warp per surviving row.  Candidates = all 32
+// columns of the best chunk + the 8 columns of the second chunk's group (40): the true top-2
+// columns are always among them.  Each candidate row is read by 8 lanes x 16 B (one 128 B line
+// per candidate), dp4a'd against the matching 16 B of the query row and reduced over the 8 lanes.
+__global__ void __launch_bounds__(256) sift_rerank_kernel(const RerankParams R) {
+  const int lane = threadIdx.x & 31;
+  const int part = lane & 7, sub = lane >> 3;
+  const int n_work = *R.work_n;
+  const int warps = gridDim.x * 8;
+  for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < n_work; w += warps) {
+    const uint4 wk = R.work[w];
+    const int pair = (int)wk.x, q = (int)wk.y, g0 = (int)wk.z, g1 = (int)wk.w;
+    const float v0 = R.work_v0[w];
+    const TcPair* pr = R.pairs + pair;
+    const uint8_t* t_u8 = pr->t_u8;
+    const int32_t* t_nrm2 = pr->t_nrm2;
+    const int t_n = pr->t_n;
+    const bool has1 = g1 != 0x7fffffff;
+    const int col_a = (g0 >> 2) * 32;          // first column of the best chunk
+    const int col_b = has1 ? g1 * GROUP : 0;   // first column of the second chunk's group
+
+    const uint4 qv = *reinterpret_cast<const uint4*>(R.q_u8 + (size_t)q * 128 + part * 16);
+    const uint32_t nq2 = (uint32_t)R.q_nrm2[q];
+    unsigned long long k0 = ~0ull, k1 = ~0ull;
+    uint32_t mn_a = 0xFFFFFFFFu;  // minimum d^2 inside the best chunk (self check)
+#pragma unroll 5
+    for (int it = 0; it < 10; it++) {
+      const int k = it * 4 + sub;
+      const int col = k < 32 ? col_a + k : col_b + (k - 32);
+      const bool ok = (k < 32 || has1) && col < t_n;
+      const int cc = ok ? col : 0;
+      const uint4 tv = *reinterpret_cast<const uint4*>(t_u8 + (size_t)cc * 128 + part * 16);
+      const uint32_t nt2 = (uint32_t)t_nrm2[cc];
+      uint32_t dot = 0;
+      dot = __dp4a(qv.x, tv.x, dot);
+      dot = __dp4a(qv.y, tv.y, dot);
+      dot = __dp4a(qv.z, tv.z, dot);
+      dot = __dp4a(qv.w, tv.w, dot);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      if (ok) {
+        const uint32_t d2 = nq2 + nt2 - 2u * dot;
+        const unsigned long long key = ((unsigned long long)d2 << 32) | (uint32_t)col;
+        if (k < 32) mn_a = min(mn_a, d2);
+        if (key < k1) {
+          if (key < k0) { k1 = k0; k0 = key; } else { k1 = key; }
+        }
+      }
     }
-    d2 = (uint32_t)(R.q_nrm2[qc] + pr->t_nrm2[col]) - 2u * dot;
-  }
-  // self check: the minimum of group g0 must equal twice the tensor-core value
-  {
-    uint32_t mn = d2;
+    // merge the four candidate lane groups (the 8 lanes of a group hold identical values)
 #pragma unroll
-    for (int off = 4; off >= 1; off >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-    if (l == 0 && row_ok && g0 != 0x7fffffff && mn != 0xFFFFFFFFu) {
-      if ((float)mn != 2.0f * v0) atomicOr(R.err_flag, 1);
+    for (int off = 8; off <= 16; off <<= 1) {
+      const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, off);
+      const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off);
+      const unsigned long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0;
+      const unsigned long long s2 = k1 < o1 ? k1 : o1;
+      k0 = lo;
+      k1 = hi < s2 ? hi : s2;
+      mn_a = min(mn_a, __shfl_xor_sync(0xffffffffu, mn_a, off));
     }
-  }
-  // 3. top-2 by (d2, col) across the 16 lanes
-  const unsigned long long key =
-      d2 == 0xFFFFFFFFu ? ~0ull : (((unsigned long long)d2 << 32) | (uint32_t)col);
-  unsigned long long k0 = key;
-#pragma unroll
-  for (int off = 8; off >= 1; off >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k0, off);
-    k0 = o < k0 ? o : k0;
-  }
-  unsigned long long k1 = key == k0 ? ~0ull : key;
-#pragma unroll
-  for (int off = 8; off >= 1; off >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k1, off);
-    k1 = o < k1 ? o : k1;
-  }
-  if (l == 0 && row_ok) {
-    uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
-    if (k0 != ~0ull) {
-      rec.x = __float_as_uint(sqrtf((float)(uint32_t)(k0 >> 32)));
-      rec.y = (uint32_t)(k0 & 0xFFFFFFFFu);
+    if (lane == 0) {
+      // self check: the best chunk's exact minimum must equal twice the tensor-core value
+      if (mn_a != 0xFFFFFFFFu && (float)mn_a != 2.0f * v0) atomicOr(R.err_flag, 1);
+      uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+      if (k0 != ~0ull) {
+        rec.x = __float_as_uint(sqrtf((float)(uint32_t)(k0 >> 32)));
+        rec.y = (uint32_t)(k0 & 0xFFFFFFFFu);
+      }
+      if (k1 != ~0ull) {
+        rec.z = __float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32)));
+        rec.w = (uint32_t)(k1 & 0xFFFFFFFFu);
+      }
+      R.part[((size_t)pair * R.n_split) * R.nq + q] = rec;
     }
-    if (k1 != ~0ull) {
-      rec.z = __float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32)));
-      rec.w = (uint32_t)(k1 & 0xFFFFFFFFu);
-    }
-    R.part[((size_t)pair * R.n_split) * R.nq + q] = rec;
-    const uint4 none = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
-    for (int sp = 1; sp < R.n_split; sp++) R.part[((size_t)pair * R.n_split + sp) * R.nq + q] = none;
   }
 }
 
@@ -790,15 +832,22 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_fl
   return 0;
 }
 
-void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
-                        const TcPair* pairs_dev, int n_pairs, int n_slots, int n_split,
-                        const uint4* cand, uint4* part, int32_t* err_flag, cudaStream_t s) {
+void launch_sift_rerank(const uint8_t* q_u8, const int32_t* q_nrm2, int nq, const TcPair* pairs_dev,
+                        int n_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
+                        uint4* work, float* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
+                        double ratio, cudaStream_t s) {
   if (nq <= 0 || n_pairs <= 0) return;
   RerankParams R;
-  R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
+  R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.pairs = pairs_dev; R.cand = cand;
   R.nq = nq; R.nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM); R.n_slots = n_slots; R.n_pairs = n_pairs;
   R.n_split = n_split; R.part = part; R.err_flag = err_flag;
-  dim3 grid((nq + 15) / 16, n_pairs);
-  sift_rerank_kernel<<<grid, 256, 0, s>>>(R);
+  R.work = work; R.work_v0 = work_v0; R.work_n = work_n;
+  R.prune = (prune && ratio >= 0.0 && ratio < 1e300) ? 1 : 0; R.ratio = ratio;
+  dim3 grid((nq + 255) / 256, n_pairs);
+  sift_merge_kernel<<<grid, 256, 0, s>>>(R);
+  COUNT_LAUNCH();
+  const long long rows = (long long)nq * n_pairs;
+  const int blocks = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
+  sift_rerank_kernel<<<blocks, 256, 0, s>>>(R);
   COUNT_LAUNCH();
 }

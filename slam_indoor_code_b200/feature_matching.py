@@ -80,7 +80,7 @@ class Context:
     def launch_count(self):
         return int(self._lib.slamb200_launch_count(self._h))
 
-    KERNELS = ("sift_tc", "sift_exact", "orb", "ransac")
+    KERNELS = ("sift_tc", "sift_exact", "orb", "ransac", "sift_rerank", "finalize")
 
     def profile_enable(self, on=True):
         check(self._lib.slamb200_profile_enable(self._h, 1 if on else 0))
