@@ -68,7 +68,26 @@ def build(force=False, verbose=False, defines=()):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    build_host_shim()
     return LIB
+
+
+def build_host_shim():
+    """The C++ drop-in TU (host/featureMatchingB200.cpp) compiled against host/cv_shim.h plus C
+    entry points for the tests.  With the real OpenCV the TU is compiled inside the reference
+    tree instead."""
+    host = os.path.join(HERE, "host")
+    out = os.path.join(LIBDIR, "libslamb200_hostshim.so")
+    deps = [os.path.join(host, f) for f in os.listdir(host)] + [LIB]
+    if _stale(out, deps):
+        cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-DSLAMB200_CV_SHIM",
+               "-I" + os.path.join(os.path.dirname(HERE), "include"), "-o", out,
+               os.path.join(host, "host_shim_test.cpp"), "-L" + LIBDIR, "-lslamb200",
+               "-Wl,-rpath,$ORIGIN", "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"host shim build failed:\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 if __name__ == "__main__":

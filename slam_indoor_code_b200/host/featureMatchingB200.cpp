@@ -1,0 +1,169 @@
+// featureMatchingB200.cpp -- the reference-side binding of libslamb200: a third translation unit
+// behind src/mainModule/featureMatching/featureMatching.h, next to featureMatchingCPU.cpp and
+// featureMatchingCUDA.cpp (the reference's CMakeLists.txt:56-67 compiles exactly one of them; a
+// USE_B200 option adds this one).  Same three symbols, same signatures, same
+// behaviour: extractDescriptor stays OpenCV-CPU (it produces this path's input), matchFeatures
+// is replaced by one C-ABI call that runs knnMatch(k=2) + getGoodMatches on the B200.
+//
+// Build against the real OpenCV inside the reference tree, or against host/cv_shim.h
+// (-DSLAMB200_CV_SHIM) where OpenCV's headers are not installed -- the shim declares exactly the
+// members this file touches.
+#ifdef SLAMB200_CV_SHIM
+#include "cv_shim.h"
+#else
+#include <opencv2/core.hpp>
+#include <opencv2/opencv.hpp>
+#include "../../config/config.h"
+#include "featureMatching.h"
+#include "featureMatchingCommon.h"
+// knnMatcherDistance exactly as getGoodMatches reads it (featureMatchingCommon.cpp:42)
+static double knnMatcherDistance() {
+  return configService.getValue<double>(ConfigFieldEnum::FM_KNN_DISTANCE);
+}
+#endif
+
+#include <exception>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "slamb200.h"
+
+using namespace cv;
+
+namespace {
+
+// One context per process, created on first use on device 0 (the reference only checks that a
+// CUDA device exists, main.cpp:30-38).  The C ABI is re-entrant, so the `threadsCount` matcher
+// threads of batch.cpp:181-201 share it.
+slamb200_ctx* context() {
+  static slamb200_ctx* ctx = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (slamb200_init(0, &ctx) != SLAMB200_OK)
+      throw std::runtime_error(std::string("slamb200_init: ") + slamb200_last_error());
+  });
+  return ctx;
+}
+
+struct DescHandle {
+  slamb200_desc* d = nullptr;
+  ~DescHandle() { if (d) slamb200_free_desc(context(), d); }
+};
+
+int descKindOf(int matcherType) {
+  switch (matcherType) {
+    case SIFT_BF:
+    case SIFT_FLANN:
+      return SLAMB200_DESC_F32X128;
+    case ORB_BF:
+      return SLAMB200_DESC_U8X32;
+    default:
+      throw std::exception();  // featureMatchingCPU.cpp:36-37
+  }
+}
+
+void upload(const Mat& desc, int kind, DescHandle& h) {
+  const int want = kind == SLAMB200_DESC_F32X128 ? CV_32F : CV_8U;
+  const int cols = kind == SLAMB200_DESC_F32X128 ? 128 : 32;
+  if (!desc.empty() && (desc.type() != want || desc.cols != cols))
+    throw std::runtime_error("descriptor Mat type/width does not fit the matcher");  // cv::Exception in OpenCV
+  const int rc = slamb200_upload_desc(context(), kind, desc.empty() ? nullptr : desc.data,
+                                      desc.empty() ? 0 : desc.rows, desc.empty() ? 0 : (size_t)desc.step,
+                                      &h.d);
+  if (rc != SLAMB200_OK) throw std::runtime_error(std::string("slamb200_upload_desc: ") + slamb200_last_error());
+}
+
+}  // namespace
+
+/*
+ * @param prevDesc [in]  query descriptors (previous frame)
+ * @param curDesc [in]   train descriptors (candidate frame)
+ * @param matches [out]  good matches, ascending queryIdx (cleared first, like getGoodMatches)
+ * @param matcherType [in] 0 - sift_bf, 1 - sift_flann, 2 - orb_bf
+ * Replaces featureMatchingCPU.cpp:17-43.
+ */
+static void matchFeatures(Mat& prevDesc, Mat& curDesc, std::vector<DMatch>& matches, int extractorType) {
+  const int kind = descKindOf(extractorType);
+  DescHandle q, t;
+  upload(prevDesc, kind, q);
+  upload(curDesc, kind, t);
+  matches.clear();
+  const int cap = prevDesc.empty() ? 0 : prevDesc.rows;
+  if (cap == 0) return;
+  static_assert(sizeof(DMatch) == sizeof(slamb200_dmatch), "cv::DMatch layout");
+  matches.resize((size_t)cap);
+  int n = 0;
+  const int rc = slamb200_match_pair(context(), extractorType, q.d, t.d, knnMatcherDistance(),
+                                     reinterpret_cast<slamb200_dmatch*>(matches.data()), cap, &n);
+  if (rc != SLAMB200_OK) {
+    matches.clear();
+    throw std::runtime_error(std::string("slamb200_match_pair: ") + slamb200_last_error());
+  }
+  matches.resize((size_t)n);
+}
+
+// featureMatchingCPU.cpp:45-66, unchanged: the descriptors are this path's input.
+void extractDescriptor(Mat& frame, std::vector<KeyPoint>& features, int matcherType, Mat& desc) {
+  cv::Ptr<cv::DescriptorExtractor> extractor;
+  switch (matcherType) {
+    case SIFT_BF:
+    case SIFT_FLANN:
+      extractor = cv::SIFT::create();
+      break;
+    case ORB_BF:
+      extractor = cv::ORB::create();
+      break;
+    default:
+      throw std::exception();
+  }
+  extractor->compute(frame, features, desc);
+}
+
+// featureMatching.h:29-36
+void matchFramesPairFeatures(Mat& firstFrame, Mat& secondFrame, std::vector<KeyPoint>& firstFeatures,
+                             std::vector<KeyPoint>& secondFeatures, int matcherType,
+                             std::vector<DMatch>& matches) {
+  Mat firstDescriptor;
+  extractDescriptor(firstFrame, firstFeatures, matcherType, firstDescriptor);
+  matchFramesPairFeatures(firstDescriptor, secondFrame, secondFeatures, matcherType, matches);
+}
+
+// featureMatching.h:47-53
+void matchFramesPairFeatures(Mat& firstFrameDescriptor, Mat& secondFrame,
+                             std::vector<KeyPoint>& secondFeatures, int matcherType,
+                             std::vector<DMatch>& matches) {
+  Mat secondDescriptor;
+  extractDescriptor(secondFrame, secondFeatures, matcherType, secondDescriptor);
+  matchFeatures(firstFrameDescriptor, secondDescriptor, matches, matcherType);
+}
+
+// Optional fast path for the batch window (batch.cpp:101-226): one query
+// descriptor against every batch element's descriptor in ONE call.  The per-frame descriptor sets
+// are uploaded once; `allMatches[i]` receives element i's good matches.
+void matchFramesBatchFeatures(Mat& firstFrameDescriptor, std::vector<Mat>& batchDescriptors,
+                              int matcherType, std::vector<std::vector<DMatch>>& allMatches) {
+  const int kind = descKindOf(matcherType);
+  DescHandle q;
+  upload(firstFrameDescriptor, kind, q);
+  std::vector<DescHandle> t(batchDescriptors.size());
+  std::vector<const slamb200_desc*> tp(batchDescriptors.size());
+  for (size_t i = 0; i < batchDescriptors.size(); i++) {
+    upload(batchDescriptors[i], kind, t[i]);
+    tp[i] = t[i].d;
+  }
+  const int P = (int)batchDescriptors.size();
+  const int cap = firstFrameDescriptor.empty() ? 0 : firstFrameDescriptor.rows;
+  allMatches.assign((size_t)P, std::vector<DMatch>());
+  if (P == 0 || cap == 0) return;
+  std::vector<slamb200_dmatch> out((size_t)P * cap);
+  std::vector<int> n((size_t)P, 0);
+  const int rc = slamb200_match_batch(context(), matcherType, q.d, tp.data(), P, knnMatcherDistance(),
+                                      out.data(), cap, n.data());
+  if (rc != SLAMB200_OK) throw std::runtime_error(std::string("slamb200_match_batch: ") + slamb200_last_error());
+  for (int p = 0; p < P; p++) {
+    const DMatch* src = reinterpret_cast<const DMatch*>(out.data() + (size_t)p * cap);
+    allMatches[(size_t)p].assign(src, src + n[(size_t)p]);
+  }
+}

@@ -1,0 +1,51 @@
+// host_shim_test.cpp -- C entry points over the shim build of featureMatchingB200.cpp so that the
+// Python tests can drive the C++ host layer (the static matchFeatures and the batch fast path)
+// exactly as the reference's callers would (batch.cpp:127-130).
+#include "featureMatchingB200.cpp"
+
+static double g_ratio = 0.7;
+double knnMatcherDistance() { return g_ratio; }
+
+extern "C" {
+
+void hostshim_set_ratio(double r) { g_ratio = r; }
+
+// matchFeatures(prevDesc, curDesc, matches, type): returns the match count or -1 on an exception.
+int hostshim_match_features(const void* q, int nq, size_t q_step, const void* t, int nt, size_t t_step,
+                            int type, cv::DMatch* out, int cap) {
+  try {
+    const bool orb = type == ORB_BF;
+    cv::Mat prev(nq, orb ? 32 : 128, orb ? CV_8U : CV_32F, const_cast<void*>(q), q_step);
+    cv::Mat cur(nt, orb ? 32 : 128, orb ? CV_8U : CV_32F, const_cast<void*>(t), t_step);
+    std::vector<cv::DMatch> m;
+    m.push_back(cv::DMatch());  // must be cleared by the callee
+    matchFeatures(prev, cur, m, type);
+    if ((int)m.size() > cap) return -2;
+    for (size_t i = 0; i < m.size(); i++) out[i] = m[i];
+    return (int)m.size();
+  } catch (...) {
+    return -1;
+  }
+}
+
+int hostshim_match_batch(const void* q, int nq, const void* const* t, const int* nt, int P, int type,
+                         cv::DMatch* out, int cap, int* n_out) {
+  try {
+    const bool orb = type == ORB_BF;
+    const int w = orb ? 32 : 128, ty = orb ? CV_8U : CV_32F;
+    const size_t step = orb ? 32 : 512;
+    cv::Mat prev(nq, w, ty, const_cast<void*>(q), step);
+    std::vector<cv::Mat> batch;
+    for (int p = 0; p < P; p++) batch.emplace_back(nt[p], w, ty, const_cast<void*>(t[p]), step);
+    std::vector<std::vector<cv::DMatch>> all;
+    matchFramesBatchFeatures(prev, batch, type, all);
+    for (int p = 0; p < P; p++) {
+      n_out[p] = (int)all[p].size();
+      for (size_t i = 0; i < all[p].size(); i++) out[(size_t)p * cap + i] = all[p][i];
+    }
+    return 0;
+  } catch (...) {
+    return -1;
+  }
+}
+}

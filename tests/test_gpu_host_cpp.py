@@ -1,0 +1,78 @@
+"""GPU: the C++ drop-in translation unit (host/featureMatchingB200.cpp) driven like the reference
+drives featureMatchingCPU.cpp -- cv::Mat descriptors in, std::vector<cv::DMatch> out -- through
+the cv_shim build.  Checker: the CPU oracle."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle, synth
+from slam_indoor_code_b200 import _capi, build
+
+
+@pytest.fixture(scope="module")
+def host():
+    build.build()
+    lib = ctypes.CDLL(os.path.join(build.LIBDIR, "libslamb200_hostshim.so"))
+    lib.hostshim_set_ratio.argtypes = [ctypes.c_double]
+    lib.hostshim_match_features.restype = ctypes.c_int
+    lib.hostshim_match_features.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p,
+                                            ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_int]
+    lib.hostshim_match_batch.restype = ctypes.c_int
+    lib.hostshim_match_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.c_void_p]
+    return lib
+
+
+def _match(host, q, t, mtype, ratio=0.7):
+    host.hostshim_set_ratio(ratio)
+    out = np.zeros(max(len(q), 1), _capi.DMATCH)
+    n = host.hostshim_match_features(_capi.ptr(q), len(q), q.strides[0] if len(q) else 0, _capi.ptr(t),
+                                     len(t), t.strides[0] if len(t) else 0, mtype, _capi.ptr(out), len(out))
+    return n, out[: max(n, 0)]
+
+
+@pytest.mark.parametrize("mtype", [0, 1, 2])
+def test_match_features_cpp(host, mtype):
+    q, t = synth.orb_pair(700, 900, 31) if mtype == 2 else synth.sift_pair(700, 900, 31)
+    n, got = _match(host, q, t, mtype)
+    assert n >= 0 and np.array_equal(got, c_oracle.match_features(mtype, q, t, 0.7))
+    n, got = _match(host, q, t, mtype, ratio=0.9)
+    assert np.array_equal(got, c_oracle.match_features(mtype, q, t, 0.9))
+
+
+def test_cv_mat_step_and_empty_mats(host):
+    q, t = synth.sift_pair(300, 400, 32)
+    wide = np.zeros((400, 144), np.float32)
+    wide[:, :128] = t
+    n, got = _match(host, q, wide[:, :128], 0)
+    assert np.array_equal(got, c_oracle.match_features(0, q, t, 0.7))
+    e = np.zeros((0, 128), np.float32)
+    assert _match(host, e, t, 0)[0] == 0          # empty query Mat -> matches cleared
+    assert _match(host, q, e, 0)[0] == 0          # empty train Mat
+
+
+def test_bad_matcher_type_throws(host):
+    q, t = synth.sift_pair(10, 10, 33)
+    assert _match(host, q, t, 5)[0] == -1         # featureMatchingCPU.cpp:37: throw std::exception()
+
+
+def test_batch_fast_path_cpp(host):
+    q = synth.sift_like(600, 34)
+    trains = [synth.sift_train_from_query(q, n, 35 + i) for i, n in enumerate((500, 800, 64))]
+    P = len(trains)
+    host.hostshim_set_ratio(0.7)
+    ptrs = (ctypes.c_void_p * P)(*[t.ctypes.data for t in trains])
+    nt = np.array([len(t) for t in trains], np.int32)
+    out = np.zeros((P, len(q)), _capi.DMATCH)
+    n_out = np.zeros(P, np.int32)
+    rc = host.hostshim_match_batch(_capi.ptr(q), len(q), ptrs, _capi.ptr(nt), P, 0, _capi.ptr(out), len(q),
+                                   _capi.ptr(n_out))
+    assert rc == 0
+    for p in range(P):
+        assert np.array_equal(out[p, : n_out[p]], c_oracle.match_features(0, q, trains[p], 0.7))
