@@ -90,3 +90,41 @@ def batchScoresFetch(ctx, stream=None):
     check(ctx._lib.slamb200_batch_scores_fetch(ctx._h, ptr(counts), ptr(best), ptr(mask), cap,
                                                ctypes.c_void_p(stream or 0)))
     return counts, best, mask
+
+
+def _cv2_five_point(K4):
+    """The CPU minimal solver: cv::findEssentialMat on exactly five matches returns the stacked
+    3k x 3 candidates of the 5-point algorithm (it stays on the CPU)."""
+    import cv2
+    Kmat = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]], np.float64)
+
+    def solve(p1, p2):
+        E = cv2.findEssentialMat(p1, p2, Kmat, cv2.RANSAC, 0.999, 1.0)[0]
+        return np.zeros((0, 9)) if E is None else np.asarray(E, np.float64).reshape(-1, 9)
+    return solve
+
+
+def findEssentialMat(ctx, points1, points2, K, RPRANSACProb=0.999, RPRANSACThreshold=5.0,
+                     five_point_fn=None, chunk=32):
+    """Drop-in for findEssentialMat(points1, points2, K, RANSAC, prob, threshold, mask)
+    (cameraTranslation.cpp:41-46): returns (E 3x3 or None, mask N x 1 uint8 or None), bit-identical
+    to OpenCV's.  The RANSAC control runs on the host (ransac_host.py), the 5-point solver on the
+    CPU, every candidate model is scored on the B200."""
+    from . import ransac_host
+    K = np.asarray(K, np.float64)
+    K4 = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], np.float64) if K.shape == (3, 3) \
+        else np.ascontiguousarray(K.reshape(4), np.float64)
+    p1 = np.ascontiguousarray(points1, np.float32).reshape(-1, 2)
+    p2 = np.ascontiguousarray(points2, np.float32).reshape(-1, 2)
+    solve = five_point_fn or _cv2_five_point(K4)
+
+    def score(models):
+        return scoreEssentialHypotheses(ctx, p1, p2, K4, models, RPRANSACThreshold)[0]
+
+    E, mask, _, _ = ransac_host.ransac_essential(p1, p2, K4, RPRANSACProb, RPRANSACThreshold, solve,
+                                                 score, chunk=chunk)
+    if E is None:
+        return None, None
+    if mask is None:
+        mask = scoreEssentialHypotheses(ctx, p1, p2, K4, E.reshape(1, 9), RPRANSACThreshold)[2]
+    return E.reshape(3, 3) if E.size == 9 else E.reshape(-1, 3), mask.reshape(-1, 1)

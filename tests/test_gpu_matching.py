@@ -327,3 +327,29 @@ def test_pinned_pipelined_upload(ctx):
     Q2 = ctx.upload_pinned(q.copy())
     ctx.synchronize()
     assert np.array_equal(ctx.matchFeatures(Q2, T, MatcherType.SIFT_BF, 0.7), got)
+
+
+def test_cfg4_large_frames_window(ctx):
+    """cfg4 shape: 50,000 descriptors per frame (196 train tiles, 196 query blocks), all pairs of
+    a 3-frame window; property checks + oracle spot rows."""
+    frames = [synth.sift_like(50000, 4000 + f) for f in range(3)]
+    frames[1][:2000] = np.clip(frames[0][:2000] + 3, 0, 255)
+    frames[2][1000:4000] = frames[0][1000:4000]
+    sets = [ctx.upload(f) for f in frames]
+    res = ctx.matchWindow(sets, MatcherType.SIFT_BF, 0.7)
+    rows = np.random.default_rng(9).choice(50000, 24, replace=False)
+    rows[:4] = [0, 1999, 1000, 3999]
+    for (i, j), m in res.items():
+        assert np.all(np.diff(m["queryIdx"]) > 0)
+        ridx, rdist = c_oracle.l2_knn2(frames[i][rows], frames[j])
+        ref = c_oracle.ratio_test(ridx, rdist, 0.7)
+        got = m[np.isin(m["queryIdx"], rows)]
+        order = np.argsort(rows)
+        exp_q = rows[order][np.isin(np.arange(len(rows))[order], ref["queryIdx"])]
+        assert sorted(got["queryIdx"].tolist()) == sorted(rows[ref["queryIdx"]].tolist())
+        for r in ref:
+            g = got[got["queryIdx"] == rows[r["queryIdx"]]][0]
+            assert g["trainIdx"] == r["trainIdx"] and g["distance"] == r["distance"]
+    assert len(res[(0, 2)]) >= 2500
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, sets[0], sets[1])
+    _check_knn(idx[rows], dist[rows], *c_oracle.l2_knn2(frames[0][rows], frames[1]))

@@ -133,3 +133,17 @@ def test_match_then_score_chain(ctx):
         rc, rb, rm, _ = c_oracle.score_essential(p1, p2, K4, E[p], 50.0)
         assert np.array_equal(counts[p], rc) and best[p] == rb
         assert np.array_equal(mask[p, : len(ref)], rm)
+
+
+@pytest.mark.parametrize("m,noise,outl,seed", [(600, 0.7, 0.3, 7000), (5000, 0.7, 0.3, 7003),
+                                               (3000, 3.0, 0.7, 7005)])
+def test_find_essential_mat_drop_in(ctx, m, noise, outl, seed):
+    """findEssentialMat(p1, p2, K, RANSAC, 0.999, 5.0, mask) end to end: host RANSAC control +
+    CPU 5-point solver + GPU scoring == cv2.findEssentialMat, E and mask bit for bit."""
+    cv2 = pytest.importorskip("cv2")
+    p1, p2, _, _ = synth.two_view(m, seed, noise_px=noise, outliers=outl)
+    Kmat = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]])
+    Ecv, mcv = cv2.findEssentialMat(p1, p2, Kmat, cv2.RANSAC, 0.999, 5.0)
+    E, mask = ct.findEssentialMat(ctx, p1, p2, Kmat, 0.999, 5.0)
+    assert np.array_equal(np.asarray(Ecv, np.float64).reshape(3, 3), E)
+    assert np.array_equal(mcv, mask)
