@@ -250,7 +250,12 @@ def run_b200(args, rank, world, local):
     log(f"[rank {rank}] generated {len(trains)} train frames in {time.perf_counter() - t_gen:.1f}s")
 
     ctx = Context(local)
-    stream = torch.cuda.current_stream().cuda_stream
+    # A real (non-default) stream: the C ABI treats a NULL stream as "the lane's own stream", so
+    # the kernels and the CUDA events that time them must share an explicit stream handle.
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     Q = ctx.upload(q)
     Ts = [ctx.upload(t) for t in trains]
     assert Q.exact_mode == 1 and all(t.exact_mode == 1 for t in Ts[:2]), \

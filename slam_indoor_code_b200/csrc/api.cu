@@ -54,9 +54,12 @@ struct Lane {
   // scoring scratch (device)
   DevBuf npts, E, counts, best, mask, m_off, p1, p2, txy, all_masks;
   // pinned staging
-  void* h_stage = nullptr;
-  size_t h_stage_cap = 0;
-  cudaEvent_t stage_free = nullptr;  // recorded after the last async copy out of h_stage
+  // pinned staging ring: the host fills slot k+1 while the copy out of slot k may still be
+  // queued behind the previous step's kernels (an enqueue never waits for the device)
+  struct StageSlot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; } stage[4];
+  int stage_i = 0;
+  void* h_stage = nullptr;           // current slot
+  cudaEvent_t stage_free = nullptr;  // current slot's event: record after the copy out of it
   cudaEvent_t done = nullptr;        // recorded after the last work queued through this lane
   int32_t* h_small = nullptr;        // pinned, N_SMALL ints (counts read-back)
   void* h_out = nullptr;             // pinned staging for the match lists on their way out
@@ -87,6 +90,12 @@ struct slamb200_ctx {
   int n_sm = 148;
   int next_lane = 0;
   cudaStream_t free_stream = nullptr;  // frees are stream-ordered here behind every lane's work
+  // Descriptor-set slabs are recycled: a freed slab waits here with the event that marks the end
+  // of all work that could still read it; the next upload of the same size makes its stream wait
+  // on that event (on the device) and reuses the memory -- no allocator call in steady state.
+  struct CachedSlab { void* p; size_t bytes; cudaEvent_t ev; };
+  std::vector<CachedSlab> slab_cache;
+  size_t slab_cache_bytes = 0;
   int sub_batch = 0;  // debug: pairs per tcgen05 launch when pipelining against the rerank
   int use_tc = 1;  // debug switch (slamb200_dbg_set_tc): 0 routes exact-mode pairs to the fp32 kernel
 };
@@ -110,15 +119,21 @@ static int buf_reserve(slamb200_ctx* c, DevBuf& b, size_t bytes, cudaStream_t s)
 }
 
 static int stage_reserve(Lane& L, size_t bytes) {
-  // the previous async copy out of the staging area must have been consumed
-  if (L.stage_free) CU(cudaEventSynchronize(L.stage_free));
-  if (bytes <= L.h_stage_cap) return SLAMB200_OK;
-  if (L.h_stage) CU(cudaFreeHost(L.h_stage));
-  L.h_stage = nullptr;
-  L.h_stage_cap = 0;
-  size_t want = bytes * 2 + 4096;
-  CU(cudaMallocHost(&L.h_stage, want));
-  L.h_stage_cap = want;
+  L.stage_i = (L.stage_i + 1) & 3;
+  Lane::StageSlot& sl = L.stage[L.stage_i];
+  if (!sl.ev) CU(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+  // the copy that last read this slot (four reservations ago) must have been consumed
+  CU(cudaEventSynchronize(sl.ev));
+  if (bytes > sl.cap) {
+    if (sl.p) CU(cudaFreeHost(sl.p));
+    sl.p = nullptr;
+    sl.cap = 0;
+    const size_t want = bytes * 2 + 4096;
+    CU(cudaMallocHost(&sl.p, want));
+    sl.cap = want;
+  }
+  L.h_stage = sl.p;
+  L.stage_free = sl.ev;
   return SLAMB200_OK;
 }
 
@@ -186,7 +201,6 @@ extern "C" int slamb200_init(int device, slamb200_ctx** out) {
   for (int i = 0; i < N_LANES; i++) {
     CU(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->lanes[i].stream2, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&c->lanes[i].stage_free, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->lanes[i].done, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&c->lanes[i].h_small, sizeof(int32_t) * N_SMALL));
   }
@@ -215,15 +229,21 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
     for (DevBuf* b : bufs)
       if (b->p) cudaFreeAsync(b->p, L.stream);
     cudaStreamSynchronize(L.stream);
-    if (L.h_stage) cudaFreeHost(L.h_stage);
+    for (auto& sl : L.stage) {
+      if (sl.p) cudaFreeHost(sl.p);
+      if (sl.ev) cudaEventDestroy(sl.ev);
+    }
     if (L.h_small) cudaFreeHost(L.h_small);
     if (L.h_out) cudaFreeHost(L.h_out);
-    if (L.stage_free) cudaEventDestroy(L.stage_free);
     if (L.done) cudaEventDestroy(L.done);
     for (cudaEvent_t e : L.sub_ev)
       if (e) cudaEventDestroy(e);
     cudaStreamDestroy(L.stream2);
     cudaStreamDestroy(L.stream);
+  }
+  for (auto& e : c->slab_cache) {
+    cudaFree(e.p);
+    cudaEventDestroy(e.ev);
   }
   if (c->free_stream) cudaStreamDestroy(c->free_stream);
   if (c->pool) cudaMemPoolDestroy(c->pool);
@@ -276,6 +296,7 @@ extern "C" int slamb200_profile_read(slamb200_ctx* c, double* ms, int64_t* launc
 }
 
 // ---- descriptor sets ------------------------------------------------------------------------
+static void* slab_from_cache(slamb200_ctx* c, size_t bytes, cudaStream_t s);
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_t row_stride,
@@ -319,7 +340,9 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   }
   DCU(cudaEventCreateWithFlags(&d->ready, cudaEventDisableTiming));
   if (kind == SLAMB200_DESC_U8X32) {
-    if ((rc = dev_alloc(c, &d->slab, (size_t)d->n_pad * 32, s))) goto done;
+    d->slab_bytes = (size_t)d->n_pad * 32;
+    if (!(d->slab = slab_from_cache(c, d->slab_bytes, s)))
+      if ((rc = dev_alloc(c, &d->slab, d->slab_bytes, s))) goto done;
     d->u8 = (uint8_t*)d->slab;
     if (d->n_pad > n) DCU(cudaMemsetAsync(d->u8 + (size_t)n * 32, 0, (size_t)(d->n_pad - n) * 32, s));
     if (n > 0) {
@@ -333,7 +356,9 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
     const size_t o_f32 = 0, o_bf16 = o_f32 + np * 512, o_augq = o_bf16 + np * 256,
                  o_augt = o_augq + np * 32, o_u8 = o_augt + np * 32, o_nrm = o_u8 + np * 128,
                  o_flags = o_nrm + np * 4, total = o_flags + 256;
-    if ((rc = dev_alloc(c, &d->slab, total, s))) goto done;
+    d->slab_bytes = total;
+    if (!(d->slab = slab_from_cache(c, total, s)))
+      if ((rc = dev_alloc(c, &d->slab, total, s))) goto done;
     char* base = (char*)d->slab;
     d->f32 = (float*)(base + o_f32);
     d->bf16 = (__nv_bfloat16*)(base + o_bf16);
@@ -376,7 +401,13 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   }
   DCU(cudaEventRecord(d->ready, s));
   DCU(cudaEventRecord(L.done, s));
-  if (!src_on_device && !no_sync) DCU(cudaStreamSynchronize(s));  // the caller may reuse `rows` on return
+  if (!src_on_device && !no_sync) {
+    // the caller may reuse `rows` on return; the same synchronisation brings the exact-mode flag back
+    if (d->flags) DCU(cudaMemcpyAsync(L.h_small, d->flags, 4, cudaMemcpyDeviceToHost, s));
+    DCU(cudaStreamSynchronize(s));
+    if (d->flags) d->host_exact = L.h_small[0] == 0 ? 1 : 0;
+    d->ready_seen = 1;
+  }
 done:
   if (ev) cudaEventDestroy(ev);
   if (rc != SLAMB200_OK) {
@@ -405,11 +436,38 @@ extern "C" int slamb200_upload_desc_device(slamb200_ctx* c, int kind, const void
 
 // Orders a free behind everything the context has queued so far without blocking the host: the
 // free stream waits (on the device) for every lane's latest work, then releases the memory.
-static void free_behind_lanes(slamb200_ctx* c, void* p, cudaEvent_t ready) {
+static void free_behind_lanes(slamb200_ctx* c, void* p, cudaEvent_t ready, size_t cache_bytes = 0) {
   std::lock_guard<std::mutex> lk(c->free_mu);
   if (ready) cudaStreamWaitEvent(c->free_stream, ready, 0);
   for (int i = 0; i < N_LANES; i++) cudaStreamWaitEvent(c->free_stream, c->lanes[i].done, 0);
+  const size_t kCacheLimit = (size_t)8 << 30;
+  if (cache_bytes > 0 && c->slab_cache_bytes + cache_bytes <= kCacheLimit) {
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventRecord(ev, c->free_stream) == cudaSuccess) {
+      c->slab_cache.push_back({p, cache_bytes, ev});
+      c->slab_cache_bytes += cache_bytes;
+      return;
+    }
+    if (ev) cudaEventDestroy(ev);
+  }
   cudaFreeAsync(p, c->free_stream);
+}
+
+// A recycled slab of exactly `bytes`, ordered behind its previous users on stream s; or nullptr.
+static void* slab_from_cache(slamb200_ctx* c, size_t bytes, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(c->free_mu);
+  for (size_t i = c->slab_cache.size(); i-- > 0;) {
+    if (c->slab_cache[i].bytes == bytes) {
+      slamb200_ctx::CachedSlab e = c->slab_cache[i];
+      c->slab_cache.erase(c->slab_cache.begin() + (long)i);
+      c->slab_cache_bytes -= bytes;
+      cudaStreamWaitEvent(s, e.ev, 0);
+      cudaEventDestroy(e.ev);
+      return e.p;
+    }
+  }
+  return nullptr;
 }
 
 extern "C" int slamb200_free_desc(slamb200_ctx* c, slamb200_desc* d) {
@@ -419,7 +477,7 @@ extern "C" int slamb200_free_desc(slamb200_ctx* c, slamb200_desc* d) {
   // Work this context queued that may still read the set drains first (stream-ordered, the host
   // does not wait).  Work the caller queued on its own streams through the *_enqueue entry
   // points must have been recorded by them (it is: every enqueue records the lane's event).
-  if (d->slab) free_behind_lanes(c, d->slab, d->ready);
+  if (d->slab) free_behind_lanes(c, d->slab, d->ready, d->slab_bytes);
   if (d->ready) cudaEventDestroy(d->ready);
   free(d);
   return SLAMB200_OK;
@@ -509,8 +567,21 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   CU(cudaMemsetAsync(L.err_flag.p, 0, 4096, s));
 
   // the descriptor sets must have finished their prep kernels
-  CU(cudaStreamWaitEvent(s, q->ready, 0));
-  for (int p = 0; p < n_pairs; p++) CU(cudaStreamWaitEvent(s, trains[p]->ready, 0));
+  {
+    auto wait_ready = [&](const slamb200_desc* d) -> cudaError_t {
+      slamb200_desc* m = const_cast<slamb200_desc*>(d);
+      if (m->ready_seen) return cudaSuccess;
+      if (cudaEventQuery(d->ready) == cudaSuccess) { m->ready_seen = 1; return cudaSuccess; }
+      cudaGetLastError();
+      return cudaStreamWaitEvent(s, d->ready, 0);
+    };
+    CU(wait_ready(q));
+    for (int p = 0; p < n_pairs; p++) CU(wait_ready(trains[p]));
+  }
+  // the exact fp32 kernel is not even launched when every set is known (on the host) to be in
+  // exact mode; sets whose flag has not been read back yet leave the decision to the device
+  bool all_exact_known = !orb && q->host_exact == 1;
+  for (int p = 0; p < n_pairs && all_exact_known; p++) all_exact_known = trains[p]->host_exact == 1;
 
   if (orb) {
     ProfScope ps(c, s, SLAMB200_K_ORB);
@@ -522,8 +593,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     // host synchronisation is needed to pick the path.
     // every (pair, split, row) record starts "absent"; the exact kernel and the rerank fill in
     // the ones they own
-    if (c->use_tc) CU(cudaMemsetAsync(L.part.p, 0xFF, sizeof(uint4) * rows * n_split, s));
-    {
+    if (!(c->use_tc && all_exact_known)) {
       ProfScope ps(c, s, SLAMB200_K_SIFT_EXACT);
       launch_sift_exact_knn2(q->f32, q->flags, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split,
                              (uint4*)L.part.p, c->use_tc ? 0 : 1, s);
@@ -569,7 +639,15 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       CU(cudaMemcpyAsync(L.tcpairs.p, tp, sizeof(TcPair) * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
       CU(cudaMemcpyAsync(L.tile_prefix.p, pre, sizeof(int32_t) * (size_t)(n_pairs + 1), cudaMemcpyHostToDevice, s));
       CU(cudaEventRecord(L.stage_free, s));
-      CU(cudaMemsetAsync(L.cand.p, 0xFF, cand_bytes, s));
+      // Slots are normally all written by the kernel (the merge pass computes which ones exist).
+      // Only when a frame pair has fewer tiles than CTA pairs do empty shares leave holes between
+      // written slots: clear the records then (small or ragged batches only).
+      bool holes = false;
+      for (int p = 0; p < n_pairs; p++) {
+        const int nt = pre[p + 1] - pre[p];
+        if (nt > 0 && nt < n_cta) holes = true;
+      }
+      if (holes) CU(cudaMemsetAsync(L.cand.p, 0xFF, cand_bytes, s));
       if ((rc = buf_reserve(c, L.work, sizeof(uint4) * rows, s))) return rc;
       if ((rc = buf_reserve(c, L.work_v0, sizeof(float) * rows, s))) return rc;
       // Sub-batch pipeline: the tcgen05 kernel of sub-batch k+1 runs on `s` while the rerank and
@@ -611,7 +689,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         }
         {
           ProfScope ps(c, s2, SLAMB200_K_SIFT_RERANK);
-          launch_sift_rerank(q->u8, q->nrm2, nq, tcp, np, n_slots, n_split, cand_k, part_k,
+          launch_sift_rerank(q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, n_cta, n_slots, n_split, cand_k, part_k,
                              (uint4*)L.work.p + (size_t)p0 * nq, (float*)L.work_v0.p + (size_t)p0 * nq,
                              (int32_t*)L.err_flag.p + 1 + (k < 1000 ? k : 1000), (int32_t*)L.err_flag.p,
                              want_knn ? 0 : 1, ratio, s2);

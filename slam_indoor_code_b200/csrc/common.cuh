@@ -35,8 +35,10 @@ struct slamb200_desc {
   int32_t* nrm2;
   int32_t* flags;      // device
   int host_exact;      // -2 unknown, else 1 when flags[0] == 0
+  int ready_seen;      // the ready event has been observed complete (no more stream waits)
   cudaEvent_t ready;   // recorded after the prep kernels
   void* slab;          // the one device allocation all the pointers above live in
+  size_t slab_bytes;
   alignas(64) unsigned char tmaps[384];  // host copies of 3 CUtensorMaps: main, augq, augt
 };
 
@@ -115,8 +117,9 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_fl
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
                               int32_t* err_flag, float* dbg, cudaStream_t s);
-void launch_sift_rerank(const uint8_t* q_u8, const int32_t* q_nrm2, int nq, const TcPair* pairs_dev,
-                        int n_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
+void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
+                        const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                        int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                         uint4* work, float* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
                         double ratio, cudaStream_t s);
 

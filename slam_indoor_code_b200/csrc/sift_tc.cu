@@ -578,9 +578,11 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
 struct RerankParams {
   const uint8_t* q_u8;
   const int32_t* q_nrm2;
+  const int32_t* q_flags;
   const TcPair* pairs;
+  const int32_t* tile_prefix;
   const uint4* cand;
-  int nq, nq_pad, n_slots, n_pairs, n_split;
+  int nq, nq_pad, n_slots, n_pairs, n_split, n_cta;
   int prune;         // 1: rows that cannot pass the ratio test skip the exact evaluation
   double ratio;
   uint4* part;       // [pair][n_split][nq]: split 0 gets the record (pre-set to "absent")
@@ -606,13 +608,34 @@ __device__ __forceinline__ bool lt_fi(float va, int ia, float vb, int ib) {
 // reaches the same verdict with the same arithmetic.  Rows that survive go to the work list.
 // General-float pairs have no slot records (the tcgen05 kernel skipped them) and are left alone.
 __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
+  __shared__ int n_valid_s;
   const int pair = blockIdx.y;
-  const int q = blockIdx.x * 256 + threadIdx.x;
+  const int q = blockIdx.x * 256 + threadIdx.x;   // one block = one 256-row query block
+  // general-float pair: its records belong to the exact fp32 kernel (block-uniform exit)
+  if (R.q_flags[0] != 0 || R.pairs[pair].t_flags[0] != 0) return;
+  if (threadIdx.x == 0) {
+    // Which slots did the tcgen05 kernel write for this (pair, query block)?  Slot 2*ord + half,
+    // ord = position of the writing share among the shares that cut the block's tile range --
+    // the same arithmetic as the kernel's flush, so no slot needs to be pre-cleared.
+    const int n_tiles = R.tile_prefix[pair + 1] - R.tile_prefix[pair];
+    int nv = 0;
+    if (n_tiles > 0) {
+      const int n_rb = R.nq_pad / 256;
+      const int n_cb = n_tiles / n_rb;
+      const int first = owner_cta(n_tiles, R.n_cta, blockIdx.x * n_cb);
+      const int last = owner_cta(n_tiles, R.n_cta, (blockIdx.x + 1) * n_cb - 1);
+      nv = 2 * (last - first + 1);
+      if (nv > R.n_slots) nv = R.n_slots;  // cannot happen (host sizing); the self check would trip
+    }
+    n_valid_s = nv;
+  }
+  __syncthreads();
+  const int n_valid = n_valid_s;
   bool survive = false;
   float v0 = __int_as_float(0x7f800000), v1 = v0;
   int g0 = 0x7fffffff, g1 = 0x7fffffff;
   if (q < R.nq) {
-    for (int s = 0; s < R.n_slots; s++) {
+    for (int s = 0; s < n_valid; s++) {
       const uint4 rec = R.cand[((size_t)pair * R.n_slots + s) * R.nq_pad + q];
       const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.z);
       const int ia = (int)rec.y, ib = (int)rec.w;
@@ -626,6 +649,9 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
       }
     }
     const bool has0 = g0 != 0x7fffffff, has1 = g1 != 0x7fffffff;
+    const uint4 none = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+    for (int sp = 1; sp < R.n_split; sp++) R.part[((size_t)pair * R.n_split + sp) * R.nq + q] = none;
+    if (!has0) R.part[((size_t)pair * R.n_split) * R.nq + q] = none;  // empty train set
     survive = has0;
     if (R.prune && has0 && has1) {
       const float d0 = sqrtf(2.0f * v0), D1 = sqrtf(2.0f * v1);
@@ -832,13 +858,15 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_fl
   return 0;
 }
 
-void launch_sift_rerank(const uint8_t* q_u8, const int32_t* q_nrm2, int nq, const TcPair* pairs_dev,
-                        int n_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
+void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
+                        const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                        int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                         uint4* work, float* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
                         double ratio, cudaStream_t s) {
   if (nq <= 0 || n_pairs <= 0) return;
   RerankParams R;
-  R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.pairs = pairs_dev; R.cand = cand;
+  R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
+  R.tile_prefix = tile_prefix_dev; R.n_cta = n_cta_pairs;
   R.nq = nq; R.nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM); R.n_slots = n_slots; R.n_pairs = n_pairs;
   R.n_split = n_split; R.part = part; R.err_flag = err_flag;
   R.work = work; R.work_v0 = work_v0; R.work_n = work_n;

@@ -22,7 +22,7 @@ for it in range(4):
           f"matchBatch {1e3*(t3-t2):.1f} ms, free {1e3*(t4-t3):.1f} ms, total {1e3*(t4-t0):.1f} ms", flush=True)
 # matchBatch split: enqueue / fetch
 Q = ctx.upload_pinned(q); Ts = [ctx.upload_pinned(t) for t in trains]; ctx.synchronize()
-st = torch.cuda.current_stream().cuda_stream
+_ts = torch.cuda.Stream(); torch.cuda.set_stream(_ts); st = _ts.cuda_stream
 for it in range(3):
     t0 = time.perf_counter()
     ctx.matchBatchEnqueue(Q, Ts, MatcherType.SIFT_BF, 0.7, st)

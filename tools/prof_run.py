@@ -9,7 +9,7 @@ from slam_indoor_code_b200 import camera_translation as ct
 which = sys.argv[1] if len(sys.argv) > 1 else "sift"
 torch.zeros(1, device="cuda")
 ctx = Context(0)
-st = torch.cuda.current_stream().cuda_stream
+_ts = torch.cuda.Stream(); torch.cuda.set_stream(_ts); st = _ts.cuda_stream
 if which == "sift":
     q = synth.sift_like(10000, 3000)
     Q = ctx.upload(q)

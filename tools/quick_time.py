@@ -17,7 +17,7 @@ def ev_time(fn, iters=20, warm=3):
 
 torch.cuda.init(); torch.zeros(1, device="cuda")
 ctx = Context(0)
-st = torch.cuda.current_stream().cuda_stream
+_ts = torch.cuda.Stream(); torch.cuda.set_stream(_ts); st = _ts.cuda_stream
 which = sys.argv[1:] or ["orb", "sift", "siftf", "ransac", "batch"]
 if "orb" in which:
     q, t = synth.orb_pair(10000, 10000, 2001)

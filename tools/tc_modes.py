@@ -6,7 +6,7 @@ from oracle import synth
 from slam_indoor_code_b200.feature_matching import Context, MatcherType
 torch.zeros(1, device="cuda")
 ctx = Context(0); lib = ctx._lib
-st = torch.cuda.current_stream().cuda_stream
+_ts = torch.cuda.Stream(); torch.cuda.set_stream(_ts); st = _ts.cuda_stream
 q = synth.sift_like(10000, 3000)
 Q = ctx.upload(q)
 NP = int(sys.argv[1]) if len(sys.argv) > 1 else 32
