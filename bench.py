@@ -318,7 +318,9 @@ def run_b200(args, rank, world, local):
                                               if k != "sift_tc" and v[1] > 0},
                 "kernel_share_of_step": tc_ms / ms_total
                 if world == 1 else None,
-                "traffic": TRAFFIC_BYTES_PER_LAUNCH}
+                "traffic": TRAFFIC_BYTES_PER_LAUNCH_N1 if world == 1 else None,
+                "traffic_note": "ncu capture of the N=1 launch (profiles/r01_ncu_sift_tc_final.txt); "
+                                "compulsory bytes 818 MB"}
 
     # ---- e2e through the C ABI with host buffers -------------------------------------------------
     for t in Ts:
@@ -335,7 +337,7 @@ def run_b200(args, rank, world, local):
     # so one thread's matching overlaps the other threads' uploads.
     from concurrent.futures import ThreadPoolExecutor
     from slam_indoor_code_b200._capi import DMATCH
-    n_workers, chunk = 3, 24
+    n_workers, chunk = args.e2e_workers, args.e2e_chunk
     chunks = [list(range(i, min(i + chunk, len(trains)))) for i in range(0, len(trains), chunk)]
     out_buf = np.empty((max(len(trains), 1), N_ROWS), DMATCH)      # caller-owned, reused per step
     n_buf = np.zeros(max(len(trains), 1), np.int32)
@@ -396,6 +398,8 @@ def run_b200(args, rank, world, local):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(q, trains, matches, args.cpu_seconds)
+            if not args.no_extras:
+                line["cpu_baseline"]["other_configs"] = cpu_extras()
         if world == 1 and not args.no_extras:
             line["extras"] = extras(ctx, stream)
         emit(line)
@@ -404,9 +408,11 @@ def run_b200(args, rank, world, local):
         dist.destroy_process_group()
 
 
-# dram bytes of the tcgen05 kernel per launch from the committed ncu capture (profiles/); null
-# until a capture of this exact kernel version exists.
-TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one tcgen05-kernel launch over the 210-pair window
+# (N=1), from the committed `ncu --set full` capture profiles/r01_ncu_sift_tc_final.txt:
+# 622.6 MB read + 183.3 MB written.  Compulsory bytes of that launch: 211 descriptor sets x 2.9 MB
+# of bf16 operands + 206 MB of slot records = 818 MB, i.e. no re-reads.
+TRAFFIC_BYTES_PER_LAUNCH_N1 = 805_879_296
 
 
 def cpu_baseline(q, trains, gpu_matches, seconds):
@@ -467,7 +473,73 @@ def extras(ctx, stream):
     kms, kn = ctx.profile_read()["ransac"]
     ctx.profile_enable(False)
     out["cfg5_ransac_2048x5000"] = {"kernel_us_per_pair": kms / kn / P * 1e3,
-                                    "fp64_tflops_40flop_convention": P * 2048 * 5000 * 40 / (kms / kn) / 1e9}
+                                    "fp64_tflops_40flop_convention": P * 2048 * 5000 * 40 / (kms / kn) / 1e9,
+                                    "dp_instr_per_s_T": P * 2048 * 5000 * 36 / (kms / kn) / 1e9}
+    # pipe-rate denominators measured on this box (csrc/microbench.cu)
+    try:
+        import ctypes
+        lib = ctx._lib
+        lib.slamb200_dbg_pipe_rate.restype = ctypes.c_double
+        lib.slamb200_dbg_pipe_rate.argtypes = [ctypes.c_int]
+        popc, fp64 = lib.slamb200_dbg_pipe_rate(0), lib.slamb200_dbg_pipe_rate(1)
+        out["pipe_rates"] = {"popc_G_per_s": popc, "fp64_dmul_dadd_G_per_s": fp64}
+        out["cfg2_orb_16_pairs"]["frac_of_popc_pipe"] = out["cfg2_orb_16_pairs"]["tpopc_per_s"] * 1e3 / popc
+        out["cfg5_ransac_2048x5000"]["frac_of_fp64_pipe"] = \
+            out["cfg5_ransac_2048x5000"]["dp_instr_per_s_T"] * 1e3 / fp64
+    except Exception as e:  # pragma: no cover
+        out["pipe_rates"] = {"error": str(e)}
+    # cfg4: 8 frames x 50,000 descriptors (4K frames), all 28 i<j pairs of the BA window
+    frames = [ctx.upload(synth.sift_like(50000, 4000 + f)) for f in range(8)]
+    for _ in range(2):
+        ctx.matchWindow(frames, MatcherType.SIFT_BF, RATIO)
+    t0 = time.perf_counter()
+    res = ctx.matchWindow(frames, MatcherType.SIFT_BF, RATIO)
+    dt = time.perf_counter() - t0
+    out["cfg4_window_8x50k"] = {"ms_per_window_host_call": dt * 1e3, "pairs": len(res),
+                                "tflops_incl_copies": len(res) * 2 * 50000.0 * 50000 * 128 / dt / 1e12}
+    for f in frames:
+        f.free()
+    return out
+
+
+def cpu_extras():
+    """CPU OpenCV timings of the other configs, bounded to a few seconds."""
+    out = {}
+    try:
+        import cv2
+    except Exception:
+        return {"unavailable": "cv2 not importable"}
+    from oracle import synth
+    cv2.setNumThreads(os.cpu_count() or 1)
+    out["cores"] = int(cv2.getNumThreads())
+
+    def best(fn, n=3):
+        b = 1e9
+        for _ in range(n):
+            t0 = time.perf_counter()
+            r = fn()
+            b = min(b, time.perf_counter() - t0)
+        return b, r
+
+    q, t = synth.orb_pair(N_ROWS, N_ROWS, 2001)
+    dt, _ = best(lambda: cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, 2))
+    out["cfg2_orb_bf_hamming_s_per_pair"] = dt
+    q, t = synth.sift_pair(N_ROWS, N_ROWS, 1001)
+    dt_bf, bf = best(lambda: cv2.BFMatcher(cv2.NORM_L2).knnMatch(q, t, 2), 2)
+    dt_fl, fl = best(lambda: cv2.FlannBasedMatcher().knnMatch(q, t, 2), 2)
+    top1 = np.mean([a[0].trainIdx == b[0].trainIdx for a, b in zip(bf, fl)])
+    good_bf = {(m[0].queryIdx, m[0].trainIdx) for m in bf if m[0].distance < RATIO * m[1].distance}
+    good_fl = {(m[0].queryIdx, m[0].trainIdx) for m in fl if m[0].distance < RATIO * m[1].distance}
+    out["cfg1_sift_bf_s_per_pair"] = dt_bf
+    out["flann"] = {"s_per_pair": dt_fl, "top1_recall_vs_bf": float(top1),
+                    "accepted_match_recall_vs_bf": len(good_bf & good_fl) / max(len(good_bf), 1),
+                    "note": "the reference's useFM-SIFT-FLANN path (approximate); this repo answers "
+                            "that flag with the exact search, recall 1.0 by construction"}
+    p1, p2, _, _ = synth.two_view(5000, 5000)
+    K4 = synth.SAMSUNG_HV_4K
+    Kmat = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]])
+    dt, _ = best(lambda: cv2.findEssentialMat(p1, p2, Kmat, cv2.RANSAC, 0.999, 5.0), 5)
+    out["cfg5_findEssentialMat_s_per_pair"] = dt
     return out
 
 
@@ -485,6 +557,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-workers", type=int, default=4, help="host threads of the e2e pipeline")
+    ap.add_argument("--e2e-chunk", type=int, default=18, help="train frames per e2e chunk")
     ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the CPU arm")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

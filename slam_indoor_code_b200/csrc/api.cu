@@ -42,7 +42,7 @@ struct DevBuf {
   size_t cap = 0;
 };
 
-#define N_LANES 4
+#define N_LANES 8
 
 struct Lane {
   cudaStream_t stream = nullptr;

@@ -50,9 +50,15 @@ constexpr int N_ASTAGE = 2;
 constexpr int N_BSTAGE = 4;
 constexpr int SMEM_BARS = 1024;
 constexpr int SMEM_BYTES = (N_ASTAGE + N_BSTAGE) * STAGE + SMEM_BARS + 1024;
-constexpr int TC_THREADS = 384;     // 12 warps
 constexpr int EPI_WARP0 = 4;
-constexpr int N_EPI_WARPS = 8;
+#ifndef SLAMB200_EPI_WARPS
+#define SLAMB200_EPI_WARPS 8   // 16 was measured slower (19.0 vs 17.2 us/pair): register cap + barrier traffic
+#endif
+constexpr int N_EPI_WARPS = SLAMB200_EPI_WARPS;       // 8 or 16
+constexpr int TC_THREADS = (EPI_WARP0 + N_EPI_WARPS) * 32;
+constexpr int COL_SPLITS = N_EPI_WARPS / 4;            // column ranges per row (2 halves / 4 quarters)
+constexpr int COLS_PER_WARP = BN / COL_SPLITS;         // 128 or 64
+constexpr int CHUNKS = COLS_PER_WARP / 32;             // 32-column tcgen05.ld chunks per tile per warp
 constexpr int GROUP = 8;            // columns per candidate group
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared address
 
@@ -469,7 +475,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     // ================= epilogue (both CTAs; each drains its own TMEM) =================
     const int ew = warp - EPI_WARP0;
     const int quarter = ew & 3;   // TMEM lane quarter this warp may read
-    const int half = ew >> 2;     // which 128 columns of the tile
+    const int half = ew >> 2;     // which column range of the tile (COLS_PER_WARP wide)
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int row_in_tile = (int)rank * BM + quarter * 32 + lane;  // within the pair's 256 rows
     TileIter it;
@@ -494,53 +500,41 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       }
       mbar_wait(t_full + 8 * t_stage, t_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + lane_addr + t_stage * BN + half * 128;
-      const int gid_tile = (it.cb * BN + half * 128) / GROUP;
+      const uint32_t t_addr = tmem_base + lane_addr + t_stage * BN + half * COLS_PER_WARP;
+      const int gid_tile = (it.cb * BN + half * COLS_PER_WARP) / GROUP;
       const bool dump = DBG && first_tile && pair_id == 0;
-      uint32_t va[32] = {}, vb[32] = {};
-      if (P.mode < 2) {
-        TMEM_LD32(t_addr, va);
-        TMEM_WAIT32(va);
-        TMEM_LD32(t_addr + 32, vb);
-      }
-      if (dump) {
+      uint32_t va[32], vb[32];  // (timing modes >= 2 read them uninitialised: results are void there)
+      if (P.mode < 2) TMEM_LD32(t_addr, va);
 #pragma unroll
-        for (int j = 0; j < 32; j++)
-          P.dbg[(size_t)row_in_tile * BN + half * 128 + j] = __uint_as_float(va[j]);
-      }
-      if (P.mode < 1) process_chunk(va, gid_tile + 0, m1, i1, m2, i2);
-      if (P.mode < 2) {
-        TMEM_WAIT32(vb);
-        TMEM_LD32(t_addr + 64, va);
-      }
-      if (dump) {
+      for (int c = 0; c < CHUNKS; c += 2) {
+        if (P.mode < 2) {
+          TMEM_WAIT32(va);
+          TMEM_LD32(t_addr + 32 * (c + 1), vb);
+        }
+        if (dump) {
 #pragma unroll
-        for (int j = 0; j < 32; j++)
-          P.dbg[(size_t)row_in_tile * BN + half * 128 + 32 + j] = __uint_as_float(vb[j]);
-      }
-      if (P.mode < 1) process_chunk(vb, gid_tile + 4, m1, i1, m2, i2);
-      if (P.mode < 2) {
-        TMEM_WAIT32(va);
-        TMEM_LD32(t_addr + 96, vb);
-      }
-      if (dump) {
+          for (int j = 0; j < 32; j++)
+            P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * c + j] = __uint_as_float(va[j]);
+        }
+        if (P.mode < 1) process_chunk(va, gid_tile + 4 * c, m1, i1, m2, i2);
+        if (P.mode < 2) {
+          TMEM_WAIT32(vb);
+          if (c + 2 < CHUNKS) TMEM_LD32(t_addr + 32 * (c + 2), va);
+        }
+        if (c + 2 >= CHUNKS) {
+          // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+          // (the leader's barrier counts the epilogue warps of both CTAs)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(t_empty + 8 * t_stage, 0);
+        }
+        if (dump) {
 #pragma unroll
-        for (int j = 0; j < 32; j++)
-          P.dbg[(size_t)row_in_tile * BN + half * 128 + 64 + j] = __uint_as_float(va[j]);
+          for (int j = 0; j < 32; j++)
+            P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * (c + 1) + j] = __uint_as_float(vb[j]);
+        }
+        if (P.mode < 1) process_chunk(vb, gid_tile + 4 * (c + 1), m1, i1, m2, i2);
       }
-      if (P.mode < 1) process_chunk(va, gid_tile + 8, m1, i1, m2, i2);
-      if (P.mode < 2) { TMEM_WAIT32(vb); }
-      // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
-      // (the leader's barrier counts the epilogue warps of both CTAs)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(t_empty + 8 * t_stage, 0);
-      if (dump) {
-#pragma unroll
-        for (int j = 0; j < 32; j++)
-          P.dbg[(size_t)row_in_tile * BN + half * 128 + 96 + j] = __uint_as_float(vb[j]);
-      }
-      if (P.mode < 1) process_chunk(vb, gid_tile + 12, m1, i1, m2, i2);
       first_tile = false;
       if (++t_stage == 2) { t_stage = 0; t_phase ^= 1; }
       new_seg = it.next(P);
@@ -548,11 +542,11 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
         // flush this segment's per-row record
         // ordinal of this share among the shares that cut the row block (<= n_slots / 2)
         int ord = seg_c - owner_cta(seg_ntiles, n_pairs_cta, seg_rb * seg_ncb);
-        if (ord < 0 || 2 * ord + 1 >= P.n_slots) {
+        if (ord < 0 || COL_SPLITS * ord + COL_SPLITS - 1 >= P.n_slots) {
           if (lane == 0) atomicOr(P.err_flag, 2);
           ord = 0;
         }
-        const int slot = 2 * ord + half;
+        const int slot = COL_SPLITS * ord + half;
         uint4 rec;
         rec.x = __float_as_uint(m1); rec.y = (uint32_t)i1;
         rec.z = __float_as_uint(m2); rec.w = (uint32_t)i2;
@@ -624,7 +618,7 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
       const int n_cb = n_tiles / n_rb;
       const int first = owner_cta(n_tiles, R.n_cta, blockIdx.x * n_cb);
       const int last = owner_cta(n_tiles, R.n_cta, (blockIdx.x + 1) * n_cb - 1);
-      nv = 2 * (last - first + 1);
+      nv = COL_SPLITS * (last - first + 1);
       if (nv > R.n_slots) nv = R.n_slots;  // cannot happen (host sizing); the self check would trip
     }
     n_valid_s = nv;
@@ -818,7 +812,7 @@ int tc_slots(int n_cb_max, int total_tiles, int n_cta) {
   int segs = (n_cb_max - 1) / tpc + 2;
   if (segs > n_cb_max) segs = n_cb_max;
   if (segs < 1) segs = 1;
-  return 2 * segs;
+  return COL_SPLITS * segs;
 }
 
 int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_flags, int nq,
