@@ -67,6 +67,7 @@ struct Lane {
   // state of the last enqueued batch
   int b_matcher = -1, b_nq = 0, b_pairs = 0, b_cap = 0;
   int s_H = 0, s_pairs = 0;
+  int32_t* status = nullptr;  // device status words of the last batch (inside the table block)
   float* dbg = nullptr;  // debug: raw accumulator dump target of the next tcgen05 launch
 };
 #define N_SMALL 65536
@@ -528,6 +529,13 @@ static int check_matcher(int matcher, const slamb200_desc* q, const slamb200_des
 
 // Queues one (query x n_pairs trains) batch on stream s using lane L's scratch.  Results:
 // L.knn_idx / L.knn_dist [P][nq][2], L.out [P][cap] dmatch, L.n_out [P].
+//
+// Everything the kernels need from the host travels in ONE pinned block and one copy:
+//   [ PairArgs[P] | TcPair[P] | tile_prefix[P+1] | status words (zeroed) ]
+// so a step costs one H2D copy plus the kernels themselves (no memsets, no per-table copies).
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+#define STATUS_BYTES 4096  // [0] self-check flag, [1+k] work-list counts
+
 static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
                          const slamb200_desc* q, const slamb200_desc* const* trains, int n_pairs,
                          double ratio, bool want_knn = false) {
@@ -537,25 +545,71 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   if (n_pairs == 0) return SLAMB200_OK;
   int rc;
   const bool orb = matcher == SLAMB200_ORB_BF;
+  const bool tc = !orb && c->use_tc && nq > 0;
   int t_max = 0;
   for (int p = 0; p < n_pairs; p++) t_max = trains[p]->n > t_max ? trains[p]->n : t_max;
   const int q_blocks = orb ? (nq + 255) / 256 : (nq + 15) / 16;
   const int n_split = pick_splits(q_blocks > 0 ? q_blocks : 1, n_pairs, t_max, orb ? 1024 : 512);
 
-  // pair table -> device
-  if ((rc = stage_reserve(L, sizeof(PairArgs) * (size_t)n_pairs))) return rc;
-  PairArgs* hp = (PairArgs*)L.h_stage;
+  // ---- host tables -----------------------------------------------------------------------
+  const size_t off_pairs = 0;
+  const size_t off_tc = align_up(sizeof(PairArgs) * (size_t)n_pairs, 64);
+  const size_t off_pre = off_tc + (tc ? sizeof(TcPair) * (size_t)n_pairs : 0);
+  const size_t off_status = align_up(off_pre + (tc ? sizeof(int32_t) * (size_t)(n_pairs + 1) : 0), 64);
+  const size_t table_bytes = off_status + STATUS_BYTES;
+  if ((rc = stage_reserve(L, table_bytes))) return rc;
+  char* hb = (char*)L.h_stage;
+  PairArgs* hp = (PairArgs*)(hb + off_pairs);
+  TcPair* tp = (TcPair*)(hb + off_tc);
+  int32_t* pre = (int32_t*)(hb + off_pre);
+  memset(hb + off_status, 0, STATUS_BYTES);
   for (int p = 0; p < n_pairs; p++) {
     hp[p].t_rows = orb ? (const void*)trains[p]->u8 : (const void*)trains[p]->f32;
     hp[p].t_flags = orb ? nullptr : trains[p]->flags;
     hp[p].t_n = trains[p]->n;
     hp[p].t_pad = trains[p]->n_pad;
   }
-  if ((rc = buf_reserve(c, L.pairs, sizeof(PairArgs) * (size_t)n_pairs, s))) return rc;
-  CU(cudaMemcpyAsync(L.pairs.p, hp, sizeof(PairArgs) * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
-  CU(cudaEventRecord(L.stage_free, s));
+  // tcgen05 path geometry: one query block of 256 rows per CTA pair, 256-column train tiles
+  const int n_rb = (nq + 255) / 256;
+  int n_cta = 1, n_slots = 2;
+  bool holes = false;
+  if (tc) {
+    long long total = 0;
+    const int max_pairs = c->n_sm / 2;  // one CTA pair per two SMs
+    int max_tiles = 0;
+    for (int p = 0; p < n_pairs; p++) {
+      const int n_cb = (trains[p]->n + 255) / 256;
+      max_tiles = n_cb * n_rb > max_tiles ? n_cb * n_rb : max_tiles;
+    }
+    n_cta = max_tiles < max_pairs ? (max_tiles > 0 ? max_tiles : 1) : max_pairs;
+    for (int p = 0; p < n_pairs; p++) {
+      memcpy(tp[p].tmap, trains[p]->tmaps, 128);             // main
+      memcpy(tp[p].tmap + 128, trains[p]->tmaps + 256, 128);  // aug, train role
+      tp[p].t_u8 = trains[p]->u8;
+      tp[p].t_nrm2 = trains[p]->nrm2;
+      tp[p].t_flags = trains[p]->flags;
+      tp[p].t_n = trains[p]->n;
+      tp[p].t_pad = trains[p]->n_pad;
+      const int n_cb = (trains[p]->n + 255) / 256;
+      pre[p] = (int32_t)total;
+      total += (long long)n_cb * n_rb;
+      // every CTA pair takes a contiguous share of this frame pair's tiles: how many shares can
+      // cut one row block of n_cb tiles
+      if (n_cb > 0) {
+        const int slots = tc_slots(n_cb, n_cb * n_rb, n_cta);
+        n_slots = slots > n_slots ? slots : n_slots;
+        // fewer tiles than CTA pairs: empty shares leave holes between written slot records
+        if (n_cb * n_rb < n_cta) holes = true;
+      }
+    }
+    pre[n_pairs] = (int32_t)total;
+    if (total > 0x7fffffffLL) return fail(SLAMB200_ERR_INVALID, "batch too large (tile count)");
+  }
 
+  // ---- device scratch ----------------------------------------------------------------------
   const size_t rows = (size_t)n_pairs * cap;
+  const size_t cand_bytes = tc ? sizeof(uint4) * (size_t)n_pairs * n_slots * (size_t)n_rb * 256 : 0;
+  if ((rc = buf_reserve(c, L.pairs, table_bytes, s))) return rc;
   if ((rc = buf_reserve(c, L.part, sizeof(uint4) * rows * n_split, s))) return rc;
   if ((rc = buf_reserve(c, L.knn_idx, sizeof(int32_t) * rows * 2, s))) return rc;
   if ((rc = buf_reserve(c, L.knn_dist, sizeof(float) * rows * 2, s))) return rc;
@@ -563,8 +617,19 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   if ((rc = buf_reserve(c, L.chunk_cnt, sizeof(int32_t) * (size_t)n_pairs * (finalize_chunks(cap) + 1), s))) return rc;
   if ((rc = buf_reserve(c, L.out, sizeof(slamb200_dmatch) * rows, s))) return rc;
   if ((rc = buf_reserve(c, L.n_out, sizeof(int32_t) * (size_t)n_pairs, s))) return rc;
-  if ((rc = buf_reserve(c, L.err_flag, 4096, s))) return rc;  // [0] self-check flag, [1+k] work counts
-  CU(cudaMemsetAsync(L.err_flag.p, 0, 4096, s));
+  if (tc) {
+    if ((rc = buf_reserve(c, L.cand, cand_bytes, s))) return rc;
+    if ((rc = buf_reserve(c, L.work, sizeof(uint4) * rows, s))) return rc;
+    if ((rc = buf_reserve(c, L.work_v0, sizeof(float) * rows, s))) return rc;
+  }
+  char* db = (char*)L.pairs.p;
+  const PairArgs* d_pairs = (const PairArgs*)(db + off_pairs);
+  const TcPair* d_tc = (const TcPair*)(db + off_tc);
+  const int32_t* d_pre = (const int32_t*)(db + off_pre);
+  int32_t* d_status = (int32_t*)(db + off_status);
+  L.status = d_status;
+  CU(cudaMemcpyAsync(db, hb, table_bytes, cudaMemcpyHostToDevice, s));
+  CU(cudaEventRecord(L.stage_free, s));
 
   // the descriptor sets must have finished their prep kernels
   {
@@ -585,78 +650,24 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
 
   if (orb) {
     ProfScope ps(c, s, SLAMB200_K_ORB);
-    launch_orb_knn2(q->u8, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split, (uint4*)L.part.p, s);
+    launch_orb_knn2(q->u8, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p, s);
   } else {
     // General-float pairs: exact fp32 kernel (it skips exact-mode pairs unless force).  Exact-mode
     // pairs (integer-valued descriptors, what cv::SIFT emits): tcgen05 candidates + dp4a rerank
     // (those kernels skip the general-float pairs).  Both read the flags on the device, so no
     // host synchronisation is needed to pick the path.
-    // every (pair, split, row) record starts "absent"; the exact kernel and the rerank fill in
-    // the ones they own
-    if (!(c->use_tc && all_exact_known)) {
+    if (!(tc && all_exact_known)) {
       ProfScope ps(c, s, SLAMB200_K_SIFT_EXACT);
-      launch_sift_exact_knn2(q->f32, q->flags, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split,
-                             (uint4*)L.part.p, c->use_tc ? 0 : 1, s);
+      launch_sift_exact_knn2(q->f32, q->flags, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p,
+                             c->use_tc ? 0 : 1, s);
     }
-    if (c->use_tc && nq > 0) {
-      const int n_rb = (nq + 255) / 256;  // one query block per CTA pair
-      if ((rc = stage_reserve(L, (sizeof(TcPair) + sizeof(int32_t)) * (size_t)(n_pairs + 1)))) return rc;
-      TcPair* tp = (TcPair*)L.h_stage;
-      int32_t* pre = (int32_t*)(tp + n_pairs);
-      long long total = 0;
-      const int max_pairs = c->n_sm / 2;  // one CTA pair per two SMs
-      int max_tiles = 0;
-      for (int p = 0; p < n_pairs; p++) {
-        const int n_cb = (trains[p]->n + 255) / 256;
-        max_tiles = n_cb * n_rb > max_tiles ? n_cb * n_rb : max_tiles;
-      }
-      const int n_cta = max_tiles < max_pairs ? (max_tiles > 0 ? max_tiles : 1) : max_pairs;
-      int n_slots = 2;
-      for (int p = 0; p < n_pairs; p++) {
-        memcpy(tp[p].tmap, trains[p]->tmaps, 128);             // main
-        memcpy(tp[p].tmap + 128, trains[p]->tmaps + 256, 128);  // aug, train role
-        tp[p].t_u8 = trains[p]->u8;
-        tp[p].t_nrm2 = trains[p]->nrm2;
-        tp[p].t_flags = trains[p]->flags;
-        tp[p].t_n = trains[p]->n;
-        tp[p].t_pad = trains[p]->n_pad;
-        const int n_cb = (trains[p]->n + 255) / 256;
-        pre[p] = (int32_t)total;
-        total += (long long)n_cb * n_rb;
-        // every CTA pair takes a contiguous share of this frame pair's tiles: how many shares
-        // can cut one row block of n_cb tiles
-        if (n_cb > 0) {
-          const int slots = tc_slots(n_cb, n_cb * n_rb, n_cta);
-          n_slots = slots > n_slots ? slots : n_slots;
-        }
-      }
-      pre[n_pairs] = (int32_t)total;
-      if (total > 0x7fffffffLL) return fail(SLAMB200_ERR_INVALID, "batch too large (tile count)");
-      const size_t cand_bytes = sizeof(uint4) * (size_t)n_pairs * n_slots * (size_t)n_rb * 256;
-      if ((rc = buf_reserve(c, L.tcpairs, sizeof(TcPair) * (size_t)n_pairs, s))) return rc;
-      if ((rc = buf_reserve(c, L.tile_prefix, sizeof(int32_t) * (size_t)(n_pairs + 1), s))) return rc;
-      if ((rc = buf_reserve(c, L.cand, cand_bytes, s))) return rc;
-      CU(cudaMemcpyAsync(L.tcpairs.p, tp, sizeof(TcPair) * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
-      CU(cudaMemcpyAsync(L.tile_prefix.p, pre, sizeof(int32_t) * (size_t)(n_pairs + 1), cudaMemcpyHostToDevice, s));
-      CU(cudaEventRecord(L.stage_free, s));
-      // Slots are normally all written by the kernel (the merge pass computes which ones exist).
-      // Only when a frame pair has fewer tiles than CTA pairs do empty shares leave holes between
-      // written slots: clear the records then (small or ragged batches only).
-      bool holes = false;
-      for (int p = 0; p < n_pairs; p++) {
-        const int nt = pre[p + 1] - pre[p];
-        if (nt > 0 && nt < n_cta) holes = true;
-      }
+    if (tc) {
+      // Slot records are normally all written by the kernel (the merge pass computes which ones
+      // exist); only the hole case needs them cleared (small or ragged batches).
       if (holes) CU(cudaMemsetAsync(L.cand.p, 0xFF, cand_bytes, s));
-      if ((rc = buf_reserve(c, L.work, sizeof(uint4) * rows, s))) return rc;
-      if ((rc = buf_reserve(c, L.work_v0, sizeof(float) * rows, s))) return rc;
-      // Sub-batch pipeline: the tcgen05 kernel of sub-batch k+1 runs on `s` while the rerank and
-      // the finalize kernels of sub-batch k run on the lane's second stream.  The tensor-core
-      // kernel leaves registers, threads and issue slots free on every SM, so the L2-bound rerank
-      // co-resides with it instead of extending the step.
-      // (measured: with the 40-candidate rerank the two sides contend for the same SM issue
-      // slots and the step does not get shorter, so the default is one sub-batch; the knob stays
-      // for experiments: slamb200_dbg_set_sub_batch)
+      // Sub-batch pipeline (debug knob, default one sub-batch): the tcgen05 kernel of sub-batch
+      // k+1 on `s` against the rerank / finalize kernels of sub-batch k on the lane's second
+      // stream.  Measured: no gain (both sides contend for the same SM issue slots).
       const int sub = (c->sub_batch > 0 && c->sub_batch < n_pairs) ? c->sub_batch : n_pairs;
       const int n_sub = (n_pairs + sub - 1) / sub;
       if ((int)L.sub_ev.size() < n_sub + 1) {
@@ -671,8 +682,8 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       for (int k = 0; k < n_sub; k++) {
         const int p0 = k * sub;
         const int np = n_pairs - p0 < sub ? n_pairs - p0 : sub;
-        const TcPair* tcp = (const TcPair*)L.tcpairs.p + p0;
-        const int32_t* pre_k = (const int32_t*)L.tile_prefix.p + p0;
+        const TcPair* tcp = d_tc + p0;
+        const int32_t* pre_k = d_pre + p0;
         const int tiles_k = pre[p0 + np] - pre[p0];
         uint4* cand_k = (uint4*)L.cand.p + (size_t)p0 * cand_per_pair;
         uint4* part_k = (uint4*)L.part.p + (size_t)p0 * n_split * nq;
@@ -680,7 +691,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         {
           ProfScope ps(c, s, SLAMB200_K_SIFT_TC);
           trc = launch_sift_tc_candidates(q->tmaps, q->flags, nq, tcp, pre_k, np, tiles_k, n_cta,
-                                          n_slots, cand_k, (int32_t*)L.err_flag.p, k == 0 ? L.dbg : nullptr, s);
+                                          n_slots, cand_k, d_status, k == 0 ? L.dbg : nullptr, s);
         }
         if (trc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
         if (s2 != s) {
@@ -689,13 +700,13 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         }
         {
           ProfScope ps(c, s2, SLAMB200_K_SIFT_RERANK);
-          launch_sift_rerank(q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, n_cta, n_slots, n_split, cand_k, part_k,
-                             (uint4*)L.work.p + (size_t)p0 * nq, (float*)L.work_v0.p + (size_t)p0 * nq,
-                             (int32_t*)L.err_flag.p + 1 + (k < 1000 ? k : 1000), (int32_t*)L.err_flag.p,
-                             want_knn ? 0 : 1, ratio, s2);
+          launch_sift_rerank(q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, n_cta, n_slots, n_split,
+                             cand_k, part_k, (uint4*)L.work.p + (size_t)p0 * nq,
+                             (float*)L.work_v0.p + (size_t)p0 * nq, d_status + 1 + (k < 1000 ? k : 1000),
+                             d_status, want_knn ? 0 : 1, ratio, s2);
         }
         ProfScope psf(c, s2, SLAMB200_K_FINALIZE);
-        launch_finalize(part_k, nq, (const PairArgs*)L.pairs.p + p0, np, n_split, 0, ratio,
+        launch_finalize(part_k, nq, d_pairs + p0, np, n_split, 0, ratio,
                         (int32_t*)L.knn_idx.p + (size_t)p0 * nq * 2,
                         (float*)L.knn_dist.p + (size_t)p0 * nq * 2, (uint8_t*)L.flags.p + (size_t)p0 * nq,
                         (int32_t*)L.chunk_cnt.p + (size_t)p0 * chunks,
@@ -711,10 +722,9 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     }
   }
   CU(cudaGetLastError());
-  launch_finalize((const uint4*)L.part.p, nq, (const PairArgs*)L.pairs.p, n_pairs, n_split,
-                  orb ? 1 : 0, ratio, (int32_t*)L.knn_idx.p, (float*)L.knn_dist.p,
-                  (uint8_t*)L.flags.p, (int32_t*)L.chunk_cnt.p, (slamb200_dmatch*)L.out.p, cap,
-                  (int32_t*)L.n_out.p, s);
+  launch_finalize((const uint4*)L.part.p, nq, d_pairs, n_pairs, n_split, orb ? 1 : 0, ratio,
+                  (int32_t*)L.knn_idx.p, (float*)L.knn_dist.p, (uint8_t*)L.flags.p,
+                  (int32_t*)L.chunk_cnt.p, (slamb200_dmatch*)L.out.p, cap, (int32_t*)L.n_out.p, s);
   CU(cudaGetLastError());
   CU(cudaEventRecord(L.done, s));
   return SLAMB200_OK;
@@ -735,7 +745,7 @@ static int fetch_batch(Lane& L, cudaStream_t s, slamb200_dmatch* out, int out_ca
   if (!out) return fail(SLAMB200_ERR_INVALID, "out is NULL");
   if (P + 1 > N_SMALL) return fail(SLAMB200_ERR_INVALID, "too many pairs in one batch");
   CU(cudaMemcpyAsync(L.h_small + 1, L.n_out.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(L.h_small, L.err_flag.p, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(L.h_small, L.status, 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   if (L.h_small[0] != 0)
     return fail(SLAMB200_ERR_INTERNAL, "device self-check failed (flag %d): tensor-core candidates "
@@ -800,7 +810,7 @@ extern "C" int slamb200_knn2(slamb200_ctx* c, int matcher, const slamb200_desc* 
     CU(cudaMemcpyAsync(idx, L.knn_idx.p, sizeof(int32_t) * 2 * (size_t)q->n, cudaMemcpyDeviceToHost, L.stream));
     CU(cudaMemcpyAsync(dist, L.knn_dist.p, sizeof(float) * 2 * (size_t)q->n, cudaMemcpyDeviceToHost, L.stream));
   }
-  CU(cudaMemcpyAsync(L.h_small, L.err_flag.p, 4, cudaMemcpyDeviceToHost, L.stream));
+  CU(cudaMemcpyAsync(L.h_small, L.status, 4, cudaMemcpyDeviceToHost, L.stream));
   CU(cudaStreamSynchronize(L.stream));
   if (L.h_small[0] != 0)
     return fail(SLAMB200_ERR_INTERNAL, "device self-check failed (flag %d)", L.h_small[0]);
