@@ -545,9 +545,11 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   if (n_pairs == 0) return SLAMB200_OK;
   int rc;
   const bool orb = matcher == SLAMB200_ORB_BF;
-  const bool tc = !orb && c->use_tc && nq > 0;
   int t_max = 0;
   for (int p = 0; p < n_pairs; p++) t_max = trains[p]->n > t_max ? trains[p]->n : t_max;
+  // the candidate records pack two 16-bit group indices: train sets beyond 524k rows take the
+  // exact fp32 kernel instead
+  const bool tc = !orb && c->use_tc && nq > 0 && t_max <= 65535 * 8;
   const int q_blocks = orb ? (nq + 255) / 256 : (nq + 15) / 16;
   const int n_split = pick_splits(q_blocks > 0 ? q_blocks : 1, n_pairs, t_max, orb ? 1024 : 512);
 
@@ -620,7 +622,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   if (tc) {
     if ((rc = buf_reserve(c, L.cand, cand_bytes, s))) return rc;
     if ((rc = buf_reserve(c, L.work, sizeof(uint4) * rows, s))) return rc;
-    if ((rc = buf_reserve(c, L.work_v0, sizeof(float) * rows, s))) return rc;
+    if ((rc = buf_reserve(c, L.work_v0, sizeof(float2) * rows, s))) return rc;
   }
   char* db = (char*)L.pairs.p;
   const PairArgs* d_pairs = (const PairArgs*)(db + off_pairs);
@@ -659,7 +661,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     if (!(tc && all_exact_known)) {
       ProfScope ps(c, s, SLAMB200_K_SIFT_EXACT);
       launch_sift_exact_knn2(q->f32, q->flags, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p,
-                             c->use_tc ? 0 : 1, s);
+                             tc ? 0 : 1, s);
     }
     if (tc) {
       // Slot records are normally all written by the kernel (the merge pass computes which ones
@@ -702,7 +704,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
           ProfScope ps(c, s2, SLAMB200_K_SIFT_RERANK);
           launch_sift_rerank(q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, n_cta, n_slots, n_split,
                              cand_k, part_k, (uint4*)L.work.p + (size_t)p0 * nq,
-                             (float*)L.work_v0.p + (size_t)p0 * nq, d_status + 1 + (k < 1000 ? k : 1000),
+                             (float2*)L.work_v0.p + (size_t)p0 * nq, d_status + 1 + (k < 1000 ? k : 1000),
                              d_status, want_knn ? 0 : 1, ratio, s2);
         }
         ProfScope psf(c, s2, SLAMB200_K_FINALIZE);

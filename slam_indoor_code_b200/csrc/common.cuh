@@ -120,7 +120,7 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_fl
 void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
                         const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                         int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
-                        uint4* work, float* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
+                        uint4* work, float2* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
                         double ratio, cudaStream_t s);
 
 int64_t* launch_counter();

@@ -278,14 +278,17 @@ __device__ int owner_cta(int total, int n, int x) {
   return c;
 }
 
-__device__ __forceinline__ void top2_group_insert(float g, int gid, float& m1, int& i1, float& m2,
-                                                  int& i2) {
+// Running top-2 over chunks, branch-free.  (m1, i1) best chunk minimum and the group that holds
+// it, s1 = the second-smallest group minimum INSIDE that best chunk, (m2, i2) second-best chunk.
+__device__ __forceinline__ void top2_chunk_insert(float g, int gid, float g2nd, float& m1, int& i1,
+                                                  float& s1, float& m2, int& i2) {
   const bool lt1 = g < m1;
   const bool lt2 = g < m2;
   m2 = lt1 ? m1 : (lt2 ? g : m2);
   i2 = lt1 ? i1 : (lt2 ? gid : i2);
   m1 = lt1 ? g : m1;
   i1 = lt1 ? gid : i1;
+  s1 = lt1 ? g2nd : s1;
 }
 
 #define TMEM_LD32(taddr, v)                                                                     \
@@ -311,11 +314,12 @@ __device__ __forceinline__ void top2_group_insert(float g, int gid, float& m1, i
                  "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),  \
                  "+r"(v[30]), "+r"(v[31])::"memory")
 
-// One 32-column chunk of a row: the chunk minimum and the 8-column group that holds it (lowest
-// group on ties) go through a branch-free running top-2 over *chunks*.  gid = column / 8 of the
-// minimum's group, so chunk = gid >> 2.  Strict '<' keeps the earlier chunk on equal values.
+// One 32-column chunk of a row: the chunk minimum, the 8-column group that holds it (lowest group
+// on ties) and the second-smallest of the four group minima go through the running top-2 over
+// chunks.  gid = column / 8 of the minimum's group, so chunk = gid >> 2.  Strict '<' keeps the
+// earlier chunk on equal values.
 __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0, float& m1, int& i1,
-                                              float& m2, int& i2) {
+                                              float& s1, float& m2, int& i2) {
   float g[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
@@ -326,11 +330,13 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0,
     g[j] = fmin3(a, b, fminf(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
   }
   const float m01 = fminf(g[0], g[1]), m23 = fminf(g[2], g[3]);
+  const float M01 = fmaxf(g[0], g[1]), M23 = fmaxf(g[2], g[3]);
   const int j01 = g[1] < g[0] ? gid0 + 1 : gid0;
   const int j23 = g[3] < g[2] ? gid0 + 3 : gid0 + 2;
   const float cm = fminf(m01, m23);
+  const float c2 = fmin3(fmaxf(m01, m23), M01, M23);  // second smallest of the four
   const int gid = m23 < m01 ? j23 : j01;
-  top2_group_insert(cm, gid, m1, i1, m2, i2);
+  top2_chunk_insert(cm, gid, c2, m1, i1, s1, m2, i2);
 }
 
 template <bool DBG>
@@ -481,7 +487,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     TileIter it;
     it.init(P, pair_id, n_pairs_cta);
     int t_stage = 0, t_phase = 0;
-    float m1 = __int_as_float(0x7f800000), m2 = m1;
+    float m1 = __int_as_float(0x7f800000), m2 = m1, s1 = m1;
     int i1 = -1, i2 = -1;
     int seg_pair = -1, seg_rb = 0;
     bool new_seg = true;
@@ -495,7 +501,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       if (new_seg) {
         seg_pair = it.pair; seg_rb = it.rb;
         seg_ntiles = it.n_tiles; seg_ncb = it.n_cb; seg_c = it.slot_c;
-        m1 = m2 = __int_as_float(0x7f800000);
+        m1 = m2 = s1 = __int_as_float(0x7f800000);
         i1 = i2 = -1;
       }
       mbar_wait(t_full + 8 * t_stage, t_phase);
@@ -516,7 +522,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
           for (int j = 0; j < 32; j++)
             P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * c + j] = __uint_as_float(va[j]);
         }
-        if (P.mode < 1) process_chunk(va, gid_tile + 4 * c, m1, i1, m2, i2);
+        if (P.mode < 1) process_chunk(va, gid_tile + 4 * c, m1, i1, s1, m2, i2);
         if (P.mode < 2) {
           TMEM_WAIT32(vb);
           if (c + 2 < CHUNKS) TMEM_LD32(t_addr + 32 * (c + 2), va);
@@ -533,7 +539,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
           for (int j = 0; j < 32; j++)
             P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * (c + 1) + j] = __uint_as_float(vb[j]);
         }
-        if (P.mode < 1) process_chunk(vb, gid_tile + 4 * (c + 1), m1, i1, m2, i2);
+        if (P.mode < 1) process_chunk(vb, gid_tile + 4 * (c + 1), m1, i1, s1, m2, i2);
       }
       first_tile = false;
       if (++t_stage == 2) { t_stage = 0; t_phase ^= 1; }
@@ -548,8 +554,10 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
         }
         const int slot = COL_SPLITS * ord + half;
         uint4 rec;
-        rec.x = __float_as_uint(m1); rec.y = (uint32_t)i1;
-        rec.z = __float_as_uint(m2); rec.w = (uint32_t)i2;
+        // {best chunk min, second chunk min, second group min inside the best chunk,
+        //  gid of the best | gid of the second << 16}; 0xFFFF = absent (gids fit: T <= 524k rows)
+        rec.x = __float_as_uint(m1); rec.y = __float_as_uint(m2); rec.z = __float_as_uint(s1);
+        rec.w = ((uint32_t)i1 & 0xFFFFu) | ((uint32_t)i2 << 16);
         P.cand[((size_t)seg_pair * P.n_slots + slot) * P.nq_pad + seg_rb * 2 * BM + row_in_tile] = rec;
       }
     }
@@ -581,7 +589,7 @@ struct RerankParams {
   double ratio;
   uint4* part;       // [pair][n_split][nq]: split 0 gets the record (pre-set to "absent")
   uint4* work;       // survivors: {pair, row, gid of the best chunk, gid of the second chunk}
-  float* work_v0;    // their tensor-core minimum (self check)
+  float2* work_v0;   // {tensor-core minimum (self check), smallest d^2/2 outside the best group}
   int32_t* work_n;   // number of survivors
   int32_t* err_flag;
 };
@@ -594,9 +602,10 @@ __device__ __forceinline__ bool lt_fi(float va, int ia, float vb, int ib) {
 // Lanes run along the rows, so every slot read is a coalesced 512 B per warp.
 //
 // Ratio-test pruning (exact, not a heuristic): v0 is the row's exact best d^2/2, and the second
-// best element is no farther than the second chunk's minimum v1.  sqrtf, float->double and the
+// best element is no farther than L = min(second group minimum inside the best chunk, second
+// chunk's minimum) -- both exact distances of real elements.  sqrtf, float->double and the
 // multiplication by a non-negative ratio are monotone, so if even the upper bound
-// D1 = sqrtf(2*v1) fails  d0 < ratio * D1  (getGoodMatches' own comparison,
+// D1 = sqrtf(2*L) fails  d0 < ratio * D1  (getGoodMatches' own comparison,
 // featureMatchingCommon.cpp:47), the true second distance fails it too: the row is rejected
 // without touching its candidates, and its record carries (d0, D1) so that the finalize kernel
 // reaches the same verdict with the same arithmetic.  Rows that survive go to the work list.
@@ -626,35 +635,40 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
   __syncthreads();
   const int n_valid = n_valid_s;
   bool survive = false;
-  float v0 = __int_as_float(0x7f800000), v1 = v0;
-  int g0 = 0x7fffffff, g1 = 0x7fffffff;
+  const float INF = __int_as_float(0x7f800000);
+  float v0 = INF, v1 = INF, s0 = INF;   // best chunk min, second chunk min, 2nd group min in best
+  int g0 = 0xFFFF, g1 = 0xFFFF;
   if (q < R.nq) {
     for (int s = 0; s < n_valid; s++) {
       const uint4 rec = R.cand[((size_t)pair * R.n_slots + s) * R.nq_pad + q];
-      const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.z);
-      const int ia = (int)rec.y, ib = (int)rec.w;
-      if (ia >= 0) {
-        if (lt_fi(a, ia, v0, g0)) { v1 = v0; g1 = g0; v0 = a; g0 = ia; }
+      const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.y), sa = __uint_as_float(rec.z);
+      const int ia = (int)(rec.w & 0xFFFFu), ib = (int)(rec.w >> 16);
+      if (ia != 0xFFFF) {
+        if (lt_fi(a, ia, v0, g0)) { v1 = v0; g1 = g0; v0 = a; g0 = ia; s0 = sa; }
         else if (lt_fi(a, ia, v1, g1)) { v1 = a; g1 = ia; }
       }
-      if (ib >= 0) {
-        if (lt_fi(b, ib, v0, g0)) { v1 = v0; g1 = g0; v0 = b; g0 = ib; }
-        else if (lt_fi(b, ib, v1, g1)) { v1 = b; g1 = ib; }
+      if (ib != 0xFFFF) {
+        // a slot's second entry can never be the global best chunk (its own first entry beats it)
+        if (lt_fi(b, ib, v1, g1)) { v1 = b; g1 = ib; }
       }
     }
-    const bool has0 = g0 != 0x7fffffff, has1 = g1 != 0x7fffffff;
+    const bool has0 = g0 != 0xFFFF;
     const uint4 none = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
     for (int sp = 1; sp < R.n_split; sp++) R.part[((size_t)pair * R.n_split + sp) * R.nq + q] = none;
     if (!has0) R.part[((size_t)pair * R.n_split) * R.nq + q] = none;  // empty train set
     survive = has0;
-    if (R.prune && has0 && has1) {
-      const float d0 = sqrtf(2.0f * v0), D1 = sqrtf(2.0f * v1);
+    // L = the smallest d^2/2 outside the best group: the second group of the best chunk or the
+    // second-best chunk.  Values >= 2^28 come from padding columns, i.e. "no such element".
+    const float L = fminf(s0, v1);
+    if (R.prune && has0 && L < 268435456.0f) {
+      const float d0 = sqrtf(2.0f * v0), D1 = sqrtf(2.0f * L);
       if (!((double)d0 < __dmul_rn(R.ratio, (double)D1))) {
         R.part[((size_t)pair * R.n_split) * R.nq + q] =
             make_uint4(__float_as_uint(d0), 0u, __float_as_uint(D1), 0u);
         survive = false;
       }
     }
+    v1 = L;  // what the survivors need downstream
   }
   // warp-aggregated append to the work list
   const unsigned bal = __ballot_sync(0xffffffffu, survive);
@@ -666,12 +680,78 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
     if (survive) {
       const int at = base + __popc(bal & ((1u << lane) - 1));
       R.work[at] = make_uint4((uint32_t)pair, (uint32_t)q, (uint32_t)g0, (uint32_t)g1);
-      R.work_v0[at] = v0;
+      R.work_v0[at] = make_float2(v0, v1);
     }
   }
 }
 
-// Pass 2, persistent warps over the work list, one warp per surviving row.  Candidates = all 32
+// Pass 2 (match output), persistent warps over the work list, one warp per surviving row.
+// Only the best group's 8 columns are evaluated: that yields the best match (index and exact
+// d^2) and the second smallest of the group; every element outside the group is bounded below by
+// L (an exact distance of a real element, from the merge pass), so the second distance is
+// exactly min(second of the group, L) -- which is all getGoodMatches needs
+// (featureMatchingCommon.cpp:47 compares distances only; DMatch carries the best index).
+// 4 lanes x 32 B per candidate row, dp4a, two shuffles to reduce, three to select.
+__global__ void __launch_bounds__(256) sift_rerank_lite_kernel(const RerankParams R) {
+  const int lane = threadIdx.x & 31;
+  const int part = lane & 3, cand = lane >> 2;
+  const int n_work = *R.work_n;
+  const int warps = gridDim.x * 8;
+  for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < n_work; w += warps) {
+    const uint4 wk = R.work[w];
+    const int pair = (int)wk.x, q = (int)wk.y, g0 = (int)wk.z;
+    const float2 vl = R.work_v0[w];
+    const TcPair* pr = R.pairs + pair;
+    const int col = g0 * GROUP + cand;
+    const bool ok = col < pr->t_n;
+    const int cc = ok ? col : 0;
+    const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)cc * 128 + part * 32);
+    const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)q * 128 + part * 32);
+    const uint4 t0 = tp[0], t1 = tp[1], q0 = qp[0], q1 = qp[1];
+    const uint32_t nt2 = (uint32_t)pr->t_nrm2[cc], nq2 = (uint32_t)R.q_nrm2[q];
+    uint32_t dot = 0;
+    dot = __dp4a(q0.x, t0.x, dot); dot = __dp4a(q0.y, t0.y, dot);
+    dot = __dp4a(q0.z, t0.z, dot); dot = __dp4a(q0.w, t0.w, dot);
+    dot = __dp4a(q1.x, t1.x, dot); dot = __dp4a(q1.y, t1.y, dot);
+    dot = __dp4a(q1.z, t1.z, dot); dot = __dp4a(q1.w, t1.w, dot);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    unsigned long long k0 = ok ? (((unsigned long long)(nq2 + nt2 - 2u * dot) << 32) | (uint32_t)col) : ~0ull;
+    unsigned long long k1 = ~0ull;
+#pragma unroll
+    for (int off = 4; off <= 16; off <<= 1) {
+      const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, off);
+      const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off);
+      const unsigned long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0;
+      const unsigned long long s2 = k1 < o1 ? k1 : o1;
+      k0 = lo;
+      k1 = hi < s2 ? hi : s2;
+    }
+    if (lane == 0) {
+      uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+      if (k0 != ~0ull) {
+        const uint32_t d2 = (uint32_t)(k0 >> 32);
+        // self check: the group's exact minimum must equal twice the tensor-core value
+        if ((float)d2 != 2.0f * vl.x) atomicOr(R.err_flag, 1);
+        rec.x = __float_as_uint(sqrtf((float)d2));
+        rec.y = (uint32_t)(k0 & 0xFFFFFFFFu);
+        // second distance: inside the group, or the bound from outside it (exact values both)
+        float d1sq = vl.y < 268435456.0f ? 2.0f * vl.y : -1.0f;
+        if (k1 != ~0ull) {
+          const float x2 = (float)(uint32_t)(k1 >> 32);
+          d1sq = (d1sq < 0.0f || x2 < d1sq) ? x2 : d1sq;
+        }
+        if (d1sq >= 0.0f) {
+          rec.z = __float_as_uint(sqrtf(d1sq));
+          rec.w = 0u;  // the second neighbour's index is not part of the match output
+        }
+      }
+      R.part[((size_t)pair * R.n_split) * R.nq + q] = rec;
+    }
+  }
+}
+
+// Pass 2 (raw k-NN output: both indices are needed), one warp per row.  Candidates = all 32
 // columns of the best chunk + the 8 columns of the second chunk's group (40): the true top-2
 // columns are always among them.  Each candidate row is read by 8 lanes x 16 B (one 128 B line
 // per candidate), dp4a'd against the matching 16 B of the query row and reduced over the 8 lanes.
@@ -683,12 +763,12 @@ __global__ void __launch_bounds__(256) sift_rerank_kernel(const RerankParams R) 
   for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < n_work; w += warps) {
     const uint4 wk = R.work[w];
     const int pair = (int)wk.x, q = (int)wk.y, g0 = (int)wk.z, g1 = (int)wk.w;
-    const float v0 = R.work_v0[w];
+    const float v0 = R.work_v0[w].x;
     const TcPair* pr = R.pairs + pair;
     const uint8_t* t_u8 = pr->t_u8;
     const int32_t* t_nrm2 = pr->t_nrm2;
     const int t_n = pr->t_n;
-    const bool has1 = g1 != 0x7fffffff;
+    const bool has1 = g1 != 0xFFFF;
     const int col_a = (g0 >> 2) * 32;          // first column of the best chunk
     const int col_b = has1 ? g1 * GROUP : 0;   // first column of the second chunk's group
 
@@ -855,7 +935,7 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_fl
 void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
                         const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                         int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
-                        uint4* work, float* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
+                        uint4* work, float2* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
                         double ratio, cudaStream_t s) {
   if (nq <= 0 || n_pairs <= 0) return;
   RerankParams R;
@@ -870,6 +950,9 @@ void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32
   COUNT_LAUNCH();
   const long long rows = (long long)nq * n_pairs;
   const int blocks = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
-  sift_rerank_kernel<<<blocks, 256, 0, s>>>(R);
+  if (prune)
+    sift_rerank_lite_kernel<<<blocks, 256, 0, s>>>(R);   // match output: distances + best index
+  else
+    sift_rerank_kernel<<<blocks, 256, 0, s>>>(R);        // raw k-NN output: both indices
   COUNT_LAUNCH();
 }
