@@ -547,6 +547,8 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   const bool orb = matcher == SLAMB200_ORB_BF;
   int t_max = 0;
   for (int p = 0; p < n_pairs; p++) t_max = trains[p]->n > t_max ? trains[p]->n : t_max;
+  if (orb && t_max >= (1 << 22))
+    return fail(SLAMB200_ERR_INVALID, "ORB train set of %d rows exceeds the 2^22-row key range", t_max);
   // the candidate records pack two 16-bit group indices: train sets beyond 524k rows take the
   // exact fp32 kernel instead
   const bool tc = !orb && c->use_tc && nq > 0 && t_max <= 65535 * 8;
