@@ -179,7 +179,9 @@ int slamb200_batch_scores_fetch(slamb200_ctx* ctx, int32_t* counts, int32_t* bes
 #define SLAMB200_K_RANSAC 3     /* Sampson counting kernel           */
 #define SLAMB200_K_SIFT_RERANK 4 /* exact dp4a rerank of the candidates */
 #define SLAMB200_K_FINALIZE 5   /* ratio test + ordered compaction    */
-#define SLAMB200_K_COUNT 6
+#define SLAMB200_K_SIFT_TC_GEN 6 /* tcgen05 kernel, general floats     */
+#define SLAMB200_K_SIFT_GEN_RERANK 7 /* certified fp32 rerank + fallback */
+#define SLAMB200_K_COUNT 8
 int slamb200_profile_enable(slamb200_ctx* ctx, int on);
 /* Synchronises, then returns the summed device time (ms) and the launch count of each kernel
  * class since the last read; ms and launches have SLAMB200_K_COUNT entries. */

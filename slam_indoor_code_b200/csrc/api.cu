@@ -50,7 +50,7 @@ struct Lane {
   std::vector<cudaEvent_t> sub_ev;
   bool busy = false;
   // matching scratch (device)
-  DevBuf pairs, tcpairs, tile_prefix, part, cand, work, work_v0, knn_idx, knn_dist, flags, chunk_cnt, out, n_out, err_flag;
+  DevBuf pairs, tcpairs, tile_prefix, part, cand, cand_g, work, work_v0, fb_list, knn_idx, knn_dist, flags, chunk_cnt, out, n_out, err_flag;
   // scoring scratch (device)
   DevBuf npts, E, counts, best, mask, m_off, p1, p2, txy, all_masks;
   // pinned staging
@@ -224,7 +224,7 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
   cudaDeviceSynchronize();
   for (int i = 0; i < N_LANES; i++) {
     Lane& L = c->lanes[i];
-    DevBuf* bufs[] = {&L.pairs, &L.tcpairs, &L.tile_prefix, &L.work, &L.work_v0, &L.part, &L.cand, &L.knn_idx, &L.knn_dist, &L.flags,
+    DevBuf* bufs[] = {&L.pairs, &L.tcpairs, &L.tile_prefix, &L.work, &L.work_v0, &L.fb_list, &L.cand_g, &L.part, &L.cand, &L.knn_idx, &L.knn_dist, &L.flags,
                       &L.chunk_cnt, &L.out, &L.n_out, &L.err_flag, &L.npts, &L.E, &L.counts,
                       &L.best, &L.mask, &L.m_off, &L.p1, &L.p2, &L.txy, &L.all_masks};
     for (DevBuf* b : bufs)
@@ -352,11 +352,12 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
       else DCU(cudaMemcpy2DAsync(d->u8, 32, rows, row_stride, 32, n, k, s));
     }
   } else {
-    // one slab: f32 | bf16 | augq | augt | u8 | nrm2 | flags  (every part 256-byte aligned)
+    // one slab: f32 | bf16 | bf16lo | augq | augt | u8 | nrm2 | nrmf | flags  (256-byte aligned)
     const size_t np = d->n_pad;
-    const size_t o_f32 = 0, o_bf16 = o_f32 + np * 512, o_augq = o_bf16 + np * 256,
-                 o_augt = o_augq + np * 32, o_u8 = o_augt + np * 32, o_nrm = o_u8 + np * 128,
-                 o_flags = o_nrm + np * 4, total = o_flags + 256;
+    const size_t o_f32 = 0, o_bf16 = o_f32 + np * 512, o_lo = o_bf16 + np * 256,
+                 o_augq = o_lo + np * 256, o_augt = o_augq + np * 32, o_u8 = o_augt + np * 32,
+                 o_nrm = o_u8 + np * 128, o_nrmf = o_nrm + np * 4, o_flags = o_nrmf + np * 4,
+                 total = o_flags + 256;
     d->slab_bytes = total;
     if (!(d->slab = slab_from_cache(c, total, s)))
       if ((rc = dev_alloc(c, &d->slab, total, s))) goto done;
@@ -367,6 +368,8 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
     d->augt = (__nv_bfloat16*)(base + o_augt);
     d->u8 = (uint8_t*)(base + o_u8);
     d->nrm2 = (int32_t*)(base + o_nrm);
+    d->bf16lo = (__nv_bfloat16*)(base + o_lo);
+    d->nrmf = (float*)(base + o_nrmf);
     d->flags = (int32_t*)(base + o_flags);
     DCU(cudaMemsetAsync(d->flags, 0, 16, s));
     const float* prep_src = d->f32;
@@ -393,9 +396,9 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
       }
     }
     launch_sift_prep(prep_src, prep_stride, n, d->n_pad, d->f32, d->bf16, d->augq, d->augt, d->u8,
-                     d->nrm2, d->flags, s);
+                     d->nrm2, d->bf16lo, d->nrmf, d->flags, s);
     DCU(cudaGetLastError());
-    if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->n_pad, d->tmaps) != 0) {
+    if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->bf16lo, d->n_pad, d->tmaps) != 0) {
       rc = fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
       goto done;
     }
@@ -587,8 +590,11 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     }
     n_cta = max_tiles < max_pairs ? (max_tiles > 0 ? max_tiles : 1) : max_pairs;
     for (int p = 0; p < n_pairs; p++) {
-      memcpy(tp[p].tmap, trains[p]->tmaps, 128);             // main
+      memcpy(tp[p].tmap, trains[p]->tmaps, 128);             // main (hi)
       memcpy(tp[p].tmap + 128, trains[p]->tmaps + 256, 128);  // aug, train role
+      memcpy(tp[p].tmap + 256, trains[p]->tmaps + 384, 128);  // lo
+      tp[p].t_f32 = trains[p]->f32;
+      tp[p].t_nrmf = trains[p]->nrmf;
       tp[p].t_u8 = trains[p]->u8;
       tp[p].t_nrm2 = trains[p]->nrm2;
       tp[p].t_flags = trains[p]->flags;
@@ -625,6 +631,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     if ((rc = buf_reserve(c, L.cand, cand_bytes, s))) return rc;
     if ((rc = buf_reserve(c, L.work, sizeof(uint4) * rows, s))) return rc;
     if ((rc = buf_reserve(c, L.work_v0, sizeof(float2) * rows, s))) return rc;
+    if ((rc = buf_reserve(c, L.fb_list, sizeof(uint2) * rows, s))) return rc;
   }
   char* db = (char*)L.pairs.p;
   const PairArgs* d_pairs = (const PairArgs*)(db + off_pairs);
@@ -656,19 +663,39 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     ProfScope ps(c, s, SLAMB200_K_ORB);
     launch_orb_knn2(q->u8, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p, s);
   } else {
-    // General-float pairs: exact fp32 kernel (it skips exact-mode pairs unless force).  Exact-mode
-    // pairs (integer-valued descriptors, what cv::SIFT emits): tcgen05 candidates + dp4a rerank
-    // (those kernels skip the general-float pairs).  Both read the flags on the device, so no
-    // host synchronisation is needed to pick the path.
-    if (!(tc && all_exact_known)) {
+    // Without the tensor-core path (debug switch, or train sets beyond 524k rows) the exact fp32
+    // kernel does every pair.  With it: integer-valued pairs (what cv::SIFT emits) take the exact-
+    // mode tcgen05 kernel + dp4a rerank; general-float pairs take the two-term-split tcgen05 kernel
+    // + certified fp32 rerank (+ exact fallback rows).  The kernels pick their pairs from the
+    // flags on the device, so no host synchronisation is needed to route.
+    if (!tc) {
       ProfScope ps(c, s, SLAMB200_K_SIFT_EXACT);
-      launch_sift_exact_knn2(q->f32, q->flags, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p,
-                             tc ? 0 : 1, s);
+      launch_sift_exact_knn2(q->f32, q->flags, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p, 1, s);
     }
     if (tc) {
       // Slot records are normally all written by the kernel (the merge pass computes which ones
       // exist); only the hole case needs them cleared (small or ragged batches).
       if (holes) CU(cudaMemsetAsync(L.cand.p, 0xFF, cand_bytes, s));
+      alignas(64) unsigned char qmaps[384];
+      memcpy(qmaps, q->tmaps, 256);              // main (hi), aug (query role)
+      memcpy(qmaps + 256, q->tmaps + 384, 128);  // lo
+      if (!all_exact_known) {
+        // general-float pairs (skipped entirely when every set is known to be integer-valued);
+        // their slot records are two 16-byte words wide and live in their own buffer
+        if ((rc = buf_reserve(c, L.cand_g, 2 * cand_bytes, s))) return rc;
+        if (holes) CU(cudaMemsetAsync(L.cand_g.p, 0xFF, 2 * cand_bytes, s));
+        int grc;
+        {
+          ProfScope ps(c, s, SLAMB200_K_SIFT_TC_GEN);
+          grc = launch_sift_tc_candidates(qmaps, q->flags, nq, d_tc, d_pre, n_pairs, pre[n_pairs], n_cta,
+                                          n_slots, (uint4*)L.cand_g.p, d_status, nullptr, 1, s);
+        }
+        if (grc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
+        ProfScope ps(c, s, SLAMB200_K_SIFT_GEN_RERANK);
+        launch_sift_gen_rerank(q->flags, q->f32, q->nrmf, nq, d_tc, d_pre, n_pairs, n_cta, n_slots, n_split,
+                               (const uint4*)L.cand_g.p, (uint4*)L.part.p, (uint2*)L.fb_list.p,
+                               d_status + 1002, s);
+      }
       // Sub-batch pipeline (debug knob, default one sub-batch): the tcgen05 kernel of sub-batch
       // k+1 on `s` against the rerank / finalize kernels of sub-batch k on the lane's second
       // stream.  Measured: no gain (both sides contend for the same SM issue slots).
@@ -694,8 +721,8 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         int trc;
         {
           ProfScope ps(c, s, SLAMB200_K_SIFT_TC);
-          trc = launch_sift_tc_candidates(q->tmaps, q->flags, nq, tcp, pre_k, np, tiles_k, n_cta,
-                                          n_slots, cand_k, d_status, k == 0 ? L.dbg : nullptr, s);
+          trc = launch_sift_tc_candidates(qmaps, q->flags, nq, tcp, pre_k, np, tiles_k, n_cta,
+                                          n_slots, cand_k, d_status, k == 0 ? L.dbg : nullptr, 0, s);
         }
         if (trc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
         if (s2 != s) {
@@ -1130,4 +1157,16 @@ extern "C" int slamb200_dbg_tc_tile(slamb200_ctx* c, const slamb200_desc* q, con
   }
   cudaFreeAsync(d, L.stream);
   return rc;
+}
+
+// Rows of the last enqueued batch (lane 0) that the general-float certificate sent to the exact
+// fallback.  Synchronises.
+extern "C" int slamb200_dbg_last_fallback_rows(slamb200_ctx* c) {
+  if (!c) return -1;
+  Lane& L = c->lanes[0];
+  if (!L.status) return -1;
+  int32_t v = -1;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpy(&v, L.status + 1002, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return v;
 }

@@ -33,13 +33,15 @@ struct slamb200_desc {
   __nv_bfloat16* augt;
   uint8_t* u8;
   int32_t* nrm2;
-  int32_t* flags;      // device
+  __nv_bfloat16* bf16lo;  // low half of the two-term bf16 split (general-float tensor-core path)
+  float* nrmf;            // |row|^2 as fp32
+  int32_t* flags;      // device: [0] general-float flag, [2] max |row|^2 (fp32 bits)
   int host_exact;      // -2 unknown, else 1 when flags[0] == 0
   int ready_seen;      // the ready event has been observed complete (no more stream waits)
   cudaEvent_t ready;   // recorded after the prep kernels
   void* slab;          // the one device allocation all the pointers above live in
   size_t slab_bytes;
-  alignas(64) unsigned char tmaps[384];  // host copies of 3 CUtensorMaps: main, augq, augt
+  alignas(64) unsigned char tmaps[512];  // host copies of 4 CUtensorMaps: main, augq, augt, lo
 };
 
 struct slamb200_pts {
@@ -98,25 +100,32 @@ void launch_score_all_masks(const double4* npts, int M, const double* E, int H, 
 // (padding rows get an "infinitely far" augmentation so they never become candidates).
 void launch_sift_prep(const float* src, size_t src_stride_floats, int n, int n_pad, float* f32,
                       __nv_bfloat16* bf16, __nv_bfloat16* augq, __nv_bfloat16* augt, uint8_t* u8,
-                      int32_t* nrm2, int32_t* flags, cudaStream_t s);
+                      int32_t* nrm2, __nv_bfloat16* bf16lo, float* nrmf, int32_t* flags,
+                      cudaStream_t s);
 
 // SIFT tcgen05 candidate kernel + dp4a rerank (sift_tc.cu).
 struct alignas(64) TcPair {
-  unsigned char tmap[256];  // the train frame's CUtensorMaps {main, aug (train role)}, read by TMA
+  unsigned char tmap[384];  // the train frame's CUtensorMaps {main, aug (train role), lo}, read by TMA
+  const float* t_f32;       // fp32 rows and norms (general-float path)
+  const float* t_nrmf;
   const uint8_t* t_u8;
   const int32_t* t_nrm2;
   const int32_t* t_flags;
   int t_n;
   int t_pad;
 };
-int tc_encode_tmaps(const void* bf16_dev, const void* augq_dev, const void* augt_dev, int n_pad,
-                    void* host_out_384B);
+int tc_encode_tmaps(const void* bf16_dev, const void* augq_dev, const void* augt_dev,
+                    const void* bf16lo_dev, int n_pad, void* host_out_512B);
 size_t tc_smem_bytes();
 int tc_slots(int n_cb_max, int total_tiles, int n_cta);
-int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_flags, int nq,
+int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_flags, int nq,
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
-                              int32_t* err_flag, float* dbg, cudaStream_t s);
+                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s);
+void launch_sift_gen_rerank(const int32_t* q_flags, const float* q_f32, const float* q_nrmf, int nq,
+                            const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                            int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
+                            uint2* fb_list, int32_t* fb_count, cudaStream_t s);
 void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
                         const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                         int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,

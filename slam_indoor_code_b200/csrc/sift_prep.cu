@@ -8,9 +8,12 @@
 //         (|q|^2 + |t|^2)/2 - q.t = d^2/2 directly:  query side [h m l 1 1 1 0..], train side
 //         [1 1 1 h m l 0..] with h+m+l = |row|^2/2 split into three bf16 pieces (24 bits, exact)
 //   u8    integer copy for the dp4a rerank;  nrm2  integer squared norms
+//   bf16lo  bf16(v - bf16(v)): the low half of a two-term bf16 split, used by the general-float
+//         tensor-core path (zero for integer-valued rows);  nrmf  |row|^2 as fp32 (fp64 sum)
 //   flags[0] != 0 when some value is not an integer in [0,255] or some |row|^2 >= 2^20
-// Padding rows [n, n_pad) get zero descriptors and a 2^30 augmentation so they are never
-// candidates.  One warp per row, one float4 per lane.
+//   flags[2] = max |row|^2 of the set (fp32 bits; error bound of the general path)
+// Padding rows [n, n_pad) get zero descriptors and a +inf augmentation (the accumulator becomes
+// +inf, never NaN: the partner's entry is 1) so they are never candidates.  One warp per row, one float4 per lane.
 #include "common.cuh"
 
 __global__ void __launch_bounds__(256)
@@ -18,6 +21,7 @@ sift_prep_kernel(const float* __restrict__ src, size_t src_stride, int n, int n_
                  float* __restrict__ f32, __nv_bfloat16* __restrict__ bf16,
                  __nv_bfloat16* __restrict__ augq, __nv_bfloat16* __restrict__ augt,
                  uint8_t* __restrict__ u8, int32_t* __restrict__ nrm2,
+                 __nv_bfloat16* __restrict__ bf16lo, float* __restrict__ nrmf,
                  int32_t* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -28,6 +32,7 @@ sift_prep_kernel(const float* __restrict__ src, size_t src_stride, int n, int n_
   const float x[4] = {v.x, v.y, v.z, v.w};
   int bad = 0, ss = 0;
   uint32_t packed = 0;
+  double sd = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const bool ok = (x[k] >= 0.f) && (x[k] <= 255.f) && (x[k] == rintf(x[k]));
@@ -42,28 +47,44 @@ sift_prep_kernel(const float* __restrict__ src, size_t src_stride, int n, int n_
   pk.y = *reinterpret_cast<uint32_t*>(&hi);
   reinterpret_cast<uint2*>(bf16 + (size_t)row * 128)[lane] = pk;
   reinterpret_cast<uint32_t*>(u8 + (size_t)row * 128)[lane] = packed;
+  {
+    // low half of the two-term split: v - bf16(v) is exact in fp32, then rounded to bf16
+    const float2 h0 = __bfloat1622float2(lo), h1 = __bfloat1622float2(hi);
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - h0.x, v.y - h0.y);
+    __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - h1.x, v.w - h1.y);
+    uint2 pl;
+    pl.x = *reinterpret_cast<uint32_t*>(&l0);
+    pl.y = *reinterpret_cast<uint32_t*>(&l1);
+    reinterpret_cast<uint2*>(bf16lo + (size_t)row * 128)[lane] = pl;
+  }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     ss += __shfl_xor_sync(0xffffffffu, ss, off);
     bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+    sd += __shfl_xor_sync(0xffffffffu, sd, off);
   }
   if (ss >= (1 << 20)) bad = 1;
+  const float nf = (float)sd;  // == ss exactly for integer-valued rows
   if (lane == 0) {
     nrm2[row] = ss;
-    if (bad && row < n) atomicOr(&flags[0], 1);
+    nrmf[row] = nf;
+    if (row < n) {
+      if (bad) atomicOr(&flags[0], 1);
+      atomicMax(&flags[2], __float_as_int(nf));
+    }
   }
   // augmentation blocks: lanes 0..15 write column `lane` of each
   if (lane < 16) {
     float h, m, l;
     if (row < n) {
-      const float half = 0.5f * (float)ss;  // exact: ss < 2^24
+      const float half = 0.5f * nf;  // three bf16 pieces hold all 24 bits
       const __nv_bfloat16 bh = __float2bfloat16_rn(half);
       const float r1 = half - __bfloat162float(bh);
       const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
       const float r2 = r1 - __bfloat162float(bm);
       h = __bfloat162float(bh); m = __bfloat162float(bm); l = r2;
     } else {
-      h = 1073741824.f; m = 0.f; l = 0.f;  // 2^30: padding rows are infinitely far
+      h = __int_as_float(0x7f800000); m = 0.f; l = 0.f;  // +inf: padding rows are infinitely far
     }
     const float one = 1.f;
     float aq = 0.f, at = 0.f;
@@ -82,10 +103,11 @@ sift_prep_kernel(const float* __restrict__ src, size_t src_stride, int n, int n_
 
 void launch_sift_prep(const float* src, size_t src_stride_floats, int n, int n_pad, float* f32,
                       __nv_bfloat16* bf16, __nv_bfloat16* augq, __nv_bfloat16* augt, uint8_t* u8,
-                      int32_t* nrm2, int32_t* flags, cudaStream_t s) {
+                      int32_t* nrm2, __nv_bfloat16* bf16lo, float* nrmf, int32_t* flags,
+                      cudaStream_t s) {
   if (n_pad <= 0) return;
   const int rows_per_block = 8;
   sift_prep_kernel<<<(n_pad + rows_per_block - 1) / rows_per_block, 256, 0, s>>>(
-      src, src_stride_floats, n, n_pad, f32, bf16, augq, augt, u8, nrm2, flags);
+      src, src_stride_floats, n, n_pad, f32, bf16, augq, augt, u8, nrm2, bf16lo, nrmf, flags);
   COUNT_LAUNCH();
 }

@@ -50,6 +50,13 @@ constexpr int N_ASTAGE = 2;
 constexpr int N_BSTAGE = 4;
 constexpr int SMEM_BARS = 1024;
 constexpr int SMEM_BYTES = (N_ASTAGE + N_BSTAGE) * STAGE + SMEM_BARS + 1024;
+// general-float variant: operands carry a hi and a lo bf16 half (two-term split), 24 + 1 MMAs per
+// tile: hi.hi + hi.lo + lo.hi + augmentation
+constexpr int STAGE_G = 4 * KBLK + 128 * 32;   // 69632
+constexpr int AUG_OFF_G = 4 * KBLK;
+constexpr int N_ASTAGE_G = 1;
+constexpr int N_BSTAGE_G = 2;
+constexpr int SMEM_BYTES_G = (N_ASTAGE_G + N_BSTAGE_G) * STAGE_G + SMEM_BARS + 1024;
 constexpr int EPI_WARP0 = 4;
 #ifndef SLAMB200_EPI_WARPS
 #define SLAMB200_EPI_WARPS 8   // 16 was measured slower (19.0 vs 17.2 us/pair): register cap + barrier traffic
@@ -63,7 +70,7 @@ constexpr int GROUP = 8;            // columns per candidate group
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared address
 
 struct alignas(64) TcParams {
-  CUtensorMap q_tmap[2];       // query maps: [0] main, [1] aug (query role); __grid_constant__
+  CUtensorMap q_tmap[3];       // query maps: [0] main (hi), [1] aug (query role), [2] lo
   const TcPair* pairs;         // per pair: train maps / aug / sizes
   const int32_t* tile_prefix;  // [P+1] tiles before pair p
   const int32_t* q_flags;
@@ -218,19 +225,23 @@ struct TileIter {
   int n_tiles;              // tiles of the current frame pair
   int cta, n_cta;
   bool skip;                // general-float train set: the exact fp32 kernel owns the pair
-  const CUtensorMap* tmap;  // train maps: [0] main, [1] aug (train role)
+  const CUtensorMap* tmap;  // train maps: [0] main (hi), [1] aug (train role), [2] lo
+  bool gen;                 // which kind of frame pair this walk visits
   // The pair table (and the tensor maps inside it) is rewritten by the host before every launch:
   // make the TMA unit's descriptor reads observe those generic-proxy writes.
   __device__ void acquire_maps() const {
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap + 1) : "memory");
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap + 2) : "memory");
   }
   // positions on the first non-empty share at or after frame pair `p`; false when none is left
   __device__ bool seek(const TcParams& P, int p) {
     for (; p < P.n_pairs; p++) {
       n_tiles = P.tile_prefix[p + 1] - P.tile_prefix[p];
       if (n_tiles == 0) continue;
-      if (P.pairs[p].t_flags[0] != 0) continue;  // general-float train set: exact kernel's
+      // exact-mode pairs (integer-valued query and train) and general-float pairs are walked by
+      // different instantiations of the kernel
+      if (((P.q_flags[0] | P.pairs[p].t_flags[0]) != 0) != gen) continue;
       slot_c = (cta + p) % n_cta;
       tile = (int)(((long long)n_tiles * slot_c) / n_cta);
       end = (int)(((long long)n_tiles * (slot_c + 1)) / n_cta);
@@ -246,8 +257,8 @@ struct TileIter {
     pair = P.n_pairs;
     return false;
   }
-  __device__ void init(const TcParams& P, int cta_, int n_cta_) {
-    cta = cta_; n_cta = n_cta_;
+  __device__ void init(const TcParams& P, int cta_, int n_cta_, bool gen_) {
+    cta = cta_; n_cta = n_cta_; gen = gen_;
     pair = 0; n_cb = 1; rb = 0; cb = 0; tile = 0; end = 0; slot_c = 0; n_tiles = 0;
     skip = false; tmap = nullptr;
     seek(P, 0);
@@ -318,8 +329,27 @@ __device__ __forceinline__ void top2_chunk_insert(float g, int gid, float g2nd, 
 // on ties) and the second-smallest of the four group minima go through the running top-2 over
 // chunks.  gid = column / 8 of the minimum's group, so chunk = gid >> 2.  Strict '<' keeps the
 // earlier chunk on equal values.
-__device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0, float& m1, int& i1,
-                                              float& s1, float& m2, int& i2) {
+// General-float variant: the accumulators are approximations, so the record keeps the best FOUR
+// chunks and the fifth-best chunk minimum: a lower bound on every column outside those four,
+// which the rerank needs to certify its answer.
+// Epilogue running state of one thread (row x column range).  Exact mode uses m[0..1], i[0..1]
+// and s (second group minimum inside the best chunk); the general-float variant keeps the best
+// FOUR chunks (m[0..3], i[0..3]) and s = the fifth-best chunk minimum, a lower bound on every
+// column outside those four.
+struct EpiState {
+  float m[4];
+  int i[4];
+  float s;
+  __device__ __forceinline__ void reset() {
+    const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { m[k] = inf; i[k] = -1; }
+    s = inf;
+  }
+};
+
+template <bool GEN>
+__device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0, EpiState& st) {
   float g[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
@@ -330,24 +360,42 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0,
     g[j] = fmin3(a, b, fminf(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
   }
   const float m01 = fminf(g[0], g[1]), m23 = fminf(g[2], g[3]);
-  const float M01 = fmaxf(g[0], g[1]), M23 = fmaxf(g[2], g[3]);
   const int j01 = g[1] < g[0] ? gid0 + 1 : gid0;
   const int j23 = g[3] < g[2] ? gid0 + 3 : gid0 + 2;
   const float cm = fminf(m01, m23);
-  const float c2 = fmin3(fmaxf(m01, m23), M01, M23);  // second smallest of the four
   const int gid = m23 < m01 ? j23 : j01;
-  top2_chunk_insert(cm, gid, c2, m1, i1, s1, m2, i2);
+  if (GEN) {
+    // branch-free sorted insert into the best four, the displaced fourth feeds the bound
+    const bool l0 = cm < st.m[0], l1 = cm < st.m[1], l2 = cm < st.m[2], l3 = cm < st.m[3];
+    st.s = l3 ? st.m[3] : fminf(st.s, cm);
+    st.m[3] = l2 ? st.m[2] : (l3 ? cm : st.m[3]);
+    st.i[3] = l2 ? st.i[2] : (l3 ? gid : st.i[3]);
+    st.m[2] = l1 ? st.m[1] : (l2 ? cm : st.m[2]);
+    st.i[2] = l1 ? st.i[1] : (l2 ? gid : st.i[2]);
+    st.m[1] = l0 ? st.m[0] : (l1 ? cm : st.m[1]);
+    st.i[1] = l0 ? st.i[0] : (l1 ? gid : st.i[1]);
+    st.m[0] = l0 ? cm : st.m[0];
+    st.i[0] = l0 ? gid : st.i[0];
+  } else {
+    const float M01 = fmaxf(g[0], g[1]), M23 = fmaxf(g[2], g[3]);
+    const float c2 = fmin3(fmaxf(m01, m23), M01, M23);  // second smallest of the four
+    top2_chunk_insert(cm, gid, c2, st.m[0], st.i[0], st.s, st.m[1], st.i[1]);
+  }
 }
 
-template <bool DBG>
+template <bool DBG, bool GEN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 sift_tc_kernel(const __grid_constant__ TcParams P) {
+  constexpr int STG = GEN ? STAGE_G : STAGE;
+  constexpr int NA = GEN ? N_ASTAGE_G : N_ASTAGE;
+  constexpr int NB = GEN ? N_BSTAGE_G : N_BSTAGE;
+  constexpr int AUG = GEN ? AUG_OFF_G : AUG_OFF;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the SWIZZLE_128B atoms (same offset in both CTAs of the pair)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + N_ASTAGE * STAGE;
-  const uint32_t bar_base = b_base + N_BSTAGE * STAGE;
+  const uint32_t b_base = smem_base + NA * STG;
+  const uint32_t bar_base = b_base + NB * STG;
   // barrier slots (8 B each)
   const uint32_t a_full = bar_base, a_empty = bar_base + 16;          // 2 + 2
   const uint32_t b_full = bar_base + 32, b_empty = bar_base + 64;     // 4 + 4
@@ -355,7 +403,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
   const uint32_t tmem_slot = bar_base + 128;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + (N_ASTAGE + N_BSTAGE) * STAGE + 128);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (NA + NB) * STG + 128);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -363,14 +411,24 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
   const int n_pairs_cta = gridDim.x >> 1;        // CTA pairs in the grid
   const int pair_id = blockIdx.x >> 1;
 
-  if (P.q_flags[0] != 0) return;  // general-float query: the exact fp32 kernel owns this batch
+  // One parallel sweep over the pair flags: a launch with no frame pair of this kernel's kind
+  // (all integer-valued, or all general-float) costs a single memory round trip.
+  {
+    const int qg = P.q_flags[0] != 0;
+    int mine = 0;
+    for (int p = threadIdx.x; p < P.n_pairs; p += TC_THREADS)
+      if (((qg | (P.pairs[p].t_flags[0] != 0)) != 0) == GEN &&
+          P.tile_prefix[p + 1] != P.tile_prefix[p])
+        mine = 1;
+    if (__syncthreads_or(mine) == 0) return;  // both CTAs of the pair reach the same verdict
+  }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < N_ASTAGE; s++) {
+    for (int s = 0; s < NA; s++) {
       mbar_init(a_full + 8 * s, 1);    // leader producer's arrive.expect_tx (bytes of both CTAs)
       mbar_init(a_empty + 8 * s, 1);   // tcgen05.commit multicast
     }
-    for (int s = 0; s < N_BSTAGE; s++) {
+    for (int s = 0; s < NB; s++) {
       mbar_init(b_full + 8 * s, 1);
       mbar_init(b_empty + 8 * s, 1);
     }
@@ -395,7 +453,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     // ================= TMA producer (both CTAs; each loads its own halves) =================
     if (elect_one()) {
       TileIter it;
-      it.init(P, pair_id, n_pairs_cta);
+      it.init(P, pair_id, n_pairs_cta, GEN);
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       int maps_of_pair = -1;
       bool new_seg = true;
@@ -410,25 +468,33 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
         }
         if (new_seg) {
           mbar_wait(a_empty + 8 * a_stage, a_phase ^ 1);
-          const uint32_t dst = a_base + a_stage * STAGE;
+          const uint32_t dst = a_base + a_stage * STG;
           const uint32_t bar = a_full + 8 * a_stage;
           const int row0 = it.rb * 2 * BM + (int)rank * BM;
-          if (rank == 0) mbar_expect_tx(bar, 2 * STAGE);
+          if (rank == 0) mbar_expect_tx(bar, 2 * STG);
           tma_load_2d(dst, P.q_tmap, bar, 0, row0);
           tma_load_2d(dst + KBLK, P.q_tmap, bar, 64, row0);
-          tma_load_2d(dst + AUG_OFF, P.q_tmap + 1, bar, 0, row0 >> 3);
-          if (++a_stage == N_ASTAGE) { a_stage = 0; a_phase ^= 1; }
+          if (GEN) {
+            tma_load_2d(dst + 2 * KBLK, P.q_tmap + 2, bar, 0, row0);
+            tma_load_2d(dst + 3 * KBLK, P.q_tmap + 2, bar, 64, row0);
+          }
+          tma_load_2d(dst + AUG, P.q_tmap + 1, bar, 0, row0 >> 3);
+          if (++a_stage == NA) { a_stage = 0; a_phase ^= 1; }
         }
         mbar_wait(b_empty + 8 * b_stage, b_phase ^ 1);
         {
-          const uint32_t dst = b_base + b_stage * STAGE;
+          const uint32_t dst = b_base + b_stage * STG;
           const uint32_t bar = b_full + 8 * b_stage;
           const int row0 = it.cb * BN + (int)rank * BNH;
-          if (rank == 0) mbar_expect_tx(bar, 2 * STAGE);
+          if (rank == 0) mbar_expect_tx(bar, 2 * STG);
           tma_load_2d(dst, it.tmap, bar, 0, row0);
           tma_load_2d(dst + KBLK, it.tmap, bar, 64, row0);
-          tma_load_2d(dst + AUG_OFF, it.tmap + 1, bar, 0, row0 >> 3);
-          if (++b_stage == N_BSTAGE) { b_stage = 0; b_phase ^= 1; }
+          if (GEN) {
+            tma_load_2d(dst + 2 * KBLK, it.tmap + 2, bar, 0, row0);
+            tma_load_2d(dst + 3 * KBLK, it.tmap + 2, bar, 64, row0);
+          }
+          tma_load_2d(dst + AUG, it.tmap + 1, bar, 0, row0 >> 3);
+          if (++b_stage == NB) { b_stage = 0; b_phase ^= 1; }
         }
         new_seg = it.next(P);
       }
@@ -437,7 +503,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     // ================= MMA issuer (leader CTA only) =================
     if (rank == 0 && elect_one()) {
       TileIter it;
-      it.init(P, pair_id, n_pairs_cta);
+      it.init(P, pair_id, n_pairs_cta, GEN);
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, t_stage = 0, t_phase = 0;
       int cur_a = 0;
       bool new_seg = true;
@@ -451,27 +517,34 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
         if (new_seg) {
           mbar_wait(a_full + 8 * a_stage, a_phase);
           cur_a = a_stage;
-          if (++a_stage == N_ASTAGE) { a_stage = 0; a_phase ^= 1; }
+          if (++a_stage == NA) { a_stage = 0; a_phase ^= 1; }
         }
         mbar_wait(b_full + 8 * b_stage, b_phase);
         mbar_wait(t_empty + 8 * t_stage, t_phase ^ 1);
         tc_fence_after();
-        const uint32_t a_addr = a_base + cur_a * STAGE;
-        const uint32_t b_addr = b_base + b_stage * STAGE;
+        const uint32_t a_addr = a_base + cur_a * STG;
+        const uint32_t b_addr = b_base + b_stage * STG;
         const uint32_t d_tmem = tmem_base + t_stage * BN;
         if (P.mode < 3) {
+          // exact mode: -(q.t); general floats: -(qh.th + qh.tl + ql.th), hi at k-blocks 0-1 and lo
+          // at k-blocks 2-3 of the stage
+          constexpr int N_TERMS = GEN ? 3 : 1;
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const uint64_t ad = desc_sw128(a_addr + (k >> 2) * KBLK + (k & 3) * 32);
-            const uint64_t bd = desc_sw128(b_addr + (k >> 2) * KBLK + (k & 3) * 32);
-            tc_mma(d_tmem, ad, bd, IDESC_NEG, k > 0 ? 1u : 0u);
+          for (int term = 0; term < N_TERMS; term++) {
+            const uint32_t ao = a_addr + (term == 2 ? 2 * KBLK : 0);
+            const uint32_t bo = b_addr + (term == 1 ? 2 * KBLK : 0);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const uint64_t ad = desc_sw128(ao + (k >> 2) * KBLK + (k & 3) * 32);
+              const uint64_t bd = desc_sw128(bo + (k >> 2) * KBLK + (k & 3) * 32);
+              tc_mma(d_tmem, ad, bd, IDESC_NEG, (term | k) > 0 ? 1u : 0u);
+            }
           }
-          tc_mma(d_tmem, desc_interleave(a_addr + AUG_OFF), desc_interleave(b_addr + AUG_OFF),
-                 IDESC_POS, 1u);
+          tc_mma(d_tmem, desc_interleave(a_addr + AUG), desc_interleave(b_addr + AUG), IDESC_POS, 1u);
         }
         tc_commit(b_empty + 8 * b_stage);
         tc_commit(t_full + 8 * t_stage);
-        if (++b_stage == N_BSTAGE) { b_stage = 0; b_phase ^= 1; }
+        if (++b_stage == NB) { b_stage = 0; b_phase ^= 1; }
         if (++t_stage == 2) { t_stage = 0; t_phase ^= 1; }
         new_seg = it.next(P);
         if (new_seg) tc_commit(a_empty + 8 * cur_a);  // the segment's MMAs are done with A
@@ -485,10 +558,10 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int row_in_tile = (int)rank * BM + quarter * 32 + lane;  // within the pair's 256 rows
     TileIter it;
-    it.init(P, pair_id, n_pairs_cta);
+    it.init(P, pair_id, n_pairs_cta, GEN);
     int t_stage = 0, t_phase = 0;
-    float m1 = __int_as_float(0x7f800000), m2 = m1, s1 = m1;
-    int i1 = -1, i2 = -1;
+    EpiState st;
+    st.reset();
     int seg_pair = -1, seg_rb = 0;
     bool new_seg = true;
     bool first_tile = true;
@@ -501,8 +574,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       if (new_seg) {
         seg_pair = it.pair; seg_rb = it.rb;
         seg_ntiles = it.n_tiles; seg_ncb = it.n_cb; seg_c = it.slot_c;
-        m1 = m2 = s1 = __int_as_float(0x7f800000);
-        i1 = i2 = -1;
+        st.reset();
       }
       mbar_wait(t_full + 8 * t_stage, t_phase);
       tc_fence_after();
@@ -522,7 +594,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
           for (int j = 0; j < 32; j++)
             P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * c + j] = __uint_as_float(va[j]);
         }
-        if (P.mode < 1) process_chunk(va, gid_tile + 4 * c, m1, i1, s1, m2, i2);
+        if (P.mode < 1) process_chunk<GEN>(va, gid_tile + 4 * c, st);
         if (P.mode < 2) {
           TMEM_WAIT32(vb);
           if (c + 2 < CHUNKS) TMEM_LD32(t_addr + 32 * (c + 2), va);
@@ -539,7 +611,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
           for (int j = 0; j < 32; j++)
             P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * (c + 1) + j] = __uint_as_float(vb[j]);
         }
-        if (P.mode < 1) process_chunk(vb, gid_tile + 4 * (c + 1), m1, i1, s1, m2, i2);
+        if (P.mode < 1) process_chunk<GEN>(vb, gid_tile + 4 * (c + 1), st);
       }
       first_tile = false;
       if (++t_stage == 2) { t_stage = 0; t_phase ^= 1; }
@@ -553,12 +625,20 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
           ord = 0;
         }
         const int slot = COL_SPLITS * ord + half;
-        uint4 rec;
-        // {best chunk min, second chunk min, second group min inside the best chunk,
-        //  gid of the best | gid of the second << 16}; 0xFFFF = absent (gids fit: T <= 524k rows)
-        rec.x = __float_as_uint(m1); rec.y = __float_as_uint(m2); rec.z = __float_as_uint(s1);
-        rec.w = ((uint32_t)i1 & 0xFFFFu) | ((uint32_t)i2 << 16);
-        P.cand[((size_t)seg_pair * P.n_slots + slot) * P.nq_pad + seg_rb * 2 * BM + row_in_tile] = rec;
+        const size_t at = ((size_t)seg_pair * P.n_slots + slot) * P.nq_pad + seg_rb * 2 * BM + row_in_tile;
+        if (GEN) {
+          // two 16-byte records: the four chunk minima; their group indices and the bound
+          P.cand[2 * at] = make_uint4(__float_as_uint(st.m[0]), __float_as_uint(st.m[1]),
+                                      __float_as_uint(st.m[2]), __float_as_uint(st.m[3]));
+          P.cand[2 * at + 1] = make_uint4(((uint32_t)st.i[0] & 0xFFFFu) | ((uint32_t)st.i[1] << 16),
+                                          ((uint32_t)st.i[2] & 0xFFFFu) | ((uint32_t)st.i[3] << 16),
+                                          __float_as_uint(st.s), 0u);
+        } else {
+          // {best chunk min, second chunk min, second group min inside the best chunk,
+          //  gid of the best | gid of the second << 16}; 0xFFFF = absent (gids fit: T <= 524k rows)
+          P.cand[at] = make_uint4(__float_as_uint(st.m[0]), __float_as_uint(st.m[1]), __float_as_uint(st.s),
+                                  ((uint32_t)st.i[0] & 0xFFFFu) | ((uint32_t)st.i[1] << 16));
+        }
       }
     }
   }
@@ -658,9 +738,9 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
     if (!has0) R.part[((size_t)pair * R.n_split) * R.nq + q] = none;  // empty train set
     survive = has0;
     // L = the smallest d^2/2 outside the best group: the second group of the best chunk or the
-    // second-best chunk.  Values >= 2^28 come from padding columns, i.e. "no such element".
+    // second-best chunk.  +inf comes from padding columns, i.e. "no such element".
     const float L = fminf(s0, v1);
-    if (R.prune && has0 && L < 268435456.0f) {
+    if (R.prune && has0 && L < INF) {
       const float d0 = sqrtf(2.0f * v0), D1 = sqrtf(2.0f * L);
       if (!((double)d0 < __dmul_rn(R.ratio, (double)D1))) {
         R.part[((size_t)pair * R.n_split) * R.nq + q] =
@@ -736,7 +816,7 @@ __global__ void __launch_bounds__(256) sift_rerank_lite_kernel(const RerankParam
         rec.x = __float_as_uint(sqrtf((float)d2));
         rec.y = (uint32_t)(k0 & 0xFFFFFFFFu);
         // second distance: inside the group, or the bound from outside it (exact values both)
-        float d1sq = vl.y < 268435456.0f ? 2.0f * vl.y : -1.0f;
+        float d1sq = vl.y < __int_as_float(0x7f800000) ? 2.0f * vl.y : -1.0f;
         if (k1 != ~0ull) {
           const float x2 = (float)(uint32_t)(k1 >> 32);
           d1sq = (d1sq < 0.0f || x2 < d1sq) ? x2 : d1sq;
@@ -829,6 +909,229 @@ __global__ void __launch_bounds__(256) sift_rerank_kernel(const RerankParams R) 
   }
 }
 
+// ================= general-float pairs: certify-or-fallback rerank =================
+struct GenParams {
+  const float* q_f32;
+  const float* q_nrmf;
+  const int32_t* q_flags;
+  const TcPair* pairs;
+  const int32_t* tile_prefix;
+  const uint4* cand;
+  int nq, nq_pad, n_slots, n_pairs, n_split, n_cta;
+  uint4* part;
+  uint2* fb_list;     // rows whose answer could not be certified: {pair, row}
+  int32_t* fb_count;
+};
+
+// sqrtf(hal::normL2Sqr_(q, t, 128)) in OpenCV's own summation order (see sift_exact.cu): 4 x 4
+// accumulators, separately rounded multiply and add, ((a0+a1)+a2)+a3 per lane, (S0+S2)+(S1+S3).
+__device__ __forceinline__ float l2_cv_order(const float* __restrict__ q, const float* __restrict__ t) {
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int l = 0; l < 4; l++) acc[a][l] = 0.f;
+#pragma unroll 2
+  for (int i = 0; i < 8; i++) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const float4 qv = *reinterpret_cast<const float4*>(q + 16 * i + 4 * a);
+      const float4 tv = *reinterpret_cast<const float4*>(t + 16 * i + 4 * a);
+      float d;
+      d = __fsub_rn(qv.x, tv.x); acc[a][0] = __fadd_rn(acc[a][0], __fmul_rn(d, d));
+      d = __fsub_rn(qv.y, tv.y); acc[a][1] = __fadd_rn(acc[a][1], __fmul_rn(d, d));
+      d = __fsub_rn(qv.z, tv.z); acc[a][2] = __fadd_rn(acc[a][2], __fmul_rn(d, d));
+      d = __fsub_rn(qv.w, tv.w); acc[a][3] = __fadd_rn(acc[a][3], __fmul_rn(d, d));
+    }
+  }
+  float S[4];
+#pragma unroll
+  for (int l = 0; l < 4; l++)
+    S[l] = __fadd_rn(__fadd_rn(__fadd_rn(acc[0][l], acc[1][l]), acc[2][l]), acc[3][l]);
+  return sqrtf(__fadd_rn(__fadd_rn(S[0], S[2]), __fadd_rn(S[1], S[3])));
+}
+
+__device__ __forceinline__ void key_top2(unsigned long long key, unsigned long long& k0,
+                                         unsigned long long& k1) {
+  if (key < k1) {
+    if (key < k0) { k1 = k0; k0 = key; } else { k1 = key; }
+  }
+}
+__device__ __forceinline__ void warp_top2(unsigned long long& k0, unsigned long long& k1) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, off);
+    const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off);
+    const unsigned long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0;
+    const unsigned long long s2 = k1 < o1 ? k1 : o1;
+    k0 = lo;
+    k1 = hi < s2 ? hi : s2;
+  }
+}
+
+// One warp per (general-float pair, query row).  The tcgen05 accumulators are approximations of
+// d^2/2 (two-term bf16 split): |2*acc - d^2| <= E = 2^-13 (|q|^2 + max|t|^2), a worst-case bound
+// (dropped lo.lo and residual terms: 2^-16.4; 400 truncating fp32 accumulations of terms whose
+// magnitudes sum to <= 1.01 (|q|^2+|t|^2): 2^-13.3).  The row's best four chunks (128 columns)
+// are evaluated exactly in OpenCV's summation order; every other column is bounded below by the
+// fifth-best chunk minimum.  If that bound, minus E, clears the exact second distance, the answer
+// is provably the one cv::BFMatcher gives (ties included); otherwise the row goes to the exact
+// full-row fallback.  Nothing is ever returned uncertified.
+__global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G) {
+  const int pair = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const TcPair* pr = G.pairs + pair;
+  if ((G.q_flags[0] | pr->t_flags[0]) == 0) return;  // exact-mode pair: not ours (block-uniform)
+  if (q >= G.nq) return;                             // warp-uniform
+  const int n_tiles = G.tile_prefix[pair + 1] - G.tile_prefix[pair];
+  int n_valid = 0;
+  if (n_tiles > 0) {
+    const int n_rb = G.nq_pad / 256, n_cb = n_tiles / n_rb, rb = q >> 8;
+    const int first = owner_cta(n_tiles, G.n_cta, rb * n_cb);
+    const int last = owner_cta(n_tiles, G.n_cta, (rb + 1) * n_cb - 1);
+    n_valid = min(COL_SPLITS * (last - first + 1), G.n_slots);
+  }
+  const float INF = __int_as_float(0x7f800000);
+  // order-preserving key: the approximations can be slightly negative, so flip like a radix sort
+  auto fkey = [](float v, int g) -> unsigned long long {
+    uint32_t u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (uint32_t)g;
+  };
+  // this lane's slot record: four sorted (value, gid) entries and a bound for the rest of its slot
+  unsigned long long ek[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  float ev[4] = {INF, INF, INF, INF};
+  float rest = INF;
+  for (int s = lane; s < n_valid; s += 32) {
+    const size_t at = ((size_t)pair * G.n_slots + s) * G.nq_pad + q;
+    const uint4 ra = G.cand[2 * at], rb2 = G.cand[2 * at + 1];
+    const float v4[4] = {__uint_as_float(ra.x), __uint_as_float(ra.y), __uint_as_float(ra.z),
+                         __uint_as_float(ra.w)};
+    const int g4[4] = {(int)(rb2.x & 0xFFFFu), (int)(rb2.x >> 16), (int)(rb2.y & 0xFFFFu),
+                       (int)(rb2.y >> 16)};
+    rest = fminf(rest, __uint_as_float(rb2.z));
+    if (s < 32) {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (g4[k] != 0xFFFF) { ek[k] = fkey(v4[k], g4[k]); ev[k] = v4[k]; }
+    } else {  // more than 32 slots: the extra records only tighten nothing, they bound
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (g4[k] != 0xFFFF) rest = fminf(rest, v4[k]);
+    }
+  }
+  // global best four chunks: four rounds of "warp minimum of the lanes' heads, owner pops"
+  int cols[4];
+  bool hask[4];
+  float cval[4];   // approximate minimum of each selected chunk
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const unsigned long long mine = ek[0];
+    unsigned long long best = mine;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+      best = o < best ? o : best;
+    }
+    hask[r] = best != ~0ull;
+    cols[r] = hask[r] ? (int)((uint32_t)best >> 2) * 32 : 0;   // first column of that chunk
+    const bool owner = hask[r] && mine == best;   // keys are unique (distinct chunks): one lane pops
+    const unsigned ob = __ballot_sync(0xffffffffu, owner);
+    cval[r] = hask[r] ? __shfl_sync(0xffffffffu, ev[0], __ffs(ob) - 1) : INF;
+    if (owner) {
+      ek[0] = ek[1]; ek[1] = ek[2]; ek[2] = ek[3]; ek[3] = ~0ull;
+      ev[0] = ev[1]; ev[1] = ev[2]; ev[2] = ev[3]; ev[3] = INF;
+    }
+  }
+  // everything this lane still holds bounds the columns that are not evaluated
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (ek[k] != ~0ull) rest = fminf(rest, ev[k]);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) rest = fminf(rest, __shfl_xor_sync(0xffffffffu, rest, off));
+
+  // Exact distances (OpenCV order), one column per lane per chunk.  Two stages: the best two
+  // chunks first; if the certificate already holds against everything else (chunks 3 and 4
+  // included), the other 64 columns are never touched -- the common case.
+  const float* qrow = G.q_f32 + (size_t)q * 128;
+  const double E = ((double)G.q_nrmf[q] + (double)__int_as_float(pr->t_flags[2])) * (1.0 / 8192.0);
+  auto certified_against = [&](float bound, unsigned long long second) -> bool {
+    if (!(bound < INF)) return true;            // +inf (or NaN): only padding is left
+    if (second == ~0ull) return false;          // fewer than two evaluated columns, more exist
+    const float d1 = __uint_as_float((uint32_t)(second >> 32));
+    const double D2 = (double)d1 * (double)d1 * (1.0 + 4.8e-7);       // d^2 of the 2nd best, rounded up
+    const double lower = (2.0 * (double)bound - E) * (1.0 - 3.9e-6);  // oracle d^2 of any other column
+    return lower > D2;
+  };
+  unsigned long long e0 = ~0ull, e1 = ~0ull;
+  bool certified = false;
+#pragma unroll 1
+  for (int stage = 0; stage < 2; stage++) {
+    unsigned long long l0 = ~0ull, l1 = ~0ull;
+#pragma unroll 1
+    for (int r = 2 * stage; r < 2 * stage + 2; r++) {
+      const int col = cols[r] + lane;
+      if (hask[r] && col < pr->t_n) {
+        const float d = l2_cv_order(qrow, pr->t_f32 + (size_t)col * 128);
+        key_top2(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)col, l0, l1);
+      }
+    }
+    warp_top2(l0, l1);
+    key_top2(l0, e0, e1);
+    key_top2(l1, e0, e1);
+    const float bound = stage == 0 ? fminf(rest, fminf(cval[2], cval[3])) : rest;
+    certified = certified_against(bound, e1);
+    if (certified || !hask[2]) break;   // warp-uniform
+  }
+  if (lane == 0) {
+    uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+    if (e0 != ~0ull) { rec.x = (uint32_t)(e0 >> 32); rec.y = (uint32_t)e0; }
+    if (e1 != ~0ull) { rec.z = (uint32_t)(e1 >> 32); rec.w = (uint32_t)e1; }
+    G.part[((size_t)pair * G.n_split) * G.nq + q] = rec;
+    const uint4 none = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+    for (int sp = 1; sp < G.n_split; sp++) G.part[((size_t)pair * G.n_split + sp) * G.nq + q] = none;
+    // not certified even after all four chunks: exact full-row fallback
+    if (!certified) {
+      const int at = atomicAdd(G.fb_count, 1);
+      G.fb_list[at] = make_uint2((uint32_t)pair, (uint32_t)q);
+    }
+  }
+}
+
+// Exact full-row scan for the rows the certificate could not clear: one block per listed row,
+// every thread strides over the train rows, OpenCV's arithmetic throughout.
+__global__ void __launch_bounds__(256) sift_gen_fallback_kernel(const GenParams G) {
+  __shared__ __align__(16) float qs[128];
+  __shared__ unsigned long long red[2][8];
+  const int n = *G.fb_count;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint2 w = G.fb_list[i];
+    const int pair = (int)w.x, q = (int)w.y;
+    const TcPair* pr = G.pairs + pair;
+    __syncthreads();
+    if (threadIdx.x < 128) qs[threadIdx.x] = G.q_f32[(size_t)q * 128 + threadIdx.x];
+    __syncthreads();
+    unsigned long long k0 = ~0ull, k1 = ~0ull;
+    for (int t = threadIdx.x; t < pr->t_n; t += 256) {
+      const float d = l2_cv_order(qs, pr->t_f32 + (size_t)t * 128);
+      key_top2(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)t, k0, k1);
+    }
+    warp_top2(k0, k1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = k0; red[1][warp] = k1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long b0 = ~0ull, b1 = ~0ull;
+      for (int k = 0; k < 8; k++) { key_top2(red[0][k], b0, b1); key_top2(red[1][k], b0, b1); }
+      uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+      if (b0 != ~0ull) { rec.x = (uint32_t)(b0 >> 32); rec.y = (uint32_t)b0; }
+      if (b1 != ~0ull) { rec.z = (uint32_t)(b1 >> 32); rec.w = (uint32_t)b1; }
+      G.part[((size_t)pair * G.n_split) * G.nq + q] = rec;
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -851,23 +1154,24 @@ EncodeTiledFn get_encode_fn() {
 int g_tc_mode = 0;
 extern "C" int slamb200_dbg_set_tc_mode(int m) { g_tc_mode = m; return 0; }
 
-// Encodes a frame's tensor maps into host_out (3 x 128 B): [0] main, [1] aug (query role),
-// [2] aug (train role).
-//   main: bf16 [n_pad][128] row-major, box 64 x 128, SWIZZLE_128B
+// Encodes a frame's tensor maps into host_out (4 x 128 B): [0] main (hi), [1] aug (query role),
+// [2] aug (train role), [3] lo half.
+//   main / lo: bf16 [n_pad][128] row-major, box 64 x 128, SWIZZLE_128B
 //   aug : the interleaved K-augmentation block viewed as bytes [n_pad/8][256], box 256 x 16
 //         (= 128 rows, a dense 4 KB copy), no swizzle
-int tc_encode_tmaps(const void* bf16_dev, const void* augq_dev, const void* augt_dev, int n_pad,
-                    void* host_out_384B) {
+int tc_encode_tmaps(const void* bf16_dev, const void* augq_dev, const void* augt_dev,
+                    const void* bf16lo_dev, int n_pad, void* host_out_512B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -1;
-  CUtensorMap* out = reinterpret_cast<CUtensorMap*>(host_out_384B);
-  {
+  CUtensorMap* out = reinterpret_cast<CUtensorMap*>(host_out_512B);
+  const void* mains[2] = {bf16_dev, bf16lo_dev};
+  for (int i = 0; i < 2; i++) {
     cuuint64_t dims[2] = {128, (cuuint64_t)n_pad};
     cuuint64_t strides[1] = {256};
     cuuint32_t box[2] = {64, 128};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(&out[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(bf16_dev), dims,
-                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = fn(&out[i == 0 ? 0 : 3], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(mains[i]),
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -2;
   }
@@ -895,23 +1199,27 @@ int tc_slots(int n_cb_max, int total_tiles, int n_cta) {
   return COL_SPLITS * segs;
 }
 
-int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_flags, int nq,
+int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_flags, int nq,
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
-                              int32_t* err_flag, float* dbg, cudaStream_t s) {
+                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(sift_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(sift_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(sift_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SMEM_BYTES) != cudaSuccess)
+        cudaFuncSetAttribute(sift_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(sift_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM_BYTES_G) != cudaSuccess ||
+        cudaFuncSetAttribute(sift_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM_BYTES_G) != cudaSuccess)
       return -1;
     attr_done = true;
   }
   if (total_tiles <= 0 || nq <= 0) return 0;
   const int n_rb = (nq + 2 * BM - 1) / (2 * BM);
   TcParams P;
-  memcpy(P.q_tmap, q_tmaps_host_256B, 256);
+  memcpy(P.q_tmap, q_tmaps_host_384B, 384);   // {main, aug (query role), lo}
   P.pairs = pairs_dev;
   P.tile_prefix = tile_prefix_dev;
   P.q_flags = q_flags;
@@ -924,12 +1232,34 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_256B, const int32_t* q_fl
   P.dbg = dbg;
   P.err_flag = err_flag;
   P.mode = g_tc_mode;
-  if (dbg)
-    sift_tc_kernel<true><<<2 * n_cta_pairs, TC_THREADS, SMEM_BYTES, s>>>(P);
-  else
-    sift_tc_kernel<false><<<2 * n_cta_pairs, TC_THREADS, SMEM_BYTES, s>>>(P);
+  const dim3 grid(2 * n_cta_pairs);
+  if (gen) {
+    if (dbg) sift_tc_kernel<true, true><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P);
+    else sift_tc_kernel<false, true><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P);
+  } else {
+    if (dbg) sift_tc_kernel<true, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P);
+    else sift_tc_kernel<false, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P);
+  }
   COUNT_LAUNCH();
   return 0;
+}
+
+void launch_sift_gen_rerank(const int32_t* q_flags, const float* q_f32, const float* q_nrmf, int nq,
+                            const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                            int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
+                            uint2* fb_list, int32_t* fb_count, cudaStream_t s) {
+  if (nq <= 0 || n_pairs <= 0) return;
+  GenParams G;
+  G.q_f32 = q_f32; G.q_nrmf = q_nrmf; G.q_flags = q_flags; G.pairs = pairs_dev;
+  G.tile_prefix = tile_prefix_dev; G.cand = cand;
+  G.nq = nq; G.nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM); G.n_slots = n_slots;
+  G.n_pairs = n_pairs; G.n_split = n_split; G.n_cta = n_cta_pairs;
+  G.part = part; G.fb_list = fb_list; G.fb_count = fb_count;
+  dim3 grid((nq + 7) / 8, n_pairs);
+  sift_gen_rerank_kernel<<<grid, 256, 0, s>>>(G);
+  COUNT_LAUNCH();
+  sift_gen_fallback_kernel<<<148 * 4, 256, 0, s>>>(G);
+  COUNT_LAUNCH();
 }
 
 void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,

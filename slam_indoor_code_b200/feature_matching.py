@@ -80,7 +80,8 @@ class Context:
     def launch_count(self):
         return int(self._lib.slamb200_launch_count(self._h))
 
-    KERNELS = ("sift_tc", "sift_exact", "orb", "ransac", "sift_rerank", "finalize")
+    KERNELS = ("sift_tc", "sift_exact", "orb", "ransac", "sift_rerank", "finalize", "sift_tc_gen",
+               "sift_gen_rerank")
 
     def profile_enable(self, on=True):
         check(self._lib.slamb200_profile_enable(self._h, 1 if on else 0))

@@ -353,3 +353,51 @@ def test_cfg4_large_frames_window(ctx):
     assert len(res[(0, 2)]) >= 2500
     idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, sets[0], sets[1])
     _check_knn(idx[rows], dist[rows], *c_oracle.l2_knn2(frames[0][rows], frames[1]))
+
+
+def test_general_float_certificate_and_fallback(ctx):
+    """General floats go through the two-term-split tensor-core kernel; its answer is only used
+    when a rigorous error bound certifies it.  Near-duplicate clusters make hundreds of train rows
+    (spread over many chunks) indistinguishable within that bound, so those query rows must take
+    the exact full-row fallback -- and everything must still equal cv2's result bit for bit."""
+    import ctypes
+    rng = np.random.default_rng(77)
+    q, t = synth.float_pair(600, 6000, 1501)
+    # 40 queries each get 150 near-copies scattered over the whole train set
+    for k in range(40):
+        rows = rng.choice(6000, 150, replace=False)
+        t[rows] = q[k] + rng.normal(0, 2e-3, (150, 128)).astype(np.float32)
+    # exact duplicates too (ties -> lowest index)
+    t[100] = t[4000] = t[5999] = q[50]
+    Q, T = ctx.upload(q), ctx.upload(t)
+    assert Q.exact_mode == 0
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, Q, T)
+    ridx, rdist = c_oracle.l2_knn2(q, t)
+    _check_knn(idx, dist, ridx, rdist)
+    good = ctx.matchFeatures(Q, T, MatcherType.SIFT_BF, 0.9)
+    assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.9))
+    # the fallback did run (device-resident batch so that the debug counter refers to this call)
+    ctx.matchBatchEnqueue(Q, [T], MatcherType.SIFT_BF, 0.9)
+    lib = ctx._lib
+    lib.slamb200_dbg_last_fallback_rows.argtypes = [ctypes.c_void_p]
+    n_fb = lib.slamb200_dbg_last_fallback_rows(ctx._h)
+    assert 30 <= n_fb <= 600, n_fb
+    got, _ = ctx.batchFetch()
+    assert np.array_equal(got[0], c_oracle.ratio_test(ridx, rdist, 0.9))
+
+
+def test_general_float_scales_and_signs(ctx):
+    """Negative values, tiny and huge magnitudes, unit-norm rows (RootSIFT-like)."""
+    rng = np.random.default_rng(78)
+    base = rng.standard_normal((900, 128)).astype(np.float32)
+    for scale in (1e-3, 1.0, 3e4):
+        q = (base[:300] * scale).astype(np.float32)
+        t = (base[200:] * scale + rng.standard_normal((700, 128)).astype(np.float32) * scale * 0.05).astype(np.float32)
+        idx, dist, _ = _knn_and_matches(ctx, MatcherType.SIFT_BF, q, t)
+        _check_knn(idx, dist, *c_oracle.l2_knn2(q, t))
+    qi, ti = synth.sift_pair(500, 800, 1502)
+    rs = lambda x: np.sqrt(x / np.maximum(x.sum(1, keepdims=True), 1e-9)).astype(np.float32)
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.SIFT_BF, rs(qi), rs(ti))
+    ridx, rdist = c_oracle.l2_knn2(rs(qi), rs(ti))
+    _check_knn(idx, dist, ridx, rdist)
+    assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.7))
