@@ -457,6 +457,17 @@ def extras(ctx, stream):
     ms = ev_time(lambda: ctx.matchBatchEnqueue(Q, [T], MatcherType.SIFT_BF, RATIO, stream), 50)
     out["cfg1_sift_single_pair"] = {"us_per_pair": ms * 1e3, "pairs_per_s": 1e3 / ms,
                                     "tflops": FLOP_PER_PAIR / ms / 1e9}
+    # cfg1 (ii): float descriptors that are not integer valued -> two-term bf16 split + certified rerank.
+    # RootSIFT (sqrt of L1-normalised SIFT) is the realistic case, uniform noise the worst case.
+    qi, ti = synth.sift_pair(N_ROWS, N_ROWS, 1002)
+    root = lambda d: np.sqrt(d / np.maximum(d.sum(1, keepdims=True), 1)).astype(np.float32)
+    for name, (q, t) in (("rootsift", (root(qi), root(ti))), ("uniform_noise", synth.float_pair(N_ROWS, N_ROWS, 1002))):
+        Qf, Tf = ctx.upload(q), ctx.upload(t)
+        ms = ev_time(lambda: ctx.matchBatchEnqueue(Qf, [Tf] * 16, MatcherType.SIFT_BF, RATIO, stream), 10)
+        out["cfg1_general_float_16_pairs_" + name] = {"us_per_pair": ms / 16 * 1e3, "pairs_per_s": 16e3 / ms,
+                                                      "tflops": 16 * FLOP_PER_PAIR / ms / 1e9}
+        Qf.free()
+        Tf.free()
     q, t = synth.orb_pair(N_ROWS, N_ROWS, 2001)
     Q, T = ctx.upload(q), ctx.upload(t)
     ms = ev_time(lambda: ctx.matchBatchEnqueue(Q, [T] * 16, MatcherType.ORB_BF, RATIO, stream), 10)

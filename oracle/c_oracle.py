@@ -116,3 +116,42 @@ def sampson_errors(pts1, pts2, K4, E):
                                      E.shape[0], _p(err))
     assert rc == 0
     return err
+
+
+def _dist(dist):
+    d = np.zeros(0, np.float64) if dist is None else np.ascontiguousarray(dist, np.float64).reshape(-1)
+    if d.size > 12:
+        assert not d[12:].any(), "tilt coefficients are outside the oracle"
+        d = d[:12].copy()
+    return d
+
+
+def project_points(obj, K4, dist, pose):
+    """cv::projectPoints restatement: pose = R (row-major 9) + t (3)."""
+    obj = np.ascontiguousarray(obj, np.float32).reshape(-1, 3)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    d = _dist(dist)
+    pose = np.ascontiguousarray(pose, np.float64).reshape(12)
+    uv = np.zeros((obj.shape[0], 2), np.float32)
+    rc = lib().oracle_project_points(_p(obj), obj.shape[0], _p(K4), _p(d), d.size, _p(pose), _p(uv))
+    assert rc == 0
+    return uv
+
+
+def score_pnp(obj, img, K4, dist, poses, reproj_err, model_points=5, want_all_masks=False):
+    obj = np.ascontiguousarray(obj, np.float32).reshape(-1, 3)
+    img = np.ascontiguousarray(img, np.float32).reshape(-1, 2)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    d = _dist(dist)
+    poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 12)
+    M, H = obj.shape[0], poses.shape[0]
+    counts = np.zeros(H, np.int32)
+    best = ctypes.c_int32(-1)
+    best_mask = np.zeros(M, np.uint8)
+    allm = np.zeros((H, M), np.uint8) if want_all_masks else None
+    rc = lib().oracle_score_pnp(_p(obj), _p(img), M, _p(K4), _p(d), d.size, _p(poses), H,
+                                ctypes.c_double(reproj_err), int(model_points), _p(counts),
+                                ctypes.byref(best), _p(best_mask),
+                                _p(allm) if allm is not None else None)
+    assert rc == 0
+    return counts, int(best.value), best_mask, allm

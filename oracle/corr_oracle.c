@@ -316,3 +316,96 @@ int oracle_match_features(int matcher, const void* q, int nq, const void* t, int
     free(idx); free(dist);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * solvePnPRansac scoring (reference call: cycleProcessing/mainCycle.cpp:155-159).
+ *
+ * OpenCV's PnPRansacCallback::computeError projects every object point with the candidate pose
+ * (cv::projectPoints -> cvProjectPoints2Internal: all arithmetic in double, result stored as
+ * float) and takes err = (float)norm(Matx21f(image - projected), NORM_L2SQR), whose accumulator
+ * type for float is float: s = 0; s += dx*dx; s += dy*dy.  RANSACPointSetRegistrator::findInliers
+ * keeps err <= (float)(reprojectionError^2).  The rotation enters as the 3x3 matrix (Rodrigues of
+ * rvec is done by the caller: it needs libm's sin/cos).  dist holds up to 12 coefficients in
+ * OpenCV order (k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4); the tilt terms (tauX, tauY) must be zero,
+ * for which the tilt matrix is the identity and "matTilt * (xd0, yd0, 1)" returns xd0, yd0.
+ * Pinned against cv2.projectPoints / cv2.solvePnPRansac (tests/test_oracle_vs_cv2.py).
+ * ---------------------------------------------------------------------------------------------- */
+static void project_cv(const double* R, const double* t, const double* k, double fx, double fy,
+                       double cx, double cy, double X, double Y, double Z, float* u, float* v) {
+    double x = R[0] * X + R[1] * Y + R[2] * Z + t[0];
+    double y = R[3] * X + R[4] * Y + R[5] * Z + t[1];
+    double z = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+    z = z ? 1. / z : 1;
+    x *= z;
+    y *= z;
+    double r2 = x * x + y * y;
+    double r4 = r2 * r2;
+    double r6 = r4 * r2;
+    double a1 = 2 * x * y;
+    double a2 = r2 + 2 * x * x;
+    double a3 = r2 + 2 * y * y;
+    double cdist = 1 + k[0] * r2 + k[1] * r4 + k[4] * r6;
+    double icdist2 = 1. / (1 + k[5] * r2 + k[6] * r4 + k[7] * r6);
+    double xd0 = x * cdist * icdist2 + k[2] * a1 + k[3] * a2 + k[8] * r2 + k[9] * r4;
+    double yd0 = y * cdist * icdist2 + k[2] * a3 + k[3] * a1 + k[10] * r2 + k[11] * r4;
+    *u = (float)(xd0 * fx + cx);
+    *v = (float)(yd0 * fy + cy);
+}
+
+static float reproj_err_cv(const double* pose, const double* k, const double* K4, const float* o,
+                           const float* m) {
+    float u, v;
+    project_cv(pose, pose + 9, k, K4[0], K4[1], K4[2], K4[3], (double)o[0], (double)o[1],
+               (double)o[2], &u, &v);
+    float dx = m[0] - u, dy = m[1] - v;
+    float s = 0;
+    s += dx * dx;
+    s += dy * dy;
+    return s;
+}
+
+/* Projects M object points with one pose (R row-major 9 doubles then t 3 doubles). */
+int oracle_project_points(const float* obj, int M, const double* K4, const double* dist,
+                          int n_dist, const double* pose, float* uv /* M*2 */) {
+    if (M < 0 || n_dist < 0 || n_dist > 12) return -1;
+    double k[12] = {0};
+    for (int i = 0; i < n_dist; i++) k[i] = dist[i];
+    for (int i = 0; i < M; i++)
+        project_cv(pose, pose + 9, k, K4[0], K4[1], K4[2], K4[3], (double)obj[3 * i],
+                   (double)obj[3 * i + 1], (double)obj[3 * i + 2], &uv[2 * i], &uv[2 * i + 1]);
+    return 0;
+}
+
+/* Scores H pose hypotheses (H x 12 doubles) against M 3D-2D correspondences.  A model replaces
+ * the best iff count > max(best, model_points - 1) (ptsetreg.cpp run()). */
+int oracle_score_pnp(const float* obj, const float* img, int M, const double* K4,
+                     const double* dist, int n_dist, const double* poses, int H,
+                     double reproj_err, int model_points, int32_t* counts, int32_t* best,
+                     uint8_t* best_mask, uint8_t* all_masks) {
+    if (M < 0 || H < 0 || n_dist < 0 || n_dist > 12) return -1;
+    double k[12] = {0};
+    for (int i = 0; i < n_dist; i++) k[i] = dist[i];
+    float t = (float)(reproj_err * reproj_err);
+#pragma omp parallel for schedule(static)
+    for (int h = 0; h < H; h++) {
+        int32_t nz = 0;
+        for (int i = 0; i < M; i++) {
+            int f = reproj_err_cv(poses + 12 * (size_t)h, k, K4, obj + 3 * i, img + 2 * i) <= t;
+            if (all_masks) all_masks[(size_t)h * M + i] = (uint8_t)f;
+            nz += f;
+        }
+        counts[h] = nz;
+    }
+    int32_t bi = -1, bc = 0;
+    for (int h = 0; h < H; h++) {
+        int32_t lim = bc > model_points - 1 ? bc : model_points - 1;
+        if (counts[h] > lim) { bc = counts[h]; bi = h; }
+    }
+    *best = bi;
+    if (best_mask) {
+        for (int i = 0; i < M; i++)
+            best_mask[i] = bi < 0 ? 0 : (uint8_t)(reproj_err_cv(poses + 12 * (size_t)bi, k, K4,
+                                                               obj + 3 * i, img + 2 * i) <= t);
+    }
+    return 0;
+}

@@ -58,32 +58,24 @@ def update_num_iters(p, ep, model_points, max_iters):
     return int(np.rint(num / denom))  # cvRound: to nearest, ties to even
 
 
-def ransac_essential(points1, points2, K4, prob, threshold, five_point_fn, score_fn, max_iters=1000,
-                     chunk=32):
-    """Returns (E [9] or None, mask [N] uint8 or None, iterations run, hypotheses scored).
+def ransac_run(count, model_points, prob, max_iters, solve_fn, score_fn, chunk=32):
+    """RANSACPointSetRegistrator::run for count > model_points: returns (best model or None,
+    iterations run, hypotheses scored).
 
-    five_point_fn(p1[5,2], p2[5,2]) -> array [k, 9] of candidate models (k may be 0);
-    score_fn(E [H,9]) -> (counts [H], masks-of-request callable) -- see camera_translation."""
-    p1 = np.ascontiguousarray(points1, np.float32).reshape(-1, 2)
-    p2 = np.ascontiguousarray(points2, np.float32).reshape(-1, 2)
-    count = p1.shape[0]
-    if count < 5:
-        return None, None, 0, 0
+    solve_fn(idx list[model_points]) -> array [k, D] of candidate models (k may be 0);
+    score_fn(models [H, D]) -> counts [H]."""
     rng = CvRNG()
     niters, it, scored = max_iters, 0, 0
     best, max_good = None, 0
-    if count == 5:  # run(): exactly the minimal set -> the solver's models, mask of ones
-        E = five_point_fn(p1, p2)
-        return (E.reshape(-1) if len(E) else None), np.ones(count, np.uint8), 0, 0
     while it < niters:
         # speculate: hypotheses of the next `chunk` iterations (never past the current budget)
         n_it = min(chunk, niters - it)
         models, owner = [], []
         for j in range(n_it):
-            idx = get_subset(rng, count)
-            E = five_point_fn(p1[idx], p2[idx])
-            for e in np.asarray(E, np.float64).reshape(-1, 9):
-                models.append(e)
+            idx = get_subset(rng, count, model_points)
+            cand = np.asarray(solve_fn(idx), np.float64)
+            for m in cand.reshape(len(cand), -1) if cand.size else ():
+                models.append(m)
                 owner.append(it + j)
         if models:
             counts = score_fn(np.array(models))
@@ -91,10 +83,29 @@ def ransac_essential(points1, points2, K4, prob, threshold, five_point_fn, score
             for h, c in enumerate(counts):
                 if owner[h] >= niters:      # the budget shrank below this iteration: discard
                     break
-                if c > max(max_good, 4):
+                if c > max(max_good, model_points - 1):
                     max_good, best = int(c), models[h].copy()
-                    niters = update_num_iters(prob, (count - max_good) / count, 5, niters)
+                    niters = update_num_iters(prob, (count - max_good) / count, model_points, niters)
         it += n_it
     # the RNG drew subsets for speculated iterations past the final budget; they are discarded,
     # and cv's loop ends at the same model because the update rule was replayed in order
-    return best, None, min(it, niters) if best is not None else it, scored
+    return best, (min(it, niters) if best is not None else it), scored
+
+
+def ransac_essential(points1, points2, K4, prob, threshold, five_point_fn, score_fn, max_iters=1000,
+                     chunk=32):
+    """Returns (E [9] or None, mask [N] uint8 or None, iterations run, hypotheses scored).
+
+    five_point_fn(p1[5,2], p2[5,2]) -> array [k, 9] of candidate models (k may be 0);
+    score_fn(E [H,9]) -> counts [H] -- see camera_translation."""
+    p1 = np.ascontiguousarray(points1, np.float32).reshape(-1, 2)
+    p2 = np.ascontiguousarray(points2, np.float32).reshape(-1, 2)
+    count = p1.shape[0]
+    if count < 5:
+        return None, None, 0, 0
+    if count == 5:  # run(): exactly the minimal set -> the solver's models, mask of ones
+        E = five_point_fn(p1, p2)
+        return (E.reshape(-1) if len(E) else None), np.ones(count, np.uint8), 0, 0
+    best, iters, scored = ransac_run(count, 5, prob, max_iters,
+                                     lambda idx: five_point_fn(p1[idx], p2[idx]), score_fn, chunk)
+    return best, None, iters, scored
