@@ -486,6 +486,20 @@ def extras(ctx, stream):
     out["cfg5_ransac_2048x5000"] = {"kernel_us_per_pair": kms / kn / P * 1e3,
                                     "fp64_tflops_40flop_convention": P * 2048 * 5000 * 40 / (kms / kn) / 1e9,
                                     "dp_instr_per_s_T": P * 2048 * 5000 * 36 / (kms / kn) / 1e9}
+    # next row 8f-2: solvePnPRansac scoring, 2048 poses x 5000 correspondences, 32 frames per launch,
+    # the reference's five distortion coefficients
+    from slam_indoor_code_b200 import pnp_ransac as pr
+    obj, img, Rp, tp = synth.pnp_scene(5000, 7000)
+    poses = synth.pnp_hypotheses(2048, Rp, tp, 7001)
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    for _ in range(3):
+        pr.scorePnPBatch(ctx, [obj] * P, [img] * P, synth.SAMSUNG_HV_4K, synth.REF_DIST5, np.stack([poses] * P), 8.0)
+    kms, kn = ctx.profile_read()["pnp"]
+    ctx.profile_enable(False)
+    # 53 explicit fp64 operations per (pose, point) with five coefficients (the reciprocal counted once)
+    out["f2_pnp_2048x5000"] = {"kernel_us_per_frame": kms / kn / P * 1e3,
+                               "fp64_ops_T_per_s": P * 2048 * 5000 * 53 / (kms / kn) / 1e9}
     # pipe-rate denominators measured on this box (csrc/microbench.cu)
     try:
         import ctypes
@@ -497,6 +511,8 @@ def extras(ctx, stream):
         out["cfg2_orb_16_pairs"]["frac_of_popc_pipe"] = out["cfg2_orb_16_pairs"]["tpopc_per_s"] * 1e3 / popc
         out["cfg5_ransac_2048x5000"]["frac_of_fp64_pipe"] = \
             out["cfg5_ransac_2048x5000"]["dp_instr_per_s_T"] * 1e3 / fp64
+        out["f2_pnp_2048x5000"]["frac_of_fp64_pipe_lower_bound"] = \
+            out["f2_pnp_2048x5000"]["fp64_ops_T_per_s"] * 1e3 / fp64
     except Exception as e:  # pragma: no cover
         out["pipe_rates"] = {"error": str(e)}
     # cfg4: 8 frames x 50,000 descriptors (4K frames), all 28 i<j pairs of the BA window

@@ -155,6 +155,30 @@ int slamb200_score_essential_batch(slamb200_ctx* ctx, int P, const float* pts1,
                                    const double* E, int H, double threshold_px, int32_t* counts,
                                    int32_t* best, uint8_t* best_mask);
 
+/* ---- next row: solvePnPRansac inlier scoring (cycleProcessing/mainCycle.cpp:155-159) --- */
+/* Scores H candidate poses against M 3D-2D correspondences exactly as cv::solvePnPRansac's loop
+ * does (PnPRansacCallback::computeError + RANSACPointSetRegistrator::findInliers): obj M x 3
+ * floats (Point3f), img M x 2 floats (Point2f), K = {fx, fy, cx, cy}, dist = n_dist (0..14)
+ * coefficients in OpenCV order k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 tauX tauY (the reference passes
+ * five; non-zero tauX/tauY -> SLAMB200_ERR_INVALID), poses = H x 12 doubles, the rotation MATRIX
+ * row-major followed by t (Rodrigues of rvec stays with the caller).  Every point is projected in
+ * fp64 in cvProjectPoints2's operation order, rounded to float, err = dx*dx + dy*dy in float,
+ * inlier iff err <= (float)(reproj_err^2); a model replaces the best iff
+ * count > max(best_count, model_points - 1) (model_points: 5, or 4 when M == 4).  Outputs as
+ * slamb200_score_essential. */
+int slamb200_score_pnp(slamb200_ctx* ctx, const float* obj, const float* img, int M,
+                       const double K[4], const double* dist, int n_dist, const double* poses,
+                       int H, double reproj_err, int model_points, int32_t* counts,
+                       int32_t* best, uint8_t* best_mask, uint8_t* all_masks);
+
+/* P independent frames in one launch sequence, ragged like slamb200_score_essential_batch:
+ * poses P*H*12 doubles, counts P*H, best P, best_mask m_off[P] bytes. */
+int slamb200_score_pnp_batch(slamb200_ctx* ctx, int P, const float* obj, const float* img,
+                             const int32_t* m_off, const double K[4], const double* dist,
+                             int n_dist, const double* poses, int H, double reproj_err,
+                             int model_points, int32_t* counts, int32_t* best,
+                             uint8_t* best_mask);
+
 /* Keypoint coordinates of a frame (cv::KeyPoint::pt as x,y float pairs, `stride` bytes apart)
  * kept in HBM so that getKeyPointCoordsFromFramePair (featureMatchingCommon.cpp:23-33) can run
  * on the device between matching and scoring. */
@@ -181,7 +205,8 @@ int slamb200_batch_scores_fetch(slamb200_ctx* ctx, int32_t* counts, int32_t* bes
 #define SLAMB200_K_FINALIZE 5   /* ratio test + ordered compaction    */
 #define SLAMB200_K_SIFT_TC_GEN 6 /* tcgen05 kernel, general floats     */
 #define SLAMB200_K_SIFT_GEN_RERANK 7 /* certified fp32 rerank + fallback */
-#define SLAMB200_K_COUNT 8
+#define SLAMB200_K_PNP 8        /* reprojection-error counting kernel */
+#define SLAMB200_K_COUNT 9
 int slamb200_profile_enable(slamb200_ctx* ctx, int on);
 /* Synchronises, then returns the summed device time (ms) and the launch count of each kernel
  * class since the last read; ms and launches have SLAMB200_K_COUNT entries. */

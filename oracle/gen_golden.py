@@ -6,8 +6,10 @@ entry points the reference calls, through the cv2 wheel:
 
   featureMatchingCPU.cpp:26-40   DescriptorMatcher BRUTEFORCE / BRUTEFORCE_HAMMING, knnMatch k=2
   cameraTranslation.cpp:41-46    findEssentialMat(p1, p2, K, RANSAC, prob, threshold, mask)
+  mainCycle.cpp:155-159          solvePnPRansac(obj, img, K, dist, rvec, tvec)   
 
-Run from the repo root:   python -m oracle.gen_golden
+Run from the repo root:   python -m oracle.gen_golden          (all fixtures)
+                          python -m oracle.gen_golden pnp      (only pnp.npz)
 Everything is seeded; outputs are committed so the GPU box (no /root/reference, possibly another
 cv2 dispatch path) checks against exactly these bytes.
 """
@@ -118,9 +120,50 @@ def main():
     cases["threshold_px"] = np.float64(5.0)
     np.savez_compressed(os.path.join(OUT, "ransac.npz"), **cases)
 
+    gen_pnp()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} fixtures, {total/1024:.0f} KiB, cv2 {cv2.__version__}")
 
 
+def gen_pnp():
+    """solvePnPRansac: cv2's own result, plus per-hypothesis inlier masks built from
+    cv2.projectPoints (the call PnPRansacCallback::computeError makes) for EPnP poses of seeded
+    5-subsets."""
+    K4 = np.array(synth.SAMSUNG_HV_4K, np.float64)
+    Kmat = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float64)
+    dists = (np.array(synth.REF_DIST5), np.zeros(5),
+             np.array([0.11, -0.23, 0.0012, -0.0007, 0.09, 0.01, -0.02, 0.003, 1e-3, -2e-3, 3e-4, 1e-4]))
+    cases = {"K4": K4, "reproj": np.float64(8.0)}
+    t = np.float32(8.0 * 8.0)
+    for c, (m, seed, dv) in enumerate(((800, 7000, 0), (2000, 7001, 0), (300, 7002, 1), (500, 7003, 2),
+                                       (33, 7004, 0))):
+        dist = dists[dv]
+        obj, img, _, _ = synth.pnp_scene(m, seed, dist=tuple(dist))
+        rng = np.random.default_rng(seed + 100)
+        poses, masks = [], []
+        while len(poses) < 16:
+            idx = rng.choice(m, 5, replace=False)
+            ok, r, tv = cv2.solvePnP(obj[idx], img[idx], Kmat, dist, flags=cv2.SOLVEPNP_EPNP)
+            if not ok:
+                continue
+            uv = cv2.projectPoints(obj, r, tv, Kmat, dist)[0].reshape(-1, 2).astype(np.float32)
+            d = img - uv                                   # float32, as Point2f - Point2f
+            err = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]    # float accumulator: s = dx*dx; s += dy*dy
+            poses.append(np.concatenate([cv2.Rodrigues(r)[0].reshape(-1), tv.reshape(-1)]))
+            masks.append((err <= t).astype(np.uint8))
+        ok, rvec, tvec, inl = cv2.solvePnPRansac(obj, img, Kmat, dist)
+        cases[f"obj_{c}"], cases[f"img_{c}"], cases[f"dist_{c}"] = obj, img, dist
+        cases[f"poses_{c}"] = np.array(poses)
+        cases[f"masks_{c}"] = np.packbits(np.array(masks), axis=1)
+        cases[f"cv_ok_{c}"] = np.bool_(ok)
+        cases[f"cv_rvec_{c}"], cases[f"cv_tvec_{c}"] = rvec.reshape(3), tvec.reshape(3)
+        cases[f"cv_inliers_{c}"] = inl.reshape(-1).astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "pnp.npz"), **cases)
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "pnp":
+        gen_pnp()
+    else:
+        main()

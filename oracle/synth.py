@@ -123,3 +123,50 @@ def pose_hypotheses(h, R, t, seed, good_frac=0.25):
         Ei = _skew(ti) @ Ri
         E[i] = (Ei / np.linalg.norm(Ei) * np.sqrt(2.0)).reshape(9)
     return E
+
+
+REF_DIST5 = (0.11, -0.23, 0.0012, -0.0007, 0.09)  # k1 k2 p1 p2 k3: the reference's 1x5 "DC" Mat
+
+
+def pnp_scene(m, seed, K4=SAMSUNG_HV_4K, dist=REF_DIST5, noise_px=0.7, outliers=0.3,
+              size=(3840, 2160)):
+    """M 3D-2D correspondences of a random camera pose (the solvePnPRansac input of
+    mainCycle.cpp:155-159): object points (float32 [M,3]), image points (float32 [M,2], Gaussian
+    noise + uniform outliers), and the true (R, t).  The image points come from this module's own
+    fp64 pinhole + Brown model (no OpenCV needed)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = K4
+    k = np.zeros(12)
+    k[:len(dist)] = dist
+    R = _rodrigues(rng.normal(0, 0.15, 3))
+    t = rng.normal(0, 0.3, 3)
+    u = rng.uniform(0, size[0], m)
+    v = rng.uniform(0, size[1], m)
+    z = rng.uniform(4.0, 20.0, m)
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], axis=1)   # camera frame
+    X = ((Xc - t) @ R).astype(np.float32)                              # world: Xc = R X + t
+    Xc = X.astype(np.float64) @ R.T + t
+    x, y = Xc[:, 0] / Xc[:, 2], Xc[:, 1] / Xc[:, 2]
+    r2 = x * x + y * y
+    cd = (1 + k[0] * r2 + k[1] * r2 ** 2 + k[4] * r2 ** 3) / (1 + k[5] * r2 + k[6] * r2 ** 2 + k[7] * r2 ** 3)
+    xd = x * cd + 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 ** 2
+    yd = y * cd + k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 ** 2
+    p = np.stack([xd * fx + cx, yd * fy + cy], axis=1) + rng.normal(0, noise_px, (m, 2))
+    n_out = int(m * outliers)
+    if n_out:
+        oi = rng.choice(m, n_out, replace=False)
+        p[oi] = np.stack([rng.uniform(0, size[0], n_out), rng.uniform(0, size[1], n_out)], axis=1)
+    return X, p.astype(np.float32), R, t
+
+
+def pnp_hypotheses(h, R, t, seed, good_frac=0.25):
+    """H candidate poses [R | t] as 12 doubles each (rotation row-major, then t), a `good_frac`
+    share close to the truth (a continuum of perturbation sizes, so that many points sit near
+    the reprojection threshold), the rest as fitted to contaminated samples."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((h, 12), np.float64)
+    for i in range(h):
+        s = 10 ** rng.uniform(-4.5, -3) if rng.random() < good_frac else 10 ** rng.uniform(-3.3, -1.5)
+        out[i, :9] = (_rodrigues(rng.normal(0, s, 3)) @ R).reshape(9)
+        out[i, 9:] = t + rng.normal(0, s * 3, 3)
+    return out

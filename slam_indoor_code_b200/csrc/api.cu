@@ -950,7 +950,7 @@ extern "C" int slamb200_score_essential_batch(slamb200_ctx* c, int P, const floa
     launch_score_counts((const double4*)L.npts.p, (const int32_t*)L.m_off.p, nullptr, 0,
                         (const double*)L.E.p, H, P, sp, (int32_t*)L.counts.p, s);
   }
-  launch_score_best((const int32_t*)L.counts.p, H, P, (int32_t*)L.best.p, s);
+  launch_score_best((const int32_t*)L.counts.p, H, P, 4, (int32_t*)L.best.p, s);
   if (best_mask)
     launch_score_mask((const double4*)L.npts.p, (const int32_t*)L.m_off.p, nullptr, 0,
                       (const double*)L.E.p, H, P, (const int32_t*)L.best.p, sp, (uint8_t*)L.mask.p, s);
@@ -987,6 +987,111 @@ extern "C" int slamb200_score_essential(slamb200_ctx* c, const float* pts1, cons
   CU(cudaMemcpyAsync(L.E.p, E, sizeof(double) * 9 * (size_t)H, cudaMemcpyHostToDevice, s));
   launch_normalize_points((const float2*)L.p1.p, (const float2*)L.p2.p, M, sp, (double4*)L.npts.p, s);
   launch_score_all_masks((const double4*)L.npts.p, M, (const double*)L.E.p, H, sp, (uint8_t*)L.all_masks.p, s);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(all_masks, L.all_masks.p, (size_t)H * M, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SLAMB200_OK;
+}
+
+// ---- solvePnPRansac scoring ---------------------------------------------------
+static int make_pnp_params(const double K[4], const double* dist, int n_dist, double reproj_err,
+                           PnpParams* pp) {
+  if (!K) return fail(SLAMB200_ERR_INVALID, "K is NULL");
+  if (n_dist < 0 || (n_dist > 0 && !dist)) return fail(SLAMB200_ERR_INVALID, "bad dist/n_dist");
+  if (n_dist > 14) return fail(SLAMB200_ERR_INVALID, "more than 14 distortion coefficients");
+  pp->fx = K[0]; pp->fy = K[1]; pp->cx = K[2]; pp->cy = K[3];
+  for (int i = 0; i < 12; i++) pp->k[i] = i < n_dist ? dist[i] : 0.0;
+  for (int i = 12; i < n_dist; i++)
+    if (dist[i] != 0.0) return fail(SLAMB200_ERR_INVALID, "tilted sensor model (tauX, tauY) is not supported");
+  pp->t = (float)(reproj_err * reproj_err);
+  pp->dist_level = 0;
+  for (int i = 0; i < 5; i++) if (pp->k[i] != 0.0) pp->dist_level = 1;
+  for (int i = 5; i < 12; i++) if (pp->k[i] != 0.0) pp->dist_level = 2;
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_score_pnp_batch(slamb200_ctx* c, int P, const float* obj, const float* img,
+                                        const int32_t* m_off, const double K[4],
+                                        const double* dist, int n_dist, const double* poses, int H,
+                                        double reproj_err, int model_points, int32_t* counts,
+                                        int32_t* best, uint8_t* best_mask) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  if (P < 0 || H < 0) return fail(SLAMB200_ERR_INVALID, "P or H negative");
+  if (model_points < 1) return fail(SLAMB200_ERR_INVALID, "model_points < 1");
+  if (P == 0) return SLAMB200_OK;
+  if (!m_off) return fail(SLAMB200_ERR_INVALID, "m_off is NULL");
+  if (m_off[0] != 0) return fail(SLAMB200_ERR_INVALID, "m_off[0] must be 0");
+  for (int p = 0; p < P; p++)
+    if (m_off[p + 1] < m_off[p]) return fail(SLAMB200_ERR_INVALID, "m_off not monotone");
+  const int total = m_off[P];
+  if ((total > 0 && (!obj || !img)) || (H > 0 && !poses)) return fail(SLAMB200_ERR_INVALID, "NULL input");
+  if ((H > 0 && !counts) || !best) return fail(SLAMB200_ERR_INVALID, "NULL output");
+  PnpParams pp;
+  int rc = make_pnp_params(K, dist, n_dist, reproj_err, &pp);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  cudaStream_t s = L.stream;
+  const size_t tot = total > 0 ? total : 1;
+  const size_t hh = (size_t)P * (H > 0 ? H : 1);
+  if ((rc = buf_reserve(c, L.p1, tot * 12, s))) return rc;
+  if ((rc = buf_reserve(c, L.p2, tot * 8, s))) return rc;
+  if ((rc = buf_reserve(c, L.npts, tot * 32, s))) return rc;
+  if ((rc = buf_reserve(c, L.m_off, sizeof(int32_t) * (size_t)(P + 1), s))) return rc;
+  if ((rc = buf_reserve(c, L.E, sizeof(double) * 12 * hh, s))) return rc;
+  if ((rc = buf_reserve(c, L.counts, sizeof(int32_t) * hh, s))) return rc;
+  if ((rc = buf_reserve(c, L.best, sizeof(int32_t) * (size_t)P, s))) return rc;
+  if ((rc = buf_reserve(c, L.mask, tot, s))) return rc;
+  if (total > 0) {
+    CU(cudaMemcpyAsync(L.p1.p, obj, (size_t)total * 12, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(L.p2.p, img, (size_t)total * 8, cudaMemcpyHostToDevice, s));
+  }
+  CU(cudaMemcpyAsync(L.m_off.p, m_off, sizeof(int32_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, s));
+  if (H > 0) CU(cudaMemcpyAsync(L.E.p, poses, sizeof(double) * 12 * (size_t)P * H, cudaMemcpyHostToDevice, s));
+  launch_pack_pnp_points((const float*)L.p1.p, (const float2*)L.p2.p, total, (double4*)L.npts.p, s);
+  {
+    ProfScope ps(c, s, SLAMB200_K_PNP);
+    launch_pnp_counts((const double4*)L.npts.p, (const int32_t*)L.m_off.p, (const double*)L.E.p, H,
+                      P, pp, (int32_t*)L.counts.p, s);
+  }
+  launch_score_best((const int32_t*)L.counts.p, H, P, model_points - 1, (int32_t*)L.best.p, s);
+  if (best_mask)
+    launch_pnp_mask((const double4*)L.npts.p, (const int32_t*)L.m_off.p, (const double*)L.E.p, H, P,
+                    (const int32_t*)L.best.p, pp, (uint8_t*)L.mask.p, s);
+  CU(cudaGetLastError());
+  if (H > 0) CU(cudaMemcpyAsync(counts, L.counts.p, sizeof(int32_t) * (size_t)P * H, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(best, L.best.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
+  if (best_mask && total > 0) CU(cudaMemcpyAsync(best_mask, L.mask.p, (size_t)total, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_score_pnp(slamb200_ctx* c, const float* obj, const float* img, int M,
+                                  const double K[4], const double* dist, int n_dist,
+                                  const double* poses, int H, double reproj_err, int model_points,
+                                  int32_t* counts, int32_t* best, uint8_t* best_mask,
+                                  uint8_t* all_masks) {
+  if (M < 0) return fail(SLAMB200_ERR_INVALID, "M negative");
+  int32_t off[2] = {0, M};
+  int rc = slamb200_score_pnp_batch(c, 1, obj, img, off, K, dist, n_dist, poses, H, reproj_err,
+                                    model_points, counts, best, best_mask);
+  if (rc || !all_masks || M == 0 || H == 0) return rc;
+  PnpParams pp;
+  if ((rc = make_pnp_params(K, dist, n_dist, reproj_err, &pp))) return rc;
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  cudaStream_t s = L.stream;
+  if ((rc = buf_reserve(c, L.p1, (size_t)M * 12, s))) return rc;
+  if ((rc = buf_reserve(c, L.p2, (size_t)M * 8, s))) return rc;
+  if ((rc = buf_reserve(c, L.npts, (size_t)M * 32, s))) return rc;
+  if ((rc = buf_reserve(c, L.E, sizeof(double) * 12 * (size_t)H, s))) return rc;
+  if ((rc = buf_reserve(c, L.all_masks, (size_t)H * M, s))) return rc;
+  CU(cudaMemcpyAsync(L.p1.p, obj, (size_t)M * 12, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(L.p2.p, img, (size_t)M * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(L.E.p, poses, sizeof(double) * 12 * (size_t)H, cudaMemcpyHostToDevice, s));
+  launch_pack_pnp_points((const float*)L.p1.p, (const float2*)L.p2.p, M, (double4*)L.npts.p, s);
+  launch_pnp_all_masks((const double4*)L.npts.p, M, (const double*)L.E.p, H, pp, (uint8_t*)L.all_masks.p, s);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(all_masks, L.all_masks.p, (size_t)H * M, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -1093,7 +1198,7 @@ extern "C" int slamb200_score_batch_enqueue(slamb200_ctx* c, const slamb200_pts*
     launch_score_counts((const double4*)L.npts.p, nullptr, (const int32_t*)L.n_out.p, cap, E_dev, H,
                         P, sp, (int32_t*)L.counts.p, s);
   }
-  launch_score_best((const int32_t*)L.counts.p, H, P, (int32_t*)L.best.p, s);
+  launch_score_best((const int32_t*)L.counts.p, H, P, 4, (int32_t*)L.best.p, s);
   launch_score_mask((const double4*)L.npts.p, nullptr, (const int32_t*)L.n_out.p, cap, E_dev, H, P,
                     (const int32_t*)L.best.p, sp, (uint8_t*)L.mask.p, s);
   CU(cudaGetLastError());

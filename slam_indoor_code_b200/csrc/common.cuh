@@ -89,12 +89,29 @@ void launch_gather_normalize(const float2* q_xy, const float2* const* t_xy,
 void launch_score_counts(const double4* npts, const int32_t* m_off, const int32_t* m_cnt,
                          int m_stride, const double* E, int H, int P, ScoreParams sp,
                          int32_t* counts, cudaStream_t s);
-void launch_score_best(const int32_t* counts, int H, int P, int32_t* best, cudaStream_t s);
+void launch_score_best(const int32_t* counts, int H, int P, int min_count, int32_t* best,
+                       cudaStream_t s);
 void launch_score_mask(const double4* npts, const int32_t* m_off, const int32_t* m_cnt,
                        int m_stride, const double* E, int H, int P, const int32_t* best,
                        ScoreParams sp, uint8_t* mask, cudaStream_t s);
 void launch_score_all_masks(const double4* npts, int M, const double* E, int H, ScoreParams sp,
                             uint8_t* masks, cudaStream_t s);
+
+// solvePnPRansac scoring (reprojection error of pose hypotheses, R row-major then t).
+struct PnpParams {
+  double fx, fy, cx, cy;
+  double k[12];    // k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4
+  float t;         // (float)(reprojectionError^2)
+  int dist_level;  // 0 none, 1 first five only, 2 all twelve
+};
+void launch_pack_pnp_points(const float* obj, const float2* img, int total, double4* out,
+                            cudaStream_t s);
+void launch_pnp_counts(const double4* pts, const int32_t* m_off, const double* poses, int H, int P,
+                       const PnpParams& pp, int32_t* counts, cudaStream_t s);
+void launch_pnp_mask(const double4* pts, const int32_t* m_off, const double* poses, int H, int P,
+                     const int32_t* best, const PnpParams& pp, uint8_t* mask, cudaStream_t s);
+void launch_pnp_all_masks(const double4* pts, int M, const double* poses, int H,
+                          const PnpParams& pp, uint8_t* masks, cudaStream_t s);
 
 // SIFT prep: fp32 rows -> bf16 / aug / u8 / norms / exact flag.  n_pad rows are written
 // (padding rows get an "infinitely far" augmentation so they never become candidates).

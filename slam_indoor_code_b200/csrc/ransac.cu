@@ -27,26 +27,101 @@
 #define RS_THREADS 128
 #define RS_PTS 512  // matches per shared-memory chunk
 
-struct Emat { double e[9]; };
+// A scorer policy names the model (doubles per hypothesis), the launch parameters and the
+// per-(hypothesis, correspondence) inlier predicate; the kernels below are shared.
+struct SampsonScorer {
+  static constexpr int ND = 9;
+  typedef ScoreParams Params;
+  __device__ static __forceinline__ int inlier(const double (&e)[9], const double4 p,
+                                               const ScoreParams& sp) {
+    const double x1 = p.x, y1 = p.y, x2 = p.z, y2 = p.w;
+    // Matx33d * Vec3d(x1, y1, 1): s = 0; s += e0*x; s += e1*y; s += e2*1
+    const double a0 = __dadd_rn(__dadd_rn(__dmul_rn(e[0], x1), __dmul_rn(e[1], y1)), e[2]);
+    const double a1 = __dadd_rn(__dadd_rn(__dmul_rn(e[3], x1), __dmul_rn(e[4], y1)), e[5]);
+    const double a2 = __dadd_rn(__dadd_rn(__dmul_rn(e[6], x1), __dmul_rn(e[7], y1)), e[8]);
+    // E^T * Vec3d(x2, y2, 1), rows 0 and 1
+    const double b0 = __dadd_rn(__dadd_rn(__dmul_rn(e[0], x2), __dmul_rn(e[3], y2)), e[6]);
+    const double b1 = __dadd_rn(__dadd_rn(__dmul_rn(e[1], x2), __dmul_rn(e[4], y2)), e[7]);
+    // x2 . Ex1
+    const double s = __dadd_rn(__dadd_rn(__dmul_rn(x2, a0), __dmul_rn(y2, a1)), a2);
+    const double num = __dmul_rn(s, s);
+    const double den = __dadd_rn(
+        __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(b0, b0)),
+        __dmul_rn(b1, b1));
+    if (num < __dmul_rn(sp.mid_lo, den)) return 1;
+    if (num > __dmul_rn(sp.mid_hi, den)) return 0;
+    return (float)__ddiv_rn(num, den) <= sp.t ? 1 : 0;  // boundary sliver, NaN, 0/0
+  }
+};
 
-__device__ __forceinline__ int sampson_inlier(const Emat& E, const double4 p, const ScoreParams& sp) {
-  const double x1 = p.x, y1 = p.y, x2 = p.z, y2 = p.w;
-  // Matx33d * Vec3d(x1, y1, 1): s = 0; s += e0*x; s += e1*y; s += e2*1
-  const double a0 = __dadd_rn(__dadd_rn(__dmul_rn(E.e[0], x1), __dmul_rn(E.e[1], y1)), E.e[2]);
-  const double a1 = __dadd_rn(__dadd_rn(__dmul_rn(E.e[3], x1), __dmul_rn(E.e[4], y1)), E.e[5]);
-  const double a2 = __dadd_rn(__dadd_rn(__dmul_rn(E.e[6], x1), __dmul_rn(E.e[7], y1)), E.e[8]);
-  // E^T * Vec3d(x2, y2, 1), rows 0 and 1
-  const double b0 = __dadd_rn(__dadd_rn(__dmul_rn(E.e[0], x2), __dmul_rn(E.e[3], y2)), E.e[6]);
-  const double b1 = __dadd_rn(__dadd_rn(__dmul_rn(E.e[1], x2), __dmul_rn(E.e[4], y2)), E.e[7]);
-  // x2 . Ex1
-  const double s = __dadd_rn(__dadd_rn(__dmul_rn(x2, a0), __dmul_rn(y2, a1)), a2);
-  const double num = __dmul_rn(s, s);
-  const double den = __dadd_rn(
-      __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(b0, b0)),
-      __dmul_rn(b1, b1));
-  if (num < __dmul_rn(sp.mid_lo, den)) return 1;
-  if (num > __dmul_rn(sp.mid_hi, den)) return 0;
-  return (float)__ddiv_rn(num, den) <= sp.t ? 1 : 0;  // boundary sliver, NaN, 0/0
+// solvePnPRansac's error (reference call cycleProcessing/mainCycle.cpp:155-159):
+// PnPRansacCallback::computeError = cv::projectPoints (cvProjectPoints2Internal: double
+// arithmetic, float result) then err = (float)norm(Matx21f(image - projected), NORM_L2SQR) with a
+// float accumulator.  The model is R (row-major) then t; a correspondence is {X, Y, Z, (u, v)
+// as two floats in the fourth double}.  DIST: 0 = all distortion coefficients zero (the
+// polynomial collapses to x*1*1 + 0 + 0 ..., skipped), 1 = k1 k2 p1 p2 k3 only (rational and
+// thin-prism terms are 1 and +0), 2 = the literal twelve-coefficient formula.  The skipped forms
+// differ from the literal one only where r^6 overflows, and there both sides reject the point
+// (literal: 0*inf = NaN; skipped: |u| beyond float range -> err = inf).
+template <int DIST>
+struct ReprojScorer {
+  static constexpr int ND = 12;
+  typedef PnpParams Params;
+  __device__ static __forceinline__ int inlier(const double (&m)[12], const double4 p,
+                                               const PnpParams& pp) {
+    const double X = p.x, Y = p.y, Z = p.z;
+    double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[0], X), __dmul_rn(m[1], Y)), __dmul_rn(m[2], Z)), m[9]);
+    double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[3], X), __dmul_rn(m[4], Y)), __dmul_rn(m[5], Z)), m[10]);
+    double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[6], X), __dmul_rn(m[7], Y)), __dmul_rn(m[8], Z)), m[11]);
+    z = z != 0.0 ? __drcp_rn(z) : 1.0;  // z ? 1./z : 1
+    x = __dmul_rn(x, z);
+    y = __dmul_rn(y, z);
+    double xd = x, yd = y;
+    if (DIST > 0) {
+      const double* k = pp.k;
+      const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+      const double r4 = __dmul_rn(r2, r2);
+      const double r6 = __dmul_rn(r4, r2);
+      const double x2 = __dmul_rn(2.0, x), y2 = __dmul_rn(2.0, y);
+      const double a1 = __dmul_rn(x2, y);                 // 2*x*y
+      const double a2 = __dadd_rn(r2, __dmul_rn(x2, x));  // r2 + 2*x*x
+      const double a3 = __dadd_rn(r2, __dmul_rn(y2, y));
+      const double cdist = __dadd_rn(__dadd_rn(__dadd_rn(1.0, __dmul_rn(k[0], r2)), __dmul_rn(k[1], r4)),
+                                     __dmul_rn(k[4], r6));
+      double xc = __dmul_rn(x, cdist), yc = __dmul_rn(y, cdist);
+      if (DIST > 1) {
+        const double icdist2 = __drcp_rn(__dadd_rn(
+            __dadd_rn(__dadd_rn(1.0, __dmul_rn(k[5], r2)), __dmul_rn(k[6], r4)), __dmul_rn(k[7], r6)));
+        xc = __dmul_rn(xc, icdist2);
+        yc = __dmul_rn(yc, icdist2);
+      }
+      xd = __dadd_rn(__dadd_rn(xc, __dmul_rn(k[2], a1)), __dmul_rn(k[3], a2));
+      yd = __dadd_rn(__dadd_rn(yc, __dmul_rn(k[2], a3)), __dmul_rn(k[3], a1));
+      if (DIST > 1) {
+        xd = __dadd_rn(__dadd_rn(xd, __dmul_rn(k[8], r2)), __dmul_rn(k[9], r4));
+        yd = __dadd_rn(__dadd_rn(yd, __dmul_rn(k[10], r2)), __dmul_rn(k[11], r4));
+      }
+    }
+    const float u = __double2float_rn(__dadd_rn(__dmul_rn(xd, pp.fx), pp.cx));
+    const float v = __double2float_rn(__dadd_rn(__dmul_rn(yd, pp.fy), pp.cy));
+    const float2 uv = *reinterpret_cast<const float2*>(&p.w);
+    const float dx = __fsub_rn(uv.x, u), dy = __fsub_rn(uv.y, v);
+    const float err = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));  // s = 0; s += dx*dx; s += dy*dy
+    return err <= pp.t ? 1 : 0;
+  }
+};
+
+// {X, Y, Z} float -> double (exact) and the image point packed into the fourth double.
+__global__ void pack_pnp_points_kernel(const float* __restrict__ obj, const float2* __restrict__ img,
+                                       int total, double4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  double4 o;
+  o.x = (double)obj[3 * (size_t)i];
+  o.y = (double)obj[3 * (size_t)i + 1];
+  o.z = (double)obj[3 * (size_t)i + 2];
+  *reinterpret_cast<float2*>(&o.w) = img[i];
+  out[i] = o;
 }
 
 __global__ void normalize_points_kernel(const float2* __restrict__ p1,
@@ -93,21 +168,22 @@ __device__ __forceinline__ void pair_range(const int32_t* m_off, const int32_t* 
   cnt = m_cnt ? m_cnt[pair] : (m_off[pair + 1] - m_off[pair]);
 }
 
+template <class S>
 __global__ void __launch_bounds__(RS_THREADS)
 score_counts_kernel(const double4* __restrict__ npts, const int32_t* __restrict__ m_off,
                     const int32_t* __restrict__ m_cnt, int m_stride,
-                    const double* __restrict__ E, int H, ScoreParams sp,
+                    const double* __restrict__ E, int H, const typename S::Params sp,
                     int32_t* __restrict__ counts) {
   __shared__ double4 pts[RS_PTS];
   const int pair = blockIdx.z;
   size_t base; int M;
   pair_range(m_off, m_cnt, m_stride, pair, base, M);
   const int h = blockIdx.x * RS_THREADS + threadIdx.x;
-  Emat Eh;
+  double Eh[S::ND];
   {
-    const double* src = E + ((size_t)pair * H + min(h, H - 1)) * 9;
+    const double* src = E + ((size_t)pair * H + min(h, H - 1)) * S::ND;
 #pragma unroll
-    for (int k = 0; k < 9; k++) Eh.e[k] = src[k];
+    for (int k = 0; k < S::ND; k++) Eh[k] = src[k];
   }
   int cnt = 0;
   // this block's slice of the matches: chunks blockIdx.y, blockIdx.y + gridDim.y, ...
@@ -117,14 +193,14 @@ score_counts_kernel(const double4* __restrict__ npts, const int32_t* __restrict_
     for (int i = threadIdx.x; i < n; i += RS_THREADS) pts[i] = npts[base + c0 + i];
     __syncthreads();
 #pragma unroll 2
-    for (int i = 0; i < n; i++) cnt += sampson_inlier(Eh, pts[i], sp);
+    for (int i = 0; i < n; i++) cnt += S::inlier(Eh, pts[i], sp);
   }
   if (h < H && cnt) atomicAdd(&counts[(size_t)pair * H + h], cnt);
 }
 
 // RANSACPointSetRegistrator::run's update rule over a fixed list: first index with the maximum
-// count, provided that count exceeds 4 (modelPoints - 1); else -1.
-__global__ void score_best_kernel(const int32_t* __restrict__ counts, int H,
+// count, provided that count exceeds min_count (modelPoints - 1); else -1.
+__global__ void score_best_kernel(const int32_t* __restrict__ counts, int H, int min_count,
                                   int32_t* __restrict__ best) {
   __shared__ unsigned long long red[32];
   const int pair = blockIdx.x;
@@ -145,39 +221,39 @@ __global__ void score_best_kernel(const int32_t* __restrict__ counts, int H,
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); w++) key = red[w] > key ? red[w] : key;
     const int32_t c = (int32_t)(key >> 32);
-    best[pair] = (H > 0 && c > 4) ? (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu)) : -1;
+    best[pair] = (H > 0 && c > min_count) ? (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu)) : -1;
   }
 }
 
+template <class S>
 __global__ void score_mask_kernel(const double4* __restrict__ npts,
                                   const int32_t* __restrict__ m_off,
                                   const int32_t* __restrict__ m_cnt, int m_stride,
                                   const double* __restrict__ E, int H,
-                                  const int32_t* __restrict__ best, ScoreParams sp,
+                                  const int32_t* __restrict__ best, const typename S::Params sp,
                                   uint8_t* __restrict__ mask) {
   const int pair = blockIdx.y;
   size_t base; int M;
   pair_range(m_off, m_cnt, m_stride, pair, base, M);
   const int b = best[pair];
-  Emat Eh;
-  if (b >= 0) {
+  double Eh[S::ND];
 #pragma unroll
-    for (int k = 0; k < 9; k++) Eh.e[k] = E[((size_t)pair * H + b) * 9 + k];
-  }
+  for (int k = 0; k < S::ND; k++) Eh[k] = b >= 0 ? E[((size_t)pair * H + b) * S::ND + k] : 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x)
-    mask[base + i] = b >= 0 ? (uint8_t)sampson_inlier(Eh, npts[base + i], sp) : (uint8_t)0;
+    mask[base + i] = b >= 0 ? (uint8_t)S::inlier(Eh, npts[base + i], sp) : (uint8_t)0;
 }
 
 // Parity aid: every (hypothesis, match) flag as a byte, one thread per match, hypotheses along y.
+template <class S>
 __global__ void score_all_masks_kernel(const double4* __restrict__ npts, int M,
-                                       const double* __restrict__ E, int H, ScoreParams sp,
-                                       uint8_t* __restrict__ masks) {
+                                       const double* __restrict__ E, int H,
+                                       const typename S::Params sp, uint8_t* __restrict__ masks) {
   const int h = blockIdx.y;
-  Emat Eh;
+  double Eh[S::ND];
 #pragma unroll
-  for (int k = 0; k < 9; k++) Eh.e[k] = E[(size_t)h * 9 + k];
+  for (int k = 0; k < S::ND; k++) Eh[k] = E[(size_t)h * S::ND + k];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x)
-    masks[(size_t)h * M + i] = (uint8_t)sampson_inlier(Eh, npts[i], sp);
+    masks[(size_t)h * M + i] = (uint8_t)S::inlier(Eh, npts[i], sp);
 }
 
 void launch_normalize_points(const float2* p1, const float2* p2, int total, ScoreParams sp,
@@ -196,9 +272,10 @@ void launch_gather_normalize(const float2* q_xy, const float2* const* t_xy,
   COUNT_LAUNCH();
 }
 
-void launch_score_counts(const double4* npts, const int32_t* m_off, const int32_t* m_cnt,
-                         int m_stride, const double* E, int H, int P, ScoreParams sp,
-                         int32_t* counts, cudaStream_t s) {
+template <class S>
+static void score_counts_t(const double4* npts, const int32_t* m_off, const int32_t* m_cnt,
+                           int m_stride, const double* E, int H, int P,
+                           const typename S::Params& sp, int32_t* counts, cudaStream_t s) {
   if (P <= 0 || H <= 0) return;
   cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)P * H, s);
   const int hb = (H + RS_THREADS - 1) / RS_THREADS;
@@ -206,29 +283,84 @@ void launch_score_counts(const double4* npts, const int32_t* m_off, const int32_
   int ms = (148 * 8 + hb * P - 1) / (hb * P);
   ms = max(1, min(ms, 16));
   dim3 grid(hb, ms, P);
-  score_counts_kernel<<<grid, RS_THREADS, 0, s>>>(npts, m_off, m_cnt, m_stride, E, H, sp, counts);
+  score_counts_kernel<S><<<grid, RS_THREADS, 0, s>>>(npts, m_off, m_cnt, m_stride, E, H, sp, counts);
   COUNT_LAUNCH();
 }
 
-void launch_score_best(const int32_t* counts, int H, int P, int32_t* best, cudaStream_t s) {
+template <class S>
+static void score_mask_t(const double4* npts, const int32_t* m_off, const int32_t* m_cnt,
+                         int m_stride, const double* E, int H, int P, const int32_t* best,
+                         const typename S::Params& sp, uint8_t* mask, cudaStream_t s) {
   if (P <= 0) return;
-  score_best_kernel<<<P, 256, 0, s>>>(counts, H, best);
+  dim3 grid(8, P);
+  score_mask_kernel<S><<<grid, 256, 0, s>>>(npts, m_off, m_cnt, m_stride, E, H, best, sp, mask);
+  COUNT_LAUNCH();
+}
+
+template <class S>
+static void score_all_masks_t(const double4* npts, int M, const double* E, int H,
+                              const typename S::Params& sp, uint8_t* masks, cudaStream_t s) {
+  if (M <= 0 || H <= 0) return;
+  dim3 grid(min((M + 255) / 256, 32), H);
+  score_all_masks_kernel<S><<<grid, 256, 0, s>>>(npts, M, E, H, sp, masks);
+  COUNT_LAUNCH();
+}
+
+void launch_score_counts(const double4* npts, const int32_t* m_off, const int32_t* m_cnt,
+                         int m_stride, const double* E, int H, int P, ScoreParams sp,
+                         int32_t* counts, cudaStream_t s) {
+  score_counts_t<SampsonScorer>(npts, m_off, m_cnt, m_stride, E, H, P, sp, counts, s);
+}
+
+void launch_score_best(const int32_t* counts, int H, int P, int min_count, int32_t* best,
+                       cudaStream_t s) {
+  if (P <= 0) return;
+  score_best_kernel<<<P, 256, 0, s>>>(counts, H, min_count, best);
   COUNT_LAUNCH();
 }
 
 void launch_score_mask(const double4* npts, const int32_t* m_off, const int32_t* m_cnt,
                        int m_stride, const double* E, int H, int P, const int32_t* best,
                        ScoreParams sp, uint8_t* mask, cudaStream_t s) {
-  if (P <= 0) return;
-  dim3 grid(8, P);
-  score_mask_kernel<<<grid, 256, 0, s>>>(npts, m_off, m_cnt, m_stride, E, H, best, sp, mask);
-  COUNT_LAUNCH();
+  score_mask_t<SampsonScorer>(npts, m_off, m_cnt, m_stride, E, H, P, best, sp, mask, s);
 }
 
 void launch_score_all_masks(const double4* npts, int M, const double* E, int H, ScoreParams sp,
                             uint8_t* masks, cudaStream_t s) {
-  if (M <= 0 || H <= 0) return;
-  dim3 grid(min((M + 255) / 256, 32), H);
-  score_all_masks_kernel<<<grid, 256, 0, s>>>(npts, M, E, H, sp, masks);
+  score_all_masks_t<SampsonScorer>(npts, M, E, H, sp, masks, s);
+}
+
+// ---- solvePnPRansac scoring --------------------------------------------------------------------
+void launch_pack_pnp_points(const float* obj, const float2* img, int total, double4* out,
+                            cudaStream_t s) {
+  if (total <= 0) return;
+  pack_pnp_points_kernel<<<(total + 255) / 256, 256, 0, s>>>(obj, img, total, out);
   COUNT_LAUNCH();
+}
+
+void launch_pnp_counts(const double4* pts, const int32_t* m_off, const double* poses, int H, int P,
+                       const PnpParams& pp, int32_t* counts, cudaStream_t s) {
+  if (pp.dist_level == 0)
+    score_counts_t<ReprojScorer<0>>(pts, m_off, nullptr, 0, poses, H, P, pp, counts, s);
+  else if (pp.dist_level == 1)
+    score_counts_t<ReprojScorer<1>>(pts, m_off, nullptr, 0, poses, H, P, pp, counts, s);
+  else
+    score_counts_t<ReprojScorer<2>>(pts, m_off, nullptr, 0, poses, H, P, pp, counts, s);
+}
+
+void launch_pnp_mask(const double4* pts, const int32_t* m_off, const double* poses, int H, int P,
+                     const int32_t* best, const PnpParams& pp, uint8_t* mask, cudaStream_t s) {
+  if (pp.dist_level == 0)
+    score_mask_t<ReprojScorer<0>>(pts, m_off, nullptr, 0, poses, H, P, best, pp, mask, s);
+  else if (pp.dist_level == 1)
+    score_mask_t<ReprojScorer<1>>(pts, m_off, nullptr, 0, poses, H, P, best, pp, mask, s);
+  else
+    score_mask_t<ReprojScorer<2>>(pts, m_off, nullptr, 0, poses, H, P, best, pp, mask, s);
+}
+
+void launch_pnp_all_masks(const double4* pts, int M, const double* poses, int H,
+                          const PnpParams& pp, uint8_t* masks, cudaStream_t s) {
+  if (pp.dist_level == 0) score_all_masks_t<ReprojScorer<0>>(pts, M, poses, H, pp, masks, s);
+  else if (pp.dist_level == 1) score_all_masks_t<ReprojScorer<1>>(pts, M, poses, H, pp, masks, s);
+  else score_all_masks_t<ReprojScorer<2>>(pts, M, poses, H, pp, masks, s);
 }

@@ -141,3 +141,30 @@ def test_ransac_first_best_and_min_count():
     # three matches can never exceed the "> 4" floor
     c, b, m, _ = c_oracle.score_essential(p1[:3], p2[:3], synth.SAMSUNG_HV_4K, E, 5.0)
     assert b == -1 and not m.any()
+
+
+# ---- solvePnPRansac scoring ------------------------------------------------------
+def test_pnp_masks_match_cv2_project_points(golden_dir):
+    """The reprojection-inlier restatement against masks built from cv2.projectPoints, for the
+    reference's five-coefficient model, no distortion, and the twelve-coefficient model."""
+    g = np.load(os.path.join(golden_dir, "pnp.npz"))
+    for c in range(5):
+        obj, img, dist, poses = g[f"obj_{c}"], g[f"img_{c}"], g[f"dist_{c}"], g[f"poses_{c}"]
+        want = np.unpackbits(g[f"masks_{c}"], axis=1)[:, :len(obj)]
+        counts, best, mask, allm = c_oracle.score_pnp(obj, img, g["K4"], dist, poses, float(g["reproj"]),
+                                                      want_all_masks=True)
+        assert np.array_equal(allm, want)
+        assert np.array_equal(counts, want.sum(1))
+        if best >= 0:
+            assert best == int(np.argmax(counts)) and counts[best] > 4
+            assert np.array_equal(mask, want[best])
+
+
+def test_pnp_cv2_ransac_inliers_are_the_mask_of_some_minimal_model(golden_dir):
+    """cv2.solvePnPRansac's inlier list has the size the update rule promises: no scored
+    hypothesis of the fixture beats it by the strict rule unless it was never drawn (sanity)."""
+    g = np.load(os.path.join(golden_dir, "pnp.npz"))
+    for c in range(5):
+        assert bool(g[f"cv_ok_{c}"])
+        inl = g[f"cv_inliers_{c}"]
+        assert len(inl) > 4 and np.all(np.diff(inl) > 0)

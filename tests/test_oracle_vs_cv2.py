@@ -50,3 +50,58 @@ def test_find_essential_mat_mask(seed):
     E = np.asarray(E, np.float64).reshape(-1, 9)[:1]
     counts, best, m, _ = c_oracle.score_essential(p1, p2, K4, E, 5.0)
     assert best == 0 and np.array_equal(m, mask.reshape(-1))
+
+
+@pytest.mark.parametrize("seed,dv", [(9200, 0), (9201, 1), (9202, 2), (9203, 3)])
+def test_project_points_bit_exact(seed, dv):
+    """cv::projectPoints (the call inside PnPRansacCallback::computeError) restated."""
+    dist = (np.array(synth.REF_DIST5), None, np.zeros(5),
+            np.array([0.2, -0.4, 0.002, -0.001, 0.1, 0.02, -0.03, 0.004, 2e-3, -1e-3, 5e-4, 2e-4]))[dv]
+    obj, img, R, t = synth.pnp_scene(3000, seed)
+    K4 = np.array(synth.SAMSUNG_HV_4K)
+    Kmat = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]])
+    rng = np.random.default_rng(seed)
+    for _ in range(4):
+        rvec, tvec = rng.normal(0, 0.3, 3), rng.normal(0, 0.5, 3)
+        want = cv2.projectPoints(obj, rvec, tvec, Kmat, dist)[0].reshape(-1, 2)
+        pose = np.concatenate([cv2.Rodrigues(rvec)[0].reshape(-1), tvec])
+        got = c_oracle.project_points(obj, K4, dist, pose)
+        assert np.array_equal(got.view(np.uint32), want.astype(np.float32).view(np.uint32))
+
+
+@pytest.mark.parametrize("m,seed", [(700, 9300), (60, 9301), (5, 9302), (4, 9303), (2500, 9304)])
+def test_solve_pnp_ransac_control_and_scoring(m, seed):
+    """cv2.solvePnPRansac rebuilt from its parts -- cv::RNG subsets, EPnP/P3P minimal solver (cv2),
+    the oracle's inlier counts, the update rule, the refit -- returns cv2's rvec, tvec, inliers."""
+    from slam_indoor_code_b200 import ransac_host
+    obj, img, _, _ = synth.pnp_scene(m, seed, outliers=0.3 if m > 10 else 0.0)
+    K4 = np.array(synth.SAMSUNG_HV_4K)
+    Kmat = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]])
+    dist = np.array(synth.REF_DIST5)
+    ok, rvec, tvec, inl = cv2.solvePnPRansac(obj, img, Kmat, dist)
+    mp, method = (4, cv2.SOLVEPNP_P3P) if m == 4 else (5, cv2.SOLVEPNP_EPNP)
+    seen = {}
+
+    def solve(idx):
+        k, r, t = cv2.solvePnP(obj[idx], img[idx], Kmat, dist, flags=method)
+        if not k:
+            return np.zeros((0, 12))
+        model = np.concatenate([cv2.Rodrigues(r)[0].reshape(-1), t.reshape(-1)])
+        seen[model.tobytes()] = (r, t)
+        return model[None]
+
+    if m == mp:  # solvePnPRansac short-cut: the minimal solver on all points, no RANSAC, no refit
+        k, r, t = cv2.solvePnP(obj, img, Kmat, dist, flags=method)
+        assert ok and k and np.array_equal(r, rvec) and np.array_equal(t, tvec)
+        assert np.array_equal(inl.reshape(-1), np.arange(m))
+        return
+    else:
+        best, _, _ = ransac_host.ransac_run(m, mp, 0.99, 100, solve,
+                                            lambda mod: c_oracle.score_pnp(obj, img, K4, dist, mod, 8.0, mp)[0])
+        mask = c_oracle.score_pnp(obj, img, K4, dist, best[None], 8.0, mp, True)[3][0]
+    got_inl = np.nonzero(mask)[0]
+    assert ok and np.array_equal(got_inl, inl.reshape(-1))
+    r0, t0 = seen[best.tobytes()]
+    k, r, t = cv2.solvePnP(obj[got_inl].astype(np.float64), img[got_inl].astype(np.float64), Kmat, dist,
+                           r0.copy(), t0.copy(), True, cv2.SOLVEPNP_ITERATIVE)
+    assert k and np.array_equal(r, rvec) and np.array_equal(t, tvec)
