@@ -53,31 +53,39 @@ int hostshim_match_batch(const void* q, int nq, const void* const* t, const int*
 // The C++ RANSAC control with a scripted solver and scorer: `n_models[i]` models come out of the
 // i-th minimal sample, model h of the run scores `scores[h]`.  Returns the iterations run; writes
 // every drawn subset and the index of the winning model (or -1).
-int hostshim_ransac_control(int count, double prob, int chunk, const int* n_models, int n_samples,
-                            const int32_t* scores, int n_scores, int* subsets_out, int subsets_cap,
-                            int* best_model) {
+int hostshim_ransac_run(int count, int model_points, int nd, double prob, int max_iters, int chunk,
+                        const int* n_models, int n_samples, const int32_t* scores, int n_scores,
+                        int* subsets_out, int subsets_cap, int* best_model) {
   int sample = 0, issued = 0;
   auto solve = [&](const int*, std::vector<double>& models) {
     const int k = sample < n_samples ? n_models[sample] : 1;
     sample++;
     for (int j = 0; j < k; j++) {
-      double m[9] = {0};
+      std::vector<double> m((size_t)nd, 0.0);
       m[0] = (double)issued++;   // the model's global ordinal, so the winner can be identified
-      models.insert(models.end(), m, m + 9);
+      models.insert(models.end(), m.begin(), m.end());
     }
   };
   auto score = [&](const double* models, int H, int32_t* counts) {
     for (int h = 0; h < H; h++) {
-      const int ord = (int)models[(size_t)h * 9];
+      const int ord = (int)models[(size_t)h * nd];
       counts[h] = ord < n_scores ? scores[ord] : 0;
     }
   };
-  double best[9];
+  std::vector<double> best((size_t)nd, 0.0);
   int iters = 0;
   std::vector<int> subsets;
-  const bool ok = slamb200::ransacEssential(count, prob, 1000, chunk, solve, score, best, &iters, &subsets);
+  const bool ok = slamb200::ransacRun(count, model_points, nd, prob, max_iters, chunk, solve, score,
+                                      best.data(), &iters, &subsets);
   *best_model = ok ? (int)best[0] : -1;
   for (size_t i = 0; i < subsets.size() && (int)i < subsets_cap; i++) subsets_out[i] = subsets[i];
   return iters;
+}
+
+int hostshim_ransac_control(int count, double prob, int chunk, const int* n_models, int n_samples,
+                            const int32_t* scores, int n_scores, int* subsets_out, int subsets_cap,
+                            int* best_model) {
+  return hostshim_ransac_run(count, 5, 9, prob, 1000, chunk, n_models, n_samples, scores, n_scores,
+                             subsets_out, subsets_cap, best_model);
 }
 }

@@ -1,6 +1,7 @@
-// ransac_control.h -- host-side control of cv::findEssentialMat's RANSAC loop around the GPU
-// scorer, for the reference-side translation unit (cameraTranslationB200.cpp).  Pure C++17, no
-// OpenCV types: the 5-point solver and the scorer are injected.
+// ransac_control.h -- host-side control of OpenCV's RANSAC loop (cv::findEssentialMat,
+// cv::solvePnPRansac) around the GPU scorers, for the reference-side translation units
+// (cameraTranslationB200.cpp, poseEstimationB200.cpp).  Pure C++17, no OpenCV types: the minimal
+// solver and the scorer are injected.
 //
 // The reference's call (src/mainModule/translation/cameraTranslation.cpp:41-46) runs OpenCV's
 // RANSACPointSetRegistrator::run with modelPoints = 5, maxIters = 1000: cv::RNG seeded with
@@ -28,8 +29,8 @@ struct CvRNG {  // cv::RNG (multiply-with-carry)
   int uniform(int a, int b) { return a == b ? a : (int)(next() % (unsigned)(b - a)) + a; }
 };
 
-inline void getSubset(CvRNG& rng, int count, int idx[5]) {
-  for (int i = 0; i < 5; i++) {
+inline void getSubset(CvRNG& rng, int count, int* idx, int modelPoints = 5) {
+  for (int i = 0; i < modelPoints; i++) {
     int v;
     bool dup;
     do {
@@ -52,16 +53,19 @@ inline int RANSACUpdateNumIters(double p, double ep, int modelPoints, int maxIte
   return denom >= 0 || -num >= maxIters * (-denom) ? maxIters : (int)std::nearbyint(num / denom);
 }
 
-// solve(idx[5], models)       appends the 9-double candidate models of one minimal sample
-// score(models, H, counts)    inlier counts of H models against all matches (the GPU call)
-// Returns the index-free best model (9 doubles) in `best`; false when no model has > 4 inliers.
+// RANSACPointSetRegistrator::run for count > modelPoints, any model size (ND doubles per model):
+//   solve(idx[modelPoints], models)   appends the candidate models of one minimal sample
+//   score(models, H, counts)          inlier counts of H models against all points (the GPU call)
+// Iterations are scored speculatively `chunk` at a time; the update rule is replayed in order and
+// work past the final budget is discarded, so the outcome equals the sequential loop's.
+// Returns the best model in `best` (ND doubles); false when no model has > modelPoints-1 inliers.
 // `subsets` (optional) receives every drawn subset, for tests.
-inline bool ransacEssential(int count, double prob, int maxIters, int chunk,
-                            const std::function<void(const int*, std::vector<double>&)>& solve,
-                            const std::function<void(const double*, int, int32_t*)>& score,
-                            double best[9], int* iterations = nullptr,
-                            std::vector<int>* subsets = nullptr) {
-  if (count < 5) return false;
+inline bool ransacRun(int count, int modelPoints, int ND, double prob, int maxIters, int chunk,
+                      const std::function<void(const int*, std::vector<double>&)>& solve,
+                      const std::function<void(const double*, int, int32_t*)>& score,
+                      double* best, int* iterations = nullptr,
+                      std::vector<int>* subsets = nullptr) {
+  if (count < modelPoints || modelPoints > 16) return false;
   CvRNG rng;
   int niters = maxIters, it = 0, maxGood = 0;
   bool found = false;
@@ -73,24 +77,25 @@ inline bool ransacEssential(int count, double prob, int maxIters, int chunk,
     models.clear();
     owner.clear();
     for (int j = 0; j < n_it; j++) {
-      int idx[5];
-      getSubset(rng, count, idx);
-      if (subsets) subsets->insert(subsets->end(), idx, idx + 5);
-      const size_t before = models.size() / 9;
+      int idx[16];
+      getSubset(rng, count, idx, modelPoints);
+      if (subsets) subsets->insert(subsets->end(), idx, idx + modelPoints);
+      const size_t before = models.size() / ND;
       solve(idx, models);
-      for (size_t k = before; k < models.size() / 9; k++) owner.push_back(it + j);
+      for (size_t k = before; k < models.size() / ND; k++) owner.push_back(it + j);
     }
-    const int H = (int)(models.size() / 9);
+    const int H = (int)(models.size() / ND);
     if (H > 0) {
       counts.assign((size_t)H, 0);
       score(models.data(), H, counts.data());
       for (int h = 0; h < H; h++) {
         if (owner[(size_t)h] >= niters) break;  // the budget shrank below this iteration
-        if (counts[(size_t)h] > (maxGood > 4 ? maxGood : 4)) {
+        const int floor_ = modelPoints - 1;
+        if (counts[(size_t)h] > (maxGood > floor_ ? maxGood : floor_)) {
           maxGood = counts[(size_t)h];
-          for (int k = 0; k < 9; k++) best[k] = models[(size_t)h * 9 + k];
+          for (int k = 0; k < ND; k++) best[k] = models[(size_t)h * ND + k];
           found = true;
-          niters = RANSACUpdateNumIters(prob, (double)(count - maxGood) / count, 5, niters);
+          niters = RANSACUpdateNumIters(prob, (double)(count - maxGood) / count, modelPoints, niters);
         }
       }
     }
@@ -98,6 +103,15 @@ inline bool ransacEssential(int count, double prob, int maxIters, int chunk,
   }
   if (iterations) *iterations = it < niters ? it : niters;
   return found;
+}
+
+// findEssentialMat's instance: five-point samples, 9-double models, maxIters 1000.
+inline bool ransacEssential(int count, double prob, int maxIters, int chunk,
+                            const std::function<void(const int*, std::vector<double>&)>& solve,
+                            const std::function<void(const double*, int, int32_t*)>& score,
+                            double best[9], int* iterations = nullptr,
+                            std::vector<int>* subsets = nullptr) {
+  return ransacRun(count, 5, 9, prob, maxIters, chunk, solve, score, best, iterations, subsets);
 }
 
 }  // namespace slamb200

@@ -62,3 +62,43 @@ def test_cpp_control_equals_python_control(host, seed, count, chunk):
     assert iters == py_iters
     n = min(len(drawn), len(subsets))
     assert n > 0 and list(subsets[:n]) == drawn[:n]
+
+
+@pytest.mark.parametrize("seed,count,mp,max_iters,chunk", [(11, 900, 5, 100, 8), (12, 30, 4, 100, 1), (13, 6, 5, 100, 8),
+                                                           (14, 4000, 5, 100, 100)])
+def test_cpp_control_pnp_instance(host, seed, count, mp, max_iters, chunk):
+    """The solvePnPRansac instance of the control (one 12-double model per sample, maxIters 100,
+    confidence 0.99, floor modelPoints-1) against ransac_host.ransac_run."""
+    host.hostshim_ransac_run.restype = ctypes.c_int
+    host.hostshim_ransac_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    rng = np.random.default_rng(seed)
+    n_models = rng.integers(0, 2, 200).astype(np.int32)            # EPnP: one model, or a failure
+    scores = rng.integers(0, max(count // 2, 6), 400).astype(np.int32)
+    scores[rng.choice(60, 3, replace=False)] = int(count * 0.8)
+    subsets = np.full(mp * 200, -1, np.int32)
+    best = ctypes.c_int(-2)
+    iters = host.hostshim_ransac_run(count, mp, 12, 0.99, max_iters, chunk, n_models.ctypes.data, len(n_models),
+                                     scores.ctypes.data, len(scores), subsets.ctypes.data, len(subsets),
+                                     ctypes.byref(best))
+    state = {"sample": 0, "issued": 0}
+    drawn = []
+
+    def solve(idx):
+        drawn.extend(idx)
+        k = int(n_models[state["sample"]]) if state["sample"] < len(n_models) else 1
+        state["sample"] += 1
+        out = np.zeros((k, 12))
+        out[:, 0] = np.arange(state["issued"], state["issued"] + k)
+        state["issued"] += k
+        return out
+
+    def score(models):
+        return [int(scores[int(m[0])]) if int(m[0]) < len(scores) else 0 for m in models]
+
+    model, py_iters, _ = ransac_host.ransac_run(count, mp, 0.99, max_iters, solve, score, chunk)
+    assert best.value == (-1 if model is None else int(model[0]))
+    assert iters == py_iters
+    n = min(len(drawn), len(subsets))
+    assert n > 0 and list(subsets[:n]) == drawn[:n]
