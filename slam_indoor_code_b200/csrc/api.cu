@@ -42,7 +42,8 @@ struct DevBuf {
   size_t cap = 0;
 };
 
-#define N_LANES 8
+#define N_LANES 10
+#define N_UPLOAD_LANES 4  // the last lanes: descriptor uploads never queue in front of a match
 
 struct Lane {
   cudaStream_t stream = nullptr;
@@ -89,7 +90,8 @@ struct slamb200_ctx {
   std::mutex batch_mu;
   std::mutex free_mu;
   int n_sm = 148;
-  int next_lane = 0;
+  int next_lane = 1;
+  int next_upload_lane = N_LANES - N_UPLOAD_LANES;
   cudaStream_t free_stream = nullptr;  // frees are stream-ordered here behind every lane's work
   // Descriptor-set slabs are recycled: a freed slab waits here with the event that marks the end
   // of all work that could still read it; the next upload of the same size makes its stream wait
@@ -141,18 +143,25 @@ static int stage_reserve(Lane& L, size_t bytes) {
 struct LaneGuard {
   slamb200_ctx* c;
   int idx;
-  LaneGuard(slamb200_ctx* c_) : c(c_), idx(-1) {
+  // Worker lanes are split in two classes so that a match (compute lane) is never enqueued behind
+  // descriptor uploads another host thread queued for *later* work (upload lanes): with one shared
+  // pool every thread's uploads and matches moved in a convoy and the PCIe link idled while all of
+  // them matched.  Lane 0 is the batch (enqueue/fetch) lane.
+  LaneGuard(slamb200_ctx* c_, bool upload = false) : c(c_), idx(-1) {
+    const int lo = upload ? N_LANES - N_UPLOAD_LANES : 1;
+    const int cnt = upload ? N_UPLOAD_LANES : N_LANES - N_UPLOAD_LANES - 1;
+    int& next = upload ? c->next_upload_lane : c->next_lane;
     std::unique_lock<std::mutex> lk(c->mu);
     for (;;) {
-      // round-robin over the worker lanes so that back-to-back uploads land on different streams
-      for (int k = 1; k < N_LANES; k++) {
-        const int i = 1 + (c->next_lane + k - 1) % (N_LANES - 1);
+      // round-robin so that back-to-back calls land on different streams
+      for (int k = 1; k <= cnt; k++) {
+        const int i = lo + (next - lo + k) % cnt;
         if (!c->lanes[i].busy) { idx = i; break; }
       }
       if (idx >= 0) break;
       c->cv.wait(lk);
     }
-    c->next_lane = idx;
+    next = idx;
     c->lanes[idx].busy = true;
   }
   ~LaneGuard() {
@@ -160,7 +169,7 @@ struct LaneGuard {
       std::lock_guard<std::mutex> lk(c->mu);
       c->lanes[idx].busy = false;
     }
-    c->cv.notify_one();
+    c->cv.notify_all();
   }
   Lane& lane() { return c->lanes[idx]; }
 };
@@ -321,7 +330,7 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   d->n = n;
   d->n_pad = round_up(n > 0 ? n : 1, SLAMB200_TILE_PAD);
   d->host_exact = -2;
-  LaneGuard g(c);
+  LaneGuard g(c, /*upload=*/true);
   Lane& L = g.lane();
   cudaStream_t s = L.stream;
   int rc = SLAMB200_OK;

@@ -42,7 +42,7 @@ def run(workers, chunk, verbose=False):
         best = min(best, dt)
     print(f"workers={workers} chunk={chunk}: best {best*1e3:.1f} ms/step -> {NP/best:.0f} pairs/s", flush=True)
     if verbose:
-        for (i, a, b, c, d) in sorted(log)[:12]:
+        for (i, a, b, c, d) in sorted(log)[:14]:
             print(f"   chunk@{i}: start {1e3*(a-t0):6.1f} upload {1e3*(b-a):5.1f} match {1e3*(c-b):5.1f} free {1e3*(d-c):4.1f}")
 
-run(1, 210); run(1, 70); run(1, 30, True); run(2, 53); run(3, 24, True); run(3, 35); run(3, 70)
+run(1, 210, True); run(1, 18, True); run(4, 18, True)
