@@ -449,7 +449,7 @@ def run_b200(args, rank, world, local):
 # (N=1), from the committed `ncu --set full` capture profiles/r01_ncu_sift_tc_final.txt:
 # 622.6 MB read + 183.3 MB written.  Compulsory bytes of that launch: 211 descriptor sets x 2.9 MB
 # of bf16 operands + 206 MB of slot records = 818 MB, i.e. no re-reads.
-TRAFFIC_BYTES_PER_LAUNCH_N1 = 805_879_296
+TRAFFIC_BYTES_PER_LAUNCH_N1 = 805_429_504
 
 
 def cpu_baseline(q, trains, gpu_matches, seconds):

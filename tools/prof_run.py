@@ -31,3 +31,42 @@ elif which == "ransac":
     for _ in range(3):
         c, b, m = ct.scoreEssentialBatch(ctx, [p1] * 16, [p2] * 16, synth.SAMSUNG_HV_4K, np.stack([E] * 16), 5.0)
     print("ok", b[:4])
+elif which == "all":
+    # one pass of every hot kernel at its bench shape: 210-pair SIFT window, 16 ORB pairs,
+    # 16 x (2048 x 5000) essential scoring, 16 x (2048 x 5000) PnP scoring
+    from slam_indoor_code_b200 import pnp_ransac as pr
+    q = synth.sift_like(10000, 3000)
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(synth.sift_train_from_query(q, 10000, 3001 + i)) for i in range(210)]
+    for _ in range(2):
+        ctx.matchBatchEnqueue(Q, Ts, MatcherType.SIFT_BF, 0.7, st)
+    torch.cuda.synchronize()
+    print("sift ok", sum(len(m) for m in ctx.batchFetch(st)[0]))
+    qo, to = synth.orb_pair(10000, 10000, 2001)
+    Qo, To = ctx.upload(qo), ctx.upload(to)
+    for _ in range(2):
+        ctx.matchBatchEnqueue(Qo, [To] * 16, MatcherType.ORB_BF, 0.7, st)
+    torch.cuda.synchronize()
+    print("orb ok", len(ctx.batchFetch(st)[0][0]))
+    p1, p2, R, tv = synth.two_view(5000, 5000)
+    E = synth.pose_hypotheses(2048, R, tv, 5001)
+    for _ in range(2):
+        c, b, m = ct.scoreEssentialBatch(ctx, [p1] * 16, [p2] * 16, synth.SAMSUNG_HV_4K, np.stack([E] * 16), 5.0)
+    print("ransac ok", b[:4])
+    obj, img, Rp, tp = synth.pnp_scene(5000, 7000)
+    poses = synth.pnp_hypotheses(2048, Rp, tp, 7001)
+    for _ in range(2):
+        c, b, m = pr.scorePnPBatch(ctx, [obj] * 16, [img] * 16, synth.SAMSUNG_HV_4K, synth.REF_DIST5, np.stack([poses] * 16), 8.0)
+    print("pnp ok", b[:4])
+elif which == "score":
+    from slam_indoor_code_b200 import pnp_ransac as pr
+    p1, p2, R, tv = synth.two_view(5000, 5000)
+    E = synth.pose_hypotheses(2048, R, tv, 5001)
+    for _ in range(2):
+        c, b, m = ct.scoreEssentialBatch(ctx, [p1] * 16, [p2] * 16, synth.SAMSUNG_HV_4K, np.stack([E] * 16), 5.0)
+    print("ransac ok", b[:4])
+    obj, img, Rp, tp = synth.pnp_scene(5000, 7000)
+    poses = synth.pnp_hypotheses(2048, Rp, tp, 7001)
+    for dist in (synth.REF_DIST5, None):
+        c, b, m = pr.scorePnPBatch(ctx, [obj] * 16, [img] * 16, synth.SAMSUNG_HV_4K, dist, np.stack([poses] * 16), 8.0)
+    print("pnp ok", b[:4])
