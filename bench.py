@@ -505,6 +505,14 @@ def extras(ctx, stream):
                                                       "tflops": 16 * FLOP_PER_PAIR / ms / 1e9}
         Qf.free()
         Tf.free()
+    # next row 8f-4: NORM_L1 (useFM-SIFT-BF of the reference's OpenCV-CUDA build) on cfg1's integer rows:
+    # Q*T*32 byte-wise SAD instructions per pair
+    Qi, Ti = ctx.upload(qi), ctx.upload(ti)
+    ms = ev_time(lambda: ctx.matchBatchEnqueue(Qi, [Ti] * 16, MatcherType.SIFT_BF_L1, RATIO, stream), 5)
+    out["f4_sift_l1_16_pairs"] = {"us_per_pair": ms / 16 * 1e3, "pairs_per_s": 16e3 / ms,
+                                  "tsad4_per_s": 16 * 32.0 * N_ROWS * N_ROWS / ms / 1e9}
+    Qi.free()
+    Ti.free()
     q, t = synth.orb_pair(N_ROWS, N_ROWS, 2001)
     Q, T = ctx.upload(q), ctx.upload(t)
     ms = ev_time(lambda: ctx.matchBatchEnqueue(Q, [T] * 16, MatcherType.ORB_BF, RATIO, stream), 10)
@@ -514,6 +522,7 @@ def extras(ctx, stream):
     p1, p2, R, tv = synth.two_view(5000, 5000)
     E = synth.pose_hypotheses(2048, R, tv, 5001)
     P = 32
+    ct.scoreEssentialBatch(ctx, [p1] * P, [p2] * P, synth.SAMSUNG_HV_4K, np.stack([E] * P), 5.0)  # warm-up
     ctx.profile_enable(True)
     ctx.profile_read()
     for _ in range(3):
@@ -528,6 +537,7 @@ def extras(ctx, stream):
     from slam_indoor_code_b200 import pnp_ransac as pr
     obj, img, Rp, tp = synth.pnp_scene(5000, 7000)
     poses = synth.pnp_hypotheses(2048, Rp, tp, 7001)
+    pr.scorePnPBatch(ctx, [obj] * P, [img] * P, synth.SAMSUNG_HV_4K, synth.REF_DIST5, np.stack([poses] * P), 8.0)
     ctx.profile_enable(True)
     ctx.profile_read()
     for _ in range(3):

@@ -50,6 +50,9 @@ extern "C" {
                                  (featureMatchingCPU.cpp:30) is approximate, its ground truth is
                                  the BF result, so recall vs BF is 1.0 by construction        */
 #define SLAMB200_ORB_BF 2     /* useFM-ORB        -> BFMatcher NORM_HAMMING (:33)              */
+#define SLAMB200_SIFT_BF_L1 3 /* not a reference enum value: what useFM-SIFT-BF means in the reference's
+                                 OpenCV-CUDA build, cuda BFMatcher NORM_L1 (featureMatchingCUDA.cpp:28);
+                                 SURVEY.md 8f-4.  Results as cv::BFMatcher(NORM_L1) on the CPU        */
 
 /* ---- descriptor kinds: what extractDescriptor emits (featureMatchingCPU.cpp:45-66) ------ */
 #define SLAMB200_DESC_F32X128 0 /* cv::SIFT: CV_32F, 128 columns */
@@ -206,7 +209,8 @@ int slamb200_batch_scores_fetch(slamb200_ctx* ctx, int32_t* counts, int32_t* bes
 #define SLAMB200_K_SIFT_TC_GEN 6 /* tcgen05 kernel, general floats     */
 #define SLAMB200_K_SIFT_GEN_RERANK 7 /* certified fp32 rerank + fallback */
 #define SLAMB200_K_PNP 8        /* reprojection-error counting kernel */
-#define SLAMB200_K_COUNT 9
+#define SLAMB200_K_SIFT_L1 9    /* NORM_L1 on integer-valued rows (byte-wise SAD) */
+#define SLAMB200_K_COUNT 10
 int slamb200_profile_enable(slamb200_ctx* ctx, int on);
 /* Synchronises, then returns the summed device time (ms) and the launch count of each kernel
  * class since the last read; ms and launches have SLAMB200_K_COUNT entries. */

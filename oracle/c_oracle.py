@@ -45,6 +45,16 @@ def l2_knn2(Q, T):
     return idx, dist
 
 
+def l1_knn2(Q, T):
+    Q = np.ascontiguousarray(Q, np.float32).reshape(-1, 128) if Q.size else np.zeros((0, 128), np.float32)
+    T = np.ascontiguousarray(T, np.float32).reshape(-1, 128) if T.size else np.zeros((0, 128), np.float32)
+    idx = np.full((Q.shape[0], 2), -1, np.int32)
+    dist = np.zeros((Q.shape[0], 2), np.float32)
+    rc = lib().oracle_l1_knn2(_p(Q), Q.shape[0], _p(T), T.shape[0], 128, _p(idx), _p(dist))
+    assert rc == 0
+    return idx, dist
+
+
 def hamming_knn2(Q, T):
     Q = np.ascontiguousarray(Q, np.uint8).reshape(-1, 32) if Q.size else np.zeros((0, 32), np.uint8)
     T = np.ascontiguousarray(T, np.uint8).reshape(-1, 32) if T.size else np.zeros((0, 32), np.uint8)
@@ -73,6 +83,8 @@ def match_features(matcher, Q, T, ratio):
         idx, dist = l2_knn2(Q, T)
     elif matcher == 2:
         idx, dist = hamming_knn2(Q, T)
+    elif matcher == 3:
+        idx, dist = l1_knn2(Q, T)
     else:
         raise ValueError("bad matcher type")  # reference: throw std::exception()
     return ratio_test(idx, dist, ratio)

@@ -118,6 +118,38 @@ int oracle_l2_knn2(const float* Q, int nq, const float* T, int nt, int dim,
     return 0;
 }
 
+/* NORM_L1 (what useFM-SIFT-BF selects in the reference's OpenCV-CUDA build,
+ * featureMatchingCUDA.cpp:28).  OpenCV-CUDA cannot run here; the CPU BFMatcher(NORM_L1) is the
+ * arithmetic owner: normL1<float,float> sums groups of four,
+ * s += |d0| + |d1| + |d2| + |d3| (left to right), in float -- pinned against cv2 bit for bit
+ * (tests/test_oracle_vs_cv2.py).  For the integer-valued rows cv::SIFT emits every order is exact. */
+static float l1_cv(const float* a, const float* b, int n) {
+    float s = 0.f;
+    int i = 0;
+    for (; i <= n - 4; i += 4) {
+        float v0 = a[i] - b[i], v1 = a[i + 1] - b[i + 1], v2 = a[i + 2] - b[i + 2],
+              v3 = a[i + 3] - b[i + 3];
+        s += fabsf(v0) + fabsf(v1) + fabsf(v2) + fabsf(v3);
+    }
+    for (; i < n; i++) s += fabsf(a[i] - b[i]);
+    return s;
+}
+
+int oracle_l1_knn2(const float* Q, int nq, const float* T, int nt, int dim,
+                   int32_t* idx /* nq*2 */, float* dist /* nq*2 */) {
+    if (nq < 0 || nt < 0 || dim <= 0) return -1;
+#pragma omp parallel for schedule(static)
+    for (int q = 0; q < nq; q++) {
+        int32_t dk[2] = {f2i(FLT_MAX), f2i(FLT_MAX)};
+        int32_t ik[2] = {-1, -1};
+        const float* a = Q + (size_t)q * dim;
+        for (int t = 0; t < nt; t++) top2_insert(f2i(l1_cv(a, T + (size_t)t * dim, dim)), t, dk, ik);
+        idx[2 * q] = ik[0]; idx[2 * q + 1] = ik[1];
+        dist[2 * q] = i2f(dk[0]); dist[2 * q + 1] = i2f(dk[1]);
+    }
+    return 0;
+}
+
 /* BFMatcher(NORM_HAMMING).knnMatch: int distances = popcount(a ^ b), converted to float in the
  * DMatch. */
 int oracle_hamming_knn2(const uint8_t* Q, int nq, const uint8_t* T, int nt, int nbytes,
@@ -310,6 +342,8 @@ int oracle_match_features(int matcher, const void* q, int nq, const void* t, int
         rc = oracle_l2_knn2((const float*)q, nq, (const float*)t, nt, 128, idx, dist);
     else if (matcher == 2)
         rc = oracle_hamming_knn2((const uint8_t*)q, nq, (const uint8_t*)t, nt, 32, idx, dist);
+    else if (matcher == 3) /* SIFT_BF as the OpenCV-CUDA build reads it: NORM_L1 */
+        rc = oracle_l1_knn2((const float*)q, nq, (const float*)t, nt, 128, idx, dist);
     else
         rc = -3; /* reference: throw std::exception() (featureMatchingCPU.cpp:37) */
     if (rc == 0) rc = oracle_ratio_test(idx, dist, nq, ratio, out, n_out);

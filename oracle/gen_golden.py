@@ -6,10 +6,11 @@ entry points the reference calls, through the cv2 wheel:
 
   featureMatchingCPU.cpp:26-40   DescriptorMatcher BRUTEFORCE / BRUTEFORCE_HAMMING, knnMatch k=2
   cameraTranslation.cpp:41-46    findEssentialMat(p1, p2, K, RANSAC, prob, threshold, mask)
+  featureMatchingCUDA.cpp:28     NORM_L1 for useFM-SIFT-BF (CPU BFMatcher as the owner)
   mainCycle.cpp:155-159          solvePnPRansac(obj, img, K, dist, rvec, tvec)   
 
 Run from the repo root:   python -m oracle.gen_golden          (all fixtures)
-                          python -m oracle.gen_golden pnp      (only pnp.npz)
+                          python -m oracle.gen_golden pnp|l1   (only pnp.npz / sift_l1.npz)
 Everything is seeded; outputs are committed so the GPU box (no /root/reference, possibly another
 cv2 dispatch path) checks against exactly these bytes.
 """
@@ -120,9 +121,21 @@ def main():
     cases["threshold_px"] = np.float64(5.0)
     np.savez_compressed(os.path.join(OUT, "ransac.npz"), **cases)
 
+    gen_l1()
     gen_pnp()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} fixtures, {total/1024:.0f} KiB, cv2 {cv2.__version__}")
+
+
+def gen_l1():
+    """NORM_L1: cv2.BFMatcher(NORM_L1) on integer rows, general floats, ties and
+    the ragged shapes -- the inputs of the existing SIFT fixtures, so only the results are stored."""
+    out = {}
+    for name in ("sift_int", "sift_float", "sift_ties", "sift_t1", "sift_t2", "sift_q1"):
+        g = np.load(os.path.join(OUT, name + ".npz"))
+        idx, dist, _ = cv_knn2(g["q"].astype(np.float32), g["t"].astype(np.float32), cv2.NORM_L1)
+        out[name + "_idx"], out[name + "_dist"] = idx, dist
+    np.savez_compressed(os.path.join(OUT, "sift_l1.npz"), **out)
 
 
 def gen_pnp():
@@ -165,5 +178,7 @@ if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "pnp":
         gen_pnp()
+    elif len(sys.argv) > 1 and sys.argv[1] == "l1":
+        gen_l1()
     else:
         main()

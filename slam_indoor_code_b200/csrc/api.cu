@@ -525,9 +525,10 @@ static int pick_splits(int q_blocks, int n_pairs, int t_max, int min_chunk) {
 
 static int check_matcher(int matcher, const slamb200_desc* q, const slamb200_desc* const* t,
                          int n_pairs) {
-  if (matcher != SLAMB200_SIFT_BF && matcher != SLAMB200_SIFT_FLANN && matcher != SLAMB200_ORB_BF)
-    return fail(SLAMB200_ERR_MATCHER, "matcher type %d is not 0 (SIFT_BF), 1 (SIFT_FLANN) or 2 (ORB_BF)",
-                matcher);
+  if (matcher != SLAMB200_SIFT_BF && matcher != SLAMB200_SIFT_FLANN && matcher != SLAMB200_ORB_BF &&
+      matcher != SLAMB200_SIFT_BF_L1)
+    return fail(SLAMB200_ERR_MATCHER,
+                "matcher type %d is not 0 (SIFT_BF), 1 (SIFT_FLANN), 2 (ORB_BF) or 3 (SIFT_BF_L1)", matcher);
   const int kind = matcher == SLAMB200_ORB_BF ? SLAMB200_DESC_U8X32 : SLAMB200_DESC_F32X128;
   if (!q) return fail(SLAMB200_ERR_INVALID, "query descriptor set is NULL");
   if (q->kind != kind) return fail(SLAMB200_ERR_KIND, "query descriptor kind does not fit the matcher");
@@ -557,13 +558,14 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   if (n_pairs == 0) return SLAMB200_OK;
   int rc;
   const bool orb = matcher == SLAMB200_ORB_BF;
+  const bool l1 = matcher == SLAMB200_SIFT_BF_L1;
   int t_max = 0;
   for (int p = 0; p < n_pairs; p++) t_max = trains[p]->n > t_max ? trains[p]->n : t_max;
   if (orb && t_max >= (1 << 22))
     return fail(SLAMB200_ERR_INVALID, "ORB train set of %d rows exceeds the 2^22-row key range", t_max);
   // the candidate records pack two 16-bit group indices: train sets beyond 524k rows take the
   // exact fp32 kernel instead
-  const bool tc = !orb && c->use_tc && nq > 0 && t_max <= 65535 * 8;
+  const bool tc = !orb && !l1 && c->use_tc && nq > 0 && t_max <= 65535 * 8;
   const int q_blocks = orb ? (nq + 255) / 256 : (nq + 15) / 16;
   const int n_split = pick_splits(q_blocks > 0 ? q_blocks : 1, n_pairs, t_max, orb ? 1024 : 512);
 
@@ -582,6 +584,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   for (int p = 0; p < n_pairs; p++) {
     hp[p].t_rows = orb ? (const void*)trains[p]->u8 : (const void*)trains[p]->f32;
     hp[p].t_flags = orb ? nullptr : trains[p]->flags;
+    hp[p].t_u8 = trains[p]->u8;
     hp[p].t_n = trains[p]->n;
     hp[p].t_pad = trains[p]->n_pad;
   }
@@ -677,9 +680,23 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     // mode tcgen05 kernel + dp4a rerank; general-float pairs take the two-term-split tcgen05 kernel
     // + certified fp32 rerank (+ exact fallback rows).  The kernels pick their pairs from the
     // flags on the device, so no host synchronisation is needed to route.
-    if (!tc) {
+    if (l1) {
+      // NORM_L1 (the OpenCV-CUDA build's useFM-SIFT-BF): integer-valued pairs on the u8 copy with
+      // the byte-wise SAD instruction, everything else in fp32 in cv::BFMatcher(NORM_L1)'s order;
+      // both kernels route on the device flags
+      const bool u8_ok = t_max <= sift_l1_max_train_rows();
+      if (u8_ok) {
+        ProfScope ps(c, s, SLAMB200_K_SIFT_L1);
+        launch_sift_l1_u8(q->u8, q->flags, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p, s);
+      }
+      if (!u8_ok || !all_exact_known) {
+        ProfScope ps(c, s, SLAMB200_K_SIFT_EXACT);
+        launch_sift_exact_knn2(q->f32, q->flags, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p,
+                               u8_ok ? 0 : 1, 1, s);
+      }
+    } else if (!tc) {
       ProfScope ps(c, s, SLAMB200_K_SIFT_EXACT);
-      launch_sift_exact_knn2(q->f32, q->flags, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p, 1, s);
+      launch_sift_exact_knn2(q->f32, q->flags, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p, 1, 0, s);
     }
     if (tc) {
       // Slot records are normally all written by the kernel (the merge pass computes which ones

@@ -54,6 +54,7 @@ struct slamb200_pts {
 struct PairArgs {
   const void* t_rows;      // train rows: float* (SIFT exact) or uint8_t* (ORB)
   const int32_t* t_flags;  // train exact-mode flag (SIFT) or nullptr
+  const uint8_t* t_u8;     // SIFT: the u8 copy of the rows (valid in exact mode); ORB: t_rows
   int t_n;                 // train row count
   int t_pad;
 };
@@ -67,7 +68,12 @@ void launch_orb_knn2(const uint8_t* q, int nq, const PairArgs* pairs, int n_pair
 // SIFT exact fp32 (cv2 summation order); skips pairs whose query and train are both in exact
 // mode (flags[0] == 0; the tcgen05 path owns those) unless force != 0.
 void launch_sift_exact_knn2(const float* q, const int32_t* q_flags, int nq, const PairArgs* pairs,
-                            int n_pairs, int n_split, uint4* part, int force, cudaStream_t s);
+                            int n_pairs, int n_split, uint4* part, int force, int norm_l1,
+                            cudaStream_t s);
+// NORM_L1 on the u8 copy of integer-valued SIFT rows (train sets up to sift_l1_max_train_rows()).
+void launch_sift_l1_u8(const uint8_t* q_u8, const int32_t* q_flags, int nq, const PairArgs* pairs,
+                       int n_pairs, int n_split, uint4* part, cudaStream_t s);
+int sift_l1_max_train_rows();
 // merge partials -> raw knn + ratio flags + per-chunk counts, then ordered compaction.
 void launch_finalize(const uint4* part, int nq, const PairArgs* pairs, int n_pairs, int n_split,
                      int hamming, double ratio, int32_t* knn_idx, float* knn_dist,

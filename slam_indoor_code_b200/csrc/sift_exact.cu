@@ -8,6 +8,10 @@
 // S[l] = ((acc0+acc1)+acc2)+acc3, d2 = (S0+S2)+(S1+S3), dist = sqrtf(d2).  Every operation below
 // is an explicit round-to-nearest intrinsic so the compiler cannot contract anything into an FMA.
 //
+// NORM = 1 is the NORM_L1 twin (the OpenCV-CUDA build's useFM-SIFT-BF, featureMatchingCUDA.cpp:28;
+// SURVEY.md 8f-4), in the order of cv::BFMatcher(NORM_L1) on the CPU: one accumulator,
+// s += ((|d0| + |d1|) + |d2|) + |d3| over groups of four elements, no square root.
+//
 // Shape: a work item is (pair, 16 query rows, one of n_split train ranges); a 256-thread block
 // holds the query rows in shared memory and streams 64-row train tiles through it.  Each thread
 // owns a 2 x 2 block of (query, train) pairs = 64 accumulators; lanes run along the train rows
@@ -19,11 +23,13 @@
 #define SE_TT 64     // train rows per tile
 #define SE_PITCH 132 // floats per shared row (128 + 4: 16-byte skew per row)
 
-__device__ __forceinline__ uint32_t dist_key(const float (&acc)[4][4]) {
+template <int NORM, int NV, int NL>
+__device__ __forceinline__ uint32_t dist_key(const float (&acc)[NV][NL]) {
+  if (NORM == 1) return __float_as_uint(acc[0][0]);
   float S[4];
 #pragma unroll
   for (int l = 0; l < 4; l++)
-    S[l] = __fadd_rn(__fadd_rn(__fadd_rn(acc[0][l], acc[1][l]), acc[2][l]), acc[3][l]);
+    S[l] = __fadd_rn(__fadd_rn(__fadd_rn(acc[0][l % NL], acc[1 % NV][l % NL]), acc[2 % NV][l % NL]), acc[3 % NV][l % NL]);
   const float d2 = __fadd_rn(__fadd_rn(S[0], S[2]), __fadd_rn(S[1], S[3]));
   return __float_as_uint(sqrtf(d2));
 }
@@ -40,6 +46,7 @@ __device__ __forceinline__ void top2_insert(uint4& r, uint32_t k, uint32_t i) {
   }
 }
 
+template <int NORM>
 __global__ void __launch_bounds__(SE_THREADS)
 sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_flags, int nq,
                        const PairArgs* __restrict__ pairs, int n_pairs, int n_split, long long n_items,
@@ -101,15 +108,16 @@ sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ 
     }
     __syncthreads();
 
-    float acc[2][2][4][4];
+    constexpr int NV = NORM == 0 ? 4 : 1, NL = NORM == 0 ? 4 : 1;
+    float acc[2][2][NV][NL];
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
       for (int b = 0; b < 2; b++)
 #pragma unroll
-        for (int v = 0; v < 4; v++)
+        for (int v = 0; v < NV; v++)
 #pragma unroll
-          for (int l = 0; l < 4; l++) acc[a][b][v][l] = 0.f;
+          for (int l = 0; l < NL; l++) acc[a][b][v][l] = 0.f;
 
     const float* q0 = sq + (2 * warp) * SE_PITCH;
     const float* q1 = q0 + SE_PITCH;
@@ -128,12 +136,19 @@ sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ 
 #pragma unroll
         for (int a = 0; a < 2; a++)
 #pragma unroll
-          for (int b = 0; b < 2; b++)
+          for (int b = 0; b < 2; b++) {
+            if (NORM == 0) {
 #pragma unroll
-            for (int l = 0; l < 4; l++) {
-              const float d = __fsub_rn(qa[a][l], tb4[b][l]);
-              acc[a][b][v][l] = __fadd_rn(acc[a][b][v][l], __fmul_rn(d, d));
+              for (int l = 0; l < 4; l++) {
+                const float d = __fsub_rn(qa[a][l], tb4[b][l]);
+                acc[a][b][v % NV][l % NL] = __fadd_rn(acc[a][b][v % NV][l % NL], __fmul_rn(d, d));
+              }
+            } else {
+              const float d0 = fabsf(__fsub_rn(qa[a][0], tb4[b][0])), d1 = fabsf(__fsub_rn(qa[a][1], tb4[b][1]));
+              const float d2 = fabsf(__fsub_rn(qa[a][2], tb4[b][2])), d3 = fabsf(__fsub_rn(qa[a][3], tb4[b][3]));
+              acc[a][b][0][0] = __fadd_rn(acc[a][b][0][0], __fadd_rn(__fadd_rn(__fadd_rn(d0, d1), d2), d3));
             }
+          }
       }
     }
 #pragma unroll
@@ -141,7 +156,7 @@ sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ 
       const int trow = tb + lane + 32 * b;
       if (trow < t_end) {
 #pragma unroll
-        for (int a = 0; a < 2; a++) top2_insert(best[a], dist_key(acc[a][b]), (uint32_t)trow);
+        for (int a = 0; a < 2; a++) top2_insert(best[a], dist_key<NORM>(acc[a][b]), (uint32_t)trow);
       }
     }
   }
@@ -167,18 +182,23 @@ sift_exact_knn2_kernel(const float* __restrict__ q, const int32_t* __restrict__ 
 }
 
 void launch_sift_exact_knn2(const float* q, const int32_t* q_flags, int nq, const PairArgs* pairs,
-                            int n_pairs, int n_split, uint4* part, int force, cudaStream_t s) {
+                            int n_pairs, int n_split, uint4* part, int force, int norm_l1,
+                            cudaStream_t s) {
   if (nq <= 0 || n_pairs <= 0) return;
   const size_t smem = (size_t)(SE_QT + SE_TT) * SE_PITCH * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(sift_exact_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
+    cudaFuncSetAttribute(sift_exact_knn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(sift_exact_knn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
   const long long n_items = (long long)((nq + SE_QT - 1) / SE_QT) * n_split * n_pairs;
   const int grid = (int)(n_items < 148 * 8 ? n_items : 148 * 8);
-  sift_exact_knn2_kernel<<<grid, SE_THREADS, smem, s>>>(q, q_flags, nq, pairs, n_pairs, n_split, n_items,
-                                                        part, force);
+  if (norm_l1)
+    sift_exact_knn2_kernel<1><<<grid, SE_THREADS, smem, s>>>(q, q_flags, nq, pairs, n_pairs, n_split,
+                                                             n_items, part, force);
+  else
+    sift_exact_knn2_kernel<0><<<grid, SE_THREADS, smem, s>>>(q, q_flags, nq, pairs, n_pairs, n_split,
+                                                             n_items, part, force);
   COUNT_LAUNCH();
 }

@@ -24,6 +24,9 @@ class MatcherType(enum.IntEnum):
     SIFT_BF = 0
     SIFT_FLANN = 1
     ORB_BF = 2
+    # not in the reference enum: what useFM-SIFT-BF means in its OpenCV-CUDA build (NORM_L1,
+    # featureMatchingCUDA.cpp:28); SURVEY.md 8f-4
+    SIFT_BF_L1 = 3
 
 
 def getMatcherTypeIndex(config):
@@ -39,7 +42,7 @@ def getMatcherTypeIndex(config):
 
 
 def _kind_of(matcher_type):
-    if matcher_type in (MatcherType.SIFT_BF, MatcherType.SIFT_FLANN):
+    if matcher_type in (MatcherType.SIFT_BF, MatcherType.SIFT_FLANN, MatcherType.SIFT_BF_L1):
         return _capi.DESC_F32X128
     if matcher_type == MatcherType.ORB_BF:
         return _capi.DESC_U8X32
@@ -81,7 +84,7 @@ class Context:
         return int(self._lib.slamb200_launch_count(self._h))
 
     KERNELS = ("sift_tc", "sift_exact", "orb", "ransac", "sift_rerank", "finalize", "sift_tc_gen",
-               "sift_gen_rerank", "pnp")
+               "sift_gen_rerank", "pnp", "sift_l1")
 
     def profile_enable(self, on=True):
         check(self._lib.slamb200_profile_enable(self._h, 1 if on else 0))

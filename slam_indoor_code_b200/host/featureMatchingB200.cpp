@@ -64,6 +64,16 @@ int descKindOf(int matcherType) {
   }
 }
 
+// The reference's two builds disagree on useFM-SIFT-BF: NORM_L2 on the CPU (featureMatchingCPU.cpp:28),
+// NORM_L1 in the OpenCV-CUDA build (featureMatchingCUDA.cpp:28).  The CPU meaning is the default;
+// -DSLAMB200_CUDA_BUILD_COMPAT selects the CUDA build's.
+inline int abiMatcher(int matcherType) {
+#ifdef SLAMB200_CUDA_BUILD_COMPAT
+  if (matcherType == SIFT_BF) return SLAMB200_SIFT_BF_L1;
+#endif
+  return matcherType;
+}
+
 void upload(const Mat& desc, int kind, DescHandle& h) {
   const int want = kind == SLAMB200_DESC_F32X128 ? CV_32F : CV_8U;
   const int cols = kind == SLAMB200_DESC_F32X128 ? 128 : 32;
@@ -95,7 +105,7 @@ static void matchFeatures(Mat& prevDesc, Mat& curDesc, std::vector<DMatch>& matc
   static_assert(sizeof(DMatch) == sizeof(slamb200_dmatch), "cv::DMatch layout");
   matches.resize((size_t)cap);
   int n = 0;
-  const int rc = slamb200_match_pair(context(), extractorType, q.d, t.d, knnMatcherDistance(),
+  const int rc = slamb200_match_pair(context(), abiMatcher(extractorType), q.d, t.d, knnMatcherDistance(),
                                      reinterpret_cast<slamb200_dmatch*>(matches.data()), cap, &n);
   if (rc != SLAMB200_OK) {
     matches.clear();
@@ -159,7 +169,7 @@ void matchFramesBatchFeatures(Mat& firstFrameDescriptor, std::vector<Mat>& batch
   if (P == 0 || cap == 0) return;
   std::vector<slamb200_dmatch> out((size_t)P * cap);
   std::vector<int> n((size_t)P, 0);
-  const int rc = slamb200_match_batch(context(), matcherType, q.d, tp.data(), P, knnMatcherDistance(),
+  const int rc = slamb200_match_batch(context(), abiMatcher(matcherType), q.d, tp.data(), P, knnMatcherDistance(),
                                       out.data(), cap, n.data());
   if (rc != SLAMB200_OK) throw std::runtime_error(std::string("slamb200_match_batch: ") + slamb200_last_error());
   for (int p = 0; p < P; p++) {

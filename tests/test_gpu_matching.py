@@ -401,3 +401,58 @@ def test_general_float_scales_and_signs(ctx):
     ridx, rdist = c_oracle.l2_knn2(rs(qi), rs(ti))
     _check_knn(idx, dist, ridx, rdist)
     assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.7))
+
+
+# ---- NORM_L1 mode: useFM-SIFT-BF as the reference's OpenCV-CUDA build reads it --
+@pytest.mark.parametrize("name", SIFT_GOLD)
+def test_sift_l1_golden(ctx, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    l1 = np.load(os.path.join(golden_dir, "sift_l1.npz"))
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.SIFT_BF_L1, _f32(g["q"]), _f32(g["t"]))
+    _check_knn(idx, dist, l1[name + "_idx"], l1[name + "_dist"])
+    assert np.array_equal(good, c_oracle.ratio_test(l1[name + "_idx"], l1[name + "_dist"], 0.7))
+
+
+@pytest.mark.parametrize("nq,nt,seed,kind", [(1000, 1500, 111, "int"), (2049, 777, 112, "int"), (130, 4100, 113, "int"),
+                                             (700, 900, 114, "float"), (255, 2049, 115, "float")])
+def test_sift_l1_seeded(ctx, nq, nt, seed, kind):
+    q, t = synth.sift_pair(nq, nt, seed) if kind == "int" else synth.float_pair(nq, nt, seed)
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.SIFT_BF_L1, q, t)
+    ridx, rdist = c_oracle.l1_knn2(q, t)
+    _check_knn(idx, dist, ridx, rdist)
+    assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.7))
+
+
+def test_sift_l1_ties_mixed_batch_and_edges(ctx):
+    # heavy ties: equal L1 distances must keep the lowest train index
+    rng = np.random.default_rng(17)
+    base = synth.sift_like(6, 18)
+    q, t = base[rng.integers(0, 6, 300)], base[rng.integers(0, 6, 2600)]
+    idx, dist, _ = _knn_and_matches(ctx, MatcherType.SIFT_BF_L1, q, t)
+    _check_knn(idx, dist, *c_oracle.l1_knn2(q, t))
+    # one batch mixing integer-valued and general-float train sets, ragged sizes, T = 0 / 1 / 2
+    qi = synth.sift_like(500, 19)
+    trains = [synth.sift_like(700, 20), synth.float_pair(1, 300, 21)[1], synth.sift_like(1, 22),
+              np.zeros((0, 128), np.float32), synth.sift_like(2, 23), synth.sift_like(1300, 24) * 0.5]
+    Q = ctx.upload(qi)
+    Ts = [ctx.upload(t) for t in trains]
+    res = ctx.matchBatch(Q, Ts, MatcherType.SIFT_BF_L1, 0.8)
+    for t, got in zip(trains, res):
+        assert np.array_equal(got, c_oracle.match_features(3, qi, t, 0.8))
+    # general-float query against integer trains
+    qf = synth.float_pair(300, 1, 25)[0]
+    res = ctx.matchBatch(ctx.upload(qf), Ts, MatcherType.SIFT_BF_L1, 0.8)
+    for t, got in zip(trains, res):
+        assert np.array_equal(got, c_oracle.match_features(3, qf, t, 0.8))
+
+
+def test_sift_l1_10k_properties(ctx):
+    """BASELINE cfg1 size: against the oracle on a row sample + planted correspondences found."""
+    q, t = synth.sift_pair(10000, 10000, 1001)
+    Q, T = ctx.upload(q), ctx.upload(t)
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF_L1, Q, T)
+    rows = np.random.default_rng(5).choice(10000, 300, replace=False)
+    ridx, rdist = c_oracle.l1_knn2(q[rows], t)
+    _check_knn(idx[rows], dist[rows], ridx, rdist)
+    good = ctx.matchFeatures(Q, T, MatcherType.SIFT_BF_L1, 0.7)
+    assert 2000 < len(good) <= 10000 and np.all(np.diff(good["queryIdx"]) > 0)

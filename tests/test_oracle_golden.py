@@ -103,7 +103,7 @@ def test_c_and_np_oracles_agree_on_seeded_inputs():
     idx, dist = np_oracle.knn2_from_matrix(np_oracle.hamming_dist_matrix(q, t))
     assert np.array_equal(a, np_oracle.ratio_test(idx, dist, 0.7)) and len(a) > 10
     with pytest.raises(ValueError):
-        c_oracle.match_features(3, q, t, 0.7)
+        c_oracle.match_features(4, q, t, 0.7)
 
 
 def test_ransac_masks_match_cv2(golden_dir):
@@ -168,3 +168,14 @@ def test_pnp_cv2_ransac_inliers_are_the_mask_of_some_minimal_model(golden_dir):
         assert bool(g[f"cv_ok_{c}"])
         inl = g[f"cv_inliers_{c}"]
         assert len(inl) > 4 and np.all(np.diff(inl) > 0)
+
+
+# ---- NORM_L1 mode ---------------------------------------------------------------
+@pytest.mark.parametrize("name", ["sift_int", "sift_float", "sift_ties", "sift_t1", "sift_t2", "sift_q1"])
+def test_c_oracle_l1_matches_cv2(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    l1 = np.load(os.path.join(golden_dir, "sift_l1.npz"))
+    idx, dist = c_oracle.l1_knn2(g["q"].astype(np.float32), g["t"].astype(np.float32))
+    assert np.array_equal(idx, l1[name + "_idx"])
+    valid = idx >= 0
+    assert np.array_equal(dist[valid].view(np.int32), l1[name + "_dist"][valid].view(np.int32))

@@ -105,3 +105,12 @@ def test_solve_pnp_ransac_control_and_scoring(m, seed):
     k, r, t = cv2.solvePnP(obj[got_inl].astype(np.float64), img[got_inl].astype(np.float64), Kmat, dist,
                            r0.copy(), t0.copy(), True, cv2.SOLVEPNP_ITERATIVE)
     assert k and np.array_equal(r, rvec) and np.array_equal(t, tvec)
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_l1_int_and_float_bit_exact(seed):
+    """BFMatcher(NORM_L1): s += |d0| + |d1| + |d2| + |d3| per group of four, in float."""
+    for q, t in (synth.sift_pair(257, 513, seed), synth.float_pair(257, 513, seed)):
+        idx, dist, _ = cv_knn2(q, t, cv2.NORM_L1)
+        oi, od = c_oracle.l1_knn2(q, t)
+        assert np.array_equal(idx, oi) and np.array_equal(dist.view(np.int32), od.view(np.int32))
