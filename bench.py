@@ -547,6 +547,17 @@ def extras(ctx, stream):
     # 53 explicit fp64 operations per (pose, point) with five coefficients (the reciprocal counted once)
     out["f2_pnp_2048x5000"] = {"kernel_us_per_frame": kms / kn / P * 1e3,
                                "fp64_ops_T_per_s": P * 2048 * 5000 * 53 / (kms / kn) / 1e9}
+    # next row 8f-4: linear triangulation of 5000 matches (one host call incl. copies)
+    from slam_indoor_code_b200 import triangulation as tri
+    K4 = synth.SAMSUNG_HV_4K
+    Km = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]])
+    tp1, tp2, tR, tt = synth.two_view(5000, 8000, outliers=0.0)
+    for _ in range(3):
+        tri.reconstruct(ctx, Km, np.eye(3), np.zeros(3), tR, tt, tp1, tp2)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        tri.reconstruct(ctx, Km, np.eye(3), np.zeros(3), tR, tt, tp1, tp2)
+    out["f4_triangulate_5000"] = {"us_per_host_call": (time.perf_counter() - t0) / 20 * 1e6}
     # pipe-rate denominators measured on this box (csrc/microbench.cu)
     try:
         import ctypes
@@ -554,7 +565,9 @@ def extras(ctx, stream):
         lib.slamb200_dbg_pipe_rate.restype = ctypes.c_double
         lib.slamb200_dbg_pipe_rate.argtypes = [ctypes.c_int]
         popc, fp64 = lib.slamb200_dbg_pipe_rate(0), lib.slamb200_dbg_pipe_rate(1)
-        out["pipe_rates"] = {"popc_G_per_s": popc, "fp64_dmul_dadd_G_per_s": fp64}
+        sad4 = lib.slamb200_dbg_pipe_rate(2)
+        out["pipe_rates"] = {"popc_G_per_s": popc, "fp64_dmul_dadd_G_per_s": fp64, "vabsdiff4_G_per_s": sad4}
+        out["f4_sift_l1_16_pairs"]["frac_of_vabsdiff4_pipe"] = out["f4_sift_l1_16_pairs"]["tsad4_per_s"] * 1e3 / sad4
         out["cfg2_orb_16_pairs"]["frac_of_popc_pipe"] = out["cfg2_orb_16_pairs"]["tpopc_per_s"] * 1e3 / popc
         out["cfg5_ransac_2048x5000"]["frac_of_fp64_pipe"] = \
             out["cfg5_ransac_2048x5000"]["dp_instr_per_s_T"] * 1e3 / fp64
@@ -614,6 +627,19 @@ def cpu_extras():
     Kmat = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]])
     dt, _ = best(lambda: cv2.findEssentialMat(p1, p2, Kmat, cv2.RANSAC, 0.999, 5.0), 5)
     out["cfg5_findEssentialMat_s_per_pair"] = dt
+    # the "next" rows: NORM_L1 matcher, solvePnPRansac, triangulation
+    dt, _ = best(lambda: cv2.BFMatcher(cv2.NORM_L1).knnMatch(q, t, 2), 2)
+    out["f4_sift_bf_l1_s_per_pair"] = dt
+    obj, img, _, _ = synth.pnp_scene(5000, 7000)
+    dist = np.array(synth.REF_DIST5)
+    dt, _ = best(lambda: cv2.solvePnPRansac(obj, img, Kmat, dist), 5)
+    out["f2_solvePnPRansac_s_per_frame"] = dt
+    tp1, tp2, tR, tt = synth.two_view(5000, 8000, outliers=0.0)
+    P1 = Kmat @ np.hstack([np.eye(3), np.zeros((3, 1))])
+    P2 = Kmat @ np.hstack([tR, tt.reshape(3, 1)])
+    a, b = tp1.T.astype(np.float64), tp2.T.astype(np.float64)
+    dt, _ = best(lambda: cv2.triangulatePoints(P1, P2, a, b), 5)
+    out["f4_triangulatePoints_5000_s"] = dt
     return out
 
 

@@ -182,6 +182,17 @@ int slamb200_score_pnp_batch(slamb200_ctx* ctx, int P, const float* obj, const f
                              int model_points, int32_t* counts, int32_t* best,
                              uint8_t* best_mask);
 
+/* ---- next row: linear triangulation (triangulation/triangulate.cpp:17-55, :91-108) --- */
+/* reconstructPointsFor3D for M matches: P1, P2 = 3x4 row-major projection matrices (K*[R|t], as
+ * reconstruct() forms them at triangulate.cpp:74-80), pts = M x 2 floats (vector<Point2f>).  Per
+ * match: the 4x4 DLT system and row 3 of Vt of its SVD (OpenCV's one-sided Jacobi sequence).
+ * points4d (4 x M row-major, the reference's homogeneous Mat; may be NULL) and points3d (M x 3 =
+ * (X,Y,Z)*(1/W), what convertHomogeneousPointsMatrixToSpatialPointsVector returns; may be NULL).
+ * Floating point: equal to OpenCV within 1e-12 relative (libm vs CUDA hypot/sqrt), not bit-exact. */
+int slamb200_triangulate(slamb200_ctx* ctx, const double P1[12], const double P2[12],
+                         const float* pts1, const float* pts2, int M, double* points4d,
+                         double* points3d);
+
 /* Keypoint coordinates of a frame (cv::KeyPoint::pt as x,y float pairs, `stride` bytes apart)
  * kept in HBM so that getKeyPointCoordsFromFramePair (featureMatchingCommon.cpp:23-33) can run
  * on the device between matching and scoring. */

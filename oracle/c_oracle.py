@@ -167,3 +167,24 @@ def score_pnp(obj, img, K4, dist, poses, reproj_err, model_points=5, want_all_ma
                                 _p(allm) if allm is not None else None)
     assert rc == 0
     return counts, int(best.value), best_mask, allm
+
+
+def svd4_null_vector(A):
+    A = np.ascontiguousarray(A, np.float64).reshape(4, 4)
+    v, w = np.zeros(4), np.zeros(4)
+    lib().oracle_svd4_null_vector(_p(A), _p(v), _p(w))
+    return v, w
+
+
+def triangulate(P1, P2, pts1, pts2):
+    """reconstructPointsFor3D: returns points4d [4, M] and points3d [M, 3]."""
+    P1 = np.ascontiguousarray(P1, np.float64).reshape(3, 4)
+    P2 = np.ascontiguousarray(P2, np.float64).reshape(3, 4)
+    pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+    pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+    M = pts1.shape[0]
+    X4 = np.zeros((4, M))
+    X3 = np.zeros((M, 3))
+    rc = lib().oracle_triangulate(_p(P1), _p(P2), _p(pts1), _p(pts2), M, _p(X4), _p(X3))
+    assert rc == 0
+    return X4, X3

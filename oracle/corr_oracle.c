@@ -443,3 +443,113 @@ int oracle_score_pnp(const float* obj, const float* img, int M, const double* K4
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear triangulation (reference: src/mainModule/triangulation/triangulate.cpp:17-55
+ * reconstructPointsFor3D, :91-108 convertHomogeneousPointsMatrixToSpatialPointsVector).
+ *
+ * Per point the reference fills A (4x4): rows x*P[2,:] - P[0,:], y*P[2,:] - P[1,:] for the two views,
+ * and takes row 3 of Vt from cv::SVD::compute(A, W, U, Vt).  For a 4x4 double matrix OpenCV runs its
+ * own one-sided Jacobi (JacobiSVDImpl_ on At = A^T, eps = 10*DBL_EPSILON, at most 30 sweeps), then
+ * sorts the singular values in descending order; restated below and pinned against cv2.SVDecomp.
+ * ---------------------------------------------------------------------------------------------- */
+static void jacobi_svd4_vt(double At[4][4], double W[4], double Vt[4][4]) {
+    const int n = 4, m = 4;
+    const double eps = DBL_EPSILON * 10;
+    for (int i = 0; i < n; i++) {
+        double sd = 0;
+        for (int k = 0; k < m; k++) sd += At[i][k] * At[i][k];
+        W[i] = sd;
+        for (int k = 0; k < n; k++) Vt[i][k] = 0;
+        Vt[i][i] = 1;
+    }
+    for (int iter = 0; iter < 30; iter++) {
+        int changed = 0;
+        for (int i = 0; i < n - 1; i++)
+            for (int j = i + 1; j < n; j++) {
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < m; k++) p += At[i][k] * At[j][k];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                double beta = a - b, gamma = hypot(p, beta), c, s;
+                if (beta < 0) {
+                    double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+                a = b = 0;
+                for (int k = 0; k < m; k++) {
+                    double t0 = c * At[i][k] + s * At[j][k];
+                    double t1 = -s * At[i][k] + c * At[j][k];
+                    At[i][k] = t0; At[j][k] = t1;
+                    a += t0 * t0; b += t1 * t1;
+                }
+                W[i] = a; W[j] = b;
+                changed = 1;
+                for (int k = 0; k < n; k++) {
+                    double t0 = c * Vt[i][k] + s * Vt[j][k];
+                    double t1 = -s * Vt[i][k] + c * Vt[j][k];
+                    Vt[i][k] = t0; Vt[j][k] = t1;
+                }
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < n; i++) {
+        double sd = 0;
+        for (int k = 0; k < m; k++) sd += At[i][k] * At[i][k];
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < n - 1; i++) {
+        int j = i;
+        for (int k = i + 1; k < n; k++)
+            if (W[j] < W[k]) j = k;
+        if (i != j) {
+            double t = W[i]; W[i] = W[j]; W[j] = t;
+            for (int k = 0; k < 4; k++) {
+                t = At[i][k]; At[i][k] = At[j][k]; At[j][k] = t;
+                t = Vt[i][k]; Vt[i][k] = Vt[j][k]; Vt[j][k] = t;
+            }
+        }
+    }
+}
+
+/* Row 3 of Vt of a 4x4 matrix A (row-major), for pinning against cv2.SVDecomp. */
+int oracle_svd4_null_vector(const double* A, double* v4, double* w4) {
+    double At[4][4], W[4], Vt[4][4];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) At[c][r] = A[4 * r + c];
+    jacobi_svd4_vt(At, W, Vt);
+    for (int k = 0; k < 4; k++) { v4[k] = Vt[3][k]; if (w4) w4[k] = W[k]; }
+    return 0;
+}
+
+/* P1, P2: 3x4 row-major doubles (K*[R|t]); pts: M x 2 floats (vector<Point2f>, widened to double as
+ * the reference does with convertTo).  points4d: 4 x M row-major (the reference's Mat layout);
+ * points3d (optional): M x 3 = (X, Y, Z) * (1 / W), the "pointCol /= w" of the reference. */
+int oracle_triangulate(const double* P1, const double* P2, const float* pts1, const float* pts2,
+                       int M, double* points4d, double* points3d) {
+    if (M < 0) return -1;
+    const double* P[2] = {P1, P2};
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < M; p++) {
+        double At[4][4], W[4], Vt[4][4];
+        for (int v = 0; v < 2; v++) {
+            const float* pt = v == 0 ? pts1 : pts2;
+            double x = (double)pt[2 * p], y = (double)pt[2 * p + 1];
+            for (int c = 0; c < 4; c++) {
+                At[c][v * 2] = x * P[v][8 + c] - P[v][c];
+                At[c][v * 2 + 1] = y * P[v][8 + c] - P[v][4 + c];
+            }
+        }
+        jacobi_svd4_vt(At, W, Vt);
+        for (int k = 0; k < 4; k++) points4d[(size_t)k * M + p] = Vt[3][k];
+        if (points3d) {
+            double iw = 1. / Vt[3][3];
+            for (int k = 0; k < 3; k++) points3d[3 * (size_t)p + k] = Vt[3][k] * iw;
+        }
+    }
+    return 0;
+}

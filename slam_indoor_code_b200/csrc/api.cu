@@ -1124,6 +1124,39 @@ extern "C" int slamb200_score_pnp(slamb200_ctx* c, const float* obj, const float
   return SLAMB200_OK;
 }
 
+// ---- linear triangulation -----------------------------------------------------
+extern "C" int slamb200_triangulate(slamb200_ctx* c, const double P1[12], const double P2[12],
+                                    const float* pts1, const float* pts2, int M, double* points4d,
+                                    double* points3d) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  if (M < 0) return fail(SLAMB200_ERR_INVALID, "M negative");
+  if (!P1 || !P2) return fail(SLAMB200_ERR_INVALID, "projection matrix is NULL");
+  if (M == 0) return SLAMB200_OK;
+  if (!pts1 || !pts2) return fail(SLAMB200_ERR_INVALID, "NULL input");
+  if (!points4d && !points3d) return fail(SLAMB200_ERR_INVALID, "NULL output");
+  TriParams tp;
+  memcpy(tp.P[0], P1, sizeof(double) * 12);
+  memcpy(tp.P[1], P2, sizeof(double) * 12);
+  CU(cudaSetDevice(c->device));
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  cudaStream_t s = L.stream;
+  int rc;
+  if ((rc = buf_reserve(c, L.p1, (size_t)M * 8, s))) return rc;
+  if ((rc = buf_reserve(c, L.p2, (size_t)M * 8, s))) return rc;
+  if ((rc = buf_reserve(c, L.npts, (size_t)M * 56, s))) return rc;   // 4 x M + M x 3 doubles
+  double* d4 = (double*)L.npts.p;
+  double* d3 = d4 + (size_t)4 * M;
+  CU(cudaMemcpyAsync(L.p1.p, pts1, (size_t)M * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(L.p2.p, pts2, (size_t)M * 8, cudaMemcpyHostToDevice, s));
+  launch_triangulate((const float2*)L.p1.p, (const float2*)L.p2.p, M, tp, d4, d3, s);
+  CU(cudaGetLastError());
+  if (points4d) CU(cudaMemcpyAsync(points4d, d4, sizeof(double) * 4 * (size_t)M, cudaMemcpyDeviceToHost, s));
+  if (points3d) CU(cudaMemcpyAsync(points3d, d3, sizeof(double) * 3 * (size_t)M, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SLAMB200_OK;
+}
+
 // ---- keypoint coordinates + chained batch scoring ---------------------------------------------
 extern "C" int slamb200_upload_pts(slamb200_ctx* c, const float* xy, int n, size_t stride,
                                    slamb200_pts** out) {

@@ -119,6 +119,11 @@ void launch_pnp_mask(const double4* pts, const int32_t* m_off, const double* pos
 void launch_pnp_all_masks(const double4* pts, int M, const double* poses, int H,
                           const PnpParams& pp, uint8_t* masks, cudaStream_t s);
 
+// Linear triangulation (triangulate.cpp:17-55): P[v] = 3x4 projection matrix of view v, row-major.
+struct TriParams { double P[2][12]; };
+void launch_triangulate(const float2* pts1, const float2* pts2, int M, const TriParams& tp,
+                        double* points4d, double* points3d, cudaStream_t s);
+
 // SIFT prep: fp32 rows -> bf16 / aug / u8 / norms / exact flag.  n_pad rows are written
 // (padding rows get an "infinitely far" augmentation so they never become candidates).
 void launch_sift_prep(const float* src, size_t src_stride_floats, int n, int n_pad, float* f32,

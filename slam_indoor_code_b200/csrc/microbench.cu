@@ -34,7 +34,23 @@ __global__ void fp64_rate_kernel(double* out, int iters, double seed) {
   if (acc == 0.123456789) out[0] = acc;
 }
 
-// returns giga-ops/s: which = 0 POPC (popc instructions), 1 FP64 (DMUL + DADD instructions)
+__global__ void sad4_rate_kernel(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { a[j] = seed + threadIdx.x * 8 + j; b[j] = seed * 2654435761u + j; }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++)   // 1 VABSDIFF4.U8.ACC per step, eight independent chains
+      asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(a[j]) : "r"(b[j]), "r"((uint32_t)i));
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc += a[j];
+  if (acc == 0x12345678u) out[0] = acc;
+}
+
+// returns giga-ops/s: which = 0 POPC (popc instructions), 1 FP64 (DMUL + DADD instructions),
+// 2 byte-wise SAD (VABSDIFF4.U8.ACC instructions)
 extern "C" double slamb200_dbg_pipe_rate(int which) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -49,6 +65,7 @@ extern "C" double slamb200_dbg_pipe_rate(int which) {
   for (int rep = 0; rep < 4; rep++) {
     cudaEventRecord(a);
     if (which == 0) popc_rate_kernel<<<blocks, threads>>>((uint32_t*)buf, iters, 17u + rep);
+    else if (which == 2) sad4_rate_kernel<<<blocks, threads>>>((uint32_t*)buf, iters, 17u + rep);
     else fp64_rate_kernel<<<blocks, threads>>>((double*)buf, iters, 1.0 + rep);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
@@ -59,6 +76,6 @@ extern "C" double slamb200_dbg_pipe_rate(int which) {
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   cudaFree(buf);
-  const double ops = (double)blocks * threads * iters * 8 * (which == 0 ? 1 : 2);
+  const double ops = (double)blocks * threads * iters * 8 * (which == 1 ? 2 : 1);
   return ops / (best * 1e-3) / 1e9;
 }

@@ -87,6 +87,10 @@ void upload(const Mat& desc, int kind, DescHandle& h) {
 
 }  // namespace
 
+// the other B200 units of the drop-in (cameraTranslationB200.cpp, poseEstimationB200.cpp,
+// triangulateB200.cpp) share the process-wide context
+slamb200_ctx* slamb200HostContext() { return context(); }
+
 /*
  * @param prevDesc [in]  query descriptors (previous frame)
  * @param curDesc [in]   train descriptors (candidate frame)

@@ -114,3 +114,25 @@ def test_l1_int_and_float_bit_exact(seed):
         idx, dist, _ = cv_knn2(q, t, cv2.NORM_L1)
         oi, od = c_oracle.l1_knn2(q, t)
         assert np.array_equal(idx, oi) and np.array_equal(dist.view(np.int32), od.view(np.int32))
+
+
+def test_triangulation_oracle_vs_cv2():
+    """OpenCV's 4x4 Jacobi SVD (row 3 of Vt) and cv2.triangulatePoints, within 1e-14: the rotation
+    sequence is restated, libm's hypot/sqrt and the build's contraction choices are not."""
+    rng = np.random.default_rng(5)
+    for i in range(300):
+        A = rng.normal(size=(4, 4)) * rng.choice([1, 100, 1e-3])
+        w, u, vt = cv2.SVDecomp(A)
+        v, wo = c_oracle.svd4_null_vector(A)
+        assert np.allclose(wo, w.reshape(-1), rtol=1e-13, atol=1e-300)
+        if w[2, 0] - w[3, 0] > 1e-3 * w[0, 0]:
+            assert np.max(np.abs(v - vt[3])) < 1e-13
+    K4 = np.array(synth.SAMSUNG_HV_4K)
+    K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]])
+    p1, p2, R, t = synth.two_view(2000, 11, outliers=0.0)
+    P1 = K @ np.hstack([np.eye(3), np.zeros((3, 1))])
+    P2 = K @ np.hstack([R, t.reshape(3, 1)])
+    X4, X3 = c_oracle.triangulate(P1, P2, p1, p2)
+    ref = cv2.triangulatePoints(P1, P2, p1.T.astype(np.float64), p2.T.astype(np.float64))
+    assert np.max(np.abs(ref - X4)) < 1e-14
+    assert np.allclose(X3, (ref[:3] / ref[3]).T, rtol=1e-11)
