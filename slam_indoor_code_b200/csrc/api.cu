@@ -801,6 +801,24 @@ static int fetch_batch(Lane& L, cudaStream_t s, slamb200_dmatch* out, int out_ca
   if (out_cap < L.b_nq) return fail(SLAMB200_ERR_INVALID, "cap %d < query rows %d", out_cap, L.b_nq);
   if (!out) return fail(SLAMB200_ERR_INVALID, "out is NULL");
   if (P + 1 > N_SMALL) return fail(SLAMB200_ERR_INVALID, "too many pairs in one batch");
+  auto ensure_h_out = [&](size_t bytes) -> int {
+    if (L.h_out_cap >= bytes) return SLAMB200_OK;
+    if (L.h_out) CU(cudaFreeHost(L.h_out));
+    L.h_out = nullptr;
+    L.h_out_cap = 0;
+    CU(cudaMallocHost(&L.h_out, bytes * 2));
+    L.h_out_cap = bytes * 2;
+    return SLAMB200_OK;
+  };
+  // Small results (the per-pair drop-in call: 160 KB for 10k rows) come back speculatively in the
+  // same round trip as their counts: one synchronisation instead of two.
+  const size_t full = sizeof(slamb200_dmatch) * (size_t)L.b_cap * P;
+  const bool speculative = full <= (size_t)1 << 20;
+  if (speculative) {
+    int rc = ensure_h_out(full);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(L.h_out, L.out.p, full, cudaMemcpyDeviceToHost, s));
+  }
   CU(cudaMemcpyAsync(L.h_small + 1, L.n_out.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(L.h_small, L.status, 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -812,15 +830,14 @@ static int fetch_batch(Lane& L, cudaStream_t s, slamb200_dmatch* out, int out_ca
     n_out[p] = L.h_small[1 + p];
     mx = n_out[p] > mx ? n_out[p] : mx;
   }
-  if (mx > 0) {
+  if (mx > 0 && speculative) {
+    for (int p = 0; p < P; p++)
+      memcpy(out + (size_t)p * out_cap, (const char*)L.h_out + sizeof(slamb200_dmatch) * (size_t)L.b_cap * p,
+             sizeof(slamb200_dmatch) * (size_t)n_out[p]);
+  } else if (mx > 0) {
     const size_t row = sizeof(slamb200_dmatch) * (size_t)mx;
-    if (L.h_out_cap < row * P) {
-      if (L.h_out) CU(cudaFreeHost(L.h_out));
-      L.h_out = nullptr;
-      L.h_out_cap = 0;
-      CU(cudaMallocHost(&L.h_out, row * P * 2));
-      L.h_out_cap = row * P * 2;
-    }
+    int rc = ensure_h_out(row * P);
+    if (rc) return rc;
     CU(cudaMemcpy2DAsync(L.h_out, row, L.out.p, sizeof(slamb200_dmatch) * (size_t)L.b_cap, row, P,
                          cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));

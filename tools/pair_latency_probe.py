@@ -33,6 +33,7 @@ for _ in range(200): ctx.matchBatchEnqueue(Q, Ts[:1], MatcherType.SIFT_BF, 0.7, 
 p = ctx.profile_read()
 print({k: (round(v[0] / max(v[1], 1) * 1e3, 2), v[1]) for k, v in p.items() if v[1]})
 # the synchronous drop-in call (slamb200_match_pair: enqueue + D2H of the matches + sync)
+for _ in range(100): ctx.matchFeatures(Q, Ts[0], MatcherType.SIFT_BF, 0.7)   # every lane warmed (pinned result buffers)
 t0 = time.perf_counter()
 for _ in range(200): ctx.matchFeatures(Q, Ts[0], MatcherType.SIFT_BF, 0.7)
 print(f"match_pair host call: {(time.perf_counter() - t0) / 200 * 1e6:.1f} us")
@@ -45,3 +46,25 @@ for nt in (2, 4, 8):
     [t.start() for t in th]; [t.join() for t in th]
     dt = time.perf_counter() - t0
     print(f"match_pair from {nt} host threads: {dt / (200 * nt) * 1e6:.1f} us/pair aggregate")
+# the C++ drop-in unit (featureMatchingB200.cpp::matchFeatures: upload both Mats, match, fetch)
+import ctypes
+from slam_indoor_code_b200 import build as _b
+hs = ctypes.CDLL(os.path.join(_b.LIBDIR, "libslamb200_hostshim.so"))
+hs.hostshim_match_features.restype = ctypes.c_int
+hs.hostshim_match_features.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+from slam_indoor_code_b200._capi import DMATCH
+tr = [synth.sift_train_from_query(q, 10000, 3001 + i) for i in range(8)]
+def cpp_worker(k, n, pinned=False):
+    out = np.zeros(10000, DMATCH)
+    for _ in range(n):
+        r = hs.hostshim_match_features(q.ctypes.data, 10000, 512, tr[k].ctypes.data, 10000, 512, 0, out.ctypes.data, 10000)
+        assert r > 0
+cpp_worker(0, 5)
+t0 = time.perf_counter(); cpp_worker(0, 100); dt = time.perf_counter() - t0
+print(f"C++ matchFeatures (pageable Mats, 2 uploads + match): {dt / 100 * 1e6:.1f} us/pair, 1 thread")
+for nt in (3, 6):
+    th = [threading.Thread(target=cpp_worker, args=(k, 100)) for k in range(nt)]
+    t0 = time.perf_counter(); [t.start() for t in th]; [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    print(f"C++ matchFeatures from {nt} host threads: {dt / (100 * nt) * 1e6:.1f} us/pair aggregate")
