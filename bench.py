@@ -12,8 +12,11 @@ scaling, no data-path collective); NCCL only gathers the per-pair match counts a
 region.
 
   value  = pairs/s with every descriptor set already resident in HBM, CUDA-event timed.
-  e2e    = pairs/s through the C ABI with HOST buffers: every step uploads the query and the 210
-           train descriptor Mats from pinned host memory, matches, and copies the match lists back.
+  e2e    = pairs/s through the C ABI with HOST buffers: every step hands the query and the 210
+           train descriptor Mats (CV_32F, host memory) to the library, matches, and copies the match
+           lists back.  Default upload = slamb200_upload_desc_packed: host threads narrow the
+           integer-valued rows to bytes (every element verified) so that 1/4 of the bytes cross
+           PCIe; --e2e-upload pinned sends the fp32 Mats as they are (PCIe-bound, ~9.3k pairs/s).
   roofline = the tcgen05 candidate kernel: 2*Q*T*128 FLOP per pair / its CUDA-event duration,
            against the measured cuBLAS bf16 peak in MEASURED_PEAKS.json.
   cpu_baseline = the same OpenCV calls the reference makes (cv2.BFMatcher.knnMatch + the
@@ -350,14 +353,13 @@ def run_b200(args, rank, world, local):
         t.free()
     Q.free()
     e2e_steps = max(0, min(args.steps, args.e2e_steps))
-    h2d = (len(trains) + 1) * N_ROWS * 512
+    # bytes that cross PCIe per step: the fp32 Mats as they are, or their verified byte images
+    h2d = (len(trains) + 1) * N_ROWS * (128 if args.e2e_upload == "packed" else 512)
+    host_mat_bytes = (len(trains) + 1) * N_ROWS * 512
     d2h = 0
 
     # The reference walks the window from `threadsCount` host threads that share the query
-    # descriptor (batch.cpp:181-201); the C ABI is re-entrant the same way.  Each host thread
-    # takes every n-th chunk of the window: upload the chunk's train Mats (page-locked host
-    # memory, read by the prep kernel straight over PCIe), match the chunk, copy its match lists
-    # back -- with the next chunk's uploads already in flight.
+    # descriptor (batch.cpp:181-201); the C ABI is re-entrant the same way.
     from concurrent.futures import ThreadPoolExecutor
     from slam_indoor_code_b200._capi import DMATCH
     n_workers, chunk = args.e2e_workers, args.e2e_chunk
@@ -366,31 +368,73 @@ def run_b200(args, rank, world, local):
     n_buf = np.zeros(max(len(trains), 1), np.int32)
     pool = ThreadPoolExecutor(n_workers)
 
-    def e2e_upload(ids):
-        return [ctx.upload_pinned(trains[i]) for i in ids]
+    up = ctx.upload_packed if args.e2e_upload == "packed" else ctx.upload_pinned
+    pack_threads = 0
+    if args.e2e_upload == "packed":
+        pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else \
+            max(0, min(os.cpu_count() or 1, 16) - args.e2e_workers)
+        ctx.set_pack_threads(pack_threads)
 
-    def e2e_worker(Qe, my_chunks):
-        """One host thread: its chunks in order, the uploads of chunk k+1 enqueued (they are
-        asynchronous) before chunk k is matched and fetched, so the PCIe link never waits for a
-        thread that is busy matching."""
-        out = []
-        nxt = e2e_upload(my_chunks[0]) if my_chunks else None
-        for k, ids in enumerate(my_chunks):
-            Te = nxt
-            nxt = e2e_upload(my_chunks[k + 1]) if k + 1 < len(my_chunks) else None
-            r = ctx.matchBatch(Qe, Te, MatcherType.SIFT_BF, RATIO, out=out_buf[ids[0]: ids[-1] + 1],
-                               n_out=n_buf[ids[0]: ids[-1] + 1])
-            for t in Te:
-                t.free()
-            out.append((ids[0], r))
-        return out
+    # Producer / consumer pipeline over the public API: `n_workers` uploader threads hand the train
+    # Mats to the library in window order (each call narrows / queues one Mat), `n_match` matcher
+    # threads take every chunk as soon as its last Mat is in, match it against the shared query set,
+    # copy its match lists back and free its sets.  Uploads never wait for a match and vice versa.
+    import itertools
+    n_match = max(1, args.e2e_matchers)
+    pool_m = ThreadPoolExecutor(n_match)
 
     def e2e_step():
         nonlocal d2h
-        Qe = ctx.upload_pinned(q)
+        Qe = up(q)
+        n = len(trains)
+        handles = [None] * n
+        left = [len(c) for c in chunks]
+        ready = [threading.Event() for _ in chunks]
+        lock = threading.Lock()
+        counter = itertools.count()
+        errors = []
+
+        def uploader():
+            try:
+                while True:
+                    i = next(counter)        # itertools.count is atomic under the GIL
+                    if i >= n:
+                        return
+                    handles[i] = up(trains[i])
+                    c = i // chunk
+                    with lock:
+                        left[c] -= 1
+                        last = left[c] == 0
+                    if last:
+                        ready[c].set()
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+                for ev in ready:
+                    ev.set()
+
+        def matcher(m):
+            out = []
+            for c in range(m, len(chunks), n_match):
+                ready[c].wait()
+                if errors:
+                    return out
+                ids = chunks[c]
+                Te = [handles[i] for i in ids]
+                r = ctx.matchBatch(Qe, Te, MatcherType.SIFT_BF, RATIO, out=out_buf[ids[0]: ids[-1] + 1],
+                                   n_out=n_buf[ids[0]: ids[-1] + 1])
+                for t in Te:
+                    t.free()
+                out.append((ids[0], r))
+            return out
+
+        ups = [pool.submit(uploader) for _ in range(n_workers)]
         parts = []
-        for part in pool.map(lambda w: e2e_worker(Qe, chunks[w::n_workers]), range(n_workers)):
+        for part in pool_m.map(matcher, range(n_match)):
             parts.extend(part)
+        for u in ups:
+            u.result()
+        if errors:
+            raise errors[0]
         Qe.free()
         res = []
         for _, r in sorted(parts, key=lambda x: x[0]):
@@ -427,6 +471,9 @@ def run_b200(args, rank, world, local):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(io[0].item()),
                     "d2h_bytes_per_step": int(io[1].item()), "steps": e2e_steps,
+                    "upload": args.e2e_upload, "host_mat_bytes_per_step": host_mat_bytes * world,
+                    "host_threads": {"uploaders": args.e2e_workers, "matchers": args.e2e_matchers,
+                                     "pack_pool": pack_threads},
                     "timing": "host wall clock between device synchronisations, max over ranks",
                     "results_equal_device_resident_run": bool(same)},
             "gpu_launches": int(launches.item()),
@@ -532,6 +579,29 @@ def extras(ctx, stream):
     out["cfg5_ransac_2048x5000"] = {"kernel_us_per_pair": kms / kn / P * 1e3,
                                     "fp64_tflops_40flop_convention": P * 2048 * 5000 * 40 / (kms / kn) / 1e9,
                                     "dp_instr_per_s_T": P * 2048 * 5000 * 36 / (kms / kn) / 1e9}
+    # cfg3's full chain on 32 pairs: match the batch, gather the matched keypoints on the device
+    # (getKeyPointCoordsFromFramePair) and score 2048 essential hypotheses per pair against that pair's
+    # accepted matches (~3000 per pair) -- enqueue only, nothing leaves the device in between
+    qc = synth.sift_like(N_ROWS, 3000)
+    Qc = ctx.upload(qc)
+    Tc = [ctx.upload(synth.sift_train_from_query(qc, N_ROWS, 3001 + i)) for i in range(32)]
+    rng = np.random.default_rng(3100)
+    KQ = ctx.upload_keypoints(rng.uniform(0, 3840, (N_ROWS, 2)).astype(np.float32))
+    KT = ctx.upload_keypoints(rng.uniform(0, 3840, (N_ROWS, 2)).astype(np.float32))
+    Ed = torch.from_numpy(np.stack([E] * 32)).to("cuda")
+
+    def chain():
+        ctx.matchBatchEnqueue(Qc, Tc, MatcherType.SIFT_BF, RATIO, stream)
+        ct.scoreBatchEnqueue(ctx, KQ, [KT] * 32, synth.SAMSUNG_HV_4K, None, 5.0, stream,
+                             E_device_ptr=Ed.data_ptr(), H=2048)
+    ms_match = ev_time(lambda: ctx.matchBatchEnqueue(Qc, Tc, MatcherType.SIFT_BF, RATIO, stream), 10)
+    ms_chain = ev_time(chain, 10)
+    out["cfg3_chain_32_pairs"] = {"match_us_per_pair": ms_match / 32 * 1e3,
+                                  "match_gather_score_us_per_pair": ms_chain / 32 * 1e3,
+                                  "hypotheses_per_pair": 2048,
+                                  "note": "random keypoint coordinates: the timing is real, the inlier counts are not meaningful"}
+    for h in Tc + [Qc, KQ, KT]:
+        h.free()
     # next row 8f-2: solvePnPRansac scoring, 2048 poses x 5000 correspondences, 32 frames per launch,
     # the reference's five distortion coefficients
     from slam_indoor_code_b200 import pnp_ransac as pr
@@ -657,8 +727,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-workers", type=int, default=3, help="host threads of the e2e pipeline")
+    ap.add_argument("--e2e-workers", type=int, default=4, help="uploader threads of the e2e pipeline")
+    ap.add_argument("--e2e-matchers", type=int, default=2, help="matcher threads of the e2e pipeline")
     ap.add_argument("--e2e-chunk", type=int, default=14, help="train frames per e2e chunk")
+    ap.add_argument("--e2e-pack-threads", type=int, default=-1,
+                    help="library threads sharing the narrowing of each Mat (-1: min(cores, 16) - uploaders)")
+    ap.add_argument("--e2e-upload", default="packed", choices=["packed", "pinned"],
+                    help="packed: rows narrowed to bytes on the host threads (verified lossless) before "
+                         "PCIe; pinned: the fp32 Mats read over PCIe as they are")
     ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the CPU arm")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -96,6 +96,18 @@ int slamb200_upload_desc_device(slamb200_ctx* ctx, int kind, const void* rows, i
  * until a matching call that uses the set has returned its results. */
 int slamb200_upload_desc_pinned(slamb200_ctx* ctx, int kind, const void* rows, int n,
                                 size_t row_stride, slamb200_desc** out);
+/* Upload that narrows on the host first: cv::SIFT's CV_32F rows are integers in [0,255], so the
+ * calling thread packs them to bytes into page-locked staging -- checking every element and every
+ * row norm -- and the GPU reads a quarter of the bytes over PCIe.  `rows` (pageable or pinned) is
+ * fully consumed when the call returns; the device work is only queued.  A Mat that is not
+ * integer valued, and every ORB Mat, takes slamb200_upload_desc's path.  Results are identical
+ * to slamb200_upload_desc in every case. */
+int slamb200_upload_desc_packed(slamb200_ctx* ctx, int kind, const void* rows, int n,
+                                size_t row_stride, slamb200_desc** out);
+/* Host threads that share the narrowing of one Mat in slamb200_upload_desc_packed (row slices; the
+ * caller's thread takes one slice too).  Default min(hardware threads, 16); 0 = callers only.  Must
+ * be called before the first packed upload. */
+int slamb200_set_pack_threads(slamb200_ctx* ctx, int n);
 int slamb200_free_desc(slamb200_ctx* ctx, slamb200_desc* d);
 int slamb200_desc_rows(const slamb200_desc* d);
 int slamb200_desc_kind(const slamb200_desc* d);

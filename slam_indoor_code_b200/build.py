@@ -25,7 +25,7 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unus
 
 
 def sources():
-    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    return sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
 
 
 def _stale(target, deps):
@@ -36,10 +36,16 @@ def _stale(target, deps):
 
 
 def _compile(src, verbose):
-    obj = os.path.join(OBJDIR, src[:-3] + ".o")
+    obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
     headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "slamb200.h"))
-    if _stale(obj, [os.path.join(CSRC, src)] + headers):
+    if src.endswith(".cpp") and _stale(obj, [os.path.join(CSRC, src)] + headers):
+        # host-only units (SIMD intrinsics): the host compiler directly
+        cmd = ["/usr/bin/g++", "-O3", "-std=c++17", "-fPIC", "-Wall", "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed on {src}:\n{r.stdout}\n{r.stderr}")
+    elif _stale(obj, [os.path.join(CSRC, src)] + headers):
         cmd = [NVCC] + ARCH + CFLAGS + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)

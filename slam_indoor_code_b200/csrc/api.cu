@@ -7,9 +7,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
+#include <atomic>
 #include <condition_variable>
+#include <deque>
+#include <functional>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -96,9 +101,75 @@ struct slamb200_ctx {
   // Descriptor-set slabs are recycled: a freed slab waits here with the event that marks the end
   // of all work that could still read it; the next upload of the same size makes its stream wait
   // on that event (on the device) and reuses the memory -- no allocator call in steady state.
-  struct CachedSlab { void* p; size_t bytes; cudaEvent_t ev; };
+  // Frees are batched: a freed slab first waits in `slab_pending` at no CUDA cost; a flush orders
+  // the whole batch behind every lane's work with one event (shared, reference counted).
+  struct SharedEv { cudaEvent_t ev; int refs; };
+  struct CachedSlab { void* p; size_t bytes; SharedEv* ev; };
   std::vector<CachedSlab> slab_cache;
+  std::vector<CachedSlab> slab_pending;
   size_t slab_cache_bytes = 0;
+  std::vector<cudaEvent_t> event_pool;  // recycled cudaEventDisableTiming events (under free_mu)
+  // Page-locked staging for slamb200_upload_desc_packed: a buffer is reusable once the event that
+  // follows its prep kernel has completed.
+  struct PinBuf { void* p; size_t cap; cudaEvent_t ev; bool busy; };
+  std::vector<PinBuf*> pin_pool;
+  std::mutex pin_mu;
+  // Host threads that share the narrowing of one Mat (row slices), so that a few caller threads
+  // can still use every core of the box; started on first use, size via slamb200_set_pack_threads.
+  struct PackPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    bool stop = false;
+    std::atomic<int> queued{0}, sleepers{0};
+    void start(int n) {
+      for (int i = 0; i < n; i++)
+        th.emplace_back([this] {
+          for (;;) {
+            std::function<void()> f;
+            // a slice takes ~60 us and slices arrive in bursts: poll for a while before sleeping
+            // (a futex wake-up costs about as much as the slice itself)
+            const auto t_idle = std::chrono::steady_clock::now();
+            while (queued.load(std::memory_order_acquire) == 0 && !stop &&
+                   std::chrono::steady_clock::now() - t_idle < std::chrono::microseconds(300))
+              __builtin_ia32_pause();
+            {
+              std::unique_lock<std::mutex> lk(mu);
+              if (q.empty()) {
+                sleepers++;
+                cv.wait(lk, [this] { return stop || !q.empty(); });
+                sleepers--;
+              }
+              if (stop && q.empty()) return;
+              f = std::move(q.front());
+              q.pop_front();
+              queued--;
+            }
+            f();
+          }
+        });
+    }
+    void submit(std::function<void()> f) {
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        q.push_back(std::move(f));
+        queued++;
+      }
+      if (sleepers.load() > 0) cv.notify_one();
+    }
+    void shutdown() {
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+      }
+      cv.notify_all();
+      for (auto& t : th) t.join();
+      th.clear();
+    }
+  } pack_pool;
+  std::once_flag pack_once;
+  int pack_threads = -1;  // -1: min(hardware threads, 16)
   int sub_batch = 0;  // debug: pairs per tcgen05 launch when pipelining against the rerank
   int use_tc = 1;  // debug switch (slamb200_dbg_set_tc): 0 routes exact-mode pairs to the fp32 kernel
 };
@@ -251,9 +322,20 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
     cudaStreamDestroy(L.stream2);
     cudaStreamDestroy(L.stream);
   }
+  for (auto& e : c->slab_pending) cudaFree(e.p);
   for (auto& e : c->slab_cache) {
     cudaFree(e.p);
-    cudaEventDestroy(e.ev);
+    if (--e.ev->refs == 0) {
+      cudaEventDestroy(e.ev->ev);
+      delete e.ev;
+    }
+  }
+  for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+  c->pack_pool.shutdown();
+  for (auto* b : c->pin_pool) {
+    cudaFreeHost(b->p);
+    cudaEventDestroy(b->ev);
+    delete b;
   }
   if (c->free_stream) cudaStreamDestroy(c->free_stream);
   if (c->pool) cudaMemPoolDestroy(c->pool);
@@ -307,11 +389,50 @@ extern "C" int slamb200_profile_read(slamb200_ctx* c, double* ms, int64_t* launc
 
 // ---- descriptor sets ------------------------------------------------------------------------
 static void* slab_from_cache(slamb200_ctx* c, size_t bytes, cudaStream_t s);
+static cudaEvent_t event_get(slamb200_ctx* c);
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- page-locked staging pool -----------------------------------------------------------------
+#define PIN_POOL_MAX 48
+static slamb200_ctx::PinBuf* pin_acquire(slamb200_ctx* c, size_t bytes) {
+  for (int spin = 0;; spin++) {
+    {
+      std::lock_guard<std::mutex> lk(c->pin_mu);
+      for (auto* b : c->pin_pool)
+        if (!b->busy && b->cap >= bytes && cudaEventQuery(b->ev) == cudaSuccess) {
+          b->busy = true;
+          return b;
+        }
+      cudaGetLastError();  // cudaErrorNotReady from the queries above
+      if ((int)c->pin_pool.size() < PIN_POOL_MAX) {
+        auto* b = new slamb200_ctx::PinBuf{nullptr, 0, nullptr, true};
+        const size_t cap = (bytes + ((size_t)1 << 21) - 1) >> 21 << 21;  // 2 MiB granules
+        if (cudaMallocHost(&b->p, cap) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b->ev, cudaEventDisableTiming) != cudaSuccess) {
+          if (b->p) cudaFreeHost(b->p);
+          delete b;
+          cudaGetLastError();
+          return nullptr;
+        }
+        b->cap = cap;
+        c->pin_pool.push_back(b);
+        return b;
+      }
+    }
+    // every buffer is in flight: the GPU drains them in tens of microseconds
+    std::this_thread::sleep_for(std::chrono::microseconds(20));
+    if (spin > 500000) return nullptr;
+  }
+}
+static void pin_release(slamb200_ctx* c, slamb200_ctx::PinBuf* b, cudaStream_t after) {
+  if (after) cudaEventRecord(b->ev, after);
+  std::lock_guard<std::mutex> lk(c->pin_mu);
+  b->busy = false;
+}
 
 static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_t row_stride,
                        bool src_on_device, cudaStream_t producer, bool no_sync,
-                       slamb200_desc** out) {
+                       slamb200_desc** out, slamb200_ctx::PinBuf* packed = nullptr) {
   if (!c || !out) return fail(SLAMB200_ERR_INVALID, "upload_desc: NULL argument");
   *out = nullptr;
   if (kind != SLAMB200_DESC_F32X128 && kind != SLAMB200_DESC_U8X32)
@@ -348,7 +469,11 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
     DCU(cudaEventRecord(ev, producer));
     DCU(cudaStreamWaitEvent(s, ev, 0));
   }
-  DCU(cudaEventCreateWithFlags(&d->ready, cudaEventDisableTiming));
+  {
+    std::lock_guard<std::mutex> lk(c->free_mu);
+    d->ready = event_get(c);
+  }
+  if (!d->ready) { rc = fail(SLAMB200_ERR_CUDA, "cudaEventCreate failed"); goto done; }
   if (kind == SLAMB200_DESC_U8X32) {
     d->slab_bytes = (size_t)d->n_pad * 32;
     if (!(d->slab = slab_from_cache(c, d->slab_bytes, s)))
@@ -383,7 +508,13 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
     DCU(cudaMemsetAsync(d->flags, 0, 16, s));
     const float* prep_src = d->f32;
     size_t prep_stride = 128;
-    if (n > 0) {
+    if (packed) {
+      // rows already narrowed to bytes in page-locked staging (verified exact on the host)
+      launch_sift_prep_u8((const uint8_t*)packed->p, n, d->n_pad, d->f32, d->bf16, d->augq, d->augt,
+                          d->u8, d->nrm2, d->bf16lo, d->nrmf, d->flags, s);
+      d->host_exact = 1;
+      d->ready_seen = 0;
+    } else if (n > 0) {
       // Page-locked, device-mapped host rows (the pipelined upload): the prep kernel reads them
       // straight over PCIe -- no staging copy, no per-copy setup cost, one pass over the data.
       const void* mapped = nullptr;
@@ -404,8 +535,9 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
         else DCU(cudaMemcpy2DAsync(d->f32, 512, rows, row_stride, 512, n, k, s));
       }
     }
-    launch_sift_prep(prep_src, prep_stride, n, d->n_pad, d->f32, d->bf16, d->augq, d->augt, d->u8,
-                     d->nrm2, d->bf16lo, d->nrmf, d->flags, s);
+    if (!packed)
+      launch_sift_prep(prep_src, prep_stride, n, d->n_pad, d->f32, d->bf16, d->augq, d->augt, d->u8,
+                       d->nrm2, d->bf16lo, d->nrmf, d->flags, s);
     DCU(cudaGetLastError());
     if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->bf16lo, d->n_pad, d->tmaps) != 0) {
       rc = fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
@@ -414,6 +546,7 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   }
   DCU(cudaEventRecord(d->ready, s));
   DCU(cudaEventRecord(L.done, s));
+  if (packed) DCU(cudaEventRecord(packed->ev, s));
   if (!src_on_device && !no_sync) {
     // the caller may reuse `rows` on return; the same synchronisation brings the exact-mode flag back
     if (d->flags) DCU(cudaMemcpyAsync(L.h_small, d->flags, 4, cudaMemcpyDeviceToHost, s));
@@ -442,43 +575,154 @@ extern "C" int slamb200_upload_desc_pinned(slamb200_ctx* c, int kind, const void
   return desc_create(c, kind, rows, n, row_stride, false, nullptr, true, out);
 }
 
+// The caller's rows are consumed before the call returns (narrowed into page-locked staging on the
+// calling thread), the GPU work is only enqueued.
+extern "C" int slamb200_upload_desc_packed(slamb200_ctx* c, int kind, const void* rows, int n,
+                                           size_t row_stride, slamb200_desc** out) {
+  if (!c || !out) return fail(SLAMB200_ERR_INVALID, "upload_desc: NULL argument");
+  if (kind != SLAMB200_DESC_F32X128 || n <= 0 || !rows)
+    return desc_create(c, kind, rows, n, row_stride, false, nullptr, false, out);
+  if (row_stride == 0) row_stride = 512;
+  if (row_stride < 512 || (row_stride % 4))
+    return fail(SLAMB200_ERR_INVALID, "upload_desc: row_stride %zu unsupported", row_stride);
+  CU(cudaSetDevice(c->device));
+  slamb200_ctx::PinBuf* b = pin_acquire(c, (size_t)n * 128);
+  if (!b) return desc_create(c, kind, rows, n, row_stride, false, nullptr, false, out);
+  // narrow + verify: row slices on the pack pool, the last slice on the calling thread
+  std::call_once(c->pack_once, [c] {
+    int nthr = c->pack_threads;
+    if (nthr < 0) {
+      nthr = (int)std::thread::hardware_concurrency();
+      nthr = nthr > 16 ? 16 : nthr;
+    }
+    c->pack_pool.start(nthr > 0 ? nthr : 0);
+  });
+  int exact = 1;
+  {
+    const int pool = (int)c->pack_pool.th.size();
+    int slices = n / 1024;                       // at least ~1k rows (0.5 MB) per slice
+    slices = slices > 8 ? 8 : slices;
+    slices = slices > pool + 1 ? pool + 1 : slices;
+    if (slices <= 1) {
+      exact = slamb200_host_pack_u8((const float*)rows, row_stride / 4, n, (uint8_t*)b->p);
+    } else {
+      std::atomic<int> pending(slices - 1), all_ok(1);
+      std::mutex mu;
+      std::condition_variable cv;
+      const int per = (n + slices - 1) / slices;
+      auto run = [&](int k) {
+        const int r0 = k * per, r1 = r0 + per < n ? r0 + per : n;
+        if (r1 > r0 && !slamb200_host_pack_u8((const float*)((const char*)rows + (size_t)r0 * row_stride),
+                                              row_stride / 4, r1 - r0, (uint8_t*)b->p + (size_t)r0 * 128))
+          all_ok.store(0);
+      };
+      for (int k = 0; k < slices - 1; k++)
+        c->pack_pool.submit([&, k] {
+          run(k);
+          if (pending.fetch_sub(1) == 1) {
+            std::lock_guard<std::mutex> lk(mu);
+            cv.notify_one();
+          }
+        });
+      run(slices - 1);
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return pending.load() == 0; });
+      exact = all_ok.load();
+    }
+  }
+  if (!exact) {
+    pin_release(c, b, nullptr);  // not integer valued: the fp32 path
+    return desc_create(c, kind, rows, n, row_stride, false, nullptr, false, out);
+  }
+  const int rc = desc_create(c, kind, rows, n, row_stride, false, nullptr, true, out, b);
+  if (rc != SLAMB200_OK) cudaDeviceSynchronize();  // a prep kernel may still be reading the staging
+  pin_release(c, b, nullptr);  // desc_create recorded b->ev behind the prep kernel
+  return rc;
+}
+
+extern "C" int slamb200_set_pack_threads(slamb200_ctx* c, int n) {
+  if (!c || n < 0 || n > 256) return fail(SLAMB200_ERR_INVALID, "set_pack_threads: bad argument");
+  if (!c->pack_pool.th.empty()) return fail(SLAMB200_ERR_INVALID, "set_pack_threads: the pool is already running");
+  c->pack_threads = n;
+  return SLAMB200_OK;
+}
+
 extern "C" int slamb200_upload_desc_device(slamb200_ctx* c, int kind, const void* rows, int n,
                                            size_t row_stride, void* stream, slamb200_desc** out) {
   return desc_create(c, kind, rows, n, row_stride, true, (cudaStream_t)stream, false, out);
 }
 
-// Orders a free behind everything the context has queued so far without blocking the host: the
-// free stream waits (on the device) for every lane's latest work, then releases the memory.
-static void free_behind_lanes(slamb200_ctx* c, void* p, cudaEvent_t ready, size_t cache_bytes = 0) {
-  std::lock_guard<std::mutex> lk(c->free_mu);
-  if (ready) cudaStreamWaitEvent(c->free_stream, ready, 0);
-  for (int i = 0; i < N_LANES; i++) cudaStreamWaitEvent(c->free_stream, c->lanes[i].done, 0);
-  const size_t kCacheLimit = (size_t)8 << 30;
-  if (cache_bytes > 0 && c->slab_cache_bytes + cache_bytes <= kCacheLimit) {
-    cudaEvent_t ev = nullptr;
-    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess &&
-        cudaEventRecord(ev, c->free_stream) == cudaSuccess) {
-      c->slab_cache.push_back({p, cache_bytes, ev});
-      c->slab_cache_bytes += cache_bytes;
-      return;
-    }
-    if (ev) cudaEventDestroy(ev);
+static cudaEvent_t event_get(slamb200_ctx* c) {  // free_mu held
+  if (!c->event_pool.empty()) {
+    cudaEvent_t e = c->event_pool.back();
+    c->event_pool.pop_back();
+    return e;
   }
-  cudaFreeAsync(p, c->free_stream);
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return e;
+}
+static void event_put(slamb200_ctx* c, cudaEvent_t e) {  // free_mu held
+  if (!e) return;
+  if (c->event_pool.size() < 1024) c->event_pool.push_back(e);
+  else cudaEventDestroy(e);
+}
+
+// Orders the pending frees behind everything the context has queued so far without blocking the
+// host: the free stream waits (on the device) for every lane's latest work -- a descriptor set's
+// own prep kernel included, its lane's `done` event was recorded behind it -- then one event marks
+// the whole batch reusable.  free_mu held.
+#define SLAB_PENDING_MAX 16
+static void flush_pending(slamb200_ctx* c) {
+  if (c->slab_pending.empty()) return;
+  for (int i = 0; i < N_LANES; i++) cudaStreamWaitEvent(c->free_stream, c->lanes[i].done, 0);
+  auto* sev = new slamb200_ctx::SharedEv{event_get(c), 0};
+  const bool ok = sev->ev && cudaEventRecord(sev->ev, c->free_stream) == cudaSuccess;
+  const size_t kCacheLimit = (size_t)8 << 30;
+  for (auto& e : c->slab_pending) {
+    if (ok && e.bytes > 0 && c->slab_cache_bytes + e.bytes <= kCacheLimit) {
+      sev->refs++;
+      c->slab_cache.push_back({e.p, e.bytes, sev});
+      c->slab_cache_bytes += e.bytes;
+    } else {
+      cudaFreeAsync(e.p, c->free_stream);
+    }
+  }
+  c->slab_pending.clear();
+  if (sev->refs == 0) {
+    event_put(c, sev->ev);
+    delete sev;
+  }
+}
+
+static void free_behind_lanes(slamb200_ctx* c, void* p, size_t cache_bytes) {
+  std::lock_guard<std::mutex> lk(c->free_mu);
+  c->slab_pending.push_back({p, cache_bytes, nullptr});
+  if (c->slab_pending.size() >= SLAB_PENDING_MAX) flush_pending(c);
 }
 
 // A recycled slab of exactly `bytes`, ordered behind its previous users on stream s; or nullptr.
 static void* slab_from_cache(slamb200_ctx* c, size_t bytes, cudaStream_t s) {
   std::lock_guard<std::mutex> lk(c->free_mu);
-  for (size_t i = c->slab_cache.size(); i-- > 0;) {
-    if (c->slab_cache[i].bytes == bytes) {
-      slamb200_ctx::CachedSlab e = c->slab_cache[i];
-      c->slab_cache.erase(c->slab_cache.begin() + (long)i);
-      c->slab_cache_bytes -= bytes;
-      cudaStreamWaitEvent(s, e.ev, 0);
-      cudaEventDestroy(e.ev);
-      return e.p;
+  for (int pass = 0; pass < 2; pass++) {
+    for (size_t i = c->slab_cache.size(); i-- > 0;) {
+      if (c->slab_cache[i].bytes == bytes) {
+        slamb200_ctx::CachedSlab e = c->slab_cache[i];
+        c->slab_cache.erase(c->slab_cache.begin() + (long)i);
+        c->slab_cache_bytes -= bytes;
+        cudaStreamWaitEvent(s, e.ev->ev, 0);
+        if (--e.ev->refs == 0) {
+          event_put(c, e.ev->ev);
+          delete e.ev;
+        }
+        return e.p;
+      }
     }
+    // nothing ready: a slab of this size may be waiting in the pending batch
+    bool have = false;
+    for (auto& e : c->slab_pending) have = have || e.bytes == bytes;
+    if (!have) break;
+    flush_pending(c);
   }
   return nullptr;
 }
@@ -490,8 +734,11 @@ extern "C" int slamb200_free_desc(slamb200_ctx* c, slamb200_desc* d) {
   // Work this context queued that may still read the set drains first (stream-ordered, the host
   // does not wait).  Work the caller queued on its own streams through the *_enqueue entry
   // points must have been recorded by them (it is: every enqueue records the lane's event).
-  if (d->slab) free_behind_lanes(c, d->slab, d->ready, d->slab_bytes);
-  if (d->ready) cudaEventDestroy(d->ready);
+  if (d->slab) free_behind_lanes(c, d->slab, d->slab_bytes);
+  if (d->ready) {
+    std::lock_guard<std::mutex> lk(c->free_mu);
+    event_put(c, d->ready);
+  }
   free(d);
   return SLAMB200_OK;
 }
@@ -1208,7 +1455,7 @@ extern "C" int slamb200_free_pts(slamb200_ctx* c, slamb200_pts* p) {
   if (!p) return SLAMB200_OK;
   if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
   cudaSetDevice(c->device);
-  if (p->xy) free_behind_lanes(c, p->xy, p->ready);
+  if (p->xy) free_behind_lanes(c, p->xy, 0);  // the upload was synchronised: only readers remain
   if (p->ready) cudaEventDestroy(p->ready);
   free(p);
   return SLAMB200_OK;

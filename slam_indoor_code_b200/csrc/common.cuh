@@ -130,6 +130,11 @@ void launch_sift_prep(const float* src, size_t src_stride_floats, int n, int n_p
                       __nv_bfloat16* bf16, __nv_bfloat16* augq, __nv_bfloat16* augt, uint8_t* u8,
                       int32_t* nrm2, __nv_bfloat16* bf16lo, float* nrmf, int32_t* flags,
                       cudaStream_t s);
+void launch_sift_prep_u8(const uint8_t* src_u8, int n, int n_pad, float* f32, __nv_bfloat16* bf16,
+                         __nv_bfloat16* augq, __nv_bfloat16* augt, uint8_t* u8, int32_t* nrm2,
+                         __nv_bfloat16* bf16lo, float* nrmf, int32_t* flags, cudaStream_t s);
+// host_pack.cpp: lossless fp32 -> u8 narrowing with full verification (1 = exact-mode rows).
+extern "C" int slamb200_host_pack_u8(const float* src, size_t stride_floats, int n, uint8_t* dst);
 
 // SIFT tcgen05 candidate kernel + dp4a rerank (sift_tc.cu).
 struct alignas(64) TcPair {

@@ -114,7 +114,8 @@ class Context:
             desc = np.ascontiguousarray(desc)
         stride = desc.strides[0] if desc.shape[0] > 1 else width * desc.itemsize
         h = ctypes.c_void_p()
-        fn = self._lib.slamb200_upload_desc_pinned if _pinned else self._lib.slamb200_upload_desc
+        fn = {False: self._lib.slamb200_upload_desc, True: self._lib.slamb200_upload_desc_pinned,
+              "packed": self._lib.slamb200_upload_desc_packed}[_pinned]
         check(fn(self._h, kind, ptr(desc), desc.shape[0], stride, ctypes.byref(h)))
         return DescriptorSet(self, h, desc.shape[0], kind)
 
@@ -122,6 +123,16 @@ class Context:
         """Pipelined upload from page-locked host memory (no synchronisation; the caller keeps
         `desc` alive and unmodified until synchronize() or until results were fetched)."""
         return self.upload(desc, kind, _pinned=True)
+
+    def set_pack_threads(self, n):
+        """Host threads sharing the narrowing inside upload_packed (before its first use)."""
+        check(self._lib.slamb200_set_pack_threads(self._h, int(n)))
+
+    def upload_packed(self, desc, kind=None):
+        """Upload that narrows integer-valued SIFT rows to bytes on the calling thread (every
+        element verified) so that a quarter of the bytes cross PCIe; `desc` is consumed on return.
+        Anything else takes upload()'s path.  Same results as upload()."""
+        return self.upload(desc, kind, _pinned="packed")
 
     def upload_device(self, dev_ptr, n, kind, row_stride=0, stream=None):
         """Rows already resident on this device (raw pointer, e.g. torch.Tensor.data_ptr())."""

@@ -456,3 +456,72 @@ def test_sift_l1_10k_properties(ctx):
     _check_knn(idx[rows], dist[rows], ridx, rdist)
     good = ctx.matchFeatures(Q, T, MatcherType.SIFT_BF_L1, 0.7)
     assert 2000 < len(good) <= 10000 and np.all(np.diff(good["queryIdx"]) > 0)
+
+
+# ---- host-narrowed upload (slamb200_upload_desc_packed) ------------------------------------------
+def test_packed_upload_equals_plain_upload(ctx):
+    q, t = synth.sift_pair(3000, 4100, 901)
+    ridx, rdist = c_oracle.l2_knn2(q, t)
+    Q, T = ctx.upload_packed(q), ctx.upload_packed(t)
+    assert Q.exact_mode == 1 and T.exact_mode == 1
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, Q, T)
+    _check_knn(idx, dist, ridx, rdist)
+    assert np.array_equal(ctx.matchFeatures(Q, T, MatcherType.SIFT_BF, 0.7), c_oracle.ratio_test(ridx, rdist, 0.7))
+    # mixed with a plainly uploaded set, and in the L1 mode (which reads the u8 and f32 copies)
+    assert np.array_equal(ctx.matchFeatures(ctx.upload(q), T, MatcherType.SIFT_BF, 0.7),
+                          c_oracle.ratio_test(ridx, rdist, 0.7))
+    assert np.array_equal(ctx.matchFeatures(Q, T, MatcherType.SIFT_BF_L1, 0.7), c_oracle.match_features(3, q, t, 0.7))
+    # row pitch (cv::Mat::step) and the caller's buffer being reusable right after the call
+    wide = np.zeros((4100, 160), np.float32)
+    wide[:, :128] = t
+    T2 = ctx.upload_packed(wide[:, :128])
+    wide[:] = 7.0
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, Q, T2)
+    _check_knn(idx, dist, ridx, rdist)
+
+
+def test_packed_upload_falls_back_for_other_data(ctx):
+    # general floats: not packable, same results as the plain path (bit-exact distances)
+    q, t = synth.float_pair(300, 500, 902)
+    Q, T = ctx.upload_packed(q), ctx.upload_packed(t)
+    assert Q.exact_mode == 0
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, Q, T)
+    _check_knn(idx, dist, *c_oracle.l2_knn2(q, t))
+    # a single non-integer element; integers whose norm breaks the exact-mode bound
+    q, t = synth.sift_pair(400, 600, 903)
+    t[77, 5] += 0.25
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, ctx.upload_packed(q), ctx.upload_packed(t))
+    _check_knn(idx, dist, *c_oracle.l2_knn2(q, t))
+    big = np.full((50, 128), 200.0, np.float32)
+    big[:, ::3] = np.arange(50, dtype=np.float32)[:, None]
+    B = ctx.upload_packed(big)
+    assert B.exact_mode == 0
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, ctx.upload_packed(q), B)
+    _check_knn(idx, dist, *c_oracle.l2_knn2(q, big))
+    # ORB and empty sets pass through
+    qo, to = synth.orb_pair(200, 300, 904)
+    idx, dist = ctx.knnMatch(MatcherType.ORB_BF, ctx.upload_packed(qo), ctx.upload_packed(to))
+    _check_knn(idx, dist, *c_oracle.hamming_knn2(qo, to))
+    E = ctx.upload_packed(np.zeros((0, 128), np.float32))
+    assert len(ctx.matchFeatures(ctx.upload_packed(q), E, MatcherType.SIFT_BF)) == 0
+
+
+def test_packed_upload_from_many_threads(ctx):
+    """More concurrent callers than staging buffers in flight at first: the pool grows and recycles."""
+    import threading
+    q = synth.sift_like(2000, 905)
+    trains = [synth.sift_train_from_query(q, 2000 + 10 * i, 906 + i) for i in range(12)]
+    want = [c_oracle.match_features(0, q, t, 0.7) for t in trains]
+    Q = ctx.upload_packed(q)
+    got = [None] * 12
+
+    def work(i):
+        for _ in range(5):
+            T = ctx.upload_packed(trains[i])
+            got[i] = ctx.matchFeatures(Q, T, MatcherType.SIFT_BF, 0.7)
+            T.free()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(12)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)

@@ -70,3 +70,11 @@ elif which == "score":
     for dist in (synth.REF_DIST5, None):
         c, b, m = pr.scorePnPBatch(ctx, [obj] * 16, [img] * 16, synth.SAMSUNG_HV_4K, dist, np.stack([poses] * 16), 8.0)
     print("pnp ok", b[:4])
+elif which == "single":
+    q = synth.sift_like(10000, 3000)
+    Q = ctx.upload(q)
+    T = ctx.upload(synth.sift_train_from_query(q, 10000, 3001))
+    for _ in range(6):
+        ctx.matchBatchEnqueue(Q, [T], MatcherType.SIFT_BF, 0.7, st)
+    torch.cuda.synchronize()
+    print("ok", len(ctx.batchFetch(st)[0][0]))
