@@ -79,7 +79,7 @@ void upload(const Mat& desc, int kind, DescHandle& h) {
   const int cols = kind == SLAMB200_DESC_F32X128 ? 128 : 32;
   if (!desc.empty() && (desc.type() != want || desc.cols != cols))
     throw std::runtime_error("descriptor Mat type/width does not fit the matcher");  // cv::Exception in OpenCV
-  const int rc = slamb200_upload_desc(context(), kind, desc.empty() ? nullptr : desc.data,
+  const int rc = slamb200_upload_desc_packed(context(), kind, desc.empty() ? nullptr : desc.data,
                                       desc.empty() ? 0 : desc.rows, desc.empty() ? 0 : (size_t)desc.step,
                                       &h.d);
   if (rc != SLAMB200_OK) throw std::runtime_error(std::string("slamb200_upload_desc: ") + slamb200_last_error());
