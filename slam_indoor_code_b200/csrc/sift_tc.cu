@@ -171,6 +171,16 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -206,6 +216,10 @@ __device__ __forceinline__ uint64_t desc_interleave(uint32_t addr) {
   d |= (uint64_t)(256 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   return d;
+}
+// kind::i8: u8 x u8 -> s32 (c_format 2), K = 32 per instruction
+__host__ __device__ constexpr uint32_t idesc_u8(int m, int n) {
+  return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_neg) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_neg << 13) | ((uint32_t)(n >> 3) << 17) |
@@ -541,6 +555,15 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
             }
           }
           tc_mma(d_tmem, desc_interleave(a_addr + AUG), desc_interleave(b_addr + AUG), IDESC_POS, 1u);
+        } else if (P.mode >= 4) {
+          // timing probe: the same tile with kind::i8 MMAs (K = 32 bytes each) on whatever bytes the
+          // stage holds; mode 4 issues the 5 a byte-wide kernel would need, mode 5 issues 9
+          const int n_i8 = P.mode == 4 ? 5 : 9;
+          for (int k = 0; k < n_i8; k++) {
+            const uint64_t ad = desc_sw128(a_addr + ((k >> 2) & 1) * KBLK + (k & 3) * 32);
+            const uint64_t bd = desc_sw128(b_addr + ((k >> 2) & 1) * KBLK + (k & 3) * 32);
+            tc_mma_i8(d_tmem, ad, bd, idesc_u8(2 * BM, BN), k > 0 ? 1u : 0u);
+          }
         }
         tc_commit(b_empty + 8 * b_stage);
         tc_commit(t_full + 8 * t_stage);
@@ -582,10 +605,10 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       const int gid_tile = (it.cb * BN + half * COLS_PER_WARP) / GROUP;
       const bool dump = DBG && first_tile && pair_id == 0;
       uint32_t va[32], vb[32];  // (timing modes >= 2 read them uninitialised: results are void there)
-      if (P.mode < 2) TMEM_LD32(t_addr, va);
+      if (P.mode < 2 || P.mode >= 6) TMEM_LD32(t_addr, va);
 #pragma unroll
       for (int c = 0; c < CHUNKS; c += 2) {
-        if (P.mode < 2) {
+        if (P.mode < 2 || P.mode >= 6) {
           TMEM_WAIT32(va);
           TMEM_LD32(t_addr + 32 * (c + 1), vb);
         }
@@ -594,8 +617,8 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
           for (int j = 0; j < 32; j++)
             P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * c + j] = __uint_as_float(va[j]);
         }
-        if (P.mode < 1) process_chunk<GEN>(va, gid_tile + 4 * c, st);
-        if (P.mode < 2) {
+        if (P.mode < 1 || P.mode == 6) process_chunk<GEN>(va, gid_tile + 4 * c, st);
+        if (P.mode < 2 || P.mode >= 6) {
           TMEM_WAIT32(vb);
           if (c + 2 < CHUNKS) TMEM_LD32(t_addr + 32 * (c + 2), va);
         }
@@ -611,7 +634,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
           for (int j = 0; j < 32; j++)
             P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * (c + 1) + j] = __uint_as_float(vb[j]);
         }
-        if (P.mode < 1) process_chunk<GEN>(vb, gid_tile + 4 * (c + 1), st);
+        if (P.mode < 1 || P.mode == 6) process_chunk<GEN>(vb, gid_tile + 4 * (c + 1), st);
       }
       first_tile = false;
       if (++t_stage == 2) { t_stage = 0; t_phase ^= 1; }

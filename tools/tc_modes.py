@@ -12,7 +12,9 @@ Q = ctx.upload(q)
 NP = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 Ts = [ctx.upload(synth.sift_train_from_query(q, 10000, 3001 + i)) for i in range(NP)]
 ctx.profile_enable(True)
-for mode in (0, 1, 2, 3, 0):
+# 0 full | 1 no chunk processing | 2 no TMEM reads (MMA+TMA) | 3 TMA only | 4/5 five/nine kind::i8 MMAs
+# (probe) | 6 epilogue without MMAs | 7 TMEM reads only
+for mode in (0, 1, 2, 3, 4, 5, 6, 7, 0):
     lib.slamb200_dbg_set_tc_mode(mode)
     for _ in range(2): ctx.matchBatchEnqueue(Q, Ts, MatcherType.SIFT_BF, 0.7, st)
     torch.cuda.synchronize(); ctx.profile_read()
