@@ -1,0 +1,62 @@
+"""GPU: the keyframe window sharded over ranks -- NCCL all-gather of the frames'
+descriptor rows, device-to-device descriptor sets, round-robin pairs -- equals the single-process
+slamb200_match_window.  Runs with as many ranks as the box has GPUs (1 on the round-end box: the
+NCCL path, the device uploads and the pair deal are still exercised), capped at 4."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, os.environ["REPO_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from oracle import synth
+from slam_indoor_code_b200 import window_sharding as ws
+from slam_indoor_code_b200.feature_matching import Context, MatcherType
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+ctx = Context(local)
+ok = True
+for matcher, F, sizes in ((MatcherType.SIFT_BF, 6, [3000, 2500, 1, 2049, 0, 4100]),
+                          (MatcherType.ORB_BF, 5, [1500, 700, 1300, 2, 900])):
+    if matcher == MatcherType.ORB_BF:
+        frames = [synth.orb_pair(max(s, 1), 1, 4100 + f, planted=0)[0][:s] for f, s in enumerate(sizes)]
+    else:
+        base = synth.sift_like(4100, 4200)
+        frames = [synth.sift_train_from_query(base, max(s, 1), 4201 + f)[:s] for f, s in enumerate(sizes)]
+    local_frames = {f: a for f, a in enumerate(frames) if ws.frame_owner(f, world) == rank}
+    out, counts = ws.match_window_on_gpus(ctx, local_frames, F, matcher, 0.7, dist, dev)
+    # single-process reference on this rank's own GPU
+    sets = [ctx.upload(a) for a in frames]
+    ref = ctx.matchWindow(sets, matcher, 0.7)
+    pairs = ws.window_pairs(F)
+    ok = ok and counts == [len(ref[p]) for p in pairs]
+    ok = ok and sorted(out.keys()) == ws.my_window_pairs(rank, world, F)
+    ok = ok and all(np.array_equal(out[p], ref[p]) for p in out)
+print("RESULT " + json.dumps({"rank": rank, "ok": bool(ok)}), flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_window_sharded_equals_single_process(tmp_path):
+    import torch
+    world = max(1, min(torch.cuda.device_count(), 4))
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, REPO_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = [json.loads(l[len("RESULT "):]) for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+    assert len(res) == world and all(d["ok"] for d in res), res

@@ -78,3 +78,61 @@ def test_reference_arm_runs_on_rank0_only():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0
     assert d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+# ---- the keyframe window across ranks: the one real exchange step -----------
+def test_window_pair_deal_is_a_balanced_partition():
+    from slam_indoor_code_b200 import window_sharding as ws
+    for n_frames in (2, 5, 8):
+        allp = ws.window_pairs(n_frames)
+        assert len(allp) == n_frames * (n_frames - 1) // 2
+        for world in (1, 2, 3, 8):
+            shares = [ws.my_window_pairs(r, world, n_frames) for r in range(world)]
+            assert sorted(p for s in shares for p in s) == sorted(allp)
+            assert max(map(len, shares)) - min(map(len, shares)) <= 1
+
+
+WINDOW_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["REPO_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from oracle import c_oracle, synth
+from slam_indoor_code_b200 import window_sharding as ws
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+F = 5
+sizes = [300, 1, 257, 0, 411]                      # ragged frames, an empty one, a single row
+frames = {f: synth.sift_like(max(sizes[f], 1), 4000 + f)[: sizes[f]] for f in range(F)}
+local = {f: a for f, a in frames.items() if ws.frame_owner(f, world) == rank}
+# the CPU oracle stands in for the device: this test is about the exchange and the pair deal
+out, counts, _ = ws.match_window_sharded(
+    local, F, 128, np.float32, dist, "cpu",
+    upload_fn=lambda t: t.numpy().copy(),
+    match_fn=lambda q, ts: [c_oracle.match_features(0, q, t, 0.8) for t in ts])
+ok = all(np.array_equal(m, c_oracle.match_features(0, frames[i], frames[j], 0.8)) for (i, j), m in out.items())
+import json
+print("RESULT " + json.dumps({"rank": rank, "keys": sorted(map(list, out.keys())), "counts": counts, "ok": bool(ok)}), flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_window_exchange_world_size_2(tmp_path):
+    script = tmp_path / "window_worker.py"
+    script.write_text(WINDOW_WORKER)
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29534", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    from oracle import c_oracle, synth
+    from slam_indoor_code_b200 import window_sharding as ws
+    sizes = [300, 1, 257, 0, 411]
+    frames = [synth.sift_like(max(s, 1), 4000 + f)[:s] for f, s in enumerate(sizes)]
+    want = [len(c_oracle.match_features(0, frames[i], frames[j], 0.8)) for i, j in ws.window_pairs(5)]
+    seen = []
+    for r, (so, _) in enumerate(outs):
+        line = [l for l in so.splitlines() if l.startswith("RESULT ")][0]
+        d = json.loads(line[len("RESULT "):])
+        assert d["rank"] == r and d["ok"] and d["counts"] == want   # all counts everywhere; own matches right
+        seen += [tuple(k) for k in d["keys"]]
+    assert sorted(seen) == ws.window_pairs(5)   # every pair matched by exactly one rank
