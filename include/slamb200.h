@@ -194,6 +194,21 @@ int slamb200_score_pnp_batch(slamb200_ctx* ctx, int P, const float* obj, const f
                              int model_points, int32_t* counts, int32_t* best,
                              uint8_t* best_mask);
 
+/* ---- next row: ORB descriptors of given keypoints (featureMatchingCPU.cpp:45-66) --- */
+/* cv::ORB::create()->compute(frame, features, desc) for the ORB_BF matcher: image = rows x cols
+ * CV_8UC3 (BGR) or CV_8UC1, `step` bytes per row; kps = n x {x, y, angle in degrees} floats
+ * (cv::KeyPoint::pt and ::angle; FAST keypoints carry angle -1, octave 0).  Keypoints within 31 px
+ * of the border are dropped exactly as compute() drops them: keep[n] (may be NULL) flags the
+ * survivors in order, *n_kept counts them -- the caller erases the others from its vector, which
+ * is what the reference observes of `features` after the call.  desc (may be NULL) receives
+ * n_kept x 32 bytes on the host; *resident (may be NULL) receives the same rows as a descriptor
+ * set already in HBM, ready for slamb200_match_*: no descriptor upload.  Bit-identical to OpenCV's
+ * descriptors (integer gray conversion, its float 7x7 Gaussian in FMA order, float rotation of the
+ * 256-pair pattern, cvRound). */
+int slamb200_orb_compute(slamb200_ctx* ctx, const uint8_t* image, int rows, int cols, int channels,
+                         size_t step, const float* kps, int n, uint8_t* keep, uint8_t* desc,
+                         int* n_kept, slamb200_desc** resident);
+
 /* ---- next row: linear triangulation (triangulation/triangulate.cpp:17-55, :91-108) --- */
 /* reconstructPointsFor3D for M matches: P1, P2 = 3x4 row-major projection matrices (K*[R|t], as
  * reconstruct() forms them at triangulate.cpp:74-80), pts = M x 2 floats (vector<Point2f>).  Per
@@ -233,7 +248,8 @@ int slamb200_batch_scores_fetch(slamb200_ctx* ctx, int32_t* counts, int32_t* bes
 #define SLAMB200_K_SIFT_GEN_RERANK 7 /* certified fp32 rerank + fallback */
 #define SLAMB200_K_PNP 8        /* reprojection-error counting kernel */
 #define SLAMB200_K_SIFT_L1 9    /* NORM_L1 on integer-valued rows (byte-wise SAD) */
-#define SLAMB200_K_COUNT 10
+#define SLAMB200_K_ORB_DESC 10  /* ORB gray + blur + descriptor kernels */
+#define SLAMB200_K_COUNT 11
 int slamb200_profile_enable(slamb200_ctx* ctx, int on);
 /* Synchronises, then returns the summed device time (ms) and the launch count of each kernel
  * class since the last read; ms and launches have SLAMB200_K_COUNT entries. */

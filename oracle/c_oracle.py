@@ -188,3 +188,31 @@ def triangulate(P1, P2, pts1, pts2):
     rc = lib().oracle_triangulate(_p(P1), _p(P2), _p(pts1), _p(pts2), M, _p(X4), _p(X3))
     assert rc == 0
     return X4, X3
+
+
+def orb_blur(image):
+    """ORB's working image: gray conversion (BGR input) + the float 7x7 Gaussian, as u8."""
+    image = np.ascontiguousarray(image, np.uint8)
+    rows, cols = image.shape[:2]
+    ch = 1 if image.ndim == 2 else image.shape[2]
+    gray = np.zeros((rows, cols), np.uint8)
+    blur = np.zeros((rows, cols), np.uint8)
+    rc = lib().oracle_orb_blur(_p(image), rows, cols, ch, ctypes.c_size_t(image.strides[0]), _p(gray), _p(blur))
+    assert rc == 0
+    return gray, blur
+
+
+def orb_compute(image, kps):
+    """cv::ORB::compute on given keypoints: kps [n, 3] = x, y, angle (degrees; FAST gives -1).
+    Returns (keep mask [n] uint8, descriptors [n_kept, 32] uint8)."""
+    image = np.ascontiguousarray(image, np.uint8)
+    rows, cols = image.shape[:2]
+    ch = 1 if image.ndim == 2 else image.shape[2]
+    kps = np.ascontiguousarray(kps, np.float32).reshape(-1, 3)
+    n = kps.shape[0]
+    keep = np.zeros(max(n, 1), np.uint8)
+    desc = np.zeros((max(n, 1), 32), np.uint8)
+    kept = lib().oracle_orb_compute(_p(image), rows, cols, ch, ctypes.c_size_t(image.strides[0]), _p(kps), n,
+                                    _p(keep), _p(desc))
+    assert kept >= 0
+    return keep[:n], desc[:kept].copy()

@@ -553,3 +553,109 @@ int oracle_triangulate(const double* P1, const double* P2, const float* pts1, co
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * ORB descriptors of given keypoints (reference: extractDescriptor,
+ * featureMatchingCPU.cpp:45-66 -> cv::ORB::create()->compute(frame, features, desc) on FAST
+ * keypoints, fastExtractor.cpp:7-13).  Restated from measurements of cv2 (tools/
+ * recover_orb_pattern.py, tests/test_oracle_vs_cv2.py), OpenCV itself being absent as source:
+ *   gray  = (B*3735 + G*19235 + R*9798 + 2^14) >> 15                       (cvtColor BGR2GRAY, 8u)
+ *   keep  = keypoints with 31 <= x < cols-31 and 31 <= y < rows-31          (runByImageBorder)
+ *   blur  = 7x7 Gaussian, sigma 2, BORDER_REFLECT_101, in float: the kernel sum is not 1 within
+ *           FLT_EPSILON, so sepFilter2D takes its float path -- rows  s = k0*p0; s = fma(kj, pj, s),
+ *           columns  c = k3*s3; c = fma(k(3+j), s(3+j) + s(3-j), c), then round-half-even to u8
+ *           (the order of the FMA-dispatched code of the cv2 wheel; 0 differing pixels in 12M)
+ *   bit k = blur[c + R(p0_k)] < blur[c + R(p1_k)],  R = rotation by kpt.angle with float
+ *           a = cosf, b = sinf:  x' = cvRound(x*a - y*b), y' = cvRound(x*b + y*a); c = cvRound(pt)
+ * ---------------------------------------------------------------------------------------------- */
+#include "../slam_indoor_code_b200/csrc/orb_pattern.h"
+
+static void orb_gauss7(float k[7]) {
+    /* getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) in double, normalised, to float */
+    double v[7], sum = 0;
+    for (int i = 0; i < 7; i++) { double x = i - 3; v[i] = exp(-0.125 * x * x); sum += v[i]; }
+    for (int i = 0; i < 7; i++) k[i] = (float)(v[i] * (1. / sum));
+}
+
+static inline int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+
+/* image: rows x cols, channels 1 (gray) or 3 (BGR), `step` bytes per row.  blur_out: rows*cols. */
+int oracle_orb_blur(const uint8_t* image, int rows, int cols, int channels, size_t step,
+                    uint8_t* gray_out /* optional */, uint8_t* blur_out) {
+    if (rows <= 0 || cols <= 0 || (channels != 1 && channels != 3)) return -1;
+    uint8_t* gray = (uint8_t*)malloc((size_t)rows * cols);
+    float* rowf = (float*)malloc(sizeof(float) * (size_t)rows * cols);
+    if (!gray || !rowf) { free(gray); free(rowf); return -2; }
+    for (int y = 0; y < rows; y++) {
+        const uint8_t* s = image + (size_t)y * step;
+        for (int x = 0; x < cols; x++)
+            gray[(size_t)y * cols + x] = channels == 1 ? s[x]
+                : (uint8_t)((s[3 * x] * 3735 + s[3 * x + 1] * 19235 + s[3 * x + 2] * 9798 + (1 << 14)) >> 15);
+    }
+    if (gray_out) memcpy(gray_out, gray, (size_t)rows * cols);
+    float k[7];
+    orb_gauss7(k);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < rows; y++)
+        for (int x = 0; x < cols; x++) {
+            float s = k[0] * (float)gray[(size_t)y * cols + reflect101(x - 3, cols)];
+            for (int j = 1; j < 7; j++)
+                s = fmaf(k[j], (float)gray[(size_t)y * cols + reflect101(x - 3 + j, cols)], s);
+            rowf[(size_t)y * cols + x] = s;
+        }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < rows; y++)
+        for (int x = 0; x < cols; x++) {
+            float c = k[3] * rowf[(size_t)y * cols + x];
+            for (int j = 1; j < 4; j++)
+                c = fmaf(k[3 + j], rowf[(size_t)reflect101(y + j, rows) * cols + x] +
+                                       rowf[(size_t)reflect101(y - j, rows) * cols + x], c);
+            float r = nearbyintf(c);
+            blur_out[(size_t)y * cols + x] = (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
+        }
+    free(gray); free(rowf);
+    return 0;
+}
+
+/* kps: n x {x, y, angle_deg} floats.  keep[n] = 1 for the keypoints compute() keeps (order
+ * preserved); desc: one 32-byte row per KEPT keypoint.  Returns the kept count or < 0. */
+int oracle_orb_compute(const uint8_t* image, int rows, int cols, int channels, size_t step,
+                       const float* kps, int n, uint8_t* keep, uint8_t* desc) {
+    if (n < 0) return -1;
+    uint8_t* blur = (uint8_t*)malloc((size_t)(rows > 0 ? rows : 1) * (cols > 0 ? cols : 1));
+    if (!blur) return -2;
+    int rc = oracle_orb_blur(image, rows, cols, channels, step, NULL, blur);
+    if (rc) { free(blur); return rc; }
+    int kept = 0;
+    for (int i = 0; i < n; i++) {
+        const float x = kps[3 * i], y = kps[3 * i + 1];
+        const int ok = x >= 31 && x < cols - 31 && y >= 31 && y < rows - 31;
+        keep[i] = (uint8_t)ok;
+        if (!ok) continue;
+        float angle = kps[3 * i + 2];
+        angle *= (float)(3.141592653589793 / 180.f);
+        const float a = cosf(angle), b = sinf(angle);
+        const int cx = (int)lrintf(x), cy = (int)lrintf(y);
+        uint8_t* d = desc + 32 * (size_t)kept++;
+        for (int byte = 0; byte < 32; byte++) {
+            int v = 0;
+            for (int bit = 0; bit < 8; bit++) {
+                const int8_t* p = kOrbPattern[8 * byte + bit];
+                int t[2];
+                for (int e = 0; e < 2; e++) {
+                    const float px = (float)p[2 * e], py = (float)p[2 * e + 1];
+                    const float xr = px * a - py * b, yr = px * b + py * a;
+                    t[e] = blur[(size_t)(cy + (int)lrintf(yr)) * cols + cx + (int)lrintf(xr)];
+                }
+                v |= (t[0] < t[1]) << bit;
+            }
+            d[byte] = (uint8_t)v;
+        }
+    }
+    free(blur);
+    return kept;
+}

@@ -170,3 +170,18 @@ def pnp_hypotheses(h, R, t, seed, good_frac=0.25):
         out[i, :9] = (_rodrigues(rng.normal(0, s, 3)) @ R).reshape(9)
         out[i, 9:] = t + rng.normal(0, s * 3, 3)
     return out
+
+
+def textured_frame(h, w, seed, channels=3):
+    """A frame with structure at several scales (blocks, gradients, noise) so that FAST fires and
+    blurred intensities differ between nearby pixels; uint8 [h, w, channels] or [h, w]."""
+    rng = np.random.default_rng(seed)
+    shape = (h, w, channels) if channels > 1 else (h, w)
+    img = np.zeros(shape, np.float32)
+    for cell, amp in ((64, 90.0), (16, 70.0), (4, 50.0), (1, 30.0)):
+        gh, gw = (h + cell - 1) // cell, (w + cell - 1) // cell
+        g = rng.random((gh, gw) + shape[2:], np.float32)
+        g = np.repeat(np.repeat(g, cell, axis=0), cell, axis=1)[:h, :w]
+        img += amp * g
+    img += np.linspace(0, 15, w, dtype=np.float32).reshape((1, w) + (1,) * (len(shape) - 2))
+    return np.clip(img, 0, 255).astype(np.uint8)

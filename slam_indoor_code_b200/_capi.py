@@ -41,6 +41,7 @@ SYMBOLS = {
     "slamb200_batch_fetch": (_i, [_vp, _vp, _i, _vp, _vp]),
     "slamb200_score_essential": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp]),
     "slamb200_score_essential_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp]),
+    "slamb200_orb_compute": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _vp, _vp, _vp, _vp]),
     "slamb200_triangulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "slamb200_score_pnp": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _d, _i, _vp, _vp, _vp, _vp]),
     "slamb200_score_pnp_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _d, _i, _vp, _vp, _vp]),

@@ -59,6 +59,7 @@ struct Lane {
   DevBuf pairs, tcpairs, tile_prefix, part, cand, cand_g, work, work_v0, fb_list, knn_idx, knn_dist, flags, chunk_cnt, out, n_out, err_flag;
   // scoring scratch (device)
   DevBuf npts, E, counts, best, mask, m_off, p1, p2, txy, all_masks;
+  DevBuf orb_img, orb_gray, orb_rowf, orb_blur, orb_kp, orb_desc;
   // pinned staging
   // pinned staging ring: the host fills slot k+1 while the copy out of slot k may still be
   // queued behind the previous step's kernels (an enqueue never waits for the device)
@@ -306,7 +307,8 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
     Lane& L = c->lanes[i];
     DevBuf* bufs[] = {&L.pairs, &L.tcpairs, &L.tile_prefix, &L.work, &L.work_v0, &L.fb_list, &L.cand_g, &L.part, &L.cand, &L.knn_idx, &L.knn_dist, &L.flags,
                       &L.chunk_cnt, &L.out, &L.n_out, &L.err_flag, &L.npts, &L.E, &L.counts,
-                      &L.best, &L.mask, &L.m_off, &L.p1, &L.p2, &L.txy, &L.all_masks};
+                      &L.best, &L.mask, &L.m_off, &L.p1, &L.p2, &L.txy, &L.all_masks,
+                      &L.orb_img, &L.orb_gray, &L.orb_rowf, &L.orb_blur, &L.orb_kp, &L.orb_desc};
     for (DevBuf* b : bufs)
       if (b->p) cudaFreeAsync(b->p, L.stream);
     cudaStreamSynchronize(L.stream);
@@ -1385,6 +1387,78 @@ extern "C" int slamb200_score_pnp(slamb200_ctx* c, const float* obj, const float
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(all_masks, L.all_masks.p, (size_t)H * M, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  return SLAMB200_OK;
+}
+
+// ---- ORB descriptors of given keypoints ---------------------------------------
+extern "C" int slamb200_orb_compute(slamb200_ctx* c, const uint8_t* image, int rows, int cols,
+                                    int channels, size_t step, const float* kps, int n,
+                                    uint8_t* keep, uint8_t* desc, int* n_kept,
+                                    slamb200_desc** resident) {
+  if (!c || !n_kept) return fail(SLAMB200_ERR_INVALID, "orb_compute: NULL argument");
+  *n_kept = 0;
+  if (resident) *resident = nullptr;
+  if (rows <= 0 || cols <= 0 || !image) return fail(SLAMB200_ERR_INVALID, "orb_compute: bad image");
+  if (channels != 1 && channels != 3)
+    return fail(SLAMB200_ERR_KIND, "orb_compute: %d-channel image (CV_8UC1 or CV_8UC3 expected)", channels);
+  if (step == 0) step = (size_t)cols * channels;
+  if (step < (size_t)cols * channels) return fail(SLAMB200_ERR_INVALID, "orb_compute: step too small");
+  if (n < 0 || (n > 0 && !kps)) return fail(SLAMB200_ERR_INVALID, "orb_compute: bad keypoints");
+  // KeyPointsFilter::runByImageBorder(keypoints, size, edgeThreshold = 31), order preserved; the
+  // centre pixel (cvRound) and the rotation (float cosf / sinf of angle * pi/180) per kept keypoint
+  std::vector<OrbKeypoint> hk;
+  hk.reserve((size_t)n);
+  for (int i = 0; i < n; i++) {
+    const float x = kps[3 * i], y = kps[3 * i + 1];
+    const bool ok = x >= 31.f && x < (float)(cols - 31) && y >= 31.f && y < (float)(rows - 31);
+    if (keep) keep[i] = ok ? 1 : 0;
+    if (!ok) continue;
+    float angle = kps[3 * i + 2];
+    angle *= (float)(3.141592653589793 / 180.f);
+    hk.push_back({(int)lrintf(x), (int)lrintf(y), cosf(angle), sinf(angle)});
+  }
+  const int kept = (int)hk.size();
+  *n_kept = kept;
+  CU(cudaSetDevice(c->device));
+  if (orb_pattern_upload() != 0) return fail(SLAMB200_ERR_CUDA, "orb_compute: pattern upload failed");
+  int rc;
+  const int n_pad = round_up(kept > 0 ? kept : 1, SLAMB200_TILE_PAD);
+  {
+    LaneGuard g(c);
+    Lane& L = g.lane();
+    cudaStream_t s = L.stream;
+    const size_t px = (size_t)rows * cols;
+    if ((rc = buf_reserve(c, L.orb_img, (size_t)rows * step, s))) return rc;
+    if ((rc = buf_reserve(c, L.orb_gray, px, s))) return rc;
+    if ((rc = buf_reserve(c, L.orb_rowf, px * sizeof(float), s))) return rc;
+    if ((rc = buf_reserve(c, L.orb_blur, px, s))) return rc;
+    if ((rc = buf_reserve(c, L.orb_kp, sizeof(OrbKeypoint) * (size_t)(kept > 0 ? kept : 1), s))) return rc;
+    if ((rc = buf_reserve(c, L.orb_desc, (size_t)n_pad * 32, s))) return rc;
+    CU(cudaMemcpyAsync(L.orb_img.p, image, (size_t)rows * step, cudaMemcpyHostToDevice, s));
+    if (kept > 0)
+      CU(cudaMemcpyAsync(L.orb_kp.p, hk.data(), sizeof(OrbKeypoint) * (size_t)kept, cudaMemcpyHostToDevice, s));
+    {
+      ProfScope ps(c, s, SLAMB200_K_ORB_DESC);
+      launch_orb_blur((const uint8_t*)L.orb_img.p, rows, cols, channels, step, (uint8_t*)L.orb_gray.p,
+                      (float*)L.orb_rowf.p, (uint8_t*)L.orb_blur.p, s);
+      launch_orb_desc((const uint8_t*)L.orb_blur.p, cols, (const OrbKeypoint*)L.orb_kp.p, kept, n_pad,
+                      (uint8_t*)L.orb_desc.p, s);
+    }
+    CU(cudaGetLastError());
+    if (desc && kept > 0)
+      CU(cudaMemcpyAsync(desc, L.orb_desc.p, (size_t)kept * 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(L.done, s));
+    // the host vector and the caller's image must outlive the copies; the resident set below is
+    // built from the device rows on the same stream
+    if (resident) {
+      // desc_create takes an upload lane of its own; order it behind this lane's work
+      rc = desc_create(c, SLAMB200_DESC_U8X32, L.orb_desc.p, kept, 32, true, s, false, resident);
+      if (rc) return rc;
+      // the lane's descriptor buffer may be overwritten by the next call only after that copy
+      CU(cudaStreamWaitEvent(s, (*resident)->ready, 0));
+    }
+    CU(cudaStreamSynchronize(s));
+  }
   return SLAMB200_OK;
 }
 

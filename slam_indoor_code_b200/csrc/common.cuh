@@ -119,6 +119,14 @@ void launch_pnp_mask(const double4* pts, const int32_t* m_off, const double* pos
 void launch_pnp_all_masks(const double4* pts, int M, const double* poses, int H,
                           const PnpParams& pp, uint8_t* masks, cudaStream_t s);
 
+// ORB descriptors of given keypoints (orb_desc.cu): centre pixel and cosf/sinf of the angle.
+struct OrbKeypoint { int cx, cy; float a, b; };
+int orb_pattern_upload();
+void launch_orb_blur(const uint8_t* img, int rows, int cols, int channels, size_t step, uint8_t* gray,
+                     float* rowf, uint8_t* blur, cudaStream_t s);
+void launch_orb_desc(const uint8_t* blur, int cols, const OrbKeypoint* kps, int n, int n_pad,
+                     uint8_t* desc, cudaStream_t s);
+
 // Linear triangulation (triangulate.cpp:17-55): P[v] = 3x4 projection matrix of view v, row-major.
 struct TriParams { double P[2][12]; };
 void launch_triangulate(const float2* pts1, const float2* pts2, int M, const TriParams& tp,

@@ -84,7 +84,7 @@ class Context:
         return int(self._lib.slamb200_launch_count(self._h))
 
     KERNELS = ("sift_tc", "sift_exact", "orb", "ransac", "sift_rerank", "finalize", "sift_tc_gen",
-               "sift_gen_rerank", "pnp", "sift_l1")
+               "sift_gen_rerank", "pnp", "sift_l1", "orb_desc")
 
     def profile_enable(self, on=True):
         check(self._lib.slamb200_profile_enable(self._h, 1 if on else 0))
