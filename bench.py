@@ -617,6 +617,23 @@ def extras(ctx, stream):
     # 53 explicit fp64 operations per (pose, point) with five coefficients (the reciprocal counted once)
     out["f2_pnp_2048x5000"] = {"kernel_us_per_frame": kms / kn / P * 1e3,
                                "fp64_ops_T_per_s": P * 2048 * 5000 * 53 / (kms / kn) / 1e9}
+    # next row 8f-3 (ORB half): descriptors of 12 000 FAST-like keypoints on a 4K BGR frame, resident
+    # output (no descriptor upload); host call incl. the 24.9 MB frame copy, and the kernels alone
+    from slam_indoor_code_b200 import orb_descriptors as od
+    frame4k = synth.textured_frame(2160, 3840, 6000, 3)
+    rngk = np.random.default_rng(6001)
+    kp4k = np.stack([rngk.integers(31, 3840 - 31, 12000), rngk.integers(31, 2160 - 31, 12000),
+                     np.full(12000, -1.0)], 1).astype(np.float32)
+    od.extractDescriptorORB(ctx, frame4k, kp4k, want_host=False, want_resident=True)[2].free()
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        od.extractDescriptorORB(ctx, frame4k, kp4k, want_host=False, want_resident=True)[2].free()
+    dt = (time.perf_counter() - t0) / 5
+    kms, kn = ctx.profile_read()["orb_desc"]
+    ctx.profile_enable(False)
+    out["f3_orb_compute_4k_12000kp"] = {"ms_per_host_call": dt * 1e3, "kernels_us": kms / max(kn, 1) * 1e3}
     # next row 8f-4: linear triangulation of 5000 matches (one host call incl. copies)
     from slam_indoor_code_b200 import triangulation as tri
     K4 = synth.SAMSUNG_HV_4K
@@ -704,6 +721,13 @@ def cpu_extras():
     dist = np.array(synth.REF_DIST5)
     dt, _ = best(lambda: cv2.solvePnPRansac(obj, img, Kmat, dist), 5)
     out["f2_solvePnPRansac_s_per_frame"] = dt
+    frame4k = synth.textured_frame(2160, 3840, 6000, 3)
+    rngk = np.random.default_rng(6001)
+    cvk = [cv2.KeyPoint(float(x), float(y), 7.0, -1.0, 0.0, 0) for x, y in
+           zip(rngk.integers(31, 3840 - 31, 12000), rngk.integers(31, 2160 - 31, 12000))]
+    orb = cv2.ORB_create()
+    dt, _ = best(lambda: orb.compute(frame4k, cvk), 3)
+    out["f3_orb_compute_4k_12000kp_s"] = dt
     tp1, tp2, tR, tt = synth.two_view(5000, 8000, outliers=0.0)
     P1 = Kmat @ np.hstack([np.eye(3), np.zeros((3, 1))])
     P2 = Kmat @ np.hstack([tR, tt.reshape(3, 1)])

@@ -560,7 +560,8 @@ int oracle_triangulate(const double* P1, const double* P2, const float* pts1, co
  * keypoints, fastExtractor.cpp:7-13).  Restated from measurements of cv2 (tools/
  * recover_orb_pattern.py, tests/test_oracle_vs_cv2.py), OpenCV itself being absent as source:
  *   gray  = (B*3735 + G*19235 + R*9798 + 2^14) >> 15                       (cvtColor BGR2GRAY, 8u)
- *   keep  = keypoints with 31 <= x < cols-31 and 31 <= y < rows-31          (runByImageBorder)
+ *   keep  = keypoints with 31 <= cvRound(x) < cols-31, 31 <= cvRound(y) < rows-31   (runByImageBorder:
+ *           Rect::contains(Point(pt)) rounds the Point2f)
  *   blur  = 7x7 Gaussian, sigma 2, BORDER_REFLECT_101, in float: the kernel sum is not 1 within
  *           FLT_EPSILON, so sepFilter2D takes its float path -- rows  s = k0*p0; s = fma(kj, pj, s),
  *           columns  c = k3*s3; c = fma(k(3+j), s(3+j) + s(3-j), c), then round-half-even to u8
@@ -633,7 +634,9 @@ int oracle_orb_compute(const uint8_t* image, int rows, int cols, int channels, s
     int kept = 0;
     for (int i = 0; i < n; i++) {
         const float x = kps[3 * i], y = kps[3 * i + 1];
-        const int ok = x >= 31 && x < cols - 31 && y >= 31 && y < rows - 31;
+        /* Rect(31, 31, cols-62, rows-62).contains(Point(pt)): the Point2f is rounded first */
+        const int rx = (int)lrintf(x), ry = (int)lrintf(y);
+        const int ok = rx >= 31 && rx < cols - 31 && ry >= 31 && ry < rows - 31;
         keep[i] = (uint8_t)ok;
         if (!ok) continue;
         float angle = kps[3 * i + 2];

@@ -7,6 +7,7 @@ entry points the reference calls, through the cv2 wheel:
   featureMatchingCPU.cpp:26-40   DescriptorMatcher BRUTEFORCE / BRUTEFORCE_HAMMING, knnMatch k=2
   cameraTranslation.cpp:41-46    findEssentialMat(p1, p2, K, RANSAC, prob, threshold, mask)
   featureMatchingCUDA.cpp:28     NORM_L1 for useFM-SIFT-BF (CPU BFMatcher as the owner)
+  featureMatchingCPU.cpp:45-66   ORB::create()->compute(frame, features, desc)     (SURVEY.md 8f-3)
   mainCycle.cpp:155-159          solvePnPRansac(obj, img, K, dist, rvec, tvec)   
 
 Run from the repo root:   python -m oracle.gen_golden          (all fixtures)
@@ -123,6 +124,7 @@ def main():
 
     gen_l1()
     gen_pnp()
+    gen_orb_desc()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} fixtures, {total/1024:.0f} KiB, cv2 {cv2.__version__}")
 
@@ -136,6 +138,21 @@ def gen_l1():
         idx, dist, _ = cv_knn2(g["q"].astype(np.float32), g["t"].astype(np.float32), cv2.NORM_L1)
         out[name + "_idx"], out[name + "_dist"] = idx, dist
     np.savez_compressed(os.path.join(OUT, "sift_l1.npz"), **out)
+
+
+def gen_orb_desc():
+    """extractDescriptor's ORB branch: FAST keypoints (angle -1) and oriented keypoints on a small
+    textured frame; cv2.ORB.compute's kept keypoints and descriptors."""
+    frame = synth.textured_frame(200, 260, 6100, 3)
+    fast = cv2.FastFeatureDetector_create(10, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16).detect(frame)[:400]
+    rng = np.random.default_rng(6101)
+    kps = np.array([[k.pt[0], k.pt[1], k.angle] for k in fast], np.float32)
+    extra = np.stack([rng.uniform(0, 260, 200), rng.uniform(0, 200, 200), rng.uniform(0, 360, 200)], 1).astype(np.float32)
+    kps = np.concatenate([kps, extra])
+    cvk = [cv2.KeyPoint(float(x), float(y), 7.0, float(a), 0.0, 0) for x, y, a in kps]
+    kept, desc = cv2.ORB_create().compute(frame, cvk)
+    kept_xy = np.array([k.pt for k in kept], np.float32)
+    np.savez_compressed(os.path.join(OUT, "orb_desc.npz"), frame=frame, kps=kps, kept_xy=kept_xy, desc=desc)
 
 
 def gen_pnp():
@@ -180,5 +197,7 @@ if __name__ == "__main__":
         gen_pnp()
     elif len(sys.argv) > 1 and sys.argv[1] == "l1":
         gen_l1()
+    elif len(sys.argv) > 1 and sys.argv[1] == "orb_desc":
+        gen_orb_desc()
     else:
         main()

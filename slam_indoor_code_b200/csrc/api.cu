@@ -1410,12 +1410,13 @@ extern "C" int slamb200_orb_compute(slamb200_ctx* c, const uint8_t* image, int r
   hk.reserve((size_t)n);
   for (int i = 0; i < n; i++) {
     const float x = kps[3 * i], y = kps[3 * i + 1];
-    const bool ok = x >= 31.f && x < (float)(cols - 31) && y >= 31.f && y < (float)(rows - 31);
+    const int rx = (int)lrintf(x), ry = (int)lrintf(y);  // Rect::contains(Point(pt)) rounds first
+    const bool ok = rx >= 31 && rx < cols - 31 && ry >= 31 && ry < rows - 31;
     if (keep) keep[i] = ok ? 1 : 0;
     if (!ok) continue;
     float angle = kps[3 * i + 2];
     angle *= (float)(3.141592653589793 / 180.f);
-    hk.push_back({(int)lrintf(x), (int)lrintf(y), cosf(angle), sinf(angle)});
+    hk.push_back({rx, ry, cosf(angle), sinf(angle)});
   }
   const int kept = (int)hk.size();
   *n_kept = kept;

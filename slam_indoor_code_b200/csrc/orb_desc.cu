@@ -11,7 +11,7 @@
 //   bit k  blur[c + R(p0_k)] < blur[c + R(p1_k)] over the 256 pairs of orb_pattern.h, R = rotation
 //          by the keypoint angle in float (x*a - y*b, x*b + y*a, separately rounded products),
 //          cvRound to the pixel grid
-// The border filter (keypoints within 31 px of the edge are dropped) and cosf/sinf of the angle run
+// The border filter (keypoints whose rounded position is within 31 px of the edge are dropped) and cosf/sinf of the angle run
 // on the host (api.cu): they are per-keypoint scalars, and libm's cosf is what OpenCV calls.
 #include "common.cuh"
 #include "orb_pattern.h"

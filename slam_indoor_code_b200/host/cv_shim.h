@@ -11,6 +11,7 @@
 
 #define CV_8U 0
 #define CV_32F 5
+#define CV_8UC3 16  // CV_MAKETYPE(CV_8U, 3)
 
 namespace cv {
 
@@ -38,6 +39,15 @@ struct Mat {
   Mat(int r, int c, int type, void* d, size_t s) : rows(r), cols(c), data((unsigned char*)d), step(s), type_(type) {}
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
   int type() const { return type_; }
+  int depth() const { return type_ & 7; }
+  int channels() const { return (type_ >> 3) + 1; }
+  void release() { rows = cols = 0; data = nullptr; step = 0; owner.reset(); }
+  void create(int r, int c, int type) {
+    const size_t esz = (size_t)((type & 7) == CV_32F ? 4 : 1) * (size_t)((type >> 3) + 1);
+    owner = std::make_shared<std::vector<unsigned char>>((size_t)r * c * esz);
+    rows = r; cols = c; type_ = type; step = (size_t)c * esz;
+    data = owner->empty() ? nullptr : owner->data();
+  }
 };
 
 template <class T> using Ptr = std::shared_ptr<T>;

@@ -2,8 +2,8 @@
 // behind src/mainModule/featureMatching/featureMatching.h, next to featureMatchingCPU.cpp and
 // featureMatchingCUDA.cpp (the reference's CMakeLists.txt:56-67 compiles exactly one of them; a
 // USE_B200 option adds this one).  Same three symbols, same signatures, same
-// behaviour: extractDescriptor stays OpenCV-CPU (it produces this path's input), matchFeatures
-// is replaced by one C-ABI call that runs knnMatch(k=2) + getGoodMatches on the B200.
+// behaviour: extractDescriptor keeps SIFT on OpenCV-CPU and computes ORB descriptors on the B200,
+// matchFeatures is one C-ABI call that runs knnMatch(k=2) + getGoodMatches on the B200.
 //
 // Build against the real OpenCV inside the reference tree, or against host/cv_shim.h
 // (-DSLAMB200_CV_SHIM) where OpenCV's headers are not installed -- the shim declares exactly the
@@ -22,6 +22,7 @@ static double knnMatcherDistance() {
 }
 #endif
 
+#include <cstring>
 #include <exception>
 #include <mutex>
 #include <stdexcept>
@@ -118,7 +119,43 @@ static void matchFeatures(Mat& prevDesc, Mat& curDesc, std::vector<DMatch>& matc
   matches.resize((size_t)n);
 }
 
-// featureMatchingCPU.cpp:45-66, unchanged: the descriptors are this path's input.
+// cv::ORB::create()->compute(frame, features, desc) on the B200: same descriptors,
+// same pruning of `features` (keypoints within 31 px of the border are erased, order kept).
+static void computeOrbB200(Mat& frame, std::vector<KeyPoint>& features, Mat& desc) {
+  if (frame.empty() || features.empty()) {  // Feature2D::compute: nothing to describe
+    desc.release();
+    if (frame.empty()) features.clear();
+    return;
+  }
+  if (frame.depth() != CV_8U || (frame.channels() != 1 && frame.channels() != 3))
+    throw std::runtime_error("ORB: CV_8UC1 or CV_8UC3 frame expected");  // cv::Exception in OpenCV
+  const int n = (int)features.size();
+  std::vector<float> k((size_t)3 * n);
+  for (int i = 0; i < n; i++) {
+    k[3 * i] = features[i].pt.x;
+    k[3 * i + 1] = features[i].pt.y;
+    k[3 * i + 2] = features[i].angle;
+  }
+  std::vector<unsigned char> keep((size_t)n), rows((size_t)n * 32);
+  int kept = 0;
+  const int rc = slamb200_orb_compute(context(), frame.data, frame.rows, frame.cols, frame.channels(),
+                                      (size_t)frame.step, k.data(), n, keep.data(), rows.data(), &kept,
+                                      nullptr);
+  if (rc != SLAMB200_OK) throw std::runtime_error(std::string("slamb200_orb_compute: ") + slamb200_last_error());
+  int w = 0;
+  for (int i = 0; i < n; i++)
+    if (keep[i]) features[w++] = features[i];
+  features.resize((size_t)w);
+  if (kept == 0) {
+    desc.release();
+    return;
+  }
+  desc.create(kept, 32, CV_8U);
+  for (int r = 0; r < kept; r++) memcpy(desc.data + (size_t)r * desc.step, rows.data() + (size_t)r * 32, 32);
+}
+
+// featureMatchingCPU.cpp:45-66.  SIFT stays OpenCV-CPU (its float image pipeline has no exact
+// definition across OpenCV builds); ORB runs on the device.
 void extractDescriptor(Mat& frame, std::vector<KeyPoint>& features, int matcherType, Mat& desc) {
   cv::Ptr<cv::DescriptorExtractor> extractor;
   switch (matcherType) {
@@ -127,8 +164,13 @@ void extractDescriptor(Mat& frame, std::vector<KeyPoint>& features, int matcherT
       extractor = cv::SIFT::create();
       break;
     case ORB_BF:
+#ifndef SLAMB200_ORB_ON_CPU
+      computeOrbB200(frame, features, desc);
+      return;
+#else
       extractor = cv::ORB::create();
       break;
+#endif
     default:
       throw std::exception();
   }

@@ -50,6 +50,32 @@ int hostshim_match_batch(const void* q, int nq, const void* const* t, const int*
   }
 }
 
+// extractDescriptor(frame, features, ORB_BF, desc): returns the number of keypoints left in
+// `features` (their x, y go to kept_xy), the descriptor rows to desc_out; -1 on an exception.
+int hostshim_extract_orb(const void* frame, int rows, int cols, int channels, size_t step, const float* kps,
+                         int n, float* kept_xy, unsigned char* desc_out, int cap) {
+  try {
+    cv::Mat f(rows, cols, channels == 3 ? CV_8UC3 : CV_8U, const_cast<void*>(frame), step);
+    std::vector<cv::KeyPoint> features((size_t)n);
+    for (int i = 0; i < n; i++) {
+      features[i].pt.x = kps[3 * i];
+      features[i].pt.y = kps[3 * i + 1];
+      features[i].angle = kps[3 * i + 2];
+    }
+    cv::Mat desc;
+    extractDescriptor(f, features, ORB_BF, desc);
+    if ((int)features.size() > cap || desc.rows != (desc.empty() ? 0 : (int)features.size())) return -2;
+    for (size_t i = 0; i < features.size(); i++) {
+      kept_xy[2 * i] = features[i].pt.x;
+      kept_xy[2 * i + 1] = features[i].pt.y;
+      memcpy(desc_out + 32 * i, desc.data + i * desc.step, 32);
+    }
+    return (int)features.size();
+  } catch (...) {
+    return -1;
+  }
+}
+
 // The C++ RANSAC control with a scripted solver and scorer: `n_models[i]` models come out of the
 // i-th minimal sample, model h of the run scores `scores[h]`.  Returns the iterations run; writes
 // every drawn subset and the index of the winning model (or -1).

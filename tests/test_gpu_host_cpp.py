@@ -76,3 +76,25 @@ def test_batch_fast_path_cpp(host):
     assert rc == 0
     for p in range(P):
         assert np.array_equal(out[p, : n_out[p]], c_oracle.match_features(0, q, trains[p], 0.7))
+
+
+def test_extract_descriptor_orb_cpp(host):
+    """extractDescriptor(frame, features, ORB_BF, desc) of the drop-in unit: descriptors on the B200,
+    `features` pruned exactly like cv::ORB::compute prunes it."""
+    host.hostshim_extract_orb.restype = ctypes.c_int
+    host.hostshim_extract_orb.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    frame = synth.textured_frame(300, 400, 41, 3)
+    rng = np.random.default_rng(42)
+    kps = np.stack([rng.integers(0, 400, 1500), rng.integers(0, 300, 1500), np.full(1500, -1.0)], 1).astype(np.float32)
+    kept_xy = np.zeros((1500, 2), np.float32)
+    desc = np.zeros((1500, 32), np.uint8)
+    n = host.hostshim_extract_orb(_capi.ptr(frame), 300, 400, 3, frame.strides[0], _capi.ptr(kps), 1500,
+                                  _capi.ptr(kept_xy), _capi.ptr(desc), 1500)
+    keep, want = c_oracle.orb_compute(frame, kps)
+    assert n == len(want) > 500
+    assert np.array_equal(kept_xy[:n], kps[keep.astype(bool), :2]) and np.array_equal(desc[:n], want)
+    # nothing survives the border filter -> empty Mat, empty vector
+    edge = np.array([[3, 3, -1], [399, 299, -1]], np.float32)
+    assert host.hostshim_extract_orb(_capi.ptr(frame), 300, 400, 3, frame.strides[0], _capi.ptr(edge), 2,
+                                     _capi.ptr(kept_xy), _capi.ptr(desc), 1500) == 0

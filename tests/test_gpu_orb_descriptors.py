@@ -66,13 +66,14 @@ def test_orb_descriptors_vs_cv2_fast_keypoints(ctx):
 def test_orb_descriptors_edges(ctx):
     frame = _frame(200, 300, 31, 3)
     # every keypoint too close to the border: nothing kept; no keypoints at all
-    k = np.array([[5, 5, -1], [299, 100, -1], [150, 199, -1], [30.5, 100, -1], [100, 169.0, -1]], np.float32)
+    k = np.array([[5, 5, -1], [299, 100, -1], [150, 199, -1], [30.4, 100, -1], [100, 168.6, -1]], np.float32)
     keep, desc, res = od.extractDescriptorORB(ctx, frame, k, want_resident=True)
     assert not keep.any() and desc.shape == (0, 32) and res.n == 0
     keep, desc, _ = od.extractDescriptorORB(ctx, frame, np.zeros((0, 3), np.float32))
     assert keep.shape == (0,) and desc.shape == (0, 32)
     # exactly on the inclusive / exclusive limits, sub-pixel positions (cvRound to the centre pixel)
-    k = np.array([[31, 31, -1], [268.99, 168.99, -1], [269, 100, -1], [100.5, 101.5, 17.0], [99.49, 100.51, 200.0]],
+    # (the border test is on the ROUNDED position: Rect::contains(Point(pt)))
+    k = np.array([[31, 31, -1], [268.4, 168.4, -1], [268.6, 100, -1], [100.5, 101.5, 17.0], [30.6, 100.51, 200.0]],
                  np.float32)
     keep, desc, _ = od.extractDescriptorORB(ctx, frame, k)
     rkeep, rdesc = c_oracle.orb_compute(frame, k)
@@ -85,3 +86,9 @@ def test_orb_descriptors_edges(ctx):
     assert np.array_equal(desc, rdesc)
     with pytest.raises(TypeError):
         od.extractDescriptorORB(ctx, frame.astype(np.float32), k)
+
+
+def test_orb_descriptors_golden(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "orb_desc.npz"))
+    keep, desc, _ = od.extractDescriptorORB(ctx, g["frame"], g["kps"])
+    assert np.array_equal(g["kps"][keep, :2], g["kept_xy"]) and np.array_equal(desc, g["desc"])

@@ -179,3 +179,11 @@ def test_c_oracle_l1_matches_cv2(golden_dir, name):
     assert np.array_equal(idx, l1[name + "_idx"])
     valid = idx >= 0
     assert np.array_equal(dist[valid].view(np.int32), l1[name + "_dist"][valid].view(np.int32))
+
+
+# ---- ORB descriptors of given keypoints -----------------------------------------
+def test_orb_descriptor_oracle_matches_cv2(golden_dir):
+    g = np.load(os.path.join(golden_dir, "orb_desc.npz"))
+    keep, desc = c_oracle.orb_compute(g["frame"], g["kps"])
+    assert np.array_equal(g["kps"][keep.astype(bool), :2], g["kept_xy"])
+    assert np.array_equal(desc, g["desc"]) and len(desc) > 150

@@ -136,3 +136,26 @@ def test_triangulation_oracle_vs_cv2():
     ref = cv2.triangulatePoints(P1, P2, p1.T.astype(np.float64), p2.T.astype(np.float64))
     assert np.max(np.abs(ref - X4)) < 1e-14
     assert np.allclose(X3, (ref[:3] / ref[3]).T, rtol=1e-11)
+
+
+@pytest.mark.parametrize("h,w,ch,seed", [(480, 640, 3, 9400), (301, 457, 1, 9401)])
+def test_orb_compute_bit_exact(h, w, ch, seed):
+    """cv2.ORB.compute on FAST keypoints (the reference's sequence) and on oriented keypoints:
+    gray conversion, ORB's float blur, the recovered comparison pattern, rotation, border filter."""
+    frame = synth.textured_frame(h, w, seed, ch)
+    kps = cv2.FastFeatureDetector_create(10, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16).detect(frame)[:6000]
+    rng = np.random.default_rng(seed)
+    for k in kps[::2]:
+        k.angle = float(rng.uniform(0, 360))
+    kept, desc = cv2.ORB_create().compute(frame, kps)
+    keep, got = c_oracle.orb_compute(frame, np.array([[k.pt[0], k.pt[1], k.angle] for k in kps], np.float32))
+    assert keep.sum() == len(kept) > 500
+    assert np.array_equal(got, desc)
+    gray, blur = c_oracle.orb_blur(frame)
+    if ch == 3:
+        assert np.array_equal(gray, cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY))
+    k32 = cv2.getGaussianKernel(7, 2, cv2.CV_32F)
+    ref = cv2.sepFilter2D(gray, cv2.CV_8U, k32, k32, borderType=cv2.BORDER_REFLECT_101)
+    # the float blur depends on the FMA dispatch of the OpenCV build: identical here, and never
+    # more than one level apart on the rare pixel whose sum sits on a rounding boundary
+    assert np.count_nonzero(blur != ref) <= 2 and np.abs(blur.astype(int) - ref).max() <= 1
