@@ -406,7 +406,9 @@ static slamb200_ctx::PinBuf* pin_acquire(slamb200_ctx* c, size_t bytes) {
           return b;
         }
       cudaGetLastError();  // cudaErrorNotReady from the queries above
-      if ((int)c->pin_pool.size() < PIN_POOL_MAX) {
+      // grow freely up to 16 buffers; beyond that only after waiting a little for one in flight
+      // (cudaMallocHost costs milliseconds and stalls the device queue)
+      if ((int)c->pin_pool.size() < 16 || ((int)c->pin_pool.size() < PIN_POOL_MAX && spin > 50)) {
         auto* b = new slamb200_ctx::PinBuf{nullptr, 0, nullptr, true};
         const size_t cap = (bytes + ((size_t)1 << 21) - 1) >> 21 << 21;  // 2 MiB granules
         if (cudaMallocHost(&b->p, cap) != cudaSuccess ||
