@@ -299,6 +299,9 @@ def run_b200(args, rank, world, local):
     ctx.profile_read()
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect()
+    gc.disable()            # as timeit does: no cyclic-GC pause while the host feeds the device
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
@@ -306,6 +309,7 @@ def run_b200(args, rank, world, local):
     ev1.record()
     barrier()
     t1 = time.perf_counter()
+    gc.enable()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     launches = torch.tensor([ctx.launch_count() - launches0], device=dev, dtype=torch.float64)
     clocks = sampler.stop(t0, t1, t_load0)
