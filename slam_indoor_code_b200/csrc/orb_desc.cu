@@ -16,7 +16,9 @@
 #include "common.cuh"
 #include "orb_pattern.h"
 
-__constant__ int8_t c_orb_pattern[256][4];
+// global (not __constant__): every lane reads its own eight entries, which the constant cache would
+// serialise 32 ways
+__device__ __align__(16) int8_t g_orb_pattern[256][4];
 
 __device__ __forceinline__ int reflect101(int p, int n) {
   if (n == 1) return 0;
@@ -74,10 +76,15 @@ orb_desc_kernel(const uint8_t* __restrict__ blur, int cols, const OrbKeypoint* _
   }
   const OrbKeypoint kp = kps[i];
   const uint8_t* center = blur + (size_t)kp.cy * cols + kp.cx;
+  // this lane's eight point pairs: 32 bytes, two 16-byte loads
+  const uint4 pa = __ldg(reinterpret_cast<const uint4*>(&g_orb_pattern[8 * lane][0]));
+  const uint4 pb = __ldg(reinterpret_cast<const uint4*>(&g_orb_pattern[8 * lane + 4][0]));
+  const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
   int v = 0;
 #pragma unroll
   for (int bit = 0; bit < 8; bit++) {
-    const int8_t* p = c_orb_pattern[8 * lane + bit];
+    const int8_t p[4] = {(int8_t)(pw[bit] & 255u), (int8_t)((pw[bit] >> 8) & 255u),
+                         (int8_t)((pw[bit] >> 16) & 255u), (int8_t)(pw[bit] >> 24)};
     int t[2];
 #pragma unroll
     for (int e = 0; e < 2; e++) {
@@ -101,7 +108,7 @@ static void orb_gauss7(Gauss7& g) {
 int orb_pattern_upload() {
   static bool done = false;
   if (done) return 0;
-  if (cudaMemcpyToSymbol(c_orb_pattern, kOrbPattern, sizeof(kOrbPattern)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_orb_pattern, kOrbPattern, sizeof(kOrbPattern)) != cudaSuccess) return -1;
   done = true;
   return 0;
 }

@@ -78,3 +78,25 @@ elif which == "single":
         ctx.matchBatchEnqueue(Q, [T], MatcherType.SIFT_BF, 0.7, st)
     torch.cuda.synchronize()
     print("ok", len(ctx.batchFetch(st)[0][0]))
+elif which == "next":
+    # the "next" rows at their bench shapes: NORM_L1 (16 pairs), ORB descriptors (4K frame, 12k kps),
+    # triangulation (5000 matches)
+    from slam_indoor_code_b200 import orb_descriptors as od, triangulation as tri
+    qi, ti = synth.sift_pair(10000, 10000, 1001)
+    Qi, Ti = ctx.upload(qi), ctx.upload(ti)
+    for _ in range(2):
+        ctx.matchBatchEnqueue(Qi, [Ti] * 16, MatcherType.SIFT_BF_L1, 0.7, st)
+    torch.cuda.synchronize()
+    print("l1 ok", len(ctx.batchFetch(st)[0][0]))
+    frame = synth.textured_frame(2160, 3840, 6000, 3)
+    rng = np.random.default_rng(6001)
+    kps = np.stack([rng.integers(31, 3840 - 31, 12000), rng.integers(31, 2160 - 31, 12000), np.full(12000, -1.0)], 1).astype(np.float32)
+    for _ in range(2):
+        keep, d, _ = od.extractDescriptorORB(ctx, frame, kps)
+    print("orb desc ok", d.shape)
+    K4 = synth.SAMSUNG_HV_4K
+    K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]])
+    p1, p2, R, t = synth.two_view(5000, 8000, outliers=0.0)
+    for _ in range(2):
+        X = tri.reconstruct(ctx, K, np.eye(3), np.zeros(3), R, t, p1, p2)
+    print("triangulate ok", X.shape)
