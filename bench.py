@@ -357,9 +357,6 @@ def run_b200(args, rank, world, local):
         t.free()
     Q.free()
     e2e_steps = max(0, min(args.steps, args.e2e_steps))
-    # bytes that cross PCIe per step: the fp32 Mats as they are, or their verified byte images
-    h2d = (len(trains) + 1) * N_ROWS * (128 if args.e2e_upload == "packed" else 512)
-    host_mat_bytes = (len(trains) + 1) * N_ROWS * 512
     d2h = 0
 
     # The reference walks the window from `threadsCount` host threads that share the query
@@ -372,12 +369,20 @@ def run_b200(args, rank, world, local):
     n_buf = np.zeros(max(len(trains), 1), np.int32)
     pool = ThreadPoolExecutor(n_workers)
 
+    # host cores this rank may use: the ranks of a node share them
+    cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    if args.e2e_upload == "auto":
+        # narrowing pays once a rank has enough cores to outrun PCIe (about eight); otherwise the
+        # fp32 Mats go over the link as they are
+        args.e2e_upload = "packed" if cores >= 8 else "pinned"
     up = ctx.upload_packed if args.e2e_upload == "packed" else ctx.upload_pinned
     pack_threads = 0
     if args.e2e_upload == "packed":
         pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else \
-            max(0, min(os.cpu_count() or 1, 16) - args.e2e_workers)
+            max(0, min(cores, 16) - args.e2e_workers)
         ctx.set_pack_threads(pack_threads)
+    # bytes that cross PCIe per step: the fp32 Mats as they are, or their verified byte images
+    h2d = (len(trains) + 1) * N_ROWS * (128 if args.e2e_upload == "packed" else 512)
 
     # Producer / consumer pipeline over the public API: `n_workers` uploader threads hand the train
     # Mats to the library in window order (each call narrows / queues one Mat), `n_match` matcher
@@ -489,7 +494,7 @@ def run_b200(args, rank, world, local):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(io[0].item()),
                     "d2h_bytes_per_step": int(io[1].item()), "steps": e2e_steps,
-                    "warmup_steps_run": len(warm_t), "upload": args.e2e_upload, "host_mat_bytes_per_step": host_mat_bytes * world,
+                    "warmup_steps_run": len(warm_t), "upload": args.e2e_upload, "host_mat_bytes_per_step": (N_PAIRS + world) * N_ROWS * 512,
                     "host_threads": {"uploaders": args.e2e_workers, "matchers": args.e2e_matchers,
                                      "pack_pool": pack_threads},
                     "timing": "host wall clock between device synchronisations, max over ranks",
@@ -774,7 +779,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=14, help="train frames per e2e chunk")
     ap.add_argument("--e2e-pack-threads", type=int, default=-1,
                     help="library threads sharing the narrowing of each Mat (-1: min(cores, 16) - uploaders)")
-    ap.add_argument("--e2e-upload", default="packed", choices=["packed", "pinned"],
+    ap.add_argument("--e2e-upload", default="auto", choices=["auto", "packed", "pinned"],
                     help="packed: rows narrowed to bytes on the host threads (verified lossless) before "
                          "PCIe; pinned: the fp32 Mats read over PCIe as they are")
     ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the CPU arm")
