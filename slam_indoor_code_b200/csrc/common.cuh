@@ -61,6 +61,33 @@ struct PairArgs {
 
 #define ABSENT_KEY 0xFFFFFFFFu
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may be scheduled
+// while its predecessor in the stream is still running; it must execute PDL_WAIT() before it
+// touches anything the predecessor wrote (the wait returns once the predecessor grid has completed
+// and its writes are visible).  PDL_TRIGGER() in the predecessor lets the dependent grid start
+// being scheduled early; without it the trigger is implicit at grid exit.  Launched without the
+// attribute both instructions are no-ops.  Used on the short kernels behind the tcgen05 kernel,
+// where launch latency is a visible part of a single-pair call.
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#ifdef __CUDACC__
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---- kernel launchers (each in its own .cu) ------------------------------------------------
 // ORB: partial top-2 per (pair, split, query).
 void launch_orb_knn2(const uint8_t* q, int nq, const PairArgs* pairs, int n_pairs, int n_split,

@@ -27,6 +27,8 @@ finalize_rows_kernel(const uint4* __restrict__ part, int nq, int n_split, int ha
   const int pair = blockIdx.y;
   const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
   int keep = 0;
+  PDL_TRIGGER();
+  PDL_WAIT();
   if (q < nq) {
     uint4 r = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
     for (int s = 0; s < n_split; s++) {
@@ -58,6 +60,7 @@ compact_kernel(const int32_t* __restrict__ knn_idx, const float* __restrict__ kn
   const int pair = blockIdx.y;
   const int chunk = blockIdx.x;
   const int q = chunk * FIN_THREADS + threadIdx.x;
+  PDL_WAIT();
   if (threadIdx.x < 32) {
     int acc = 0;
     for (int c = threadIdx.x; c < chunk; c += 32) acc += chunk_cnt[pair * gridDim.x + c];
@@ -102,10 +105,10 @@ void launch_finalize(const uint4* part, int nq, const PairArgs* pairs, int n_pai
     return;
   }
   dim3 grid(finalize_chunks(nq), n_pairs);
-  finalize_rows_kernel<<<grid, FIN_THREADS, 0, s>>>(part, nq, n_split, hamming, ratio, knn_idx,
-                                                    knn_dist, flags, chunk_cnt);
+  launch_pdl(finalize_rows_kernel, grid, dim3(FIN_THREADS), 0, s, part, nq, n_split, hamming, ratio, knn_idx,
+             knn_dist, flags, chunk_cnt);
   COUNT_LAUNCH();
-  compact_kernel<<<grid, FIN_THREADS, 0, s>>>(knn_idx, knn_dist, flags, chunk_cnt, nq, out, cap,
-                                              n_out);
+  launch_pdl(compact_kernel, grid, dim3(FIN_THREADS), 0, s, (const int32_t*)knn_idx, (const float*)knn_dist,
+             (const uint8_t*)flags, (const int32_t*)chunk_cnt, nq, out, cap, n_out);
   COUNT_LAUNCH();
 }

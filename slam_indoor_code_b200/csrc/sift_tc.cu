@@ -462,6 +462,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  PDL_TRIGGER();   // the merge kernel behind this one may be scheduled now; it waits for our exit
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs; each loads its own halves) =================
@@ -717,6 +718,8 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
   __shared__ int n_valid_s;
   const int pair = blockIdx.y;
   const int q = blockIdx.x * 256 + threadIdx.x;   // one block = one 256-row query block
+  PDL_TRIGGER();
+  PDL_WAIT();
   // general-float pair: its records belong to the exact fp32 kernel (block-uniform exit)
   if (R.q_flags[0] != 0 || R.pairs[pair].t_flags[0] != 0) return;
   if (threadIdx.x == 0) {
@@ -798,6 +801,8 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
 __global__ void __launch_bounds__(256) sift_rerank_lite_kernel(const RerankParams R) {
   const int lane = threadIdx.x & 31;
   const int part = lane & 3, cand = lane >> 2;
+  PDL_TRIGGER();
+  PDL_WAIT();
   const int n_work = *R.work_n;
   const int warps = gridDim.x * 8;
   for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < n_work; w += warps) {
@@ -861,6 +866,8 @@ __global__ void __launch_bounds__(256) sift_rerank_lite_kernel(const RerankParam
 __global__ void __launch_bounds__(256) sift_rerank_kernel(const RerankParams R) {
   const int lane = threadIdx.x & 31;
   const int part = lane & 7, sub = lane >> 3;
+  PDL_TRIGGER();
+  PDL_WAIT();
   const int n_work = *R.work_n;
   const int warps = gridDim.x * 8;
   for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < n_work; w += warps) {
@@ -1299,13 +1306,13 @@ void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32
   R.work = work; R.work_v0 = work_v0; R.work_n = work_n;
   R.prune = (prune && ratio >= 0.0 && ratio < 1e300) ? 1 : 0; R.ratio = ratio;
   dim3 grid((nq + 255) / 256, n_pairs);
-  sift_merge_kernel<<<grid, 256, 0, s>>>(R);
+  launch_pdl(sift_merge_kernel, grid, dim3(256), 0, s, R);
   COUNT_LAUNCH();
   const long long rows = (long long)nq * n_pairs;
   const int blocks = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
   if (prune)
-    sift_rerank_lite_kernel<<<blocks, 256, 0, s>>>(R);   // match output: distances + best index
+    launch_pdl(sift_rerank_lite_kernel, dim3(blocks), dim3(256), 0, s, R);   // match output: distances + best index
   else
-    sift_rerank_kernel<<<blocks, 256, 0, s>>>(R);        // raw k-NN output: both indices
+    launch_pdl(sift_rerank_kernel, dim3(blocks), dim3(256), 0, s, R);        // raw k-NN output: both indices
   COUNT_LAUNCH();
 }
