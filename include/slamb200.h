@@ -104,6 +104,29 @@ int slamb200_upload_desc_pinned(slamb200_ctx* ctx, int kind, const void* rows, i
  * to slamb200_upload_desc in every case. */
 int slamb200_upload_desc_packed(slamb200_ctx* ctx, int kind, const void* rows, int n,
                                 size_t row_stride, slamb200_desc** out);
+/* ---- descriptor sets across processes (one process per GPU, keyframe window) ----- */
+/* A set uploaded with slamb200_upload_desc_shared lives in an allocation that other processes on
+ * the node can map (CUDA IPC).  slamb200_desc_export fills a plain 128-byte record that may be
+ * sent to the other ranks by any means (it waits for the set's prep kernel first);
+ * slamb200_desc_import maps the exporter's prepared slab -- bf16 operands, norms, byte copy, flags
+ * -- into this process and returns an ordinary handle: every entry point accepts it, the tcgen05
+ * kernel then TMA-loads that frame's tiles over NVLink while it computes (no all-gather of rows,
+ * no second prep pass).  A peer-mapped QUERY set costs one pass over its operand per frame pair;
+ * a peer-mapped TRAIN set would be re-read once per query block, so copy it first with
+ * slamb200_desc_localize (one device-to-device transfer of the prepared slab).  The exporter must
+ * keep its set alive until every importer has freed its mapping. */
+typedef struct slamb200_desc_ipc {
+  unsigned char handle[64]; /* cudaIpcMemHandle_t */
+  int kind, n, n_pad, device, exact, reserved;
+  unsigned long long slab_bytes;
+  unsigned char pad[32];
+} slamb200_desc_ipc;
+int slamb200_upload_desc_shared(slamb200_ctx* ctx, int kind, const void* rows, int n,
+                                size_t row_stride, slamb200_desc** out);
+int slamb200_desc_export(slamb200_ctx* ctx, const slamb200_desc* d, slamb200_desc_ipc* out);
+int slamb200_desc_import(slamb200_ctx* ctx, const slamb200_desc_ipc* in, slamb200_desc** out);
+int slamb200_desc_localize(slamb200_ctx* ctx, const slamb200_desc* src, slamb200_desc** out);
+
 /* Host threads that share the narrowing of one Mat in slamb200_upload_desc_packed (row slices; the
  * caller's thread takes one slice too).  Default min(hardware threads, 16); 0 = callers only.  Must
  * be called before the first packed upload. */

@@ -29,6 +29,10 @@ SYMBOLS = {
     "slamb200_upload_desc_pinned": (_i, [_vp, _i, _vp, _i, _sz, _pp]),
     "slamb200_upload_desc_packed": (_i, [_vp, _i, _vp, _i, _sz, _pp]),
     "slamb200_set_pack_threads": (_i, [_vp, _i]),
+    "slamb200_upload_desc_shared": (_i, [_vp, _i, _vp, _i, _sz, _pp]),
+    "slamb200_desc_export": (_i, [_vp, _vp, _vp]),
+    "slamb200_desc_import": (_i, [_vp, _vp, _pp]),
+    "slamb200_desc_localize": (_i, [_vp, _vp, _pp]),
     "slamb200_free_desc": (_i, [_vp, _vp]),
     "slamb200_desc_rows": (_i, [_vp]),
     "slamb200_desc_kind": (_i, [_vp]),

@@ -434,9 +434,29 @@ static void pin_release(slamb200_ctx* c, slamb200_ctx::PinBuf* b, cudaStream_t a
   b->busy = false;
 }
 
+// one SIFT slab: f32 | bf16 | bf16lo | augq | augt | u8 | nrm2 | nrmf | flags  (256-byte aligned)
+static size_t sift_slab_bytes(size_t np) { return np * (512 + 256 + 256 + 32 + 32 + 128 + 4 + 4) + 256; }
+static void sift_slab_point(slamb200_desc* d) {
+  const size_t np = (size_t)d->n_pad;
+  const size_t o_f32 = 0, o_bf16 = o_f32 + np * 512, o_lo = o_bf16 + np * 256,
+               o_augq = o_lo + np * 256, o_augt = o_augq + np * 32, o_u8 = o_augt + np * 32,
+               o_nrm = o_u8 + np * 128, o_nrmf = o_nrm + np * 4, o_flags = o_nrmf + np * 4;
+  char* base = (char*)d->slab;
+  d->f32 = (float*)(base + o_f32);
+  d->bf16 = (__nv_bfloat16*)(base + o_bf16);
+  d->augq = (__nv_bfloat16*)(base + o_augq);
+  d->augt = (__nv_bfloat16*)(base + o_augt);
+  d->u8 = (uint8_t*)(base + o_u8);
+  d->nrm2 = (int32_t*)(base + o_nrm);
+  d->bf16lo = (__nv_bfloat16*)(base + o_lo);
+  d->nrmf = (float*)(base + o_nrmf);
+  d->flags = (int32_t*)(base + o_flags);
+}
+
 static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_t row_stride,
                        bool src_on_device, cudaStream_t producer, bool no_sync,
-                       slamb200_desc** out, slamb200_ctx::PinBuf* packed = nullptr) {
+                       slamb200_desc** out, slamb200_ctx::PinBuf* packed = nullptr,
+                       bool shared = false) {
   if (!c || !out) return fail(SLAMB200_ERR_INVALID, "upload_desc: NULL argument");
   *out = nullptr;
   if (kind != SLAMB200_DESC_F32X128 && kind != SLAMB200_DESC_U8X32)
@@ -480,8 +500,12 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   if (!d->ready) { rc = fail(SLAMB200_ERR_CUDA, "cudaEventCreate failed"); goto done; }
   if (kind == SLAMB200_DESC_U8X32) {
     d->slab_bytes = (size_t)d->n_pad * 32;
-    if (!(d->slab = slab_from_cache(c, d->slab_bytes, s)))
+    if (shared) {
+      DCU(cudaMalloc(&d->slab, d->slab_bytes));
+      d->shared = 1;
+    } else if (!(d->slab = slab_from_cache(c, d->slab_bytes, s))) {
       if ((rc = dev_alloc(c, &d->slab, d->slab_bytes, s))) goto done;
+    }
     d->u8 = (uint8_t*)d->slab;
     if (d->n_pad > n) DCU(cudaMemsetAsync(d->u8 + (size_t)n * 32, 0, (size_t)(d->n_pad - n) * 32, s));
     if (n > 0) {
@@ -490,25 +514,17 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
       else DCU(cudaMemcpy2DAsync(d->u8, 32, rows, row_stride, 32, n, k, s));
     }
   } else {
-    // one slab: f32 | bf16 | bf16lo | augq | augt | u8 | nrm2 | nrmf | flags  (256-byte aligned)
-    const size_t np = d->n_pad;
-    const size_t o_f32 = 0, o_bf16 = o_f32 + np * 512, o_lo = o_bf16 + np * 256,
-                 o_augq = o_lo + np * 256, o_augt = o_augq + np * 32, o_u8 = o_augt + np * 32,
-                 o_nrm = o_u8 + np * 128, o_nrmf = o_nrm + np * 4, o_flags = o_nrmf + np * 4,
-                 total = o_flags + 256;
+    const size_t total = sift_slab_bytes(d->n_pad);
     d->slab_bytes = total;
-    if (!(d->slab = slab_from_cache(c, total, s)))
+    if (shared) {
+      // exportable over CUDA IPC: a plain allocation of its own (pool memory cannot be exported
+      // with cudaIpcGetMemHandle)
+      DCU(cudaMalloc(&d->slab, total));
+      d->shared = 1;
+    } else if (!(d->slab = slab_from_cache(c, total, s))) {
       if ((rc = dev_alloc(c, &d->slab, total, s))) goto done;
-    char* base = (char*)d->slab;
-    d->f32 = (float*)(base + o_f32);
-    d->bf16 = (__nv_bfloat16*)(base + o_bf16);
-    d->augq = (__nv_bfloat16*)(base + o_augq);
-    d->augt = (__nv_bfloat16*)(base + o_augt);
-    d->u8 = (uint8_t*)(base + o_u8);
-    d->nrm2 = (int32_t*)(base + o_nrm);
-    d->bf16lo = (__nv_bfloat16*)(base + o_lo);
-    d->nrmf = (float*)(base + o_nrmf);
-    d->flags = (int32_t*)(base + o_flags);
+    }
+    sift_slab_point(d);
     DCU(cudaMemsetAsync(d->flags, 0, 16, s));
     const float* prep_src = d->f32;
     size_t prep_stride = 128;
@@ -644,6 +660,125 @@ extern "C" int slamb200_upload_desc_packed(slamb200_ctx* c, int kind, const void
   return rc;
 }
 
+// ---- descriptor sets across processes (one process per GPU): CUDA IPC over NVLink --------------
+extern "C" int slamb200_upload_desc_shared(slamb200_ctx* c, int kind, const void* rows, int n,
+                                           size_t row_stride, slamb200_desc** out) {
+  return desc_create(c, kind, rows, n, row_stride, false, nullptr, false, out, nullptr, true);
+}
+
+extern "C" int slamb200_desc_export(slamb200_ctx* c, const slamb200_desc* d, slamb200_desc_ipc* out) {
+  if (!c || !d || !out) return fail(SLAMB200_ERR_INVALID, "desc_export: NULL argument");
+  if (!d->shared) return fail(SLAMB200_ERR_INVALID, "desc_export: the set was not created with slamb200_upload_desc_shared");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(d->ready));   // the importer has no event to wait on
+  memset(out, 0, sizeof(*out));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, d->slab));
+  static_assert(sizeof(h) == sizeof(out->handle), "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out->handle, &h, sizeof(h));
+  out->kind = d->kind;
+  out->n = d->n;
+  out->n_pad = d->n_pad;
+  out->device = c->device;
+  out->slab_bytes = (unsigned long long)d->slab_bytes;
+  out->exact = slamb200_desc_exact_mode(d);
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_desc_import(slamb200_ctx* c, const slamb200_desc_ipc* in, slamb200_desc** out) {
+  if (!c || !in || !out) return fail(SLAMB200_ERR_INVALID, "desc_import: NULL argument");
+  *out = nullptr;
+  if (in->kind != SLAMB200_DESC_F32X128 && in->kind != SLAMB200_DESC_U8X32)
+    return fail(SLAMB200_ERR_KIND, "desc_import: unknown descriptor kind %d", in->kind);
+  if (in->n < 0 || in->n_pad < in->n || in->n_pad % SLAMB200_TILE_PAD)
+    return fail(SLAMB200_ERR_INVALID, "desc_import: bad sizes");
+  const size_t want = in->kind == SLAMB200_DESC_F32X128 ? sift_slab_bytes((size_t)in->n_pad) : (size_t)in->n_pad * 32;
+  if (in->slab_bytes != want) return fail(SLAMB200_ERR_INVALID, "desc_import: slab size mismatch");
+  CU(cudaSetDevice(c->device));
+  slamb200_desc* d = (slamb200_desc*)aligned_alloc(64, (sizeof(slamb200_desc) + 63) / 64 * 64);
+  if (!d) return fail(SLAMB200_ERR_NOMEM, "host allocation failed");
+  memset(d, 0, sizeof(slamb200_desc));
+  d->kind = in->kind;
+  d->n = in->n;
+  d->n_pad = in->n_pad;
+  d->slab_bytes = want;
+  d->imported = 1;
+  d->host_exact = in->kind == SLAMB200_DESC_F32X128 ? (in->exact == 1 ? 1 : 0) : -2;
+  d->ready_seen = 1;   // the exporter synchronised on its prep kernels
+  cudaIpcMemHandle_t h;
+  memcpy(&h, in->handle, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(&d->slab, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    free(d);
+    return fail(SLAMB200_ERR_CUDA, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+  }
+  if (d->kind == SLAMB200_DESC_U8X32) {
+    d->u8 = (uint8_t*)d->slab;
+  } else {
+    sift_slab_point(d);
+    if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->bf16lo, d->n_pad, d->tmaps) != 0) {
+      cudaIpcCloseMemHandle(d->slab);
+      free(d);
+      return fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed on the peer mapping");
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lk(c->free_mu);
+    d->ready = event_get(c);   // never recorded: queries as complete
+  }
+  *out = d;
+  return SLAMB200_OK;
+}
+
+// A local copy of a (peer-mapped) set: one device-to-device transfer of the prepared slab over
+// NVLink, no second prep pass.
+extern "C" int slamb200_desc_localize(slamb200_ctx* c, const slamb200_desc* src, slamb200_desc** out) {
+  if (!c || !src || !out) return fail(SLAMB200_ERR_INVALID, "desc_localize: NULL argument");
+  *out = nullptr;
+  CU(cudaSetDevice(c->device));
+  slamb200_desc* d = (slamb200_desc*)aligned_alloc(64, (sizeof(slamb200_desc) + 63) / 64 * 64);
+  if (!d) return fail(SLAMB200_ERR_NOMEM, "host allocation failed");
+  memcpy(d, src, sizeof(slamb200_desc));
+  d->imported = 0;
+  d->shared = 0;
+  d->slab = nullptr;
+  d->ready = nullptr;
+  d->ready_seen = 0;
+  int rc = SLAMB200_OK;
+  {
+    LaneGuard g(c, /*upload=*/true);
+    Lane& L = g.lane();
+    cudaStream_t s = L.stream;
+    if (!(d->slab = slab_from_cache(c, d->slab_bytes, s))) rc = dev_alloc(c, &d->slab, d->slab_bytes, s);
+    if (rc == SLAMB200_OK) {
+      if (!src->ready_seen && cudaStreamWaitEvent(s, src->ready, 0) != cudaSuccess) rc = SLAMB200_ERR_CUDA;
+      if (cudaMemcpyAsync(d->slab, src->slab, d->slab_bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        rc = fail(SLAMB200_ERR_CUDA, "desc_localize: peer copy failed");
+      {
+        std::lock_guard<std::mutex> lk(c->free_mu);
+        d->ready = event_get(c);
+      }
+      if (rc == SLAMB200_OK && (!d->ready || cudaEventRecord(d->ready, s) != cudaSuccess)) rc = SLAMB200_ERR_CUDA;
+      cudaEventRecord(L.done, s);
+    }
+  }
+  if (rc == SLAMB200_OK) {
+    if (d->kind == SLAMB200_DESC_U8X32) {
+      d->u8 = (uint8_t*)d->slab;
+    } else {
+      sift_slab_point(d);
+      if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->bf16lo, d->n_pad, d->tmaps) != 0)
+        rc = fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    }
+  }
+  if (rc != SLAMB200_OK) {
+    slamb200_free_desc(c, d);
+    return rc;
+  }
+  *out = d;
+  return SLAMB200_OK;
+}
+
 extern "C" int slamb200_set_pack_threads(slamb200_ctx* c, int n) {
   if (!c || n < 0 || n > 256) return fail(SLAMB200_ERR_INVALID, "set_pack_threads: bad argument");
   if (!c->pack_pool.th.empty()) return fail(SLAMB200_ERR_INVALID, "set_pack_threads: the pool is already running");
@@ -738,7 +873,15 @@ extern "C" int slamb200_free_desc(slamb200_ctx* c, slamb200_desc* d) {
   // Work this context queued that may still read the set drains first (stream-ordered, the host
   // does not wait).  Work the caller queued on its own streams through the *_enqueue entry
   // points must have been recorded by them (it is: every enqueue records the lane's event).
-  if (d->slab) free_behind_lanes(c, d->slab, d->slab_bytes);
+  if (d->slab && (d->imported || d->shared)) {
+    // peer mappings and exportable allocations are released synchronously, behind everything the
+    // context has queued (rare: once per frame of a sharded window)
+    for (int i = 0; i < N_LANES; i++) cudaStreamSynchronize(c->lanes[i].stream);
+    if (d->imported) cudaIpcCloseMemHandle(d->slab);
+    else cudaFree(d->slab);
+  } else if (d->slab) {
+    free_behind_lanes(c, d->slab, d->slab_bytes);
+  }
   if (d->ready) {
     std::lock_guard<std::mutex> lk(c->free_mu);
     event_put(c, d->ready);

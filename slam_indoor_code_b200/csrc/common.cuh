@@ -41,6 +41,8 @@ struct slamb200_desc {
   cudaEvent_t ready;   // recorded after the prep kernels
   void* slab;          // the one device allocation all the pointers above live in
   size_t slab_bytes;
+  int shared;          // 1: the slab is a plain cudaMalloc allocation (exportable over CUDA IPC)
+  int imported;        // 1: the slab is another process's allocation mapped here (peer memory)
   alignas(64) unsigned char tmaps[512];  // host copies of 4 CUtensorMaps: main, augq, augt, lo
 };
 

@@ -115,7 +115,8 @@ class Context:
         stride = desc.strides[0] if desc.shape[0] > 1 else width * desc.itemsize
         h = ctypes.c_void_p()
         fn = {False: self._lib.slamb200_upload_desc, True: self._lib.slamb200_upload_desc_pinned,
-              "packed": self._lib.slamb200_upload_desc_packed}[_pinned]
+              "packed": self._lib.slamb200_upload_desc_packed,
+              "shared": self._lib.slamb200_upload_desc_shared}[_pinned]
         check(fn(self._h, kind, ptr(desc), desc.shape[0], stride, ctypes.byref(h)))
         return DescriptorSet(self, h, desc.shape[0], kind)
 
@@ -133,6 +134,27 @@ class Context:
         element verified) so that a quarter of the bytes cross PCIe; `desc` is consumed on return.
         Anything else takes upload()'s path.  Same results as upload()."""
         return self.upload(desc, kind, _pinned="packed")
+
+    # -- sets shared between the ranks of a node (one process per GPU; CUDA IPC over NVLink) --------
+    def upload_shared(self, desc, kind=None):
+        """Like upload(), into an allocation other processes can map (export_ipc / import_ipc)."""
+        return self.upload(desc, kind, _pinned="shared")
+
+    def import_ipc(self, record):
+        """A peer rank's exported set (the 128 bytes of DescriptorSet.export_ipc()) as a handle
+        on this rank: its prepared operands are read over NVLink by whatever kernel uses it."""
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(bytes(record))
+        h = ctypes.c_void_p()
+        check(self._lib.slamb200_desc_import(self._h, ctypes.byref(buf), ctypes.byref(h)))
+        n = int(self._lib.slamb200_desc_rows(h))
+        kind = int(self._lib.slamb200_desc_kind(h))
+        return DescriptorSet(self, h, n, kind)
+
+    def localize(self, ds):
+        """A local copy of a (peer-mapped) set: one device-to-device transfer of the prepared slab."""
+        h = ctypes.c_void_p()
+        check(self._lib.slamb200_desc_localize(self._h, ds._h, ctypes.byref(h)))
+        return DescriptorSet(self, h, ds.n, ds.kind)
 
     def upload_device(self, dev_ptr, n, kind, row_stride=0, stream=None):
         """Rows already resident on this device (raw pointer, e.g. torch.Tensor.data_ptr())."""
@@ -236,6 +258,13 @@ class DescriptorSet:
     @property
     def exact_mode(self):
         return int(self._ctx._lib.slamb200_desc_exact_mode(self._h))
+
+    def export_ipc(self):
+        """128-byte record another rank of the node can pass to Context.import_ipc (the set must
+        come from upload_shared and stay alive until the importers have freed their mappings)."""
+        buf = (ctypes.c_ubyte * 128)()
+        check(self._ctx._lib.slamb200_desc_export(self._ctx._h, self._h, ctypes.byref(buf)))
+        return bytes(buf)
 
     def free(self):
         if self._h and self._ctx._h:

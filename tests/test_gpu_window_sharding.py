@@ -1,5 +1,6 @@
 """GPU: the keyframe window sharded over ranks -- NCCL all-gather of the frames'
-descriptor rows, device-to-device descriptor sets, round-robin pairs -- equals the single-process
+descriptor rows, device-to-device descriptor sets, round-robin pairs, and the fused form that reads
+the other ranks' prepared operands over NVLink through CUDA IPC -- equals the single-process
 slamb200_match_window.  Runs with as many ranks as the box has GPUs (1 on the round-end box: the
 NCCL path, the device uploads and the pair deal are still exercised), capped at 4."""
 import json
@@ -36,6 +37,10 @@ for matcher, F, sizes in ((MatcherType.SIFT_BF, 6, [3000, 2500, 1, 2049, 0, 4100
         frames = [synth.sift_train_from_query(base, max(s, 1), 4201 + f)[:s] for f, s in enumerate(sizes)]
     local_frames = {f: a for f, a in enumerate(frames) if ws.frame_owner(f, world) == rank}
     out, counts = ws.match_window_on_gpus(ctx, local_frames, F, matcher, 0.7, dist, dev)
+    # the fused form: prepared operands read over NVLink through CUDA IPC, nothing gathered
+    out2, counts2 = ws.match_window_peer(ctx, local_frames, F, matcher, 0.7, dist, dev)
+    ok = ok and counts2 == counts and sorted(out2.keys()) == sorted(out.keys())
+    ok = ok and all(np.array_equal(out2[p], out[p]) for p in out)
     # single-process reference on this rank's own GPU
     sets = [ctx.upload(a) for a in frames]
     ref = ctx.matchWindow(sets, matcher, 0.7)
