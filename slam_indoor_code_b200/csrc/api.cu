@@ -661,6 +661,8 @@ extern "C" int slamb200_upload_desc_packed(slamb200_ctx* c, int kind, const void
 }
 
 // ---- descriptor sets across processes (one process per GPU): CUDA IPC over NVLink --------------
+static_assert(sizeof(slamb200_desc_ipc) == 128, "slamb200_desc_ipc is a 128-byte wire record");
+
 extern "C" int slamb200_upload_desc_shared(slamb200_ctx* c, int kind, const void* rows, int n,
                                            size_t row_stride, slamb200_desc** out) {
   return desc_create(c, kind, rows, n, row_stride, false, nullptr, false, out, nullptr, true);
