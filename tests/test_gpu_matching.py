@@ -525,3 +525,17 @@ def test_packed_upload_from_many_threads(ctx):
     [t.join() for t in th]
     for g, w in zip(got, want):
         assert np.array_equal(g, w)
+
+
+def test_sift_l1_train_set_beyond_packed_key_range(ctx):
+    """More than 2^17 train rows: the byte-wise kernel's packed (distance, index) key no longer
+    fits and the fp32 kernel takes the pair -- same results."""
+    q = synth.sift_like(48, 931)
+    t = synth.sift_like(140000, 932)
+    t[139999] = q[7]                      # an exact copy at the very end of the range
+    t[131072] = q[9]
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.SIFT_BF_L1, q, t)
+    ridx, rdist = c_oracle.l1_knn2(q, t)
+    _check_knn(idx, dist, ridx, rdist)
+    assert idx[7, 0] == 139999 and idx[9, 0] == 131072
+    assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.7))
