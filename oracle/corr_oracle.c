@@ -17,13 +17,19 @@
  *                              src/mainModule/translation/cameraTranslation.cpp:41-46
  *       (OpenCV calib3d five-point.cpp EMEstimatorCallback::computeError +
  *        ptsetreg.cpp RANSACPointSetRegistrator::findInliers / run()).
+ *   - the "next" rows of SURVEY.md 8f, each introduced by its own comment block below:
+ *       solvePnPRansac scoring      src/mainModule/cycleProcessing/mainCycle.cpp:155-159
+ *       NORM_L1 kNN                 src/mainModule/featureMatching/featureMatchingCUDA.cpp:28
+ *       linear triangulation        src/mainModule/triangulation/triangulate.cpp:17-55, :91-108
+ *       ORB descriptors (compute)   src/mainModule/featureMatching/featureMatchingCPU.cpp:45-66
  *
  * Parity pin: the reference ships no tests or golden vectors, so this
  * oracle is pinned against the reference's own arithmetic owner, OpenCV, through the cv2 wheel
  * (tests/test_oracle_vs_cv2.py, and the committed cv2-generated fixtures in tests/golden/ made by
  * oracle/gen_golden.py).
  *
- * Build: see oracle/Makefile (-O2 -ffp-contract=off: no FMA contraction anywhere in here).
+ * Build: see oracle/Makefile (-O2 -ffp-contract=off: no FMA contraction anywhere in here; the one
+ * place OpenCV's own code fuses -- ORB's float blur -- calls fmaf explicitly).
  */
 #include <math.h>
 #include <stdint.h>
