@@ -106,3 +106,108 @@ def score_essential(pts1, pts2, K4, E, threshold_px):
             best, bc = h, int(counts[h])
     best_mask = masks[best] if best >= 0 else np.zeros(masks.shape[1], np.uint8)
     return counts, best, best_mask, masks
+
+
+# ---- the "next" rows of SURVEY.md 8f, restated a second time ---------------------------------------
+def l1_dist_matrix(Q, T, block=64):
+    """cv::BFMatcher(NORM_L1): s += |d0| + |d1| + |d2| + |d3| over groups of four, in float
+    (featureMatchingCUDA.cpp:28 is the mode; the CPU matcher owns the arithmetic)."""
+    Q = np.asarray(Q, np.float32).reshape(-1, 128)
+    T = np.asarray(T, np.float32).reshape(-1, 128)
+    out = np.empty((Q.shape[0], T.shape[0]), np.float32)
+    for s in range(0, Q.shape[0], block):
+        a = np.abs(Q[s:s + block, None, :] - T[None, :, :]).reshape(-1, T.shape[0], 32, 4)
+        acc = np.zeros(a.shape[:2], np.float32)
+        for g in range(32):
+            acc = acc + (((a[:, :, g, 0] + a[:, :, g, 1]) + a[:, :, g, 2]) + a[:, :, g, 3])
+        out[s:s + block] = acc
+    return out
+
+
+def project_points(obj, K4, dist, pose):
+    """cv::projectPoints in cvProjectPoints2Internal's operation order (mainCycle.cpp:155-159 ->
+    PnPRansacCallback::computeError); pose = R row-major (9) + t (3)."""
+    k = np.zeros(12)
+    if dist is not None:
+        d = np.asarray(dist, np.float64).reshape(-1)
+        k[:min(len(d), 12)] = d[:12]
+    fx, fy, cx, cy = (float(v) for v in K4)
+    R = np.asarray(pose, np.float64)[:9].reshape(3, 3)
+    t = np.asarray(pose, np.float64)[9:]
+    X = np.asarray(obj, np.float32).reshape(-1, 3).astype(np.float64)
+    x = R[0, 0] * X[:, 0] + R[0, 1] * X[:, 1] + R[0, 2] * X[:, 2] + t[0]
+    y = R[1, 0] * X[:, 0] + R[1, 1] * X[:, 1] + R[1, 2] * X[:, 2] + t[1]
+    z = R[2, 0] * X[:, 0] + R[2, 1] * X[:, 1] + R[2, 2] * X[:, 2] + t[2]
+    with np.errstate(all="ignore"):
+        z = np.where(z != 0, 1.0 / z, 1.0)
+        x, y = x * z, y * z
+        r2 = x * x + y * y
+        r4 = r2 * r2
+        r6 = r4 * r2
+        a1 = 2 * x * y
+        a2 = r2 + 2 * x * x
+        a3 = r2 + 2 * y * y
+        cdist = 1 + k[0] * r2 + k[1] * r4 + k[4] * r6
+        icdist2 = 1.0 / (1 + k[5] * r2 + k[6] * r4 + k[7] * r6)
+        xd0 = x * cdist * icdist2 + k[2] * a1 + k[3] * a2 + k[8] * r2 + k[9] * r4
+        yd0 = y * cdist * icdist2 + k[2] * a3 + k[3] * a1 + k[10] * r2 + k[11] * r4
+        return np.stack([xd0 * fx + cx, yd0 * fy + cy], 1).astype(np.float32)
+
+
+def score_pnp(obj, img, K4, dist, poses, reproj_err, model_points=5):
+    """counts[H], best (-1: none above model_points-1), best mask, all masks [H, M]."""
+    img = np.asarray(img, np.float32).reshape(-1, 2)
+    poses = np.asarray(poses, np.float64).reshape(-1, 12)
+    t = np.float32(reproj_err * reproj_err)
+    masks = np.zeros((len(poses), len(img)), np.uint8)
+    with np.errstate(all="ignore"):
+        for h, pose in enumerate(poses):
+            d = img - project_points(obj, K4, dist, pose)        # float32
+            err = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]          # float accumulator
+            masks[h] = err <= t
+    counts = masks.sum(1).astype(np.int32)
+    best, bc = -1, 0
+    for h, c in enumerate(counts):
+        if c > max(bc, model_points - 1):
+            best, bc = h, int(c)
+    return counts, best, (masks[best] if best >= 0 else np.zeros(len(img), np.uint8)), masks
+
+
+def orb_compute(image, kps, pattern):
+    """cv::ORB::compute on given keypoints (featureMatchingCPU.cpp:45-66): `pattern` is the
+    [256, 4] table of csrc/orb_pattern.h.  Needs cv2 only for the reflect-101 padding."""
+    import cv2
+    image = np.asarray(image, np.uint8)
+    if image.ndim == 3:
+        b, g, r = (image[..., i].astype(np.int64) for i in range(3))
+        gray = ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
+    else:
+        gray = image
+    H, W = gray.shape
+    v = np.exp(-0.125 * (np.arange(7) - 3.0) ** 2)
+    k = (v * (1.0 / v.sum())).astype(np.float32)
+
+    def fma(a, b, c):   # exact product in float64, one rounding of the sum (float32 operands)
+        return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(np.float32)
+
+    P = cv2.copyMakeBorder(gray, 3, 3, 3, 3, cv2.BORDER_REFLECT_101).astype(np.float32)
+    s = (P[:, 0:W] * k[0]).astype(np.float32)
+    for j in range(1, 7):
+        s = fma(P[:, j:j + W], k[j], s)
+    c = (s[3:3 + H] * k[3]).astype(np.float32)
+    for j in range(1, 4):
+        c = fma((s[3 + j:3 + j + H] + s[3 - j:3 - j + H]).astype(np.float32), k[3 + j], c)
+    blur = np.clip(np.rint(c), 0, 255).astype(np.uint8)
+    kps = np.asarray(kps, np.float32).reshape(-1, 3)
+    cx, cy = np.rint(kps[:, 0]).astype(np.int64), np.rint(kps[:, 1]).astype(np.int64)
+    keep = (cx >= 31) & (cx < W - 31) & (cy >= 31) & (cy < H - 31)
+    ang = (kps[keep, 2] * np.float32(np.pi / 180.0)).astype(np.float32)
+    a, b = np.cos(ang.astype(np.float64)).astype(np.float32), np.sin(ang.astype(np.float64)).astype(np.float32)
+    pat = np.asarray(pattern, np.float32)
+    bits = []
+    for e in range(2):
+        px, py = pat[None, :, 2 * e], pat[None, :, 2 * e + 1]
+        xr = (px * a[:, None]).astype(np.float32) - (py * b[:, None]).astype(np.float32)
+        yr = (px * b[:, None]).astype(np.float32) + (py * a[:, None]).astype(np.float32)
+        bits.append(blur[cy[keep, None] + np.rint(yr).astype(np.int64), cx[keep, None] + np.rint(xr).astype(np.int64)])
+    return keep.astype(np.uint8), np.packbits(bits[0] < bits[1], axis=1, bitorder="little")

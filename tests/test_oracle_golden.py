@@ -187,3 +187,28 @@ def test_orb_descriptor_oracle_matches_cv2(golden_dir):
     keep, desc = c_oracle.orb_compute(g["frame"], g["kps"])
     assert np.array_equal(g["kps"][keep.astype(bool), :2], g["kept_xy"])
     assert np.array_equal(desc, g["desc"]) and len(desc) > 150
+
+
+# ---- the next rows restated twice: the C oracle against the independent NumPy statement -----------
+def test_c_and_np_oracles_agree_on_next_rows(golden_dir):
+    import re
+    from oracle import synth
+    q, t = synth.float_pair(90, 130, 601)
+    idx, dist = np_oracle.knn2_from_matrix(np_oracle.l1_dist_matrix(q, t))
+    ci, cd = c_oracle.l1_knn2(q, t)
+    assert np.array_equal(idx, ci) and np.array_equal(dist.view(np.int32), cd.view(np.int32))
+    obj, img, R, tt = synth.pnp_scene(700, 602)
+    poses = synth.pnp_hypotheses(24, R, tt, 603)
+    for dist_c in (synth.REF_DIST5, None, (0.1, -0.2, 1e-3, -1e-3, 0.05, 0.01, -0.02, 0.003, 1e-3, 0, 2e-4, 0)):
+        a = c_oracle.score_pnp(obj, img, synth.SAMSUNG_HV_4K, dist_c, poses, 8.0, want_all_masks=True)
+        b = np_oracle.score_pnp(obj, img, synth.SAMSUNG_HV_4K, dist_c, poses, 8.0)
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2])
+        assert np.array_equal(a[3], b[3])
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = np.array([[int(v) for v in re.findall(r"-?\d+", l)]
+                    for l in open(os.path.join(here, "slam_indoor_code_b200", "csrc", "orb_pattern.h"))
+                    if l.strip().startswith("{")])
+    g = np.load(os.path.join(golden_dir, "orb_desc.npz"))
+    keep, desc = np_oracle.orb_compute(g["frame"], g["kps"], pat)
+    ck, cdsc = c_oracle.orb_compute(g["frame"], g["kps"])
+    assert np.array_equal(keep, ck) and np.array_equal(desc, cdsc) and np.array_equal(desc, g["desc"])
