@@ -84,7 +84,8 @@ int slamb200_synchronize(slamb200_ctx* ctx);
 
 /* ---- descriptor sets: replaces the per-call cuda::GpuMat uploads of
  *      featureMatchingCUDA.cpp:98-99 with "upload once per frame" ----------------------- */
-/* rows: host pointer to n rows of the kind's type, row_stride bytes apart (cv::Mat::step). */
+/* rows: host pointer to n rows of the kind's type, row_stride bytes apart (cv::Mat::step).  The
+ * rows are consumed when the call returns.  (Implemented by slamb200_upload_desc_packed below.) */
 int slamb200_upload_desc(slamb200_ctx* ctx, int kind, const void* rows, int n, size_t row_stride,
                          slamb200_desc** out);
 /* Same, but `rows` is a device pointer on the context's device (bytes already in HBM);

@@ -585,9 +585,14 @@ done:
 #undef DCU
 }
 
+extern "C" int slamb200_upload_desc_packed(slamb200_ctx* c, int kind, const void* rows, int n,
+                                           size_t row_stride, slamb200_desc** out);
+// The plain upload IS the narrowing upload: same contract (rows consumed on return), same
+// results, a quarter of the PCIe bytes for the Mats cv::SIFT produces, and page-locked staging
+// instead of a pageable copy; anything that does not narrow losslessly takes the fp32 copy.
 extern "C" int slamb200_upload_desc(slamb200_ctx* c, int kind, const void* rows, int n,
                                     size_t row_stride, slamb200_desc** out) {
-  return desc_create(c, kind, rows, n, row_stride, false, nullptr, false, out);
+  return slamb200_upload_desc_packed(c, kind, rows, n, row_stride, out);
 }
 
 extern "C" int slamb200_upload_desc_pinned(slamb200_ctx* c, int kind, const void* rows, int n,

@@ -45,6 +45,8 @@ __attribute__((target("avx2"))) static int pack_rows_avx2(const float* src, size
     h = _mm_add_epi32(h, _mm_shuffle_epi32(h, 0x4e));
     h = _mm_add_epi32(h, _mm_shuffle_epi32(h, 0xb1));
     norm_bad |= _mm_cvtsi128_si32(h) >= (1 << 20);
+    // a Mat of general floats is recognised within its first rows: stop reading it
+    if ((r & 63) == 63 && (norm_bad || !_mm256_testz_si256(bad, bad))) return 0;
   }
   return _mm256_testz_si256(bad, bad) && !norm_bad;
 }
