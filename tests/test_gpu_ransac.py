@@ -147,3 +147,25 @@ def test_find_essential_mat_drop_in(ctx, m, noise, outl, seed):
     E, mask = ct.findEssentialMat(ctx, p1, p2, Kmat, 0.999, 5.0)
     assert np.array_equal(np.asarray(Ecv, np.float64).reshape(3, 3), E)
     assert np.array_equal(mcv, mask)
+
+
+def test_cfg5_full_batch_properties(ctx):
+    """BASELINE cfg5 at full size: 210 pairs x 2048 hypotheses x 5000 matches in one call; sampled
+    pairs against the oracle, and the size-independent properties on all of them (the winner has
+    the maximal count, first best wins, its mask sums to its count)."""
+    P, H, M = 210, 2048, 5000
+    p1s, p2s, Es = [], [], []
+    base = [synth.two_view(M, 5000 + k) for k in range(6)]
+    hyp = [synth.pose_hypotheses(H, b[2], b[3], 5100 + k) for k, b in enumerate(base)]
+    for p in range(P):
+        p1s.append(base[p % 6][0]); p2s.append(base[p % 6][1]); Es.append(hyp[p % 6])
+    counts, best, masks = ct.scoreEssentialBatch(ctx, p1s, p2s, K4, np.stack(Es), 5.0)
+    assert counts.shape == (P, H)
+    for p in (0, 1, 5, 100, 209):
+        rc, rb, rm, _ = c_oracle.score_essential(p1s[p], p2s[p], K4, Es[p], 5.0)
+        assert np.array_equal(counts[p], rc) and best[p] == rb and np.array_equal(masks[p], rm)
+    for p in range(P):
+        b = int(best[p])
+        assert b == int(np.argmax(counts[p])) and counts[p, b] > 4
+        assert int(masks[p].sum()) == int(counts[p, b])
+        assert np.array_equal(counts[p], counts[p % 6])          # identical inputs, identical counts
