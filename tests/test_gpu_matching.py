@@ -539,3 +539,30 @@ def test_sift_l1_train_set_beyond_packed_key_range(ctx):
     _check_knn(idx, dist, ridx, rdist)
     assert idx[7, 0] == 139999 and idx[9, 0] == 131072
     assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.7))
+
+
+def test_cfg3_full_window_properties(ctx):
+    """BASELINE cfg3 at full size: one 10k-row query frame against 210 train frames in one call.
+    Size-independent properties on every pair, the oracle on sampled pairs and rows."""
+    q = synth.sift_like(10000, 3000)
+    trains = [synth.sift_train_from_query(q, 10000, 3001 + p) for p in range(210)]
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(t) for t in trains]
+    res = ctx.matchBatch(Q, Ts, MatcherType.SIFT_BF, 0.7)
+    assert len(res) == 210
+    for p, m in enumerate(res):
+        assert 2000 < len(m) <= 10000, p                       # the planted correspondences are found
+        assert np.all(np.diff(m["queryIdx"]) > 0) and np.all(m["imgIdx"] == 0)
+        assert m["trainIdx"].min() >= 0 and m["trainIdx"].max() < 10000
+    rows = np.random.default_rng(9).choice(10000, 250, replace=False)
+    for p in (0, 104, 209):
+        ridx, rdist = c_oracle.l2_knn2(q[rows], trains[p])
+        want = c_oracle.ratio_test(ridx, rdist, 0.7)
+        got = res[p][np.isin(res[p]["queryIdx"], rows)]
+        order = {int(r): k for k, r in enumerate(rows)}
+        got_local = np.array(sorted((order[int(g["queryIdx"])], int(g["trainIdx"]), float(g["distance"])) for g in got))
+        want_local = np.array(sorted((int(w["queryIdx"]), int(w["trainIdx"]), float(w["distance"])) for w in want))
+        assert np.array_equal(got_local, want_local), p
+        assert np.array_equal(res[p], ctx.matchFeatures(Q, Ts[p], MatcherType.SIFT_BF, 0.7))
+    for t in Ts:
+        t.free()
