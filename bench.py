@@ -266,6 +266,16 @@ def run_b200(args, rank, world, local):
     log(f"[rank {rank}] generated {len(trains)} train frames in {time.perf_counter() - t_gen:.1f}s")
 
     ctx = Context(local)
+    # host cores this rank may use: the ranks of a node share them.  The library's pack pool is
+    # sized before the first upload (every upload narrows integer-valued Mats on the host).
+    cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    if args.e2e_upload == "auto":
+        # for the e2e pipeline narrowing pays once a rank has enough cores to outrun PCIe (about
+        # eight); otherwise the fp32 Mats go over the link as they are
+        args.e2e_upload = "packed" if cores >= 8 else "pinned"
+    pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else \
+        max(0, min(cores, 16) - args.e2e_workers)
+    ctx.set_pack_threads(pack_threads)
     # A real (non-default) stream: the C ABI treats a NULL stream as "the lane's own stream", so
     # the kernels and the CUDA events that time them must share an explicit stream handle.
     tstream = torch.cuda.Stream(device=dev)
@@ -369,18 +379,7 @@ def run_b200(args, rank, world, local):
     n_buf = np.zeros(max(len(trains), 1), np.int32)
     pool = ThreadPoolExecutor(n_workers)
 
-    # host cores this rank may use: the ranks of a node share them
-    cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
-    if args.e2e_upload == "auto":
-        # narrowing pays once a rank has enough cores to outrun PCIe (about eight); otherwise the
-        # fp32 Mats go over the link as they are
-        args.e2e_upload = "packed" if cores >= 8 else "pinned"
     up = ctx.upload_packed if args.e2e_upload == "packed" else ctx.upload_pinned
-    pack_threads = 0
-    if args.e2e_upload == "packed":
-        pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else \
-            max(0, min(cores, 16) - args.e2e_workers)
-        ctx.set_pack_threads(pack_threads)
     # bytes that cross PCIe per step: the fp32 Mats as they are, or their verified byte images
     h2d = (len(trains) + 1) * N_ROWS * (128 if args.e2e_upload == "packed" else 512)
 
@@ -496,7 +495,7 @@ def run_b200(args, rank, world, local):
                     "d2h_bytes_per_step": int(io[1].item()), "steps": e2e_steps,
                     "warmup_steps_run": len(warm_t), "upload": args.e2e_upload, "host_mat_bytes_per_step": (N_PAIRS + world) * N_ROWS * 512,
                     "host_threads": {"uploaders": args.e2e_workers, "matchers": args.e2e_matchers,
-                                     "pack_pool": pack_threads},
+                                     "pack_pool": pack_threads if args.e2e_upload == "packed" else 0},
                     "timing": "host wall clock between device synchronisations, max over ranks",
                     "results_equal_device_resident_run": bool(same)},
             "gpu_launches": int(launches.item()),

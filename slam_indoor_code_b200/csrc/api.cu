@@ -171,6 +171,7 @@ struct slamb200_ctx {
   } pack_pool;
   std::once_flag pack_once;
   int pack_threads = -1;  // -1: min(hardware threads, 16)
+  bool pack_started = false;
   int sub_batch = 0;  // debug: pairs per tcgen05 launch when pipelining against the rerank
   int use_tc = 1;  // debug switch (slamb200_dbg_set_tc): 0 routes exact-mode pairs to the fp32 kernel
 };
@@ -621,6 +622,7 @@ extern "C" int slamb200_upload_desc_packed(slamb200_ctx* c, int kind, const void
       nthr = nthr > 16 ? 16 : nthr;
     }
     c->pack_pool.start(nthr > 0 ? nthr : 0);
+    c->pack_started = true;
   });
   int exact = 1;
   {
@@ -788,7 +790,11 @@ extern "C" int slamb200_desc_localize(slamb200_ctx* c, const slamb200_desc* src,
 
 extern "C" int slamb200_set_pack_threads(slamb200_ctx* c, int n) {
   if (!c || n < 0 || n > 256) return fail(SLAMB200_ERR_INVALID, "set_pack_threads: bad argument");
-  if (!c->pack_pool.th.empty()) return fail(SLAMB200_ERR_INVALID, "set_pack_threads: the pool is already running");
+  if (!c->pack_pool.th.empty() || c->pack_started)
+    return (int)c->pack_pool.th.size() == n
+               ? SLAMB200_OK
+               : fail(SLAMB200_ERR_INVALID, "set_pack_threads: the pool is already running with %d threads",
+                      (int)c->pack_pool.th.size());
   c->pack_threads = n;
   return SLAMB200_OK;
 }
