@@ -954,7 +954,10 @@ static int check_matcher(int matcher, const slamb200_desc* q, const slamb200_des
 //   [ PairArgs[P] | TcPair[P] | tile_prefix[P+1] | status words (zeroed) ]
 // so a step costs one H2D copy plus the kernels themselves (no memsets, no per-table copies).
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-#define STATUS_BYTES 4096  // [0] self-check flag, [1+k] work-list counts
+static_assert(1024 + SIFT_GEN_FB_ITEMS <= 8192 / 4, "status area too small");
+constexpr size_t FB_PART_BYTES = sizeof(unsigned long long) * 2 * SIFT_GEN_FB_ITEMS;
+#define STATUS_BYTES 8192  // [0] self-check flag, [1+k] work-list counts, [1002] fallback rows,
+                           // [1024 + i] finished segments of fallback row i (split scan)
 
 static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
                          const slamb200_desc* q, const slamb200_desc* const* trains, int n_pairs,
@@ -1050,7 +1053,8 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     if ((rc = buf_reserve(c, L.cand, cand_bytes, s))) return rc;
     if ((rc = buf_reserve(c, L.work, sizeof(uint4) * rows, s))) return rc;
     if ((rc = buf_reserve(c, L.work_v0, sizeof(float2) * rows, s))) return rc;
-    if ((rc = buf_reserve(c, L.fb_list, sizeof(uint2) * rows, s))) return rc;
+    // head: partial keys of the split fallback scan, then the list of fallback rows
+    if ((rc = buf_reserve(c, L.fb_list, FB_PART_BYTES + sizeof(uint2) * rows, s))) return rc;
   }
   char* db = (char*)L.pairs.p;
   const PairArgs* d_pairs = (const PairArgs*)(db + off_pairs);
@@ -1126,8 +1130,9 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         if (grc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
         ProfScope ps(c, s, SLAMB200_K_SIFT_GEN_RERANK);
         launch_sift_gen_rerank(q->flags, q->f32, q->nrmf, nq, d_tc, d_pre, n_pairs, n_cta, n_slots, n_split,
-                               (const uint4*)L.cand_g.p, (uint4*)L.part.p, (uint2*)L.fb_list.p,
-                               d_status + 1002, s);
+                               (const uint4*)L.cand_g.p, (uint4*)L.part.p,
+                               (uint2*)((char*)L.fb_list.p + FB_PART_BYTES), d_status + 1002,
+                               (unsigned long long*)L.fb_list.p, d_status + 1024, s);
       }
       // Sub-batch pipeline (debug knob, default one sub-batch): the tcgen05 kernel of sub-batch
       // k+1 on `s` against the rerank / finalize kernels of sub-batch k on the lane's second

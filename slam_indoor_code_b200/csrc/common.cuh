@@ -195,7 +195,11 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_fl
 void launch_sift_gen_rerank(const int32_t* q_flags, const float* q_f32, const float* q_nrmf, int nq,
                             const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                             int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
-                            uint2* fb_list, int32_t* fb_count, cudaStream_t s);
+                            uint2* fb_list, int32_t* fb_count, unsigned long long* fb_part,
+                            int32_t* fb_done, cudaStream_t s);
+// scratch of the split fallback scan: fb_part holds SIFT_GEN_FB_ITEMS x 2 keys, fb_done
+// SIFT_GEN_FB_ITEMS counters that must be zero when the kernels start
+constexpr int SIFT_GEN_FB_ITEMS = 148 * 4;
 void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
                         const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                         int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,

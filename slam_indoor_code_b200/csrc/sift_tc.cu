@@ -344,21 +344,24 @@ __device__ __forceinline__ void top2_chunk_insert(float g, int gid, float g2nd, 
 // chunks.  gid = column / 8 of the minimum's group, so chunk = gid >> 2.  Strict '<' keeps the
 // earlier chunk on equal values.
 // General-float variant: the accumulators are approximations, so the record keeps the best FOUR
-// chunks and the fifth-best chunk minimum: a lower bound on every column outside those four,
-// which the rerank needs to certify its answer.
+// chunks, the fifth-best chunk minimum (a lower bound on every column outside those four) and
+// the smallest second group minimum of any chunk (with the former: a lower bound on every column
+// outside the best 8-column group of each kept chunk), which the rerank needs to certify its
+// answer after reading 32, or else 128, candidate rows.
 // Epilogue running state of one thread (row x column range).  Exact mode uses m[0..1], i[0..1]
 // and s (second group minimum inside the best chunk); the general-float variant keeps the best
-// FOUR chunks (m[0..3], i[0..3]) and s = the fifth-best chunk minimum, a lower bound on every
-// column outside those four.
+// FOUR chunks (m[0..3], i[0..3]), s = the fifth-best chunk minimum and s2 = the smallest second
+// group minimum over all chunks.
 struct EpiState {
   float m[4];
   int i[4];
-  float s;
+  float s, s2;
   __device__ __forceinline__ void reset() {
     const float inf = __int_as_float(0x7f800000);
 #pragma unroll
     for (int k = 0; k < 4; k++) { m[k] = inf; i[k] = -1; }
     s = inf;
+    s2 = inf;
   }
 };
 
@@ -378,10 +381,16 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0,
   const int j23 = g[3] < g[2] ? gid0 + 3 : gid0 + 2;
   const float cm = fminf(m01, m23);
   const int gid = m23 < m01 ? j23 : j01;
+  const float M01 = fmaxf(g[0], g[1]), M23 = fmaxf(g[2], g[3]);
+  const float c2 = fmin3(fmaxf(m01, m23), M01, M23);  // second smallest of the four
   if (GEN) {
-    // branch-free sorted insert into the best four, the displaced fourth feeds the bound
+    // branch-free sorted insert of the chunk into the best four; the displaced fourth feeds the
+    // bound (s >= m[3] always: s is a minimum over chunks that were not among the four smallest).
+    // s2 = the smallest "second group minimum" of any chunk: together with s it bounds every
+    // column outside the best GROUP of each of the four kept chunks.
     const bool l0 = cm < st.m[0], l1 = cm < st.m[1], l2 = cm < st.m[2], l3 = cm < st.m[3];
     st.s = l3 ? st.m[3] : fminf(st.s, cm);
+    st.s2 = fminf(st.s2, c2);
     st.m[3] = l2 ? st.m[2] : (l3 ? cm : st.m[3]);
     st.i[3] = l2 ? st.i[2] : (l3 ? gid : st.i[3]);
     st.m[2] = l1 ? st.m[1] : (l2 ? cm : st.m[2]);
@@ -391,8 +400,6 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0,
     st.m[0] = l0 ? cm : st.m[0];
     st.i[0] = l0 ? gid : st.i[0];
   } else {
-    const float M01 = fmaxf(g[0], g[1]), M23 = fmaxf(g[2], g[3]);
-    const float c2 = fmin3(fmaxf(m01, m23), M01, M23);  // second smallest of the four
     top2_chunk_insert(cm, gid, c2, st.m[0], st.i[0], st.s, st.m[1], st.i[1]);
   }
 }
@@ -651,12 +658,12 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
         const int slot = COL_SPLITS * ord + half;
         const size_t at = ((size_t)seg_pair * P.n_slots + slot) * P.nq_pad + seg_rb * 2 * BM + row_in_tile;
         if (GEN) {
-          // two 16-byte records: the four chunk minima; their group indices and the bound
+          // two 16-byte records: the four chunk minima; their group indices and the two bounds
           P.cand[2 * at] = make_uint4(__float_as_uint(st.m[0]), __float_as_uint(st.m[1]),
                                       __float_as_uint(st.m[2]), __float_as_uint(st.m[3]));
           P.cand[2 * at + 1] = make_uint4(((uint32_t)st.i[0] & 0xFFFFu) | ((uint32_t)st.i[1] << 16),
                                           ((uint32_t)st.i[2] & 0xFFFFu) | ((uint32_t)st.i[3] << 16),
-                                          __float_as_uint(st.s), 0u);
+                                          __float_as_uint(st.s), __float_as_uint(st.s2));
         } else {
           // {best chunk min, second chunk min, second group min inside the best chunk,
           //  gid of the best | gid of the second << 16}; 0xFFFF = absent (gids fit: T <= 524k rows)
@@ -951,6 +958,8 @@ struct GenParams {
   uint4* part;
   uint2* fb_list;     // rows whose answer could not be certified: {pair, row}
   int32_t* fb_count;
+  unsigned long long* fb_part;   // [FB_GRID][2] partial top-2 keys of the split fallback scan
+  int32_t* fb_done;              // [FB_GRID] finished segments per listed row (zero on entry)
 };
 
 // sqrtf(hal::normL2Sqr_(q, t, 128)) in OpenCV's own summation order (see sift_exact.cu): 4 x 4
@@ -1002,11 +1011,14 @@ __device__ __forceinline__ void warp_top2(unsigned long long& k0, unsigned long 
 // One warp per (general-float pair, query row).  The tcgen05 accumulators are approximations of
 // d^2/2 (two-term bf16 split): |2*acc - d^2| <= E = 2^-13 (|q|^2 + max|t|^2), a worst-case bound
 // (dropped lo.lo and residual terms: 2^-16.4; 400 truncating fp32 accumulations of terms whose
-// magnitudes sum to <= 1.01 (|q|^2+|t|^2): 2^-13.3).  The row's best four chunks (128 columns)
-// are evaluated exactly in OpenCV's summation order; every other column is bounded below by the
-// fifth-best chunk minimum.  If that bound, minus E, clears the exact second distance, the answer
-// is provably the one cv::BFMatcher gives (ties included); otherwise the row goes to the exact
-// full-row fallback.  Nothing is ever returned uncertified.
+// magnitudes sum to <= 1.01 (|q|^2+|t|^2): 2^-13.3).  Stage 0 evaluates the best 8-column group
+// of each of the row's best four chunks (32 columns, one per lane) exactly, in OpenCV's summation
+// order; every other column is bounded below by the fifth-best chunk minimum or by the smallest
+// second group minimum of a chunk.  If that bound, minus E, clears the exact second distance, the
+// answer is provably the one cv::BFMatcher gives (ties included).  Otherwise (the two nearest
+// rows share a chunk: ~0.3 % of rows) stage 1 evaluates the four chunks completely (128 columns)
+// against the fifth-chunk bound, and what is still uncertified goes to the exact full-row
+// fallback.  Nothing is ever returned uncertified.
 __global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G) {
   const int pair = blockIdx.y;
   const int lane = threadIdx.x & 31;
@@ -1029,10 +1041,11 @@ __global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G)
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
     return ((unsigned long long)u << 32) | (uint32_t)g;
   };
-  // this lane's slot record: four sorted (value, gid) entries and a bound for the rest of its slot
+  // this lane's slot record: four sorted (value, gid) entries and the bounds for the rest of its
+  // slot.  rest: columns outside the kept chunks; rest2: also the kept chunks' other groups.
   unsigned long long ek[4] = {~0ull, ~0ull, ~0ull, ~0ull};
   float ev[4] = {INF, INF, INF, INF};
-  float rest = INF;
+  float rest = INF, rest2 = INF;
   for (int s = lane; s < n_valid; s += 32) {
     const size_t at = ((size_t)pair * G.n_slots + s) * G.nq_pad + q;
     const uint4 ra = G.cand[2 * at], rb2 = G.cand[2 * at + 1];
@@ -1041,6 +1054,7 @@ __global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G)
     const int g4[4] = {(int)(rb2.x & 0xFFFFu), (int)(rb2.x >> 16), (int)(rb2.y & 0xFFFFu),
                        (int)(rb2.y >> 16)};
     rest = fminf(rest, __uint_as_float(rb2.z));
+    rest2 = fminf(rest2, __uint_as_float(rb2.w));
     if (s < 32) {
 #pragma unroll
       for (int k = 0; k < 4; k++)
@@ -1051,10 +1065,9 @@ __global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G)
         if (g4[k] != 0xFFFF) rest = fminf(rest, v4[k]);
     }
   }
-  // global best four chunks: four rounds of "warp minimum of the lanes' heads, owner pops"
-  int cols[4];
-  bool hask[4];
-  float cval[4];   // approximate minimum of each selected chunk
+  // global best four chunks: four rounds of "warp minimum of the lanes' heads, owner pops".
+  // Lane r (mod 4) remembers the group (column / 8) holding the minimum of the r-th chunk.
+  int gsel = -1;
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     const unsigned long long mine = ek[0];
@@ -1064,12 +1077,10 @@ __global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G)
       const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
       best = o < best ? o : best;
     }
-    hask[r] = best != ~0ull;
-    cols[r] = hask[r] ? (int)((uint32_t)best >> 2) * 32 : 0;   // first column of that chunk
-    const bool owner = hask[r] && mine == best;   // keys are unique (distinct chunks): one lane pops
-    const unsigned ob = __ballot_sync(0xffffffffu, owner);
-    cval[r] = hask[r] ? __shfl_sync(0xffffffffu, ev[0], __ffs(ob) - 1) : INF;
-    if (owner) {
+    const bool has = best != ~0ull;
+    if (has && (lane & 3) == r) gsel = (int)(uint32_t)best;
+    // keys are unique (distinct chunks): exactly one lane pops
+    if (has && mine == best) {
       ek[0] = ek[1]; ek[1] = ek[2]; ek[2] = ek[3]; ek[3] = ~0ull;
       ev[0] = ev[1]; ev[1] = ev[2]; ev[2] = ev[3]; ev[3] = INF;
     }
@@ -1079,14 +1090,14 @@ __global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G)
   for (int k = 0; k < 4; k++)
     if (ek[k] != ~0ull) rest = fminf(rest, ev[k]);
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) rest = fminf(rest, __shfl_xor_sync(0xffffffffu, rest, off));
+  for (int off = 16; off >= 1; off >>= 1) {
+    rest = fminf(rest, __shfl_xor_sync(0xffffffffu, rest, off));
+    rest2 = fminf(rest2, __shfl_xor_sync(0xffffffffu, rest2, off));
+  }
 
-  // Exact distances (OpenCV order), one column per lane per chunk.  Two stages: the best two
-  // chunks first; if the certificate already holds against everything else (chunks 3 and 4
-  // included), the other 64 columns are never touched -- the common case.
   const float* qrow = G.q_f32 + (size_t)q * 128;
   const double E = ((double)G.q_nrmf[q] + (double)__int_as_float(pr->t_flags[2])) * (1.0 / 8192.0);
-  auto certified_against = [&](float bound, unsigned long long second) -> bool {
+  auto certified_against = [=](float bound, unsigned long long second) -> bool {
     if (!(bound < INF)) return true;            // +inf (or NaN): only padding is left
     if (second == ~0ull) return false;          // fewer than two evaluated columns, more exist
     const float d1 = __uint_as_float((uint32_t)(second >> 32));
@@ -1094,25 +1105,32 @@ __global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G)
     const double lower = (2.0 * (double)bound - E) * (1.0 - 3.9e-6);  // oracle d^2 of any other column
     return lower > D2;
   };
+  // stage 0: lane 8r+j takes column j of the best group of the r-th chunk
   unsigned long long e0 = ~0ull, e1 = ~0ull;
-  bool certified = false;
+  {
+    const int g = __shfl_sync(0xffffffffu, gsel, lane >> 3);
+    const int col = g * GROUP + (lane & 7);
+    if (g >= 0 && col < pr->t_n) {
+      const float d = l2_cv_order(qrow, pr->t_f32 + (size_t)col * 128);
+      e0 = ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)col;
+    }
+    warp_top2(e0, e1);
+  }
+  bool certified = certified_against(fminf(rest, rest2), e1);
+  if (!certified) {   // warp-uniform
+    // stage 1: the four chunks completely, one column per lane per chunk
+    e0 = ~0ull; e1 = ~0ull;
 #pragma unroll 1
-  for (int stage = 0; stage < 2; stage++) {
-    unsigned long long l0 = ~0ull, l1 = ~0ull;
-#pragma unroll 1
-    for (int r = 2 * stage; r < 2 * stage + 2; r++) {
-      const int col = cols[r] + lane;
-      if (hask[r] && col < pr->t_n) {
+    for (int r = 0; r < 4; r++) {
+      const int g = __shfl_sync(0xffffffffu, gsel, r);
+      const int col = (g >> 2) * 32 + lane;
+      if (g >= 0 && col < pr->t_n) {
         const float d = l2_cv_order(qrow, pr->t_f32 + (size_t)col * 128);
-        key_top2(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)col, l0, l1);
+        key_top2(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)col, e0, e1);
       }
     }
-    warp_top2(l0, l1);
-    key_top2(l0, e0, e1);
-    key_top2(l1, e0, e1);
-    const float bound = stage == 0 ? fminf(rest, fminf(cval[2], cval[3])) : rest;
-    certified = certified_against(bound, e1);
-    if (certified || !hask[2]) break;   // warp-uniform
+    warp_top2(e0, e1);
+    certified = certified_against(rest, e1);
   }
   if (lane == 0) {
     uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
@@ -1129,35 +1147,64 @@ __global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G)
   }
 }
 
-// Exact full-row scan for the rows the certificate could not clear: one block per listed row,
-// every thread strides over the train rows, OpenCV's arithmetic throughout.
+// Exact full-row scan for the rows the certificate could not clear, OpenCV's arithmetic
+// throughout.  A work item is (listed row, segment of the train set): with few rows listed (the
+// usual case: a handful per pair) each row is cut into up to 32 segments so that the scan is
+// spread over the whole grid instead of running ~40 dependent distance evaluations per thread
+// in a few blocks; the block that finishes a row's last segment merges the partial top-2 keys
+// (a key is distance bits : train index, so the merge is order independent).
+constexpr int FB_GRID = SIFT_GEN_FB_ITEMS;
 __global__ void __launch_bounds__(256) sift_gen_fallback_kernel(const GenParams G) {
   __shared__ __align__(16) float qs[128];
   __shared__ unsigned long long red[2][8];
+  __shared__ int s_last;
   const int n = *G.fb_count;
-  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+  if (n <= 0) return;
+  const int S = n >= FB_GRID ? 1 : min(32, FB_GRID / n);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int item = blockIdx.x; item < n * S; item += gridDim.x) {
+    const int i = item / S, seg = item - i * S;
     const uint2 w = G.fb_list[i];
     const int pair = (int)w.x, q = (int)w.y;
     const TcPair* pr = G.pairs + pair;
     __syncthreads();
     if (threadIdx.x < 128) qs[threadIdx.x] = G.q_f32[(size_t)q * 128 + threadIdx.x];
     __syncthreads();
+    const int len = (pr->t_n + S - 1) / S;
+    const int t_end = min(pr->t_n, (seg + 1) * len);
     unsigned long long k0 = ~0ull, k1 = ~0ull;
-    for (int t = threadIdx.x; t < pr->t_n; t += 256) {
+    for (int t = seg * len + threadIdx.x; t < t_end; t += 256) {
       const float d = l2_cv_order(qs, pr->t_f32 + (size_t)t * 128);
       key_top2(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)t, k0, k1);
     }
     warp_top2(k0, k1);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { red[0][warp] = k0; red[1][warp] = k1; }
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long b0 = ~0ull, b1 = ~0ull;
       for (int k = 0; k < 8; k++) { key_top2(red[0][k], b0, b1); key_top2(red[1][k], b0, b1); }
-      uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
-      if (b0 != ~0ull) { rec.x = (uint32_t)(b0 >> 32); rec.y = (uint32_t)b0; }
-      if (b1 != ~0ull) { rec.z = (uint32_t)(b1 >> 32); rec.w = (uint32_t)b1; }
-      G.part[((size_t)pair * G.n_split) * G.nq + q] = rec;
+      bool last = true;
+      if (S > 1) {
+        // n * S <= FB_GRID work items: one scratch slot each
+        G.fb_part[2 * item] = b0;
+        G.fb_part[2 * item + 1] = b1;
+        __threadfence();
+        last = atomicAdd(G.fb_done + i, 1) == S - 1;
+        if (last) {
+          __threadfence();
+          b0 = ~0ull; b1 = ~0ull;
+          for (int k = 0; k < S; k++) {
+            key_top2(__ldcg(G.fb_part + 2 * (i * S + k)), b0, b1);
+            key_top2(__ldcg(G.fb_part + 2 * (i * S + k) + 1), b0, b1);
+          }
+        }
+      }
+      if (last) {
+        uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+        if (b0 != ~0ull) { rec.x = (uint32_t)(b0 >> 32); rec.y = (uint32_t)b0; }
+        if (b1 != ~0ull) { rec.z = (uint32_t)(b1 >> 32); rec.w = (uint32_t)b1; }
+        G.part[((size_t)pair * G.n_split) * G.nq + q] = rec;
+      }
     }
   }
 }
@@ -1277,7 +1324,8 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_fl
 void launch_sift_gen_rerank(const int32_t* q_flags, const float* q_f32, const float* q_nrmf, int nq,
                             const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                             int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
-                            uint2* fb_list, int32_t* fb_count, cudaStream_t s) {
+                            uint2* fb_list, int32_t* fb_count, unsigned long long* fb_part,
+                            int32_t* fb_done, cudaStream_t s) {
   if (nq <= 0 || n_pairs <= 0) return;
   GenParams G;
   G.q_f32 = q_f32; G.q_nrmf = q_nrmf; G.q_flags = q_flags; G.pairs = pairs_dev;
@@ -1285,10 +1333,11 @@ void launch_sift_gen_rerank(const int32_t* q_flags, const float* q_f32, const fl
   G.nq = nq; G.nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM); G.n_slots = n_slots;
   G.n_pairs = n_pairs; G.n_split = n_split; G.n_cta = n_cta_pairs;
   G.part = part; G.fb_list = fb_list; G.fb_count = fb_count;
+  G.fb_part = fb_part; G.fb_done = fb_done;
   dim3 grid((nq + 7) / 8, n_pairs);
   sift_gen_rerank_kernel<<<grid, 256, 0, s>>>(G);
   COUNT_LAUNCH();
-  sift_gen_fallback_kernel<<<148 * 4, 256, 0, s>>>(G);
+  sift_gen_fallback_kernel<<<FB_GRID, 256, 0, s>>>(G);
   COUNT_LAUNCH();
 }
 
