@@ -1105,14 +1105,45 @@ __global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G)
     const double lower = (2.0 * (double)bound - E) * (1.0 - 3.9e-6);  // oracle d^2 of any other column
     return lower > D2;
   };
-  // stage 0: lane 8r+j takes column j of the best group of the r-th chunk
+  // stage 0: the best group of each of the four chunks.  A group is 8 consecutive train rows
+  // (4 KB); four lanes share a row -- lane a of the quad owns OpenCV's accumulator a (elements
+  // 16 i + 4 a .. + 3), so every load instruction reads whole 64-byte pieces of 8 rows -- and the
+  // quad then combines the accumulators in OpenCV's order.
   unsigned long long e0 = ~0ull, e1 = ~0ull;
   {
-    const int g = __shfl_sync(0xffffffffu, gsel, lane >> 3);
-    const int col = g * GROUP + (lane & 7);
-    if (g >= 0 && col < pr->t_n) {
-      const float d = l2_cv_order(qrow, pr->t_f32 + (size_t)col * 128);
-      e0 = ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)col;
+    const int a = lane & 3, j = lane >> 2, quad0 = lane & ~3;
+    float4 q4[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) q4[i] = *reinterpret_cast<const float4*>(qrow + 16 * i + 4 * a);
+#pragma unroll 2
+    for (int r = 0; r < 4; r++) {
+      const int g = __shfl_sync(0xffffffffu, gsel, r);
+      if (g < 0) continue;   // warp-uniform
+      const int col = g * GROUP + j;
+      const float* trow = pr->t_f32 + (size_t)col * 128 + 4 * a;   // padding rows exist up to n_pad
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float4 tv = *reinterpret_cast<const float4*>(trow + 16 * i);
+        float d;
+        d = __fsub_rn(q4[i].x, tv.x); acc.x = __fadd_rn(acc.x, __fmul_rn(d, d));
+        d = __fsub_rn(q4[i].y, tv.y); acc.y = __fadd_rn(acc.y, __fmul_rn(d, d));
+        d = __fsub_rn(q4[i].z, tv.z); acc.z = __fadd_rn(acc.z, __fmul_rn(d, d));
+        d = __fsub_rn(q4[i].w, tv.w); acc.w = __fadd_rn(acc.w, __fmul_rn(d, d));
+      }
+      float S[4];
+      const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        const float a0 = __shfl_sync(0xffffffffu, av[l], quad0 + 0);
+        const float a1 = __shfl_sync(0xffffffffu, av[l], quad0 + 1);
+        const float a2 = __shfl_sync(0xffffffffu, av[l], quad0 + 2);
+        const float a3 = __shfl_sync(0xffffffffu, av[l], quad0 + 3);
+        S[l] = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+      }
+      const float d = sqrtf(__fadd_rn(__fadd_rn(S[0], S[2]), __fadd_rn(S[1], S[3])));
+      if (a == 0 && col < pr->t_n)
+        key_top2(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)col, e0, e1);
     }
     warp_top2(e0, e1);
   }
