@@ -590,9 +590,22 @@ def extras(ctx, stream):
     Ti.free()
     q, t = synth.orb_pair(N_ROWS, N_ROWS, 2001)
     Q, T = ctx.upload(q), ctx.upload(t)
+    # cfg2 through the XOR/POPC kernel (bound: the POPC pipe) ...
+    ctx.debug_orb_kernel(tensor_cores=False)
     ms = ev_time(lambda: ctx.matchBatchEnqueue(Q, [T] * 16, MatcherType.ORB_BF, RATIO, stream), 10)
-    out["cfg2_orb_16_pairs"] = {"us_per_pair": ms / 16 * 1e3, "pairs_per_s": 16e3 / ms,
+    out["cfg2_orb_16_pairs"] = {"kernel": "orb_knn2_kernel (XOR + carry-save + POPC)",
+                                "us_per_pair": ms / 16 * 1e3, "pairs_per_s": 16e3 / ms,
                                 "tpopc_per_s": 16 * 8e8 / ms / 1e9}
+    # ... and through the tcgen05 kernel on the bits spread to e4m3 0/1 bytes (the default route):
+    # Hamming = squared L2 of the bit vectors, 2*Q*T*256 fp8 flop per pair on the tensor pipe
+    ctx.debug_orb_kernel(tensor_cores=True)
+    ms = ev_time(lambda: ctx.matchBatchEnqueue(Q, [T] * 16, MatcherType.ORB_BF, RATIO, stream), 20)
+    out["cfg2_orb_16_pairs_tcgen05"] = {"kernel": "sift_tc_kernel, kind::f8f6f4 (default ORB route)",
+                                        "us_per_pair": ms / 16 * 1e3, "pairs_per_s": 16e3 / ms,
+                                        "fp8_tflops": 16 * 2.0 * N_ROWS * N_ROWS * 256 / ms / 1e9,
+                                        "popc_equivalent_T_per_s": 16 * 8e8 / ms / 1e9}
+    ms = ev_time(lambda: ctx.matchBatchEnqueue(Q, [T], MatcherType.ORB_BF, RATIO, stream), 50)
+    out["cfg2_orb_single_pair_tcgen05"] = {"us_per_pair": ms * 1e3, "pairs_per_s": 1e3 / ms}
     # cfg5: 2048 hypotheses x 5000 matches, 32 pairs per launch, host-call timing incl. copies
     p1, p2, R, tv = synth.two_view(5000, 5000)
     E = synth.pose_hypotheses(2048, R, tv, 5001)

@@ -174,6 +174,7 @@ struct slamb200_ctx {
   bool pack_started = false;
   int sub_batch = 0;  // debug: pairs per tcgen05 launch when pipelining against the rerank
   int use_tc = 1;  // debug switch (slamb200_dbg_set_tc): 0 routes exact-mode pairs to the fp32 kernel
+  int use_tc_orb = 1;  // debug switch (slamb200_dbg_set_tc_orb): 0 routes ORB pairs to the XOR/POPC kernel
 };
 
 static int dev_alloc(slamb200_ctx* c, void** p, size_t bytes, cudaStream_t s) {
@@ -454,6 +455,19 @@ static void sift_slab_point(slamb200_desc* d) {
   d->flags = (int32_t*)(base + o_flags);
 }
 
+// one ORB slab: u8 rows | e4m3 0/1 bytes (tcgen05 operand) | augq | augt | flags (zero: the
+// tensor-core kernels read them as "exact mode")
+static size_t orb_slab_bytes(size_t np) { return np * (32 + 256 + 32 + 32) + 256; }
+static void orb_slab_point(slamb200_desc* d) {
+  const size_t np = (size_t)d->n_pad;
+  char* base = (char*)d->slab;
+  d->u8 = (uint8_t*)base;
+  d->bf16 = (__nv_bfloat16*)(base + np * 32);            // the e4m3 bytes, 256 per row like a bf16 SIFT row
+  d->augq = (__nv_bfloat16*)(base + np * (32 + 256));
+  d->augt = (__nv_bfloat16*)(base + np * (32 + 256 + 32));
+  d->flags = (int32_t*)(base + np * (32 + 256 + 32 + 32));
+}
+
 static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_t row_stride,
                        bool src_on_device, cudaStream_t producer, bool no_sync,
                        slamb200_desc** out, slamb200_ctx::PinBuf* packed = nullptr,
@@ -500,19 +514,27 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   }
   if (!d->ready) { rc = fail(SLAMB200_ERR_CUDA, "cudaEventCreate failed"); goto done; }
   if (kind == SLAMB200_DESC_U8X32) {
-    d->slab_bytes = (size_t)d->n_pad * 32;
+    d->slab_bytes = orb_slab_bytes(d->n_pad);
     if (shared) {
       DCU(cudaMalloc(&d->slab, d->slab_bytes));
       d->shared = 1;
     } else if (!(d->slab = slab_from_cache(c, d->slab_bytes, s))) {
       if ((rc = dev_alloc(c, &d->slab, d->slab_bytes, s))) goto done;
     }
-    d->u8 = (uint8_t*)d->slab;
+    orb_slab_point(d);
+    DCU(cudaMemsetAsync(d->flags, 0, 16, s));
     if (d->n_pad > n) DCU(cudaMemsetAsync(d->u8 + (size_t)n * 32, 0, (size_t)(d->n_pad - n) * 32, s));
     if (n > 0) {
       const cudaMemcpyKind k = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
       if (row_stride == 32) DCU(cudaMemcpyAsync(d->u8, rows, (size_t)n * 32, k, s));
       else DCU(cudaMemcpy2DAsync(d->u8, 32, rows, row_stride, 32, n, k, s));
+    }
+    // the bits spread to e4m3 bytes + popcount augmentation: operands of the tcgen05 kernel
+    launch_orb_tc_prep(d->u8, n, d->n_pad, (uint8_t*)d->bf16, (uint8_t*)d->augq, (uint8_t*)d->augt, s);
+    DCU(cudaGetLastError());
+    if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->bf16, d->n_pad, d->tmaps) != 0) {
+      rc = fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+      goto done;
     }
   } else {
     const size_t total = sift_slab_bytes(d->n_pad);
@@ -570,9 +592,10 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   if (packed) DCU(cudaEventRecord(packed->ev, s));
   if (!src_on_device && !no_sync) {
     // the caller may reuse `rows` on return; the same synchronisation brings the exact-mode flag back
-    if (d->flags) DCU(cudaMemcpyAsync(L.h_small, d->flags, 4, cudaMemcpyDeviceToHost, s));
+    const bool sift = kind == SLAMB200_DESC_F32X128;
+    if (sift) DCU(cudaMemcpyAsync(L.h_small, d->flags, 4, cudaMemcpyDeviceToHost, s));
     DCU(cudaStreamSynchronize(s));
-    if (d->flags) d->host_exact = L.h_small[0] == 0 ? 1 : 0;
+    if (sift) d->host_exact = L.h_small[0] == 0 ? 1 : 0;
     d->ready_seen = 1;
   }
 done:
@@ -701,7 +724,7 @@ extern "C" int slamb200_desc_import(slamb200_ctx* c, const slamb200_desc_ipc* in
     return fail(SLAMB200_ERR_KIND, "desc_import: unknown descriptor kind %d", in->kind);
   if (in->n < 0 || in->n_pad < in->n || in->n_pad % SLAMB200_TILE_PAD)
     return fail(SLAMB200_ERR_INVALID, "desc_import: bad sizes");
-  const size_t want = in->kind == SLAMB200_DESC_F32X128 ? sift_slab_bytes((size_t)in->n_pad) : (size_t)in->n_pad * 32;
+  const size_t want = in->kind == SLAMB200_DESC_F32X128 ? sift_slab_bytes((size_t)in->n_pad) : orb_slab_bytes((size_t)in->n_pad);
   if (in->slab_bytes != want) return fail(SLAMB200_ERR_INVALID, "desc_import: slab size mismatch");
   CU(cudaSetDevice(c->device));
   slamb200_desc* d = (slamb200_desc*)aligned_alloc(64, (sizeof(slamb200_desc) + 63) / 64 * 64);
@@ -721,11 +744,11 @@ extern "C" int slamb200_desc_import(slamb200_ctx* c, const slamb200_desc_ipc* in
     free(d);
     return fail(SLAMB200_ERR_CUDA, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
   }
-  if (d->kind == SLAMB200_DESC_U8X32) {
-    d->u8 = (uint8_t*)d->slab;
-  } else {
-    sift_slab_point(d);
-    if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->bf16lo, d->n_pad, d->tmaps) != 0) {
+  if (d->kind == SLAMB200_DESC_U8X32) orb_slab_point(d);
+  else sift_slab_point(d);
+  {
+    if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->kind == SLAMB200_DESC_U8X32 ? d->bf16 : d->bf16lo,
+                        d->n_pad, d->tmaps) != 0) {
       cudaIpcCloseMemHandle(d->slab);
       free(d);
       return fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed on the peer mapping");
@@ -772,13 +795,11 @@ extern "C" int slamb200_desc_localize(slamb200_ctx* c, const slamb200_desc* src,
     }
   }
   if (rc == SLAMB200_OK) {
-    if (d->kind == SLAMB200_DESC_U8X32) {
-      d->u8 = (uint8_t*)d->slab;
-    } else {
-      sift_slab_point(d);
-      if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->bf16lo, d->n_pad, d->tmaps) != 0)
-        rc = fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-    }
+    if (d->kind == SLAMB200_DESC_U8X32) orb_slab_point(d);
+    else sift_slab_point(d);
+    if (tc_encode_tmaps(d->bf16, d->augq, d->augt, d->kind == SLAMB200_DESC_U8X32 ? d->bf16 : d->bf16lo,
+                        d->n_pad, d->tmaps) != 0)
+      rc = fail(SLAMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   }
   if (rc != SLAMB200_OK) {
     slamb200_free_desc(c, d);
@@ -975,7 +996,9 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     return fail(SLAMB200_ERR_INVALID, "ORB train set of %d rows exceeds the 2^22-row key range", t_max);
   // the candidate records pack two 16-bit group indices: train sets beyond 524k rows take the
   // exact fp32 kernel instead
-  const bool tc = !orb && !l1 && c->use_tc && nq > 0 && t_max <= 65535 * 8;
+  // ORB takes the same tcgen05 candidate kernel on e4m3 0/1 bytes (Hamming = squared L2 of the
+  // bit vectors); the XOR/POPC kernel remains for huge train sets and behind the debug switch
+  const bool tc = !l1 && (orb ? c->use_tc_orb : c->use_tc) && nq > 0 && t_max <= 65535 * 8;
   const int q_blocks = orb ? (nq + 255) / 256 : (nq + 15) / 16;
   const int n_split = pick_splits(q_blocks > 0 ? q_blocks : 1, n_pairs, t_max, orb ? 1024 : 512);
 
@@ -1079,10 +1102,10 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   }
   // the exact fp32 kernel is not even launched when every set is known (on the host) to be in
   // exact mode; sets whose flag has not been read back yet leave the decision to the device
-  bool all_exact_known = !orb && q->host_exact == 1;
-  for (int p = 0; p < n_pairs && all_exact_known; p++) all_exact_known = trains[p]->host_exact == 1;
+  bool all_exact_known = orb || q->host_exact == 1;
+  for (int p = 0; p < n_pairs && all_exact_known && !orb; p++) all_exact_known = trains[p]->host_exact == 1;
 
-  if (orb) {
+  if (orb && !tc) {
     ProfScope ps(c, s, SLAMB200_K_ORB);
     launch_orb_knn2(q->u8, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p, s);
   } else {
@@ -1158,9 +1181,10 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         uint4* part_k = (uint4*)L.part.p + (size_t)p0 * n_split * nq;
         int trc;
         {
-          ProfScope ps(c, s, SLAMB200_K_SIFT_TC);
+          ProfScope ps(c, s, orb ? SLAMB200_K_ORB : SLAMB200_K_SIFT_TC);
           trc = launch_sift_tc_candidates(qmaps, q->flags, nq, tcp, pre_k, np, tiles_k, n_cta,
-                                          n_slots, cand_k, d_status, k == 0 ? L.dbg : nullptr, 0, s);
+                                          n_slots, cand_k, d_status, k == 0 ? L.dbg : nullptr, 0, s,
+                                          orb ? 1 : 0);
         }
         if (trc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
         if (s2 != s) {
@@ -1168,14 +1192,14 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
           CU(cudaStreamWaitEvent(s2, L.sub_ev[k], 0));
         }
         {
-          ProfScope ps(c, s2, SLAMB200_K_SIFT_RERANK);
+          ProfScope ps(c, s2, orb ? SLAMB200_K_ORB : SLAMB200_K_SIFT_RERANK);
           launch_sift_rerank(q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, n_cta, n_slots, n_split,
                              cand_k, part_k, (uint4*)L.work.p + (size_t)p0 * nq,
                              (float2*)L.work_v0.p + (size_t)p0 * nq, d_status + 1 + (k < 1000 ? k : 1000),
-                             d_status, want_knn ? 0 : 1, ratio, s2);
+                             d_status, want_knn ? 0 : 1, ratio, s2, orb ? 1 : 0);
         }
         ProfScope psf(c, s2, SLAMB200_K_FINALIZE);
-        launch_finalize(part_k, nq, d_pairs + p0, np, n_split, 0, ratio,
+        launch_finalize(part_k, nq, d_pairs + p0, np, n_split, orb ? 1 : 0, ratio,
                         (int32_t*)L.knn_idx.p + (size_t)p0 * nq * 2,
                         (float*)L.knn_dist.p + (size_t)p0 * nq * 2, (uint8_t*)L.flags.p + (size_t)p0 * nq,
                         (int32_t*)L.chunk_cnt.p + (size_t)p0 * chunks,
@@ -1801,6 +1825,12 @@ extern "C" int slamb200_dbg_set_tc(slamb200_ctx* c, int on) {
   return SLAMB200_OK;
 }
 
+extern "C" int slamb200_dbg_set_tc_orb(slamb200_ctx* c, int on) {
+  if (!c) return SLAMB200_ERR_INVALID;
+  c->use_tc_orb = on ? 1 : 0;
+  return SLAMB200_OK;
+}
+
 // Raw fp32 accumulators (d^2/2) of the first 256 x 256 tile of (query, train): out[256*256].
 extern "C" int slamb200_dbg_tc_tile(slamb200_ctx* c, const slamb200_desc* q, const slamb200_desc* t,
                                     float* out) {
@@ -1814,7 +1844,7 @@ extern "C" int slamb200_dbg_tc_tile(slamb200_ctx* c, const slamb200_desc* q, con
   CU(cudaMemsetAsync(d, 0, 256 * 256 * 4, L.stream));
   L.dbg = d;
   const slamb200_desc* tt[1] = {t};
-  rc = enqueue_batch(c, L, L.stream, SLAMB200_SIFT_BF, q, tt, 1, 0.7);
+  rc = enqueue_batch(c, L, L.stream, q->kind == SLAMB200_DESC_U8X32 ? SLAMB200_ORB_BF : SLAMB200_SIFT_BF, q, tt, 1, 0.7);
   L.dbg = nullptr;
   if (rc == SLAMB200_OK) {
     cudaError_t e = cudaMemcpyAsync(out, d, 256 * 256 * 4, cudaMemcpyDeviceToHost, L.stream);

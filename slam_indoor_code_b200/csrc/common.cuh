@@ -191,7 +191,7 @@ int tc_slots(int n_cb_max, int total_tiles, int n_cta);
 int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_flags, int nq,
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
-                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s);
+                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s, int fp8 = 0);
 void launch_sift_gen_rerank(const int32_t* q_flags, const float* q_f32, const float* q_nrmf, int nq,
                             const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                             int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
@@ -204,7 +204,11 @@ void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32
                         const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                         int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                         uint4* work, float2* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
-                        double ratio, cudaStream_t s);
+                        double ratio, cudaStream_t s, int orb = 0);
+// ORB rows -> tcgen05 operands (sift_prep.cu): e4m3 0/1 bytes [n_pad][256] and the two
+// augmentation blocks [n_pad/8][256 B]
+void launch_orb_tc_prep(const uint8_t* u8, int n, int n_pad, uint8_t* e4, uint8_t* augq,
+                        uint8_t* augt, cudaStream_t s);
 
 int64_t* launch_counter();
 #define COUNT_LAUNCH() (++(*launch_counter()))

@@ -15,6 +15,7 @@
 // Padding rows [n, n_pad) get zero descriptors and a +inf augmentation (the accumulator becomes
 // +inf, never NaN: the partner's entry is 1) so they are never candidates.  One warp per row, one float4 per lane.
 #include "common.cuh"
+#include <cuda_fp8.h>
 
 // U8SRC: the rows arrive already narrowed to bytes (slamb200_upload_desc_packed: the host verified
 // that they are integers in [0,255]); src then points at n x 128 bytes, typically page-locked host
@@ -137,5 +138,63 @@ void launch_sift_prep_u8(const uint8_t* src_u8, int n, int n_pad, float* f32, __
   sift_prep_kernel<true><<<(n_pad + rows_per_block - 1) / rows_per_block, 256, 0, s>>>(
       reinterpret_cast<const float*>(src_u8), 32, n, n_pad, f32, bf16, augq, augt, u8, nrm2, bf16lo,
       nrmf, flags);
+  COUNT_LAUNCH();
+}
+
+
+// ---- ORB rows as tcgen05 operands -------------------------------------------------------------
+// Hamming(q, t) over 256 bits = |q - t|^2 over 256 values in {0, 1}, so the SIFT candidate kernel
+// applies as it stands once the bits are spread to bytes: e4m3 (0x00 / 0x38 = 1.0) for
+// tcgen05.mma.kind::f8f6f4, 256 bytes per row -- byte for byte the shape of a bf16 SIFT row, so
+// the tensor maps, the shared-memory stages and the UMMA descriptors are shared.  The
+// augmentation blocks carry popcount/2 as three e4m3 pieces (16 k + j + 0.5 b: four significant
+// bits each, exact): query side [h m l 1 1 1 0..], train side [1 1 1 h m l 0..], 32 bytes per
+// row in the no-swizzle core-matrix order (8 rows x 16 bytes, the two K halves 128 bytes apart).
+// e4m3 has no infinity: padding rows get 448 (real accumulators are <= 128), which the merge pass
+// treats as "no such column".  One warp per row, one descriptor byte per lane.
+__device__ __forceinline__ uint8_t e4m3_small(int v) {   // integers 0..15 and 16 * (0..8), exact
+  return (uint8_t)__nv_cvt_float_to_fp8((float)v, __NV_SATFINITE, __NV_E4M3);
+}
+__global__ void __launch_bounds__(256)
+orb_tc_prep_kernel(const uint8_t* __restrict__ u8, int n, int n_pad, uint8_t* __restrict__ e4,
+                   uint8_t* __restrict__ augq, uint8_t* __restrict__ augt) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  const uint32_t b = row < n ? u8[(size_t)row * 32 + lane] : 0u;
+  uint2 o;
+  o.x = ((b & 1u) ? 0x38u : 0u) | ((b & 2u) ? 0x3800u : 0u) | ((b & 4u) ? 0x380000u : 0u) |
+        ((b & 8u) ? 0x38000000u : 0u);
+  o.y = ((b & 16u) ? 0x38u : 0u) | ((b & 32u) ? 0x3800u : 0u) | ((b & 64u) ? 0x380000u : 0u) |
+        ((b & 128u) ? 0x38000000u : 0u);
+  reinterpret_cast<uint2*>(e4 + (size_t)row * 256)[lane] = o;
+  int pc = __popc(b);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, off);
+  uint8_t h, m, l;
+  if (row < n) {
+    h = e4m3_small((pc >> 5) << 4);   // popcount / 2 = 16 * (pc >> 5) + ((pc >> 1) & 15) + 0.5 * (pc & 1)
+    m = e4m3_small((pc >> 1) & 15);
+    l = (pc & 1) ? 0x30 : 0x00;       // 0.5
+  } else {
+    h = 0x7E; m = 0; l = 0;           // 448, the largest e4m3 value
+  }
+  const uint8_t one = 0x38;
+  uint8_t aq = 0, at = 0;
+  if (lane == 0) { aq = h; at = one; }
+  if (lane == 1) { aq = m; at = one; }
+  if (lane == 2) { aq = l; at = one; }
+  if (lane == 3) { aq = one; at = h; }
+  if (lane == 4) { aq = one; at = m; }
+  if (lane == 5) { aq = one; at = l; }
+  const size_t at_off = (size_t)(row >> 3) * 256 + (size_t)(lane >> 4) * 128 + (row & 7) * 16 + (lane & 15);
+  augq[at_off] = aq;
+  augt[at_off] = at;
+}
+
+void launch_orb_tc_prep(const uint8_t* u8, int n, int n_pad, uint8_t* e4, uint8_t* augq,
+                        uint8_t* augt, cudaStream_t s) {
+  if (n_pad <= 0) return;
+  orb_tc_prep_kernel<<<(n_pad + 7) / 8, 256, 0, s>>>(u8, n, n_pad, e4, augq, augt);
   COUNT_LAUNCH();
 }

@@ -83,6 +83,7 @@ struct alignas(64) TcParams {
   float* dbg;                  // optional raw accumulator dump of pair 0's first tile [256][256]
   int32_t* err_flag;
   int mode;                    // 0 = product; 1..3 = timing experiments (results invalid)
+  int fp8;                     // operands are e4m3 bytes (ORB bits expanded to 0/1): kind::f8f6f4, K = 32
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -171,6 +172,17 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 with 8-bit operands: plain bytes in shared memory, K = 32 per instruction
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -220,6 +232,10 @@ __device__ __forceinline__ uint64_t desc_interleave(uint32_t addr) {
 // kind::i8: u8 x u8 -> s32 (c_format 2), K = 32 per instruction
 __host__ __device__ constexpr uint32_t idesc_u8(int m, int n) {
   return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// kind::f8f6f4: a/b format 0 = E4M3, fp32 accumulators
+__host__ __device__ constexpr uint32_t idesc_e4m3(int m, int n, int a_neg) {
+  return (1u << 4) | ((uint32_t)a_neg << 13) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_neg) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_neg << 13) | ((uint32_t)(n >> 3) << 17) |
@@ -547,7 +563,18 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
         const uint32_t a_addr = a_base + cur_a * STG;
         const uint32_t b_addr = b_base + b_stage * STG;
         const uint32_t d_tmem = tmem_base + t_stage * BN;
-        if (P.mode < 3) {
+        if (!GEN && P.fp8) {
+          // ORB bits as e4m3 0/1 bytes: a stage row is 256 bytes = 256 elements, 32 per MMA; the
+          // descriptor arithmetic is byte for byte that of the bf16 operand
+          constexpr uint32_t F8_NEG = idesc_e4m3(2 * BM, BN, 1), F8_POS = idesc_e4m3(2 * BM, BN, 0);
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const uint64_t ad = desc_sw128(a_addr + (k >> 2) * KBLK + (k & 3) * 32);
+            const uint64_t bd = desc_sw128(b_addr + (k >> 2) * KBLK + (k & 3) * 32);
+            tc_mma_f8(d_tmem, ad, bd, F8_NEG, k > 0 ? 1u : 0u);
+          }
+          tc_mma_f8(d_tmem, desc_interleave(a_addr + AUG), desc_interleave(b_addr + AUG), F8_POS, 1u);
+        } else if (P.mode < 3) {
           // exact mode: -(q.t); general floats: -(qh.th + qh.tl + ql.th), hi at k-blocks 0-1 and lo
           // at k-blocks 2-3 of the stage
           constexpr int N_TERMS = GEN ? 3 : 1;
@@ -697,6 +724,7 @@ struct RerankParams {
   const uint4* cand;
   int nq, nq_pad, n_slots, n_pairs, n_split, n_cta;
   int prune;         // 1: rows that cannot pass the ratio test skip the exact evaluation
+  int orb;           // ORB sets: the accumulators are Hamming/2, q_u8 / t_u8 are the 32-byte rows
   double ratio;
   uint4* part;       // [pair][n_split][nq]: split 0 gets the record (pre-set to "absent")
   uint4* work;       // survivors: {pair, row, gid of the best chunk, gid of the second chunk}
@@ -705,6 +733,7 @@ struct RerankParams {
   int32_t* err_flag;
 };
 
+constexpr float ORB_PAD_THRESHOLD = 200.0f;
 __device__ __forceinline__ bool lt_fi(float va, int ia, float vb, int ib) {
   return va < vb || (va == vb && ia < ib);
 }
@@ -754,8 +783,16 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
   if (q < R.nq) {
     for (int s = 0; s < n_valid; s++) {
       const uint4 rec = R.cand[((size_t)pair * R.n_slots + s) * R.nq_pad + q];
-      const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.y), sa = __uint_as_float(rec.z);
-      const int ia = (int)(rec.w & 0xFFFFu), ib = (int)(rec.w >> 16);
+      const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.y);
+      float sa = __uint_as_float(rec.z);
+      int ia = (int)(rec.w & 0xFFFFu), ib = (int)(rec.w >> 16);
+      if (R.orb) {
+        // e4m3 has no infinity: padding rows carry 448 in their augmentation, real values are
+        // Hamming / 2 <= 128
+        if (a > ORB_PAD_THRESHOLD) ia = 0xFFFF;
+        if (b > ORB_PAD_THRESHOLD) ib = 0xFFFF;
+        if (sa > ORB_PAD_THRESHOLD) sa = INF;
+      }
       if (ia != 0xFFFF) {
         if (lt_fi(a, ia, v0, g0)) { v1 = v0; g1 = g0; v0 = a; g0 = ia; s0 = sa; }
         else if (lt_fi(a, ia, v1, g1)) { v1 = a; g1 = ia; }
@@ -774,10 +811,12 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
     // second-best chunk.  +inf comes from padding columns, i.e. "no such element".
     const float L = fminf(s0, v1);
     if (R.prune && has0 && L < INF) {
-      const float d0 = sqrtf(2.0f * v0), D1 = sqrtf(2.0f * L);
+      // ORB: the distance is the Hamming count itself (int -> float), its record key the count
+      const float d0 = R.orb ? 2.0f * v0 : sqrtf(2.0f * v0), D1 = R.orb ? 2.0f * L : sqrtf(2.0f * L);
       if (!((double)d0 < __dmul_rn(R.ratio, (double)D1))) {
         R.part[((size_t)pair * R.n_split) * R.nq + q] =
-            make_uint4(__float_as_uint(d0), 0u, __float_as_uint(D1), 0u);
+            R.orb ? make_uint4((uint32_t)d0, 0u, (uint32_t)D1, 0u)
+                  : make_uint4(__float_as_uint(d0), 0u, __float_as_uint(D1), 0u);
         survive = false;
       }
     }
@@ -858,7 +897,10 @@ __global__ void __launch_bounds__(256) sift_rerank_lite_kernel(const RerankParam
         }
         if (d1sq >= 0.0f) {
           rec.z = __float_as_uint(sqrtf(d1sq));
-          rec.w = 0u;  // the second neighbour's index is not part of the match output
+          // the second neighbour's index is not part of the match output; the placeholder must
+          // sort behind every real index, or an equal second distance would overtake the best
+          // entry in the finalize merge (visible with ratios above 1)
+          rec.w = 0xFFFFFFFEu;
         }
       }
       R.part[((size_t)pair * R.n_split) * R.nq + q] = rec;
@@ -941,6 +983,129 @@ __global__ void __launch_bounds__(256) sift_rerank_kernel(const RerankParams R) 
         rec.z = __float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32)));
         rec.w = (uint32_t)(k1 & 0xFFFFFFFFu);
       }
+      R.part[((size_t)pair * R.n_split) * R.nq + q] = rec;
+    }
+  }
+}
+
+// ---- ORB through the tensor cores: Hamming(q, t) = |q - t|^2 over the 256 bits as 0/1 values ----
+// The tcgen05 kernel runs unchanged on e4m3 0/1 bytes (kind::f8f6f4, fp32 accumulators hold
+// Hamming / 2 exactly), so the candidate logic, its tie rules and the ratio-test pruning are the
+// exact-mode SIFT ones; only the exact evaluation of the candidates differs: XOR + POPC on the
+// original 32-byte rows, as cv::BFMatcher(NORM_HAMMING) does
+// (src/mainModule/featureMatching/featureMatchingCPU.cpp:33-35, :40).
+// Match output: the best group's 8 columns, 4 lanes x 8 bytes per candidate row.
+__global__ void __launch_bounds__(256) orb_rerank_lite_kernel(const RerankParams R) {
+  const int lane = threadIdx.x & 31;
+  const int part = lane & 3, cand = lane >> 2;
+  PDL_TRIGGER();
+  PDL_WAIT();
+  const int n_work = *R.work_n;
+  const int warps = gridDim.x * 8;
+  const float INF = __int_as_float(0x7f800000);
+  for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < n_work; w += warps) {
+    const uint4 wk = R.work[w];
+    const int pair = (int)wk.x, q = (int)wk.y, g0 = (int)wk.z;
+    const float2 vl = R.work_v0[w];
+    const TcPair* pr = R.pairs + pair;
+    const int col = g0 * GROUP + cand;
+    const bool ok = col < pr->t_n;
+    const int cc = ok ? col : 0;
+    const unsigned long long tv = *reinterpret_cast<const unsigned long long*>(pr->t_u8 + (size_t)cc * 32 + part * 8);
+    const unsigned long long qv = *reinterpret_cast<const unsigned long long*>(R.q_u8 + (size_t)q * 32 + part * 8);
+    uint32_t h = (uint32_t)__popcll(qv ^ tv);
+    h += __shfl_xor_sync(0xffffffffu, h, 1);
+    h += __shfl_xor_sync(0xffffffffu, h, 2);
+    unsigned long long k0 = ok ? (((unsigned long long)h << 32) | (uint32_t)col) : ~0ull;
+    unsigned long long k1 = ~0ull;
+#pragma unroll
+    for (int off = 4; off <= 16; off <<= 1) {
+      const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, off);
+      const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off);
+      const unsigned long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0;
+      const unsigned long long s2 = k1 < o1 ? k1 : o1;
+      k0 = lo;
+      k1 = hi < s2 ? hi : s2;
+    }
+    if (lane == 0) {
+      uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+      if (k0 != ~0ull) {
+        const uint32_t h0 = (uint32_t)(k0 >> 32);
+        // self check: the group's exact minimum must equal twice the tensor-core value
+        if ((float)h0 != 2.0f * vl.x) atomicOr(R.err_flag, 1);
+        rec.x = h0;
+        rec.y = (uint32_t)(k0 & 0xFFFFFFFFu);
+        // second distance: inside the group, or the bound from outside it (exact values both)
+        uint32_t h1 = vl.y < INF ? (uint32_t)(2.0f * vl.y) : 0xFFFFFFFFu;
+        if (k1 != ~0ull) h1 = min(h1, (uint32_t)(k1 >> 32));
+        if (h1 != 0xFFFFFFFFu) {
+          rec.z = h1;
+          // the second neighbour's index is not part of the match output; the placeholder must
+          // sort behind every real index, or an equal second distance would overtake the best
+          // entry in the finalize merge (visible with ratios above 1)
+          rec.w = 0xFFFFFFFEu;
+        }
+      }
+      R.part[((size_t)pair * R.n_split) * R.nq + q] = rec;
+    }
+  }
+}
+
+// Raw k-NN output (both indices): the best chunk's 32 columns + the 8 columns of the second
+// chunk's group, 4 lanes per candidate row, 8 candidates per pass.
+__global__ void __launch_bounds__(256) orb_rerank_kernel(const RerankParams R) {
+  const int lane = threadIdx.x & 31;
+  const int part = lane & 3, cand = lane >> 2;
+  PDL_TRIGGER();
+  PDL_WAIT();
+  const int n_work = *R.work_n;
+  const int warps = gridDim.x * 8;
+  for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < n_work; w += warps) {
+    const uint4 wk = R.work[w];
+    const int pair = (int)wk.x, q = (int)wk.y, g0 = (int)wk.z, g1 = (int)wk.w;
+    const float v0 = R.work_v0[w].x;
+    const TcPair* pr = R.pairs + pair;
+    const int t_n = pr->t_n;
+    const bool has1 = g1 != 0xFFFF;
+    const int col_a = (g0 >> 2) * 32;          // first column of the best chunk
+    const int col_b = has1 ? g1 * GROUP : 0;   // first column of the second chunk's group
+    const unsigned long long qv = *reinterpret_cast<const unsigned long long*>(R.q_u8 + (size_t)q * 32 + part * 8);
+    unsigned long long k0 = ~0ull, k1 = ~0ull;
+    uint32_t mn_a = 0xFFFFFFFFu;  // minimum inside the best chunk (self check)
+#pragma unroll
+    for (int it = 0; it < 5; it++) {
+      const int k = it * 8 + cand;
+      const int col = k < 32 ? col_a + k : col_b + (k - 32);
+      const bool ok = (k < 32 || has1) && col < t_n;
+      const int cc = ok ? col : 0;
+      const unsigned long long tv = *reinterpret_cast<const unsigned long long*>(pr->t_u8 + (size_t)cc * 32 + part * 8);
+      uint32_t h = (uint32_t)__popcll(qv ^ tv);
+      h += __shfl_xor_sync(0xffffffffu, h, 1);
+      h += __shfl_xor_sync(0xffffffffu, h, 2);
+      if (ok) {
+        const unsigned long long key = ((unsigned long long)h << 32) | (uint32_t)col;
+        if (k < 32) mn_a = min(mn_a, h);
+        if (key < k1) {
+          if (key < k0) { k1 = k0; k0 = key; } else { k1 = key; }
+        }
+      }
+    }
+    // merge the eight candidate lane groups (the 4 lanes of a group hold identical values)
+#pragma unroll
+    for (int off = 4; off <= 16; off <<= 1) {
+      const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, off);
+      const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off);
+      const unsigned long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0;
+      const unsigned long long s2 = k1 < o1 ? k1 : o1;
+      k0 = lo;
+      k1 = hi < s2 ? hi : s2;
+      mn_a = min(mn_a, __shfl_xor_sync(0xffffffffu, mn_a, off));
+    }
+    if (lane == 0) {
+      if (mn_a != 0xFFFFFFFFu && (float)mn_a != 2.0f * v0) atomicOr(R.err_flag, 1);
+      uint4 rec = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+      if (k0 != ~0ull) { rec.x = (uint32_t)(k0 >> 32); rec.y = (uint32_t)(k0 & 0xFFFFFFFFu); }
+      if (k1 != ~0ull) { rec.z = (uint32_t)(k1 >> 32); rec.w = (uint32_t)(k1 & 0xFFFFFFFFu); }
       R.part[((size_t)pair * R.n_split) * R.nq + q] = rec;
     }
   }
@@ -1188,7 +1353,6 @@ constexpr int FB_GRID = SIFT_GEN_FB_ITEMS;
 __global__ void __launch_bounds__(256) sift_gen_fallback_kernel(const GenParams G) {
   __shared__ __align__(16) float qs[128];
   __shared__ unsigned long long red[2][8];
-  __shared__ int s_last;
   const int n = *G.fb_count;
   if (n <= 0) return;
   const int S = n >= FB_GRID ? 1 : min(32, FB_GRID / n);
@@ -1310,7 +1474,7 @@ int tc_slots(int n_cb_max, int total_tiles, int n_cta) {
 int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_flags, int nq,
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
-                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s) {
+                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s, int fp8) {
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(sift_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1340,6 +1504,7 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_fl
   P.dbg = dbg;
   P.err_flag = err_flag;
   P.mode = g_tc_mode;
+  P.fp8 = fp8;
   const dim3 grid(2 * n_cta_pairs);
   if (gen) {
     if (dbg) sift_tc_kernel<true, true><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P);
@@ -1376,9 +1541,10 @@ void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32
                         const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                         int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                         uint4* work, float2* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
-                        double ratio, cudaStream_t s) {
+                        double ratio, cudaStream_t s, int orb) {
   if (nq <= 0 || n_pairs <= 0) return;
   RerankParams R;
+  R.orb = orb;
   R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
   R.tile_prefix = tile_prefix_dev; R.n_cta = n_cta_pairs;
   R.nq = nq; R.nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM); R.n_slots = n_slots; R.n_pairs = n_pairs;
@@ -1390,9 +1556,13 @@ void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32
   COUNT_LAUNCH();
   const long long rows = (long long)nq * n_pairs;
   const int blocks = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
-  if (prune)
+  if (orb) {
+    if (prune) launch_pdl(orb_rerank_lite_kernel, dim3(blocks), dim3(256), 0, s, R);
+    else launch_pdl(orb_rerank_kernel, dim3(blocks), dim3(256), 0, s, R);
+  } else if (prune) {
     launch_pdl(sift_rerank_lite_kernel, dim3(blocks), dim3(256), 0, s, R);   // match output: distances + best index
-  else
+  } else {
     launch_pdl(sift_rerank_kernel, dim3(blocks), dim3(256), 0, s, R);        // raw k-NN output: both indices
+  }
   COUNT_LAUNCH();
 }

@@ -86,6 +86,14 @@ class Context:
     KERNELS = ("sift_tc", "sift_exact", "orb", "ransac", "sift_rerank", "finalize", "sift_tc_gen",
                "sift_gen_rerank", "pnp", "sift_l1", "orb_desc")
 
+    def debug_orb_kernel(self, tensor_cores=True):
+        """Developer switch: ORB pairs through the tcgen05 kernel on e4m3 0/1 bytes (default) or
+        through the XOR/POPC kernel.  Both give cv::BFMatcher(NORM_HAMMING)'s results."""
+        f = self._lib.slamb200_dbg_set_tc_orb
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        f.restype = ctypes.c_int
+        check(f(self._h, 1 if tensor_cores else 0))
+
     def profile_enable(self, on=True):
         check(self._lib.slamb200_profile_enable(self._h, 1 if on else 0))
 

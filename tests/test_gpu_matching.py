@@ -566,3 +566,76 @@ def test_cfg3_full_window_properties(ctx):
         assert np.array_equal(res[p], ctx.matchFeatures(Q, Ts[p], MatcherType.SIFT_BF, 0.7))
     for t in Ts:
         t.free()
+
+
+# ---- ORB: the two kernels (tcgen05 on e4m3 0/1 bytes, XOR/POPC) against the same oracle -------------
+@pytest.fixture(params=["tcgen05", "xor_popc"])
+def orb_kernel(ctx, request):
+    ctx.debug_orb_kernel(tensor_cores=request.param == "tcgen05")
+    yield request.param
+    ctx.debug_orb_kernel(tensor_cores=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nq,nt,seed", [(1500, 2500, 411), (4097, 300, 412), (100, 5000, 413), (257, 9, 414),
+                                        (3, 2, 415), (700, 10007, 416)])
+def test_orb_both_kernels_seeded(ctx, orb_kernel, nq, nt, seed):
+    q, t = synth.orb_pair(nq, nt, seed)
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.ORB_BF, q, t)
+    ridx, rdist = c_oracle.hamming_knn2(q, t)
+    _check_knn(idx, dist, ridx, rdist)
+    assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.7))
+
+
+@pytest.mark.gpu
+def test_orb_both_kernels_ties_and_extremes(ctx, orb_kernel):
+    """Masses of equal distances (lowest train index wins), all-zero / all-one rows (popcount 0 and
+    256: the ends of the augmentation encoding), identical sets (distance 0)."""
+    rng = np.random.default_rng(16)
+    base = rng.integers(0, 256, (7, 32), dtype=np.uint8)
+    base[0] = 0
+    base[1] = 255
+    q = base[rng.integers(0, 7, 600)]
+    t = base[rng.integers(0, 7, 4100)]
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.ORB_BF, q, t)
+    ridx, rdist = c_oracle.hamming_knn2(q, t)
+    _check_knn(idx, dist, ridx, rdist)
+    assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.7))
+    # every popcount from 0 to 256 on both sides
+    rows = np.zeros((257, 32), np.uint8)
+    for k in range(257):
+        bits = np.zeros(256, np.uint8)
+        bits[rng.permutation(256)[:k]] = 1
+        rows[k] = np.packbits(bits)
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.ORB_BF, rows, rows[::-1].copy(), ratio=0.9)
+    ridx, rdist = c_oracle.hamming_knn2(rows, rows[::-1].copy())
+    _check_knn(idx, dist, ridx, rdist)
+    assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.9))
+
+
+@pytest.mark.gpu
+def test_orb_both_kernels_batch_and_ratios(ctx, orb_kernel):
+    q, _ = synth.orb_pair(900, 10, 421)
+    trains = [synth.orb_pair(10, n, 422 + i)[1] for i, n in enumerate((1200, 1, 0, 333, 2048))]
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(t) for t in trains]
+    for ratio in (0.0, 0.7, 1.0, 1.5):
+        got = ctx.matchBatch(Q, Ts, MatcherType.ORB_BF, ratio)
+        for g, t in zip(got, trains):
+            assert np.array_equal(g, c_oracle.match_features(2, q, t, ratio))
+
+
+@pytest.mark.gpu
+def test_sift_equal_best_and_second_with_ratio_above_one(ctx):
+    """Duplicated train rows: d0 == d1 exactly.  With a ratio above 1 such rows are kept, and the
+    match must still carry the lower of the two train indices (cv::BFMatcher's strict-'<' insert)."""
+    q, t = synth.sift_pair(500, 900, 731)
+    t = np.concatenate([t, t[::-1]]).copy()       # every train row twice
+    ridx, rdist = c_oracle.l2_knn2(q, t)
+    assert np.all(rdist[:, 0] == rdist[:, 1])
+    Q, T = ctx.upload(q), ctx.upload(t)
+    for r in (0.7, 1.0, 1.25, 2.0):
+        assert np.array_equal(ctx.matchFeatures(Q, T, MatcherType.SIFT_BF, r),
+                              c_oracle.ratio_test(ridx, rdist, r))
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, Q, T)
+    _check_knn(idx, dist, ridx, rdist)
