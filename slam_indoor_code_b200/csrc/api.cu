@@ -1171,6 +1171,9 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       cudaStream_t s2 = n_sub > 1 ? L.stream2 : s;
       const size_t cand_per_pair = (size_t)n_slots * n_rb * 256;
       const int chunks = finalize_chunks(cap);
+      // a query set known (on the host) to be general floats makes every pair a general-float
+      // pair: the exact-mode kernels would find nothing to do
+      const bool none_exact = !orb && q->host_exact == 0;
       for (int k = 0; k < n_sub; k++) {
         const int p0 = k * sub;
         const int np = n_pairs - p0 < sub ? n_pairs - p0 : sub;
@@ -1179,8 +1182,8 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         const int tiles_k = pre[p0 + np] - pre[p0];
         uint4* cand_k = (uint4*)L.cand.p + (size_t)p0 * cand_per_pair;
         uint4* part_k = (uint4*)L.part.p + (size_t)p0 * n_split * nq;
-        int trc;
-        {
+        int trc = 0;
+        if (!none_exact) {
           ProfScope ps(c, s, orb ? SLAMB200_K_ORB : SLAMB200_K_SIFT_TC);
           trc = launch_sift_tc_candidates(qmaps, q->flags, nq, tcp, pre_k, np, tiles_k, n_cta,
                                           n_slots, cand_k, d_status, k == 0 ? L.dbg : nullptr, 0, s,
@@ -1191,7 +1194,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
           CU(cudaEventRecord(L.sub_ev[k], s));
           CU(cudaStreamWaitEvent(s2, L.sub_ev[k], 0));
         }
-        {
+        if (!none_exact) {
           ProfScope ps(c, s2, orb ? SLAMB200_K_ORB : SLAMB200_K_SIFT_RERANK);
           launch_sift_rerank(q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, n_cta, n_slots, n_split,
                              cand_k, part_k, (uint4*)L.work.p + (size_t)p0 * nq,

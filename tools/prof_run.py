@@ -25,6 +25,14 @@ elif which == "orb":
         ctx.matchBatchEnqueue(Q, [T] * 8, MatcherType.ORB_BF, 0.7, st)
     torch.cuda.synchronize()
     print("ok", len(ctx.batchFetch(st)[0][0]))
+elif which == "gen":
+    # general-float SIFT (uniform noise): split-bf16 tcgen05 kernel + certified rerank
+    q, t = synth.float_pair(10000, 10000, 1002)
+    Q, T = ctx.upload(q), ctx.upload(t)
+    for _ in range(3):
+        ctx.matchBatchEnqueue(Q, [T] * 8, MatcherType.SIFT_BF, 0.7, st)
+    torch.cuda.synchronize()
+    print("ok", len(ctx.batchFetch(st)[0][0]))
 elif which == "ransac":
     p1, p2, R, tv = synth.two_view(5000, 5000)
     E = synth.pose_hypotheses(2048, R, tv, 5001)
