@@ -174,6 +174,7 @@ struct slamb200_ctx {
   bool pack_started = false;
   int sub_batch = 0;  // debug: pairs per tcgen05 launch when pipelining against the rerank
   int use_tc = 1;  // debug switch (slamb200_dbg_set_tc): 0 routes exact-mode pairs to the fp32 kernel
+  int fused_tail = 1;  // debug switch (slamb200_dbg_set_fused_tail): 0 = separate merge / rerank / finalize kernels
   int use_tc_orb = 1;  // debug switch (slamb200_dbg_set_tc_orb): 0 routes ORB pairs to the XOR/POPC kernel
 };
 
@@ -1194,6 +1195,26 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
           CU(cudaEventRecord(L.sub_ev[k], s));
           CU(cudaStreamWaitEvent(s2, L.sub_ev[k], 0));
         }
+        if (c->fused_tail && !want_knn) {
+          // match output: merge, best-group rerank and ratio test in one kernel, then compaction
+          // (general-float pairs of the batch are finalized by the same kernel from their records)
+          {
+            ProfScope ps(c, s2, orb ? SLAMB200_K_ORB : SLAMB200_K_SIFT_RERANK);
+            launch_tc_tail_fused(q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, n_cta, n_slots, n_split,
+                                 cand_k, part_k, d_status, ratio, orb ? 1 : 0,
+                                 (int32_t*)L.knn_idx.p + (size_t)p0 * nq * 2,
+                                 (float*)L.knn_dist.p + (size_t)p0 * nq * 2,
+                                 (uint8_t*)L.flags.p + (size_t)p0 * nq,
+                                 (int32_t*)L.chunk_cnt.p + (size_t)p0 * chunks, s2);
+          }
+          ProfScope psf(c, s2, SLAMB200_K_FINALIZE);
+          launch_compact(nq, np, (const int32_t*)L.knn_idx.p + (size_t)p0 * nq * 2,
+                         (const float*)L.knn_dist.p + (size_t)p0 * nq * 2,
+                         (const uint8_t*)L.flags.p + (size_t)p0 * nq,
+                         (const int32_t*)L.chunk_cnt.p + (size_t)p0 * chunks,
+                         (slamb200_dmatch*)L.out.p + (size_t)p0 * cap, cap, (int32_t*)L.n_out.p + p0, s2);
+          continue;
+        }
         if (!none_exact) {
           ProfScope ps(c, s2, orb ? SLAMB200_K_ORB : SLAMB200_K_SIFT_RERANK);
           launch_sift_rerank(q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, n_cta, n_slots, n_split,
@@ -1825,6 +1846,12 @@ extern "C" int slamb200_dbg_set_sub_batch(slamb200_ctx* c, int pairs) {
 extern "C" int slamb200_dbg_set_tc(slamb200_ctx* c, int on) {
   if (!c) return SLAMB200_ERR_INVALID;
   c->use_tc = on ? 1 : 0;
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_dbg_set_fused_tail(slamb200_ctx* c, int on) {
+  if (!c) return SLAMB200_ERR_INVALID;
+  c->fused_tail = on ? 1 : 0;
   return SLAMB200_OK;
 }
 

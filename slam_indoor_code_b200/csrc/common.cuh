@@ -205,6 +205,15 @@ void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32
                         int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                         uint4* work, float2* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
                         double ratio, cudaStream_t s, int orb = 0);
+// merge + best-group rerank + ratio test in one kernel (match output only); then launch_compact
+void launch_tc_tail_fused(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
+                          const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                          int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
+                          int32_t* err_flag, double ratio, int orb, int32_t* knn_idx, float* knn_dist,
+                          uint8_t* flags, int32_t* chunk_cnt, cudaStream_t s);
+void launch_compact(int nq, int n_pairs, const int32_t* knn_idx, const float* knn_dist,
+                    const uint8_t* flags, const int32_t* chunk_cnt, slamb200_dmatch* out, int cap,
+                    int32_t* n_out, cudaStream_t s);
 // ORB rows -> tcgen05 operands (sift_prep.cu): e4m3 0/1 bytes [n_pad][256] and the two
 // augmentation blocks [n_pad/8][256 B]
 void launch_orb_tc_prep(const uint8_t* u8, int n, int n_pad, uint8_t* e4, uint8_t* augq,

@@ -112,3 +112,19 @@ void launch_finalize(const uint4* part, int nq, const PairArgs* pairs, int n_pai
              (const uint8_t*)flags, (const int32_t*)chunk_cnt, nq, out, cap, n_out);
   COUNT_LAUNCH();
 }
+
+// Ordered compaction alone, behind a kernel that has already produced flags / chunk counts / best
+// index and distance per row (the fused tail of the tensor-core match path, sift_tc.cu).
+void launch_compact(int nq, int n_pairs, const int32_t* knn_idx, const float* knn_dist,
+                    const uint8_t* flags, const int32_t* chunk_cnt, slamb200_dmatch* out, int cap,
+                    int32_t* n_out, cudaStream_t s) {
+  if (n_pairs <= 0) return;
+  if (nq <= 0) {
+    cudaMemsetAsync(n_out, 0, sizeof(int32_t) * n_pairs, s);
+    return;
+  }
+  dim3 grid(finalize_chunks(nq), n_pairs);
+  launch_pdl(compact_kernel, grid, dim3(FIN_THREADS), 0, s, knn_idx, knn_dist, flags, chunk_cnt, nq, out, cap,
+             n_out);
+  COUNT_LAUNCH();
+}

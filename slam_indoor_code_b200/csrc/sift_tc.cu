@@ -1111,6 +1111,249 @@ __global__ void __launch_bounds__(256) orb_rerank_kernel(const RerankParams R) {
   }
 }
 
+// ================= fused tail of the match path =================
+// merge -> rerank (best group only) -> ratio test for one block of 256 query rows of one frame
+// pair, in one kernel: the three passes above exchange their intermediate results (work list,
+// partial records) through shared memory instead of HBM, and a single-pair call loses two
+// dependent launches.  Output is what compact_kernel (finalize.cu) consumes: the kept flag, the
+// best index and distance per row, and the block's kept count.  General-float pairs (their
+// records come from the certified rerank) take the plain finalize branch.  The arithmetic of each
+// step is that of sift_merge_kernel / sift_rerank_lite_kernel / orb_rerank_lite_kernel /
+// finalize_rows_kernel; the raw k-NN output keeps the separate kernels.
+__device__ __forceinline__ void part_top2_insert(uint4& r, uint32_t k, uint32_t i) {
+  const bool lt2 = k < r.z || (k == r.z && i < r.w);
+  if (lt2) {
+    const bool lt1 = k < r.x || (k == r.x && i < r.y);
+    if (lt1) { r.z = r.x; r.w = r.y; r.x = k; r.y = i; }
+    else { r.z = k; r.w = i; }
+  }
+}
+
+template <bool ORB>
+__global__ void __launch_bounds__(256)
+tc_tail_fused_kernel(const RerankParams R, int32_t* __restrict__ knn_idx, float* __restrict__ knn_dist,
+                     uint8_t* __restrict__ flags, int32_t* __restrict__ chunk_cnt) {
+  __shared__ int n_valid_s, n_surv_s;
+  __shared__ uint16_t s_list[256];
+  __shared__ float s_v0[256], s_L[256], s_d0[256], s_d1[256];
+  __shared__ int s_g0[256], s_idx[256];
+  const int pair = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = blockIdx.x * 256 + tid;
+  PDL_TRIGGER();
+  PDL_WAIT();
+  const TcPair* pr = R.pairs + pair;
+  const float INF = __int_as_float(0x7f800000);
+  int keep = 0;
+  if (R.q_flags[0] != 0 || pr->t_flags[0] != 0) {
+    // general-float pair (block-uniform): finalize its records
+    if (q < R.nq) {
+      uint4 r = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+      for (int sp = 0; sp < R.n_split; sp++) {
+        const uint4 p = R.part[((size_t)pair * R.n_split + sp) * R.nq + q];
+        if (p.y != 0xFFFFFFFFu) part_top2_insert(r, p.x, p.y);
+        if (p.w != 0xFFFFFFFFu) part_top2_insert(r, p.z, p.w);
+      }
+      const bool has0 = r.y != 0xFFFFFFFFu, has1 = r.w != 0xFFFFFFFFu;
+      const float d0 = __uint_as_float(r.x), d1 = __uint_as_float(r.z);
+      const size_t o = ((size_t)pair * R.nq + q) * 2;
+      knn_idx[o] = has0 ? (int32_t)r.y : -1;
+      knn_dist[o] = has0 ? d0 : 0.f;
+      keep = (has0 && has1 && (double)d0 < __dmul_rn(R.ratio, (double)d1)) ? 1 : 0;
+      flags[(size_t)pair * R.nq + q] = (uint8_t)keep;
+    }
+  } else {
+    if (tid == 0) {
+      // slots the tcgen05 kernel wrote for this (pair, query block): see sift_merge_kernel
+      const int n_tiles = R.tile_prefix[pair + 1] - R.tile_prefix[pair];
+      int nv = 0;
+      if (n_tiles > 0) {
+        const int n_rb = R.nq_pad / 256;
+        const int n_cb = n_tiles / n_rb;
+        const int first = owner_cta(n_tiles, R.n_cta, blockIdx.x * n_cb);
+        const int last = owner_cta(n_tiles, R.n_cta, (blockIdx.x + 1) * n_cb - 1);
+        nv = COL_SPLITS * (last - first + 1);
+        if (nv > R.n_slots) nv = R.n_slots;
+      }
+      n_valid_s = nv;
+      n_surv_s = 0;
+    }
+    __syncthreads();
+    const int n_valid = n_valid_s;
+    bool survive = false;
+    float v0 = INF, v1 = INF, s0 = INF;
+    int g0 = 0xFFFF, g1 = 0xFFFF;
+    if (q < R.nq) {
+      for (int sb = 0; sb < n_valid; sb += 4) {
+        uint4 recs[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)   // independent loads first, then the dependent merge
+          recs[j] = sb + j < n_valid ? R.cand[((size_t)pair * R.n_slots + sb + j) * R.nq_pad + q]
+                                     : make_uint4(0x7f800000u, 0x7f800000u, 0x7f800000u, 0xFFFFFFFFu);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint4 rec = recs[j];
+          const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.y);
+          float sa = __uint_as_float(rec.z);
+          int ia = (int)(rec.w & 0xFFFFu), ib = (int)(rec.w >> 16);
+          if (ORB) {
+            if (a > ORB_PAD_THRESHOLD) ia = 0xFFFF;
+            if (b > ORB_PAD_THRESHOLD) ib = 0xFFFF;
+            if (sa > ORB_PAD_THRESHOLD) sa = INF;
+          }
+          if (ia != 0xFFFF) {
+            if (lt_fi(a, ia, v0, g0)) { v1 = v0; g1 = g0; v0 = a; g0 = ia; s0 = sa; }
+            else if (lt_fi(a, ia, v1, g1)) { v1 = a; g1 = ia; }
+          }
+          if (ib != 0xFFFF) {
+            if (lt_fi(b, ib, v1, g1)) { v1 = b; g1 = ib; }
+          }
+        }
+      }
+      const bool has0 = g0 != 0xFFFF;
+      survive = has0;
+      const float L = fminf(s0, v1);
+      if (R.prune && has0 && L < INF) {
+        const float d0 = ORB ? 2.0f * v0 : sqrtf(2.0f * v0), D1 = ORB ? 2.0f * L : sqrtf(2.0f * L);
+        if (!((double)d0 < __dmul_rn(R.ratio, (double)D1))) survive = false;   // exact pruning
+      }
+      s_v0[tid] = v0; s_L[tid] = L; s_g0[tid] = g0;
+    }
+    {
+      const unsigned bal = __ballot_sync(0xffffffffu, survive);
+      int base = 0;
+      if (lane == 0 && bal) base = atomicAdd(&n_surv_s, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (survive) s_list[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)tid;
+    }
+    __syncthreads();
+    const int n_surv = n_surv_s;
+    // Survivors of the block: one warp per row, 4 lanes x 8 candidates.  Four rows are in flight
+    // per warp (all their loads are issued before the first reduction): a single-pair call has
+    // only 40 of these blocks, so the dependent-load latency per row is what matters.
+    const int part = lane & 3, cand = lane >> 2;
+    constexpr int U = 4;
+    for (int i0 = warp; i0 < n_surv; i0 += 8 * U) {
+      int rr[U], colv[U];
+      bool okv[U];
+      uint32_t dist[U];   // exact integer distance of this lane's candidate: d^2 (SIFT) or Hamming (ORB)
+      if (ORB) {
+        unsigned long long tv[U], qv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int i = i0 + 8 * u;
+          rr[u] = i < n_surv ? s_list[i] : -1;
+          const int r = rr[u] >= 0 ? rr[u] : 0;
+          colv[u] = s_g0[r] * GROUP + cand;
+          okv[u] = rr[u] >= 0 && colv[u] < pr->t_n;
+          const int cc = okv[u] ? colv[u] : 0;
+          tv[u] = *reinterpret_cast<const unsigned long long*>(pr->t_u8 + (size_t)cc * 32 + part * 8);
+          qv[u] = *reinterpret_cast<const unsigned long long*>(R.q_u8 + (size_t)(blockIdx.x * 256 + r) * 32 + part * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) dist[u] = (uint32_t)__popcll(qv[u] ^ tv[u]);
+      } else {
+        uint4 t0[U], t1[U], q0[U], q1[U];
+        uint32_t nn[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int i = i0 + 8 * u;
+          rr[u] = i < n_surv ? s_list[i] : -1;
+          const int r = rr[u] >= 0 ? rr[u] : 0;
+          colv[u] = s_g0[r] * GROUP + cand;
+          okv[u] = rr[u] >= 0 && colv[u] < pr->t_n;
+          const int cc = okv[u] ? colv[u] : 0;
+          const int qq = blockIdx.x * 256 + r;
+          const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)cc * 128 + part * 32);
+          const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 128 + part * 32);
+          t0[u] = tp[0]; t1[u] = tp[1]; q0[u] = qp[0]; q1[u] = qp[1];
+          nn[u] = (uint32_t)pr->t_nrm2[cc] + (uint32_t)R.q_nrm2[qq];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          uint32_t dot = 0;
+          dot = __dp4a(q0[u].x, t0[u].x, dot); dot = __dp4a(q0[u].y, t0[u].y, dot);
+          dot = __dp4a(q0[u].z, t0[u].z, dot); dot = __dp4a(q0[u].w, t0[u].w, dot);
+          dot = __dp4a(q1[u].x, t1[u].x, dot); dot = __dp4a(q1[u].y, t1[u].y, dot);
+          dot = __dp4a(q1[u].z, t1[u].z, dot); dot = __dp4a(q1[u].w, t1[u].w, dot);
+          dist[u] = dot;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {   // the four lanes of a candidate hold partial dot products
+          dist[u] += __shfl_xor_sync(0xffffffffu, dist[u], 1);
+          dist[u] += __shfl_xor_sync(0xffffffffu, dist[u], 2);
+          dist[u] = nn[u] - 2u * dist[u];
+        }
+      }
+      if (ORB) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          dist[u] += __shfl_xor_sync(0xffffffffu, dist[u], 1);
+          dist[u] += __shfl_xor_sync(0xffffffffu, dist[u], 2);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (rr[u] < 0) continue;   // warp-uniform
+        const int r = rr[u];
+        unsigned long long k0 = okv[u] ? (((unsigned long long)dist[u] << 32) | (uint32_t)colv[u]) : ~0ull;
+        unsigned long long k1 = ~0ull;
+#pragma unroll
+        for (int off = 4; off <= 16; off <<= 1) {
+          const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, off);
+          const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off);
+          const unsigned long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0;
+          const unsigned long long s2 = k1 < o1 ? k1 : o1;
+          k0 = lo;
+          k1 = hi < s2 ? hi : s2;
+        }
+        if (lane == 0) {
+          float d0 = 0.f, d1 = -1.f;   // d1 < 0: no second neighbour
+          int idx = -1;
+          if (k0 != ~0ull) {
+            const uint32_t x0 = (uint32_t)(k0 >> 32);
+            // self check: the group's exact minimum must equal twice the tensor-core value
+            if ((float)x0 != 2.0f * s_v0[r]) atomicOr(R.err_flag, 1);
+            idx = (int)(uint32_t)(k0 & 0xFFFFFFFFu);
+            // second distance: inside the group, or the bound from outside it (exact values both)
+            const float Lr = s_L[r];
+            float x1 = Lr < INF ? 2.0f * Lr : -1.0f;
+            if (k1 != ~0ull) {
+              const float x2 = (float)(uint32_t)(k1 >> 32);
+              x1 = (x1 < 0.0f || x2 < x1) ? x2 : x1;
+            }
+            if (ORB) {
+              d0 = (float)x0;
+              d1 = x1;
+            } else {
+              d0 = sqrtf((float)x0);
+              d1 = x1 >= 0.0f ? sqrtf(x1) : -1.0f;
+            }
+          }
+          s_d0[r] = d0; s_d1[r] = d1; s_idx[r] = idx;
+        }
+      }
+    }
+    __syncthreads();
+    if (q < R.nq) {
+      int idx = -1;
+      float d0 = 0.f;
+      if (survive) {
+        idx = s_idx[tid];
+        d0 = s_d0[tid];
+        const float d1 = s_d1[tid];
+        keep = (idx >= 0 && d1 >= 0.0f && (double)d0 < __dmul_rn(R.ratio, (double)d1)) ? 1 : 0;
+      }
+      const size_t o = ((size_t)pair * R.nq + q) * 2;
+      knn_idx[o] = idx;
+      knn_dist[o] = d0;
+      flags[(size_t)pair * R.nq + q] = (uint8_t)keep;
+    }
+  }
+  const int n = __syncthreads_count(keep);
+  if (tid == 0) chunk_cnt[pair * gridDim.x + blockIdx.x] = n;
+}
+
 // ================= general-float pairs: certify-or-fallback rerank =================
 struct GenParams {
   const float* q_f32;
@@ -1564,5 +1807,27 @@ void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32
   } else {
     launch_pdl(sift_rerank_kernel, dim3(blocks), dim3(256), 0, s, R);        // raw k-NN output: both indices
   }
+  COUNT_LAUNCH();
+}
+
+// The fused tail of the match path: fills knn_idx[.][0], knn_dist[.][0], flags and chunk_cnt for
+// compact_kernel (launch_compact, finalize.cu).
+void launch_tc_tail_fused(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
+                          const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                          int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
+                          int32_t* err_flag, double ratio, int orb, int32_t* knn_idx, float* knn_dist,
+                          uint8_t* flags, int32_t* chunk_cnt, cudaStream_t s) {
+  if (nq <= 0 || n_pairs <= 0) return;
+  RerankParams R;
+  R.orb = orb;
+  R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
+  R.tile_prefix = tile_prefix_dev; R.n_cta = n_cta_pairs;
+  R.nq = nq; R.nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM); R.n_slots = n_slots; R.n_pairs = n_pairs;
+  R.n_split = n_split; R.part = part; R.err_flag = err_flag;
+  R.work = nullptr; R.work_v0 = nullptr; R.work_n = nullptr;
+  R.prune = (ratio >= 0.0 && ratio < 1e300) ? 1 : 0; R.ratio = ratio;
+  dim3 grid((nq + 255) / 256, n_pairs);
+  if (orb) launch_pdl(tc_tail_fused_kernel<true>, grid, dim3(256), 0, s, R, knn_idx, knn_dist, flags, chunk_cnt);
+  else launch_pdl(tc_tail_fused_kernel<false>, grid, dim3(256), 0, s, R, knn_idx, knn_dist, flags, chunk_cnt);
   COUNT_LAUNCH();
 }
