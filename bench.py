@@ -522,9 +522,9 @@ def run_b200(args, rank, world, local):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one tcgen05-kernel launch over the 210-pair window
 # (N=1), from the committed `ncu --set full` capture profiles/r01_ncu_sift_tc_final.txt:
-# 622.5 MB read + 182.9 MB written.  Compulsory bytes of that launch: 211 descriptor sets x 2.9 MB
+# 631.2 MB read + 185.1 MB written.  Compulsory bytes of that launch: 211 descriptor sets x 2.9 MB
 # of bf16 operands + 206 MB of slot records = 818 MB, i.e. no re-reads.
-TRAFFIC_BYTES_PER_LAUNCH_N1 = 805_429_504
+TRAFFIC_BYTES_PER_LAUNCH_N1 = 816_323_072
 
 
 def cpu_baseline(q, trains, gpu_matches, seconds):
@@ -705,11 +705,22 @@ def extras(ctx, stream):
         out["pipe_rates"] = {"error": str(e)}
     # cfg4: 8 frames x 50,000 descriptors (4K frames), all 28 i<j pairs of the BA window
     frames = [ctx.upload(synth.sift_like(50000, 4000 + f)) for f in range(8)]
-    for _ in range(2):
+    # the synchronous calls rotate over the context's lanes, each of which sizes its own scratch
+    # on first use: warm up until two consecutive windows agree, then take the best of three
+    prev = None
+    for _ in range(12):
+        t0 = time.perf_counter()
         ctx.matchWindow(frames, MatcherType.SIFT_BF, RATIO)
-    t0 = time.perf_counter()
-    res = ctx.matchWindow(frames, MatcherType.SIFT_BF, RATIO)
-    dt = time.perf_counter() - t0
+        cur = time.perf_counter() - t0
+        if prev is not None and abs(cur - prev) < 0.1 * prev:
+            break
+        prev = cur
+    dt = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res = ctx.matchWindow(frames, MatcherType.SIFT_BF, RATIO)
+        cur = time.perf_counter() - t0
+        dt = cur if dt is None else min(dt, cur)
     out["cfg4_window_8x50k"] = {"ms_per_window_host_call": dt * 1e3, "pairs": len(res),
                                 "tflops_incl_copies": len(res) * 2 * 50000.0 * 50000 * 128 / dt / 1e12}
     for f in frames:
