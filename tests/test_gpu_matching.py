@@ -639,3 +639,47 @@ def test_sift_equal_best_and_second_with_ratio_above_one(ctx):
                               c_oracle.ratio_test(ridx, rdist, r))
     idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, Q, T)
     _check_knn(idx, dist, ridx, rdist)
+
+
+@pytest.mark.gpu
+def test_general_float_two_nearest_in_one_chunk(ctx):
+    """The certified rerank first reads only the best 8-column group of each of the four best
+    32-column chunks.  Here the two nearest train rows of every query sit in the SAME chunk but in
+    different groups, so that first stage cannot certify and the whole-chunk stage must."""
+    rng = np.random.default_rng(91)
+    q, t = synth.float_pair(512, 4096, 1510)
+    for k in range(512):
+        c = int(rng.integers(0, 4096 // 32))
+        g = rng.permutation(4)[:2]
+        a, b = 32 * c + 8 * int(g[0]) + int(rng.integers(0, 8)), 32 * c + 8 * int(g[1]) + int(rng.integers(0, 8))
+        t[a] = q[k] + rng.normal(0, 0.5, 128).astype(np.float32)
+        t[b] = q[k] + rng.normal(0, 0.9, 128).astype(np.float32)
+    idx, dist, good = _knn_and_matches(ctx, MatcherType.SIFT_BF, q, t, ratio=0.8)
+    ridx, rdist = c_oracle.l2_knn2(q, t)
+    _check_knn(idx, dist, ridx, rdist)
+    assert np.array_equal(good, c_oracle.ratio_test(ridx, rdist, 0.8))
+    # the construction did what it says for most rows (later plants may overwrite earlier ones)
+    same_chunk = (ridx[:, 0] // 32 == ridx[:, 1] // 32) & (ridx[:, 0] // 8 != ridx[:, 1] // 8)
+    assert same_chunk.mean() > 0.6
+
+
+@pytest.mark.gpu
+def test_general_float_many_fallback_rows(ctx):
+    """More uncertifiable rows than the fallback grid has blocks: the unsplit full-row scan."""
+    import ctypes
+    rng = np.random.default_rng(92)
+    q, t = synth.float_pair(800, 30000, 1511)
+    for k in range(700):
+        rows = rng.choice(30000, 40, replace=False)
+        t[rows] = q[k] + rng.normal(0, 2e-3, (40, 128)).astype(np.float32)
+    Q, T = ctx.upload(q), ctx.upload(t)
+    idx, dist = ctx.knnMatch(MatcherType.SIFT_BF, Q, T)
+    ridx, rdist = c_oracle.l2_knn2(q, t)
+    _check_knn(idx, dist, ridx, rdist)
+    ctx.matchBatchEnqueue(Q, [T], MatcherType.SIFT_BF, 0.95)
+    lib = ctx._lib
+    lib.slamb200_dbg_last_fallback_rows.argtypes = [ctypes.c_void_p]
+    n_fb = lib.slamb200_dbg_last_fallback_rows(ctx._h)
+    assert n_fb >= 592, n_fb
+    got, _ = ctx.batchFetch()
+    assert np.array_equal(got[0], c_oracle.ratio_test(ridx, rdist, 0.95))
