@@ -30,8 +30,18 @@
 // second best is either in that same chunk or is the minimum of the second-best chunk (ties
 // resolve to the lowest index at every level).  So the rerank evaluates 32 + 8 = 40 candidates per
 // row exactly -- integer dp4a on the u8 copies -- and emits (sqrtf(d^2), index) records that the
-// shared finalize kernels turn into the ratio-tested, ordered match list.  A device-side self check compares each rerank minimum with the
-// tensor-core value and raises err_flag on any mismatch (never expected).
+// shared finalize kernels turn into the ratio-tested, ordered match list.  A device-side self
+// check compares each rerank minimum with the tensor-core value and raises err_flag on any
+// mismatch (never expected).
+//
+// Also in this file:
+//  * the match-output tail fused into one kernel (tc_tail_fused_kernel: slot merge, exact
+//    ratio-test pruning, best-group rerank, ratio test; compaction follows in finalize.cu);
+//  * general-float sets (GEN instantiation: two-term bf16 split, 25 MMAs per tile) with the
+//    certified fp32 rerank in OpenCV's summation order and the exact fallback scan;
+//  * ORB: the same exact-mode kernel on e4m3 0/1 bytes (kind::f8f6f4, TcParams::fp8) -- Hamming
+//    distance is the squared L2 distance of the bit vectors -- with XOR/POPC rerank kernels
+//    (featureMatchingCPU.cpp:33-35: BRUTEFORCE_HAMMING).
 #include <cuda.h>
 #include <stdio.h>
 #include <string.h>
