@@ -356,6 +356,8 @@ def run_b200(args, rank, world, local):
                 "algorithmic_flop_per_step": FLOP_PER_PAIR * len(pairs),
                 "other_kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()
                                               if k != "sift_tc" and v[1] > 0},
+                "other_kernels_note": "sift_rerank = tc_tail_fused_kernel (slot merge + best-group rerank + "
+                                      "ratio test), finalize = compact_kernel (ordered compaction)",
                 "kernel_share_of_step": tc_ms / ms_total
                 if world == 1 else None,
                 "traffic": TRAFFIC_BYTES_PER_LAUNCH_N1 if world == 1 else None,
