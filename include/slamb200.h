@@ -233,6 +233,18 @@ int slamb200_orb_compute(slamb200_ctx* ctx, const uint8_t* image, int rows, int 
                          size_t step, const float* kps, int n, uint8_t* keep, uint8_t* desc,
                          int* n_kept, slamb200_desc** resident);
 
+/* ---- next row: FAST keypoints (featureExtraction/fastExtractor.cpp:7-13) --- */
+/* FastFeatureDetector::create(threshold, nonmax, TYPE_9_16)->detect(image, points), the reference's
+ * fastExtractor (callers cycleProcessing/batch.cpp:245, mainCycleInternals.cpp:144 with
+ * featureExtractingThreshold): image = rows x cols CV_8UC3 (BGR, converted like cvtColor) or
+ * CV_8UC1, `step` bytes per row.  kps receives up to cap rows of {x, y, response} floats in
+ * OpenCV's order (row by row, left to right) -- KeyPoint(x, y, size 7, angle -1, response);
+ * response is the corner score with suppression and 0 without, as in OpenCV.  *n_found is the
+ * number of keypoints in the frame; when it exceeds cap only the first cap are written.  Same
+ * keypoints and responses as OpenCV. */
+int slamb200_fast_detect(slamb200_ctx* ctx, const uint8_t* image, int rows, int cols, int channels,
+                         size_t step, int threshold, int nonmax, float* kps, int cap, int* n_found);
+
 /* ---- next row: linear triangulation (triangulation/triangulate.cpp:17-55, :91-108) --- */
 /* reconstructPointsFor3D for M matches: P1, P2 = 3x4 row-major projection matrices (K*[R|t], as
  * reconstruct() forms them at triangulate.cpp:74-80), pts = M x 2 floats (vector<Point2f>).  Per
@@ -273,7 +285,8 @@ int slamb200_batch_scores_fetch(slamb200_ctx* ctx, int32_t* counts, int32_t* bes
 #define SLAMB200_K_PNP 8        /* reprojection-error counting kernel */
 #define SLAMB200_K_SIFT_L1 9    /* NORM_L1 on integer-valued rows (byte-wise SAD) */
 #define SLAMB200_K_ORB_DESC 10  /* ORB gray + blur + descriptor kernels */
-#define SLAMB200_K_COUNT 11
+#define SLAMB200_K_FAST 11      /* gray + FAST score, suppression, ordered output */
+#define SLAMB200_K_COUNT 12
 int slamb200_profile_enable(slamb200_ctx* ctx, int on);
 /* Synchronises, then returns the summed device time (ms) and the launch count of each kernel
  * class since the last read; ms and launches have SLAMB200_K_COUNT entries. */

@@ -216,3 +216,18 @@ def orb_compute(image, kps):
                                     _p(keep), _p(desc))
     assert kept >= 0
     return keep[:n], desc[:kept].copy()
+
+
+def fast_detect(image, threshold=10, nonmax=True, want_scores=False):
+    """FastFeatureDetector::create(threshold, nonmax, TYPE_9_16)->detect(image): [n, 3] float32 rows
+    of x, y, response in OpenCV's order (row by row, left to right)."""
+    image = np.ascontiguousarray(image, np.uint8)
+    rows, cols = image.shape[:2]
+    ch = 1 if image.ndim == 2 else image.shape[2]
+    cap = max(rows * cols, 1)
+    kp = np.zeros((cap, 3), np.float32)
+    score = np.zeros((rows, cols), np.uint8)
+    n = lib().oracle_fast_detect(_p(image), rows, cols, ch, ctypes.c_size_t(image.strides[0]), int(threshold),
+                                 1 if nonmax else 0, _p(kp), cap, _p(score))
+    assert n >= 0
+    return (kp[:n].copy(), score) if want_scores else kp[:n].copy()

@@ -668,3 +668,112 @@ int oracle_orb_compute(const uint8_t* image, int rows, int cols, int channels, s
     free(blur);
     return kept;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * FAST keypoints (reference: featureExtraction/fastExtractor.cpp:7-13 --
+ * FastFeatureDetector::create(threshold, suppression, TYPE_9_16)->detect(frame, points), called
+ * from cycleProcessing/batch.cpp:245 and mainCycleInternals.cpp:144 with
+ * featureExtractingThreshold).
+ *
+ * OpenCV features2d (fast.cpp FAST_t<16>, fast_score.cpp cornerScore<16>): a BGR frame is
+ * converted with cvtColor(BGR2GRAY); pixel (x, y), 3 <= x < cols-3, 3 <= y < rows-3, is a corner
+ * iff at least 9 contiguous pixels of the 16-pixel Bresenham circle are all darker than v - t or
+ * all brighter than v + t (strict); its score is the largest threshold for which it stays a corner
+ * (min/max over the nine-pixel arcs, below); with suppression a corner survives iff its score is
+ * strictly greater than the scores of its 8 neighbours (non-corners score 0).  Keypoints come out
+ * row by row, left to right: KeyPoint(x, y, size 7, angle -1, response = score; 0 without
+ * suppression).  Pinned against cv2.FastFeatureDetector (tests/test_oracle_vs_cv2.py).
+ * ---------------------------------------------------------------------------------------------- */
+static const int kFastCircle[16][2] = {{0, 3}, {1, 3}, {2, 2}, {3, 1}, {3, 0}, {3, -1}, {2, -2}, {1, -3},
+                                       {0, -3}, {-1, -3}, {-2, -2}, {-3, -1}, {-3, 0}, {-3, 1}, {-2, 2}, {-1, 3}};
+
+static int fast_is_corner(const uint8_t* p, const int* off, int t) {
+    const int v = p[0];
+    int dark = 0, bright = 0;
+    for (int k = 0; k < 25; k++) {   /* the circle, wrapped by 9: every arc of 9 is seen */
+        const int x = p[off[k & 15]];
+        dark = x < v - t ? dark + 1 : 0;
+        bright = x > v + t ? bright + 1 : 0;
+        if (dark > 8 || bright > 8) return 1;
+    }
+    return 0;
+}
+
+static int fast_corner_score(const uint8_t* p, const int* off, int threshold) {
+    int d[25];
+    const int v = p[0];
+    for (int k = 0; k < 25; k++) d[k] = v - p[off[k & 15]];
+    int a0 = threshold;
+    for (int k = 0; k < 16; k += 2) {
+        int a = d[k + 1] < d[k + 2] ? d[k + 1] : d[k + 2];
+        a = a < d[k + 3] ? a : d[k + 3];
+        if (a <= a0) continue;
+        for (int j = 4; j <= 8; j++) a = a < d[k + j] ? a : d[k + j];
+        int m = a < d[k] ? a : d[k];
+        a0 = a0 > m ? a0 : m;
+        m = a < d[k + 9] ? a : d[k + 9];
+        a0 = a0 > m ? a0 : m;
+    }
+    int b0 = -a0;
+    for (int k = 0; k < 16; k += 2) {
+        int b = d[k + 1] > d[k + 2] ? d[k + 1] : d[k + 2];
+        for (int j = 3; j <= 5; j++) b = b > d[k + j] ? b : d[k + j];
+        if (b >= b0) continue;
+        for (int j = 6; j <= 8; j++) b = b > d[k + j] ? b : d[k + j];
+        int m = b > d[k] ? b : d[k];
+        b0 = b0 < m ? b0 : m;
+        m = b > d[k + 9] ? b : d[k + 9];
+        b0 = b0 < m ? b0 : m;
+    }
+    return -b0 - 1;
+}
+
+/* image: rows x cols, channels 1 (gray) or 3 (BGR), `step` bytes per row.  kp: up to cap rows of
+ * {x, y, response}.  Returns the number of keypoints found (may exceed cap: only cap are written)
+ * or < 0.  score_out (optional, rows*cols): the score map before suppression (0 = not a corner). */
+int oracle_fast_detect(const uint8_t* image, int rows, int cols, int channels, size_t step,
+                       int threshold, int nonmax, float* kp, int cap, uint8_t* score_out) {
+    if (rows < 0 || cols < 0 || (channels != 1 && channels != 3)) return -1;
+    const size_t npx = (size_t)(rows > 0 ? rows : 1) * (cols > 0 ? cols : 1);
+    uint8_t* gray = (uint8_t*)malloc(npx);
+    uint8_t* score = (uint8_t*)calloc(npx, 1);
+    uint8_t* corner = (uint8_t*)calloc(npx, 1);
+    if (!gray || !score || !corner) { free(gray); free(score); free(corner); return -2; }
+    for (int y = 0; y < rows; y++) {
+        const uint8_t* s = image + (size_t)y * step;
+        for (int x = 0; x < cols; x++)
+            gray[(size_t)y * cols + x] = channels == 1 ? s[x]
+                : (uint8_t)((s[3 * x] * 3735 + s[3 * x + 1] * 19235 + s[3 * x + 2] * 9798 + (1 << 14)) >> 15);
+    }
+    threshold = threshold < 0 ? 0 : threshold > 255 ? 255 : threshold;
+    int off[16];
+    for (int k = 0; k < 16; k++) off[k] = kFastCircle[k][0] + kFastCircle[k][1] * cols;
+#pragma omp parallel for schedule(static)
+    for (int y = 3; y < rows - 3; y++)
+        for (int x = 3; x < cols - 3; x++) {
+            const uint8_t* p = gray + (size_t)y * cols + x;
+            if (fast_is_corner(p, off, threshold)) {
+                corner[(size_t)y * cols + x] = 1;
+                score[(size_t)y * cols + x] = (uint8_t)fast_corner_score(p, off, threshold);
+            }
+        }
+    int n = 0;
+    for (int y = 3; y < rows - 3; y++)
+        for (int x = 3; x < cols - 3; x++) {
+            const size_t o = (size_t)y * cols + x;
+            if (!corner[o]) continue;
+            const int s = score[o];
+            int keep = 1;
+            if (nonmax)
+                keep = s > score[o - 1] && s > score[o + 1] && s > score[o - cols - 1] && s > score[o - cols] &&
+                       s > score[o - cols + 1] && s > score[o + cols - 1] && s > score[o + cols] &&
+                       s > score[o + cols + 1];
+            if (keep) {
+                if (n < cap) { kp[3 * n] = (float)x; kp[3 * n + 1] = (float)y; kp[3 * n + 2] = nonmax ? (float)s : 0.f; }
+                n++;
+            }
+        }
+    if (score_out) memcpy(score_out, score, (size_t)rows * cols);
+    free(gray); free(score); free(corner);
+    return n;
+}

@@ -191,6 +191,17 @@ def gen_pnp():
     np.savez_compressed(os.path.join(OUT, "pnp.npz"), **cases)
 
 
+def gen_fast():
+    """fastExtractor (fastExtractor.cpp:7-13): cv2's FAST-9/16 keypoints {x, y, response} of a small
+    BGR frame, with and without suppression, at the reference's default threshold and another."""
+    frame = synth.textured_frame(120, 168, 6200, 3)
+    out = {"frame": frame}
+    for thr, nms in ((10, True), (10, False), (25, True)):
+        kps = cv2.FastFeatureDetector_create(thr, nms, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16).detect(frame)
+        out[f"kp_t{thr}_n{int(nms)}"] = np.array([[k.pt[0], k.pt[1], k.response] for k in kps], np.float32).reshape(-1, 3)
+    np.savez_compressed(os.path.join(OUT, "fast.npz"), **out)
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "pnp":
@@ -199,5 +210,7 @@ if __name__ == "__main__":
         gen_l1()
     elif len(sys.argv) > 1 and sys.argv[1] == "orb_desc":
         gen_orb_desc()
+    elif len(sys.argv) > 1 and sys.argv[1] == "fast":
+        gen_fast()
     else:
         main()

@@ -60,6 +60,7 @@ struct Lane {
   // scoring scratch (device)
   DevBuf npts, E, counts, best, mask, m_off, p1, p2, txy, all_masks;
   DevBuf orb_img, orb_gray, orb_rowf, orb_blur, orb_kp, orb_desc;
+  DevBuf fast_score, fast_cnt, fast_kp;
   // pinned staging
   // pinned staging ring: the host fills slot k+1 while the copy out of slot k may still be
   // queued behind the previous step's kernels (an enqueue never waits for the device)
@@ -311,7 +312,8 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
     DevBuf* bufs[] = {&L.pairs, &L.tcpairs, &L.tile_prefix, &L.work, &L.work_v0, &L.fb_list, &L.cand_g, &L.part, &L.cand, &L.knn_idx, &L.knn_dist, &L.flags,
                       &L.chunk_cnt, &L.out, &L.n_out, &L.err_flag, &L.npts, &L.E, &L.counts,
                       &L.best, &L.mask, &L.m_off, &L.p1, &L.p2, &L.txy, &L.all_masks,
-                      &L.orb_img, &L.orb_gray, &L.orb_rowf, &L.orb_blur, &L.orb_kp, &L.orb_desc};
+                      &L.orb_img, &L.orb_gray, &L.orb_rowf, &L.orb_blur, &L.orb_kp, &L.orb_desc,
+                      &L.fast_score, &L.fast_cnt, &L.fast_kp};
     for (DevBuf* b : bufs)
       if (b->p) cudaFreeAsync(b->p, L.stream);
     cudaStreamSynchronize(L.stream);
@@ -1669,6 +1671,54 @@ extern "C" int slamb200_orb_compute(slamb200_ctx* c, const uint8_t* image, int r
       // the lane's descriptor buffer may be overwritten by the next call only after that copy
       CU(cudaStreamWaitEvent(s, (*resident)->ready, 0));
     }
+    CU(cudaStreamSynchronize(s));
+  }
+  return SLAMB200_OK;
+}
+
+// ---- FAST keypoints (fastExtractor.cpp:7-13) --------------------------------------
+extern "C" int slamb200_fast_detect(slamb200_ctx* c, const uint8_t* image, int rows, int cols,
+                                    int channels, size_t step, int threshold, int nonmax,
+                                    float* kps, int cap, int* n_found) {
+  if (!c || !n_found) return fail(SLAMB200_ERR_INVALID, "fast_detect: NULL argument");
+  *n_found = 0;
+  if (rows < 0 || cols < 0 || ((rows > 0 && cols > 0) && !image))
+    return fail(SLAMB200_ERR_INVALID, "fast_detect: bad image");
+  if (channels != 1 && channels != 3)
+    return fail(SLAMB200_ERR_KIND, "fast_detect: %d-channel image (CV_8UC1 or CV_8UC3 expected)", channels);
+  if (cap < 0 || (cap > 0 && !kps)) return fail(SLAMB200_ERR_INVALID, "fast_detect: bad output buffer");
+  if (rows > 65535) return fail(SLAMB200_ERR_INVALID, "fast_detect: more than 65535 rows");
+  if (rows < 7 || cols < 7) return SLAMB200_OK;   // no pixel is 3 px away from every border
+  if (step == 0) step = (size_t)cols * channels;
+  if (step < (size_t)cols * channels) return fail(SLAMB200_ERR_INVALID, "fast_detect: step too small");
+  CU(cudaSetDevice(c->device));
+  int rc;
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  cudaStream_t s = L.stream;
+  const size_t px = (size_t)rows * cols;
+  const int nb = fast_blocks(rows, cols);
+  if ((rc = buf_reserve(c, L.orb_img, (size_t)rows * step, s))) return rc;
+  if ((rc = buf_reserve(c, L.orb_gray, px, s))) return rc;
+  if ((rc = buf_reserve(c, L.fast_score, px * sizeof(int16_t), s))) return rc;
+  if ((rc = buf_reserve(c, L.fast_cnt, sizeof(int32_t) * ((size_t)nb + 1), s))) return rc;
+  if ((rc = buf_reserve(c, L.fast_kp, sizeof(float) * 3 * (size_t)(cap > 0 ? cap : 1), s))) return rc;
+  CU(cudaMemcpyAsync(L.orb_img.p, image, (size_t)rows * step, cudaMemcpyHostToDevice, s));
+  {
+    ProfScope ps(c, s, SLAMB200_K_FAST);
+    launch_orb_gray((const uint8_t*)L.orb_img.p, rows, cols, channels, step, (uint8_t*)L.orb_gray.p, s);
+    launch_fast_detect((const uint8_t*)L.orb_gray.p, rows, cols, threshold, nonmax ? 1 : 0,
+                       (int16_t*)L.fast_score.p, (int32_t*)L.fast_cnt.p, (float*)L.fast_kp.p, cap, s);
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(L.h_small, (int32_t*)L.fast_cnt.p + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(L.done, s));
+  CU(cudaStreamSynchronize(s));
+  const int found = L.h_small[0];
+  *n_found = found;
+  const int n_copy = found < cap ? found : cap;
+  if (n_copy > 0) {
+    CU(cudaMemcpyAsync(kps, L.fast_kp.p, sizeof(float) * 3 * (size_t)n_copy, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
   }
   return SLAMB200_OK;

@@ -151,6 +151,12 @@ void launch_pnp_all_masks(const double4* pts, int M, const double* poses, int H,
 // ORB descriptors of given keypoints (orb_desc.cu): centre pixel and cosf/sinf of the angle.
 struct OrbKeypoint { int cx, cy; float a, b; };
 int orb_pattern_upload();
+void launch_orb_gray(const uint8_t* img, int rows, int cols, int channels, size_t step, uint8_t* gray,
+                     cudaStream_t s);
+// FAST-9/16 keypoints of a gray frame (fast_detect.cu): score map, suppression, ordered output
+int fast_blocks(int rows, int cols);
+void launch_fast_detect(const uint8_t* gray, int rows, int cols, int threshold, int nonmax,
+                        int16_t* score, int32_t* cnt, float* kp, int cap, cudaStream_t s);
 void launch_orb_blur(const uint8_t* img, int rows, int cols, int channels, size_t step, uint8_t* gray,
                      float* rowf, uint8_t* blur, cudaStream_t s);
 void launch_orb_desc(const uint8_t* blur, int cols, const OrbKeypoint* kps, int n, int n_pad,

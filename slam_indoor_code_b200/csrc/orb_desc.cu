@@ -113,6 +113,15 @@ int orb_pattern_upload() {
   return 0;
 }
 
+// cvtColor(BGR2GRAY) alone (the FAST detector works on the gray frame)
+void launch_orb_gray(const uint8_t* img, int rows, int cols, int channels, size_t step, uint8_t* gray,
+                     cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return;
+  dim3 grid((cols + 255) / 256, rows);
+  orb_gray_kernel<<<grid, 256, 0, s>>>(img, rows, cols, channels, step, gray);
+  COUNT_LAUNCH();
+}
+
 void launch_orb_blur(const uint8_t* img, int rows, int cols, int channels, size_t step, uint8_t* gray,
                      float* rowf, uint8_t* blur, cudaStream_t s) {
   if (rows <= 0 || cols <= 0) return;

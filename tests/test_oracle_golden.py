@@ -189,6 +189,15 @@ def test_orb_descriptor_oracle_matches_cv2(golden_dir):
     assert np.array_equal(desc, g["desc"]) and len(desc) > 150
 
 
+# ---- FAST keypoints (fastExtractor.cpp:7-13) ---------------------------------------
+def test_fast_oracle_matches_cv2_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "fast.npz"))
+    for thr, nms in ((10, True), (10, False), (25, True)):
+        ref = g[f"kp_t{thr}_n{int(nms)}"]
+        got = c_oracle.fast_detect(g["frame"], thr, nms)
+        assert np.array_equal(got, ref) and (len(ref) > 20 or thr > 10)
+
+
 # ---- the next rows restated twice: the C oracle against the independent NumPy statement -----------
 def test_c_and_np_oracles_agree_on_next_rows(golden_dir):
     import re

@@ -159,3 +159,18 @@ def test_orb_compute_bit_exact(h, w, ch, seed):
     # the float blur depends on the FMA dispatch of the OpenCV build: identical here, and never
     # more than one level apart on the rare pixel whose sum sits on a rounding boundary
     assert np.count_nonzero(blur != ref) <= 2 and np.abs(blur.astype(int) - ref).max() <= 1
+
+
+@pytest.mark.parametrize("h,w,ch,seed,thr,nms", [(480, 640, 3, 9500, 10, True), (301, 457, 1, 9501, 10, False),
+                                                  (240, 320, 3, 9502, 0, True), (240, 320, 3, 9503, 35, True),
+                                                  (7, 9, 3, 9504, 10, True), (6, 64, 1, 9505, 10, True),
+                                                  (200, 200, 3, 9506, 255, True)])
+def test_fast_detect_bit_exact(h, w, ch, seed, thr, nms):
+    """The reference's fastExtractor (fastExtractor.cpp:7-13): positions, order and responses of
+    cv2's FAST-9/16 keypoints, BGR frames included (the detector converts them itself)."""
+    frame = synth.textured_frame(h, w, seed, ch)
+    kps = cv2.FastFeatureDetector_create(thr, nms, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16).detect(frame)
+    ref = np.array([[k.pt[0], k.pt[1], k.response] for k in kps], np.float32).reshape(-1, 3)
+    got = c_oracle.fast_detect(frame, thr, nms)
+    assert np.array_equal(got, ref)
+    assert all(k.size == 7.0 and k.angle == -1.0 and k.octave == 0 for k in kps[:50])
