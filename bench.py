@@ -677,6 +677,20 @@ def extras(ctx, stream):
     kms, kn = ctx.profile_read()["orb_desc"]
     ctx.profile_enable(False)
     out["f3_orb_compute_4k_12000kp"] = {"ms_per_host_call": dt * 1e3, "kernels_us": kms / max(kn, 1) * 1e3}
+    # next row 8f-3, the detector in front of it: fastExtractor (FAST-9/16, threshold 10, suppression)
+    # on the same 4K BGR frame; the host call includes the 24.9 MB pageable frame copy and the
+    # keypoint read-back
+    from slam_indoor_code_b200 import fast_extractor as fe
+    n_fast = len(fe.fastExtractor(ctx, frame4k, 10, True))
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        fe.fastExtractor(ctx, frame4k, 10, True, max_points=n_fast)
+    dt = (time.perf_counter() - t0) / 5
+    kms, kn = ctx.profile_read()["fast"]
+    ctx.profile_enable(False)
+    out["f3_fast_4k"] = {"ms_per_host_call": dt * 1e3, "kernels_us": kms / max(kn, 1) * 1e3, "keypoints": n_fast}
     # next row 8f-4: linear triangulation of 5000 matches (one host call incl. copies)
     from slam_indoor_code_b200 import triangulation as tri
     K4 = synth.SAMSUNG_HV_4K
@@ -782,6 +796,9 @@ def cpu_extras():
     orb = cv2.ORB_create()
     dt, _ = best(lambda: orb.compute(frame4k, cvk), 3)
     out["f3_orb_compute_4k_12000kp_s"] = dt
+    fast = cv2.FastFeatureDetector_create(10, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    dt, _ = best(lambda: fast.detect(frame4k), 3)
+    out["f3_fast_4k_s"] = dt
     tp1, tp2, tR, tt = synth.two_view(5000, 8000, outliers=0.0)
     P1 = Kmat @ np.hstack([np.eye(3), np.zeros((3, 1))])
     P2 = Kmat @ np.hstack([tR, tt.reshape(3, 1)])

@@ -2,6 +2,7 @@
 // Python tests can drive the C++ host layer (the static matchFeatures and the batch fast path)
 // exactly as the reference's callers would (batch.cpp:127-130).
 #include "featureMatchingB200.cpp"
+#include "fastExtractorB200.cpp"
 #include "ransac_control.h"
 
 static double g_ratio = 0.7;
@@ -113,5 +114,25 @@ int hostshim_ransac_control(int count, double prob, int chunk, const int* n_mode
                             int* best_model) {
   return hostshim_ransac_run(count, 5, 9, prob, 1000, chunk, n_models, n_samples, scores, n_scores,
                              subsets_out, subsets_cap, best_model);
+}
+}
+
+extern "C" {
+// fastExtractor(frame, points, threshold, suppression): returns the number of keypoints, their
+// {x, y, response, size, angle} rows in out (cap rows); -1 on an exception.
+int hostshim_fast_extractor(const void* frame, int rows, int cols, int channels, size_t step, int threshold,
+                            int suppression, float* out, int cap) {
+  try {
+    cv::Mat f(rows, cols, channels == 3 ? CV_8UC3 : CV_8U, const_cast<void*>(frame), step);
+    std::vector<cv::KeyPoint> points(3);   // must be replaced by the callee
+    fastExtractor(f, points, threshold, suppression != 0, cv::FastFeatureDetector::TYPE_9_16);
+    for (size_t i = 0; i < points.size() && (int)i < cap; i++) {
+      out[5 * i] = points[i].pt.x; out[5 * i + 1] = points[i].pt.y; out[5 * i + 2] = points[i].response;
+      out[5 * i + 3] = points[i].size; out[5 * i + 4] = points[i].angle;
+    }
+    return (int)points.size();
+  } catch (...) {
+    return -1;
+  }
 }
 }

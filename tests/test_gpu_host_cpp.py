@@ -98,3 +98,22 @@ def test_extract_descriptor_orb_cpp(host):
     edge = np.array([[3, 3, -1], [399, 299, -1]], np.float32)
     assert host.hostshim_extract_orb(_capi.ptr(frame), 300, 400, 3, frame.strides[0], _capi.ptr(edge), 2,
                                      _capi.ptr(kept_xy), _capi.ptr(desc), 1500) == 0
+
+
+def test_fast_extractor_cpp(host):
+    """fastExtractor(frame, points, threshold) of host/fastExtractorB200.cpp: the keypoint vector the
+    reference's callers get (batch.cpp:245), from the B200."""
+    host.hostshim_fast_extractor.restype = ctypes.c_int
+    host.hostshim_fast_extractor.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    frame = synth.textured_frame(360, 480, 51, 3)
+    want = c_oracle.fast_detect(frame, 10, True)
+    out = np.zeros((len(want) + 8, 5), np.float32)
+    n = host.hostshim_fast_extractor(_capi.ptr(frame), 360, 480, 3, frame.strides[0], 10, 1, _capi.ptr(out), len(out))
+    assert n == len(want) > 1000
+    assert np.array_equal(out[:n, :3], want)
+    assert np.all(out[:n, 3] == 7.0) and np.all(out[:n, 4] == -1.0)
+    # a frame too small to hold a corner, and a threshold nothing passes
+    tiny = synth.textured_frame(6, 6, 52, 3)
+    assert host.hostshim_fast_extractor(_capi.ptr(tiny), 6, 6, 3, tiny.strides[0], 10, 1, _capi.ptr(out), len(out)) == 0
+    assert host.hostshim_fast_extractor(_capi.ptr(frame), 360, 480, 3, frame.strides[0], 255, 1, _capi.ptr(out), len(out)) == 0
