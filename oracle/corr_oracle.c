@@ -22,6 +22,7 @@
  *       NORM_L1 kNN                 src/mainModule/featureMatching/featureMatchingCUDA.cpp:28
  *       linear triangulation        src/mainModule/triangulation/triangulate.cpp:17-55, :91-108
  *       ORB descriptors (compute)   src/mainModule/featureMatching/featureMatchingCPU.cpp:45-66
+ *       FAST keypoints (detect)     src/mainModule/featureExtraction/fastExtractor.cpp:7-13
  *
  * Parity pin: the reference ships no tests or golden vectors, so this
  * oracle is pinned against the reference's own arithmetic owner, OpenCV, through the cv2 wheel

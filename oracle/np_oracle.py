@@ -211,3 +211,44 @@ def orb_compute(image, kps, pattern):
         yr = (px * b[:, None]).astype(np.float32) + (py * a[:, None]).astype(np.float32)
         bits.append(blur[cy[keep, None] + np.rint(yr).astype(np.int64), cx[keep, None] + np.rint(xr).astype(np.int64)])
     return keep.astype(np.uint8), np.packbits(bits[0] < bits[1], axis=1, bitorder="little")
+
+
+# ---- FAST-9/16 keypoints (fastExtractor.cpp:7-13), an array statement independent of the C loops ----
+_FAST_CIRCLE = ((0, 3), (1, 3), (2, 2), (3, 1), (3, 0), (3, -1), (2, -2), (1, -3), (0, -3), (-1, -3),
+                (-2, -2), (-3, -1), (-3, 0), (-3, 1), (-2, 2), (-1, 3))
+
+
+def fast_detect(image, threshold=10, nonmax=True):
+    """cv::FastFeatureDetector(threshold, nonmax, TYPE_9_16)::detect as whole-image array operations:
+    the sixteen circle differences as shifted planes, the sixteen 9-pixel arcs as min / max over
+    planes, suppression as a strict comparison with the 3x3 neighbourhood.  Returns [n, 3] float32
+    rows {x, y, response} in row-major order."""
+    img = np.asarray(image, np.uint8)
+    if img.ndim == 3:
+        b, g, r = (img[..., c].astype(np.int64) for c in range(3))
+        img = ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)   # cvtColor BGR2GRAY
+    rows, cols = img.shape
+    if rows < 7 or cols < 7:
+        return np.zeros((0, 3), np.float32)
+    t = min(max(int(threshold), 0), 255)
+    v = img[3:rows - 3, 3:cols - 3].astype(np.int32)
+    d = np.stack([v - img[3 + dy:rows - 3 + dy, 3 + dx:cols - 3 + dx].astype(np.int32) for dx, dy in _FAST_CIRCLE])
+    arcs = [[(s + j) % 16 for j in range(9)] for s in range(16)]
+    arc_min = np.stack([d[a].min(0) for a in arcs])   # darker side: every pixel of the arc has d > t
+    arc_max = np.stack([d[a].max(0) for a in arcs])   # brighter side: every pixel has d < -t
+    corner = (arc_min > t).any(0) | (arc_max < -t).any(0)
+    a0 = np.maximum(t, arc_min.max(0))
+    b0 = np.minimum(-a0, arc_max.min(0))
+    score = np.where(corner, -b0 - 1, 0).astype(np.int32)
+    full = np.zeros((rows, cols), np.int32)
+    full[3:rows - 3, 3:cols - 3] = score
+    keep = np.zeros((rows, cols), bool)
+    keep[3:rows - 3, 3:cols - 3] = corner
+    if nonmax:
+        pad = np.pad(full, 1)
+        neigh = np.stack([pad[1 + dy:rows + 1 + dy, 1 + dx:cols + 1 + dx]
+                          for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy) != (0, 0)]).max(0)
+        keep &= full > neigh
+    ys, xs = np.nonzero(keep)
+    resp = full[ys, xs] if nonmax else np.zeros(len(ys))
+    return np.stack([xs, ys, resp], 1).astype(np.float32).reshape(-1, 3)

@@ -198,6 +198,19 @@ def test_fast_oracle_matches_cv2_golden(golden_dir):
         assert np.array_equal(got, ref) and (len(ref) > 20 or thr > 10)
 
 
+def test_fast_np_statement_matches_cv2_golden_and_c_oracle(golden_dir):
+    """FAST restated twice: whole-image array operations (np_oracle) against the cv2 fixture and
+    against the C loops on fresh frames (gray and BGR, with and without suppression)."""
+    from oracle import synth
+    g = np.load(os.path.join(golden_dir, "fast.npz"))
+    for thr, nms in ((10, True), (10, False), (25, True)):
+        assert np.array_equal(np_oracle.fast_detect(g["frame"], thr, nms), g[f"kp_t{thr}_n{int(nms)}"])
+    for h, w, ch, seed, thr, nms in [(200, 300, 3, 611, 10, True), (133, 157, 1, 612, 0, True),
+                                     (128, 128, 3, 613, 40, False), (7, 9, 1, 614, 10, True)]:
+        f = synth.textured_frame(h, w, seed, ch)
+        assert np.array_equal(np_oracle.fast_detect(f, thr, nms), c_oracle.fast_detect(f, thr, nms))
+
+
 # ---- the next rows restated twice: the C oracle against the independent NumPy statement -----------
 def test_c_and_np_oracles_agree_on_next_rows(golden_dir):
     import re
