@@ -245,6 +245,17 @@ int slamb200_orb_compute(slamb200_ctx* ctx, const uint8_t* image, int rows, int 
 int slamb200_fast_detect(slamb200_ctx* ctx, const uint8_t* image, int rows, int cols, int channels,
                          size_t step, int threshold, int nonmax, float* kps, int cap, int* n_found);
 
+/* slamb200_fast_detect followed by slamb200_orb_compute on the same frame in one call (the
+ * reference's front end for useFM-ORB: fastExtractor at batch.cpp:245, then extractDescriptor,
+ * featureMatchingCPU.cpp:45-66): the frame crosses PCIe and is converted to gray once.  kps / cap /
+ * n_found as in slamb200_fast_detect, except that cap < *n_found is an error (SLAMB200_ERR_INVALID,
+ * *n_found set: retry with a larger buffer); keep (may be NULL, n_found bytes), desc (may be NULL),
+ * n_kept and resident as in slamb200_orb_compute.  Same results as the two calls. */
+int slamb200_fast_orb_compute(slamb200_ctx* ctx, const uint8_t* image, int rows, int cols, int channels,
+                              size_t step, int threshold, int nonmax, float* kps, int cap,
+                              int* n_found, uint8_t* keep, uint8_t* desc, int* n_kept,
+                              slamb200_desc** resident);
+
 /* ---- next row: linear triangulation (triangulation/triangulate.cpp:17-55, :91-108) --- */
 /* reconstructPointsFor3D for M matches: P1, P2 = 3x4 row-major projection matrices (K*[R|t], as
  * reconstruct() forms them at triangulate.cpp:74-80), pts = M x 2 floats (vector<Point2f>).  Per

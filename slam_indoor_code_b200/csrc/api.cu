@@ -1724,6 +1724,101 @@ extern "C" int slamb200_fast_detect(slamb200_ctx* c, const uint8_t* image, int r
   return SLAMB200_OK;
 }
 
+// fastExtractor followed by extractDescriptor(ORB) on the same frame in one call: the frame is
+// uploaded and converted to gray once, the keypoints go to the host (the reference keeps them in
+// BatchElement::features) and the descriptors of those that survive ORB's border filter stay in
+// HBM as a resident set.  Equal to slamb200_fast_detect + slamb200_orb_compute.
+extern "C" int slamb200_fast_orb_compute(slamb200_ctx* c, const uint8_t* image, int rows, int cols,
+                                         int channels, size_t step, int threshold, int nonmax,
+                                         float* kps, int cap, int* n_found, uint8_t* keep,
+                                         uint8_t* desc, int* n_kept, slamb200_desc** resident) {
+  if (!c || !n_found || !n_kept) return fail(SLAMB200_ERR_INVALID, "fast_orb_compute: NULL argument");
+  *n_found = 0;
+  *n_kept = 0;
+  if (resident) *resident = nullptr;
+  if (rows <= 0 || cols <= 0 || !image) return fail(SLAMB200_ERR_INVALID, "fast_orb_compute: bad image");
+  if (channels != 1 && channels != 3)
+    return fail(SLAMB200_ERR_KIND, "fast_orb_compute: %d-channel image (CV_8UC1 or CV_8UC3 expected)", channels);
+  if (cap < 0 || (cap > 0 && !kps)) return fail(SLAMB200_ERR_INVALID, "fast_orb_compute: bad output buffer");
+  if (rows > 65535) return fail(SLAMB200_ERR_INVALID, "fast_orb_compute: more than 65535 rows");
+  if (step == 0) step = (size_t)cols * channels;
+  if (step < (size_t)cols * channels) return fail(SLAMB200_ERR_INVALID, "fast_orb_compute: step too small");
+  CU(cudaSetDevice(c->device));
+  if (orb_pattern_upload() != 0) return fail(SLAMB200_ERR_CUDA, "fast_orb_compute: pattern upload failed");
+  int rc;
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  cudaStream_t s = L.stream;
+  const size_t px = (size_t)rows * cols;
+  int found = 0;
+  if ((rc = buf_reserve(c, L.orb_img, (size_t)rows * step, s))) return rc;
+  if ((rc = buf_reserve(c, L.orb_gray, px, s))) return rc;
+  CU(cudaMemcpyAsync(L.orb_img.p, image, (size_t)rows * step, cudaMemcpyHostToDevice, s));
+  launch_orb_gray((const uint8_t*)L.orb_img.p, rows, cols, channels, step, (uint8_t*)L.orb_gray.p, s);
+  if (rows >= 7 && cols >= 7) {
+    const int nb = fast_blocks(rows, cols);
+    if ((rc = buf_reserve(c, L.fast_score, px * sizeof(int16_t), s))) return rc;
+    if ((rc = buf_reserve(c, L.fast_cnt, sizeof(int32_t) * ((size_t)nb + 1), s))) return rc;
+    if ((rc = buf_reserve(c, L.fast_kp, sizeof(float) * 3 * (size_t)(cap > 0 ? cap : 1), s))) return rc;
+    {
+      ProfScope ps(c, s, SLAMB200_K_FAST);
+      launch_fast_detect((const uint8_t*)L.orb_gray.p, rows, cols, threshold, nonmax ? 1 : 0,
+                         (int16_t*)L.fast_score.p, (int32_t*)L.fast_cnt.p, (float*)L.fast_kp.p, cap, s);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(L.h_small, (int32_t*)L.fast_cnt.p + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    found = L.h_small[0];
+  }
+  *n_found = found;
+  if (found > cap)
+    return fail(SLAMB200_ERR_INVALID, "fast_orb_compute: %d keypoints, buffer holds %d (retry with cap >= *n_found)",
+                found, cap);
+  if (found > 0) {
+    CU(cudaMemcpyAsync(kps, L.fast_kp.p, sizeof(float) * 3 * (size_t)found, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  // KeyPointsFilter::runByImageBorder(.., 31) on the host, as in slamb200_orb_compute; every FAST
+  // keypoint has angle -1 degree, rotated with libm's float cosf / sinf like cv::ORB does
+  float angle = -1.0f;
+  angle *= (float)(3.141592653589793 / 180.f);
+  const float ca = cosf(angle), sa = sinf(angle);
+  std::vector<OrbKeypoint> hk;
+  hk.reserve((size_t)found);
+  for (int i = 0; i < found; i++) {
+    const int rx = (int)lrintf(kps[3 * (size_t)i]), ry = (int)lrintf(kps[3 * (size_t)i + 1]);
+    const bool ok = rx >= 31 && rx < cols - 31 && ry >= 31 && ry < rows - 31;
+    if (keep) keep[i] = ok ? 1 : 0;
+    if (ok) hk.push_back({rx, ry, ca, sa});
+  }
+  const int kept = (int)hk.size();
+  *n_kept = kept;
+  const int n_pad = round_up(kept > 0 ? kept : 1, SLAMB200_TILE_PAD);
+  if ((rc = buf_reserve(c, L.orb_rowf, px * sizeof(float), s))) return rc;
+  if ((rc = buf_reserve(c, L.orb_blur, px, s))) return rc;
+  if ((rc = buf_reserve(c, L.orb_kp, sizeof(OrbKeypoint) * (size_t)(kept > 0 ? kept : 1), s))) return rc;
+  if ((rc = buf_reserve(c, L.orb_desc, (size_t)n_pad * 32, s))) return rc;
+  if (kept > 0)
+    CU(cudaMemcpyAsync(L.orb_kp.p, hk.data(), sizeof(OrbKeypoint) * (size_t)kept, cudaMemcpyHostToDevice, s));
+  {
+    ProfScope ps(c, s, SLAMB200_K_ORB_DESC);
+    launch_orb_blur_gray((const uint8_t*)L.orb_gray.p, rows, cols, (float*)L.orb_rowf.p, (uint8_t*)L.orb_blur.p, s);
+    launch_orb_desc((const uint8_t*)L.orb_blur.p, cols, (const OrbKeypoint*)L.orb_kp.p, kept, n_pad,
+                    (uint8_t*)L.orb_desc.p, s);
+  }
+  CU(cudaGetLastError());
+  if (desc && kept > 0)
+    CU(cudaMemcpyAsync(desc, L.orb_desc.p, (size_t)kept * 32, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(L.done, s));
+  if (resident) {
+    rc = desc_create(c, SLAMB200_DESC_U8X32, L.orb_desc.p, kept, 32, true, s, false, resident);
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(s, (*resident)->ready, 0));
+  }
+  CU(cudaStreamSynchronize(s));
+  return SLAMB200_OK;
+}
+
 // ---- linear triangulation -----------------------------------------------------
 extern "C" int slamb200_triangulate(slamb200_ctx* c, const double P1[12], const double P2[12],
                                     const float* pts1, const float* pts2, int M, double* points4d,

@@ -153,6 +153,7 @@ struct OrbKeypoint { int cx, cy; float a, b; };
 int orb_pattern_upload();
 void launch_orb_gray(const uint8_t* img, int rows, int cols, int channels, size_t step, uint8_t* gray,
                      cudaStream_t s);
+void launch_orb_blur_gray(const uint8_t* gray, int rows, int cols, float* rowf, uint8_t* blur, cudaStream_t s);
 // FAST-9/16 keypoints of a gray frame (fast_detect.cu): score map, suppression, ordered output
 int fast_blocks(int rows, int cols);
 void launch_fast_detect(const uint8_t* gray, int rows, int cols, int threshold, int nonmax,

@@ -122,6 +122,17 @@ void launch_orb_gray(const uint8_t* img, int rows, int cols, int channels, size_
   COUNT_LAUNCH();
 }
 
+// ORB's blur of a frame that is already gray on the device (the FAST detector made it)
+void launch_orb_blur_gray(const uint8_t* gray, int rows, int cols, float* rowf, uint8_t* blur, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return;
+  Gauss7 g;
+  orb_gauss7(g);
+  dim3 grid((cols + 255) / 256, rows);
+  orb_blur_rows_kernel<<<grid, 256, 0, s>>>(gray, rows, cols, g, rowf);
+  orb_blur_cols_kernel<<<grid, 256, 0, s>>>(rowf, rows, cols, g, blur);
+  COUNT_LAUNCH(); COUNT_LAUNCH();
+}
+
 void launch_orb_blur(const uint8_t* img, int rows, int cols, int channels, size_t step, uint8_t* gray,
                      float* rowf, uint8_t* blur, cudaStream_t s) {
   if (rows <= 0 || cols <= 0) return;

@@ -63,3 +63,23 @@ def test_fast_then_orb_descriptors(ctx):
     keep, desc, _ = od.extractDescriptorORB(ctx, frame, kps)
     rkeep, rdesc = c_oracle.orb_compute(frame, fe.to_orb_keypoints(c_oracle.fast_detect(frame, 10, True)))
     assert np.array_equal(np.asarray(keep, bool), rkeep.astype(bool)) and np.array_equal(desc, rdesc)
+
+
+@pytest.mark.parametrize("h,w,ch,seed", [(480, 640, 3, 9630), (300, 333, 1, 9631), (70, 70, 3, 9632), (40, 400, 3, 9633)])
+def test_fast_and_orb_in_one_call(ctx, h, w, ch, seed):
+    """slamb200_fast_orb_compute = fastExtractor + extractDescriptor(ORB) with one frame upload; the
+    resident descriptor set matches like an uploaded one."""
+    from slam_indoor_code_b200.feature_matching import MatcherType
+    frame = synth.textured_frame(h, w, seed, ch)
+    pts, keep, desc, res = fe.fastExtractorAndDescribeORB(ctx, frame, 10, True, want_resident=True)
+    ref_pts = c_oracle.fast_detect(frame, 10, True)
+    rkeep, rdesc = c_oracle.orb_compute(frame, fe.to_orb_keypoints(ref_pts))
+    assert np.array_equal(pts, ref_pts)
+    assert np.array_equal(keep, rkeep.astype(bool)) and np.array_equal(desc, rdesc)
+    assert res.n == len(rdesc)
+    if len(rdesc) >= 2:
+        T = ctx.upload(rdesc)
+        assert np.array_equal(ctx.matchFeatures(res, T, MatcherType.ORB_BF, 0.99),
+                              c_oracle.match_features(2, rdesc, rdesc, 0.99))
+        T.free()
+    res.free()
