@@ -223,3 +223,41 @@ void matchFramesBatchFeatures(Mat& firstFrameDescriptor, std::vector<Mat>& batch
     allMatches[(size_t)p].assign(src, src + n[(size_t)p]);
   }
 }
+
+// The rule by which both search variants of the reference pick the new good frame from a matched
+// batch (batch.cpp:120-148 single-threaded, :283-307 after the matcher threads): walk the batch
+// from its last element down to skipFramesFromBatchHead; an element is good when it has at least
+// requiredMatchedPointsCount matches and at least as many as the good element so far; with
+// useFirstFitInBatch the first good element ends the walk.  Returns the index or FRAME_NOT_FOUND
+// (-1, batch.h:6).  The comparisons are the reference's: size_t against int, i.e. a negative
+// requirement converts to a huge unsigned value and nothing is good.
+int selectGoodFrameFromMatchCounts(const std::vector<size_t>& matched, int requiredMatchedPointsCount,
+                                   bool useFirstFitInBatch, int skipFramesFromBatchHead) {
+  int goodIndex = -1;
+  size_t goodSize = 0;   // goodMatches.size() of an empty vector
+  for (int batchIndex = (int)matched.size() - 1; batchIndex >= skipFramesFromBatchHead; batchIndex--) {
+    if (batchIndex < 0) break;   // a negative skip count would read before the batch in the reference
+    const size_t m = matched[(size_t)batchIndex];
+    if (m >= (size_t)requiredMatchedPointsCount && m >= goodSize) {
+      goodIndex = batchIndex;
+      goodSize = m;
+      if (useFirstFitInBatch) break;
+    }
+  }
+  return goodIndex;
+}
+
+// The whole search of findGoodFramesFromBatch* (batch.cpp:101-226) on descriptors in ONE matcher
+// call: every element of the batch is matched against the previous frame's descriptor
+// (speculatively, like the reference's multi-threaded variant), then the reference's rule picks
+// the good frame.  allMatches[i] = element i's matches (BatchElement::matches).
+int findGoodFrameFromBatchDescriptors(Mat& previousDescriptor, std::vector<Mat>& batchDescriptors,
+                                      int matcherType, int requiredMatchedPointsCount,
+                                      bool useFirstFitInBatch, int skipFramesFromBatchHead,
+                                      std::vector<std::vector<DMatch>>& allMatches) {
+  matchFramesBatchFeatures(previousDescriptor, batchDescriptors, matcherType, allMatches);
+  std::vector<size_t> matched(allMatches.size());
+  for (size_t i = 0; i < allMatches.size(); i++) matched[i] = allMatches[i].size();
+  return selectGoodFrameFromMatchCounts(matched, requiredMatchedPointsCount, useFirstFitInBatch,
+                                        skipFramesFromBatchHead);
+}

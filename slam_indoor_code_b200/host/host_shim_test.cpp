@@ -136,3 +136,31 @@ int hostshim_fast_extractor(const void* frame, int rows, int cols, int channels,
   }
 }
 }
+
+extern "C" {
+// selectGoodFrameFromMatchCounts over plain arrays (host logic only: no GPU needed)
+int hostshim_select_good_frame(const long long* matched, int n, int required, int first_fit, int skip_head) {
+  std::vector<size_t> m((size_t)n);
+  for (int i = 0; i < n; i++) m[(size_t)i] = (size_t)matched[i];
+  return selectGoodFrameFromMatchCounts(m, required, first_fit != 0, skip_head);
+}
+
+// findGoodFrameFromBatchDescriptors: returns the good index, -2 on an exception; n_out[p] = matches of element p
+int hostshim_find_good_frame(const void* q, int nq, const void* const* t, const int* nt, int P, int type,
+                             int required, int first_fit, int skip_head, int* n_out) {
+  try {
+    const bool orb = type == ORB_BF;
+    const int w = orb ? 32 : 128, ty = orb ? CV_8U : CV_32F;
+    const size_t step = orb ? 32 : 512;
+    cv::Mat prev(nq, w, ty, const_cast<void*>(q), step);
+    std::vector<cv::Mat> batch;
+    for (int p = 0; p < P; p++) batch.emplace_back(nt[p], w, ty, const_cast<void*>(t[p]), step);
+    std::vector<std::vector<cv::DMatch>> all;
+    const int good = findGoodFrameFromBatchDescriptors(prev, batch, type, required, first_fit != 0, skip_head, all);
+    for (int p = 0; p < P; p++) n_out[p] = (int)all[(size_t)p].size();
+    return good;
+  } catch (...) {
+    return -2;
+  }
+}
+}

@@ -117,3 +117,34 @@ def test_fast_extractor_cpp(host):
     tiny = synth.textured_frame(6, 6, 52, 3)
     assert host.hostshim_fast_extractor(_capi.ptr(tiny), 6, 6, 3, tiny.strides[0], 10, 1, _capi.ptr(out), len(out)) == 0
     assert host.hostshim_fast_extractor(_capi.ptr(frame), 360, 480, 3, frame.strides[0], 255, 1, _capi.ptr(out), len(out)) == 0
+
+
+def test_find_good_frame_from_batch_cpp_and_python(host, ctx):
+    """The batch search of batch.cpp:101-226 in one matcher call: per-element match counts equal to
+    the oracle's, the good index equal to the reference's rule, in the C++ unit and the Python mirror."""
+    from slam_indoor_code_b200 import batch_search as bs
+    from slam_indoor_code_b200.feature_matching import MatcherType
+    host.hostshim_find_good_frame.restype = ctypes.c_int
+    host.hostshim_find_good_frame.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p]
+    q = synth.sift_like(700, 61)
+    # elements with different numbers of true correspondences (and one unrelated frame)
+    trains = [synth.sift_train_from_query(q, 600 + 40 * i, 62 + i, planted=p)
+              for i, p in enumerate((0.1, 0.4, 0.0, 0.4, 0.25))]
+    counts = [len(c_oracle.match_features(0, q, t, 0.7)) for t in trains]
+    host.hostshim_set_ratio(0.7)
+    P = len(trains)
+    ptrs = (ctypes.c_void_p * P)(*[t.ctypes.data for t in trains])
+    nts = np.array([len(t) for t in trains], np.int32)
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(t) for t in trains]
+    for required, first_fit, skip in [(50, False, 0), (50, True, 0), (max(counts) + 1, False, 0),
+                                      (1, False, 2), (counts[4], True, 0)]:
+        want = bs.selectGoodFrameFromMatchCounts(counts, required, first_fit, skip)
+        n_out = np.zeros(P, np.int32)
+        good = host.hostshim_find_good_frame(_capi.ptr(q), len(q), ptrs, _capi.ptr(nts), P, 0, required,
+                                             int(first_fit), skip, _capi.ptr(n_out))
+        assert good == want and list(n_out) == counts
+        g2, all_matches = bs.findGoodFrameFromBatch(ctx, Q, Ts, MatcherType.SIFT_BF, required, first_fit, skip)
+        assert g2 == want and [len(m) for m in all_matches] == counts
