@@ -73,7 +73,7 @@ def my_pairs(rank, world, n=N_PAIRS):
 def make_inputs(pairs, pinned):
     """Query frame + the owned train frames (seeds of SURVEY.md 8d cfg3), as float32 N x 128."""
     import torch
-    from oracle import synth  # input generator only (shared with the tests)
+    import synth_inputs as synth
     q = synth.sift_like(N_ROWS, 3000)
 
     def hold(a):
@@ -549,7 +549,7 @@ def cpu_baseline(q, trains, gpu_matches, seconds):
 def extras(ctx, stream):
     """Short device-resident probes of the other BASELINE.json configs (not the headline)."""
     import torch
-    from oracle import synth
+    import synth_inputs as synth
     from slam_indoor_code_b200 import camera_translation as ct
     from slam_indoor_code_b200.feature_matching import MatcherType
     out = {}
@@ -751,7 +751,7 @@ def cpu_extras():
         import cv2
     except Exception:
         return {"unavailable": "cv2 not importable"}
-    from oracle import synth
+    import synth_inputs as synth
     cv2.setNumThreads(os.cpu_count() or 1)
     out["cores"] = int(cv2.getNumThreads())
 

@@ -84,8 +84,9 @@ int slamb200_synchronize(slamb200_ctx* ctx);
 
 /* ---- descriptor sets: replaces the per-call cuda::GpuMat uploads of
  *      featureMatchingCUDA.cpp:98-99 with "upload once per frame" ----------------------- */
-/* rows: host pointer to n rows of the kind's type, row_stride bytes apart (cv::Mat::step).  The
- * rows are consumed when the call returns.  (Implemented by slamb200_upload_desc_packed below.) */
+/* rows: host pointer to n rows of the kind's type, row_stride bytes apart (cv::Mat::step; any
+ * multiple of the element size, no alignment requirement on `rows` for any upload entry point).
+ * The rows are consumed when the call returns.  (Implemented by slamb200_upload_desc_packed.) */
 int slamb200_upload_desc(slamb200_ctx* ctx, int kind, const void* rows, int n, size_t row_stride,
                          slamb200_desc** out);
 /* Same, but `rows` is a device pointer on the context's device (bytes already in HBM);
@@ -166,7 +167,10 @@ int slamb200_match_window(slamb200_ctx* ctx, int matcher, const slamb200_desc* c
 
 /* Device-resident variants: enqueue the batch on `stream` (cudaStream_t; NULL = the lane's own
  * stream), keep the results in HBM inside the context, return without synchronising.
- * slamb200_batch_fetch copies the results of the last enqueue to the host. */
+ * slamb200_batch_fetch copies the results of the last enqueue to the host.
+ * The context keeps ONE result set for these four entry points (enqueue / fetch / score enqueue /
+ * scores fetch): each call is ordered on the device behind the previous one whatever stream it
+ * was given, and a new enqueue overwrites the results of the last.  n_pairs <= 65534. */
 int slamb200_match_batch_enqueue(slamb200_ctx* ctx, int matcher, const slamb200_desc* query,
                                  const slamb200_desc* const* trains, int n_pairs, double ratio,
                                  void* stream);
@@ -276,8 +280,9 @@ int slamb200_free_pts(slamb200_ctx* ctx, slamb200_pts* p);
 
 /* Chained batch: score, for every pair of the last slamb200_match_batch_enqueue, H hypotheses
  * (E: n_pairs*H*9 doubles, host memory or already resident on the context's device) against that pair's accepted matches, gathering the coordinates
- * on the device (query_pts / train_pts[p]).  Results stay in HBM until
- * slamb200_batch_scores_fetch.  Enqueue-only. */
+ * on the device (query_pts / train_pts[p]).  train_pts holds one set per pair of that batch, each
+ * with at least as many points as the pair's train descriptor set has rows (checked:
+ * SLAMB200_ERR_INVALID).  Results stay in HBM until slamb200_batch_scores_fetch.  Enqueue-only. */
 int slamb200_score_batch_enqueue(slamb200_ctx* ctx, const slamb200_pts* query_pts,
                                  const slamb200_pts* const* train_pts, const double K[4],
                                  const double* E, int H, double threshold_px, void* stream);

@@ -20,7 +20,7 @@ import os
 import cv2
 import numpy as np
 
-from . import synth
+import synth_inputs as synth
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 

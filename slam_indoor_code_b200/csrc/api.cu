@@ -21,8 +21,9 @@
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static int64_t g_launches = 0;
-int64_t* launch_counter() { return &g_launches; }
+// kernels launched by this library since load: bumped from concurrently running lanes
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -74,6 +75,7 @@ struct Lane {
   size_t h_out_cap = 0;
   // state of the last enqueued batch
   int b_matcher = -1, b_nq = 0, b_pairs = 0, b_cap = 0;
+  std::vector<int> b_tn;      // train rows of every pair of the last batch (bounds of trainIdx)
   int s_H = 0, s_pairs = 0;
   int32_t* status = nullptr;  // device status words of the last batch (inside the table block)
   float* dbg = nullptr;  // debug: raw accumulator dump target of the next tcgen05 launch
@@ -123,7 +125,7 @@ struct slamb200_ctx {
     std::mutex mu;
     std::condition_variable cv;
     std::deque<std::function<void()>> q;
-    bool stop = false;
+    std::atomic<bool> stop{false};
     std::atomic<int> queued{0}, sleepers{0};
     void start(int n) {
       for (int i = 0; i < n; i++)
@@ -140,7 +142,7 @@ struct slamb200_ctx {
               std::unique_lock<std::mutex> lk(mu);
               if (q.empty()) {
                 sleepers++;
-                cv.wait(lk, [this] { return stop || !q.empty(); });
+                cv.wait(lk, [this] { return stop.load() || !q.empty(); });
                 sleepers--;
               }
               if (stop && q.empty()) return;
@@ -253,7 +255,7 @@ struct LaneGuard {
 // ---------------------------------------------------------------------------------------------
 extern "C" int slamb200_version(void) { return SLAMB200_VERSION; }
 extern "C" const char* slamb200_last_error(void) { return g_err; }
-extern "C" int64_t slamb200_launch_count(const slamb200_ctx*) { return g_launches; }
+extern "C" int64_t slamb200_launch_count(const slamb200_ctx*) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int slamb200_init(int device, slamb200_ctx** out) {
   if (!out) return fail(SLAMB200_ERR_INVALID, "slamb200_init: out is NULL");
@@ -482,7 +484,7 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   if (n < 0 || (n > 0 && !rows)) return fail(SLAMB200_ERR_INVALID, "upload_desc: bad rows/n");
   const size_t row_bytes = kind == SLAMB200_DESC_F32X128 ? 512 : 32;
   if (row_stride == 0) row_stride = row_bytes;
-  if (row_stride < row_bytes || (kind == SLAMB200_DESC_F32X128 && (row_stride % 16)))
+  if (row_stride < row_bytes || (kind == SLAMB200_DESC_F32X128 && (row_stride % 4)))
     return fail(SLAMB200_ERR_INVALID, "upload_desc: row_stride %zu unsupported", row_stride);
   CU(cudaSetDevice(c->device));
   slamb200_desc* d =
@@ -506,7 +508,10 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
       goto done;                                                                    \
     }                                                                               \
   } while (0)
-  if (producer && src_on_device) {
+  if (src_on_device) {
+    // The bytes were produced on `producer`; NULL names the legacy default stream, which the
+    // (non-blocking) upload lanes do not synchronise with implicitly, so it is recorded like any
+    // other stream.
     DCU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     DCU(cudaEventRecord(ev, producer));
     DCU(cudaStreamWaitEvent(s, ev, 0));
@@ -564,7 +569,9 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
       // Page-locked, device-mapped host rows (the pipelined upload): the prep kernel reads them
       // straight over PCIe -- no staging copy, no per-copy setup cost, one pass over the data.
       const void* mapped = nullptr;
-      if (!src_on_device && no_sync) {
+      // (the prep kernel reads float4: base and pitch must be 16-byte aligned, anything else is
+      // copied first)
+      if (!src_on_device && no_sync && row_stride % 16 == 0 && ((uintptr_t)rows & 15) == 0) {
         cudaPointerAttributes pa;
         if (cudaPointerGetAttributes(&pa, rows) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
             pa.devicePointer != nullptr)
@@ -988,7 +995,12 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
                          double ratio, bool want_knn = false) {
   const int nq = q->n;
   const int cap = nq > 0 ? nq : 1;
+  // a batch whose counts could not be fetched (fetch_batch reads them through h_small) is
+  // rejected before any GPU work is queued
+  if (n_pairs + 1 > N_SMALL) return fail(SLAMB200_ERR_INVALID, "too many pairs in one batch (%d)", n_pairs);
   L.b_matcher = matcher; L.b_nq = nq; L.b_pairs = n_pairs; L.b_cap = cap;
+  L.b_tn.resize((size_t)n_pairs);
+  for (int p = 0; p < n_pairs; p++) L.b_tn[(size_t)p] = trains[p]->n;
   if (n_pairs == 0) return SLAMB200_OK;
   int rc;
   const bool orb = matcher == SLAMB200_ORB_BF;
@@ -1262,7 +1274,6 @@ static int fetch_batch(Lane& L, cudaStream_t s, slamb200_dmatch* out, int out_ca
   }
   if (out_cap < L.b_nq) return fail(SLAMB200_ERR_INVALID, "cap %d < query rows %d", out_cap, L.b_nq);
   if (!out) return fail(SLAMB200_ERR_INVALID, "out is NULL");
-  if (P + 1 > N_SMALL) return fail(SLAMB200_ERR_INVALID, "too many pairs in one batch");
   auto ensure_h_out = [&](size_t bytes) -> int {
     if (L.h_out_cap >= bytes) return SLAMB200_OK;
     if (L.h_out) CU(cudaFreeHost(L.h_out));
@@ -1381,6 +1392,10 @@ extern "C" int slamb200_match_batch_enqueue(slamb200_ctx* c, int matcher, const 
   std::lock_guard<std::mutex> lk(c->batch_mu);
   Lane& L = c->lanes[0];
   cudaStream_t s = stream ? (cudaStream_t)stream : L.stream;
+  // Lane 0 owns ONE scratch set; the previous batch may have been queued on another stream and
+  // may still be running or unfetched there: order this stream behind it (a no-op in the usual
+  // same-stream case).
+  CU(cudaStreamWaitEvent(s, L.done, 0));
   return enqueue_batch(c, L, s, matcher, q, trains, n_pairs, ratio);
 }
 
@@ -1391,6 +1406,7 @@ extern "C" int slamb200_batch_fetch(slamb200_ctx* c, slamb200_dmatch* out, int c
   std::lock_guard<std::mutex> lk(c->batch_mu);
   Lane& L = c->lanes[0];
   cudaStream_t s = stream ? (cudaStream_t)stream : L.stream;
+  CU(cudaStreamWaitEvent(s, L.done, 0));   // the batch may have been enqueued on another stream
   return fetch_batch(L, s, out, cap, n_out);
 }
 
@@ -1909,6 +1925,15 @@ extern "C" int slamb200_score_batch_enqueue(slamb200_ctx* c, const slamb200_pts*
   if (P <= 0) return fail(SLAMB200_ERR_INVALID, "no batch has been enqueued on this context");
   if (!query_pts || !train_pts) return fail(SLAMB200_ERR_INVALID, "NULL keypoint sets");
   if (query_pts->n < L.b_nq) return fail(SLAMB200_ERR_INVALID, "query keypoints < query rows");
+  // train_pts must hold one set per pair of the batch (b_pairs entries), each covering every
+  // trainIdx the matcher can have produced: the gather indexes it with trainIdx < rows(train p)
+  for (int p = 0; p < P; p++) {
+    if (!train_pts[p]) return fail(SLAMB200_ERR_INVALID, "train keypoint set %d is NULL", p);
+    if (train_pts[p]->n < L.b_tn[(size_t)p])
+      return fail(SLAMB200_ERR_INVALID, "train keypoint set %d has %d points, its descriptor set %d rows",
+                  p, train_pts[p]->n, L.b_tn[(size_t)p]);
+  }
+  CU(cudaStreamWaitEvent(s, L.done, 0));   // the match batch may have been enqueued on another stream
   // E (unless it is already resident on this device) and the train keypoint pointer table go
   // through the pinned staging area
   const size_t e_bytes = sizeof(double) * 9 * (size_t)P * H;
@@ -1971,10 +1996,11 @@ extern "C" int slamb200_batch_scores_fetch(slamb200_ctx* c, int32_t* counts, int
   cudaStream_t s = stream ? (cudaStream_t)stream : L.stream;
   const int P = L.s_pairs, H = L.s_H;
   if (P <= 0) return fail(SLAMB200_ERR_INVALID, "no scores have been enqueued on this context");
+  if (best_mask && mask_cap < L.b_cap) return fail(SLAMB200_ERR_INVALID, "mask_cap %d < %d", mask_cap, L.b_cap);
+  CU(cudaStreamWaitEvent(s, L.done, 0));
   if (counts) CU(cudaMemcpyAsync(counts, L.counts.p, sizeof(int32_t) * (size_t)P * H, cudaMemcpyDeviceToHost, s));
   if (best) CU(cudaMemcpyAsync(best, L.best.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
   if (best_mask) {
-    if (mask_cap < L.b_cap) return fail(SLAMB200_ERR_INVALID, "mask_cap %d < %d", mask_cap, L.b_cap);
     CU(cudaMemcpy2DAsync(best_mask, mask_cap, L.mask.p, L.b_cap, L.b_cap, P, cudaMemcpyDeviceToHost, s));
   }
   CU(cudaStreamSynchronize(s));
