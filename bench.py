@@ -221,7 +221,7 @@ def run_reference(args, rank, world):
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(world, n_sample_note=f"CPU arm: {n_sample} pairs per step"),
+        "config": workload_config(world),
         "tflops": value * FLOP_PER_PAIR / 1e12,
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind,
                          "sample": sample},
@@ -232,14 +232,12 @@ def run_reference(args, rank, world):
     emit(line)
 
 
-def workload_config(world, n_sample_note=None):
+def workload_config(world):
     cfg = {"workload": "cfg3: framesBatchSize=210 window, 1 query frame x 210 train frames, "
                        "10000 SIFT 128-d descriptors per frame, BF L2 kNN k=2 + ratio 0.7",
            "pairs": N_PAIRS, "rows_per_frame": N_ROWS, "ratio": RATIO,
            "sharding": f"{N_PAIRS} pairs split contiguously over {world} rank(s); no data-path collective",
            "l2": "inputs larger than L2 (211 resident descriptor sets, 0.6 GB of bf16 operands per step)"}
-    if n_sample_note:
-        cfg["note"] = n_sample_note
     return cfg
 
 
@@ -262,7 +260,9 @@ def run_b200(args, rank, world, local):
 
     pairs = my_pairs(rank, world)
     t_gen = time.perf_counter()
-    q, trains = make_inputs(pairs, pinned=True)
+    # PAGEABLE host Mats, as cv::SIFT::compute leaves them (a cv::Mat is never page-locked); only
+    # --e2e-upload pinned (an explicit experiment) allocates them page-locked
+    q, trains = make_inputs(pairs, pinned=args.e2e_upload == "pinned")
     log(f"[rank {rank}] generated {len(trains)} train frames in {time.perf_counter() - t_gen:.1f}s")
 
     ctx = Context(local)
@@ -270,9 +270,7 @@ def run_b200(args, rank, world, local):
     # sized before the first upload (every upload narrows integer-valued Mats on the host).
     cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     if args.e2e_upload == "auto":
-        # for the e2e pipeline narrowing pays once a rank has enough cores to outrun PCIe (about
-        # eight); otherwise the fp32 Mats go over the link as they are
-        args.e2e_upload = "packed" if cores >= 8 else "pinned"
+        args.e2e_upload = "packed"
     pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else \
         max(0, min(cores, 16) - args.e2e_workers)
     ctx.set_pack_threads(pack_threads)
@@ -347,11 +345,22 @@ def run_b200(args, rank, world, local):
     if tc_n > 0:
         # every timed step launches the kernel over this rank's pairs (possibly in sub-batches)
         achieved = FLOP_PER_PAIR * len(pairs) * args.steps / (tc_ms / 1e3) / 1e12
-        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        # Which measured peak applies follows from the timing regime: MEASURED_PEAKS.json's sustained
+        # figure is cuBLAS run back to back for seconds (SM clock settled at ~1.3 GHz under the power
+        # cap), its burst figure the best of ten isolated GEMMs.  A timed region shorter than one
+        # second never reaches the sustained regime (the clocks line shows it), so it is held to
+        # the BURST peak; a run of a second or more to the sustained one.
+        burst = float(peaks.get("bf16_tflops"))
+        sustained = float(peaks.get("bf16_tflops_sustained", burst))
+        timed_s = ms_total / 1e3
+        use_burst = timed_s < 1.0
+        peak = burst if use_burst else sustained
         roof = {"bound": "tensor", "kernel": "sift_tc_kernel (tcgen05 bf16 candidates)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
-                "frac_of_burst": achieved / float(peaks.get("bf16_tflops", peak)),
+                "peak_source": peak_src + (f", burst bf16 (timed region {timed_s:.3f} s < 1 s: the clocks never "
+                                           "settle into the sustained regime)" if use_burst else
+                                           f", sustained bf16 (timed region {timed_s:.1f} s)"),
+                "frac_of_burst": achieved / burst, "frac_of_sustained": achieved / sustained,
                 "kernel_ms_per_step": tc_ms / args.steps, "kernel_launches_per_step": tc_n / args.steps,
                 "algorithmic_flop_per_step": FLOP_PER_PAIR * len(pairs),
                 "other_kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()
@@ -495,7 +504,9 @@ def run_b200(args, rank, world, local):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(io[0].item()),
                     "d2h_bytes_per_step": int(io[1].item()), "steps": e2e_steps,
-                    "warmup_steps_run": len(warm_t), "upload": args.e2e_upload, "host_mat_bytes_per_step": (N_PAIRS + world) * N_ROWS * 512,
+                    "warmup_steps_run": len(warm_t), "upload": args.e2e_upload,
+                    "host_buffers": "page-locked" if args.e2e_upload == "pinned" else "pageable (numpy arrays)",
+                    "host_mat_bytes_per_step": (N_PAIRS + world) * N_ROWS * 512,
                     "host_threads": {"uploaders": args.e2e_workers, "matchers": args.e2e_matchers,
                                      "pack_pool": pack_threads if args.e2e_upload == "packed" else 0},
                     "timing": "host wall clock between device synchronisations, max over ranks",
@@ -830,7 +841,8 @@ def main():
     ap.add_argument("--e2e-upload", default="auto", choices=["auto", "packed", "pinned"],
                     help="packed: rows narrowed to bytes on the host threads (verified lossless) before "
                          "PCIe; pinned: the fp32 Mats read over PCIe as they are")
-    ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the CPU arm")
+    ap.add_argument("--ref-pairs", type=int, default=8, help="pairs per step of the CPU arm (a bounded sample "
+                    "of the 210-pair window: ~1 s per step on 16 cores)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

@@ -177,6 +177,43 @@ int slamb200_match_batch_enqueue(slamb200_ctx* ctx, int matcher, const slamb200_
 int slamb200_batch_fetch(slamb200_ctx* ctx, slamb200_dmatch* out, int cap, int* n_out,
                          void* stream);
 
+/* ---- one process, every GPU of the box ------------------------------------
+ * The reference is ONE process that walks the framesBatchSize window from `threadsCount` host
+ * threads (batch.cpp:162-226).  A device set gives that process all its GPUs behind the same call
+ * shape: the query frame's prepared descriptor set is replicated over NVLink (one upload, peer
+ * copies of the prepared slab, no second prep pass), every train frame lives on ONE device (the
+ * one that will match it: frame i of an n-frame window on device i*G/n, slamb200_set_owner), a
+ * batch call enqueues each device's share on that device without waiting and gathers the match
+ * lists once.  No data-path collective: pairs are independent.  Results are those of
+ * slamb200_match_batch on a single device, pair for pair. */
+typedef struct slamb200_set slamb200_set;      /* contexts on n devices of this process        */
+typedef struct slamb200_mdesc slamb200_mdesc;  /* a descriptor set resident on one or all of them */
+/* n_devices <= 0: every visible sm_100 device; otherwise devices 0 .. n_devices-1. */
+int slamb200_set_init(int n_devices, slamb200_set** out);
+int slamb200_set_shutdown(slamb200_set* set);
+int slamb200_set_devices(const slamb200_set* set);
+/* The single-device context of member i (every slamb200_* entry point may be used on it). */
+slamb200_ctx* slamb200_set_ctx(slamb200_set* set, int i);
+/* Device that owns item i of n under the contiguous split (i*G/n). */
+int slamb200_set_owner(const slamb200_set* set, int i, int n);
+/* Host rows -> a set resident on member `member`, or (member < 0) replicated on every member. */
+int slamb200_set_upload(slamb200_set* set, int member, int kind, const void* rows, int n,
+                        size_t row_stride, slamb200_mdesc** out);
+int slamb200_set_free_desc(slamb200_set* set, slamb200_mdesc* d);
+int slamb200_mdesc_rows(const slamb200_mdesc* d);
+/* One query frame against n_pairs train frames, each matched on the device it lives on (a
+ * replicated train set on the member with the least work).  out / cap / n_out as
+ * slamb200_match_batch.  The query must be replicated. */
+int slamb200_set_match_batch(slamb200_set* set, int matcher, const slamb200_mdesc* query,
+                             const slamb200_mdesc* const* trains, int n_pairs, double ratio,
+                             slamb200_dmatch* out, int cap, int* n_out);
+/* Device-resident form: enqueue on every member, then fetch.  device_ms (may be NULL, n members)
+ * receives each member's device time of the last enqueue (CUDA events around its share). */
+int slamb200_set_match_batch_enqueue(slamb200_set* set, int matcher, const slamb200_mdesc* query,
+                                     const slamb200_mdesc* const* trains, int n_pairs, double ratio);
+int slamb200_set_batch_fetch(slamb200_set* set, slamb200_dmatch* out, int cap, int* n_out,
+                             float* device_ms);
+
 /* ---- hot path B: RANSAC essential-matrix inlier scoring (cameraTranslation.cpp:41-46) --- */
 /* Scores H candidate essential matrices (row-major 3x3 doubles, in normalised coordinates, as
  * the 5-point solver returns them) against M matches exactly as cv::findEssentialMat's RANSAC

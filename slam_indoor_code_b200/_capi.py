@@ -55,6 +55,17 @@ SYMBOLS = {
     "slamb200_free_pts": (_i, [_vp, _vp]),
     "slamb200_score_batch_enqueue": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _d, _vp]),
     "slamb200_batch_scores_fetch": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "slamb200_set_init": (_i, [_i, _pp]),
+    "slamb200_set_shutdown": (_i, [_vp]),
+    "slamb200_set_devices": (_i, [_vp]),
+    "slamb200_set_ctx": (_vp, [_vp, _i]),
+    "slamb200_set_owner": (_i, [_vp, _i, _i]),
+    "slamb200_set_upload": (_i, [_vp, _i, _i, _vp, _i, _sz, _pp]),
+    "slamb200_set_free_desc": (_i, [_vp, _vp]),
+    "slamb200_mdesc_rows": (_i, [_vp]),
+    "slamb200_set_match_batch": (_i, [_vp, _i, _vp, _vp, _i, _d, _vp, _i, _vp]),
+    "slamb200_set_match_batch_enqueue": (_i, [_vp, _i, _vp, _vp, _i, _d]),
+    "slamb200_set_batch_fetch": (_i, [_vp, _vp, _i, _vp, _vp]),
     "slamb200_profile_enable": (_i, [_vp, _i]),
     "slamb200_profile_read": (_i, [_vp, _vp, _vp]),
 }

@@ -33,6 +33,9 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// last-error text for the other translation units of the library (device_set.cu)
+int set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+
 #define CU(call)                                                                       \
   do {                                                                                 \
     cudaError_t e__ = (call);                                                          \
@@ -1038,7 +1041,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   }
   // tcgen05 path geometry: one query block of 256 rows per CTA pair, 256-column train tiles
   const int n_rb = (nq + 255) / 256;
-  int n_cta = 1, n_slots = 2;
+  int n_cta = 1, n_slots = 2, wide = 0;
   bool holes = false;
   if (tc) {
     long long total = 0;
@@ -1049,6 +1052,8 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       max_tiles = n_cb * n_rb > max_tiles ? n_cb * n_rb : max_tiles;
     }
     n_cta = max_tiles < max_pairs ? (max_tiles > 0 ? max_tiles : 1) : max_pairs;
+    // the kernels' share arithmetic multiplies a tile index by the number of CTA pairs
+    wide = (unsigned long long)max_tiles * (unsigned long long)n_cta >= (1ull << 32) ? 1 : 0;
     for (int p = 0; p < n_pairs; p++) {
       memcpy(tp[p].tmap, trains[p]->tmaps, 128);             // main (hi)
       memcpy(tp[p].tmap + 128, trains[p]->tmaps + 256, 128);  // aug, train role
@@ -1163,14 +1168,15 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         {
           ProfScope ps(c, s, SLAMB200_K_SIFT_TC_GEN);
           grc = launch_sift_tc_candidates(qmaps, q->flags, nq, d_tc, d_pre, n_pairs, pre[n_pairs], n_cta,
-                                          n_slots, (uint4*)L.cand_g.p, d_status, nullptr, 1, s);
+                                          n_slots, (uint4*)L.cand_g.p, d_status, nullptr, 1, s, 0,
+                                          q->host_exact == 0 ? 1 : 0, wide);
         }
         if (grc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
         ProfScope ps(c, s, SLAMB200_K_SIFT_GEN_RERANK);
         launch_sift_gen_rerank(q->flags, q->f32, q->nrmf, nq, d_tc, d_pre, n_pairs, n_cta, n_slots, n_split,
                                (const uint4*)L.cand_g.p, (uint4*)L.part.p,
                                (uint2*)((char*)L.fb_list.p + FB_PART_BYTES), d_status + 1002,
-                               (unsigned long long*)L.fb_list.p, d_status + 1024, s);
+                               (unsigned long long*)L.fb_list.p, d_status + 1024, s, wide);
       }
       // Sub-batch pipeline (debug knob, default one sub-batch): the tcgen05 kernel of sub-batch
       // k+1 on `s` against the rerank / finalize kernels of sub-batch k on the lane's second
@@ -1202,7 +1208,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
           ProfScope ps(c, s, orb ? SLAMB200_K_ORB : SLAMB200_K_SIFT_TC);
           trc = launch_sift_tc_candidates(qmaps, q->flags, nq, tcp, pre_k, np, tiles_k, n_cta,
                                           n_slots, cand_k, d_status, k == 0 ? L.dbg : nullptr, 0, s,
-                                          orb ? 1 : 0);
+                                          orb ? 1 : 0, all_exact_known ? 1 : 0, wide);
         }
         if (trc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
         if (s2 != s) {
@@ -1219,7 +1225,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
                                  (int32_t*)L.knn_idx.p + (size_t)p0 * nq * 2,
                                  (float*)L.knn_dist.p + (size_t)p0 * nq * 2,
                                  (uint8_t*)L.flags.p + (size_t)p0 * nq,
-                                 (int32_t*)L.chunk_cnt.p + (size_t)p0 * chunks, s2);
+                                 (int32_t*)L.chunk_cnt.p + (size_t)p0 * chunks, s2, wide);
           }
           ProfScope psf(c, s2, SLAMB200_K_FINALIZE);
           launch_compact(nq, np, (const int32_t*)L.knn_idx.p + (size_t)p0 * nq * 2,
@@ -1234,7 +1240,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
           launch_sift_rerank(q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, n_cta, n_slots, n_split,
                              cand_k, part_k, (uint4*)L.work.p + (size_t)p0 * nq,
                              (float2*)L.work_v0.p + (size_t)p0 * nq, d_status + 1 + (k < 1000 ? k : 1000),
-                             d_status, want_knn ? 0 : 1, ratio, s2, orb ? 1 : 0);
+                             d_status, want_knn ? 0 : 1, ratio, s2, orb ? 1 : 0, wide);
         }
         ProfScope psf(c, s2, SLAMB200_K_FINALIZE);
         launch_finalize(part_k, nq, d_pairs + p0, np, n_split, orb ? 1 : 0, ratio,

@@ -198,12 +198,13 @@ int tc_slots(int n_cb_max, int total_tiles, int n_cta);
 int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_flags, int nq,
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
-                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s, int fp8 = 0);
+                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s, int fp8 = 0,
+                              int kinds_known = 0, int wide = 0);
 void launch_sift_gen_rerank(const int32_t* q_flags, const float* q_f32, const float* q_nrmf, int nq,
                             const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                             int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                             uint2* fb_list, int32_t* fb_count, unsigned long long* fb_part,
-                            int32_t* fb_done, cudaStream_t s);
+                            int32_t* fb_done, cudaStream_t s, int wide = 0);
 // scratch of the split fallback scan: fb_part holds SIFT_GEN_FB_ITEMS x 2 keys, fb_done
 // SIFT_GEN_FB_ITEMS counters that must be zero when the kernels start
 constexpr int SIFT_GEN_FB_ITEMS = 148 * 4;
@@ -211,13 +212,13 @@ void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32
                         const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                         int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                         uint4* work, float2* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
-                        double ratio, cudaStream_t s, int orb = 0);
+                        double ratio, cudaStream_t s, int orb = 0, int wide = 0);
 // merge + best-group rerank + ratio test in one kernel (match output only); then launch_compact
 void launch_tc_tail_fused(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
                           const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                           int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                           int32_t* err_flag, double ratio, int orb, int32_t* knn_idx, float* knn_dist,
-                          uint8_t* flags, int32_t* chunk_cnt, cudaStream_t s);
+                          uint8_t* flags, int32_t* chunk_cnt, cudaStream_t s, int wide = 0);
 void launch_compact(int nq, int n_pairs, const int32_t* knn_idx, const float* knn_dist,
                     const uint8_t* flags, const int32_t* chunk_cnt, slamb200_dmatch* out, int cap,
                     int32_t* n_out, cudaStream_t s);
@@ -227,4 +228,5 @@ void launch_orb_tc_prep(const uint8_t* u8, int n, int n_pad, uint8_t* e4, uint8_
                         uint8_t* augt, cudaStream_t s);
 
 void count_launch();
+int set_error(int code, const char* msg);   // fills slamb200_last_error() of the calling thread
 #define COUNT_LAUNCH() count_launch()

@@ -92,8 +92,11 @@ struct alignas(64) TcParams {
   uint4* cand;                 // [pair][slot][nq_pad]
   float* dbg;                  // optional raw accumulator dump of pair 0's first tile [256][256]
   int32_t* err_flag;
-  int mode;                    // 0 = product; 1..3 = timing experiments (results invalid)
+  int mode;                    // 0 = product; 1..7 = timing experiments (results invalid; MODES builds only)
   int fp8;                     // operands are e4m3 bytes (ORB bits expanded to 0/1): kind::f8f6f4, K = 32
+  int kinds_known;             // the host knows every pair of this launch is of this kernel's kind
+                               // (integer-valued / general floats): no flag loads in the tile walk
+  int wide;                    // tiles x CTA pairs can exceed 2^32: 64-bit share arithmetic
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -258,13 +261,29 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_neg) {
 // train set, which therefore stays L2-resident (2.9 MB) instead of every CTA pair dragging its own
 // train set through HBM; contiguous shares keep the segments (same query block) long.  The share
 // owner rotates with the frame-pair index so that rounding does not always favour the same CTAs.
+// Share arithmetic.  begin(c) = floor(total * c / n); the owner of tile x is the share c with
+// begin(c) <= x < begin(c + 1), i.e. the largest c with total * c < (x + 1) * n:
+// c = floor(((x + 1) * n - 1) / total).  32-bit unless the launch says the products can overflow
+// (`wide`, uniform): these run on the single threads that feed the TMA unit and the tensor core
+// at every frame-pair boundary, where a 64-bit division subroutine is a visible bubble.
+__device__ __forceinline__ int share_begin(int total, int c, int n, bool wide) {
+  return wide ? (int)(((unsigned long long)(unsigned)total * (unsigned)c) / (unsigned)n)
+              : (int)(((unsigned)total * (unsigned)c) / (unsigned)n);
+}
+__device__ __forceinline__ int owner_cta(int total, int n, int x, bool wide) {
+  return wide ? (int)(((unsigned long long)(unsigned)(x + 1) * (unsigned)n - 1ull) / (unsigned)total)
+              : (int)(((unsigned)(x + 1) * (unsigned)n - 1u) / (unsigned)total);
+}
+
 struct TileIter {
   int pair, rb, cb, n_cb;
   int tile, end;            // local tile index inside the current frame pair, and the share's end
   int slot_c;               // this CTA pair's (rotated) position for the current frame pair
   int n_tiles;              // tiles of the current frame pair
   int cta, n_cta;
-  bool skip;                // general-float train set: the exact fp32 kernel owns the pair
+  int t_n;                  // rows of the current train set (the last column tile may be partial)
+  int scan_p, scan_slot;    // next frame pair the walk looks at, and this CTA pair's position there
+  int pfx0, pfx1, pfx2;     // tile_prefix[scan_p], [scan_p + 1], [scan_p + 2] (read one pair ahead)
   const CUtensorMap* tmap;  // train maps: [0] main (hi), [1] aug (train role), [2] lo
   bool gen;                 // which kind of frame pair this walk visits
   // The pair table (and the tensor maps inside it) is rewritten by the host before every launch:
@@ -274,23 +293,36 @@ struct TileIter {
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap + 1) : "memory");
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap + 2) : "memory");
   }
-  // positions on the first non-empty share at or after frame pair `p`; false when none is left
-  __device__ bool seek(const TcParams& P, int p) {
-    for (; p < P.n_pairs; p++) {
-      n_tiles = P.tile_prefix[p + 1] - P.tile_prefix[p];
-      if (n_tiles == 0) continue;
+  // positions on the first non-empty share at or after frame pair scan_p; false when none is left
+  __device__ bool seek(const TcParams& P) {
+    for (; scan_p < P.n_pairs;) {
+      const int p = scan_p;
+      const int nt = pfx1 - pfx0;
+      const int slot = scan_slot;
+      // advance the scan state first: the prefix of the pair after next is requested now and is
+      // not needed before the next seek (one whole share of MMAs later)
+      scan_p = p + 1;
+      scan_slot = slot + 1 == n_cta ? 0 : slot + 1;
+      pfx0 = pfx1;
+      pfx1 = pfx2;
+      if (p + 3 <= P.n_pairs) pfx2 = P.tile_prefix[p + 3];
+      if (nt == 0) continue;
       // exact-mode pairs (integer-valued query and train) and general-float pairs are walked by
       // different instantiations of the kernel
-      if (((P.q_flags[0] | P.pairs[p].t_flags[0]) != 0) != gen) continue;
-      slot_c = (cta + p) % n_cta;
-      tile = (int)(((long long)n_tiles * slot_c) / n_cta);
-      end = (int)(((long long)n_tiles * (slot_c + 1)) / n_cta);
-      if (tile >= end) continue;
+      if (!P.kinds_known && ((P.q_flags[0] | P.pairs[p].t_flags[0]) != 0) != gen) continue;
+      const bool wide = P.wide != 0;
+      const int t0 = share_begin(nt, slot, n_cta, wide);
+      const int t1 = share_begin(nt, slot + 1, n_cta, wide);
+      if (t0 >= t1) continue;
       pair = p;
-      n_cb = n_tiles / P.n_rb;
-      rb = tile / n_cb;
-      cb = tile - rb * n_cb;
-      skip = false;
+      slot_c = slot;
+      n_tiles = nt;
+      tile = t0;
+      end = t1;
+      n_cb = (int)((unsigned)nt / (unsigned)P.n_rb);
+      rb = (int)((unsigned)t0 / (unsigned)n_cb);
+      cb = t0 - rb * n_cb;
+      t_n = P.pairs[p].t_n;
       tmap = reinterpret_cast<const CUtensorMap*>(P.pairs[p].tmap);
       return true;
     }
@@ -299,16 +331,27 @@ struct TileIter {
   }
   __device__ void init(const TcParams& P, int cta_, int n_cta_, bool gen_) {
     cta = cta_; n_cta = n_cta_; gen = gen_;
-    pair = 0; n_cb = 1; rb = 0; cb = 0; tile = 0; end = 0; slot_c = 0; n_tiles = 0;
-    skip = false; tmap = nullptr;
-    seek(P, 0);
+    pair = 0; n_cb = 1; rb = 0; cb = 0; tile = 0; end = 0; slot_c = 0; n_tiles = 0; t_n = 0;
+    tmap = nullptr;
+    scan_p = 0;
+    scan_slot = cta_;     // (cta + p) % n_cta at p = 0, kept incrementally
+    pfx0 = P.tile_prefix[0];
+    pfx1 = P.n_pairs >= 1 ? P.tile_prefix[1] : pfx0;
+    pfx2 = P.n_pairs >= 2 ? P.tile_prefix[2] : pfx1;
+    seek(P);
   }
   __device__ bool valid() const { return tile < end; }
+  // valid columns of the current tile rounded up to whole 32-column chunks (the rows up to the
+  // set's 256-row padding exist and carry an unreachable augmentation): the MMA's N
+  __device__ int n_eff() const {
+    const int left = t_n - cb * BN;
+    return left >= BN ? BN : ((left + 31) & ~31);
+  }
   // returns true when the next tile starts a new (pair, row block) segment
   __device__ bool next(const TcParams& P) {
     tile++;
     if (tile >= end) {
-      if (!seek(P, pair + 1)) { tile = 0; end = 0; }
+      if (!seek(P)) { tile = 0; end = 0; }
       return true;
     }
     if (++cb < n_cb) return false;
@@ -317,17 +360,6 @@ struct TileIter {
     return true;
   }
 };
-
-__device__ __forceinline__ int cta_range_begin(int total, int c, int n) {
-  return (int)(((long long)total * c) / n);
-}
-__device__ int owner_cta(int total, int n, int x) {
-  int c = (int)(((long long)x * n) / total);
-  if (c >= n) c = n - 1;
-  while (c + 1 < n && cta_range_begin(total, c + 1, n) <= x) c++;
-  while (c > 0 && cta_range_begin(total, c, n) > x) c--;
-  return c;
-}
 
 // Running top-2 over chunks, branch-free.  (m1, i1) best chunk minimum and the group that holds
 // it, s1 = the second-smallest group minimum INSIDE that best chunk, (m2, i2) second-best chunk.
@@ -430,13 +462,17 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0,
   }
 }
 
-template <bool DBG, bool GEN>
+// MODES = false is the product: `mode` is the constant 0 and none of the timing experiments below
+// exists in the instruction stream.  MODES = true (tools/tc_modes.py through
+// slamb200_dbg_set_tc_mode) selects role ablations at run time; their results are void.
+template <bool DBG, bool GEN, bool MODES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 sift_tc_kernel(const __grid_constant__ TcParams P) {
   constexpr int STG = GEN ? STAGE_G : STAGE;
   constexpr int NA = GEN ? N_ASTAGE_G : N_ASTAGE;
   constexpr int NB = GEN ? N_BSTAGE_G : N_BSTAGE;
   constexpr int AUG = GEN ? AUG_OFF_G : AUG_OFF;
+  const int mode = MODES ? P.mode : 0;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the SWIZZLE_128B atoms (same offset in both CTAs of the pair)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -460,7 +496,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
 
   // One parallel sweep over the pair flags: a launch with no frame pair of this kernel's kind
   // (all integer-valued, or all general-float) costs a single memory round trip.
-  {
+  if (!P.kinds_known) {
     const int qg = P.q_flags[0] != 0;
     int mine = 0;
     for (int p = threadIdx.x; p < P.n_pairs; p += TC_THREADS)
@@ -506,10 +542,6 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       int maps_of_pair = -1;
       bool new_seg = true;
       while (it.valid()) {
-        if (it.skip) {  // general-float train set: skipped here (exact kernel)
-          new_seg = it.next(P) || new_seg;
-          continue;
-        }
         if (maps_of_pair != it.pair) {
           it.acquire_maps();
           maps_of_pair = it.pair;
@@ -533,7 +565,9 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
         {
           const uint32_t dst = b_base + b_stage * STG;
           const uint32_t bar = b_full + 8 * b_stage;
-          const int row0 = it.cb * BN + (int)rank * BNH;
+          // the MMA takes the first N/2 rows of each CTA's stage as this CTA's half of the N
+          // columns: on a partial last tile (N < 256) the second CTA starts N/2 rows in, not 128
+          const int row0 = it.cb * BN + (int)rank * (it.n_eff() >> 1);
           if (rank == 0) mbar_expect_tx(bar, 2 * STG);
           tma_load_2d(dst, it.tmap, bar, 0, row0);
           tma_load_2d(dst + KBLK, it.tmap, bar, 64, row0);
@@ -555,13 +589,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, t_stage = 0, t_phase = 0;
       int cur_a = 0;
       bool new_seg = true;
-      constexpr uint32_t IDESC_NEG = idesc_bf16(2 * BM, BN, 1);
-      constexpr uint32_t IDESC_POS = idesc_bf16(2 * BM, BN, 0);
       while (it.valid()) {
-        if (it.skip) {
-          new_seg = it.next(P) || new_seg;
-          continue;
-        }
         if (new_seg) {
           mbar_wait(a_full + 8 * a_stage, a_phase);
           cur_a = a_stage;
@@ -573,20 +601,24 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
         const uint32_t a_addr = a_base + cur_a * STG;
         const uint32_t b_addr = b_base + b_stage * STG;
         const uint32_t d_tmem = tmem_base + t_stage * BN;
+        // N of this tile's instructions: 256, or the valid columns of a partial last tile in whole
+        // chunks (the instruction descriptor's N field is bits 17-22 = N >> 3)
+        const uint32_t n_bits = (uint32_t)(it.n_eff() >> 3) << 17;
         if (!GEN && P.fp8) {
           // ORB bits as e4m3 0/1 bytes: a stage row is 256 bytes = 256 elements, 32 per MMA; the
           // descriptor arithmetic is byte for byte that of the bf16 operand
-          constexpr uint32_t F8_NEG = idesc_e4m3(2 * BM, BN, 1), F8_POS = idesc_e4m3(2 * BM, BN, 0);
+          const uint32_t f8_neg = idesc_e4m3(2 * BM, 0, 1) | n_bits, f8_pos = idesc_e4m3(2 * BM, 0, 0) | n_bits;
 #pragma unroll
           for (int k = 0; k < 8; k++) {
             const uint64_t ad = desc_sw128(a_addr + (k >> 2) * KBLK + (k & 3) * 32);
             const uint64_t bd = desc_sw128(b_addr + (k >> 2) * KBLK + (k & 3) * 32);
-            tc_mma_f8(d_tmem, ad, bd, F8_NEG, k > 0 ? 1u : 0u);
+            tc_mma_f8(d_tmem, ad, bd, f8_neg, k > 0 ? 1u : 0u);
           }
-          tc_mma_f8(d_tmem, desc_interleave(a_addr + AUG), desc_interleave(b_addr + AUG), F8_POS, 1u);
-        } else if (P.mode < 3) {
+          tc_mma_f8(d_tmem, desc_interleave(a_addr + AUG), desc_interleave(b_addr + AUG), f8_pos, 1u);
+        } else if (mode < 3) {
           // exact mode: -(q.t); general floats: -(qh.th + qh.tl + ql.th), hi at k-blocks 0-1 and lo
           // at k-blocks 2-3 of the stage
+          const uint32_t idesc_neg = idesc_bf16(2 * BM, 0, 1) | n_bits, idesc_pos = idesc_bf16(2 * BM, 0, 0) | n_bits;
           constexpr int N_TERMS = GEN ? 3 : 1;
 #pragma unroll
           for (int term = 0; term < N_TERMS; term++) {
@@ -596,14 +628,14 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
             for (int k = 0; k < 8; k++) {
               const uint64_t ad = desc_sw128(ao + (k >> 2) * KBLK + (k & 3) * 32);
               const uint64_t bd = desc_sw128(bo + (k >> 2) * KBLK + (k & 3) * 32);
-              tc_mma(d_tmem, ad, bd, IDESC_NEG, (term | k) > 0 ? 1u : 0u);
+              tc_mma(d_tmem, ad, bd, idesc_neg, (term | k) > 0 ? 1u : 0u);
             }
           }
-          tc_mma(d_tmem, desc_interleave(a_addr + AUG), desc_interleave(b_addr + AUG), IDESC_POS, 1u);
-        } else if (P.mode >= 4) {
+          tc_mma(d_tmem, desc_interleave(a_addr + AUG), desc_interleave(b_addr + AUG), idesc_pos, 1u);
+        } else if (MODES && mode >= 4) {
           // timing probe: the same tile with kind::i8 MMAs (K = 32 bytes each) on whatever bytes the
           // stage holds; mode 4 issues the 5 a byte-wide kernel would need, mode 5 issues 9
-          const int n_i8 = P.mode == 4 ? 5 : 9;
+          const int n_i8 = mode == 4 ? 5 : 9;
           for (int k = 0; k < n_i8; k++) {
             const uint64_t ad = desc_sw128(a_addr + ((k >> 2) & 1) * KBLK + (k & 3) * 32);
             const uint64_t bd = desc_sw128(b_addr + ((k >> 2) & 1) * KBLK + (k & 3) * 32);
@@ -625,6 +657,8 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     const int half = ew >> 2;     // which column range of the tile (COLS_PER_WARP wide)
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int row_in_tile = (int)rank * BM + quarter * 32 + lane;  // within the pair's 256 rows
+    const bool do_ld = !MODES || mode < 2 || mode >= 6;
+    const bool do_proc = !MODES || mode < 1 || mode == 6;
     TileIter it;
     it.init(P, pair_id, n_pairs_cta, GEN);
     int t_stage = 0, t_phase = 0;
@@ -635,51 +669,76 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     bool first_tile = true;
     int seg_ntiles = 1, seg_ncb = 1, seg_c = 0;
     while (it.valid()) {
-      if (it.skip) {
-        new_seg = it.next(P) || new_seg;
-        continue;
-      }
       if (new_seg) {
         seg_pair = it.pair; seg_rb = it.rb;
         seg_ntiles = it.n_tiles; seg_ncb = it.n_cb; seg_c = it.slot_c;
         st.reset();
       }
+      // whole chunks of this warp's column range that hold columns of the tile (4 except on a
+      // partial last tile, where the MMA wrote only the first n_eff columns of the stage)
+      int n_chunks = (it.n_eff() - half * COLS_PER_WARP) >> 5;
+      n_chunks = n_chunks < 0 ? 0 : (n_chunks > CHUNKS ? CHUNKS : n_chunks);
       mbar_wait(t_full + 8 * t_stage, t_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + lane_addr + t_stage * BN + half * COLS_PER_WARP;
       const int gid_tile = (it.cb * BN + half * COLS_PER_WARP) / GROUP;
       const bool dump = DBG && first_tile && pair_id == 0;
-      uint32_t va[32], vb[32];  // (timing modes >= 2 read them uninitialised: results are void there)
-      if (P.mode < 2 || P.mode >= 6) TMEM_LD32(t_addr, va);
+      uint32_t va[32], vb[32];
+      if (MODES) {   // (modes without TMEM reads process whatever the registers hold)
 #pragma unroll
-      for (int c = 0; c < CHUNKS; c += 2) {
-        if (P.mode < 2 || P.mode >= 6) {
-          TMEM_WAIT32(va);
-          TMEM_LD32(t_addr + 32 * (c + 1), vb);
-        }
-        if (dump) {
+        for (int j = 0; j < 32; j++) { va[j] = 0; vb[j] = 0; }
+      }
+      if (n_chunks == CHUNKS) {
+        if (do_ld) TMEM_LD32(t_addr, va);
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * c + j] = __uint_as_float(va[j]);
-        }
-        if (P.mode < 1 || P.mode == 6) process_chunk<GEN>(va, gid_tile + 4 * c, st);
-        if (P.mode < 2 || P.mode >= 6) {
-          TMEM_WAIT32(vb);
-          if (c + 2 < CHUNKS) TMEM_LD32(t_addr + 32 * (c + 2), va);
-        }
-        if (c + 2 >= CHUNKS) {
-          // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
-          // (the leader's barrier counts the epilogue warps of both CTAs)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(t_empty + 8 * t_stage, 0);
-        }
-        if (dump) {
+        for (int c = 0; c < CHUNKS; c += 2) {
+          if (do_ld) {
+            TMEM_WAIT32(va);
+            TMEM_LD32(t_addr + 32 * (c + 1), vb);
+          }
+          if (dump) {
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * (c + 1) + j] = __uint_as_float(vb[j]);
+            for (int j = 0; j < 32; j++)
+              P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * c + j] = __uint_as_float(va[j]);
+          }
+          if (do_proc) process_chunk<GEN>(va, gid_tile + 4 * c, st);
+          if (do_ld) {
+            TMEM_WAIT32(vb);
+            if (c + 2 < CHUNKS) TMEM_LD32(t_addr + 32 * (c + 2), va);
+          }
+          if (c + 2 >= CHUNKS) {
+            // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+            // (the leader's barrier counts the epilogue warps of both CTAs)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(t_empty + 8 * t_stage, 0);
+          }
+          if (dump) {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * (c + 1) + j] = __uint_as_float(vb[j]);
+          }
+          if (do_proc) process_chunk<GEN>(vb, gid_tile + 4 * (c + 1), st);
         }
-        if (P.mode < 1 || P.mode == 6) process_chunk<GEN>(vb, gid_tile + 4 * (c + 1), st);
+      } else {
+        // partial last tile of a train set whose row count is not a multiple of 256: only the
+        // chunks the MMA wrote (the rest of the stage holds another tile's accumulators)
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; c++) {
+          if (do_ld) {
+            TMEM_LD32(t_addr + 32 * c, va);
+            TMEM_WAIT32(va);
+          }
+          if (dump) {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              P.dbg[(size_t)row_in_tile * BN + half * COLS_PER_WARP + 32 * c + j] = __uint_as_float(va[j]);
+          }
+          if (do_proc) process_chunk<GEN>(va, gid_tile + 4 * c, st);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(t_empty + 8 * t_stage, 0);
       }
       first_tile = false;
       if (++t_stage == 2) { t_stage = 0; t_phase ^= 1; }
@@ -687,7 +746,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       if (new_seg) {
         // flush this segment's per-row record
         // ordinal of this share among the shares that cut the row block (<= n_slots / 2)
-        int ord = seg_c - owner_cta(seg_ntiles, n_pairs_cta, seg_rb * seg_ncb);
+        int ord = seg_c - owner_cta(seg_ntiles, n_pairs_cta, seg_rb * seg_ncb, P.wide != 0);
         if (ord < 0 || COL_SPLITS * ord + COL_SPLITS - 1 >= P.n_slots) {
           if (lane == 0) atomicOr(P.err_flag, 2);
           ord = 0;
@@ -733,6 +792,7 @@ struct RerankParams {
   const int32_t* tile_prefix;
   const uint4* cand;
   int nq, nq_pad, n_slots, n_pairs, n_split, n_cta;
+  int wide;          // 64-bit share arithmetic (as TcParams::wide)
   int prune;         // 1: rows that cannot pass the ratio test skip the exact evaluation
   int orb;           // ORB sets: the accumulators are Hamming/2, q_u8 / t_u8 are the 32-byte rows
   double ratio;
@@ -777,8 +837,8 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
     if (n_tiles > 0) {
       const int n_rb = R.nq_pad / 256;
       const int n_cb = n_tiles / n_rb;
-      const int first = owner_cta(n_tiles, R.n_cta, blockIdx.x * n_cb);
-      const int last = owner_cta(n_tiles, R.n_cta, (blockIdx.x + 1) * n_cb - 1);
+      const int first = owner_cta(n_tiles, R.n_cta, blockIdx.x * n_cb, R.wide != 0);
+      const int last = owner_cta(n_tiles, R.n_cta, (blockIdx.x + 1) * n_cb - 1, R.wide != 0);
       nv = COL_SPLITS * (last - first + 1);
       if (nv > R.n_slots) nv = R.n_slots;  // cannot happen (host sizing); the self check would trip
     }
@@ -1180,8 +1240,8 @@ tc_tail_fused_kernel(const RerankParams R, int32_t* __restrict__ knn_idx, float*
       if (n_tiles > 0) {
         const int n_rb = R.nq_pad / 256;
         const int n_cb = n_tiles / n_rb;
-        const int first = owner_cta(n_tiles, R.n_cta, blockIdx.x * n_cb);
-        const int last = owner_cta(n_tiles, R.n_cta, (blockIdx.x + 1) * n_cb - 1);
+        const int first = owner_cta(n_tiles, R.n_cta, blockIdx.x * n_cb, R.wide != 0);
+        const int last = owner_cta(n_tiles, R.n_cta, (blockIdx.x + 1) * n_cb - 1, R.wide != 0);
         nv = COL_SPLITS * (last - first + 1);
         if (nv > R.n_slots) nv = R.n_slots;
       }
@@ -1238,110 +1298,77 @@ tc_tail_fused_kernel(const RerankParams R, int32_t* __restrict__ knn_idx, float*
     }
     __syncthreads();
     const int n_surv = n_surv_s;
-    // Survivors of the block: one warp per row, 4 lanes x 8 candidates.  Four rows are in flight
-    // per warp (all their loads are issued before the first reduction): a single-pair call has
-    // only 40 of these blocks, so the dependent-load latency per row is what matters.
-    const int part = lane & 3, cand = lane >> 2;
-    constexpr int U = 4;
-    for (int i0 = warp; i0 < n_surv; i0 += 8 * U) {
-      int rr[U], colv[U];
-      bool okv[U];
-      uint32_t dist[U];   // exact integer distance of this lane's candidate: d^2 (SIFT) or Hamming (ORB)
+    // Survivors of the block: eight lanes per row, one lane per candidate of the best group (its
+    // whole row: 8 x 16 B, the eight lanes of a group share the query row), four rows per warp and
+    // 32 per pass of the block.  The (distance, column) pair of a candidate fits one 32-bit key --
+    // d^2 < 2^22 for integer-valued rows, Hamming <= 256, three bits for the position inside the
+    // group -- so the top-2 of a group costs three rounds of two shuffles and four min / max.
+    // (A whole warp per row with 64-bit keys made this kernel instruction-bound: 0.24 ms per
+    // 210-pair window against a DRAM floor of 0.07 ms.)
+    const int cand = lane & 7, sub = lane >> 3;
+    for (int i0 = 0; i0 < n_surv; i0 += 32) {
+      const int i = i0 + warp * 4 + sub;
+      const bool have = i < n_surv;
+      const int r = have ? s_list[i] : 0;
+      const int col = s_g0[r] * GROUP + cand;
+      const bool ok = have && col < pr->t_n;
+      const int cc = ok ? col : 0;
+      const int qq = blockIdx.x * 256 + r;
+      uint32_t dist;   // exact integer distance of this lane's candidate: d^2 (SIFT) or Hamming (ORB)
       if (ORB) {
-        unsigned long long tv[U], qv[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int i = i0 + 8 * u;
-          rr[u] = i < n_surv ? s_list[i] : -1;
-          const int r = rr[u] >= 0 ? rr[u] : 0;
-          colv[u] = s_g0[r] * GROUP + cand;
-          okv[u] = rr[u] >= 0 && colv[u] < pr->t_n;
-          const int cc = okv[u] ? colv[u] : 0;
-          tv[u] = *reinterpret_cast<const unsigned long long*>(pr->t_u8 + (size_t)cc * 32 + part * 8);
-          qv[u] = *reinterpret_cast<const unsigned long long*>(R.q_u8 + (size_t)(blockIdx.x * 256 + r) * 32 + part * 8);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) dist[u] = (uint32_t)__popcll(qv[u] ^ tv[u]);
+        const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)cc * 32);
+        const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 32);
+        const uint4 t0 = tp[0], t1 = tp[1], q0 = qp[0], q1 = qp[1];
+        dist = (uint32_t)(__popc(q0.x ^ t0.x) + __popc(q0.y ^ t0.y) + __popc(q0.z ^ t0.z) + __popc(q0.w ^ t0.w) +
+                          __popc(q1.x ^ t1.x) + __popc(q1.y ^ t1.y) + __popc(q1.z ^ t1.z) + __popc(q1.w ^ t1.w));
       } else {
-        uint4 t0[U], t1[U], q0[U], q1[U];
-        uint32_t nn[U];
+        const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)cc * 128);
+        const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 128);
+        uint4 tv[8], qv[8];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int i = i0 + 8 * u;
-          rr[u] = i < n_surv ? s_list[i] : -1;
-          const int r = rr[u] >= 0 ? rr[u] : 0;
-          colv[u] = s_g0[r] * GROUP + cand;
-          okv[u] = rr[u] >= 0 && colv[u] < pr->t_n;
-          const int cc = okv[u] ? colv[u] : 0;
-          const int qq = blockIdx.x * 256 + r;
-          const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)cc * 128 + part * 32);
-          const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 128 + part * 32);
-          t0[u] = tp[0]; t1[u] = tp[1]; q0[u] = qp[0]; q1[u] = qp[1];
-          nn[u] = (uint32_t)pr->t_nrm2[cc] + (uint32_t)R.q_nrm2[qq];
-        }
+        for (int k = 0; k < 8; k++) { tv[k] = tp[k]; qv[k] = qp[k]; }
+        const uint32_t nn = (uint32_t)pr->t_nrm2[cc] + (uint32_t)R.q_nrm2[qq];
+        uint32_t dot = 0;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          uint32_t dot = 0;
-          dot = __dp4a(q0[u].x, t0[u].x, dot); dot = __dp4a(q0[u].y, t0[u].y, dot);
-          dot = __dp4a(q0[u].z, t0[u].z, dot); dot = __dp4a(q0[u].w, t0[u].w, dot);
-          dot = __dp4a(q1[u].x, t1[u].x, dot); dot = __dp4a(q1[u].y, t1[u].y, dot);
-          dot = __dp4a(q1[u].z, t1[u].z, dot); dot = __dp4a(q1[u].w, t1[u].w, dot);
-          dist[u] = dot;
+        for (int k = 0; k < 8; k++) {
+          dot = __dp4a(qv[k].x, tv[k].x, dot); dot = __dp4a(qv[k].y, tv[k].y, dot);
+          dot = __dp4a(qv[k].z, tv[k].z, dot); dot = __dp4a(qv[k].w, tv[k].w, dot);
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {   // the four lanes of a candidate hold partial dot products
-          dist[u] += __shfl_xor_sync(0xffffffffu, dist[u], 1);
-          dist[u] += __shfl_xor_sync(0xffffffffu, dist[u], 2);
-          dist[u] = nn[u] - 2u * dist[u];
-        }
+        dist = nn - 2u * dot;
       }
-      if (ORB) {
+      uint32_t k0 = ok ? ((dist << 3) | (uint32_t)cand) : 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          dist[u] += __shfl_xor_sync(0xffffffffu, dist[u], 1);
-          dist[u] += __shfl_xor_sync(0xffffffffu, dist[u], 2);
-        }
+      for (int off = 1; off <= 4; off <<= 1) {
+        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, off);
+        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, off);
+        const uint32_t hi = max(k0, o0);
+        k0 = min(k0, o0);
+        k1 = min(hi, min(k1, o1));
       }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (rr[u] < 0) continue;   // warp-uniform
-        const int r = rr[u];
-        unsigned long long k0 = okv[u] ? (((unsigned long long)dist[u] << 32) | (uint32_t)colv[u]) : ~0ull;
-        unsigned long long k1 = ~0ull;
-#pragma unroll
-        for (int off = 4; off <= 16; off <<= 1) {
-          const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, off);
-          const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off);
-          const unsigned long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0;
-          const unsigned long long s2 = k1 < o1 ? k1 : o1;
-          k0 = lo;
-          k1 = hi < s2 ? hi : s2;
-        }
-        if (lane == 0) {
-          float d0 = 0.f, d1 = -1.f;   // d1 < 0: no second neighbour
-          int idx = -1;
-          if (k0 != ~0ull) {
-            const uint32_t x0 = (uint32_t)(k0 >> 32);
-            // self check: the group's exact minimum must equal twice the tensor-core value
-            if ((float)x0 != 2.0f * s_v0[r]) atomicOr(R.err_flag, 1);
-            idx = (int)(uint32_t)(k0 & 0xFFFFFFFFu);
-            // second distance: inside the group, or the bound from outside it (exact values both)
-            const float Lr = s_L[r];
-            float x1 = Lr < INF ? 2.0f * Lr : -1.0f;
-            if (k1 != ~0ull) {
-              const float x2 = (float)(uint32_t)(k1 >> 32);
-              x1 = (x1 < 0.0f || x2 < x1) ? x2 : x1;
-            }
-            if (ORB) {
-              d0 = (float)x0;
-              d1 = x1;
-            } else {
-              d0 = sqrtf((float)x0);
-              d1 = x1 >= 0.0f ? sqrtf(x1) : -1.0f;
-            }
+      if (have && cand == 0) {
+        float d0 = 0.f, d1 = -1.f;   // d1 < 0: no second neighbour
+        int idx = -1;
+        if (k0 != 0xFFFFFFFFu) {
+          const uint32_t x0 = k0 >> 3;
+          // self check: the group's exact minimum must equal twice the tensor-core value
+          if ((float)x0 != 2.0f * s_v0[r]) atomicOr(R.err_flag, 1);
+          idx = s_g0[r] * GROUP + (int)(k0 & 7u);
+          // second distance: inside the group, or the bound from outside it (exact values both)
+          const float Lr = s_L[r];
+          float x1 = Lr < INF ? 2.0f * Lr : -1.0f;
+          if (k1 != 0xFFFFFFFFu) {
+            const float x2 = (float)(k1 >> 3);
+            x1 = (x1 < 0.0f || x2 < x1) ? x2 : x1;
           }
-          s_d0[r] = d0; s_d1[r] = d1; s_idx[r] = idx;
+          if (ORB) {
+            d0 = (float)x0;
+            d1 = x1;
+          } else {
+            d0 = sqrtf((float)x0);
+            d1 = x1 >= 0.0f ? sqrtf(x1) : -1.0f;
+          }
         }
+        s_d0[r] = d0; s_d1[r] = d1; s_idx[r] = idx;
       }
     }
     __syncthreads();
@@ -1373,6 +1400,7 @@ struct GenParams {
   const int32_t* tile_prefix;
   const uint4* cand;
   int nq, nq_pad, n_slots, n_pairs, n_split, n_cta;
+  int wide;
   uint4* part;
   uint2* fb_list;     // rows whose answer could not be certified: {pair, row}
   int32_t* fb_count;
@@ -1448,8 +1476,8 @@ __global__ void __launch_bounds__(256) sift_gen_rerank_kernel(const GenParams G)
   int n_valid = 0;
   if (n_tiles > 0) {
     const int n_rb = G.nq_pad / 256, n_cb = n_tiles / n_rb, rb = q >> 8;
-    const int first = owner_cta(n_tiles, G.n_cta, rb * n_cb);
-    const int last = owner_cta(n_tiles, G.n_cta, (rb + 1) * n_cb - 1);
+    const int first = owner_cta(n_tiles, G.n_cta, rb * n_cb, G.wide != 0);
+    const int last = owner_cta(n_tiles, G.n_cta, (rb + 1) * n_cb - 1, G.wide != 0);
     n_valid = min(COL_SPLITS * (last - first + 1), G.n_slots);
   }
   const float INF = __int_as_float(0x7f800000);
@@ -1727,16 +1755,19 @@ int tc_slots(int n_cb_max, int total_tiles, int n_cta) {
 int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_flags, int nq,
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
-                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s, int fp8) {
+                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s, int fp8,
+                              int kinds_known, int wide) {
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(sift_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(sift_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(sift_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(sift_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(sift_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(sift_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(sift_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SMEM_BYTES_G) != cudaSuccess ||
-        cudaFuncSetAttribute(sift_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(sift_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SMEM_BYTES_G) != cudaSuccess)
       return -1;
     attr_done = true;
@@ -1758,13 +1789,16 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_fl
   P.err_flag = err_flag;
   P.mode = g_tc_mode;
   P.fp8 = fp8;
+  P.kinds_known = kinds_known;
+  P.wide = wide;
   const dim3 grid(2 * n_cta_pairs);
   if (gen) {
-    if (dbg) sift_tc_kernel<true, true><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P);
-    else sift_tc_kernel<false, true><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P);
+    if (dbg) sift_tc_kernel<true, true, false><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P);
+    else sift_tc_kernel<false, true, false><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P);
   } else {
-    if (dbg) sift_tc_kernel<true, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P);
-    else sift_tc_kernel<false, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P);
+    if (dbg) sift_tc_kernel<true, false, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P);
+    else if (g_tc_mode != 0) sift_tc_kernel<false, false, true><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P);   // role ablations
+    else sift_tc_kernel<false, false, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P);
   }
   COUNT_LAUNCH();
   return 0;
@@ -1774,9 +1808,10 @@ void launch_sift_gen_rerank(const int32_t* q_flags, const float* q_f32, const fl
                             const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                             int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                             uint2* fb_list, int32_t* fb_count, unsigned long long* fb_part,
-                            int32_t* fb_done, cudaStream_t s) {
+                            int32_t* fb_done, cudaStream_t s, int wide) {
   if (nq <= 0 || n_pairs <= 0) return;
   GenParams G;
+  G.wide = wide;
   G.q_f32 = q_f32; G.q_nrmf = q_nrmf; G.q_flags = q_flags; G.pairs = pairs_dev;
   G.tile_prefix = tile_prefix_dev; G.cand = cand;
   G.nq = nq; G.nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM); G.n_slots = n_slots;
@@ -1794,9 +1829,10 @@ void launch_sift_rerank(const int32_t* q_flags, const uint8_t* q_u8, const int32
                         const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                         int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                         uint4* work, float2* work_v0, int32_t* work_n, int32_t* err_flag, int prune,
-                        double ratio, cudaStream_t s, int orb) {
+                        double ratio, cudaStream_t s, int orb, int wide) {
   if (nq <= 0 || n_pairs <= 0) return;
   RerankParams R;
+  R.wide = wide;
   R.orb = orb;
   R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
   R.tile_prefix = tile_prefix_dev; R.n_cta = n_cta_pairs;
@@ -1826,9 +1862,10 @@ void launch_tc_tail_fused(const int32_t* q_flags, const uint8_t* q_u8, const int
                           const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                           int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
                           int32_t* err_flag, double ratio, int orb, int32_t* knn_idx, float* knn_dist,
-                          uint8_t* flags, int32_t* chunk_cnt, cudaStream_t s) {
+                          uint8_t* flags, int32_t* chunk_cnt, cudaStream_t s, int wide) {
   if (nq <= 0 || n_pairs <= 0) return;
   RerankParams R;
+  R.wide = wide;
   R.orb = orb;
   R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
   R.tile_prefix = tile_prefix_dev; R.n_cta = n_cta_pairs;

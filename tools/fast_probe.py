@@ -2,7 +2,7 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cv2, numpy as np
-from oracle import synth
+import synth_inputs as synth
 from slam_indoor_code_b200.feature_matching import Context
 from slam_indoor_code_b200 import fast_extractor as fe
 ctx = Context(0)

@@ -3,7 +3,7 @@ and a 50k x 50k pair matched with the query read over NVLink vs both sets local.
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
-from oracle import synth
+import synth_inputs as synth
 from slam_indoor_code_b200.feature_matching import Context, MatcherType
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local); dev = torch.device("cuda", local)

@@ -4,7 +4,7 @@ kernels."""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import synth, c_oracle
+import synth_inputs as synth, c_oracle
 from slam_indoor_code_b200.feature_matching import Context, MatcherType
 from slam_indoor_code_b200 import _capi
 

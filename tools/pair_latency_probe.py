@@ -3,7 +3,7 @@ host enqueue cost, per-kernel device times)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import synth
+import synth_inputs as synth
 from slam_indoor_code_b200.feature_matching import Context, MatcherType
 
 torch.cuda.init(); torch.zeros(1, device="cuda")

@@ -2,7 +2,7 @@
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import synth
+import synth_inputs as synth
 from slam_indoor_code_b200.feature_matching import Context, MatcherType
 torch.zeros(1, device="cuda")
 ctx = Context(0); lib = ctx._lib

@@ -3,7 +3,7 @@ time of exchange (NCCL all-gather) + device uploads + matching, max over ranks."
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
-from oracle import synth
+import synth_inputs as synth
 from slam_indoor_code_b200 import window_sharding as ws
 from slam_indoor_code_b200.feature_matching import Context, MatcherType
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
