@@ -1429,6 +1429,7 @@ static int make_score_params(const double K[4], double threshold_px, ScoreParams
   const float u = nextafterf(t, INFINITY);
   const double mid = ((double)t + (double)u) * 0.5;
   sp->t = t;
+  sp->mid = mid;
   sp->mid_lo = mid * (1.0 - ldexp(1.0, -49));
   sp->mid_hi = mid * (1.0 + ldexp(1.0, -49));
   return SLAMB200_OK;

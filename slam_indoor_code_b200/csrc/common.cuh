@@ -114,6 +114,7 @@ int finalize_chunks(int nq);
 struct ScoreParams {
   double ax, ay, bx, by;  // normalisation: x = u*ax + bx
   double mid_lo, mid_hi;  // fast accept / reject bounds on num/den
+  double mid;             // midpoint(t, nextafterf(t)) itself (the counting kernel's integer-domain test)
   float t;                // (float)(thr*thr)
 };
 void launch_normalize_points(const float2* p1, const float2* p2, int total, ScoreParams sp,

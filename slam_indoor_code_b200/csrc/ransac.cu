@@ -52,6 +52,36 @@ struct SampsonScorer {
     if (num > __dmul_rn(sp.mid_hi, den)) return 0;
     return (float)__ddiv_rn(num, den) <= sp.t ? 1 : 0;  // boundary sliver, NaN, 0/0
   }
+  // The counting kernel's form of the same test, branch-free: 1 = inlier, 0 = outlier, 2 = inside
+  // the sliver (the caller then takes inlier()).  num and m = RN(mid * den) are non-negative
+  // doubles, whose order is the order of their bit patterns as integers: "num is more than 32
+  // ulps below m" implies num < mid*den*(1 - 2^-49) (an ulp is at least 2^-53 of the value, m is
+  // within 2^-53 of mid*den), likewise above -- the proofs of inlier() with a wider margin.  One
+  // DMUL and two 64-bit integer compares (ALU pipe) replace two DMULs and two DSETPs on the FP64
+  // pipe, and without branches the compiler interleaves the dependent chains of several matches.
+  // NaN (0/0, inf/inf, NaN inputs) lands in the sliver or on the outlier side, where inlier()
+  // and this test agree: a NaN pattern compares above every finite value, and a NaN den makes
+  // num NaN as well.
+  static constexpr bool HAS_CLASSIFY = true;
+  __device__ static __forceinline__ int classify(const double (&e)[9], const double4 p,
+                                                 const ScoreParams& sp) {
+    const double x1 = p.x, y1 = p.y, x2 = p.z, y2 = p.w;
+    const double a0 = __dadd_rn(__dadd_rn(__dmul_rn(e[0], x1), __dmul_rn(e[1], y1)), e[2]);
+    const double a1 = __dadd_rn(__dadd_rn(__dmul_rn(e[3], x1), __dmul_rn(e[4], y1)), e[5]);
+    const double a2 = __dadd_rn(__dadd_rn(__dmul_rn(e[6], x1), __dmul_rn(e[7], y1)), e[8]);
+    const double b0 = __dadd_rn(__dadd_rn(__dmul_rn(e[0], x2), __dmul_rn(e[3], y2)), e[6]);
+    const double b1 = __dadd_rn(__dadd_rn(__dmul_rn(e[1], x2), __dmul_rn(e[4], y2)), e[7]);
+    const double s = __dadd_rn(__dadd_rn(__dmul_rn(x2, a0), __dmul_rn(y2, a1)), a2);
+    const double num = __dmul_rn(s, s);
+    const double den = __dadd_rn(
+        __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(b0, b0)),
+        __dmul_rn(b1, b1));
+    const unsigned long long nb = (unsigned long long)__double_as_longlong(num);
+    const unsigned long long mb = (unsigned long long)__double_as_longlong(__dmul_rn(sp.mid, den));
+    const int in = nb + 32ull < mb ? 1 : 0;
+    const int out = nb > mb + 32ull ? 1 : 0;
+    return in ? 1 : (out ? 0 : 2);
+  }
 };
 
 // solvePnPRansac's error (reference call cycleProcessing/mainCycle.cpp:155-159):
@@ -67,6 +97,10 @@ template <int DIST>
 struct ReprojScorer {
   static constexpr int ND = 12;
   typedef PnpParams Params;
+  static constexpr bool HAS_CLASSIFY = false;
+  __device__ static __forceinline__ int classify(const double (&m)[12], const double4 p, const PnpParams& pp) {
+    return inlier(m, p, pp);
+  }
   __device__ static __forceinline__ int inlier(const double (&m)[12], const double4 p,
                                                const PnpParams& pp) {
     const double X = p.x, Y = p.y, Z = p.z;
@@ -192,8 +226,25 @@ score_counts_kernel(const double4* __restrict__ npts, const int32_t* __restrict_
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += RS_THREADS) pts[i] = npts[base + c0 + i];
     __syncthreads();
+    if (S::HAS_CLASSIFY) {
+      // four matches at a time, branch-free; the rare boundary cases are redone exactly afterwards
+      int i = 0;
+      for (; i + 4 <= n; i += 4) {
+        int c[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) c[u] = S::classify(Eh, pts[i + u], sp);
+        cnt += (c[0] == 1) + (c[1] == 1) + (c[2] == 1) + (c[3] == 1);
+        if (((c[0] | c[1] | c[2] | c[3]) & 2) != 0) {
+#pragma unroll 1
+          for (int u = 0; u < 4; u++)
+            if (c[u] == 2) cnt += S::inlier(Eh, pts[i + u], sp);
+        }
+      }
+      for (; i < n; i++) cnt += S::inlier(Eh, pts[i], sp);
+    } else {
 #pragma unroll 2
-    for (int i = 0; i < n; i++) cnt += S::inlier(Eh, pts[i], sp);
+      for (int i = 0; i < n; i++) cnt += S::inlier(Eh, pts[i], sp);
+    }
   }
   if (h < H && cnt) atomicAdd(&counts[(size_t)pair * H + h], cnt);
 }

@@ -1298,43 +1298,65 @@ tc_tail_fused_kernel(const RerankParams R, int32_t* __restrict__ knn_idx, float*
     }
     __syncthreads();
     const int n_surv = n_surv_s;
-    // Survivors of the block: eight lanes per row, one lane per candidate of the best group (its
-    // whole row: 8 x 16 B, the eight lanes of a group share the query row), four rows per warp and
-    // 32 per pass of the block.  The (distance, column) pair of a candidate fits one 32-bit key --
-    // d^2 < 2^22 for integer-valued rows, Hamming <= 256, three bits for the position inside the
-    // group -- so the top-2 of a group costs three rounds of two shuffles and four min / max.
-    // (A whole warp per row with 64-bit keys made this kernel instruction-bound: 0.24 ms per
-    // 210-pair window against a DRAM floor of 0.07 ms.)
+    // Survivors of the block: eight lanes per row (four rows per warp, 32 per pass of the block),
+    // lane c ending up with candidate c of the row's best group.  The group's eight train rows are
+    // 1 KB of consecutive bytes: each load instruction takes ONE 128-byte row per survivor row,
+    // lane c its 16-byte slice c (coalesced: four cache lines per instruction; a lane reading its
+    // own candidate row touched 32 lines per instruction and the kernel was bound by the L1's
+    // tag stage, ncu l1tex 80 %), multiplies it with its slice of the query row, and a
+    // reduce-scatter over the eight lanes (4 + 2 + 1 shuffles) leaves candidate c's dot product
+    // in lane c.  The (distance, column) pair of a candidate fits one 32-bit key -- d^2 < 2^22
+    // for integer-valued rows, Hamming <= 256, three bits for the position inside the group -- so
+    // the top-2 of a group costs three rounds of two shuffles and four min / max.
     const int cand = lane & 7, sub = lane >> 3;
     for (int i0 = 0; i0 < n_surv; i0 += 32) {
       const int i = i0 + warp * 4 + sub;
       const bool have = i < n_surv;
       const int r = have ? s_list[i] : 0;
-      const int col = s_g0[r] * GROUP + cand;
+      const int col0 = s_g0[r] * GROUP;
+      const int col = col0 + cand;
       const bool ok = have && col < pr->t_n;
-      const int cc = ok ? col : 0;
       const int qq = blockIdx.x * 256 + r;
       uint32_t dist;   // exact integer distance of this lane's candidate: d^2 (SIFT) or Hamming (ORB)
       if (ORB) {
+        const int cc = ok ? col : 0;
         const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)cc * 32);
         const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 32);
         const uint4 t0 = tp[0], t1 = tp[1], q0 = qp[0], q1 = qp[1];
         dist = (uint32_t)(__popc(q0.x ^ t0.x) + __popc(q0.y ^ t0.y) + __popc(q0.z ^ t0.z) + __popc(q0.w ^ t0.w) +
                           __popc(q1.x ^ t1.x) + __popc(q1.y ^ t1.y) + __popc(q1.z ^ t1.z) + __popc(q1.w ^ t1.w));
       } else {
-        const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)cc * 128);
-        const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 128);
-        uint4 tv[8], qv[8];
+        // (rows up to the set's 256-row padding exist: a group never leaves the allocation)
+        const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)col0 * 128) + cand;
+        const uint4 qv = *(reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 128) + cand);
+        uint4 tv[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { tv[k] = tp[k]; qv[k] = qp[k]; }
-        const uint32_t nn = (uint32_t)pr->t_nrm2[cc] + (uint32_t)R.q_nrm2[qq];
-        uint32_t dot = 0;
+        for (int k = 0; k < 8; k++) tv[k] = tp[8 * k];
+        const uint32_t nn = (uint32_t)pr->t_nrm2[ok ? col : 0] + (uint32_t)R.q_nrm2[qq];
+        uint32_t pd[8];   // pd[k]: this lane's slice of q . (candidate row k)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-          dot = __dp4a(qv[k].x, tv[k].x, dot); dot = __dp4a(qv[k].y, tv[k].y, dot);
-          dot = __dp4a(qv[k].z, tv[k].z, dot); dot = __dp4a(qv[k].w, tv[k].w, dot);
+          uint32_t d = __dp4a(qv.x, tv[k].x, 0u);
+          d = __dp4a(qv.y, tv[k].y, d);
+          d = __dp4a(qv.z, tv[k].z, d);
+          pd[k] = __dp4a(qv.w, tv[k].w, d);
         }
-        dist = nn - 2u * dot;
+        const bool b4 = (cand & 4) != 0, b2 = (cand & 2) != 0, b1 = (cand & 1) != 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t send = b4 ? pd[j] : pd[j + 4], keep = b4 ? pd[j + 4] : pd[j];
+          pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const uint32_t send = b2 ? pd[j] : pd[j + 2], keep = b2 ? pd[j + 2] : pd[j];
+          pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        {
+          const uint32_t send = b1 ? pd[0] : pd[1], keep = b1 ? pd[1] : pd[0];
+          pd[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        dist = nn - 2u * pd[0];
       }
       uint32_t k0 = ok ? ((dist << 3) | (uint32_t)cand) : 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
 #pragma unroll

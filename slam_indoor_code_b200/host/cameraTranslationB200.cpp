@@ -5,11 +5,16 @@
 // RANSAC control is ransac_control.h, every candidate is scored on the B200.  Result: the same E
 // and the same N x 1 uchar mask as OpenCV's own loop.
 //
-// This unit needs the real OpenCV (calib3d) and is compiled inside the reference tree; the control
-// logic it relies on is compiled and tested here on its own (host_shim_test.cpp).
-#ifndef SLAMB200_CV_SHIM
+// Built against the real OpenCV (calib3d) inside the reference tree, or against host/cv_shim.h
+// (-DSLAMB200_CV_SHIM), where the 5-point solver is injected by the test harness
+// (tests/test_gpu_host_cpp.py plugs in cv2's): the whole call then returns cv2.findEssentialMat's
+// E and mask bit for bit.
+#ifdef SLAMB200_CV_SHIM
+#include "cv_shim.h"
+#else
 #include <opencv2/calib3d.hpp>
 #include <opencv2/core.hpp>
+#endif
 
 #include <stdexcept>
 #include <string>
@@ -30,7 +35,6 @@ cv::Mat findEssentialMatB200(slamb200_ctx* ctx, const std::vector<cv::Point2f>& 
     for (int i = 0; i < 5; i++) { a[i] = points1[idx[i]]; b[i] = points2[idx[i]]; }
     cv::Mat E = cv::findEssentialMat(a, b, Kd, cv::RANSAC, 0.999, 1.0);  // 3k x 3 stacked candidates
     if (E.empty()) return;
-    E = E.reshape(1, E.rows / 3 * 9 / 9);
     for (int r = 0; r + 2 < E.rows; r += 3)
       for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) models.push_back(E.at<double>(r + i, j));
@@ -49,4 +53,3 @@ cv::Mat findEssentialMatB200(slamb200_ctx* ctx, const std::vector<cv::Point2f>& 
                            threshold, &c, &b, mask.data, nullptr);
   return cv::Mat(3, 3, CV_64F, best).clone();
 }
-#endif

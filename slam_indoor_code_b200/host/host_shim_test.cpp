@@ -3,7 +3,12 @@
 // exactly as the reference's callers would (batch.cpp:127-130).
 #include "featureMatchingB200.cpp"
 #include "fastExtractorB200.cpp"
+#include "cameraTranslationB200.cpp"
+#include "poseEstimationB200.cpp"
+#include "triangulateB200.cpp"
 #include "ransac_control.h"
+
+LogFilesStreams logStreams;   // misc/IOmisc.h:19 in the reference
 
 static double g_ratio = 0.7;
 double knnMatcherDistance() { return g_ratio; }
@@ -162,5 +167,125 @@ int hostshim_find_good_frame(const void* q, int nq, const void* const* t, const 
   } catch (...) {
     return -2;
   }
+}
+}
+
+// ---- the other B200 units of the drop-in, with the CPU solvers injected by the harness ----------
+extern "C" {
+void hostshim_set_solvers(cv::shim::FivePointFn f5, cv::shim::SolvePnPFn pnp, cv::shim::RodriguesFn rod) {
+  cv::shim::five_point() = f5;
+  cv::shim::solve_pnp() = pnp;
+  cv::shim::rodrigues() = rod;
+}
+
+// findEssentialMatB200 (cameraTranslation.cpp:41-46): 1 = model found (E_out, mask_out filled), 0 = none, -1 = exception
+int hostshim_find_essential_mat(const float* p1, const float* p2, int N, const double* K9, double prob, double thr,
+                                double* E_out, unsigned char* mask_out) {
+  try {
+    std::vector<cv::Point2f> a((size_t)N), b((size_t)N);
+    for (int i = 0; i < N; i++) { a[i] = cv::Point2f(p1[2 * i], p1[2 * i + 1]); b[i] = cv::Point2f(p2[2 * i], p2[2 * i + 1]); }
+    cv::Mat K(3, 3, CV_64F, const_cast<double*>(K9)), mask;
+    cv::Mat E = findEssentialMatB200(slamb200HostContext(), a, b, K, prob, thr, mask);
+    if (E.empty()) return 0;
+    for (int i = 0; i < 9; i++) E_out[i] = E.at<double>(i / 3, i % 3);
+    for (int i = 0; i < N; i++) mask_out[i] = mask.at<unsigned char>(i, 0);
+    return 1;
+  } catch (...) {
+    return -1;
+  }
+}
+
+// solvePnPRansacB200 (mainCycle.cpp:155-159): returns 1/0 like cv::solvePnPRansac, -1 on an exception
+int hostshim_solve_pnp_ransac(const float* obj, const float* img, int N, const double* K9, const double* dist,
+                              int n_dist, double* rvec_out, double* tvec_out, int* inliers_out, int* n_inliers) {
+  try {
+    std::vector<cv::Point3f> o((size_t)N);
+    std::vector<cv::Point2f> m((size_t)N);
+    for (int i = 0; i < N; i++) { o[i] = cv::Point3f(obj[3 * i], obj[3 * i + 1], obj[3 * i + 2]); m[i] = cv::Point2f(img[2 * i], img[2 * i + 1]); }
+    cv::Mat K(3, 3, CV_64F, const_cast<double*>(K9)), D, rvec, tvec;
+    if (n_dist > 0) D = cv::Mat(1, n_dist, CV_64F, const_cast<double*>(dist));
+    std::vector<int> inl;
+    const bool ok = solvePnPRansacB200(slamb200HostContext(), o, m, K, D, rvec, tvec, &inl);
+    if (!ok) return 0;
+    for (int i = 0; i < 3; i++) { rvec_out[i] = rvec.at<double>(i); tvec_out[i] = tvec.at<double>(i); }
+    *n_inliers = (int)inl.size();
+    for (size_t i = 0; i < inl.size(); i++) inliers_out[i] = inl[i];
+    return 1;
+  } catch (...) {
+    return -1;
+  }
+}
+
+// triangulationWrapper (triangulate.cpp:57-72): N x 2 CV_64F point Mats, 3 x 4 projection matrices -> 4 x N
+int hostshim_triangulate(const double* p1, const double* p2, int N, const double* P1, const double* P2, double* out4xN) {
+  try {
+    cv::Mat a(N, 2, CV_64F, const_cast<double*>(p1)), b(N, 2, CV_64F, const_cast<double*>(p2));
+    cv::Mat m1(3, 4, CV_64F, const_cast<double*>(P1)), m2(3, 4, CV_64F, const_cast<double*>(P2)), X;
+    triangulationWrapper(a, b, m1, m2, X);
+    if (X.rows != 4 || X.cols != N) return -2;
+    for (int r = 0; r < 4; r++) memcpy(out4xN + (size_t)r * N, X.ptr<double>(r), sizeof(double) * (size_t)N);
+    return 0;
+  } catch (...) {
+    return -1;
+  }
+}
+
+// ---- caller-owned Mats that persist across calls (what BatchElement / the previous frame hold) ----
+void* hostshim_mat_create(const void* rows, int n, int cols, int type) {
+  cv::Mat* m = new cv::Mat();
+  m->create(n, cols, type);
+  if (n > 0) memcpy(m->data, rows, (size_t)n * m->step);
+  return m;
+}
+void hostshim_mat_free(void* m) { delete (cv::Mat*)m; }
+void hostshim_mat_write(void* m, const void* rows) {   // in-place rewrite of the same buffer
+  cv::Mat* mm = (cv::Mat*)m;
+  memcpy(mm->data, rows, (size_t)mm->rows * mm->step);
+}
+int hostshim_match_mats(void* q, void* t, int type, cv::DMatch* out, int cap) {
+  try {
+    std::vector<cv::DMatch> m;
+    matchFeatures(*(cv::Mat*)q, *(cv::Mat*)t, m, type);
+    if ((int)m.size() > cap) return -2;
+    for (size_t i = 0; i < m.size(); i++) out[i] = m[i];
+    return (int)m.size();
+  } catch (...) {
+    return -1;
+  }
+}
+void hostshim_cache_stats(long long* hits, long long* misses) {
+  size_t h = 0, m = 0;
+  slamb200HostCacheStats(&h, &m);
+  *hits = (long long)h;
+  *misses = (long long)m;
+}
+void hostshim_cache_clear() { slamb200HostCacheClear(); }
+
+// matchFramesPairFeatures(firstFrameDescriptor, secondFrame, secondFeatures, ORB_BF, matches)
+// (featureMatching.h:47-53) on a persistent query Mat and a BGR / gray frame with FAST-like keypoints
+int hostshim_match_frames_pair_orb(void* q_desc, const void* frame, int rows, int cols, int channels, size_t step,
+                                   const float* kps, int n, cv::DMatch* out, int cap, int* n_features_left) {
+  try {
+    cv::Mat f(rows, cols, channels == 3 ? CV_8UC3 : CV_8U, const_cast<void*>(frame), step);
+    std::vector<cv::KeyPoint> features((size_t)n);
+    for (int i = 0; i < n; i++) { features[i].pt.x = kps[3 * i]; features[i].pt.y = kps[3 * i + 1]; features[i].angle = kps[3 * i + 2]; }
+    std::vector<cv::DMatch> m;
+    matchFramesPairFeatures(*(cv::Mat*)q_desc, f, features, ORB_BF, m);
+    *n_features_left = (int)features.size();
+    if ((int)m.size() > cap) return -2;
+    for (size_t i = 0; i < m.size(); i++) out[i] = m[i];
+    return (int)m.size();
+  } catch (...) {
+    return -1;
+  }
+}
+// the text written to logStreams.timeStream so far (and clears it)
+int hostshim_time_log(char* buf, int cap) {
+  const std::string s = logStreams.timeStream.str();
+  logStreams.timeStream.str("");
+  const int n = (int)s.size() < cap - 1 ? (int)s.size() : cap - 1;
+  memcpy(buf, s.data(), (size_t)n);
+  buf[n] = 0;
+  return n;
 }
 }

@@ -12,11 +12,15 @@
 // twin of this unit (slam_indoor_code_b200/pnp_ransac.py) is held bit-exact to cv2.solvePnPRansac
 // in tests/test_gpu_pnp.py.
 //
-// This unit needs the real OpenCV (calib3d) and is compiled inside the reference tree; the control
-// logic it relies on is compiled and tested here on its own (host_shim_test.cpp).
-#ifndef SLAMB200_CV_SHIM
+// Built against the real OpenCV (calib3d) inside the reference tree, or against host/cv_shim.h
+// (-DSLAMB200_CV_SHIM), where cv::solvePnP and cv::Rodrigues are injected by the test harness
+// (tests/test_gpu_host_cpp.py plugs in cv2's).
+#ifdef SLAMB200_CV_SHIM
+#include "cv_shim.h"
+#else
 #include <opencv2/calib3d.hpp>
 #include <opencv2/core.hpp>
+#endif
 
 #include <cstring>
 #include <stdexcept>
@@ -93,4 +97,3 @@ bool solvePnPRansacB200(slamb200_ctx* ctx, const std::vector<cv::Point3f>& objec
   if (inliers) inliers->swap(inl);
   return ok;
 }
-#endif

@@ -3,9 +3,13 @@
 // per-point loop of reconstructPointsFor3D (:17-55) runs on the B200 through slamb200_triangulate.
 // reconstruct() (:74-89) and the rest of triangulate.cpp stay as they are and call this.
 //
-// Needs the real OpenCV headers; compiled inside the reference tree.
-#ifndef SLAMB200_CV_SHIM
+// Built against the real OpenCV inside the reference tree, or against host/cv_shim.h
+// (-DSLAMB200_CV_SHIM) for the tests of this repository.
+#ifdef SLAMB200_CV_SHIM
+#include "cv_shim.h"
+#else
 #include <opencv2/core.hpp>
+#endif
 
 #include <stdexcept>
 #include <string>
@@ -33,4 +37,3 @@ void triangulationWrapper(cv::InputArray projPoints1, cv::InputArray projPoints2
                                       p1.ptr<float>(), p2.ptr<float>(), p1.rows, out.ptr<double>(), nullptr);
   if (rc != SLAMB200_OK) throw std::runtime_error(std::string("slamb200_triangulate: ") + slamb200_last_error());
 }
-#endif
