@@ -13,10 +13,9 @@ region.
 
   value  = pairs/s with every descriptor set already resident in HBM, CUDA-event timed.
   e2e    = pairs/s through the C ABI with HOST buffers: every step hands the query and the 210
-           train descriptor Mats (CV_32F, host memory) to the library, matches, and copies the match
-           lists back.  Default upload = slamb200_upload_desc_packed: host threads narrow the
-           integer-valued rows to bytes (every element verified) so that 1/4 of the bytes cross
-           PCIe; --e2e-upload pinned sends the fp32 Mats as they are (PCIe-bound, ~9.3k pairs/s).
+           train descriptor Mats (CV_32F, PAGEABLE host memory) to slamb200_match_batch_host, which
+           narrows the integer-valued rows to bytes on host threads (every element verified: 1/4 of
+           the bytes cross PCIe), uploads, matches chunk by chunk and copies the match lists back.
   roofline = the tcgen05 candidate kernel: 2*Q*T*128 FLOP per pair / its CUDA-event duration,
            against the measured cuBLAS bf16 peak in MEASURED_PEAKS.json.
   cpu_baseline = the same OpenCV calls the reference makes (cv2.BFMatcher.knnMatch + the
@@ -269,10 +268,13 @@ def run_b200(args, rank, world, local):
     # host cores this rank may use: the ranks of a node share them.  The library's pack pool is
     # sized before the first upload (every upload narrows integer-valued Mats on the host).
     cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    if args.e2e_uploaders > 0:
+        os.environ["SLAMB200_HOST_NARROWERS"] = str(args.e2e_uploaders)   # read once by the library, before its first host call
     if args.e2e_upload == "auto":
         args.e2e_upload = "packed"
-    pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else \
-        max(0, min(cores, 16) - args.e2e_workers)
+    # host threads of this rank that narrow Mats inside the library: its cores minus the submitter,
+    # the matching caller and one for the driver
+    pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else max(0, min(cores, 27) - 4)
     ctx.set_pack_threads(pack_threads)
     # A real (non-default) stream: the C ABI treats a NULL stream as "the lane's own stream", so
     # the kernels and the CUDA events that time them must share an explicit stream handle.
@@ -380,84 +382,23 @@ def run_b200(args, rank, world, local):
     e2e_steps = max(0, min(args.steps, args.e2e_steps))
     d2h = 0
 
-    # The reference walks the window from `threadsCount` host threads that share the query
-    # descriptor (batch.cpp:181-201); the C ABI is re-entrant the same way.
-    from concurrent.futures import ThreadPoolExecutor
+    # One call per step through the C ABI: slamb200_match_batch_host takes the query Mat and this
+    # rank's train Mats from (pageable) host memory, narrows them on the library's pack pool, queues
+    # the prep kernels, matches every chunk as soon as its last Mat is resident and copies the
+    # match lists back -- the call a search of the reference makes when it hands its descriptors
+    # over (batch.cpp:120-148); uploads never wait for a match and vice versa, and no Python runs
+    # between the Mats.
     from slam_indoor_code_b200._capi import DMATCH
-    n_workers, chunk = args.e2e_workers, args.e2e_chunk
-    chunks = [list(range(i, min(i + chunk, len(trains)))) for i in range(0, len(trains), chunk)]
     out_buf = np.empty((max(len(trains), 1), N_ROWS), DMATCH)      # caller-owned, reused per step
     n_buf = np.zeros(max(len(trains), 1), np.int32)
-    pool = ThreadPoolExecutor(n_workers)
-
-    up = ctx.upload_packed if args.e2e_upload == "packed" else ctx.upload_pinned
-    # bytes that cross PCIe per step: the fp32 Mats as they are, or their verified byte images
-    h2d = (len(trains) + 1) * N_ROWS * (128 if args.e2e_upload == "packed" else 512)
-
-    # Producer / consumer pipeline over the public API: `n_workers` uploader threads hand the train
-    # Mats to the library in window order (each call narrows / queues one Mat), `n_match` matcher
-    # threads take every chunk as soon as its last Mat is in, match it against the shared query set,
-    # copy its match lists back and free its sets.  Uploads never wait for a match and vice versa.
-    import itertools
-    n_match = max(1, args.e2e_matchers)
-    pool_m = ThreadPoolExecutor(n_match)
+    if args.e2e_upload != "packed":
+        log("--e2e-upload pinned is an upload experiment of the old Python pipeline; the e2e call narrows on the host")
+    # bytes that cross PCIe per step: the verified byte images of the fp32 Mats
+    h2d = (len(trains) + 1) * N_ROWS * 128
 
     def e2e_step():
         nonlocal d2h
-        Qe = up(q)
-        n = len(trains)
-        handles = [None] * n
-        left = [len(c) for c in chunks]
-        ready = [threading.Event() for _ in chunks]
-        lock = threading.Lock()
-        counter = itertools.count()
-        errors = []
-
-        def uploader():
-            try:
-                while True:
-                    i = next(counter)        # itertools.count is atomic under the GIL
-                    if i >= n:
-                        return
-                    handles[i] = up(trains[i])
-                    c = i // chunk
-                    with lock:
-                        left[c] -= 1
-                        last = left[c] == 0
-                    if last:
-                        ready[c].set()
-            except Exception as e:  # pragma: no cover
-                errors.append(e)
-                for ev in ready:
-                    ev.set()
-
-        def matcher(m):
-            out = []
-            for c in range(m, len(chunks), n_match):
-                ready[c].wait()
-                if errors:
-                    return out
-                ids = chunks[c]
-                Te = [handles[i] for i in ids]
-                r = ctx.matchBatch(Qe, Te, MatcherType.SIFT_BF, RATIO, out=out_buf[ids[0]: ids[-1] + 1],
-                                   n_out=n_buf[ids[0]: ids[-1] + 1])
-                for t in Te:
-                    t.free()
-                out.append((ids[0], r))
-            return out
-
-        ups = [pool.submit(uploader) for _ in range(n_workers)]
-        parts = []
-        for part in pool_m.map(matcher, range(n_match)):
-            parts.extend(part)
-        for u in ups:
-            u.result()
-        if errors:
-            raise errors[0]
-        Qe.free()
-        res = []
-        for _, r in sorted(parts, key=lambda x: x[0]):
-            res.extend(r)
+        res = ctx.matchBatchHost(q, trains, MatcherType.SIFT_BF, RATIO, out=out_buf, n_out=n_buf)
         d2h = len(res) * 4 + sum(len(r) for r in res) * 16
         return res
 
@@ -492,6 +433,45 @@ def run_b200(args, rank, world, local):
         dist.all_reduce(io, op=dist.ReduceOp.SUM)
     e2e_value = N_PAIRS * e2e_steps / float(te.item()) if e2e_steps else None
     same = all(np.array_equal(a, b) for a, b in zip(res, matches))
+    # What bounds e2e on this box: every step reads the rank's fp32 Mats (5.12 MB each, far beyond
+    # the CPU caches) out of host DRAM once to narrow them.  The same narrowing alone -- no GPU, no
+    # PCIe, the threads this rank may use -- gives the host-side floor of the step.
+    narrow = None
+    if e2e_steps and trains:
+        import ctypes
+        fn = ctx._lib.slamb200_host_pack_u8
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        nthr = max(1, min(cores, 16))
+        dst = [np.zeros((N_ROWS, 128), np.uint8) for _ in range(nthr)]
+
+        def nwork(t):
+            for f in range(t, len(trains), nthr):
+                fn(trains[f].ctypes.data, 128, N_ROWS, dst[t].ctypes.data)
+        best_n = 1e9
+        for _ in range(3):
+            barrier()
+            t0n = time.perf_counter()
+            th = [threading.Thread(target=nwork, args=(t,)) for t in range(nthr)]
+            [x.start() for x in th]
+            [x.join() for x in th]
+            best_n = min(best_n, time.perf_counter() - t0n)
+        tn = torch.tensor([best_n], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        narrow = {"ms_per_step_narrowing_alone": float(tn.item()) * 1e3, "threads_per_rank": nthr,
+                  "host_read_GB_per_s_all_ranks": N_PAIRS * N_ROWS * 512 / float(tn.item()) / 1e9,
+                  "pairs_per_s_floor": N_PAIRS / float(tn.item()),
+                  "note": "slamb200_host_pack_u8 over the same pageable Mats, no GPU work: the host-DRAM-bound "
+                          "floor of a step whose inputs are fp32 Mats in pageable memory"}
+
+    shared = None
+    if not args.no_extras:
+        try:
+            shared = multi_rank_extras(ctx, stream, rank, world, local, dev, pairs, q, trains, matches, barrier)
+        except Exception as e:  # pragma: no cover
+            shared = {"error": repr(e)}
+            log(f"[rank {rank}] multi-rank extras failed: {e!r}")
 
     if rank == 0:
         line = {
@@ -507,10 +487,12 @@ def run_b200(args, rank, world, local):
                     "warmup_steps_run": len(warm_t), "upload": args.e2e_upload,
                     "host_buffers": "page-locked" if args.e2e_upload == "pinned" else "pageable (numpy arrays)",
                     "host_mat_bytes_per_step": (N_PAIRS + world) * N_ROWS * 512,
-                    "host_threads": {"uploaders": args.e2e_workers, "matchers": args.e2e_matchers,
-                                     "pack_pool": pack_threads if args.e2e_upload == "packed" else 0},
+                    "call": "slamb200_match_batch_host (one C-ABI call per step: narrowing, uploads, matching and "
+                            "result copies pipelined inside the library)",
+                    "host_threads": {"narrowing": int(os.environ.get("SLAMB200_HOST_NARROWERS", pack_threads + 1)),
+                                     "submit": 1, "match_and_copy_out": 1},
                     "timing": "host wall clock between device synchronisations, max over ranks",
-                    "results_equal_device_resident_run": bool(same)},
+                    "results_equal_device_resident_run": bool(same), "host_floor": narrow},
             "gpu_launches": int(launches.item()),
             "roofline": roof,
             "checksum": {"good_matches_total": int(n_good.sum()), "pairs": int((n_good > 0).sum())},
@@ -522,6 +504,8 @@ def run_b200(args, rank, world, local):
                     line["cpu_baseline"]["other_configs"] = cpu_extras()
                 except Exception as e:  # pragma: no cover
                     line["cpu_baseline"]["other_configs"] = {"error": repr(e)}
+        if shared is not None:
+            line["window_extras"] = shared
         if world == 1 and not args.no_extras:
             try:
                 line["extras"] = extras(ctx, stream)
@@ -532,6 +516,175 @@ def run_b200(args, rank, world, local):
     if world > 1:
         dist.destroy_process_group()
 
+
+
+# ------------------------------------------------------------------------------------------------
+# Side measurements that every rank takes part in (N >= 1): BASELINE cfg3 as stated (matching +
+# RANSAC essential scoring over the rank's share of the window, keypoints consistent with the
+# planted correspondences), cfg4 (8 x 50k-row keyframe window) through both exchange forms with
+# a self-check against the single-GPU result, and the in-process device set on rank 0.
+def multi_rank_extras(ctx, stream, rank, world, local, dev, pairs, q, trains, matches, barrier):
+    import torch
+    import torch.distributed as dist
+    import synth_inputs as synth
+    from slam_indoor_code_b200 import camera_translation as ct
+    from slam_indoor_code_b200 import window_sharding as ws
+    from slam_indoor_code_b200.feature_matching import MatcherType
+    out = {}
+
+    def reduce_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_min(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
+    # ---- cfg3 chain: match -> device gather (getKeyPointCoordsFromFramePair) -> 2048 hypotheses ----
+    H = 2048
+    kq, kts_all, poses = synth.window_geometry(N_ROWS, N_ROWS, [3001 + p for p in range(N_PAIRS)], 3500)
+    kts = [kts_all[p] for p in pairs]
+    E = np.stack([synth.pose_hypotheses_fast(H, *poses[p], 3600 + p) for p in pairs]) if pairs else np.zeros((0, H, 9))
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(t) for t in trains]
+    KQ = ctx.upload_keypoints(kq)
+    KTs = [ctx.upload_keypoints(k) for k in kts]
+    Ed = torch.from_numpy(E).to(dev)
+
+    def chain():
+        ctx.matchBatchEnqueue(Q, Ts, MatcherType.SIFT_BF, RATIO, stream)
+        if pairs:
+            ct.scoreBatchEnqueue(ctx, KQ, KTs, synth.SAMSUNG_HV_4K, None, 5.0, stream, E_device_ptr=Ed.data_ptr(), H=H)
+
+    for _ in range(3):
+        chain()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        chain()
+    b.record()
+    barrier()
+    ms = reduce_max(a.elapsed_time(b) / 10)
+    ok = True
+    if pairs:
+        counts, best, mask = ct.batchScoresFetch(ctx, stream)
+        got, _ = ctx.batchFetch(stream)
+        ok = all(np.array_equal(g, m) for g, m in zip(got, matches))
+        # real geometry: the winning hypothesis explains the accepted matches
+        ok = ok and all(best[i] >= 0 and counts[i, best[i]] > 0.8 * len(got[i]) for i in range(len(pairs)))
+    out["cfg3_chain_match_gather_score"] = {
+        "ms_per_window": ms, "us_per_pair": ms * 1e3 / N_PAIRS * world if world else None,
+        "pairs_per_s": N_PAIRS / (ms / 1e3), "hypotheses_per_pair": H,
+        "note": "whole 210-pair window split over the ranks; us_per_pair is per-GPU time per pair; keypoints "
+                "consistent with the planted correspondences (synth_inputs.window_geometry)",
+        "matches_equal_and_winner_explains_80pct": bool(reduce_min(1.0 if ok else 0.0) > 0.5)}
+    for h in KTs + [KQ] + Ts + [Q]:
+        h.free()
+    del Ed
+
+    # ---- cfg4: 8 frames x 50,000 rows, all 28 pairs, frames owned round-robin by the ranks ----------
+    F, ROWS = 8, 50000
+    frames = {f: synth.sift_like(ROWS, 4000 + f) for f in range(F) if ws.frame_owner(f, world) == rank}
+    flop = 28 * 2.0 * ROWS * ROWS * 128
+    best_t = 1e9
+    out_a = counts_a = None
+    for it in range(4):
+        barrier()
+        t0 = time.perf_counter()
+        out_a, counts_a = ws.match_window_on_gpus(ctx, frames, F, MatcherType.SIFT_BF, RATIO, dist, dev) \
+            if world > 1 else _window_single(ctx, frames, F)
+        torch.cuda.synchronize()
+        dt = reduce_max(time.perf_counter() - t0)
+        if it >= 1:
+            best_t = min(best_t, dt)
+    res4 = {"n_gpus": world, "pairs": 28,
+            "nccl_allgather_rows" if world > 1 else "single_gpu_host_call": {"ms_per_window": best_t * 1e3, "tflops": flop / best_t / 1e12}}
+    if world > 1:
+        w = ws.PeerWindow(ctx, dist, dev)
+        barrier()
+        t0 = time.perf_counter()
+        w.publish(frames, F)
+        w.match(F, MatcherType.SIFT_BF, RATIO)
+        torch.cuda.synchronize()
+        first = reduce_max(time.perf_counter() - t0)
+        best_p = 1e9
+        out_b = None
+        for it in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            out_b, _ = w.match(F, MatcherType.SIFT_BF, RATIO, gather_counts=False)
+            torch.cuda.synchronize()
+            best_p = min(best_p, reduce_max(time.perf_counter() - t0))
+        same = all(np.array_equal(out_b[p], out_a[p]) for p in out_a)
+        res4["ipc_peer_operands_over_nvlink"] = {"ms_per_window_steady": best_p * 1e3,
+                                                 "first_window_incl_publish_ms": first * 1e3,
+                                                 "tflops": flop / best_p / 1e12,
+                                                 "equal_to_nccl_form": bool(reduce_min(1.0 if same else 0.0) > 0.5)}
+        w.close()
+        # self-check against the single-process window on rank 0's GPU (every frame regenerated there)
+        check = 1.0
+        if rank == 0:
+            allf = [ctx.upload(synth.sift_like(ROWS, 4000 + f)) for f in range(F)]
+            ref = ctx.matchWindow(allf, MatcherType.SIFT_BF, RATIO)
+            check = 1.0 if counts_a == [len(ref[p]) for p in ws.window_pairs(F)] and \
+                all(np.array_equal(out_a[p], ref[p]) for p in out_a) else 0.0
+            for f in allf:
+                f.free()
+        res4["sharded_equals_single_gpu_window"] = bool(reduce_min(check) > 0.5)
+        res4["ranks_that_ran"] = world
+    out["cfg4_window_8x50k"] = res4
+
+    # ---- one process, all GPUs: the device set (rank 0 drives every GPU, the other ranks wait) -------
+    barrier()
+    if rank == 0:
+        try:
+            from slam_indoor_code_b200.device_set import DeviceSet
+            import synth_inputs as synth2
+            n_dev = max(1, min(world, torch.cuda.device_count()))
+            with DeviceSet(n_dev) as ds:
+                full_q = q
+                full_trains = [synth2.sift_train_from_query(full_q, N_ROWS, 3001 + p) for p in range(N_PAIRS)] \
+                    if world > 1 else trains
+                Qs = ds.upload(full_q)
+                Tss = [ds.upload(t, ds.owner(i, N_PAIRS)) for i, t in enumerate(full_trains)]
+                for _ in range(3):
+                    ds.matchBatchEnqueue(Qs, Tss, MatcherType.SIFT_BF, RATIO)
+                    got, n_out, dms = ds.batchFetch()
+                best_dev, best_host = 1e9, 1e9
+                for _ in range(8):
+                    t0 = time.perf_counter()
+                    ds.matchBatchEnqueue(Qs, Tss, MatcherType.SIFT_BF, RATIO)
+                    got, n_out, dms = ds.batchFetch()
+                    best_host = min(best_host, time.perf_counter() - t0)
+                    best_dev = min(best_dev, float(dms.max()))
+                out["inprocess_device_set"] = {
+                    "devices": n_dev, "pairs_per_s_device_time_max_over_devices": N_PAIRS / (best_dev / 1e3),
+                    "ms_per_window_device": best_dev,
+                    "pairs_per_s_host_call_incl_result_copies": N_PAIRS / best_host,
+                    "ms_per_window_host_call": best_host * 1e3,
+                    "good_matches_total": int(n_out.sum()),
+                    "note": "slamb200_set_*: one process drives every GPU (query replicated by peer copies of the "
+                            "prepared set, trains resident on their owners, one enqueue per device, results gathered once)"}
+                for h in Tss + [Qs]:
+                    h.free()
+        except Exception as e:  # pragma: no cover
+            out["inprocess_device_set"] = {"error": repr(e)}
+    barrier()
+    return out
+
+
+def _window_single(ctx, frames, F):
+    from slam_indoor_code_b200.feature_matching import MatcherType
+    sets = [ctx.upload(frames[f]) for f in range(F)]
+    res = ctx.matchWindow(sets, MatcherType.SIFT_BF, RATIO)
+    for s_ in sets:
+        s_.free()
+    return res, [len(res[p]) for p in sorted(res)]
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one tcgen05-kernel launch over the 210-pair window
 # (N=1), from the committed `ncu --set full` capture profiles/r01_ncu_sift_tc_final.txt:
@@ -633,29 +786,6 @@ def extras(ctx, stream):
     out["cfg5_ransac_2048x5000"] = {"kernel_us_per_pair": kms / kn / P * 1e3,
                                     "fp64_tflops_40flop_convention": P * 2048 * 5000 * 40 / (kms / kn) / 1e9,
                                     "dp_instr_per_s_T": P * 2048 * 5000 * 36 / (kms / kn) / 1e9}
-    # cfg3's full chain on 32 pairs: match the batch, gather the matched keypoints on the device
-    # (getKeyPointCoordsFromFramePair) and score 2048 essential hypotheses per pair against that pair's
-    # accepted matches (~3000 per pair) -- enqueue only, nothing leaves the device in between
-    qc = synth.sift_like(N_ROWS, 3000)
-    Qc = ctx.upload(qc)
-    Tc = [ctx.upload(synth.sift_train_from_query(qc, N_ROWS, 3001 + i)) for i in range(32)]
-    rng = np.random.default_rng(3100)
-    KQ = ctx.upload_keypoints(rng.uniform(0, 3840, (N_ROWS, 2)).astype(np.float32))
-    KT = ctx.upload_keypoints(rng.uniform(0, 3840, (N_ROWS, 2)).astype(np.float32))
-    Ed = torch.from_numpy(np.stack([E] * 32)).to("cuda")
-
-    def chain():
-        ctx.matchBatchEnqueue(Qc, Tc, MatcherType.SIFT_BF, RATIO, stream)
-        ct.scoreBatchEnqueue(ctx, KQ, [KT] * 32, synth.SAMSUNG_HV_4K, None, 5.0, stream,
-                             E_device_ptr=Ed.data_ptr(), H=2048)
-    ms_match = ev_time(lambda: ctx.matchBatchEnqueue(Qc, Tc, MatcherType.SIFT_BF, RATIO, stream), 10)
-    ms_chain = ev_time(chain, 10)
-    out["cfg3_chain_32_pairs"] = {"match_us_per_pair": ms_match / 32 * 1e3,
-                                  "match_gather_score_us_per_pair": ms_chain / 32 * 1e3,
-                                  "hypotheses_per_pair": 2048,
-                                  "note": "random keypoint coordinates: the timing is real, the inlier counts are not meaningful"}
-    for h in Tc + [Qc, KQ, KT]:
-        h.free()
     # next row 8f-2: solvePnPRansac scoring, 2048 poses x 5000 correspondences, 32 frames per launch,
     # the reference's five distortion coefficients
     from slam_indoor_code_b200 import pnp_ransac as pr
@@ -730,28 +860,6 @@ def extras(ctx, stream):
             out["f2_pnp_2048x5000"]["fp64_ops_T_per_s"] * 1e3 / fp64
     except Exception as e:  # pragma: no cover
         out["pipe_rates"] = {"error": str(e)}
-    # cfg4: 8 frames x 50,000 descriptors (4K frames), all 28 i<j pairs of the BA window
-    frames = [ctx.upload(synth.sift_like(50000, 4000 + f)) for f in range(8)]
-    # the synchronous calls rotate over the context's lanes, each of which sizes its own scratch
-    # on first use: warm up until two consecutive windows agree, then take the best of three
-    prev = None
-    for _ in range(12):
-        t0 = time.perf_counter()
-        ctx.matchWindow(frames, MatcherType.SIFT_BF, RATIO)
-        cur = time.perf_counter() - t0
-        if prev is not None and abs(cur - prev) < 0.1 * prev:
-            break
-        prev = cur
-    dt = None
-    for _ in range(3):
-        t0 = time.perf_counter()
-        res = ctx.matchWindow(frames, MatcherType.SIFT_BF, RATIO)
-        cur = time.perf_counter() - t0
-        dt = cur if dt is None else min(dt, cur)
-    out["cfg4_window_8x50k"] = {"ms_per_window_host_call": dt * 1e3, "pairs": len(res),
-                                "tflops_incl_copies": len(res) * 2 * 50000.0 * 50000 * 128 / dt / 1e12}
-    for f in frames:
-        f.free()
     return out
 
 
@@ -833,14 +941,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--e2e-workers", type=int, default=4, help="uploader threads of the e2e pipeline")
-    ap.add_argument("--e2e-matchers", type=int, default=2, help="matcher threads of the e2e pipeline")
-    ap.add_argument("--e2e-chunk", type=int, default=14, help="train frames per e2e chunk")
+    ap.add_argument("--e2e-uploaders", type=int, default=-1,
+                    help="narrowing threads inside slamb200_match_batch_host (-1: pack threads + 1)")
     ap.add_argument("--e2e-pack-threads", type=int, default=-1,
                     help="library threads sharing the narrowing of each Mat (-1: min(cores, 16) - uploaders)")
     ap.add_argument("--e2e-upload", default="auto", choices=["auto", "packed", "pinned"],
-                    help="packed: rows narrowed to bytes on the host threads (verified lossless) before "
-                         "PCIe; pinned: the fp32 Mats read over PCIe as they are")
+                    help="packed (default): pageable host Mats, rows narrowed to bytes on the host threads (verified "
+                         "lossless) before PCIe; pinned: allocates the Mats page-locked (experiment)")
     ap.add_argument("--ref-pairs", type=int, default=8, help="pairs per step of the CPU arm (a bounded sample "
                     "of the 210-pair window: ~1 s per step on 16 cores)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -160,6 +160,17 @@ int slamb200_match_batch(slamb200_ctx* ctx, int matcher, const slamb200_desc* qu
                          const slamb200_desc* const* trains, int n_pairs, double ratio,
                          slamb200_dmatch* out, int cap, int* n_out);
 
+/* The same window from HOST descriptor Mats that are not resident yet, in one call: query rows
+ * (nq x row type, q_stride bytes apart) and n_pairs train Mats (t_rows[p], t_n[p] rows, t_stride[p]
+ * bytes apart; t_stride may be NULL = dense).  Uploads and matching overlap inside the library
+ * (host-side narrowing on the pack pool, chunks matched as their last Mat arrives); nothing stays
+ * resident afterwards.  Results as slamb200_match_batch.  This is the end-to-end call of a search
+ * whose descriptors live in host memory (bench.py `e2e`). */
+int slamb200_match_batch_host(slamb200_ctx* ctx, int matcher, const void* q_rows, int nq,
+                              size_t q_stride, const void* const* t_rows, const int* t_n,
+                              const size_t* t_stride, int n_pairs, double ratio, slamb200_dmatch* out,
+                              int cap, int* n_out);
+
 /* All i<j pairs of a frame window (BAMaxFramesCnt window, config 4): pair order is
  * (0,1),(0,2)...(0,n-1),(1,2)...; frame i is the query, frame j the train. */
 int slamb200_match_window(slamb200_ctx* ctx, int matcher, const slamb200_desc* const* frames,

@@ -40,6 +40,7 @@ SYMBOLS = {
     "slamb200_knn2": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "slamb200_match_pair": (_i, [_vp, _i, _vp, _vp, _d, _vp, _i, _vp]),
     "slamb200_match_batch": (_i, [_vp, _i, _vp, _vp, _i, _d, _vp, _i, _vp]),
+    "slamb200_match_batch_host": (_i, [_vp, _i, _vp, _i, _sz, _vp, _vp, _vp, _i, _d, _vp, _i, _vp]),
     "slamb200_match_window": (_i, [_vp, _i, _vp, _i, _d, _vp, _i, _vp]),
     "slamb200_match_batch_enqueue": (_i, [_vp, _i, _vp, _vp, _i, _d, _vp]),
     "slamb200_batch_fetch": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -36,6 +36,7 @@ static int fail(int code, const char* fmt, ...) {
 // last-error text for the other translation units of the library (device_set.cu)
 int set_error(int code, const char* msg) { return fail(code, "%s", msg); }
 
+
 #define CU(call)                                                                       \
   do {                                                                                 \
     cudaError_t e__ = (call);                                                          \
@@ -300,6 +301,20 @@ extern "C" int slamb200_init(int device, slamb200_ctx** out) {
   return SLAMB200_OK;
 }
 
+int ctx_device(const slamb200_ctx* c) { return c->device; }
+int ctx_grant_peer_access(slamb200_ctx* c, int peer_device) {
+  cudaMemAccessDesc acc;
+  memset(&acc, 0, sizeof(acc));
+  acc.location.type = cudaMemLocationTypeDevice;
+  acc.location.id = peer_device;
+  acc.flags = cudaMemAccessFlagsProtReadWrite;
+  if (cudaMemPoolSetAccess(c->pool, &acc, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return SLAMB200_ERR_CUDA;
+  }
+  return SLAMB200_OK;
+}
+
 extern "C" int slamb200_synchronize(slamb200_ctx* c) {
   if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
   CU(cudaSetDevice(c->device));
@@ -498,6 +513,7 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
   d->n = n;
   d->n_pad = round_up(n > 0 ? n : 1, SLAMB200_TILE_PAD);
   d->host_exact = -2;
+  d->device = c->device;
   LaneGuard g(c, /*upload=*/true);
   Lane& L = g.lane();
   cudaStream_t s = L.stream;
@@ -655,7 +671,7 @@ extern "C" int slamb200_upload_desc_packed(slamb200_ctx* c, int kind, const void
     int nthr = c->pack_threads;
     if (nthr < 0) {
       nthr = (int)std::thread::hardware_concurrency();
-      nthr = nthr > 16 ? 16 : nthr;
+      nthr = nthr > 24 ? 24 : nthr;
     }
     c->pack_pool.start(nthr > 0 ? nthr : 0);
     c->pack_started = true;
@@ -748,6 +764,7 @@ extern "C" int slamb200_desc_import(slamb200_ctx* c, const slamb200_desc_ipc* in
   d->n_pad = in->n_pad;
   d->slab_bytes = want;
   d->imported = 1;
+  d->device = in->device;
   d->host_exact = in->kind == SLAMB200_DESC_F32X128 ? (in->exact == 1 ? 1 : 0) : -2;
   d->ready_seen = 1;   // the exporter synchronised on its prep kernels
   cudaIpcMemHandle_t h;
@@ -786,6 +803,7 @@ extern "C" int slamb200_desc_localize(slamb200_ctx* c, const slamb200_desc* src,
   memcpy(d, src, sizeof(slamb200_desc));
   d->imported = 0;
   d->shared = 0;
+  d->device = c->device;
   d->slab = nullptr;
   d->ready = nullptr;
   d->ready_seen = 0;
@@ -797,8 +815,14 @@ extern "C" int slamb200_desc_localize(slamb200_ctx* c, const slamb200_desc* src,
     if (!(d->slab = slab_from_cache(c, d->slab_bytes, s))) rc = dev_alloc(c, &d->slab, d->slab_bytes, s);
     if (rc == SLAMB200_OK) {
       if (!src->ready_seen && cudaStreamWaitEvent(s, src->ready, 0) != cudaSuccess) rc = SLAMB200_ERR_CUDA;
-      if (cudaMemcpyAsync(d->slab, src->slab, d->slab_bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
-        rc = fail(SLAMB200_ERR_CUDA, "desc_localize: peer copy failed");
+      // a set of another device of THIS process (device set) travels by a peer copy -- direct over
+      // NVLink when the owner's pool grants this device access (ctx_grant_peer_access), staged by
+      // the driver otherwise; a mapping of another process's set (CUDA IPC) is an ordinary
+      // device pointer here
+      cudaError_t ce = (!src->imported && src->device != c->device)
+                           ? cudaMemcpyPeerAsync(d->slab, c->device, src->slab, src->device, d->slab_bytes, s)
+                           : cudaMemcpyAsync(d->slab, src->slab, d->slab_bytes, cudaMemcpyDeviceToDevice, s);
+      if (ce != cudaSuccess) rc = fail(SLAMB200_ERR_CUDA, "desc_localize: peer copy failed: %s", cudaGetErrorString(ce));
       {
         std::lock_guard<std::mutex> lk(c->free_mu);
         d->ready = event_get(c);
@@ -1384,6 +1408,139 @@ extern "C" int slamb200_match_window(slamb200_ctx* c, int matcher,
     if (rc) return rc;
     pair0 += np;
   }
+  return SLAMB200_OK;
+}
+
+// ---- the whole window from HOST Mats in one call ------------------------------------------------
+// What a search of the reference does with its descriptors (batch.cpp:120-148, :181-201: one
+// previous-frame descriptor against every batch element) when none of them is resident yet.  A
+// three-stage pipeline inside the library:
+//   narrow  : `SLAMB200_HOST_NARROWERS` threads (default: hardware threads - 3, at most 24) take
+//             train Mats in window order and narrow whole Mats to bytes into page-locked staging
+//             (no CUDA submission from these threads: they only stream host memory);
+//   submit  : ONE thread queues the prep kernel of every narrowed Mat (the driver serialises
+//             submissions anyway: a dozen threads in the driver contend for its lock);
+//   match   : the calling thread matches every chunk of `SLAMB200_HOST_CHUNK` (14) pairs as soon
+//             as its last Mat is in, and copies its match lists out.
+// The step is bound by the narrowing, i.e. by reading the fp32 Mats out of host DRAM once.  Same
+// results as uploading everything and calling slamb200_match_batch.
+extern "C" int slamb200_match_batch_host(slamb200_ctx* c, int matcher, const void* q_rows, int nq,
+                                         size_t q_stride, const void* const* t_rows, const int* t_n,
+                                         const size_t* t_stride, int n_pairs, double ratio,
+                                         slamb200_dmatch* out, int cap, int* n_out) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  if (n_pairs < 0 || nq < 0) return fail(SLAMB200_ERR_INVALID, "negative size");
+  if (matcher != SLAMB200_SIFT_BF && matcher != SLAMB200_SIFT_FLANN && matcher != SLAMB200_ORB_BF &&
+      matcher != SLAMB200_SIFT_BF_L1)
+    return fail(SLAMB200_ERR_MATCHER, "matcher type %d is not 0 (SIFT_BF), 1 (SIFT_FLANN), 2 (ORB_BF) or 3 (SIFT_BF_L1)", matcher);
+  if (n_pairs > 0 && (!t_rows || !t_n || !n_out)) return fail(SLAMB200_ERR_INVALID, "NULL argument");
+  if (nq > 0 && n_pairs > 0 && (!out || cap < nq)) return fail(SLAMB200_ERR_INVALID, "out is NULL or cap < query rows");
+  const int kind = matcher == SLAMB200_ORB_BF ? SLAMB200_DESC_U8X32 : SLAMB200_DESC_F32X128;
+  static const int narrow_env = [] { const char* e = getenv("SLAMB200_HOST_NARROWERS"); return e ? atoi(e) : 0; }();
+  static const int chunk_env = [] { const char* e = getenv("SLAMB200_HOST_CHUNK"); return e ? atoi(e) : 14; }();
+  const int chunk = chunk_env > 0 ? chunk_env : 14;
+  const int n_chunks = (n_pairs + chunk - 1) / chunk;
+  CU(cudaSetDevice(c->device));
+  slamb200_desc* qd = nullptr;
+  int rc = slamb200_upload_desc_packed(c, kind, q_rows, nq, q_stride, &qd);
+  if (rc != SLAMB200_OK) return rc;
+  std::vector<slamb200_desc*> td((size_t)n_pairs, nullptr);
+  std::vector<int> left((size_t)(n_chunks > 0 ? n_chunks : 1));
+  for (int k = 0; k < n_chunks; k++) left[(size_t)k] = (k + 1) * chunk <= n_pairs ? chunk : n_pairs - k * chunk;
+  struct Job { int i; slamb200_ctx::PinBuf* b; };
+  std::mutex mu;
+  std::condition_variable cv_jobs, cv_chunks;
+  std::deque<Job> jobs;
+  std::atomic<int> next(0);
+  int first_err = SLAMB200_OK;
+  char err_text[512] = "";
+  auto stride_of = [&](int i) -> size_t {
+    const size_t st = t_stride ? t_stride[i] : 0;
+    return st ? st : (kind == SLAMB200_DESC_F32X128 ? 512 : 32);
+  };
+  auto narrower = [&] {
+    cudaSetDevice(c->device);
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n_pairs) return;
+      slamb200_ctx::PinBuf* b = nullptr;
+      const size_t st = stride_of(i);
+      if (kind == SLAMB200_DESC_F32X128 && t_n[i] > 0 && t_rows[i] && st >= 512 && st % 4 == 0) {
+        b = pin_acquire(c, (size_t)t_n[i] * 128);
+        if (b && !slamb200_host_pack_u8((const float*)t_rows[i], st / 4, t_n[i], (uint8_t*)b->p)) {
+          pin_release(c, b, nullptr);   // not integer valued: the fp32 path
+          b = nullptr;
+        }
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        jobs.push_back({i, b});
+      }
+      cv_jobs.notify_one();
+    }
+  };
+  auto submitter = [&] {
+    cudaSetDevice(c->device);
+    for (int done = 0; done < n_pairs; done++) {
+      Job j;
+      int err;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_jobs.wait(lk, [&] { return !jobs.empty(); });
+        j = jobs.front();
+        jobs.pop_front();
+        err = first_err;
+      }
+      int r = err;
+      if (err == SLAMB200_OK) {
+        r = j.b ? desc_create(c, kind, t_rows[j.i], t_n[j.i], stride_of(j.i), false, nullptr, true, &td[(size_t)j.i], j.b)
+                : desc_create(c, kind, t_rows[j.i], t_n[j.i], t_stride ? t_stride[j.i] : 0, false, nullptr, false,
+                              &td[(size_t)j.i]);
+        if (r != SLAMB200_OK && j.b) cudaDeviceSynchronize();   // a prep kernel may still be reading the staging
+      }
+      if (j.b) pin_release(c, j.b, nullptr);   // desc_create recorded its event behind the prep kernel
+      std::lock_guard<std::mutex> lk(mu);
+      if (r != SLAMB200_OK && first_err == SLAMB200_OK) {
+        first_err = r;
+        snprintf(err_text, sizeof(err_text), "%s", g_err);
+      }
+      if (--left[(size_t)(j.i / chunk)] == 0) cv_chunks.notify_all();
+    }
+  };
+  int n_narrow = narrow_env > 0 ? narrow_env : (int)std::thread::hardware_concurrency() - 3;
+  if (c->pack_threads >= 0) n_narrow = c->pack_threads + 1;   // the caller sized the host side (slamb200_set_pack_threads)
+  n_narrow = n_narrow > 24 ? 24 : (n_narrow < 1 ? 1 : n_narrow);
+  if (n_narrow > n_pairs) n_narrow = n_pairs;
+  std::vector<std::thread> th;
+  for (int k = 0; k < n_narrow; k++) th.emplace_back(narrower);
+  if (n_pairs > 0) th.emplace_back(submitter);
+  for (int k = 0; k < n_chunks; k++) {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_chunks.wait(lk, [&] { return left[(size_t)k] == 0; });
+      if (first_err != SLAMB200_OK) break;
+    }
+    const int p0 = k * chunk, np = (k + 1) * chunk <= n_pairs ? chunk : n_pairs - p0;
+    const int r = slamb200_match_batch(c, matcher, qd, td.data() + p0, np, ratio,
+                                       out ? out + (size_t)p0 * cap : nullptr, cap, n_out + p0);
+    if (r != SLAMB200_OK) {
+      std::lock_guard<std::mutex> lk(mu);
+      if (first_err == SLAMB200_OK) {
+        first_err = r;
+        snprintf(err_text, sizeof(err_text), "%s", g_err);
+      }
+      break;
+    }
+    for (int p = p0; p < p0 + np; p++) {
+      slamb200_free_desc(c, td[(size_t)p]);
+      td[(size_t)p] = nullptr;
+    }
+  }
+  for (auto& t : th) t.join();
+  for (slamb200_desc* d : td)
+    if (d) slamb200_free_desc(c, d);
+  slamb200_free_desc(c, qd);
+  if (first_err != SLAMB200_OK) return fail(first_err, "%s", err_text);
   return SLAMB200_OK;
 }
 

@@ -41,6 +41,7 @@ struct slamb200_desc {
   cudaEvent_t ready;   // recorded after the prep kernels
   void* slab;          // the one device allocation all the pointers above live in
   size_t slab_bytes;
+  int device;          // CUDA device the slab lives on
   int shared;          // 1: the slab is a plain cudaMalloc allocation (exportable over CUDA IPC)
   int imported;        // 1: the slab is another process's allocation mapped here (peer memory)
   alignas(64) unsigned char tmaps[512];  // host copies of 4 CUtensorMaps: main, augq, augt, lo
@@ -88,6 +89,28 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+#endif
+
+// One-time setup that CUDA keeps PER DEVICE (function attributes, __device__ / __constant__
+// symbols): a process may hold contexts on several devices (device_set.cu), so "done once" is
+// tracked for each of them.  run(f) executes f (returning true on success) the first time it is
+// called with the current device; concurrent callers wait for that first setup to finish.
+#ifdef __CUDACC__
+#include <mutex>
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[64] = {};
+  template <class F>
+  bool run(F f) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return false;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[d]) return true;
+    if (!f()) return false;
+    done[d] = true;
+    return true;
+  }
+};
 #endif
 
 // ---- kernel launchers (each in its own .cu) ------------------------------------------------
@@ -229,5 +252,8 @@ void launch_orb_tc_prep(const uint8_t* u8, int n, int n_pad, uint8_t* e4, uint8_
                         uint8_t* augt, cudaStream_t s);
 
 void count_launch();
-int set_error(int code, const char* msg);   // fills slamb200_last_error() of the calling thread
+int set_error(int code, const char* msg);
+// lets `peer_device` read the context's stream-ordered allocations (descriptor slabs) directly
+int ctx_grant_peer_access(slamb200_ctx* c, int peer_device);
+int ctx_device(const slamb200_ctx* c);   // fills slamb200_last_error() of the calling thread
 #define COUNT_LAUNCH() count_launch()

@@ -70,6 +70,8 @@ extern "C" int slamb200_set_init(int n_devices, slamb200_set** out) {
       if (k != i && cudaDeviceCanAccessPeer(&can, i, k) == cudaSuccess && can) {
         cudaError_t e = cudaDeviceEnablePeerAccess(k, 0);
         if (e != cudaSuccess) cudaGetLastError();   // already enabled (by the host application)
+        // descriptor slabs are stream-ordered pool allocations: device i may read member k's pool
+        ctx_grant_peer_access(s->ctx[k], i);
       }
     }
   }

@@ -106,11 +106,8 @@ static void orb_gauss7(Gauss7& g) {
 }
 
 int orb_pattern_upload() {
-  static bool done = false;
-  if (done) return 0;
-  if (cudaMemcpyToSymbol(g_orb_pattern, kOrbPattern, sizeof(kOrbPattern)) != cudaSuccess) return -1;
-  done = true;
-  return 0;
+  static PerDeviceOnce once;   // a __device__ symbol has one instance per device
+  return once.run([] { return cudaMemcpyToSymbol(g_orb_pattern, kOrbPattern, sizeof(kOrbPattern)) == cudaSuccess; }) ? 0 : -1;
 }
 
 // cvtColor(BGR2GRAY) alone (the FAST detector works on the gray frame)

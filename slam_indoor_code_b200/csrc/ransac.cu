@@ -202,7 +202,10 @@ __device__ __forceinline__ void pair_range(const int32_t* m_off, const int32_t* 
   cnt = m_cnt ? m_cnt[pair] : (m_off[pair + 1] - m_off[pair]);
 }
 
-template <class S>
+// HPT hypotheses per thread (h, h + RS_THREADS, ...): every match read from shared memory feeds HPT
+// independent dependency chains (more instruction-level parallelism on the FP64 pipe, fewer
+// shared-memory reads per scored pair).
+template <class S, int HPT>
 __global__ void __launch_bounds__(RS_THREADS)
 score_counts_kernel(const double4* __restrict__ npts, const int32_t* __restrict__ m_off,
                     const int32_t* __restrict__ m_cnt, int m_stride,
@@ -212,14 +215,17 @@ score_counts_kernel(const double4* __restrict__ npts, const int32_t* __restrict_
   const int pair = blockIdx.z;
   size_t base; int M;
   pair_range(m_off, m_cnt, m_stride, pair, base, M);
-  const int h = blockIdx.x * RS_THREADS + threadIdx.x;
-  double Eh[S::ND];
-  {
-    const double* src = E + ((size_t)pair * H + min(h, H - 1)) * S::ND;
+  const int h0 = blockIdx.x * RS_THREADS * HPT + threadIdx.x;
+  double Eh[HPT][S::ND];
 #pragma unroll
-    for (int k = 0; k < S::ND; k++) Eh[k] = src[k];
+  for (int v = 0; v < HPT; v++) {
+    const double* src = E + ((size_t)pair * H + min(h0 + v * RS_THREADS, H - 1)) * S::ND;
+#pragma unroll
+    for (int k = 0; k < S::ND; k++) Eh[v][k] = src[k];
   }
-  int cnt = 0;
+  int cnt[HPT];
+#pragma unroll
+  for (int v = 0; v < HPT; v++) cnt[v] = 0;
   // this block's slice of the matches: chunks blockIdx.y, blockIdx.y + gridDim.y, ...
   for (int c0 = blockIdx.y * RS_PTS; c0 < M; c0 += gridDim.y * RS_PTS) {
     const int n = min(RS_PTS, M - c0);
@@ -227,26 +233,46 @@ score_counts_kernel(const double4* __restrict__ npts, const int32_t* __restrict_
     for (int i = threadIdx.x; i < n; i += RS_THREADS) pts[i] = npts[base + c0 + i];
     __syncthreads();
     if (S::HAS_CLASSIFY) {
-      // four matches at a time, branch-free; the rare boundary cases are redone exactly afterwards
+      // U matches x HPT hypotheses at a time, branch-free; the rare boundary cases are redone
+      // exactly afterwards
+      constexpr int U = HPT > 1 ? 2 : 4;
       int i = 0;
-      for (; i + 4 <= n; i += 4) {
-        int c[4];
+      for (; i + U <= n; i += U) {
+        int c[U][HPT];
+        int any = 0;
 #pragma unroll
-        for (int u = 0; u < 4; u++) c[u] = S::classify(Eh, pts[i + u], sp);
-        cnt += (c[0] == 1) + (c[1] == 1) + (c[2] == 1) + (c[3] == 1);
-        if (((c[0] | c[1] | c[2] | c[3]) & 2) != 0) {
-#pragma unroll 1
-          for (int u = 0; u < 4; u++)
-            if (c[u] == 2) cnt += S::inlier(Eh, pts[i + u], sp);
+        for (int u = 0; u < U; u++) {
+          const double4 p = pts[i + u];
+#pragma unroll
+          for (int v = 0; v < HPT; v++) {
+            c[u][v] = S::classify(Eh[v], p, sp);
+            cnt[v] += c[u][v] & 1;
+            any |= c[u][v];
+          }
+        }
+        if ((any & 2) != 0) {
+#pragma unroll
+          for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int v = 0; v < HPT; v++)
+              if (c[u][v] == 2) cnt[v] += S::inlier(Eh[v], pts[i + u], sp);
         }
       }
-      for (; i < n; i++) cnt += S::inlier(Eh, pts[i], sp);
+      for (; i < n; i++)
+#pragma unroll
+        for (int v = 0; v < HPT; v++) cnt[v] += S::inlier(Eh[v], pts[i], sp);
     } else {
 #pragma unroll 2
-      for (int i = 0; i < n; i++) cnt += S::inlier(Eh, pts[i], sp);
+      for (int i = 0; i < n; i++)
+#pragma unroll
+        for (int v = 0; v < HPT; v++) cnt[v] += S::inlier(Eh[v], pts[i], sp);
     }
   }
-  if (h < H && cnt) atomicAdd(&counts[(size_t)pair * H + h], cnt);
+#pragma unroll
+  for (int v = 0; v < HPT; v++) {
+    const int h = h0 + v * RS_THREADS;
+    if (h < H && cnt[v]) atomicAdd(&counts[(size_t)pair * H + h], cnt[v]);
+  }
 }
 
 // RANSACPointSetRegistrator::run's update rule over a fixed list: first index with the maximum
@@ -329,12 +355,15 @@ static void score_counts_t(const double4* npts, const int32_t* m_off, const int3
                            const typename S::Params& sp, int32_t* counts, cudaStream_t s) {
   if (P <= 0 || H <= 0) return;
   cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)P * H, s);
-  const int hb = (H + RS_THREADS - 1) / RS_THREADS;
+  // two hypotheses per thread once there are enough of them to fill the blocks that way
+  const int hpt = (S::HAS_CLASSIFY && H >= 2 * RS_THREADS) ? 2 : 1;
+  const int hb = (H + RS_THREADS * hpt - 1) / (RS_THREADS * hpt);
   // enough match-splits to fill the machine for a few waves when P*hb alone cannot
   int ms = (148 * 8 + hb * P - 1) / (hb * P);
   ms = max(1, min(ms, 16));
   dim3 grid(hb, ms, P);
-  score_counts_kernel<S><<<grid, RS_THREADS, 0, s>>>(npts, m_off, m_cnt, m_stride, E, H, sp, counts);
+  if (hpt == 2) score_counts_kernel<S, 2><<<grid, RS_THREADS, 0, s>>>(npts, m_off, m_cnt, m_stride, E, H, sp, counts);
+  else score_counts_kernel<S, 1><<<grid, RS_THREADS, 0, s>>>(npts, m_off, m_cnt, m_stride, E, H, sp, counts);
   COUNT_LAUNCH();
 }
 

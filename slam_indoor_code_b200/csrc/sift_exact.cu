@@ -186,12 +186,11 @@ void launch_sift_exact_knn2(const float* q, const int32_t* q_flags, int nq, cons
                             cudaStream_t s) {
   if (nq <= 0 || n_pairs <= 0) return;
   const size_t smem = (size_t)(SE_QT + SE_TT) * SE_PITCH * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(sift_exact_knn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(sift_exact_knn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_once;   // per-device attribute
+  attr_once.run([smem] {
+    return cudaFuncSetAttribute(sift_exact_knn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+           cudaFuncSetAttribute(sift_exact_knn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+  });
   const long long n_items = (long long)((nq + SE_QT - 1) / SE_QT) * n_split * n_pairs;
   const int grid = (int)(n_items < 148 * 8 ? n_items : 148 * 8);
   if (norm_l1)

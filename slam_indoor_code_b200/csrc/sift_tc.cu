@@ -1779,21 +1779,20 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_fl
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
                               int32_t* err_flag, float* dbg, int gen, cudaStream_t s, int fp8,
                               int kinds_known, int wide) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(sift_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(sift_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(sift_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(sift_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SMEM_BYTES_G) != cudaSuccess ||
-        cudaFuncSetAttribute(sift_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SMEM_BYTES_G) != cudaSuccess)
-      return -1;
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_once;   // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute
+  if (!attr_once.run([] {
+        return cudaFuncSetAttribute(sift_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(sift_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(sift_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(sift_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM_BYTES_G) == cudaSuccess &&
+               cudaFuncSetAttribute(sift_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM_BYTES_G) == cudaSuccess;
+      }))
+    return -1;
   if (total_tiles <= 0 || nq <= 0) return 0;
   const int n_rb = (nq + 2 * BM - 1) / (2 * BM);
   TcParams P;

@@ -219,6 +219,35 @@ class Context:
                                              ptr(n_out)))
         return [out[p, : n_out[p]].copy() if own else out[p, : n_out[p]] for p in range(P)]
 
+    def matchBatchHost(self, prevDesc, trainDescs, matcherType, knnMatcherDistance=0.7, out=None, n_out=None):
+        """The batch window from HOST descriptor Mats (numpy arrays, pageable is fine) in one call:
+        uploads and matching overlap inside the library, nothing stays resident.  List of
+        good-match arrays (views into `out` when the caller owns it)."""
+        kind = _kind_of(matcherType)
+        width, want = (128, np.float32) if kind == _capi.DESC_F32X128 else (32, np.uint8)
+
+        def mat(a):
+            a = np.asarray(a)
+            if a.dtype != want or a.ndim != 2 or a.shape[1] != width:
+                raise ValueError(f"descriptor Mat {a.dtype} {a.shape} does not fit the matcher")
+            return a if a.strides[1] == a.itemsize else np.ascontiguousarray(a)
+        q = mat(prevDesc)
+        ts = [mat(t) for t in trainDescs]
+        P = len(ts)
+        cap = max(q.shape[0], 1)
+        own = out is None
+        if own:
+            out = np.empty((max(P, 1), cap), DMATCH)
+            n_out = np.zeros(max(P, 1), np.int32)
+        ptrs = (ctypes.c_void_p * max(P, 1))(*[t.ctypes.data for t in ts])
+        rows = np.array([t.shape[0] for t in ts] or [0], np.int32)
+        strides = (ctypes.c_size_t * max(P, 1))(*[t.strides[0] if t.shape[0] > 1 else width * t.itemsize for t in ts])
+        check(self._lib.slamb200_match_batch_host(self._h, int(matcherType), ptr(q), q.shape[0],
+                                                  q.strides[0] if q.shape[0] > 1 else width * q.itemsize, ptrs, ptr(rows),
+                                                  strides, P, float(knnMatcherDistance), ptr(out), out.shape[1],
+                                                  ptr(n_out)))
+        return [out[p, : n_out[p]].copy() if own else out[p, : n_out[p]] for p in range(P)]
+
     def matchWindow(self, frames, matcherType, knnMatcherDistance=0.7):
         """All i<j pairs of a frame window: dict {(i, j): matches}."""
         _kind_of(matcherType)

@@ -59,6 +59,23 @@ struct DescHandle {
   ~DescHandle() { if (d) slamb200_free_desc(context(), d); }
 };
 
+// Every GPU of the box behind the batch entry point (one process, as the reference
+// is): with more than one sm_100 device visible -- and unless SLAMB200_MULTI_GPU=0 -- the batch
+// search spreads its window over a device set (include/slamb200.h).  nullptr = single device.
+slamb200_set* deviceSet() {
+  static slamb200_set* set = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* e = getenv("SLAMB200_MULTI_GPU");
+    if (e && atoi(e) == 0) return;
+    slamb200_set* s = nullptr;
+    if (slamb200_set_init(e ? atoi(e) > 1 ? atoi(e) : 0 : 0, &s) != SLAMB200_OK) return;
+    if (slamb200_set_devices(s) > 1) set = s;
+    else slamb200_set_shutdown(s);
+  });
+  return set;
+}
+
 int descKindOf(int matcherType) {
   switch (matcherType) {
     case SIFT_BF:
@@ -356,6 +373,40 @@ void matchFramesPairFeatures(Mat& firstFrameDescriptor, Mat& secondFrame,
 void matchFramesBatchFeatures(Mat& firstFrameDescriptor, std::vector<Mat>& batchDescriptors,
                               int matcherType, std::vector<std::vector<DMatch>>& allMatches) {
   const int kind = descKindOf(matcherType);
+  if (slamb200_set* set = deviceSet()) {
+    // several GPUs: the previous frame's descriptor replicated over NVLink, batch element i on
+    // device i*G/n, one enqueue per device, results gathered once
+    const int P = (int)batchDescriptors.size();
+    const int cap = firstFrameDescriptor.empty() ? 0 : firstFrameDescriptor.rows;
+    allMatches.assign((size_t)P, std::vector<DMatch>());
+    if (P == 0 || cap == 0) return;
+    auto up = [&](const Mat& m, int member, slamb200_mdesc** out) {
+      const int want = kind == SLAMB200_DESC_F32X128 ? CV_32F : CV_8U;
+      if (!m.empty() && (m.type() != want || m.cols != (kind == SLAMB200_DESC_F32X128 ? 128 : 32)))
+        throw std::runtime_error("descriptor Mat type/width does not fit the matcher");
+      if (slamb200_set_upload(set, member, kind, m.empty() ? nullptr : m.data, m.empty() ? 0 : m.rows,
+                              m.empty() ? 0 : (size_t)m.step, out) != SLAMB200_OK)
+        throw std::runtime_error(std::string("slamb200_set_upload: ") + slamb200_last_error());
+    };
+    struct Guard {
+      slamb200_set* s;
+      std::vector<slamb200_mdesc*> d;
+      ~Guard() { for (slamb200_mdesc* m : d) slamb200_set_free_desc(s, m); }
+    } g{set, {}};
+    g.d.assign((size_t)P + 1, nullptr);
+    up(firstFrameDescriptor, -1, &g.d[0]);
+    for (int i = 0; i < P; i++) up(batchDescriptors[(size_t)i], slamb200_set_owner(set, i, P), &g.d[(size_t)i + 1]);
+    std::vector<slamb200_dmatch> out((size_t)P * cap);
+    std::vector<int> n((size_t)P, 0);
+    if (slamb200_set_match_batch(set, abiMatcher(matcherType), g.d[0], g.d.data() + 1, P, knnMatcherDistance(),
+                                 out.data(), cap, n.data()) != SLAMB200_OK)
+      throw std::runtime_error(std::string("slamb200_set_match_batch: ") + slamb200_last_error());
+    for (int p = 0; p < P; p++) {
+      const DMatch* src = reinterpret_cast<const DMatch*>(out.data() + (size_t)p * cap);
+      allMatches[(size_t)p].assign(src, src + n[(size_t)p]);
+    }
+    return;
+  }
   // every Mat that owns its buffer is resident after its first use: a batch element that stays
   // in the window over several searches (batch.cpp:112-114 re-describes it each time in the
   // reference) is uploaded once in its lifetime

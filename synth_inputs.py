@@ -227,3 +227,33 @@ def window_geometry(nq, nt, train_seeds, seed, K4=SAMSUNG_HV_4K, noise_px=0.7, s
         kts.append(kt.astype(np.float32))
         poses.append((R, t))
     return kq, kts, poses
+
+
+def _rodrigues_batch(w):
+    """Rotation matrices of h rotation vectors [h,3] -> [h,3,3] (vectorised _rodrigues)."""
+    th = np.linalg.norm(w, axis=1)
+    k = w / np.maximum(th, 1e-300)[:, None]
+    Kx = np.zeros((len(w), 3, 3))
+    Kx[:, 0, 1], Kx[:, 0, 2] = -k[:, 2], k[:, 1]
+    Kx[:, 1, 0], Kx[:, 1, 2] = k[:, 2], -k[:, 0]
+    Kx[:, 2, 0], Kx[:, 2, 1] = -k[:, 1], k[:, 0]
+    I = np.eye(3)[None]
+    R = I + np.sin(th)[:, None, None] * Kx + (1 - np.cos(th))[:, None, None] * (Kx @ Kx)
+    R[th < 1e-12] = np.eye(3)
+    return R
+
+
+def pose_hypotheses_fast(h, R, t, seed, good_frac=0.25):
+    """pose_hypotheses without the Python loop (same distribution, not the same draws): [h, 9]."""
+    rng = np.random.default_rng(seed)
+    s = np.where(rng.random(h) < good_frac, 0.002, 0.3)
+    Ri = _rodrigues_batch(rng.normal(0, 1.0, (h, 3)) * s[:, None]) @ R
+    ti = t[None] + rng.normal(0, 1.0, (h, 3)) * s[:, None]
+    ti /= np.linalg.norm(ti, axis=1, keepdims=True)
+    Tx = np.zeros((h, 3, 3))
+    Tx[:, 0, 1], Tx[:, 0, 2] = -ti[:, 2], ti[:, 1]
+    Tx[:, 1, 0], Tx[:, 1, 2] = ti[:, 2], -ti[:, 0]
+    Tx[:, 2, 0], Tx[:, 2, 1] = -ti[:, 1], ti[:, 0]
+    E = Tx @ Ri
+    E /= np.linalg.norm(E.reshape(h, 9), axis=1)[:, None, None] / np.sqrt(2.0)
+    return np.ascontiguousarray(E.reshape(h, 9))

@@ -130,3 +130,34 @@ def test_launch_counter_counts_concurrent_lanes(ctx):
     [x.start() for x in th]
     [x.join() for x in th]
     assert ctx.launch_count() - n0 == 300 * per_call
+
+
+def test_match_batch_host_equals_resident_batch(ctx):
+    """slamb200_match_batch_host: the whole window from pageable host Mats in one call (uploads and
+    matching pipelined inside the library) == upload everything + slamb200_match_batch; ragged
+    window, a pitched Mat, an empty Mat, general floats inside the window, more pairs than a chunk."""
+    q = synth.sift_like(1500, 9300)
+    sizes = [1400, 1, 0, 2600] + [900 + 13 * i for i in range(37)]
+    trains = [synth.sift_train_from_query(q, max(s, 1), 9301 + i)[:s] for i, s in enumerate(sizes)]
+    wide = np.zeros((len(trains[4]), 160), np.float32)
+    wide[:, :128] = trains[4]
+    trains[4] = wide[:, :128]                                  # a cv::Mat ROI: pitch 640 bytes
+    trains[7] = (trains[7] * np.float32(0.37)).astype(np.float32)   # not integer valued
+    got = ctx.matchBatchHost(q, trains, MatcherType.SIFT_BF, 0.7)
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(np.ascontiguousarray(t)) for t in trains]
+    want = ctx.matchBatch(Q, Ts, MatcherType.SIFT_BF, 0.7)
+    assert len(got) == len(want) == len(trains)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert np.array_equal(got[0], c_oracle.match_features(0, q, np.ascontiguousarray(trains[0]), 0.7))
+    assert np.array_equal(got[7], c_oracle.match_features(0, q, trains[7], 0.7))
+    # ORB, and an empty window
+    qo, _ = synth.orb_pair(1200, 10, 9400)
+    to = [synth.orb_pair(10, 700 + 50 * i, 9401 + i)[1] for i in range(5)]
+    for g, t in zip(ctx.matchBatchHost(qo, to, MatcherType.ORB_BF, 0.7), to):
+        assert np.array_equal(g, c_oracle.match_features(2, qo, t, 0.7))
+    assert ctx.matchBatchHost(q, [], MatcherType.SIFT_BF, 0.7) == []
+    # a Mat of the wrong type is refused with the library's error, nothing leaks or hangs
+    with pytest.raises((Slamb200Error, ValueError)):
+        ctx.matchBatchHost(q, [trains[0], qo], MatcherType.SIFT_BF, 0.7)
