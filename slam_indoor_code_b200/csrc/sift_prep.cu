@@ -17,36 +17,12 @@
 #include "common.cuh"
 #include <cuda_fp8.h>
 
-// U8SRC: the rows arrive already narrowed to bytes (slamb200_upload_desc_packed: the host verified
-// that they are integers in [0,255]); src then points at n x 128 bytes, typically page-locked host
-// memory read straight over PCIe -- 16-byte requests from eight lanes per row, spread by shuffles.
-template <bool U8SRC>
-__global__ void __launch_bounds__(256)
-sift_prep_kernel(const float* __restrict__ src, size_t src_stride, int n, int n_pad,
-                 float* __restrict__ f32, __nv_bfloat16* __restrict__ bf16,
-                 __nv_bfloat16* __restrict__ augq, __nv_bfloat16* __restrict__ augt,
-                 uint8_t* __restrict__ u8, int32_t* __restrict__ nrm2,
-                 __nv_bfloat16* __restrict__ bf16lo, float* __restrict__ nrmf,
-                 int32_t* __restrict__ flags) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n_pad) return;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (U8SRC) {
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (row < n && lane < 8)
-      w = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src) + (size_t)row * 128)[lane];
-    const int from = lane >> 2;
-    const uint32_t w0 = __shfl_sync(0xffffffffu, w.x, from), w1 = __shfl_sync(0xffffffffu, w.y, from);
-    const uint32_t w2 = __shfl_sync(0xffffffffu, w.z, from), w3 = __shfl_sync(0xffffffffu, w.w, from);
-    const uint32_t word = (lane & 3) == 0 ? w0 : (lane & 3) == 1 ? w1 : (lane & 3) == 2 ? w2 : w3;
-    v = make_float4((float)(word & 255u), (float)((word >> 8) & 255u), (float)((word >> 16) & 255u),
-                    (float)(word >> 24));
-    reinterpret_cast<float4*>(f32 + (size_t)row * 128)[lane] = v;
-  } else {
-    if (row < n) v = reinterpret_cast<const float4*>(src + (size_t)row * src_stride)[lane];
-    if (src != f32 || row >= n) reinterpret_cast<float4*>(f32 + (size_t)row * 128)[lane] = v;
-  }
+// Everything derived from one row's 128 values (lane l holds values 4l .. 4l+3 in v).
+__device__ __forceinline__ void prep_row(const float4 v, const int row, const int lane, const int n,
+                                         __nv_bfloat16* __restrict__ bf16, __nv_bfloat16* __restrict__ augq,
+                                         __nv_bfloat16* __restrict__ augt, uint8_t* __restrict__ u8,
+                                         int32_t* __restrict__ nrm2, __nv_bfloat16* __restrict__ bf16lo,
+                                         float* __restrict__ nrmf, int32_t* __restrict__ flags) {
   const float x[4] = {v.x, v.y, v.z, v.w};
   int bad = 0, ss = 0;
   uint32_t packed = 0;
@@ -119,13 +95,63 @@ sift_prep_kernel(const float* __restrict__ src, size_t src_stride, int n, int n_
   }
 }
 
+// fp32 source rows (device memory, or page-locked host memory read over PCIe): one warp per row,
+// one float4 per lane -- a 512-byte request per warp.
+__global__ void __launch_bounds__(256)
+sift_prep_kernel(const float* __restrict__ src, size_t src_stride, int n, int n_pad,
+                 float* __restrict__ f32, __nv_bfloat16* __restrict__ bf16,
+                 __nv_bfloat16* __restrict__ augq, __nv_bfloat16* __restrict__ augt,
+                 uint8_t* __restrict__ u8, int32_t* __restrict__ nrm2,
+                 __nv_bfloat16* __restrict__ bf16lo, float* __restrict__ nrmf,
+                 int32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < n) v = reinterpret_cast<const float4*>(src + (size_t)row * src_stride)[lane];
+  if (src != f32 || row >= n) reinterpret_cast<float4*>(f32 + (size_t)row * 128)[lane] = v;
+  prep_row(v, row, lane, n, bf16, augq, augt, u8, nrm2, bf16lo, nrmf, flags);
+}
+
+// Rows already narrowed to bytes (slamb200_upload_desc_packed: the host verified that they are
+// integers in [0,255]); src points at n x 128 bytes, typically page-locked host memory read
+// straight over PCIe.  A warp takes FOUR consecutive rows with one 512-byte request (lane l the
+// 16 bytes at 16 l: a row per eight lanes) and then prepares them one after the other, the bytes
+// spread by shuffles -- with one row (128 bytes) per request the link ran at half its rate.
+__global__ void __launch_bounds__(256)
+sift_prep_u8_kernel(const uint8_t* __restrict__ src, int n, int n_pad,
+                    float* __restrict__ f32, __nv_bfloat16* __restrict__ bf16,
+                    __nv_bfloat16* __restrict__ augq, __nv_bfloat16* __restrict__ augt,
+                    uint8_t* __restrict__ u8, int32_t* __restrict__ nrm2,
+                    __nv_bfloat16* __restrict__ bf16lo, float* __restrict__ nrmf,
+                    int32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4;
+  if (row0 >= n_pad) return;
+  uint4 w = make_uint4(0, 0, 0, 0);
+  if (row0 + (lane >> 3) < n) w = reinterpret_cast<const uint4*>(src + (size_t)row0 * 128)[lane];
+#pragma unroll
+  for (int rr = 0; rr < 4; rr++) {
+    const int row = row0 + rr;
+    if (row >= n_pad) break;   // warp-uniform
+    const int from = rr * 8 + (lane >> 2);
+    const uint32_t w0 = __shfl_sync(0xffffffffu, w.x, from), w1 = __shfl_sync(0xffffffffu, w.y, from);
+    const uint32_t w2 = __shfl_sync(0xffffffffu, w.z, from), w3 = __shfl_sync(0xffffffffu, w.w, from);
+    const uint32_t word = (lane & 3) == 0 ? w0 : (lane & 3) == 1 ? w1 : (lane & 3) == 2 ? w2 : w3;
+    const float4 v = make_float4((float)(word & 255u), (float)((word >> 8) & 255u), (float)((word >> 16) & 255u),
+                                 (float)(word >> 24));
+    reinterpret_cast<float4*>(f32 + (size_t)row * 128)[lane] = v;
+    prep_row(v, row, lane, n, bf16, augq, augt, u8, nrm2, bf16lo, nrmf, flags);
+  }
+}
+
 void launch_sift_prep(const float* src, size_t src_stride_floats, int n, int n_pad, float* f32,
                       __nv_bfloat16* bf16, __nv_bfloat16* augq, __nv_bfloat16* augt, uint8_t* u8,
                       int32_t* nrm2, __nv_bfloat16* bf16lo, float* nrmf, int32_t* flags,
                       cudaStream_t s) {
   if (n_pad <= 0) return;
   const int rows_per_block = 8;
-  sift_prep_kernel<false><<<(n_pad + rows_per_block - 1) / rows_per_block, 256, 0, s>>>(
+  sift_prep_kernel<<<(n_pad + rows_per_block - 1) / rows_per_block, 256, 0, s>>>(
       src, src_stride_floats, n, n_pad, f32, bf16, augq, augt, u8, nrm2, bf16lo, nrmf, flags);
   COUNT_LAUNCH();
 }
@@ -134,10 +160,9 @@ void launch_sift_prep_u8(const uint8_t* src_u8, int n, int n_pad, float* f32, __
                          __nv_bfloat16* augq, __nv_bfloat16* augt, uint8_t* u8, int32_t* nrm2,
                          __nv_bfloat16* bf16lo, float* nrmf, int32_t* flags, cudaStream_t s) {
   if (n_pad <= 0) return;
-  const int rows_per_block = 8;
-  sift_prep_kernel<true><<<(n_pad + rows_per_block - 1) / rows_per_block, 256, 0, s>>>(
-      reinterpret_cast<const float*>(src_u8), 32, n, n_pad, f32, bf16, augq, augt, u8, nrm2, bf16lo,
-      nrmf, flags);
+  const int rows_per_block = 32;   // 8 warps x 4 rows
+  sift_prep_u8_kernel<<<(n_pad + rows_per_block - 1) / rows_per_block, 256, 0, s>>>(
+      src_u8, n, n_pad, f32, bf16, augq, augt, u8, nrm2, bf16lo, nrmf, flags);
   COUNT_LAUNCH();
 }
 
