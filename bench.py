@@ -832,6 +832,20 @@ def extras(ctx, stream):
     kms, kn = ctx.profile_read()["fast"]
     ctx.profile_enable(False)
     out["f3_fast_4k"] = {"ms_per_host_call": dt * 1e3, "kernels_us": kms / max(kn, 1) * 1e3, "keypoints": n_fast}
+    # next row 8f-3, second half: SIFT descriptors of 12 000 FAST-like keypoints (size 7, angle -1) on the
+    # same 4K frame, resident output; tolerance-pinned against cv2 (tests/test_gpu_sift_descriptors.py)
+    from slam_indoor_code_b200 import sift_descriptors as sdm
+    kp4s = np.concatenate([kp4k[:, :2], np.full((12000, 1), 7.0, np.float32), np.full((12000, 1), -1.0, np.float32)], 1)
+    sdm.extractDescriptorSIFT(ctx, frame4k, kp4s, want_host=False, want_resident=True)[1].free()
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        sdm.extractDescriptorSIFT(ctx, frame4k, kp4s, want_host=False, want_resident=True)[1].free()
+    dt = (time.perf_counter() - t0) / 5
+    kms, kn = ctx.profile_read()["sift_desc"]
+    ctx.profile_enable(False)
+    out["f3_sift_compute_4k_12000kp"] = {"ms_per_host_call": dt * 1e3, "kernels_us": kms / max(kn, 1) * 1e3}
     # next row 8f-4: linear triangulation of 5000 matches (one host call incl. copies)
     from slam_indoor_code_b200 import triangulation as tri
     K4 = synth.SAMSUNG_HV_4K
@@ -915,6 +929,9 @@ def cpu_extras():
     orb = cv2.ORB_create()
     dt, _ = best(lambda: orb.compute(frame4k, cvk), 3)
     out["f3_orb_compute_4k_12000kp_s"] = dt
+    sift = cv2.SIFT_create()
+    dt, _ = best(lambda: sift.compute(frame4k, cvk), 3)
+    out["f3_sift_compute_4k_12000kp_s"] = dt
     fast = cv2.FastFeatureDetector_create(10, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
     dt, _ = best(lambda: fast.detect(frame4k), 3)
     out["f3_fast_4k_s"] = dt

@@ -285,6 +285,21 @@ int slamb200_orb_compute(slamb200_ctx* ctx, const uint8_t* image, int rows, int 
                          size_t step, const float* kps, int n, uint8_t* keep, uint8_t* desc,
                          int* n_kept, slamb200_desc** resident);
 
+/* ---- next row: SIFT descriptors of given keypoints (featureMatchingCPU.cpp:45-66) --- */
+/* cv::SIFT::create()->compute(frame, features, desc) for the SIFT_BF / SIFT_FLANN matchers on
+ * keypoints of octave 0 / layer 0 -- the only kind the reference produces (fastExtractor.cpp:7-13:
+ * FAST keypoints, size 7, angle -1).  image as in slamb200_orb_compute; kps = n x {x, y, size,
+ * angle in degrees} floats.  No keypoint is dropped (cv::SIFT::compute keeps them all).  desc (may
+ * be NULL) receives n x 128 floats on the host, integer valued like cv::SIFT's; *resident (may be
+ * NULL) the same rows as a descriptor set already in HBM, ready for slamb200_match_*.
+ * TOLERANCE, not bit-exactness: the working image (gray -> float -> 13-tap Gaussian) equals
+ * OpenCV's bit for bit; the descriptors follow calcSIFTDescriptor operation by operation but
+ * OpenCV's exp / magnitude are IPP routines and its histogram sum runs in sample order, so a
+ * scaled value that lands within ~1e-4 of a rounding boundary may round the other way: every
+ * element is within 1 of OpenCV's and >= 99.9 % are equal (measured 99.998 %). */
+int slamb200_sift_compute(slamb200_ctx* ctx, const uint8_t* image, int rows, int cols, int channels,
+                          size_t step, const float* kps, int n, float* desc, slamb200_desc** resident);
+
 /* ---- next row: FAST keypoints (featureExtraction/fastExtractor.cpp:7-13) --- */
 /* FastFeatureDetector::create(threshold, nonmax, TYPE_9_16)->detect(image, points), the reference's
  * fastExtractor (callers cycleProcessing/batch.cpp:245, mainCycleInternals.cpp:144 with
@@ -350,7 +365,8 @@ int slamb200_batch_scores_fetch(slamb200_ctx* ctx, int32_t* counts, int32_t* bes
 #define SLAMB200_K_SIFT_L1 9    /* NORM_L1 on integer-valued rows (byte-wise SAD) */
 #define SLAMB200_K_ORB_DESC 10  /* ORB gray + blur + descriptor kernels */
 #define SLAMB200_K_FAST 11      /* gray + FAST score, suppression, ordered output */
-#define SLAMB200_K_COUNT 12
+#define SLAMB200_K_SIFT_DESC 12 /* SIFT base image blur + descriptor kernel */
+#define SLAMB200_K_COUNT 13
 int slamb200_profile_enable(slamb200_ctx* ctx, int on);
 /* Synchronises, then returns the summed device time (ms) and the launch count of each kernel
  * class since the last read; ms and launches have SLAMB200_K_COUNT entries. */

@@ -231,3 +231,30 @@ def fast_detect(image, threshold=10, nonmax=True, want_scores=False):
                                  1 if nonmax else 0, _p(kp), cap, _p(score))
     assert n >= 0
     return (kp[:n].copy(), score) if want_scores else kp[:n].copy()
+
+
+def sift_base(image):
+    """SIFT's working image for octave-0 keypoints: gray -> float -> 13-tap Gaussian (sigma
+    sqrt(1.6^2 - 0.5^2)); equals cv2.GaussianBlur on the float gray frame bit for bit."""
+    image = np.ascontiguousarray(image, np.uint8)
+    rows, cols = image.shape[:2]
+    ch = 1 if image.ndim == 2 else image.shape[2]
+    base = np.zeros((rows, cols), np.float32)
+    rc = lib().oracle_sift_base(_p(image), rows, cols, ch, ctypes.c_size_t(image.strides[0]), _p(base))
+    assert rc == 0
+    return base
+
+
+def sift_compute(image, kps, raw=False):
+    """cv::SIFT::compute on given octave-0 keypoints: kps [n, 4] = x, y, size, angle (FAST gives
+    size 7, angle -1).  Returns descriptors [n, 128] float32 (integer valued unless raw)."""
+    image = np.ascontiguousarray(image, np.uint8)
+    rows, cols = image.shape[:2]
+    ch = 1 if image.ndim == 2 else image.shape[2]
+    kps = np.ascontiguousarray(kps, np.float32).reshape(-1, 4)
+    n = kps.shape[0]
+    desc = np.zeros((max(n, 1), 128), np.float32)
+    rc = lib().oracle_sift_compute(_p(image), rows, cols, ch, ctypes.c_size_t(image.strides[0]), _p(kps), n,
+                                   _p(desc), 1 if raw else 0)
+    assert rc == 0
+    return desc[:n]

@@ -778,3 +778,174 @@ int oracle_fast_detect(const uint8_t* image, int rows, int cols, int channels, s
     free(gray); free(score); free(corner);
     return n;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * SIFT descriptors of given keypoints (reference: extractDescriptor,
+ * featureMatchingCPU.cpp:45-66 -> cv::SIFT::create()->compute(frame, features, desc) on FAST
+ * keypoints, fastExtractor.cpp:7-13: KeyPoint(x, y, size 7, angle -1, octave 0)).  Restated from
+ * OpenCV's published algorithm (SIFT_Impl::detectAndCompute with useProvidedKeypoints,
+ * createInitialImage, calcSIFTDescriptor) and pinned to the cv2 wheel by measurement:
+ *   gray  = the integer cvtColor formula (as for ORB / FAST), converted to float (scale 1)
+ *   base  = GaussianBlur(gray, sigma = sqrtf(1.6^2 - 0.5^2)), 13 taps (cvRound(sigma*8 + 1) | 1),
+ *           BORDER_REFLECT_101, float: rows  s = k0*p0; s = fma(kj, pj, s),  columns
+ *           c = k6*s; c = fma(k(6+j), s(+j) + s(-j), c)  -- the order of the cv2 wheel's
+ *           sepFilter2D (scalar, unfused tails beyond the last whole vector of a row): 0
+ *           differing pixels against cv2.GaussianBlur on float frames of any size
+ *   every keypoint of octave 0 / layer 0 (the only kind FAST produces) reads that base image:
+ *           firstOctave = 0, no image doubling, no further pyramid level is touched
+ *   desc  = calcSIFTDescriptor(base, pt, 360 - angle, size/2, d = 4, n = 8): samples in a
+ *           (2 radius + 1)^2 window, gradient by central differences, orientation by the degree-7
+ *           fastAtan2 polynomial, magnitude, Gaussian weight, trilinear vote into the
+ *           6 x 6 x 10 histogram in sample order; circular wrap; L2 norm, clip at 0.2, renormalise
+ *           to 512, saturate_cast<uchar>.
+ * cv::hal::magnitude32f / exp32f are IPP routines in the wheel and differ from sqrtf / expf in the
+ * last ulp on a fraction of inputs, and OpenCV's AVX2 code sums the squared norm in another order:
+ * this restatement equals cv2.SIFT.compute on 99.998 % of the ELEMENTS (the rest differ by 1) --
+ * a tolerance pin, not a bit-exact one (tests/test_oracle_vs_cv2.py states the bound).
+ * ---------------------------------------------------------------------------------------------- */
+void oracle_sift_gauss13(float k[13], float* sigma_out) {
+    const float sigma = sqrtf(fmaxf(1.6f * 1.6f - 0.5f * 0.5f, 0.01f));
+    double v[13], sum = 0;
+    for (int i = 0; i < 13; i++) { double x = i - 6; v[i] = exp(-x * x / (2.0 * (double)sigma * (double)sigma)); sum += v[i]; }
+    for (int i = 0; i < 13; i++) k[i] = (float)(v[i] * (1. / sum));
+    if (sigma_out) *sigma_out = sigma;
+}
+
+/* image: rows x cols, channels 1 or 3 (BGR), `step` bytes per row -> base (rows*cols floats) */
+int oracle_sift_base(const uint8_t* image, int rows, int cols, int channels, size_t step, float* base) {
+    if (rows <= 0 || cols <= 0 || (channels != 1 && channels != 3)) return -1;
+    float* gray = (float*)malloc(sizeof(float) * (size_t)rows * cols);
+    float* rowf = (float*)malloc(sizeof(float) * (size_t)rows * cols);
+    if (!gray || !rowf) { free(gray); free(rowf); return -2; }
+    for (int y = 0; y < rows; y++) {
+        const uint8_t* s = image + (size_t)y * step;
+        for (int x = 0; x < cols; x++)
+            gray[(size_t)y * cols + x] = (float)(channels == 1 ? s[x]
+                : (uint8_t)((s[3 * x] * 3735 + s[3 * x + 1] * 19235 + s[3 * x + 2] * 9798 + (1 << 14)) >> 15));
+    }
+    float k[13];
+    oracle_sift_gauss13(k, NULL);
+    /* The wheel's row filter is 4 pixels wide, its column filter 8; the pixels beyond the last
+     * whole vector of a row go through scalar code that multiplies and adds separately (measured:
+     * with these two widths 0 pixels differ on frames of any width, with any other pair some do). */
+    const int body_r = cols & ~3, body_c = cols & ~7;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < rows; y++)
+        for (int x = 0; x < cols; x++) {
+            float s = k[0] * gray[(size_t)y * cols + reflect101(x - 6, cols)];
+            for (int j = 1; j < 13; j++) {
+                const float p = gray[(size_t)y * cols + reflect101(x - 6 + j, cols)];
+                s = x < body_r ? fmaf(k[j], p, s) : s + k[j] * p;
+            }
+            rowf[(size_t)y * cols + x] = s;
+        }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < rows; y++)
+        for (int x = 0; x < cols; x++) {
+            float c = k[6] * rowf[(size_t)y * cols + x];
+            for (int j = 1; j <= 6; j++) {
+                const float p = rowf[(size_t)reflect101(y + j, rows) * cols + x] +
+                                rowf[(size_t)reflect101(y - j, rows) * cols + x];
+                c = x < body_c ? fmaf(k[6 + j], p, c) : c + k[6 + j] * p;
+            }
+            base[(size_t)y * cols + x] = c;
+        }
+    free(gray); free(rowf);
+    return 0;
+}
+
+static float sift_fast_atan2(float y, float x) {   /* cv::fastAtan2, degrees */
+    const float p1 = 0.9997878412794807f * (float)(180 / M_PI), p3 = -0.3258083974640975f * (float)(180 / M_PI);
+    const float p5 = 0.1555786518463281f * (float)(180 / M_PI), p7 = -0.04432655554792128f * (float)(180 / M_PI);
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON); c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON); c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+/* kps: n x {x, y, size, angle_deg} floats (octave 0, layer 0).  desc: n x 128 floats (integer
+ * valued, as cv::SIFT emits them); raw != 0 skips the final rounding (the values before
+ * saturate_cast, for tolerance analysis). */
+int oracle_sift_compute(const uint8_t* image, int rows, int cols, int channels, size_t step,
+                        const float* kps, int n, float* desc, int raw) {
+    if (n < 0) return -1;
+    float* base = (float*)malloc(sizeof(float) * (size_t)(rows > 0 ? rows : 1) * (cols > 0 ? cols : 1));
+    if (!base) return -2;
+    int rc = oracle_sift_base(image, rows, cols, channels, step, base);
+    if (rc) { free(base); return rc; }
+    const int d = 4, nb = 8;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int q = 0; q < n; q++) {
+        const float px = kps[4 * q], py = kps[4 * q + 1], size = kps[4 * q + 2], kang = kps[4 * q + 3];
+        float angle = 360.f - kang;
+        if (fabsf(angle - 360.f) < FLT_EPSILON) angle = 0.f;
+        const float ori = angle, scl = size * 0.5f;
+        const int ptx = (int)lrintf(px), pty = (int)lrintf(py);
+        float cos_t = cosf(ori * (float)(M_PI / 180)), sin_t = sinf(ori * (float)(M_PI / 180));
+        const float bins_per_rad = nb / 360.f, exp_scale = -1.f / (d * d * 0.5f), hist_width = 3.0f * scl;
+        int radius = (int)lrintf(hist_width * 1.4142135623730951f * (d + 1) * 0.5f);
+        const int maxr = (int)sqrt((double)cols * cols + (double)rows * rows);
+        if (radius > maxr) radius = maxr;
+        cos_t /= hist_width;
+        sin_t /= hist_width;
+        float hist[6 * 6 * 10];
+        memset(hist, 0, sizeof(hist));
+        for (int i = -radius; i <= radius; i++)
+            for (int j = -radius; j <= radius; j++) {
+                const float c_rot = j * cos_t - i * sin_t, r_rot = j * sin_t + i * cos_t;
+                float rbin = r_rot + d / 2 - 0.5f, cbin = c_rot + d / 2 - 0.5f;
+                const int r = pty + i, c = ptx + j;
+                if (!(rbin > -1 && rbin < d && cbin > -1 && cbin < d && r > 0 && r < rows - 1 && c > 0 && c < cols - 1))
+                    continue;
+                const float dx = base[(size_t)r * cols + c + 1] - base[(size_t)r * cols + c - 1];
+                const float dy = base[(size_t)(r - 1) * cols + c] - base[(size_t)(r + 1) * cols + c];
+                const float w = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+                float obin = (sift_fast_atan2(dy, dx) - ori) * bins_per_rad;
+                const float mag = sqrtf(dx * dx + dy * dy) * w;
+                const int r0 = (int)floorf(rbin), c0 = (int)floorf(cbin);
+                int o0 = (int)floorf(obin);
+                rbin -= r0; cbin -= c0; obin -= o0;
+                if (o0 < 0) o0 += nb;
+                if (o0 >= nb) o0 -= nb;
+                const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+                const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11, v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+                const float v111 = v_rc11 * obin, v110 = v_rc11 - v111, v101 = v_rc10 * obin, v100 = v_rc10 - v101;
+                const float v011 = v_rc01 * obin, v010 = v_rc01 - v011, v001 = v_rc00 * obin, v000 = v_rc00 - v001;
+                const int idx = ((r0 + 1) * (d + 2) + c0 + 1) * (nb + 2) + o0;
+                hist[idx] += v000; hist[idx + 1] += v001;
+                hist[idx + (nb + 2)] += v010; hist[idx + (nb + 3)] += v011;
+                hist[idx + (d + 2) * (nb + 2)] += v100; hist[idx + (d + 2) * (nb + 2) + 1] += v101;
+                hist[idx + (d + 3) * (nb + 2)] += v110; hist[idx + (d + 3) * (nb + 2) + 1] += v111;
+            }
+        float v[128];
+        for (int i = 0; i < d; i++)
+            for (int j = 0; j < d; j++) {
+                const int idx = ((i + 1) * (d + 2) + (j + 1)) * (nb + 2);
+                hist[idx] += hist[idx + nb];
+                hist[idx + 1] += hist[idx + nb + 1];
+                for (int k = 0; k < nb; k++) v[(i * d + j) * nb + k] = hist[idx + k];
+            }
+        float nrm2 = 0;
+        for (int k = 0; k < 128; k++) nrm2 += v[k] * v[k];
+        const float thr = sqrtf(nrm2) * 0.2f;
+        nrm2 = 0;
+        for (int k = 0; k < 128; k++) { const float t = v[k] < thr ? v[k] : thr; v[k] = t; nrm2 += t * t; }
+        nrm2 = 512.f / fmaxf(sqrtf(nrm2), FLT_EPSILON);
+        for (int k = 0; k < 128; k++) {
+            const float t = v[k] * nrm2;
+            if (raw) { desc[(size_t)q * 128 + k] = t; continue; }
+            long iv = lrintf(t);                       /* saturate_cast<uchar>(float): cvRound, clamp */
+            desc[(size_t)q * 128 + k] = (float)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+        }
+    }
+    free(base);
+    return 0;
+}

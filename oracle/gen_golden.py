@@ -202,9 +202,33 @@ def gen_fast():
     np.savez_compressed(os.path.join(OUT, "fast.npz"), **out)
 
 
+def gen_sift_desc():
+    """extractDescriptor's SIFT branch: FAST keypoints (size 7, angle -1) plus keypoints of other sizes
+    and orientations on a small textured frame whose width is NOT a multiple of 8 (the scalar tails of
+    OpenCV's separable filter are part of the pin): cv2's float base image (GaussianBlur of the gray
+    frame with createInitialImage's sigma) as a checksum-free slice, and cv2.SIFT.compute's rows."""
+    frame = synth.textured_frame(150, 205, 6300, 3)
+    fast = cv2.FastFeatureDetector_create(15, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16).detect(frame)[:300]
+    rng = np.random.default_rng(6301)
+    kps = np.array([[k.pt[0], k.pt[1], k.size, k.angle] for k in fast], np.float32)
+    extra = np.stack([rng.uniform(0, 205, 120), rng.uniform(0, 150, 120), rng.uniform(2, 12, 120),
+                      rng.uniform(0, 360, 120)], 1).astype(np.float32)
+    kps = np.concatenate([kps, extra])
+    cvk = [cv2.KeyPoint(float(x), float(y), float(s), float(a), 0.0, 0) for x, y, s, a in kps]
+    kept, desc = cv2.SIFT_create().compute(frame, cvk)
+    assert len(kept) == len(cvk)
+    gray = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY).astype(np.float32)
+    sigma = float(np.sqrt(np.float32(np.float32(1.6) * np.float32(1.6) - np.float32(0.25))))
+    base = cv2.GaussianBlur(gray, (0, 0), sigma)
+    np.savez_compressed(os.path.join(OUT, "sift_desc.npz"), frame=frame, kps=kps, desc=desc.astype(np.uint8),
+                        base_rows=base[[0, 1, 74, 148, 149]], base_cols=base[:, [0, 1, 199, 200, 203, 204]])
+
+
 if __name__ == "__main__":
     import sys
-    if len(sys.argv) > 1 and sys.argv[1] == "pnp":
+    if len(sys.argv) > 1 and sys.argv[1] == "sift_desc":
+        gen_sift_desc()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pnp":
         gen_pnp()
     elif len(sys.argv) > 1 and sys.argv[1] == "l1":
         gen_l1()

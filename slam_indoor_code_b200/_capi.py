@@ -47,6 +47,7 @@ SYMBOLS = {
     "slamb200_score_essential": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp]),
     "slamb200_score_essential_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp]),
     "slamb200_orb_compute": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _vp, _vp, _vp, _vp]),
+    "slamb200_sift_compute": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _vp, _pp]),
     "slamb200_fast_detect": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _vp, _i, _vp]),
     "slamb200_fast_orb_compute": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _pp]),
     "slamb200_triangulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),

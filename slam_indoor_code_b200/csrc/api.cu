@@ -66,6 +66,7 @@ struct Lane {
   DevBuf npts, E, counts, best, mask, m_off, p1, p2, txy, all_masks;
   DevBuf orb_img, orb_gray, orb_rowf, orb_blur, orb_kp, orb_desc;
   DevBuf fast_score, fast_cnt, fast_kp;
+  DevBuf sift_rowf, sift_base, sift_kp, sift_desc;
   // pinned staging
   // pinned staging ring: the host fills slot k+1 while the copy out of slot k may still be
   // queued behind the previous step's kernels (an enqueue never waits for the device)
@@ -333,7 +334,7 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
                       &L.chunk_cnt, &L.out, &L.n_out, &L.err_flag, &L.npts, &L.E, &L.counts,
                       &L.best, &L.mask, &L.m_off, &L.p1, &L.p2, &L.txy, &L.all_masks,
                       &L.orb_img, &L.orb_gray, &L.orb_rowf, &L.orb_blur, &L.orb_kp, &L.orb_desc,
-                      &L.fast_score, &L.fast_cnt, &L.fast_kp};
+                      &L.fast_score, &L.fast_cnt, &L.fast_kp, &L.sift_rowf, &L.sift_base, &L.sift_kp, &L.sift_desc};
     for (DevBuf* b : bufs)
       if (b->p) cudaFreeAsync(b->p, L.stream);
     cudaStreamSynchronize(L.stream);
@@ -1856,6 +1857,77 @@ extern "C" int slamb200_orb_compute(slamb200_ctx* c, const uint8_t* image, int r
   return SLAMB200_OK;
 }
 
+// ---- SIFT descriptors of given keypoints (second half) ----------------------------
+extern "C" int slamb200_sift_compute(slamb200_ctx* c, const uint8_t* image, int rows, int cols,
+                                     int channels, size_t step, const float* kps, int n, float* desc,
+                                     slamb200_desc** resident) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "sift_compute: ctx is NULL");
+  if (resident) *resident = nullptr;
+  if (rows <= 0 || cols <= 0 || !image) return fail(SLAMB200_ERR_INVALID, "sift_compute: bad image");
+  if (channels != 1 && channels != 3)
+    return fail(SLAMB200_ERR_KIND, "sift_compute: %d-channel image (CV_8UC1 or CV_8UC3 expected)", channels);
+  if (step == 0) step = (size_t)cols * channels;
+  if (step < (size_t)cols * channels) return fail(SLAMB200_ERR_INVALID, "sift_compute: step too small");
+  if (n < 0 || (n > 0 && !kps)) return fail(SLAMB200_ERR_INVALID, "sift_compute: bad keypoints");
+  // what calcSIFTDescriptor derives from a keypoint before its sample loop (float, libm's cosf / sinf)
+  std::vector<SiftKeypoint> hk((size_t)n);
+  const int max_radius = (int)sqrt((double)cols * cols + (double)rows * rows);
+  for (int i = 0; i < n; i++) {
+    const float x = kps[4 * (size_t)i], y = kps[4 * (size_t)i + 1], size = kps[4 * (size_t)i + 2];
+    float angle = 360.f - kps[4 * (size_t)i + 3];
+    if (fabsf(angle - 360.f) < 1.1920928955078125e-07f) angle = 0.f;
+    const float scl = size * 0.5f, hist_width = 3.0f * scl;
+    SiftKeypoint k;
+    k.ptx = (int)lrintf(x);
+    k.pty = (int)lrintf(y);
+    k.ori = angle;
+    k.cos_t = cosf(angle * (float)(3.14159265358979323846 / 180)) / hist_width;
+    k.sin_t = sinf(angle * (float)(3.14159265358979323846 / 180)) / hist_width;
+    int radius = (int)lrintf(hist_width * 1.4142135623730951f * 5 * 0.5f);
+    k.radius = radius < max_radius ? radius : max_radius;
+    if (!(size > 0.f) || k.radius > 4096)
+      return fail(SLAMB200_ERR_INVALID, "sift_compute: keypoint %d has size %g", i, (double)size);
+    hk[(size_t)i] = k;
+  }
+  CU(cudaSetDevice(c->device));
+  if (sift_gauss_upload() != 0) return fail(SLAMB200_ERR_CUDA, "sift_compute: kernel table upload failed");
+  int rc;
+  const int n_pad = round_up(n > 0 ? n : 1, SLAMB200_TILE_PAD);
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  cudaStream_t s = L.stream;
+  const size_t px = (size_t)rows * cols;
+  if ((rc = buf_reserve(c, L.orb_img, (size_t)rows * step, s))) return rc;
+  if ((rc = buf_reserve(c, L.orb_gray, px, s))) return rc;
+  if ((rc = buf_reserve(c, L.sift_rowf, px * sizeof(float), s))) return rc;
+  if ((rc = buf_reserve(c, L.sift_base, px * sizeof(float), s))) return rc;
+  if ((rc = buf_reserve(c, L.sift_kp, sizeof(SiftKeypoint) * (size_t)(n > 0 ? n : 1), s))) return rc;
+  if ((rc = buf_reserve(c, L.sift_desc, sizeof(float) * 128 * (size_t)n_pad, s))) return rc;
+  CU(cudaMemcpyAsync(L.orb_img.p, image, (size_t)rows * step, cudaMemcpyHostToDevice, s));
+  if (n > 0) CU(cudaMemcpyAsync(L.sift_kp.p, hk.data(), sizeof(SiftKeypoint) * (size_t)n, cudaMemcpyHostToDevice, s));
+  {
+    ProfScope ps(c, s, SLAMB200_K_SIFT_DESC);
+    launch_orb_gray((const uint8_t*)L.orb_img.p, rows, cols, channels, step, (uint8_t*)L.orb_gray.p, s);
+    launch_sift_base((const uint8_t*)L.orb_gray.p, rows, cols, (float*)L.sift_rowf.p, (float*)L.sift_base.p, s);
+    if (launch_sift_desc((const float*)L.sift_base.p, rows, cols, (const SiftKeypoint*)L.sift_kp.p, n, n_pad,
+                         (float*)L.sift_desc.p, s) != 0)
+      return fail(SLAMB200_ERR_CUDA, "sift_compute: kernel configuration failed");
+  }
+  CU(cudaGetLastError());
+  if (desc && n > 0)
+    CU(cudaMemcpyAsync(desc, L.sift_desc.p, sizeof(float) * 128 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(L.done, s));
+  if (resident) {
+    // the rows are already in HBM: the resident set is prepared from them on an upload lane,
+    // ordered behind this lane's work; this lane's buffer may be reused only after that
+    rc = desc_create(c, SLAMB200_DESC_F32X128, L.sift_desc.p, n, 512, true, s, false, resident);
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(s, (*resident)->ready, 0));
+  }
+  CU(cudaStreamSynchronize(s));   // hk and the caller's image must outlive the copies
+  return SLAMB200_OK;
+}
+
 // ---- FAST keypoints (fastExtractor.cpp:7-13) --------------------------------------
 extern "C" int slamb200_fast_detect(slamb200_ctx* c, const uint8_t* image, int rows, int cols,
                                     int channels, size_t step, int threshold, int nonmax,
@@ -2172,6 +2244,32 @@ extern "C" int slamb200_batch_scores_fetch(slamb200_ctx* c, int32_t* counts, int
 }
 
 // ---- debug hooks (not part of the public header) ----------------------------------------------
+// SIFT's working image of a frame (gray -> float -> 13-tap Gaussian) as the descriptor kernel reads
+// it: out = rows x cols floats.  For the bit-exactness test against cv2.GaussianBlur.
+extern "C" int slamb200_dbg_sift_base(slamb200_ctx* c, const uint8_t* image, int rows, int cols, int channels,
+                                      size_t step, float* out) {
+  if (!c || !image || !out || rows <= 0 || cols <= 0 || (channels != 1 && channels != 3)) return SLAMB200_ERR_INVALID;
+  if (step == 0) step = (size_t)cols * channels;
+  CU(cudaSetDevice(c->device));
+  if (sift_gauss_upload() != 0) return fail(SLAMB200_ERR_CUDA, "kernel table upload failed");
+  LaneGuard g(c);
+  Lane& L = g.lane();
+  cudaStream_t s = L.stream;
+  const size_t px = (size_t)rows * cols;
+  int rc;
+  if ((rc = buf_reserve(c, L.orb_img, (size_t)rows * step, s))) return rc;
+  if ((rc = buf_reserve(c, L.orb_gray, px, s))) return rc;
+  if ((rc = buf_reserve(c, L.sift_rowf, px * sizeof(float), s))) return rc;
+  if ((rc = buf_reserve(c, L.sift_base, px * sizeof(float), s))) return rc;
+  CU(cudaMemcpyAsync(L.orb_img.p, image, (size_t)rows * step, cudaMemcpyHostToDevice, s));
+  launch_orb_gray((const uint8_t*)L.orb_img.p, rows, cols, channels, step, (uint8_t*)L.orb_gray.p, s);
+  launch_sift_base((const uint8_t*)L.orb_gray.p, rows, cols, (float*)L.sift_rowf.p, (float*)L.sift_base.p, s);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, L.sift_base.p, px * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SLAMB200_OK;
+}
+
 extern "C" int slamb200_dbg_set_sub_batch(slamb200_ctx* c, int pairs) {
   if (!c) return SLAMB200_ERR_INVALID;
   c->sub_batch = pairs;

@@ -187,6 +187,15 @@ void launch_orb_blur(const uint8_t* img, int rows, int cols, int channels, size_
 void launch_orb_desc(const uint8_t* blur, int cols, const OrbKeypoint* kps, int n, int n_pad,
                      uint8_t* desc, cudaStream_t s);
 
+// SIFT descriptors of given octave-0 keypoints (sift_desc.cu): the rounded centre, the window
+// radius, cos / sin of the orientation divided by the histogram width, the orientation in degrees
+// -- everything calcSIFTDescriptor derives from the keypoint before its sample loop (host, libm).
+struct SiftKeypoint { int ptx, pty, radius; float cos_t, sin_t, ori; };
+int sift_gauss_upload();
+void launch_sift_base(const uint8_t* gray, int rows, int cols, float* rowf, float* base, cudaStream_t s);
+int launch_sift_desc(const float* base, int rows, int cols, const SiftKeypoint* kps, int n, int n_pad,
+                     float* desc, cudaStream_t s);
+
 // Linear triangulation (triangulate.cpp:17-55): P[v] = 3x4 projection matrix of view v, row-major.
 struct TriParams { double P[2][12]; };
 void launch_triangulate(const float2* pts1, const float2* pts2, int M, const TriParams& tp,

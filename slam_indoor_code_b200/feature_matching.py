@@ -84,7 +84,7 @@ class Context:
         return int(self._lib.slamb200_launch_count(self._h))
 
     KERNELS = ("sift_tc", "sift_exact", "orb", "ransac", "sift_rerank", "finalize", "sift_tc_gen",
-               "sift_gen_rerank", "pnp", "sift_l1", "orb_desc", "fast")
+               "sift_gen_rerank", "pnp", "sift_l1", "orb_desc", "fast", "sift_desc")
 
     def debug_orb_kernel(self, tensor_cores=True):
         """Developer switch: ORB pairs through the tcgen05 kernel on e4m3 0/1 bytes (default) or

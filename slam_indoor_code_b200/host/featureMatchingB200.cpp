@@ -320,13 +320,45 @@ static void computeOrbB200(Mat& frame, std::vector<KeyPoint>& features, Mat& des
   for (int r = 0; r < kept; r++) memcpy(desc.data + (size_t)r * desc.step, rows.data() + (size_t)r * 32, 32);
 }
 
-// featureMatchingCPU.cpp:45-66.  SIFT stays OpenCV-CPU (its float image pipeline has no exact
-// definition across OpenCV builds); ORB runs on the device.
+// cv::SIFT::create()->compute(frame, features, desc) on the B200 for octave-0 / layer-0 keypoints
+// (what fastExtractor produces): no keypoint is dropped, desc is n x 128 CV_32F with
+// integer values.  Held to a tolerance against OpenCV (every element within 1, >= 99.9 % equal:
+// include/slamb200.h), not to bit-exactness -- compile with -DSLAMB200_SIFT_ON_CPU to keep cv::SIFT.
+// Returns false when a keypoint lives on another pyramid level (the caller then runs cv::SIFT).
+static bool computeSiftB200(Mat& frame, std::vector<KeyPoint>& features, Mat& desc) {
+  if (frame.empty() || features.empty()) {  // Feature2D::compute: nothing to describe
+    desc.release();
+    if (frame.empty()) features.clear();
+    return true;
+  }
+  if (frame.depth() != CV_8U || (frame.channels() != 1 && frame.channels() != 3)) return false;
+  const int n = (int)features.size();
+  std::vector<float> k((size_t)4 * n);
+  for (int i = 0; i < n; i++) {
+    if ((features[i].octave & 0xFFFF) != 0) return false;   // octave and layer of unpackOctave
+    k[4 * i] = features[i].pt.x;
+    k[4 * i + 1] = features[i].pt.y;
+    k[4 * i + 2] = features[i].size;
+    k[4 * i + 3] = features[i].angle;
+  }
+  desc.create(n, 128, CV_32F);
+  const int rc = slamb200_sift_compute(context(), frame.data, frame.rows, frame.cols, frame.channels(),
+                                       (size_t)frame.step, k.data(), n, (float*)desc.data, nullptr);
+  if (rc != SLAMB200_OK) throw std::runtime_error(std::string("slamb200_sift_compute: ") + slamb200_last_error());
+  return true;
+}
+
+// featureMatchingCPU.cpp:45-66.  ORB descriptors are computed on the device (bit-identical to
+// cv::ORB); SIFT descriptors of FAST keypoints too (tolerance-pinned, see computeSiftB200), unless
+// the unit is compiled with -DSLAMB200_SIFT_ON_CPU.
 void extractDescriptor(Mat& frame, std::vector<KeyPoint>& features, int matcherType, Mat& desc) {
   cv::Ptr<cv::DescriptorExtractor> extractor;
   switch (matcherType) {
     case SIFT_BF:
     case SIFT_FLANN:
+#ifndef SLAMB200_SIFT_ON_CPU
+      if (computeSiftB200(frame, features, desc)) return;
+#endif
       extractor = cv::SIFT::create();
       break;
     case ORB_BF:

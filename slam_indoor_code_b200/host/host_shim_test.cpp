@@ -82,6 +82,31 @@ int hostshim_extract_orb(const void* frame, int rows, int cols, int channels, si
   }
 }
 
+// extractDescriptor(frame, features, SIFT_BF, desc): returns the number of keypoints left in `features`
+// (SIFT drops none), the descriptor rows (n x 128 floats) in desc_out; -1 on an exception.
+int hostshim_extract_sift(const void* frame, int rows, int cols, int channels, size_t step, const float* kps,
+                          int n, float* desc_out, int cap) {
+  try {
+    cv::Mat f(rows, cols, channels == 3 ? CV_8UC3 : CV_8U, const_cast<void*>(frame), step);
+    std::vector<cv::KeyPoint> features((size_t)n);
+    for (int i = 0; i < n; i++) {
+      features[i].pt.x = kps[4 * i];
+      features[i].pt.y = kps[4 * i + 1];
+      features[i].size = kps[4 * i + 2];
+      features[i].angle = kps[4 * i + 3];
+    }
+    cv::Mat desc;
+    extractDescriptor(f, features, SIFT_BF, desc);
+    if ((int)features.size() > cap || desc.rows != (desc.empty() ? 0 : (int)features.size()) ||
+        (!desc.empty() && (desc.cols != 128 || desc.type() != CV_32F)))
+      return -2;
+    for (int i = 0; i < desc.rows; i++) memcpy(desc_out + (size_t)128 * i, desc.data + (size_t)i * desc.step, 512);
+    return (int)features.size();
+  } catch (...) {
+    return -1;
+  }
+}
+
 // The C++ RANSAC control with a scripted solver and scorer: `n_models[i]` models come out of the
 // i-th minimal sample, model h of the run scores `scores[h]`.  Returns the iterations run; writes
 // every drawn subset and the index of the winning model (or -1).

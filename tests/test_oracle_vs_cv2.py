@@ -174,3 +174,23 @@ def test_fast_detect_bit_exact(h, w, ch, seed, thr, nms):
     got = c_oracle.fast_detect(frame, thr, nms)
     assert np.array_equal(got, ref)
     assert all(k.size == 7.0 and k.angle == -1.0 and k.octave == 0 for k in kps[:50])
+
+
+def test_sift_base_image_and_descriptors_vs_live_cv2():
+    """SIFT extraction on FAST keypoints against live cv2: the working image bit for bit on frames
+    of awkward sizes, the descriptors within the stated tolerance (cv::hal::exp32f / magnitude32f
+    are IPP routines in the wheel and cannot be pinned to the last ulp)."""
+    sigma = float(np.sqrt(np.float32(np.float32(1.6) * np.float32(1.6) - np.float32(0.25))))
+    for rows, cols, ch in ((97, 131, 1), (64, 135, 3), (50, 37, 3), (33, 7, 1), (240, 320, 3)):
+        frame = synth.textured_frame(rows, cols, 6400 + cols, ch)
+        gray = (cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) if ch == 3 else frame).astype(np.float32)
+        assert np.array_equal(c_oracle.sift_base(frame), cv2.GaussianBlur(gray, (0, 0), sigma)), (rows, cols)
+    frame = synth.textured_frame(480, 640, 6401, 3)
+    kps = cv2.FastFeatureDetector_create(20, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16).detect(frame)
+    assert len(kps) > 2000
+    kept, want = cv2.SIFT_create().compute(frame, kps)
+    assert len(kept) == len(kps)                      # SIFT drops no keypoint
+    arr = np.array([[k.pt[0], k.pt[1], k.size, k.angle] for k in kps], np.float32)
+    got = c_oracle.sift_compute(frame, arr)
+    assert np.abs(got - want).max() <= 1.0
+    assert np.mean(got == want) >= 0.999
