@@ -81,6 +81,8 @@ struct Lane {
   // state of the last enqueued batch
   int b_matcher = -1, b_nq = 0, b_pairs = 0, b_cap = 0;
   std::vector<int> b_tn;      // train rows of every pair of the last batch (bounds of trainIdx)
+  cudaStream_t b_stream = nullptr;   // stream of the last lane-0 call (same stream: already ordered)
+  bool b_stream_set = false;
   int s_H = 0, s_pairs = 0;
   int32_t* status = nullptr;  // device status words of the last batch (inside the table block)
   float* dbg = nullptr;  // debug: raw accumulator dump target of the next tcgen05 launch
@@ -1557,9 +1559,11 @@ extern "C" int slamb200_match_batch_enqueue(slamb200_ctx* c, int matcher, const 
   Lane& L = c->lanes[0];
   cudaStream_t s = stream ? (cudaStream_t)stream : L.stream;
   // Lane 0 owns ONE scratch set; the previous batch may have been queued on another stream and
-  // may still be running or unfetched there: order this stream behind it (a no-op in the usual
-  // same-stream case).
-  CU(cudaStreamWaitEvent(s, L.done, 0));
+  // may still be running or unfetched there: order this stream behind it (nothing to do in the
+  // usual same-stream case).
+  if (!L.b_stream_set || L.b_stream != s) CU(cudaStreamWaitEvent(s, L.done, 0));
+  L.b_stream = s;
+  L.b_stream_set = true;
   return enqueue_batch(c, L, s, matcher, q, trains, n_pairs, ratio);
 }
 
@@ -1570,7 +1574,7 @@ extern "C" int slamb200_batch_fetch(slamb200_ctx* c, slamb200_dmatch* out, int c
   std::lock_guard<std::mutex> lk(c->batch_mu);
   Lane& L = c->lanes[0];
   cudaStream_t s = stream ? (cudaStream_t)stream : L.stream;
-  CU(cudaStreamWaitEvent(s, L.done, 0));   // the batch may have been enqueued on another stream
+  if (!L.b_stream_set || L.b_stream != s) CU(cudaStreamWaitEvent(s, L.done, 0));   // enqueued on another stream
   return fetch_batch(L, s, out, cap, n_out);
 }
 
@@ -2169,7 +2173,9 @@ extern "C" int slamb200_score_batch_enqueue(slamb200_ctx* c, const slamb200_pts*
       return fail(SLAMB200_ERR_INVALID, "train keypoint set %d has %d points, its descriptor set %d rows",
                   p, train_pts[p]->n, L.b_tn[(size_t)p]);
   }
-  CU(cudaStreamWaitEvent(s, L.done, 0));   // the match batch may have been enqueued on another stream
+  if (!L.b_stream_set || L.b_stream != s) CU(cudaStreamWaitEvent(s, L.done, 0));   // the match batch ran on another stream
+  L.b_stream = s;   // the next lane-0 call is ordered behind THIS stream's work (L.done is re-recorded below)
+  L.b_stream_set = true;
   // E (unless it is already resident on this device) and the train keypoint pointer table go
   // through the pinned staging area
   const size_t e_bytes = sizeof(double) * 9 * (size_t)P * H;

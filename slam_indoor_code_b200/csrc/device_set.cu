@@ -8,15 +8,75 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
 
 #define SET_MAX 16
 
+// One host thread per member (the reference's search strides its batch with `threadsCount` host
+// threads, batch.cpp:181-201): the members' enqueues and fetches run side by side instead of one
+// after the other on the calling thread.
+struct SetWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has_job = false, done = true, stop = false;
+  int rc = 0;
+  void start() {
+    th = std::thread([this] {
+      for (;;) {
+        std::function<int()> f;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [this] { return has_job || stop; });
+          if (stop) return;
+          f = std::move(job);
+          has_job = false;
+        }
+        const int r = f();
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          rc = r;
+          done = true;
+        }
+        cv.notify_all();
+      }
+    });
+  }
+  void submit(std::function<int()> f) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      job = std::move(f);
+      has_job = true;
+      done = false;
+    }
+    cv.notify_all();
+  }
+  int wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [this] { return done; });
+    return rc;
+  }
+  void shutdown() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    if (th.joinable()) th.join();
+  }
+};
+
 struct slamb200_set {
   int n = 0;
+  SetWorker worker[SET_MAX];   // members 1 .. n-1 (member 0 runs on the calling thread)
   int dev[SET_MAX];
   slamb200_ctx* ctx[SET_MAX];
   cudaStream_t stream[SET_MAX];
@@ -25,8 +85,9 @@ struct slamb200_set {
   // the last enqueued batch: which global pairs each member holds, in its local order
   std::vector<int> part[SET_MAX];
   int b_pairs = 0, b_nq = 0;
-  std::vector<slamb200_dmatch> tmp;   // scatter buffer for members whose pairs are not contiguous
-  std::vector<int> tmp_n;
+  std::vector<slamb200_dmatch> tmp[SET_MAX];   // scatter buffers for members whose pairs are not contiguous
+  std::vector<int> tmp_n[SET_MAX];
+  std::string err[SET_MAX];
 };
 
 struct slamb200_mdesc {
@@ -75,12 +136,31 @@ extern "C" int slamb200_set_init(int n_devices, slamb200_set** out) {
       }
     }
   }
+  for (int i = 1; i < n; i++) s->worker[i].start();
   *out = s;
   return SLAMB200_OK;
 }
 
+// runs f(member) for every member, members 1.. on their worker threads, member 0 here
+template <class F>
+static int for_each_member(slamb200_set* s, F f) {
+  for (int i = 1; i < s->n; i++)
+    s->worker[i].submit([s, f, i] {
+      const int r = f(i);
+      if (r != SLAMB200_OK) s->err[i] = slamb200_last_error();   // the worker thread's message
+      return r;
+    });
+  int rc = f(0);
+  for (int i = 1; i < s->n; i++) {
+    const int r = s->worker[i].wait();
+    if (rc == SLAMB200_OK && r != SLAMB200_OK) rc = set_error(r, s->err[i].c_str());
+  }
+  return rc;
+}
+
 extern "C" int slamb200_set_shutdown(slamb200_set* s) {
   if (!s) return SLAMB200_OK;
+  for (int i = 1; i < s->n; i++) s->worker[i].shutdown();
   for (int i = 0; i < s->n; i++) {
     cudaSetDevice(s->dev[i]);
     cudaStreamSynchronize(s->stream[i]);
@@ -159,41 +239,42 @@ static int set_enqueue(slamb200_set* s, int matcher, const slamb200_mdesc* q,
   }
   s->b_pairs = n_pairs;
   s->b_nq = q->rows;
-  std::vector<const slamb200_desc*> local;
-  for (int i = 0; i < s->n; i++) {
-    local.clear();
+  // enqueue only, every member from its own host thread: all of them start on their share before
+  // the first one is fetched
+  return for_each_member(s, [=](int i) -> int {
+    std::vector<const slamb200_desc*> local;
     for (int p : s->part[i]) local.push_back(trains[p]->d[i]);
     cudaSetDevice(s->dev[i]);
     cudaEventRecord(s->ev0[i], s->stream[i]);
-    // enqueue only: every member starts on its share before the first one is fetched
-    int rc = slamb200_match_batch_enqueue(s->ctx[i], matcher, q->d[i], local.data(), (int)local.size(), ratio,
-                                          (void*)s->stream[i]);
+    const int rc = slamb200_match_batch_enqueue(s->ctx[i], matcher, q->d[i], local.data(), (int)local.size(), ratio,
+                                                (void*)s->stream[i]);
     cudaEventRecord(s->ev1[i], s->stream[i]);
-    if (rc != SLAMB200_OK) return rc;
-  }
-  return SLAMB200_OK;
+    return rc;
+  });
 }
 
 static int set_fetch(slamb200_set* s, slamb200_dmatch* out, int cap, int* n_out, float* device_ms) {
   if (s->b_pairs > 0 && !n_out) return SLAMB200_ERR_INVALID;
-  for (int i = 0; i < s->n; i++) {
+  return for_each_member(s, [=](int i) -> int {
     const std::vector<int>& part = s->part[i];
     if (device_ms) device_ms[i] = 0.f;
-    if (part.empty()) continue;
+    if (part.empty()) return SLAMB200_OK;
     cudaSetDevice(s->dev[i]);
     bool contiguous = true;
     for (size_t k = 1; k < part.size(); k++) contiguous = contiguous && part[k] == part[k - 1] + 1;
     int rc;
-    if (contiguous) {
+    if (contiguous) {   // the usual placement: the member's results land where they belong
       rc = slamb200_batch_fetch(s->ctx[i], out ? out + (size_t)part[0] * cap : nullptr, cap, n_out + part[0],
                                 (void*)s->stream[i]);
     } else {
-      s->tmp.resize(part.size() * (size_t)cap);
-      s->tmp_n.resize(part.size());
-      rc = slamb200_batch_fetch(s->ctx[i], s->tmp.data(), cap, s->tmp_n.data(), (void*)s->stream[i]);
+      std::vector<slamb200_dmatch>& tmp = s->tmp[i];
+      std::vector<int>& tmp_n = s->tmp_n[i];
+      tmp.resize(part.size() * (size_t)cap);
+      tmp_n.resize(part.size());
+      rc = slamb200_batch_fetch(s->ctx[i], tmp.data(), cap, tmp_n.data(), (void*)s->stream[i]);
       for (size_t k = 0; rc == SLAMB200_OK && k < part.size(); k++) {
-        n_out[part[k]] = s->tmp_n[k];
-        if (out) memcpy(out + (size_t)part[k] * cap, s->tmp.data() + k * (size_t)cap, sizeof(slamb200_dmatch) * (size_t)s->tmp_n[k]);
+        n_out[part[k]] = tmp_n[k];
+        if (out) memcpy(out + (size_t)part[k] * cap, tmp.data() + k * (size_t)cap, sizeof(slamb200_dmatch) * (size_t)tmp_n[k]);
       }
     }
     if (rc != SLAMB200_OK) return rc;
@@ -201,8 +282,8 @@ static int set_fetch(slamb200_set* s, slamb200_dmatch* out, int cap, int* n_out,
       cudaEventSynchronize(s->ev1[i]);
       cudaEventElapsedTime(&device_ms[i], s->ev0[i], s->ev1[i]);
     }
-  }
-  return SLAMB200_OK;
+    return SLAMB200_OK;
+  });
 }
 
 extern "C" int slamb200_set_match_batch_enqueue(slamb200_set* s, int matcher, const slamb200_mdesc* q,

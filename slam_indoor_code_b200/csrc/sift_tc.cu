@@ -58,7 +58,7 @@ constexpr int AUG_OFF = 2 * KBLK;   // K-augmentation block behind the two k-blo
 constexpr int STAGE = 2 * KBLK + 128 * 32;  // 36864: one 128-row operand stage (A or B half)
 constexpr int N_ASTAGE = 2;
 constexpr int N_BSTAGE = 4;
-constexpr int SMEM_BARS = 1024;
+constexpr int SMEM_BARS = 3072;     // mbarriers, the TMEM base slot, and the 2 KB record-exchange area
 constexpr int SMEM_BYTES = (N_ASTAGE + N_BSTAGE) * STAGE + SMEM_BARS + 1024;
 // general-float variant: operands carry a hi and a lo bf16 half (two-term split), 24 + 1 MMAs per
 // tile: hi.hi + hi.lo + lo.hi + augmentation
@@ -751,7 +751,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
           if (lane == 0) atomicOr(P.err_flag, 2);
           ord = 0;
         }
-        const int slot = COL_SPLITS * ord + half;
+        const int slot = GEN ? COL_SPLITS * ord + half : ord;   // exact mode: the halves are merged below
         const size_t at = ((size_t)seg_pair * P.n_slots + slot) * P.nq_pad + seg_rb * 2 * BM + row_in_tile;
         if (GEN) {
           // two 16-byte records: the four chunk minima; their group indices and the two bounds
@@ -761,10 +761,39 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
                                           ((uint32_t)st.i[2] & 0xFFFFu) | ((uint32_t)st.i[3] << 16),
                                           __float_as_uint(st.s), __float_as_uint(st.s2));
         } else {
+          // The two warps that share these rows (column halves of every tile) combine their
+          // records through shared memory: ONE record per (share, row) reaches HBM instead of two
+          // (half the slot-record traffic of the kernel and of the tail behind it).
           // {best chunk min, second chunk min, second group min inside the best chunk,
           //  gid of the best | gid of the second << 16}; 0xFFFF = absent (gids fit: T <= 524k rows)
-          P.cand[at] = make_uint4(__float_as_uint(st.m[0]), __float_as_uint(st.m[1]), __float_as_uint(st.s),
-                                  ((uint32_t)st.i[0] & 0xFFFFu) | ((uint32_t)st.i[1] << 16));
+          uint4* xch = reinterpret_cast<uint4*>(smem_gen + (NA + NB) * STG + 1024) + quarter * 32 + lane;
+          if (half == 1)
+            *xch = make_uint4(__float_as_uint(st.m[0]), __float_as_uint(st.m[1]), __float_as_uint(st.s),
+                              ((uint32_t)st.i[0] & 0xFFFFu) | ((uint32_t)st.i[1] << 16));
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+          if (half == 0) {
+            const uint4 o = *xch;
+            float am0 = st.m[0], am1 = st.m[1], as = st.s;
+            int ag0 = st.i[0] & 0xFFFF, ag1 = st.i[1] & 0xFFFF;
+            const float bm0 = __uint_as_float(o.x), bm1 = __uint_as_float(o.y), bs = __uint_as_float(o.z);
+            const int bg0 = (int)(o.w & 0xFFFFu), bg1 = (int)(o.w >> 16);
+            // (value, group) lexicographic order; an absent entry is (+inf, 0xFFFF) and loses every tie
+            const bool b_first = bm0 < am0 || (bm0 == am0 && bg0 < ag0);
+            float m0, m1, sv;
+            int g0, g1;
+            if (b_first) {
+              m0 = bm0; g0 = bg0; sv = bs;
+              const bool own = bm1 < am0 || (bm1 == am0 && bg1 < ag0);   // winner's second vs loser's best
+              m1 = own ? bm1 : am0; g1 = own ? bg1 : ag0;
+            } else {
+              m0 = am0; g0 = ag0; sv = as;
+              const bool own = am1 < bm0 || (am1 == bm0 && ag1 < bg0);
+              m1 = own ? am1 : bm0; g1 = own ? ag1 : bg0;
+            }
+            P.cand[at] = make_uint4(__float_as_uint(m0), __float_as_uint(m1), __float_as_uint(sv),
+                                    (uint32_t)g0 | ((uint32_t)g1 << 16));
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // the exchange slot may be rewritten
         }
       }
     }
@@ -839,7 +868,7 @@ __global__ void __launch_bounds__(256) sift_merge_kernel(const RerankParams R) {
       const int n_cb = n_tiles / n_rb;
       const int first = owner_cta(n_tiles, R.n_cta, blockIdx.x * n_cb, R.wide != 0);
       const int last = owner_cta(n_tiles, R.n_cta, (blockIdx.x + 1) * n_cb - 1, R.wide != 0);
-      nv = COL_SPLITS * (last - first + 1);
+      nv = last - first + 1;               // one merged record per share (the kernel's flush)
       if (nv > R.n_slots) nv = R.n_slots;  // cannot happen (host sizing); the self check would trip
     }
     n_valid_s = nv;
@@ -1242,7 +1271,7 @@ tc_tail_fused_kernel(const RerankParams R, int32_t* __restrict__ knn_idx, float*
         const int n_cb = n_tiles / n_rb;
         const int first = owner_cta(n_tiles, R.n_cta, blockIdx.x * n_cb, R.wide != 0);
         const int last = owner_cta(n_tiles, R.n_cta, (blockIdx.x + 1) * n_cb - 1, R.wide != 0);
-        nv = COL_SPLITS * (last - first + 1);
+        nv = last - first + 1;               // one merged record per share
         if (nv > R.n_slots) nv = R.n_slots;
       }
       n_valid_s = nv;
