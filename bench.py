@@ -247,8 +247,12 @@ def run_b200(args, rank, world, local):
     from slam_indoor_code_b200.feature_matching import Context, MatcherType
 
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a host-side barrier for the section in which rank 0 alone drives every GPU: an NCCL barrier
+        # would leave a spinning kernel on the other ranks' GPUs for as long as they wait
+        cpu_group = dist.new_group(backend="gloo")
     dev = torch.device("cuda", local)
     torch.zeros(1, device=dev)
 
@@ -272,9 +276,9 @@ def run_b200(args, rank, world, local):
         os.environ["SLAMB200_HOST_NARROWERS"] = str(args.e2e_uploaders)   # read once by the library, before its first host call
     if args.e2e_upload == "auto":
         args.e2e_upload = "packed"
-    # host threads of this rank that narrow Mats inside the library: its cores minus the submitter,
-    # the matching caller and one for the driver
-    pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else max(0, min(cores, 27) - 4)
+    # host threads of this rank that narrow Mats inside the library (pack_threads + 1 of them): its
+    # cores minus one -- the submitting and the matching thread mostly wait
+    pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else max(0, min(cores, 25) - 2)
     ctx.set_pack_threads(pack_threads)
     # A real (non-default) stream: the C ABI treats a NULL stream as "the lane's own stream", so
     # the kernels and the CUDA events that time them must share an explicit stream handle.
@@ -372,8 +376,13 @@ def run_b200(args, rank, world, local):
                 "kernel_share_of_step": tc_ms / ms_total
                 if world == 1 else None,
                 "traffic": TRAFFIC_BYTES_PER_LAUNCH_N1 if world == 1 else None,
-                "traffic_note": "ncu capture of the N=1 launch (profiles/r01_ncu_sift_tc_final.txt); "
-                                "compulsory bytes 818 MB"}
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 210-pair launch, ncu --set full "
+                                "(profiles/r02/r02_ncu_final_sift_tc_tail_compact.txt): 617.0 MB read + 93.6 MB written; "
+                                "algorithmic bytes 574 MB (211 bf16 sets 540 MB + 33.6 MB of results) + 103 MB of "
+                                "slot records the tail consumes",
+                "tensor_pipe_active_pct": 88.2 if world == 1 else None,
+                "tensor_pipe_note": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed of the same "
+                                    "launch (profiles/r02/r02_ncu_tensor_pipe.txt)"}
 
     # ---- e2e through the C ABI with host buffers -------------------------------------------------
     for t in Ts:
@@ -468,7 +477,8 @@ def run_b200(args, rank, world, local):
     shared = None
     if not args.no_extras:
         try:
-            shared = multi_rank_extras(ctx, stream, rank, world, local, dev, pairs, q, trains, matches, barrier)
+            shared = multi_rank_extras(ctx, stream, rank, world, local, dev, pairs, q, trains, matches, barrier,
+                                       cpu_group)
         except Exception as e:  # pragma: no cover
             shared = {"error": repr(e)}
             log(f"[rank {rank}] multi-rank extras failed: {e!r}")
@@ -523,7 +533,7 @@ def run_b200(args, rank, world, local):
 # RANSAC essential scoring over the rank's share of the window, keypoints consistent with the
 # planted correspondences), cfg4 (8 x 50k-row keyframe window) through both exchange forms with
 # a self-check against the single-GPU result, and the in-process device set on rank 0.
-def multi_rank_extras(ctx, stream, rank, world, local, dev, pairs, q, trains, matches, barrier):
+def multi_rank_extras(ctx, stream, rank, world, local, dev, pairs, q, trains, matches, barrier, cpu_group=None):
     import torch
     import torch.distributed as dist
     import synth_inputs as synth
@@ -639,7 +649,8 @@ def multi_rank_extras(ctx, stream, rank, world, local, dev, pairs, q, trains, ma
         res4["ranks_that_ran"] = world
     out["cfg4_window_8x50k"] = res4
 
-    # ---- one process, all GPUs: the device set (rank 0 drives every GPU, the other ranks wait) -------
+    # ---- one process, all GPUs: the device set (rank 0 drives every GPU; the other ranks wait on the
+    # HOST, their GPUs idle) ------------------------------------------------------------------------
     barrier()
     if rank == 0:
         try:
@@ -674,6 +685,8 @@ def multi_rank_extras(ctx, stream, rank, world, local, dev, pairs, q, trains, ma
                     h.free()
         except Exception as e:  # pragma: no cover
             out["inprocess_device_set"] = {"error": repr(e)}
+    if cpu_group is not None:
+        dist.barrier(group=cpu_group)
     barrier()
     return out
 
@@ -687,10 +700,11 @@ def _window_single(ctx, frames, F):
     return res, [len(res[p]) for p in sorted(res)]
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one tcgen05-kernel launch over the 210-pair window
-# (N=1), from the committed `ncu --set full` capture profiles/r01_ncu_sift_tc_final.txt:
-# 631.2 MB read + 185.1 MB written.  Compulsory bytes of that launch: 211 descriptor sets x 2.9 MB
-# of bf16 operands + 206 MB of slot records = 818 MB, i.e. no re-reads.
-TRAFFIC_BYTES_PER_LAUNCH_N1 = 816_323_072
+# (N=1), from the committed `ncu --set full` capture profiles/r02/r02_ncu_final_sift_tc_tail_compact.txt:
+# 616.95 MB read + 93.59 MB written.  Compulsory bytes of that launch: 211 descriptor sets x 2.9 MB
+# of bf16 operands (two 1.28 MB k-blocks + augmentation per set) + 103 MB of slot records
+# (one per share and row) = 0.71 GB, i.e. no re-reads.
+TRAFFIC_BYTES_PER_LAUNCH_N1 = 710_546_688
 
 
 def cpu_baseline(q, trains, gpu_matches, seconds):

@@ -23,6 +23,8 @@
  *       linear triangulation        src/mainModule/triangulation/triangulate.cpp:17-55, :91-108
  *       ORB descriptors (compute)   src/mainModule/featureMatching/featureMatchingCPU.cpp:45-66
  *       FAST keypoints (detect)     src/mainModule/featureExtraction/fastExtractor.cpp:7-13
+ *       SIFT descriptors (compute)  src/mainModule/featureMatching/featureMatchingCPU.cpp:45-66
+ *           (working image pinned bit for bit; descriptors pinned to a TOLERANCE, see its block)
  *
  * Parity pin: the reference ships no tests or golden vectors, so this
  * oracle is pinned against the reference's own arithmetic owner, OpenCV, through the cv2 wheel
@@ -30,7 +32,7 @@
  * oracle/gen_golden.py).
  *
  * Build: see oracle/Makefile (-O2 -ffp-contract=off: no FMA contraction anywhere in here; the one
- * place OpenCV's own code fuses -- ORB's float blur -- calls fmaf explicitly).
+ * places OpenCV's own code fuses -- ORB's and SIFT's float blurs -- call fmaf explicitly).
  */
 #include <math.h>
 #include <stdint.h>

@@ -144,6 +144,15 @@ extern "C" int slamb200_set_init(int n_devices, slamb200_set** out) {
 // runs f(member) for every member, members 1.. on their worker threads, member 0 here
 template <class F>
 static int for_each_member(slamb200_set* s, F f) {
+  static const bool threads = [] { const char* e = getenv("SLAMB200_SET_THREADS"); return !e || atoi(e) != 0; }();
+  if (!threads) {   // everything on the calling thread, member after member
+    int rc = SLAMB200_OK;
+    for (int i = 0; i < s->n; i++) {
+      const int r = f(i);
+      if (rc == SLAMB200_OK) rc = r;
+    }
+    return rc;
+  }
   for (int i = 1; i < s->n; i++)
     s->worker[i].submit([s, f, i] {
       const int r = f(i);
