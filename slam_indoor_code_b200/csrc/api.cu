@@ -61,7 +61,8 @@ struct Lane {
   std::vector<cudaEvent_t> sub_ev;
   bool busy = false;
   // matching scratch (device)
-  DevBuf pairs, tcpairs, tile_prefix, part, cand, cand_g, work, work_v0, fb_list, knn_idx, knn_dist, flags, chunk_cnt, out, n_out, err_flag;
+  DevBuf pairs, tcpairs, tile_prefix, part, cand, cand_g, work, work_v0, fb_list, knn_idx, knn_dist, flags, chunk_cnt, out, n_out, err_flag, scan, seg_done, status_fixed;
+  uint32_t scan_epoch = 0;           // launches that have used `scan` (look-back words carry it)
   // scoring scratch (device)
   DevBuf npts, E, counts, best, mask, m_off, p1, p2, txy, all_masks;
   DevBuf orb_img, orb_gray, orb_rowf, orb_blur, orb_kp, orb_desc;
@@ -184,7 +185,12 @@ struct slamb200_ctx {
   bool pack_started = false;
   int sub_batch = 0;  // debug: pairs per tcgen05 launch when pipelining against the rerank
   int use_tc = 1;  // debug switch (slamb200_dbg_set_tc): 0 routes exact-mode pairs to the fp32 kernel
-  int fused_tail = 1;  // debug switch (slamb200_dbg_set_fused_tail): 0 = separate merge / rerank / finalize kernels
+  int fused_tail = -1;  // form of the match path's tail (debug switch slamb200_dbg_set_fused_tail):
+                        // 0 = separate merge / rerank / finalize kernels, 1 = one tail kernel + compaction kernel,
+                        // 2 = tail and compaction in one kernel (look-back), 3 = experimental: the tail inside the
+                        // tcgen05 kernel where the batch allows it (else as 2) -- correct, measured slower;
+                        // -1 (default) = by batch size: 2 up to 32 pairs (one launch and ~11 us less per call),
+                        // 1 beyond (the look-back keeps blocks resident: +0.07 ms per 210-pair window)
   int use_tc_orb = 1;  // debug switch (slamb200_dbg_set_tc_orb): 0 routes ORB pairs to the XOR/POPC kernel
 };
 
@@ -284,6 +290,7 @@ extern "C" int slamb200_init(int device, slamb200_ctx** out) {
   if (!c) return fail(SLAMB200_ERR_NOMEM, "host allocation failed");
   c->device = device;
   c->n_sm = prop.multiProcessorCount;
+  if (const char* e = getenv("SLAMB200_TAIL_FORM")) c->fused_tail = atoi(e);   // developer switch, see fused_tail
   cudaMemPoolProps pp;
   memset(&pp, 0, sizeof(pp));
   pp.allocType = cudaMemAllocationTypePinned;
@@ -333,7 +340,7 @@ extern "C" int slamb200_shutdown(slamb200_ctx* c) {
   for (int i = 0; i < N_LANES; i++) {
     Lane& L = c->lanes[i];
     DevBuf* bufs[] = {&L.pairs, &L.tcpairs, &L.tile_prefix, &L.work, &L.work_v0, &L.fb_list, &L.cand_g, &L.part, &L.cand, &L.knn_idx, &L.knn_dist, &L.flags,
-                      &L.chunk_cnt, &L.out, &L.n_out, &L.err_flag, &L.npts, &L.E, &L.counts,
+                      &L.chunk_cnt, &L.out, &L.n_out, &L.err_flag, &L.scan, &L.seg_done, &L.status_fixed, &L.npts, &L.E, &L.counts,
                       &L.best, &L.mask, &L.m_off, &L.p1, &L.p2, &L.txy, &L.all_masks,
                       &L.orb_img, &L.orb_gray, &L.orb_rowf, &L.orb_blur, &L.orb_kp, &L.orb_desc,
                       &L.fast_score, &L.fast_cnt, &L.fast_kp, &L.sift_rowf, &L.sift_base, &L.sift_kp, &L.sift_desc};
@@ -1047,18 +1054,34 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   const int q_blocks = orb ? (nq + 255) / 256 : (nq + 15) / 16;
   const int n_split = pick_splits(q_blocks > 0 ? q_blocks : 1, n_pairs, t_max, orb ? 1024 : 512);
 
+  // the exact fp32 kernel is not even launched when every set is known (on the host) to be in
+  // exact mode; sets whose flag has not been read back yet leave the decision to the device
+  bool all_exact_known = orb || q->host_exact == 1;
+  for (int p = 0; p < n_pairs && all_exact_known && !orb; p++) all_exact_known = trains[p]->host_exact == 1;
+  // Small batches of known kind on the one-kernel tail (the per-pair drop-in call): the pair table
+  // travels in the kernel parameters and the status words live in a buffer that stays zero, so the
+  // call queues no copy at all in front of its two kernels.
+  const int tail_form = c->fused_tail >= 0 ? c->fused_tail : (n_pairs <= 32 ? 2 : 1);
+  const bool inline_tables = tc && n_pairs <= tc_inline_max() && all_exact_known && !want_knn &&
+                             tail_form >= 2 && !(c->sub_batch > 0 && c->sub_batch < n_pairs);
+
   // ---- host tables -----------------------------------------------------------------------
   const size_t off_pairs = 0;
   const size_t off_tc = align_up(sizeof(PairArgs) * (size_t)n_pairs, 64);
   const size_t off_pre = off_tc + (tc ? sizeof(TcPair) * (size_t)n_pairs : 0);
   const size_t off_status = align_up(off_pre + (tc ? sizeof(int32_t) * (size_t)(n_pairs + 1) : 0), 64);
   const size_t table_bytes = off_status + STATUS_BYTES;
-  if ((rc = stage_reserve(L, table_bytes))) return rc;
-  char* hb = (char*)L.h_stage;
+  alignas(64) char inline_buf[4096];
+  static_assert(sizeof(inline_buf) >= 64 + (sizeof(PairArgs) + sizeof(TcPair) + 4) * 4 + 128, "inline table buffer");
+  char* hb = inline_buf;
+  if (!inline_tables) {
+    if ((rc = stage_reserve(L, table_bytes))) return rc;
+    hb = (char*)L.h_stage;
+    memset(hb + off_status, 0, STATUS_BYTES);
+  }
   PairArgs* hp = (PairArgs*)(hb + off_pairs);
   TcPair* tp = (TcPair*)(hb + off_tc);
   int32_t* pre = (int32_t*)(hb + off_pre);
-  memset(hb + off_status, 0, STATUS_BYTES);
   for (int p = 0; p < n_pairs; p++) {
     hp[p].t_rows = orb ? (const void*)trains[p]->u8 : (const void*)trains[p]->f32;
     hp[p].t_flags = orb ? nullptr : trains[p]->flags;
@@ -1069,6 +1092,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   // tcgen05 path geometry: one query block of 256 rows per CTA pair, 256-column train tiles
   const int n_rb = (nq + 255) / 256;
   int n_cta = 1, n_slots = 2, wide = 0;
+  int min_cb = 1 << 30;   // column tiles of the smallest train set of the batch
   bool holes = false;
   if (tc) {
     long long total = 0;
@@ -1093,6 +1117,7 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
       tp[p].t_n = trains[p]->n;
       tp[p].t_pad = trains[p]->n_pad;
       const int n_cb = (trains[p]->n + 255) / 256;
+      min_cb = n_cb < min_cb ? n_cb : min_cb;
       pre[p] = (int32_t)total;
       total += (long long)n_cb * n_rb;
       // every CTA pair takes a contiguous share of this frame pair's tiles: how many shares can
@@ -1111,7 +1136,14 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
   // ---- device scratch ----------------------------------------------------------------------
   const size_t rows = (size_t)n_pairs * cap;
   const size_t cand_bytes = tc ? sizeof(uint4) * (size_t)n_pairs * n_slots * (size_t)n_rb * 256 : 0;
-  if ((rc = buf_reserve(c, L.pairs, table_bytes, s))) return rc;
+  if (inline_tables) {
+    if (!L.status_fixed.p) {
+      if ((rc = buf_reserve(c, L.status_fixed, STATUS_BYTES, s))) return rc;
+      CU(cudaMemsetAsync(L.status_fixed.p, 0, L.status_fixed.cap, s));
+    }
+  } else if ((rc = buf_reserve(c, L.pairs, table_bytes, s))) {
+    return rc;
+  }
   if ((rc = buf_reserve(c, L.part, sizeof(uint4) * rows * n_split, s))) return rc;
   if ((rc = buf_reserve(c, L.knn_idx, sizeof(int32_t) * rows * 2, s))) return rc;
   if ((rc = buf_reserve(c, L.knn_dist, sizeof(float) * rows * 2, s))) return rc;
@@ -1127,13 +1159,17 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     if ((rc = buf_reserve(c, L.fb_list, FB_PART_BYTES + sizeof(uint2) * rows, s))) return rc;
   }
   char* db = (char*)L.pairs.p;
-  const PairArgs* d_pairs = (const PairArgs*)(db + off_pairs);
-  const TcPair* d_tc = (const TcPair*)(db + off_tc);
-  const int32_t* d_pre = (const int32_t*)(db + off_pre);
-  int32_t* d_status = (int32_t*)(db + off_status);
+  const PairArgs* d_pairs = inline_tables ? nullptr : (const PairArgs*)(db + off_pairs);
+  const TcPair* d_tc = inline_tables ? nullptr : (const TcPair*)(db + off_tc);
+  const int32_t* d_pre = inline_tables ? nullptr : (const int32_t*)(db + off_pre);
+  int32_t* d_status = inline_tables ? (int32_t*)L.status_fixed.p : (int32_t*)(db + off_status);
+  const TcPair* inl_tc = inline_tables ? tp : nullptr;
+  const int32_t* inl_pre = inline_tables ? pre : nullptr;
   L.status = d_status;
-  CU(cudaMemcpyAsync(db, hb, table_bytes, cudaMemcpyHostToDevice, s));
-  CU(cudaEventRecord(L.stage_free, s));
+  if (!inline_tables) {
+    CU(cudaMemcpyAsync(db, hb, table_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaEventRecord(L.stage_free, s));
+  }
 
   // the descriptor sets must have finished their prep kernels
   {
@@ -1147,11 +1183,6 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
     CU(wait_ready(q));
     for (int p = 0; p < n_pairs; p++) CU(wait_ready(trains[p]));
   }
-  // the exact fp32 kernel is not even launched when every set is known (on the host) to be in
-  // exact mode; sets whose flag has not been read back yet leave the decision to the device
-  bool all_exact_known = orb || q->host_exact == 1;
-  for (int p = 0; p < n_pairs && all_exact_known && !orb; p++) all_exact_known = trains[p]->host_exact == 1;
-
   if (orb && !tc) {
     ProfScope ps(c, s, SLAMB200_K_ORB);
     launch_orb_knn2(q->u8, nq, d_pairs, n_pairs, n_split, (uint4*)L.part.p, s);
@@ -1230,19 +1261,61 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         const int tiles_k = pre[p0 + np] - pre[p0];
         uint4* cand_k = (uint4*)L.cand.p + (size_t)p0 * cand_per_pair;
         uint4* part_k = (uint4*)L.part.p + (size_t)p0 * n_split * nq;
+        // look-back words of the ordered compaction (both one-kernel forms of the tail): one per
+        // (pair, row block, CTA of the pair), cleared only when (re)allocated -- the epoch tells
+        // the launches apart
+        if (tail_form >= 2 && !want_knn) {
+          const size_t scan_bytes = sizeof(unsigned long long) * (size_t)n_pairs * chunks * 2;
+          if (scan_bytes > L.scan.cap || !L.scan.p || L.scan_epoch >= (1u << 30) - 2) {
+            if ((rc = buf_reserve(c, L.scan, scan_bytes, s))) return rc;
+            CU(cudaMemsetAsync(L.scan.p, 0, L.scan.cap, s));
+            L.scan_epoch = 0;
+          }
+        }
+        // The whole match path in one kernel: every pair integer-valued (or ORB) and known to be so
+        // on the host, no empty shares, and row blocks long enough (>= 12 column tiles) for the two
+        // tail warps of a CTA to keep up with its epilogue.
+        if (tail_form >= 3 && !want_knn && !none_exact && all_exact_known && !holes && min_cb >= 12 &&
+            n_sub == 1) {
+          const size_t done_bytes = sizeof(int32_t) * (size_t)n_pairs * chunks * 2;
+          if (done_bytes > L.seg_done.cap || !L.seg_done.p) {
+            if ((rc = buf_reserve(c, L.seg_done, done_bytes, s))) return rc;
+            CU(cudaMemsetAsync(L.seg_done.p, 0, L.seg_done.cap, s));
+          }
+          ProfScope ps(c, s, orb ? SLAMB200_K_ORB : SLAMB200_K_SIFT_TC);
+          const int mrc = launch_sift_tc_match(qmaps, q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, tiles_k, n_cta,
+                                               n_slots, cand_k, d_status, ratio, orb ? 1 : 0, wide,
+                                               (unsigned long long*)L.scan.p, ++L.scan_epoch,
+                                               (int32_t*)L.seg_done.p, (slamb200_dmatch*)L.out.p, cap,
+                                               (int32_t*)L.n_out.p, s, inl_tc, inl_pre);
+          if (mrc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
+          continue;
+        }
         int trc = 0;
         if (!none_exact) {
           ProfScope ps(c, s, orb ? SLAMB200_K_ORB : SLAMB200_K_SIFT_TC);
           trc = launch_sift_tc_candidates(qmaps, q->flags, nq, tcp, pre_k, np, tiles_k, n_cta,
                                           n_slots, cand_k, d_status, k == 0 ? L.dbg : nullptr, 0, s,
-                                          orb ? 1 : 0, all_exact_known ? 1 : 0, wide);
+                                          orb ? 1 : 0, all_exact_known ? 1 : 0, wide, inl_tc, inl_pre);
         }
         if (trc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
         if (s2 != s) {
           CU(cudaEventRecord(L.sub_ev[k], s));
           CU(cudaStreamWaitEvent(s2, L.sub_ev[k], 0));
         }
-        if (c->fused_tail && !want_knn) {
+        if (tail_form >= 2 && !want_knn) {
+          // match output: merge, best-group rerank, ratio test AND the ordered compaction in one
+          // kernel (look-back over the 256-row blocks of a pair); general-float pairs of the batch
+          // are finalized by the same kernel from their records
+          ProfScope ps(c, s2, orb ? SLAMB200_K_ORB : SLAMB200_K_SIFT_RERANK);
+          launch_tc_tail_compact(q->flags, q->u8, q->nrm2, nq, tcp, pre_k, np, n_cta, n_slots, n_split,
+                                 cand_k, part_k, d_status, ratio, orb ? 1 : 0,
+                                 (unsigned long long*)L.scan.p + (size_t)p0 * chunks, ++L.scan_epoch,
+                                 (slamb200_dmatch*)L.out.p + (size_t)p0 * cap, cap, (int32_t*)L.n_out.p + p0, s2,
+                                 wide, inl_tc, inl_pre);
+          continue;
+        }
+        if (tail_form >= 1 && !want_knn) {
           // match output: merge, best-group rerank and ratio test in one kernel, then compaction
           // (general-float pairs of the batch are finalized by the same kernel from their records)
           {
@@ -1328,6 +1401,7 @@ static int fetch_batch(Lane& L, cudaStream_t s, slamb200_dmatch* out, int out_ca
   CU(cudaMemcpyAsync(L.h_small + 1, L.n_out.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(L.h_small, L.status, 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  if (L.h_small[0] != 0) cudaMemsetAsync(L.status, 0, 4, s);   // (the status words of small batches persist)
   if (L.h_small[0] != 0)
     return fail(SLAMB200_ERR_INTERNAL, "device self-check failed (flag %d): tensor-core candidates "
                 "disagree with the exact rerank", L.h_small[0]);
@@ -2290,7 +2364,7 @@ extern "C" int slamb200_dbg_set_tc(slamb200_ctx* c, int on) {
 
 extern "C" int slamb200_dbg_set_fused_tail(slamb200_ctx* c, int on) {
   if (!c) return SLAMB200_ERR_INVALID;
-  c->fused_tail = on ? 1 : 0;
+  c->fused_tail = on;   // see slamb200_ctx::fused_tail (-1 = by batch size)
   return SLAMB200_OK;
 }
 

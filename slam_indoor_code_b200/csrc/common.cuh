@@ -232,7 +232,8 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_fl
                               const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                               int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
                               int32_t* err_flag, float* dbg, int gen, cudaStream_t s, int fp8 = 0,
-                              int kinds_known = 0, int wide = 0);
+                              int kinds_known = 0, int wide = 0, const TcPair* inl_pairs_host = nullptr,
+                              const int32_t* inl_prefix_host = nullptr);
 void launch_sift_gen_rerank(const int32_t* q_flags, const float* q_f32, const float* q_nrmf, int nq,
                             const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
                             int n_cta_pairs, int n_slots, int n_split, const uint4* cand, uint4* part,
@@ -255,6 +256,28 @@ void launch_tc_tail_fused(const int32_t* q_flags, const uint8_t* q_u8, const int
 void launch_compact(int nq, int n_pairs, const int32_t* knn_idx, const float* knn_dist,
                     const uint8_t* flags, const int32_t* chunk_cnt, slamb200_dmatch* out, int cap,
                     int32_t* n_out, cudaStream_t s);
+// candidates AND tail in one kernel (exact-mode / ORB match output, no empty shares, kinds known):
+// scan and seg_done hold one entry per (pair, 256-row block, CTA of the pair), zeroed when allocated
+int launch_sift_tc_match(const void* q_tmaps_host_384B, const int32_t* q_flags, const uint8_t* q_u8,
+                         const int32_t* q_nrm2, int nq, const TcPair* pairs_dev,
+                         const int32_t* tile_prefix_dev, int n_pairs, int total_tiles, int n_cta_pairs,
+                         int n_slots, uint4* cand, int32_t* err_flag, double ratio, int fp8, int wide,
+                         unsigned long long* scan, uint32_t epoch, int32_t* seg_done, slamb200_dmatch* out,
+                         int cap, int32_t* n_out, cudaStream_t s, const TcPair* inl_pairs_host = nullptr,
+                         const int32_t* inl_prefix_host = nullptr);
+// batches of up to tc_inline_max() pairs may pass their tables on the host (inl_*_host): they travel
+// in the kernel parameters and pairs_dev / tile_prefix_dev are not read
+int tc_inline_max();
+// the same tail and the ordered compaction (decoupled look-back) in ONE kernel: match lists land in
+// out / n_out.  scan: one 64-bit word per (pair, 256-row block), zeroed when allocated; epoch in
+// 1 .. 2^30 - 1, different for every launch that shares `scan`
+void launch_tc_tail_compact(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
+                            const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                            int n_cta_pairs, int n_slots, int n_split, const uint4* cand, const uint4* part,
+                            int32_t* err_flag, double ratio, int orb, unsigned long long* scan,
+                            uint32_t epoch, slamb200_dmatch* out, int cap, int32_t* n_out, cudaStream_t s,
+                            int wide = 0, const TcPair* inl_pairs_host = nullptr,
+                            const int32_t* inl_prefix_host = nullptr);
 // ORB rows -> tcgen05 operands (sift_prep.cu): e4m3 0/1 bytes [n_pad][256] and the two
 // augmentation blocks [n_pad/8][256 B]
 void launch_orb_tc_prep(const uint8_t* u8, int n, int n_pad, uint8_t* e4, uint8_t* augq,

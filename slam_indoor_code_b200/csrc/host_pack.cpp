@@ -9,10 +9,12 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 
 #if defined(__x86_64__)
 #include <immintrin.h>
 
+template <bool NT>
 __attribute__((target("avx2"))) static int pack_rows_avx2(const float* src, size_t stride, int n,
                                                           uint8_t* dst) {
   __m256i bad = _mm256_setzero_si256();
@@ -39,7 +41,11 @@ __attribute__((target("avx2"))) static int pack_rows_avx2(const float* src, size
       const __m256i p01 = _mm256_packs_epi32(i0, i1), p23 = _mm256_packs_epi32(i2, i3);
       sq = _mm256_add_epi32(sq, _mm256_add_epi32(_mm256_madd_epi16(p01, p01), _mm256_madd_epi16(p23, p23)));
       const __m256i p = _mm256_permutevar8x32_epi32(_mm256_packus_epi16(p01, p23), perm);
-      _mm256_storeu_si256((__m256i*)(d + i), p);
+      // NT: the staging buffer is written once and next read by the GPU over PCIe -- streaming
+      // stores spare the read-for-ownership of every destination line (a quarter of the bytes
+      // this loop moves) and keep the fp32 source from being evicted by its own output
+      if (NT) _mm256_stream_si256((__m256i*)(d + i), p);
+      else _mm256_storeu_si256((__m256i*)(d + i), p);
     }
     __m128i h = _mm_add_epi32(_mm256_castsi256_si128(sq), _mm256_extracti128_si256(sq, 1));
     h = _mm_add_epi32(h, _mm_shuffle_epi32(h, 0x4e));
@@ -48,6 +54,7 @@ __attribute__((target("avx2"))) static int pack_rows_avx2(const float* src, size
     // a Mat of general floats is recognised within its first rows: stop reading it
     if ((r & 63) == 63 && (norm_bad || !_mm256_testz_si256(bad, bad))) return 0;
   }
+  if (NT) _mm_sfence();
   return _mm256_testz_si256(bad, bad) && !norm_bad;
 }
 #endif
@@ -76,7 +83,11 @@ static int pack_rows_scalar(const float* src, size_t stride, int n, uint8_t* dst
 extern "C" int slamb200_host_pack_u8(const float* src, size_t stride, int n, uint8_t* dst) {
 #if defined(__x86_64__)
   static const int have_avx2 = __builtin_cpu_supports("avx2");
-  if (have_avx2) return pack_rows_avx2(src, stride, n, dst);
+  static const int nt = [] { const char* e = getenv("SLAMB200_PACK_NT"); return e ? atoi(e) : 0; }();
+  if (have_avx2) {
+    if (nt && ((uintptr_t)dst & 31) == 0) return pack_rows_avx2<true>(src, stride, n, dst);
+    return pack_rows_avx2<false>(src, stride, n, dst);
+  }
 #endif
   return pack_rows_scalar(src, stride, n, dst);
 }

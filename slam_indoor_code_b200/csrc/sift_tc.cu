@@ -44,6 +44,7 @@
 //    (featureMatchingCPU.cpp:33-35: BRUTEFORCE_HAMMING).
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -60,6 +61,12 @@ constexpr int N_ASTAGE = 2;
 constexpr int N_BSTAGE = 4;
 constexpr int SMEM_BARS = 3072;     // mbarriers, the TMEM base slot, and the 2 KB record-exchange area
 constexpr int SMEM_BYTES = (N_ASTAGE + N_BSTAGE) * STAGE + SMEM_BARS + 1024;
+// with the tail inside the kernel (TAIL instantiation): the scratch of one 128-row unit behind the
+// barrier area, and a ring of finished segments between the epilogue and the tail warps
+constexpr int SMEM_TAIL = 3584;
+constexpr int SMEM_BYTES_TAIL = SMEM_BYTES + SMEM_TAIL;
+constexpr int JOB_RING = 8;
+constexpr int BAR_TAIL = 5;         // named barrier of the two tail warps (1..4: the epilogue's quarter pairs)
 // general-float variant: operands carry a hi and a lo bf16 half (two-term split), 24 + 1 MMAs per
 // tile: hi.hi + hi.lo + lo.hi + augmentation
 constexpr int STAGE_G = 4 * KBLK + 128 * 32;   // 69632
@@ -98,6 +105,26 @@ struct alignas(64) TcParams {
                                // (integer-valued / general floats): no flag loads in the tile walk
   int wide;                    // tiles x CTA pairs can exceed 2^32: 64-bit share arithmetic
 };
+
+// Small batches (the per-pair drop-in call above all) carry their pair table in the kernel
+// parameters instead of a device buffer filled by a copy in front of the launch: the tensor maps are
+// then read from parameter space, as the query's always are.
+constexpr int TC_INLINE_MAX = 4;
+struct alignas(64) InlineTables {
+  TcPair pairs[TC_INLINE_MAX];
+  int32_t prefix[TC_INLINE_MAX + 1];
+  int n;                       // 0: the tables are in device memory (TcParams / RerankParams pointers)
+};
+
+// Timeline probe (MODES builds, mode 8 = the product's behaviour + eight time stamps per CTA; read
+// back by slamb200_dbg_tc_trace, tools/tc_trace.py): where a short launch spends its time.
+__device__ unsigned long long g_tc_trace[160 * 8];
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(k) do { if (trace) g_tc_trace[(blockIdx.x % 160) * 8 + (k)] = global_ns(); } while (0)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -285,6 +312,8 @@ struct TileIter {
   int scan_p, scan_slot;    // next frame pair the walk looks at, and this CTA pair's position there
   int pfx0, pfx1, pfx2;     // tile_prefix[scan_p], [scan_p + 1], [scan_p + 2] (read one pair ahead)
   const CUtensorMap* tmap;  // train maps: [0] main (hi), [1] aug (train role), [2] lo
+  const TcPair* pairs;      // the launch's pair table and tile prefix (device memory or parameters)
+  const int32_t* prefix;
   bool gen;                 // which kind of frame pair this walk visits
   // The pair table (and the tensor maps inside it) is rewritten by the host before every launch:
   // make the TMA unit's descriptor reads observe those generic-proxy writes.
@@ -305,11 +334,11 @@ struct TileIter {
       scan_slot = slot + 1 == n_cta ? 0 : slot + 1;
       pfx0 = pfx1;
       pfx1 = pfx2;
-      if (p + 3 <= P.n_pairs) pfx2 = P.tile_prefix[p + 3];
+      if (p + 3 <= P.n_pairs) pfx2 = prefix[p + 3];
       if (nt == 0) continue;
       // exact-mode pairs (integer-valued query and train) and general-float pairs are walked by
       // different instantiations of the kernel
-      if (!P.kinds_known && ((P.q_flags[0] | P.pairs[p].t_flags[0]) != 0) != gen) continue;
+      if (!P.kinds_known && ((P.q_flags[0] | pairs[p].t_flags[0]) != 0) != gen) continue;
       const bool wide = P.wide != 0;
       const int t0 = share_begin(nt, slot, n_cta, wide);
       const int t1 = share_begin(nt, slot + 1, n_cta, wide);
@@ -322,22 +351,24 @@ struct TileIter {
       n_cb = (int)((unsigned)nt / (unsigned)P.n_rb);
       rb = (int)((unsigned)t0 / (unsigned)n_cb);
       cb = t0 - rb * n_cb;
-      t_n = P.pairs[p].t_n;
-      tmap = reinterpret_cast<const CUtensorMap*>(P.pairs[p].tmap);
+      t_n = pairs[p].t_n;
+      tmap = reinterpret_cast<const CUtensorMap*>(pairs[p].tmap);
       return true;
     }
     pair = P.n_pairs;
     return false;
   }
-  __device__ void init(const TcParams& P, int cta_, int n_cta_, bool gen_) {
+  __device__ void init(const TcParams& P, const TcPair* pairs_, const int32_t* prefix_, int cta_, int n_cta_,
+                       bool gen_) {
     cta = cta_; n_cta = n_cta_; gen = gen_;
+    pairs = pairs_; prefix = prefix_;
     pair = 0; n_cb = 1; rb = 0; cb = 0; tile = 0; end = 0; slot_c = 0; n_tiles = 0; t_n = 0;
     tmap = nullptr;
     scan_p = 0;
     scan_slot = cta_;     // (cta + p) % n_cta at p = 0, kept incrementally
-    pfx0 = P.tile_prefix[0];
-    pfx1 = P.n_pairs >= 1 ? P.tile_prefix[1] : pfx0;
-    pfx2 = P.n_pairs >= 2 ? P.tile_prefix[2] : pfx1;
+    pfx0 = prefix[0];
+    pfx1 = P.n_pairs >= 1 ? prefix[1] : pfx0;
+    pfx2 = P.n_pairs >= 2 ? prefix[2] : pfx1;
     seek(P);
   }
   __device__ bool valid() const { return tile < end; }
@@ -462,17 +493,378 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], int gid0,
   }
 }
 
+// ---- rerank: merge the slot records, prune by the ratio test, evaluate the survivors exactly ---
+struct RerankParams {
+  const uint8_t* q_u8;
+  const int32_t* q_nrm2;
+  const int32_t* q_flags;
+  const TcPair* pairs;
+  const int32_t* tile_prefix;
+  const uint4* cand;
+  int nq, nq_pad, n_slots, n_pairs, n_split, n_cta;
+  int wide;          // 64-bit share arithmetic (as TcParams::wide)
+  int prune;         // 1: rows that cannot pass the ratio test skip the exact evaluation
+  int orb;           // ORB sets: the accumulators are Hamming/2, q_u8 / t_u8 are the 32-byte rows
+  double ratio;
+  uint4* part;       // [pair][n_split][nq]: split 0 gets the record (pre-set to "absent")
+  uint4* work;       // survivors: {pair, row, gid of the best chunk, gid of the second chunk}
+  float2* work_v0;   // {tensor-core minimum (self check), smallest d^2/2 outside the best group}
+  int32_t* work_n;   // number of survivors
+  int32_t* err_flag;
+};
+
+constexpr float ORB_PAD_THRESHOLD = 200.0f;
+__device__ __forceinline__ bool lt_fi(float va, int ia, float vb, int ib) {
+  return va < vb || (va == vb && ia < ib);
+}
+
+__device__ __forceinline__ void part_top2_insert(uint4& r, uint32_t k, uint32_t i) {
+  const bool lt2 = k < r.z || (k == r.z && i < r.w);
+  if (lt2) {
+    const bool lt1 = k < r.x || (k == r.x && i < r.y);
+    if (lt1) { r.z = r.x; r.w = r.y; r.x = k; r.y = i; }
+    else { r.z = k; r.w = i; }
+  }
+}
+
+
+// ================= tail + ordered compaction as ONE unit of work =================
+// tail_unit: everything between the slot records of ROWS consecutive query rows of one frame pair
+// and their entries in the pair's match list -- slot merge, exact ratio-test pruning, best-group
+// rerank, ratio test (the arithmetic of tc_tail_fused_kernel above, operation for operation) and
+// the ORDERED compaction (ascending queryIdx, getGoodMatches' loop order,
+// featureMatchingCommon.cpp:43-49), done here by a decoupled look-back over the units of the pair
+// instead of a second kernel: a unit publishes its kept count, sums the counts of the units before
+// it back to the nearest published prefix, publishes its own prefix and writes its matches behind
+// it.  One 64-bit word per (pair, unit): {launch epoch : 30, state : 2, count : 32}; the epoch
+// makes words of earlier launches read as "not there yet", so the array is never cleared.
+// NT threads work on a unit (a thread block of 256 on 256 rows in tc_tail_compact_kernel; the two
+// tail warps of a tcgen05 CTA on the CTA's 128 rows when the tail runs inside sift_tc_kernel).
+template <int ROWS>
+struct TailSmem {
+  float v0[ROWS], L[ROWS], d0[ROWS], d1[ROWS];
+  int g0[ROWS], idx[ROWS];
+  uint32_t keep_mask[ROWS / 32];
+  int keep_off[ROWS / 32];
+  uint16_t list[ROWS];
+  int n_surv, base;
+  int flag;                   // in-kernel tail: "this CTA flushed the unit's last segment"
+};
+
+struct CompactArgs {
+  unsigned long long* scan;   // [pair][units per pair] look-back words
+  uint32_t epoch;             // 1 .. 2^30 - 1, different for every launch that shares `scan`
+  slamb200_dmatch* out;       // [pair][cap]
+  int cap;
+  int32_t* n_out;             // [pair]
+  int dbg_skip;               // timing experiments only (TcTail::dbg_skip)
+};
+
+__device__ __forceinline__ unsigned long long scan_ld(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void scan_st(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr uint32_t SCAN_AGG = 1, SCAN_PREFIX = 2;
+__device__ __forceinline__ unsigned long long scan_word(uint32_t epoch, uint32_t state, uint32_t v) {
+  return ((unsigned long long)((epoch << 2) | state) << 32) | v;
+}
+
+template <int BAR, int NT>
+__device__ __forceinline__ void group_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
+}
+
+// Exclusive prefix of unit `unit`'s count over the units of its pair (one warp, all 32 lanes).
+// Units before it are either published already or will be without waiting for this one (see the
+// callers for why), so the spin terminates.
+__device__ __forceinline__ int scan_lookback(unsigned long long* scan_pair, uint32_t epoch, int unit, int n,
+                                             int lane) {
+  if (unit == 0) {
+    if (lane == 0) scan_st(scan_pair, scan_word(epoch, SCAN_PREFIX, (uint32_t)n));
+    return 0;
+  }
+  if (lane == 0) scan_st(scan_pair + unit, scan_word(epoch, SCAN_AGG, (uint32_t)n));
+  int base = 0;
+  for (int j = unit - 1;;) {
+    const int k = j - lane;   // lane 0 looks at the nearest unit
+    unsigned long long w = scan_word(epoch, SCAN_PREFIX, 0);   // before unit 0: an empty prefix
+    if (k >= 0) w = scan_ld(scan_pair + k);
+    const uint32_t hi = (uint32_t)(w >> 32);
+    const bool ready = (hi >> 2) == epoch && (hi & 3u) != 0;
+    const unsigned rm = __ballot_sync(0xffffffffu, ready);
+    const unsigned pm = __ballot_sync(0xffffffffu, ready && (hi & 3u) == SCAN_PREFIX);
+    const int first = pm ? __ffs(pm) - 1 : 32;                 // nearest published prefix in the window
+    const unsigned need = first >= 32 ? 0xffffffffu : ((2u << first) - 1u);
+    if ((rm & need) != need) {
+      __nanosleep(64);
+      continue;
+    }
+    int v = lane <= first ? (int)(uint32_t)w : 0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    base += v;
+    if (first < 32) break;
+    j -= 32;
+  }
+  if (lane == 0) scan_st(scan_pair + unit, scan_word(epoch, SCAN_PREFIX, (uint32_t)(base + n)));
+  return base;
+}
+
+template <bool ORB, int NT, int ROWS, int BAR>
+__device__ __forceinline__ void tail_unit(const RerankParams& R, const CompactArgs& C, const TcPair* pairs_tab,
+                                          const int32_t* prefix_tab, int pair, int rb, int q0, int unit,
+                                          int units_per_pair, bool gen_pair, TailSmem<ROWS>& sm, int tid) {
+  static_assert(ROWS % NT == 0 && NT % 32 == 0 && ROWS / 32 <= 32, "unit geometry");
+  const int lane = tid & 31, warp = tid >> 5;
+  const TcPair* pr = pairs_tab + pair;
+  const int t_n = pr->t_n;
+  const uint8_t* __restrict__ t_u8 = pr->t_u8;
+  const int32_t* __restrict__ t_nrm2 = pr->t_nrm2;
+  const float INF = __int_as_float(0x7f800000);
+  if (tid == 0) sm.n_surv = 0;
+  for (int r = tid; r < ROWS; r += NT) { sm.idx[r] = -1; sm.d0[r] = 0.f; sm.d1[r] = -1.f; }
+  group_sync<BAR, NT>();
+  if (gen_pair) {
+    // general-float pair: its records come from the certified rerank; finalize them
+    for (int r = tid; r < ROWS; r += NT) {
+      const int q = q0 + r;
+      if (q >= R.nq) continue;
+      uint4 rr = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
+      for (int sp = 0; sp < R.n_split; sp++) {
+        const uint4 p = R.part[((size_t)pair * R.n_split + sp) * R.nq + q];
+        if (p.y != 0xFFFFFFFFu) part_top2_insert(rr, p.x, p.y);
+        if (p.w != 0xFFFFFFFFu) part_top2_insert(rr, p.z, p.w);
+      }
+      if (rr.y != 0xFFFFFFFFu) {
+        sm.idx[r] = (int)rr.y;
+        sm.d0[r] = __uint_as_float(rr.x);
+        // (a NaN second distance fails `d1 >= 0` below exactly as it fails the ratio test)
+        if (rr.w != 0xFFFFFFFFu) sm.d1[r] = __uint_as_float(rr.z);
+      }
+    }
+  } else {
+    // slots the tcgen05 kernel wrote for this (pair, query block): one merged record per share
+    int n_valid = 0;
+    {
+      const int n_tiles = prefix_tab[pair + 1] - prefix_tab[pair];
+      if (n_tiles > 0) {
+        const int n_rb = R.nq_pad / 256;
+        const int n_cb = n_tiles / n_rb;
+        const int first = owner_cta(n_tiles, R.n_cta, rb * n_cb, R.wide != 0);
+        const int last = owner_cta(n_tiles, R.n_cta, (rb + 1) * n_cb - 1, R.wide != 0);
+        n_valid = last - first + 1;
+        if (n_valid > R.n_slots) n_valid = R.n_slots;
+      }
+    }
+    for (int r = tid; r < ROWS; r += NT) {
+      const int q = q0 + r;
+      bool survive = false;
+      if (q < R.nq) {
+        float v0 = INF, v1 = INF, s0 = INF;
+        int g0 = 0xFFFF, g1 = 0xFFFF;
+        for (int sb = 0; sb < n_valid; sb += 4) {
+          uint4 recs[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++)   // independent loads first (L2: the records may have been
+                                        // written by other SMs during this very kernel)
+            recs[j] = sb + j < n_valid ? __ldcg(R.cand + ((size_t)pair * R.n_slots + sb + j) * R.nq_pad + q)
+                                       : make_uint4(0x7f800000u, 0x7f800000u, 0x7f800000u, 0xFFFFFFFFu);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint4 rec = recs[j];
+            const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.y);
+            float sa = __uint_as_float(rec.z);
+            int ia = (int)(rec.w & 0xFFFFu), ib = (int)(rec.w >> 16);
+            if (ORB) {
+              if (a > ORB_PAD_THRESHOLD) ia = 0xFFFF;
+              if (b > ORB_PAD_THRESHOLD) ib = 0xFFFF;
+              if (sa > ORB_PAD_THRESHOLD) sa = INF;
+            }
+            if (ia != 0xFFFF) {
+              if (lt_fi(a, ia, v0, g0)) { v1 = v0; g1 = g0; v0 = a; g0 = ia; s0 = sa; }
+              else if (lt_fi(a, ia, v1, g1)) { v1 = a; g1 = ia; }
+            }
+            if (ib != 0xFFFF) {
+              if (lt_fi(b, ib, v1, g1)) { v1 = b; g1 = ib; }
+            }
+          }
+        }
+        const bool has0 = g0 != 0xFFFF;
+        survive = has0;
+        const float L = fminf(s0, v1);
+        if (R.prune && has0 && L < INF) {
+          const float d0 = ORB ? 2.0f * v0 : sqrtf(2.0f * v0), D1 = ORB ? 2.0f * L : sqrtf(2.0f * L);
+          if (!((double)d0 < __dmul_rn(R.ratio, (double)D1))) survive = false;   // exact pruning
+        }
+        sm.v0[r] = v0; sm.L[r] = L; sm.g0[r] = g0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, survive);
+      int at = 0;
+      if (lane == 0 && bal) at = atomicAdd(&sm.n_surv, __popc(bal));
+      at = __shfl_sync(0xffffffffu, at, 0);
+      if (survive) sm.list[at + __popc(bal & ((1u << lane) - 1))] = (uint16_t)r;
+    }
+    group_sync<BAR, NT>();
+    const int n_surv = (C.dbg_skip & 1) ? 0 : sm.n_surv;
+    // survivors: eight lanes per row, lane c ending up with candidate c of the row's best group
+    // (coalesced 16-byte slices + reduce-scatter, see tc_tail_fused_kernel)
+    const int cand = lane & 7;
+    for (int i0 = 0; i0 < n_surv; i0 += NT / 8) {
+      const int i = i0 + (tid >> 3);
+      const bool have = i < n_surv;
+      const int r = have ? sm.list[i] : 0;
+      const int gg = have ? sm.g0[r] : 0;
+      const int col0 = gg * GROUP;
+      const int col = col0 + cand;
+      const bool ok = have && col < t_n;
+      const int qq = q0 + r;
+      uint32_t dist;   // exact integer distance of this lane's candidate: d^2 (SIFT) or Hamming (ORB)
+      if (ORB) {
+        const int cc = ok ? col : 0;
+        const uint4* tp = reinterpret_cast<const uint4*>(t_u8 + (size_t)cc * 32);
+        const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 32);
+        const uint4 t0 = tp[0], t1 = tp[1], qa = qp[0], qb = qp[1];
+        dist = (uint32_t)(__popc(qa.x ^ t0.x) + __popc(qa.y ^ t0.y) + __popc(qa.z ^ t0.z) + __popc(qa.w ^ t0.w) +
+                          __popc(qb.x ^ t1.x) + __popc(qb.y ^ t1.y) + __popc(qb.z ^ t1.z) + __popc(qb.w ^ t1.w));
+      } else {
+        // (rows up to the set's 256-row padding exist: a group never leaves the allocation)
+        const uint4* tp = reinterpret_cast<const uint4*>(t_u8 + (size_t)col0 * 128) + cand;
+        const uint4 qv = *(reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 128) + cand);
+        uint4 tv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) tv[k] = tp[8 * k];
+        const uint32_t nn = (uint32_t)t_nrm2[ok ? col : 0] + (uint32_t)R.q_nrm2[qq];
+        uint32_t pd[8];   // pd[k]: this lane's slice of q . (candidate row k)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          uint32_t d = __dp4a(qv.x, tv[k].x, 0u);
+          d = __dp4a(qv.y, tv[k].y, d);
+          d = __dp4a(qv.z, tv[k].z, d);
+          pd[k] = __dp4a(qv.w, tv[k].w, d);
+        }
+        const bool b4 = (cand & 4) != 0, b2 = (cand & 2) != 0, b1 = (cand & 1) != 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t send = b4 ? pd[j] : pd[j + 4], keep = b4 ? pd[j + 4] : pd[j];
+          pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const uint32_t send = b2 ? pd[j] : pd[j + 2], keep = b2 ? pd[j + 2] : pd[j];
+          pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        {
+          const uint32_t send = b1 ? pd[0] : pd[1], keep = b1 ? pd[1] : pd[0];
+          pd[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        dist = nn - 2u * pd[0];
+      }
+      uint32_t k0 = ok ? ((dist << 3) | (uint32_t)cand) : 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+#pragma unroll
+      for (int off = 1; off <= 4; off <<= 1) {
+        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, off);
+        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, off);
+        const uint32_t hi = max(k0, o0);
+        k0 = min(k0, o0);
+        k1 = min(hi, min(k1, o1));
+      }
+      if (have && cand == 0 && k0 != 0xFFFFFFFFu) {
+        const uint32_t x0 = k0 >> 3;
+        // self check: the group's exact minimum must equal twice the tensor-core value
+        if ((float)x0 != 2.0f * sm.v0[r]) atomicOr(R.err_flag, 1);
+        // second distance: inside the group, or the bound from outside it (exact values both)
+        const float Lr = sm.L[r];
+        float x1 = Lr < INF ? 2.0f * Lr : -1.0f;
+        if (k1 != 0xFFFFFFFFu) {
+          const float x2 = (float)(k1 >> 3);
+          x1 = (x1 < 0.0f || x2 < x1) ? x2 : x1;
+        }
+        sm.idx[r] = gg * GROUP + (int)(k0 & 7u);
+        sm.d0[r] = ORB ? (float)x0 : sqrtf((float)x0);
+        sm.d1[r] = ORB ? x1 : (x1 >= 0.0f ? sqrtf(x1) : -1.0f);
+      }
+    }
+  }
+  group_sync<BAR, NT>();
+  // ratio test (double, strict), 32 consecutive rows per warp and pass
+  for (int r = tid; r < ROWS; r += NT) {
+    const int q = q0 + r;
+    const float d1 = sm.d1[r];
+    const bool keep = q < R.nq && sm.idx[r] >= 0 && d1 >= 0.0f &&
+                      (double)sm.d0[r] < __dmul_rn(R.ratio, (double)d1);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) sm.keep_mask[r >> 5] = bal;
+  }
+  group_sync<BAR, NT>();
+  if (warp == 0) {
+    const int c = lane < ROWS / 32 ? __popc(sm.keep_mask[lane]) : 0;
+    int incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    const int n = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane < ROWS / 32) sm.keep_off[lane] = incl - c;
+    const int base = (C.dbg_skip & 2) ? 0 : scan_lookback(C.scan + (size_t)pair * units_per_pair, C.epoch, unit, n, lane);
+    if (lane == 0) {
+      sm.base = base;
+      if (unit == units_per_pair - 1) C.n_out[pair] = base + n;
+    }
+  }
+  group_sync<BAR, NT>();
+  {
+    const int base = sm.base;
+    int4* outp = reinterpret_cast<int4*>(C.out + (size_t)pair * C.cap);
+    for (int r = tid; r < ROWS; r += NT) {
+      const uint32_t m = sm.keep_mask[r >> 5];
+      if (!((m >> (r & 31)) & 1u)) continue;
+      const int off = base + sm.keep_off[r >> 5] + __popc(m & ((1u << (r & 31)) - 1u));
+      if (off < C.cap) outp[off] = make_int4(q0 + r, sm.idx[r], 0, __float_as_int(sm.d0[r]));
+    }
+  }
+}
+
+// What the tail warps of the TAIL instantiation need beside TcParams.
+struct TcTail {
+  RerankParams R;
+  CompactArgs C;              // scan: one word per (pair, row block, CTA of the pair)
+  int32_t* seg_done;          // [pair][row block][CTA of the pair]: segments flushed so far; zero
+                              // before the first launch, left at zero by every launch
+  int dbg_skip;               // timing experiments (SLAMB200_TAIL_SKIP; results void): 1 no survivors,
+                              // 2 no look-back, 4 no tail work at all
+};
+static_assert(sizeof(TailSmem<128>) <= SMEM_TAIL, "tail scratch does not fit its shared-memory area");
+
 // MODES = false is the product: `mode` is the constant 0 and none of the timing experiments below
 // exists in the instruction stream.  MODES = true (tools/tc_modes.py through
 // slamb200_dbg_set_tc_mode) selects role ablations at run time; their results are void.
-template <bool DBG, bool GEN, bool MODES>
+// TAIL = true (exact-mode match output, every share non-empty): warps 2 and 3 turn the slot records
+// of a finished (pair, row block) into its entries of the match list while the other roles go on
+// (tail_unit above) -- no tail kernel behind this one, and the records are read back while they
+// are still in L2.  The epilogue hands every flushed segment to them through a ring in shared
+// memory (mbarrier full / empty pairs, like the operand stages); they count the segments of a
+// row block in a global counter, and the CTA that flushes the last one owns the unit.  Its ring is
+// in walk order, so is every other CTA's: the smallest unit that has not published its count is
+// never behind a larger one, which is why the look-back's spin always ends.
+template <bool DBG, bool GEN, bool MODES, bool TAIL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-sift_tc_kernel(const __grid_constant__ TcParams P) {
+sift_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcTail TT,
+               const __grid_constant__ InlineTables IT) {
+  static_assert(!TAIL || (!GEN && !DBG && !MODES), "the in-kernel tail exists for the exact-mode product only");
   constexpr int STG = GEN ? STAGE_G : STAGE;
   constexpr int NA = GEN ? N_ASTAGE_G : N_ASTAGE;
   constexpr int NB = GEN ? N_BSTAGE_G : N_BSTAGE;
   constexpr int AUG = GEN ? AUG_OFF_G : AUG_OFF;
-  const int mode = MODES ? P.mode : 0;
+  const TcPair* pairs_tab = IT.n ? IT.pairs : P.pairs;
+  const int32_t* prefix_tab = IT.n ? IT.prefix : P.tile_prefix;
+  const int mode = MODES ? (P.mode == 8 ? 0 : P.mode) : 0;
+  const bool trace = MODES && P.mode == 8;
+  if (threadIdx.x == 0) TC_STAMP(0);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the SWIZZLE_128B atoms (same offset in both CTAs of the pair)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -484,6 +876,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
   const uint32_t b_full = bar_base + 32, b_empty = bar_base + 64;     // 4 + 4
   const uint32_t t_full = bar_base + 96, t_empty = bar_base + 112;    // 2 + 2
   const uint32_t tmem_slot = bar_base + 128;
+  const uint32_t job_full = bar_base + 192, job_empty = bar_base + 256;   // JOB_RING + JOB_RING (TAIL)
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (NA + NB) * STG + 128);
@@ -500,8 +893,8 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     const int qg = P.q_flags[0] != 0;
     int mine = 0;
     for (int p = threadIdx.x; p < P.n_pairs; p += TC_THREADS)
-      if (((qg | (P.pairs[p].t_flags[0] != 0)) != 0) == GEN &&
-          P.tile_prefix[p + 1] != P.tile_prefix[p])
+      if (((qg | (pairs_tab[p].t_flags[0] != 0)) != 0) == GEN &&
+          prefix_tab[p + 1] != prefix_tab[p])
         mine = 1;
     if (__syncthreads_or(mine) == 0) return;  // both CTAs of the pair reach the same verdict
   }
@@ -519,6 +912,12 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       mbar_init(t_full + 8 * s, 1);                  // tcgen05.commit multicast
       mbar_init(t_empty + 8 * s, 2 * N_EPI_WARPS);   // epilogue warps of both CTAs (leader's copy)
     }
+    if (TAIL) {
+      for (int s = 0; s < JOB_RING; s++) {
+        mbar_init(job_full + 8 * s, 4);    // the four epilogue warps that store a segment's records
+        mbar_init(job_empty + 8 * s, 1);   // the tail warps have read the entry
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -531,19 +930,20 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) TC_STAMP(1);
   PDL_TRIGGER();   // the merge kernel behind this one may be scheduled now; it waits for our exit
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs; each loads its own halves) =================
     if (elect_one()) {
       TileIter it;
-      it.init(P, pair_id, n_pairs_cta, GEN);
+      it.init(P, pairs_tab, prefix_tab, pair_id, n_pairs_cta, GEN);
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       int maps_of_pair = -1;
       bool new_seg = true;
       while (it.valid()) {
         if (maps_of_pair != it.pair) {
-          it.acquire_maps();
+          if (!IT.n) it.acquire_maps();   // (maps in the parameters need no proxy fence)
           maps_of_pair = it.pair;
         }
         if (new_seg) {
@@ -585,9 +985,10 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     // ================= MMA issuer (leader CTA only) =================
     if (rank == 0 && elect_one()) {
       TileIter it;
-      it.init(P, pair_id, n_pairs_cta, GEN);
+      it.init(P, pairs_tab, prefix_tab, pair_id, n_pairs_cta, GEN);
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, t_stage = 0, t_phase = 0;
       int cur_a = 0;
+      int n_issued = 0;
       bool new_seg = true;
       while (it.valid()) {
         if (new_seg) {
@@ -598,6 +999,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
         mbar_wait(b_full + 8 * b_stage, b_phase);
         mbar_wait(t_empty + 8 * t_stage, t_phase ^ 1);
         tc_fence_after();
+        if (MODES && n_issued++ == 0) TC_STAMP(2);
         const uint32_t a_addr = a_base + cur_a * STG;
         const uint32_t b_addr = b_base + b_stage * STG;
         const uint32_t d_tmem = tmem_base + t_stage * BN;
@@ -649,6 +1051,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
         new_seg = it.next(P);
         if (new_seg) tc_commit(a_empty + 8 * cur_a);  // the segment's MMAs are done with A
       }
+      if (MODES) { TC_STAMP(3); if (trace) g_tc_trace[(blockIdx.x % 160) * 8 + 7] = (unsigned long long)n_issued; }
     }
   } else if (warp >= EPI_WARP0) {
     // ================= epilogue (both CTAs; each drains its own TMEM) =================
@@ -660,7 +1063,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     const bool do_ld = !MODES || mode < 2 || mode >= 6;
     const bool do_proc = !MODES || mode < 1 || mode == 6;
     TileIter it;
-    it.init(P, pair_id, n_pairs_cta, GEN);
+    it.init(P, pairs_tab, prefix_tab, pair_id, n_pairs_cta, GEN);
     int t_stage = 0, t_phase = 0;
     EpiState st;
     st.reset();
@@ -668,6 +1071,8 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
     bool new_seg = true;
     bool first_tile = true;
     int seg_ntiles = 1, seg_ncb = 1, seg_c = 0;
+    int seg_i = 0;   // TAIL: segments this CTA has flushed
+    volatile int2* jobs = reinterpret_cast<volatile int2*>(smem_gen + (NA + NB) * STG + 320);
     while (it.valid()) {
       if (new_seg) {
         seg_pair = it.pair; seg_rb = it.rb;
@@ -680,6 +1085,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
       n_chunks = n_chunks < 0 ? 0 : (n_chunks > CHUNKS ? CHUNKS : n_chunks);
       mbar_wait(t_full + 8 * t_stage, t_phase);
       tc_fence_after();
+      if (MODES && first_tile && ew == 0 && lane == 0) TC_STAMP(4);
       const uint32_t t_addr = tmem_base + lane_addr + t_stage * BN + half * COLS_PER_WARP;
       const int gid_tile = (it.cb * BN + half * COLS_PER_WARP) / GROUP;
       const bool dump = DBG && first_tile && pair_id == 0;
@@ -794,7 +1200,64 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
                                     (uint32_t)g0 | ((uint32_t)g1 << 16));
           }
           asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // the exchange slot may be rewritten
+          if (TAIL && half == 0) {
+            // hand the segment to the tail warps: the entry, then one arrival per storing warp (the
+            // arrival releases this warp's record stores to whoever waits on the barrier)
+            const int slot_i = seg_i % JOB_RING;
+            if (ew == 0 && lane == 0) {
+              mbar_wait(job_empty + 8 * slot_i, ((seg_i / JOB_RING) & 1) ^ 1);
+              jobs[slot_i].x = seg_pair;
+              jobs[slot_i].y = seg_rb;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(job_full + 8 * slot_i);
+            seg_i++;
+          }
         }
+      }
+    }
+    if (TAIL && half == 0) {   // end of this CTA's walk
+      const int slot_i = seg_i % JOB_RING;
+      if (ew == 0 && lane == 0) {
+        mbar_wait(job_empty + 8 * slot_i, ((seg_i / JOB_RING) & 1) ^ 1);
+        jobs[slot_i].x = -1;
+        jobs[slot_i].y = 0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(job_full + 8 * slot_i);
+    }
+    if (MODES && ew == 0 && lane == 0) TC_STAMP(5);
+  } else if (TAIL && (warp == 2 || warp == 3)) {
+    // ================= tail (both CTAs; each finishes units of its own 128 rows) =================
+    const int tid = (warp - 2) * 32 + lane;
+    TailSmem<128>& sm = *reinterpret_cast<TailSmem<128>*>(smem_gen + (NA + NB) * STG + SMEM_BARS);
+    volatile int2* jobs = reinterpret_cast<volatile int2*>(smem_gen + (NA + NB) * STG + 320);
+    for (int s = 0;; s++) {
+      const int slot_i = s % JOB_RING;
+      mbar_wait(job_full + 8 * slot_i, (s / JOB_RING) & 1);
+      const int pair = jobs[slot_i].x, rb = jobs[slot_i].y;
+      group_sync<BAR_TAIL, 64>();                       // both warps hold the entry
+      if (tid == 0) mbar_arrive(job_empty + 8 * slot_i);
+      if (pair < 0) break;
+      if (tid == 0) {
+        // one more share has flushed its records of this row block; the last one owns the unit
+        const int n_tiles = prefix_tab[pair + 1] - prefix_tab[pair];
+        const int n_cb = n_tiles / P.n_rb;
+        const int first = owner_cta(n_tiles, n_pairs_cta, rb * n_cb, P.wide != 0);
+        const int last = owner_cta(n_tiles, n_pairs_cta, (rb + 1) * n_cb - 1, P.wide != 0);
+        int32_t* cnt = TT.seg_done + ((size_t)pair * P.n_rb + rb) * 2 + rank;
+        __threadfence();                                // (cumulative: covers the epilogue's stores)
+        const int old = atomicAdd(cnt, 1);
+        const int mine = old == last - first;
+        if (mine) *cnt = 0;                             // nobody else touches it in this launch
+        __threadfence();
+        sm.flag = mine;
+      }
+      group_sync<BAR_TAIL, 64>();
+      if (sm.flag && !(TT.dbg_skip & 4)) {
+        const int q0 = rb * 2 * BM + (int)rank * BM;
+        if (P.fp8) tail_unit<true, 64, 128, BAR_TAIL>(TT.R, TT.C, pairs_tab, prefix_tab, pair, rb, q0, rb * 2 + (int)rank, P.n_rb * 2, false, sm, tid);
+        else tail_unit<false, 64, 128, BAR_TAIL>(TT.R, TT.C, pairs_tab, prefix_tab, pair, rb, q0, rb * 2 + (int)rank, P.n_rb * 2, false, sm, tid);
       }
     }
   }
@@ -805,6 +1268,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
   __syncwarp();
   tc_fence_before();
   cluster_sync_all();
+  if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512)
@@ -812,31 +1276,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P) {
   }
 }
 
-// ---- rerank: merge the slot records, prune by the ratio test, evaluate the survivors exactly ---
-struct RerankParams {
-  const uint8_t* q_u8;
-  const int32_t* q_nrm2;
-  const int32_t* q_flags;
-  const TcPair* pairs;
-  const int32_t* tile_prefix;
-  const uint4* cand;
-  int nq, nq_pad, n_slots, n_pairs, n_split, n_cta;
-  int wide;          // 64-bit share arithmetic (as TcParams::wide)
-  int prune;         // 1: rows that cannot pass the ratio test skip the exact evaluation
-  int orb;           // ORB sets: the accumulators are Hamming/2, q_u8 / t_u8 are the 32-byte rows
-  double ratio;
-  uint4* part;       // [pair][n_split][nq]: split 0 gets the record (pre-set to "absent")
-  uint4* work;       // survivors: {pair, row, gid of the best chunk, gid of the second chunk}
-  float2* work_v0;   // {tensor-core minimum (self check), smallest d^2/2 outside the best group}
-  int32_t* work_n;   // number of survivors
-  int32_t* err_flag;
-};
-
-constexpr float ORB_PAD_THRESHOLD = 200.0f;
-__device__ __forceinline__ bool lt_fi(float va, int ia, float vb, int ib) {
-  return va < vb || (va == vb && ia < ib);
-}
-
+// ---- rerank kernels (RerankParams and the shared tail are defined above the tcgen05 kernel) ---
 // Pass 1, one thread per (pair, row): merges the row's slot records into its best two chunks.
 // Lanes run along the rows, so every slot read is a coalesced 512 B per warp.
 //
@@ -1219,15 +1659,6 @@ __global__ void __launch_bounds__(256) orb_rerank_kernel(const RerankParams R) {
 // records come from the certified rerank) take the plain finalize branch.  The arithmetic of each
 // step is that of sift_merge_kernel / sift_rerank_lite_kernel / orb_rerank_lite_kernel /
 // finalize_rows_kernel; the raw k-NN output keeps the separate kernels.
-__device__ __forceinline__ void part_top2_insert(uint4& r, uint32_t k, uint32_t i) {
-  const bool lt2 = k < r.z || (k == r.z && i < r.w);
-  if (lt2) {
-    const bool lt1 = k < r.x || (k == r.x && i < r.y);
-    if (lt1) { r.z = r.x; r.w = r.y; r.x = k; r.y = i; }
-    else { r.z = k; r.w = i; }
-  }
-}
-
 template <bool ORB>
 __global__ void __launch_bounds__(256)
 tc_tail_fused_kernel(const RerankParams R, int32_t* __restrict__ knn_idx, float* __restrict__ knn_dist,
@@ -1440,6 +1871,23 @@ tc_tail_fused_kernel(const RerankParams R, int32_t* __restrict__ knn_idx, float*
   }
   const int n = __syncthreads_count(keep);
   if (tid == 0) chunk_cnt[pair * gridDim.x + blockIdx.x] = n;
+}
+
+// The match path's tail as one kernel behind the tcgen05 kernel: a block per (256 query rows,
+// frame pair).  The look-back waits only on blocks of the same pair with a smaller index, which the
+// hardware dispatches first.
+template <bool ORB>
+__global__ void __launch_bounds__(256)
+tc_tail_compact_kernel(const RerankParams R, const CompactArgs C, const __grid_constant__ InlineTables IT) {
+  __shared__ TailSmem<256> sm;
+  PDL_TRIGGER();
+  PDL_WAIT();
+  const TcPair* pairs_tab = IT.n ? IT.pairs : R.pairs;
+  const int32_t* prefix_tab = IT.n ? IT.prefix : R.tile_prefix;
+  const int pair = blockIdx.y;
+  const bool gen_pair = R.q_flags[0] != 0 || pairs_tab[pair].t_flags[0] != 0;
+  tail_unit<ORB, 256, 256, 0>(R, C, pairs_tab, prefix_tab, pair, blockIdx.x, blockIdx.x * 256, blockIdx.x, gridDim.x, gen_pair, sm,
+                              threadIdx.x);
 }
 
 // ================= general-float pairs: certify-or-fallback rerank =================
@@ -1757,6 +2205,10 @@ EncodeTiledFn get_encode_fn() {
 
 int g_tc_mode = 0;
 extern "C" int slamb200_dbg_set_tc_mode(int m) { g_tc_mode = m; return 0; }
+// the time stamps of the last mode-8 launch: out[160][8] (ns, %globaltimer; [7] = tiles issued)
+extern "C" int slamb200_dbg_tc_trace(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 160 * 8) == cudaSuccess ? 0 : -1;
+}
 
 // Encodes a frame's tensor maps into host_out (4 x 128 B): [0] main (hi), [1] aug (query role),
 // [2] aug (train role), [3] lo half.
@@ -1803,28 +2255,39 @@ int tc_slots(int n_cb_max, int total_tiles, int n_cta) {
   return COL_SPLITS * segs;
 }
 
-int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_flags, int nq,
-                              const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
-                              int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
-                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s, int fp8,
-                              int kinds_known, int wide) {
+static bool tc_attrs_once() {
   static PerDeviceOnce attr_once;   // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute
-  if (!attr_once.run([] {
-        return cudaFuncSetAttribute(sift_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    SMEM_BYTES) == cudaSuccess &&
-               cudaFuncSetAttribute(sift_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    SMEM_BYTES) == cudaSuccess &&
-               cudaFuncSetAttribute(sift_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    SMEM_BYTES) == cudaSuccess &&
-               cudaFuncSetAttribute(sift_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    SMEM_BYTES_G) == cudaSuccess &&
-               cudaFuncSetAttribute(sift_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    SMEM_BYTES_G) == cudaSuccess;
-      }))
-    return -1;
-  if (total_tiles <= 0 || nq <= 0) return 0;
+  return attr_once.run([] {
+    return cudaFuncSetAttribute(sift_tc_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(sift_tc_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SMEM_BYTES_TAIL) == cudaSuccess &&
+           cudaFuncSetAttribute(sift_tc_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(sift_tc_kernel<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(sift_tc_kernel<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SMEM_BYTES_G) == cudaSuccess &&
+           cudaFuncSetAttribute(sift_tc_kernel<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SMEM_BYTES_G) == cudaSuccess;
+  });
+}
+
+// pairs_host != nullptr: the table travels in the parameters (n_pairs <= TC_INLINE_MAX)
+static void tc_fill_inline(InlineTables& IT, const TcPair* pairs_host, const int32_t* prefix_host, int n_pairs) {
+  IT.n = 0;
+  if (!pairs_host || n_pairs > TC_INLINE_MAX) return;
+  IT.n = n_pairs;
+  memcpy(IT.pairs, pairs_host, sizeof(TcPair) * (size_t)n_pairs);
+  memcpy(IT.prefix, prefix_host, sizeof(int32_t) * (size_t)(n_pairs + 1));
+}
+int tc_inline_max() { return TC_INLINE_MAX; }
+
+static void tc_fill_params(TcParams& P, const void* q_tmaps_host_384B, const int32_t* q_flags, int nq,
+                           const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                           int total_tiles, int n_slots, uint4* cand, int32_t* err_flag, float* dbg, int fp8,
+                           int kinds_known, int wide) {
   const int n_rb = (nq + 2 * BM - 1) / (2 * BM);
-  TcParams P;
   memcpy(P.q_tmap, q_tmaps_host_384B, 384);   // {main, aug (query role), lo}
   P.pairs = pairs_dev;
   P.tile_prefix = tile_prefix_dev;
@@ -1841,15 +2304,73 @@ int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_fl
   P.fp8 = fp8;
   P.kinds_known = kinds_known;
   P.wide = wide;
+}
+
+int launch_sift_tc_candidates(const void* q_tmaps_host_384B, const int32_t* q_flags, int nq,
+                              const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                              int total_tiles, int n_cta_pairs, int n_slots, uint4* cand,
+                              int32_t* err_flag, float* dbg, int gen, cudaStream_t s, int fp8,
+                              int kinds_known, int wide, const TcPair* inl_pairs_host,
+                              const int32_t* inl_prefix_host) {
+  if (!tc_attrs_once()) return -1;
+  if (total_tiles <= 0 || nq <= 0) return 0;
+  InlineTables IT;
+  tc_fill_inline(IT, inl_pairs_host, inl_prefix_host, n_pairs);
+  TcParams P;
+  tc_fill_params(P, q_tmaps_host_384B, q_flags, nq, pairs_dev, tile_prefix_dev, n_pairs, total_tiles, n_slots,
+                 cand, err_flag, dbg, fp8, kinds_known, wide);
+  TcTail TT;
+  memset(&TT, 0, sizeof(TT));
   const dim3 grid(2 * n_cta_pairs);
   if (gen) {
-    if (dbg) sift_tc_kernel<true, true, false><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P);
-    else sift_tc_kernel<false, true, false><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P);
+    if (dbg) sift_tc_kernel<true, true, false, false><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P, TT, IT);
+    else sift_tc_kernel<false, true, false, false><<<grid, TC_THREADS, SMEM_BYTES_G, s>>>(P, TT, IT);
   } else {
-    if (dbg) sift_tc_kernel<true, false, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P);
-    else if (g_tc_mode != 0) sift_tc_kernel<false, false, true><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P);   // role ablations
-    else sift_tc_kernel<false, false, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P);
+    if (dbg) sift_tc_kernel<true, false, false, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P, TT, IT);
+    else if (g_tc_mode != 0) sift_tc_kernel<false, false, true, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P, TT, IT);   // role ablations
+    else sift_tc_kernel<false, false, false, false><<<grid, TC_THREADS, SMEM_BYTES, s>>>(P, TT, IT);
   }
+  COUNT_LAUNCH();
+  return 0;
+}
+
+// The whole match path of a batch of integer-valued (or ORB) pairs in ONE kernel: candidates on the
+// tensor cores, and the tail (slot merge, pruning, best-group rerank, ratio test, ordered
+// compaction) on two otherwise idle warps of every CTA while the tiles go on.  Requires every pair
+// to have at least as many tiles as there are CTA pairs (no empty shares) and the kinds known on
+// the host.  scan: one word per (pair, row block, CTA of the pair), zeroed when allocated;
+// seg_done: one int32 per (pair, row block, CTA of the pair), zeroed when allocated.
+int launch_sift_tc_match(const void* q_tmaps_host_384B, const int32_t* q_flags, const uint8_t* q_u8,
+                         const int32_t* q_nrm2, int nq, const TcPair* pairs_dev,
+                         const int32_t* tile_prefix_dev, int n_pairs, int total_tiles, int n_cta_pairs,
+                         int n_slots, uint4* cand, int32_t* err_flag, double ratio, int fp8, int wide,
+                         unsigned long long* scan, uint32_t epoch, int32_t* seg_done, slamb200_dmatch* out,
+                         int cap, int32_t* n_out, cudaStream_t s, const TcPair* inl_pairs_host,
+                         const int32_t* inl_prefix_host) {
+  if (!tc_attrs_once()) return -1;
+  if (total_tiles <= 0 || nq <= 0) return 0;
+  InlineTables IT;
+  tc_fill_inline(IT, inl_pairs_host, inl_prefix_host, n_pairs);
+  TcParams P;
+  tc_fill_params(P, q_tmaps_host_384B, q_flags, nq, pairs_dev, tile_prefix_dev, n_pairs, total_tiles, n_slots,
+                 cand, err_flag, nullptr, fp8, 1, wide);
+  P.mode = 0;
+  TcTail TT;
+  memset(&TT, 0, sizeof(TT));
+  RerankParams& R = TT.R;
+  R.wide = wide;
+  R.orb = fp8;
+  R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
+  R.tile_prefix = tile_prefix_dev; R.n_cta = n_cta_pairs;
+  R.nq = nq; R.nq_pad = P.nq_pad; R.n_slots = n_slots; R.n_pairs = n_pairs;
+  R.n_split = 1; R.part = nullptr; R.err_flag = err_flag;
+  R.prune = (ratio >= 0.0 && ratio < 1e300) ? 1 : 0; R.ratio = ratio;
+  TT.C.scan = scan; TT.C.epoch = epoch; TT.C.out = out; TT.C.cap = cap; TT.C.n_out = n_out;
+  TT.seg_done = seg_done;
+  static const int skip = getenv("SLAMB200_TAIL_SKIP") ? atoi(getenv("SLAMB200_TAIL_SKIP")) : 0;
+  TT.dbg_skip = skip; TT.C.dbg_skip = skip;
+  const dim3 grid(2 * n_cta_pairs);
+  sift_tc_kernel<false, false, false, true><<<grid, TC_THREADS, SMEM_BYTES_TAIL, s>>>(P, TT, IT);
   COUNT_LAUNCH();
   return 0;
 }
@@ -1926,5 +2447,46 @@ void launch_tc_tail_fused(const int32_t* q_flags, const uint8_t* q_u8, const int
   dim3 grid((nq + 255) / 256, n_pairs);
   if (orb) launch_pdl(tc_tail_fused_kernel<true>, grid, dim3(256), 0, s, R, knn_idx, knn_dist, flags, chunk_cnt);
   else launch_pdl(tc_tail_fused_kernel<false>, grid, dim3(256), 0, s, R, knn_idx, knn_dist, flags, chunk_cnt);
+  COUNT_LAUNCH();
+}
+
+// Tail + ordered compaction in one kernel (tc_tail_compact_kernel): the match lists land in
+// out[pair][cap] / n_out[pair] directly.  `scan` holds one 64-bit word per (pair, 256-row block),
+// zeroed once when allocated; `epoch` (1 .. 2^30 - 1) must differ between launches that share it.
+void launch_tc_tail_compact(const int32_t* q_flags, const uint8_t* q_u8, const int32_t* q_nrm2, int nq,
+                            const TcPair* pairs_dev, const int32_t* tile_prefix_dev, int n_pairs,
+                            int n_cta_pairs, int n_slots, int n_split, const uint4* cand, const uint4* part,
+                            int32_t* err_flag, double ratio, int orb, unsigned long long* scan,
+                            uint32_t epoch, slamb200_dmatch* out, int cap, int32_t* n_out, cudaStream_t s,
+                            int wide, const TcPair* inl_pairs_host, const int32_t* inl_prefix_host) {
+  if (nq <= 0 || n_pairs <= 0) return;
+  InlineTables IT;
+  tc_fill_inline(IT, inl_pairs_host, inl_prefix_host, n_pairs);
+  RerankParams R;
+  R.wide = wide;
+  R.orb = orb;
+  R.q_u8 = q_u8; R.q_nrm2 = q_nrm2; R.q_flags = q_flags; R.pairs = pairs_dev; R.cand = cand;
+  R.tile_prefix = tile_prefix_dev; R.n_cta = n_cta_pairs;
+  R.nq = nq; R.nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM); R.n_slots = n_slots; R.n_pairs = n_pairs;
+  R.n_split = n_split; R.part = const_cast<uint4*>(part); R.err_flag = err_flag;
+  R.work = nullptr; R.work_v0 = nullptr; R.work_n = nullptr;
+  R.prune = (ratio >= 0.0 && ratio < 1e300) ? 1 : 0; R.ratio = ratio;
+  CompactArgs C;
+  C.scan = scan; C.epoch = epoch; C.out = out; C.cap = cap; C.n_out = n_out; C.dbg_skip = 0;
+  // The tcgen05 kernel in front of this one (and behind it, in a loop of calls) runs with the
+  // largest shared-memory carve-out; asking for the same one here spares the SMs a reconfiguration
+  // of their L1 / shared split between the two kernels of a call.
+  static PerDeviceOnce carve_once;
+  carve_once.run([] {
+    if (getenv("SLAMB200_NO_CARVEOUT")) return true;
+    cudaFuncSetAttribute(tc_tail_compact_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(tc_tail_compact_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    return true;
+  });
+  dim3 grid((nq + 255) / 256, n_pairs);
+  if (orb) launch_pdl(tc_tail_compact_kernel<true>, grid, dim3(256), 0, s, R, C, IT);
+  else launch_pdl(tc_tail_compact_kernel<false>, grid, dim3(256), 0, s, R, C, IT);
   COUNT_LAUNCH();
 }

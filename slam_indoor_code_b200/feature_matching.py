@@ -94,6 +94,17 @@ class Context:
         f.restype = ctypes.c_int
         check(f(self._h, 1 if tensor_cores else 0))
 
+    def debug_tail_form(self, form=-1):
+        """Developer switch for the tail of the tensor-core match path (slot merge, best-group rerank,
+        ratio test, ordered compaction): 2 = one kernel behind the tcgen05 kernel, 1 = tail kernel +
+        compaction kernel, 0 = separate merge / rerank / finalize kernels, 3 = experimental, inside the
+        tcgen05 kernel where the batch allows it; -1 (default) = 2 for batches of up to 32 pairs, 1
+        beyond.  Every form gives the same match lists."""
+        f = self._lib.slamb200_dbg_set_fused_tail
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        f.restype = ctypes.c_int
+        check(f(self._h, int(form)))
+
     def profile_enable(self, on=True):
         check(self._lib.slamb200_profile_enable(self._h, 1 if on else 0))
 

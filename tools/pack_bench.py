@@ -10,8 +10,8 @@ fn.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
 F = 210
 rng = np.random.default_rng(0)
 src = [rng.integers(0, 256, (10000, 128)).astype(np.float32) // 4 for _ in range(F)]
-dst = [np.zeros((10000, 128), np.uint8) for _ in range(16)]
-for nt in (1, 2, 4, 8, 12, 16):
+dst = [np.zeros((10000, 128), np.uint8) for _ in range(48)]
+for nt in (1, 2, 4, 8, 12, 16, 24, 32, 48):
     def work(t):
         for f in range(t, F, nt):
             assert fn(src[f].ctypes.data, 128, 10000, dst[t].ctypes.data) == 1

@@ -22,7 +22,7 @@ Ts = [ctx.upload(synth.sift_train_from_query(q, 10000, 3001 + i)) for i in range
 qo, to = synth.orb_pair(10000, 10000, 2001)
 Qo = ctx.upload(qo); To = [ctx.upload(to) for _ in range(16)]
 for rep in range(2):
-    for fused in (1, 0):
+    for fused in (2, 1):
         lib.slamb200_dbg_set_fused_tail(ctx._h, fused)
         r = []
         for P, it in ((1, 200), (16, 30), (64, 10)):
