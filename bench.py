@@ -276,9 +276,9 @@ def run_b200(args, rank, world, local):
         os.environ["SLAMB200_HOST_NARROWERS"] = str(args.e2e_uploaders)   # read once by the library, before its first host call
     if args.e2e_upload == "auto":
         args.e2e_upload = "packed"
-    # host threads of this rank that narrow Mats inside the library (pack_threads + 1 of them): its
+    # host threads of this rank that narrow Mats inside the library (its persistent pack pool): its
     # cores minus one -- the submitting and the matching thread mostly wait
-    pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else max(0, min(cores, 25) - 2)
+    pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else max(1, min(cores, 25) - 1)
     ctx.set_pack_threads(pack_threads)
     # A real (non-default) stream: the C ABI treats a NULL stream as "the lane's own stream", so
     # the kernels and the CUDA events that time them must share an explicit stream handle.
@@ -499,7 +499,7 @@ def run_b200(args, rank, world, local):
                     "host_mat_bytes_per_step": (N_PAIRS + world) * N_ROWS * 512,
                     "call": "slamb200_match_batch_host (one C-ABI call per step: narrowing, uploads, matching and "
                             "result copies pipelined inside the library)",
-                    "host_threads": {"narrowing": int(os.environ.get("SLAMB200_HOST_NARROWERS", pack_threads + 1)),
+                    "host_threads": {"narrowing": int(os.environ.get("SLAMB200_HOST_NARROWERS", pack_threads)),
                                      "submit": 1, "match_and_copy_out": 1},
                     "timing": "host wall clock between device synchronisations, max over ranks",
                     "results_equal_device_resident_run": bool(same), "host_floor": narrow},

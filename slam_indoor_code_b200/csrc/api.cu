@@ -183,6 +183,7 @@ struct slamb200_ctx {
   std::once_flag pack_once;
   int pack_threads = -1;  // -1: min(hardware threads, 16)
   bool pack_started = false;
+  std::atomic<int> pool_busy{0};   // long-running narrowing workers of slamb200_match_batch_host on the pool
   int sub_batch = 0;  // debug: pairs per tcgen05 launch when pipelining against the rerank
   int use_tc = 1;  // debug switch (slamb200_dbg_set_tc): 0 routes exact-mode pairs to the fp32 kernel
   int fused_tail = -1;  // form of the match path's tail (debug switch slamb200_dbg_set_fused_tail):
@@ -589,8 +590,17 @@ static int desc_create(slamb200_ctx* c, int kind, const void* rows, int n, size_
     const float* prep_src = d->f32;
     size_t prep_stride = 128;
     if (packed) {
-      // rows already narrowed to bytes in page-locked staging (verified exact on the host)
-      launch_sift_prep_u8((const uint8_t*)packed->p, n, d->n_pad, d->f32, d->bf16, d->augq, d->augt,
+      // rows already narrowed to bytes in page-locked staging (verified exact on the host).
+      // SLAMB200_UPLOAD_DMA=1: a copy engine brings them into the slab's byte part and the prep
+      // kernel reads HBM (its blocks then never sit on an SM waiting for PCIe while a match kernel
+      // wants every SM); default: the prep kernel reads the staging over PCIe itself.
+      static const int dma = [] { const char* e = getenv("SLAMB200_UPLOAD_DMA"); return e ? atoi(e) : 0; }();
+      const uint8_t* src8 = (const uint8_t*)packed->p;
+      if (dma && n > 0) {
+        DCU(cudaMemcpyAsync(d->u8, packed->p, (size_t)n * 128, cudaMemcpyHostToDevice, s));
+        src8 = d->u8;
+      }
+      launch_sift_prep_u8(src8, n, d->n_pad, d->f32, d->bf16, d->augq, d->augt,
                           d->u8, d->nrm2, d->bf16lo, d->nrmf, d->flags, s);
       d->host_exact = 1;
       d->ready_seen = 0;
@@ -663,6 +673,18 @@ extern "C" int slamb200_upload_desc_pinned(slamb200_ctx* c, int kind, const void
   return desc_create(c, kind, rows, n, row_stride, false, nullptr, true, out);
 }
 
+static void pack_pool_start(slamb200_ctx* c) {
+  std::call_once(c->pack_once, [c] {
+    int nthr = c->pack_threads;
+    if (nthr < 0) {
+      nthr = (int)std::thread::hardware_concurrency();
+      nthr = nthr > 24 ? 24 : nthr;
+    }
+    c->pack_pool.start(nthr > 0 ? nthr : 0);
+    c->pack_started = true;
+  });
+}
+
 // The caller's rows are consumed before the call returns (narrowed into page-locked staging on the
 // calling thread), the GPU work is only enqueued.
 extern "C" int slamb200_upload_desc_packed(slamb200_ctx* c, int kind, const void* rows, int n,
@@ -677,18 +699,11 @@ extern "C" int slamb200_upload_desc_packed(slamb200_ctx* c, int kind, const void
   slamb200_ctx::PinBuf* b = pin_acquire(c, (size_t)n * 128);
   if (!b) return desc_create(c, kind, rows, n, row_stride, false, nullptr, false, out);
   // narrow + verify: row slices on the pack pool, the last slice on the calling thread
-  std::call_once(c->pack_once, [c] {
-    int nthr = c->pack_threads;
-    if (nthr < 0) {
-      nthr = (int)std::thread::hardware_concurrency();
-      nthr = nthr > 24 ? 24 : nthr;
-    }
-    c->pack_pool.start(nthr > 0 ? nthr : 0);
-    c->pack_started = true;
-  });
+  pack_pool_start(c);
   int exact = 1;
   {
-    const int pool = (int)c->pack_pool.th.size();
+    // (while a slamb200_match_batch_host call occupies the pool, narrow on the calling thread)
+    const int pool = c->pool_busy.load() > 0 ? 0 : (int)c->pack_pool.th.size();
     int slices = n / 1024;                       // at least ~1k rows (0.5 MB) per slice
     slices = slices > 8 ? 8 : slices;
     slices = slices > pool + 1 ? pool + 1 : slices;
@@ -1516,44 +1531,112 @@ extern "C" int slamb200_match_batch_host(slamb200_ctx* c, int matcher, const voi
   static const int narrow_env = [] { const char* e = getenv("SLAMB200_HOST_NARROWERS"); return e ? atoi(e) : 0; }();
   static const int chunk_env = [] { const char* e = getenv("SLAMB200_HOST_CHUNK"); return e ? atoi(e) : 14; }();
   const int chunk = chunk_env > 0 ? chunk_env : 14;
-  const int n_chunks = (n_pairs + chunk - 1) / chunk;
+  // chunks of `chunk` pairs, the last ones halving (14, 7, 4, 3): what runs behind the last narrowed
+  // Mat is one short match call, not a whole chunk
+  std::vector<int> chunk_start{0};
+  {
+    int rem = n_pairs;
+    while (rem > 2 * chunk) { chunk_start.push_back(chunk_start.back() + chunk); rem -= chunk; }
+    while (rem > 0) {
+      int t = (rem + 1) / 2 < 3 ? 3 : (rem + 1) / 2;
+      t = t > rem ? rem : (t > chunk ? chunk : t);
+      chunk_start.push_back(chunk_start.back() + t);
+      rem -= t;
+    }
+  }
+  const int n_chunks = (int)chunk_start.size() - 1;
+  std::vector<int> chunk_of((size_t)(n_pairs > 0 ? n_pairs : 1), 0);
+  for (int k = 0; k < n_chunks; k++)
+    for (int i = chunk_start[(size_t)k]; i < chunk_start[(size_t)k + 1]; i++) chunk_of[(size_t)i] = k;
+  // developer trace (SLAMB200_HOST_TRACE=1): where a step spends its wall time
+  static const int trace = [] { const char* e = getenv("SLAMB200_HOST_TRACE"); return e ? atoi(e) : 0; }();
+  const auto T0 = std::chrono::steady_clock::now();
+  auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(); };
+  std::atomic<int> narrowed(0);
+  double t_q = 0, t_spawn = 0, t_first_narrow = 0, t_last_narrow = 0, t_last_submit = 0, t_first_chunk_ready = 0, t_wait_chunks = 0, t_match = 0;
   CU(cudaSetDevice(c->device));
   slamb200_desc* qd = nullptr;
   int rc = slamb200_upload_desc_packed(c, kind, q_rows, nq, q_stride, &qd);
   if (rc != SLAMB200_OK) return rc;
+  t_q = since();
   std::vector<slamb200_desc*> td((size_t)n_pairs, nullptr);
   std::vector<int> left((size_t)(n_chunks > 0 ? n_chunks : 1));
-  for (int k = 0; k < n_chunks; k++) left[(size_t)k] = (k + 1) * chunk <= n_pairs ? chunk : n_pairs - k * chunk;
+  for (int k = 0; k < n_chunks; k++) left[(size_t)k] = chunk_start[(size_t)k + 1] - chunk_start[(size_t)k];
   struct Job { int i; slamb200_ctx::PinBuf* b; };
   std::mutex mu;
   std::condition_variable cv_jobs, cv_chunks;
   std::deque<Job> jobs;
-  std::atomic<int> next(0);
   int first_err = SLAMB200_OK;
   char err_text[512] = "";
   auto stride_of = [&](int i) -> size_t {
     const size_t st = t_stride ? t_stride[i] : 0;
     return st ? st : (kind == SLAMB200_DESC_F32X128 ? 512 : 32);
   };
+  // Narrowing, Mat after Mat IN WINDOW ORDER with every thread on the same Mat: a Mat is cut into
+  // slices of ~1k rows and one counter hands out (Mat, slice) in order, so Mats become resident one
+  // by one (every ~50 us with 16 threads) instead of a thread count of them together every ~800 us
+  // -- the first chunk can be matched after 14 Mats' worth of narrowing, and behind the LAST byte
+  // narrowed only one Mat's prep and one short chunk remain.
+  constexpr int SLICE_ROWS = 1024;
+  struct MatState { std::atomic<int> pending; std::atomic<int> ok; std::atomic<slamb200_ctx::PinBuf*> b; std::atomic<int> claimed; };
+  std::vector<MatState> ms((size_t)(n_pairs > 0 ? n_pairs : 1));
+  std::vector<int> slice0((size_t)n_pairs + 1, 0);
+  for (int i = 0; i < n_pairs; i++) {
+    const size_t st = stride_of(i);
+    const bool packable = kind == SLAMB200_DESC_F32X128 && t_n[i] > 0 && t_rows[i] && st >= 512 && st % 4 == 0;
+    const int ns = packable ? (t_n[i] + SLICE_ROWS - 1) / SLICE_ROWS : 1;
+    slice0[(size_t)i + 1] = slice0[(size_t)i] + ns;
+    ms[(size_t)i].pending.store(ns);
+    ms[(size_t)i].ok.store(packable ? 1 : 0);
+    ms[(size_t)i].b.store(nullptr);
+    ms[(size_t)i].claimed.store(0);
+  }
+  const int total_slices = slice0[(size_t)n_pairs];
+  std::atomic<int> next(0);
   auto narrower = [&] {
     cudaSetDevice(c->device);
+    int i = 0;
     for (;;) {
-      const int i = next.fetch_add(1);
-      if (i >= n_pairs) return;
-      slamb200_ctx::PinBuf* b = nullptr;
+      const int g = next.fetch_add(1);
+      if (g >= total_slices) return;
+      while (slice0[(size_t)i + 1] <= g) i++;   // (g only grows on this thread)
+      MatState& M = ms[(size_t)i];
+      const int k = g - slice0[(size_t)i];
       const size_t st = stride_of(i);
-      if (kind == SLAMB200_DESC_F32X128 && t_n[i] > 0 && t_rows[i] && st >= 512 && st % 4 == 0) {
-        b = pin_acquire(c, (size_t)t_n[i] * 128);
-        if (b && !slamb200_host_pack_u8((const float*)t_rows[i], st / 4, t_n[i], (uint8_t*)b->p)) {
-          pin_release(c, b, nullptr);   // not integer valued: the fp32 path
-          b = nullptr;
+      if (M.ok.load(std::memory_order_relaxed)) {
+        // the thread that draws a Mat's first slice gets its staging buffer; the others wait for it
+        slamb200_ctx::PinBuf* b = nullptr;
+        if (k == 0) {
+          b = pin_acquire(c, (size_t)t_n[i] * 128);
+          if (!b) M.ok.store(0);
+          M.b.store(b, std::memory_order_release);
+          M.claimed.store(1, std::memory_order_release);
+        } else {
+          while (!M.claimed.load(std::memory_order_acquire)) __builtin_ia32_pause();
+          b = M.b.load(std::memory_order_acquire);
+        }
+        if (b && M.ok.load(std::memory_order_relaxed)) {
+          const int r0 = k * SLICE_ROWS, r1 = r0 + SLICE_ROWS < t_n[i] ? r0 + SLICE_ROWS : t_n[i];
+          if (!slamb200_host_pack_u8((const float*)((const char*)t_rows[i] + (size_t)r0 * st), st / 4, r1 - r0,
+                                     (uint8_t*)b->p + (size_t)r0 * 128))
+            M.ok.store(0);   // not integer valued: the whole Mat takes the fp32 path
         }
       }
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        jobs.push_back({i, b});
+      if (M.pending.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        slamb200_ctx::PinBuf* b = M.b.load(std::memory_order_acquire);
+        if (b && !M.ok.load()) {
+          pin_release(c, b, nullptr);
+          b = nullptr;
+        }
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          jobs.push_back({i, b});
+          const int kk = narrowed.fetch_add(1) + 1;
+          if (kk == 1) t_first_narrow = since();
+          if (kk == n_pairs) t_last_narrow = since();
+        }
+        cv_jobs.notify_one();
       }
-      cv_jobs.notify_one();
     }
   };
   auto submitter = [&] {
@@ -1581,25 +1664,53 @@ extern "C" int slamb200_match_batch_host(slamb200_ctx* c, int matcher, const voi
         first_err = r;
         snprintf(err_text, sizeof(err_text), "%s", g_err);
       }
-      if (--left[(size_t)(j.i / chunk)] == 0) cv_chunks.notify_all();
+      if (--left[(size_t)chunk_of[(size_t)j.i]] == 0) cv_chunks.notify_all();
+      if (done == n_pairs - 1) t_last_submit = since();
     }
   };
-  int n_narrow = narrow_env > 0 ? narrow_env : (int)std::thread::hardware_concurrency() - 3;
-  if (c->pack_threads >= 0) n_narrow = c->pack_threads + 1;   // the caller sized the host side (slamb200_set_pack_threads)
-  n_narrow = n_narrow > 24 ? 24 : (n_narrow < 1 ? 1 : n_narrow);
-  if (n_narrow > n_pairs) n_narrow = n_pairs;
+  // narrowing threads: the context's persistent pack pool (slamb200_set_pack_threads; default: the
+  // hardware threads, at most 24), all of it unless SLAMB200_HOST_NARROWERS says fewer; one thread
+  // of this call queues the prep kernels
+  pack_pool_start(c);
+  int n_narrow = (int)c->pack_pool.th.size();
+  {
+    // one hardware thread stays free for the submitting and the matching thread: with every core
+    // narrowing they are scheduled late and the step takes twice as long (measured)
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 1 && n_narrow > hw - 1) n_narrow = hw - 1;
+  }
+  if (narrow_env > 0 && narrow_env < n_narrow) n_narrow = narrow_env;
+  if (n_narrow > total_slices) n_narrow = total_slices;
+  std::atomic<int> workers_left(n_narrow);
+  std::mutex done_mu;
+  std::condition_variable done_cv;
+  c->pool_busy.fetch_add(1);
+  for (int k = 0; k < n_narrow; k++)
+    c->pack_pool.submit([&] {
+      narrower();
+      if (workers_left.fetch_sub(1) == 1) {
+        std::lock_guard<std::mutex> lk(done_mu);
+        done_cv.notify_all();
+      }
+    });
   std::vector<std::thread> th;
-  for (int k = 0; k < n_narrow; k++) th.emplace_back(narrower);
   if (n_pairs > 0) th.emplace_back(submitter);
+  if (n_narrow == 0 && n_pairs > 0) narrower();   // a context without pool threads: narrow here
+  t_spawn = since();
   for (int k = 0; k < n_chunks; k++) {
     {
+      const double tw = since();
       std::unique_lock<std::mutex> lk(mu);
       cv_chunks.wait(lk, [&] { return left[(size_t)k] == 0; });
+      t_wait_chunks += since() - tw;
+      if (k == 0) t_first_chunk_ready = since();
       if (first_err != SLAMB200_OK) break;
     }
-    const int p0 = k * chunk, np = (k + 1) * chunk <= n_pairs ? chunk : n_pairs - p0;
+    const int p0 = chunk_start[(size_t)k], np = chunk_start[(size_t)k + 1] - p0;
+    const double tm = since();
     const int r = slamb200_match_batch(c, matcher, qd, td.data() + p0, np, ratio,
                                        out ? out + (size_t)p0 * cap : nullptr, cap, n_out + p0);
+    t_match += since() - tm;
     if (r != SLAMB200_OK) {
       std::lock_guard<std::mutex> lk(mu);
       if (first_err == SLAMB200_OK) {
@@ -1613,10 +1724,21 @@ extern "C" int slamb200_match_batch_host(slamb200_ctx* c, int matcher, const voi
       td[(size_t)p] = nullptr;
     }
   }
+  const double t_chunks_done = since();
+  {   // (an error may have ended the loop early: the workers still hold references to this frame)
+    std::unique_lock<std::mutex> lk(done_mu);
+    done_cv.wait(lk, [&] { return workers_left.load() <= 0; });
+  }
+  c->pool_busy.fetch_sub(1);
   for (auto& t : th) t.join();
   for (slamb200_desc* d : td)
     if (d) slamb200_free_desc(c, d);
   slamb200_free_desc(c, qd);
+  if (trace)
+    fprintf(stderr, "[match_batch_host] q %.2f spawn %.2f first narrow %.2f first chunk ready %.2f last narrow %.2f "
+            "last submit %.2f chunks done %.2f end %.2f ms | waiting for chunks %.2f, in match calls %.2f (%d narrowers)\n",
+            t_q, t_spawn, t_first_narrow, t_first_chunk_ready, t_last_narrow, t_last_submit, t_chunks_done, since(),
+            t_wait_chunks, t_match, n_narrow);
   if (first_err != SLAMB200_OK) return fail(first_err, "%s", err_text);
   return SLAMB200_OK;
 }

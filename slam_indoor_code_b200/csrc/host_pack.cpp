@@ -83,7 +83,7 @@ static int pack_rows_scalar(const float* src, size_t stride, int n, uint8_t* dst
 extern "C" int slamb200_host_pack_u8(const float* src, size_t stride, int n, uint8_t* dst) {
 #if defined(__x86_64__)
   static const int have_avx2 = __builtin_cpu_supports("avx2");
-  static const int nt = [] { const char* e = getenv("SLAMB200_PACK_NT"); return e ? atoi(e) : 0; }();
+  static const int nt = [] { const char* e = getenv("SLAMB200_PACK_NT"); return e ? atoi(e) : 1; }();
   if (have_avx2) {
     if (nt && ((uintptr_t)dst & 31) == 0) return pack_rows_avx2<true>(src, stride, n, dst);
     return pack_rows_avx2<false>(src, stride, n, dst);
