@@ -277,8 +277,11 @@ def run_b200(args, rank, world, local):
     if args.e2e_upload == "auto":
         args.e2e_upload = "packed"
     # host threads of this rank that narrow Mats inside the library (its persistent pack pool): its
-    # cores minus one -- the submitting and the matching thread mostly wait
-    pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else max(1, min(cores, 25) - 1)
+    # cores minus one -- the submitting and the matching thread mostly wait, but with every core
+    # narrowing they are scheduled late and the step takes twice as long (measured: 15 of 16 is the
+    # best split at N = 1); with several ranks on the box, one more core per rank is left alone
+    pack_threads = args.e2e_pack_threads if args.e2e_pack_threads >= 0 else \
+        max(1, min(cores, 25) - (1 if world == 1 else 2))
     ctx.set_pack_threads(pack_threads)
     # A real (non-default) stream: the C ABI treats a NULL stream as "the lane's own stream", so
     # the kernels and the CUDA events that time them must share an explicit stream handle.
