@@ -1237,19 +1237,54 @@ static int enqueue_batch(slamb200_ctx* c, Lane& L, cudaStream_t s, int matcher,
         // their slot records are two 16-byte words wide and live in their own buffer
         if ((rc = buf_reserve(c, L.cand_g, 2 * cand_bytes, s))) return rc;
         if (holes) CU(cudaMemsetAsync(L.cand_g.p, 0xFF, 2 * cand_bytes, s));
-        int grc;
-        {
-          ProfScope ps(c, s, SLAMB200_K_SIFT_TC_GEN);
-          grc = launch_sift_tc_candidates(qmaps, q->flags, nq, d_tc, d_pre, n_pairs, pre[n_pairs], n_cta,
-                                          n_slots, (uint4*)L.cand_g.p, d_status, nullptr, 1, s, 0,
-                                          q->host_exact == 0 ? 1 : 0, wide);
+        // Sub-batches of general-float pairs: the tcgen05 kernel of sub-batch k+1 on `s` runs
+        // beside the certified rerank of sub-batch k on the lane's second stream.  The GEN kernel
+        // is bound by the tensor pipe (25 MMAs per tile) and leaves registers, 14 KB of shared
+        // memory and most issue slots of every SM free; the rerank is bound by L2 reads -- unlike
+        // the exact-mode pair of kernels (below) the two do not compete.
+        static const int gen_sub_env = [] { const char* e = getenv("SLAMB200_GEN_SUB"); return e ? atoi(e) : 4; }();
+        const int gsub = (gen_sub_env > 0 && n_pairs >= 2 * gen_sub_env) ? gen_sub_env : n_pairs;
+        const int g_nsub = (n_pairs + gsub - 1) / gsub;
+        if ((int)L.sub_ev.size() < g_nsub + 1) {
+          const size_t old_n = L.sub_ev.size();
+          L.sub_ev.resize(g_nsub + 1, nullptr);
+          for (size_t i = old_n; i < L.sub_ev.size(); i++)
+            CU(cudaEventCreateWithFlags(&L.sub_ev[i], cudaEventDisableTiming));
         }
-        if (grc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
-        ProfScope ps(c, s, SLAMB200_K_SIFT_GEN_RERANK);
-        launch_sift_gen_rerank(q->flags, q->f32, q->nrmf, nq, d_tc, d_pre, n_pairs, n_cta, n_slots, n_split,
-                               (const uint4*)L.cand_g.p, (uint4*)L.part.p,
-                               (uint2*)((char*)L.fb_list.p + FB_PART_BYTES), d_status + 1002,
-                               (unsigned long long*)L.fb_list.p, d_status + 1024, s, wide);
+        cudaStream_t gs2 = g_nsub > 1 ? L.stream2 : s;
+        const size_t cand_per_pair_g = 2 * (size_t)n_slots * n_rb * 256;
+        for (int k = 0; k < g_nsub; k++) {
+          const int p0 = k * gsub;
+          const int np = n_pairs - p0 < gsub ? n_pairs - p0 : gsub;
+          const int tiles_k = pre[p0 + np] - pre[p0];
+          uint4* cand_gk = (uint4*)L.cand_g.p + (size_t)p0 * cand_per_pair_g;
+          uint4* part_k = (uint4*)L.part.p + (size_t)p0 * n_split * nq;
+          int grc;
+          {
+            ProfScope ps(c, s, SLAMB200_K_SIFT_TC_GEN);
+            grc = launch_sift_tc_candidates(qmaps, q->flags, nq, d_tc + p0, d_pre + p0, np, tiles_k, n_cta,
+                                            n_slots, cand_gk, d_status, nullptr, 1, s, 0,
+                                            q->host_exact == 0 ? 1 : 0, wide);
+          }
+          if (grc != 0) return fail(SLAMB200_ERR_CUDA, "tcgen05 kernel configuration failed");
+          if (gs2 != s) {
+            CU(cudaEventRecord(L.sub_ev[k], s));
+            CU(cudaStreamWaitEvent(gs2, L.sub_ev[k], 0));
+          }
+          // the fallback bookkeeping (row count, per-row segment counters) starts from zero for
+          // every rerank launch: the table copy cleared it for the first one
+          if (k > 0)
+            CU(cudaMemsetAsync(d_status + 1002, 0, sizeof(int32_t) * (size_t)(1024 - 1002 + SIFT_GEN_FB_ITEMS), gs2));
+          ProfScope ps(c, gs2, SLAMB200_K_SIFT_GEN_RERANK);
+          launch_sift_gen_rerank(q->flags, q->f32, q->nrmf, nq, d_tc + p0, d_pre + p0, np, n_cta, n_slots, n_split,
+                                 (const uint4*)cand_gk, part_k,
+                                 (uint2*)((char*)L.fb_list.p + FB_PART_BYTES), d_status + 1002,
+                                 (unsigned long long*)L.fb_list.p, d_status + 1024, gs2, wide);
+        }
+        if (gs2 != s) {
+          CU(cudaEventRecord(L.sub_ev[g_nsub], gs2));
+          CU(cudaStreamWaitEvent(s, L.sub_ev[g_nsub], 0));
+        }
       }
       // Sub-batch pipeline (debug knob, default one sub-batch): the tcgen05 kernel of sub-batch
       // k+1 on `s` against the rerank / finalize kernels of sub-batch k on the lane's second

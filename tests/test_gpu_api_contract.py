@@ -1,5 +1,7 @@
 """GPU: ordering and validation contracts of the C ABI (include/slamb200.h) that the call sites of
 the reference rely on implicitly (one default stream, OpenCV Mats with arbitrary pitch)."""
+import threading
+
 import numpy as np
 import pytest
 
@@ -161,3 +163,35 @@ def test_match_batch_host_equals_resident_batch(ctx):
     # a Mat of the wrong type is refused with the library's error, nothing leaks or hangs
     with pytest.raises((Slamb200Error, ValueError)):
         ctx.matchBatchHost(q, [trains[0], qo], MatcherType.SIFT_BF, 0.7)
+
+
+def test_match_batch_host_sliced_narrowing_edges(ctx):
+    """The narrowing stage works on 1k-row slices of a Mat from several threads: a value that is
+    not an integer in a LATE slice sends the whole Mat down the fp32 path (its other slices were
+    already narrowed), and two calls at once -- plus a plain upload from a third thread while the
+    pool is taken -- give the single-threaded results."""
+    q = synth.sift_like(2100, 9500)
+    trains = [synth.sift_train_from_query(q, 5000 + 300 * i, 9501 + i) for i in range(9)]
+    trains[3][4700, 17] += np.float32(0.5)      # slice 4 of 5
+    trains[6][0, 0] = np.float32(300.0)         # out of the byte range, slice 0
+    want = [c_oracle.match_features(0, q, t, 0.7) for t in trains]
+    res = {}
+
+    def call(k):
+        res[k] = ctx.matchBatchHost(q, trains, MatcherType.SIFT_BF, 0.7)
+
+    def upload(k):
+        T = ctx.upload(trains[0])
+        Q = ctx.upload(q)
+        res[k] = ctx.matchFeatures(Q, T, MatcherType.SIFT_BF, 0.7)
+        Q.free(); T.free()
+
+    th = [threading.Thread(target=call, args=(0,)), threading.Thread(target=call, args=(1,)),
+          threading.Thread(target=upload, args=(2,))]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    for k in (0, 1):
+        assert len(res[k]) == len(want)
+        for g, w in zip(res[k], want):
+            assert np.array_equal(g, w)
+    assert np.array_equal(res[2], want[0])

@@ -683,3 +683,28 @@ def test_general_float_many_fallback_rows(ctx):
     assert n_fb >= 592, n_fb
     got, _ = ctx.batchFetch()
     assert np.array_equal(got[0], c_oracle.ratio_test(ridx, rdist, 0.95))
+
+
+def test_general_float_batch_in_sub_batches(ctx):
+    """Ten general-float pairs in one call: the batch runs as sub-batches whose certified rerank
+    overlaps the next sub-batch's tcgen05 kernel on a second stream, each rerank launch with its
+    own (re-zeroed) fallback bookkeeping.  Uncertifiable rows are planted in pairs of different
+    sub-batches (a few, and more than the split scan's grid), one pair is integer valued."""
+    rng = np.random.default_rng(93)
+    q, _ = synth.float_pair(600, 8, 1520)
+    trains = []
+    for p in range(10):
+        t = synth.float_pair(8, 3000 + 217 * p, 1521 + p)[1]
+        t[:200] = q[:200] + rng.normal(0, 1.5, (200, 128)).astype(np.float32)     # true neighbours
+        if p in (1, 6, 9):                                                           # near-ties: fallback rows
+            n_rows = 30 if p != 6 else 500
+            for k in range(n_rows):
+                rows = rng.choice(len(t), 40, replace=False)
+                t[rows] = q[k] + rng.normal(0, 2e-3, (40, 128)).astype(np.float32)
+        trains.append(t)
+    trains[4] = synth.sift_train_from_query(synth.sift_like(600, 77), 3500, 78)      # an exact-mode train set
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(t) for t in trains]
+    got = ctx.matchBatch(Q, Ts, MatcherType.SIFT_BF, 0.9)
+    for p, (g, t) in enumerate(zip(got, trains)):
+        assert np.array_equal(g, c_oracle.match_features(0, q, t, 0.9)), p
