@@ -614,7 +614,7 @@ __device__ __forceinline__ int scan_lookback(unsigned long long* scan_pair, uint
   return base;
 }
 
-template <bool ORB, int NT, int ROWS, int BAR>
+template <bool ORB, int NT, int ROWS, int BAR, int SU>
 __device__ __forceinline__ void tail_unit(const RerankParams& R, const CompactArgs& C, const TcPair* pairs_tab,
                                           const int32_t* prefix_tab, int pair, int rb, int q0, int unit,
                                           int units_per_pair, bool gen_pair, TailSmem<ROWS>& sm, int tid) {
@@ -711,81 +711,100 @@ __device__ __forceinline__ void tail_unit(const RerankParams& R, const CompactAr
     group_sync<BAR, NT>();
     const int n_surv = (C.dbg_skip & 1) ? 0 : sm.n_surv;
     // survivors: eight lanes per row, lane c ending up with candidate c of the row's best group
-    // (coalesced 16-byte slices + reduce-scatter, see tc_tail_fused_kernel)
+    // (coalesced 16-byte slices + reduce-scatter, see tc_tail_fused_kernel).  SU rows per lane group
+    // and pass, all their loads issued before the first is used: a block of a single-pair call is
+    // a chain of dependent memory round trips, and SU = 3 turns its three survivor passes into one.
     const int cand = lane & 7;
-    for (int i0 = 0; i0 < n_surv; i0 += NT / 8) {
-      const int i = i0 + (tid >> 3);
-      const bool have = i < n_surv;
-      const int r = have ? sm.list[i] : 0;
-      const int gg = have ? sm.g0[r] : 0;
-      const int col0 = gg * GROUP;
-      const int col = col0 + cand;
-      const bool ok = have && col < t_n;
-      const int qq = q0 + r;
-      uint32_t dist;   // exact integer distance of this lane's candidate: d^2 (SIFT) or Hamming (ORB)
-      if (ORB) {
-        const int cc = ok ? col : 0;
-        const uint4* tp = reinterpret_cast<const uint4*>(t_u8 + (size_t)cc * 32);
-        const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 32);
-        const uint4 t0 = tp[0], t1 = tp[1], qa = qp[0], qb = qp[1];
-        dist = (uint32_t)(__popc(qa.x ^ t0.x) + __popc(qa.y ^ t0.y) + __popc(qa.z ^ t0.z) + __popc(qa.w ^ t0.w) +
-                          __popc(qb.x ^ t1.x) + __popc(qb.y ^ t1.y) + __popc(qb.z ^ t1.z) + __popc(qb.w ^ t1.w));
-      } else {
-        // (rows up to the set's 256-row padding exist: a group never leaves the allocation)
-        const uint4* tp = reinterpret_cast<const uint4*>(t_u8 + (size_t)col0 * 128) + cand;
-        const uint4 qv = *(reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 128) + cand);
-        uint4 tv[8];
+    for (int i0 = 0; i0 < n_surv; i0 += SU * (NT / 8)) {
+      bool have[SU], ok[SU];
+      int rr[SU], gg[SU];
+      uint4 qv[SU], tv[SU][ORB ? 2 : 8], qw[SU];
+      uint32_t nn[SU];
 #pragma unroll
-        for (int k = 0; k < 8; k++) tv[k] = tp[8 * k];
-        const uint32_t nn = (uint32_t)t_nrm2[ok ? col : 0] + (uint32_t)R.q_nrm2[qq];
-        uint32_t pd[8];   // pd[k]: this lane's slice of q . (candidate row k)
+      for (int u = 0; u < SU; u++) {
+        const int i = i0 + u * (NT / 8) + (tid >> 3);
+        have[u] = i < n_surv;
+        rr[u] = have[u] ? sm.list[i] : 0;
+        gg[u] = have[u] ? sm.g0[rr[u]] : 0;
+        const int col0 = gg[u] * GROUP;
+        const int col = col0 + cand;
+        ok[u] = have[u] && col < t_n;
+        const int qq = q0 + rr[u];
+        if (ORB) {
+          const int cc = ok[u] ? col : 0;
+          const uint4* tp = reinterpret_cast<const uint4*>(t_u8 + (size_t)cc * 32);
+          const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 32);
+          tv[u][0] = tp[0]; tv[u][1] = tp[1]; qv[u] = qp[0]; qw[u] = qp[1];
+          nn[u] = 0;
+        } else {
+          // (rows up to the set's 256-row padding exist: a group never leaves the allocation)
+          const uint4* tp = reinterpret_cast<const uint4*>(t_u8 + (size_t)col0 * 128) + cand;
+          qv[u] = *(reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 128) + cand);
+          qw[u] = qv[u];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          uint32_t d = __dp4a(qv.x, tv[k].x, 0u);
-          d = __dp4a(qv.y, tv[k].y, d);
-          d = __dp4a(qv.z, tv[k].z, d);
-          pd[k] = __dp4a(qv.w, tv[k].w, d);
+          for (int k = 0; k < 8; k++) tv[u][ORB ? 0 : k] = tp[8 * k];
+          nn[u] = (uint32_t)t_nrm2[ok[u] ? col : 0] + (uint32_t)R.q_nrm2[qq];
         }
-        const bool b4 = (cand & 4) != 0, b2 = (cand & 2) != 0, b1 = (cand & 1) != 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t send = b4 ? pd[j] : pd[j + 4], keep = b4 ? pd[j + 4] : pd[j];
-          pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          const uint32_t send = b2 ? pd[j] : pd[j + 2], keep = b2 ? pd[j + 2] : pd[j];
-          pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        {
-          const uint32_t send = b1 ? pd[0] : pd[1], keep = b1 ? pd[1] : pd[0];
-          pd[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        }
-        dist = nn - 2u * pd[0];
       }
-      uint32_t k0 = ok ? ((dist << 3) | (uint32_t)cand) : 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
 #pragma unroll
-      for (int off = 1; off <= 4; off <<= 1) {
-        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, off);
-        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, off);
-        const uint32_t hi = max(k0, o0);
-        k0 = min(k0, o0);
-        k1 = min(hi, min(k1, o1));
-      }
-      if (have && cand == 0 && k0 != 0xFFFFFFFFu) {
-        const uint32_t x0 = k0 >> 3;
-        // self check: the group's exact minimum must equal twice the tensor-core value
-        if ((float)x0 != 2.0f * sm.v0[r]) atomicOr(R.err_flag, 1);
-        // second distance: inside the group, or the bound from outside it (exact values both)
-        const float Lr = sm.L[r];
-        float x1 = Lr < INF ? 2.0f * Lr : -1.0f;
-        if (k1 != 0xFFFFFFFFu) {
-          const float x2 = (float)(k1 >> 3);
-          x1 = (x1 < 0.0f || x2 < x1) ? x2 : x1;
+      for (int u = 0; u < SU; u++) {
+        uint32_t dist;   // exact integer distance of this lane's candidate: d^2 (SIFT) or Hamming (ORB)
+        if (ORB) {
+          const uint4 t0 = tv[u][0], t1 = tv[u][ORB ? 1 : 0], qa = qv[u], qb = qw[u];
+          dist = (uint32_t)(__popc(qa.x ^ t0.x) + __popc(qa.y ^ t0.y) + __popc(qa.z ^ t0.z) + __popc(qa.w ^ t0.w) +
+                            __popc(qb.x ^ t1.x) + __popc(qb.y ^ t1.y) + __popc(qb.z ^ t1.z) + __popc(qb.w ^ t1.w));
+        } else {
+          uint32_t pd[8];   // pd[k]: this lane's slice of q . (candidate row k)
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const uint4 t = tv[u][ORB ? 0 : k];
+            uint32_t d = __dp4a(qv[u].x, t.x, 0u);
+            d = __dp4a(qv[u].y, t.y, d);
+            d = __dp4a(qv[u].z, t.z, d);
+            pd[k] = __dp4a(qv[u].w, t.w, d);
+          }
+          const bool b4 = (cand & 4) != 0, b2 = (cand & 2) != 0, b1 = (cand & 1) != 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t send = b4 ? pd[j] : pd[j + 4], keep = b4 ? pd[j + 4] : pd[j];
+            pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const uint32_t send = b2 ? pd[j] : pd[j + 2], keep = b2 ? pd[j + 2] : pd[j];
+            pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+          {
+            const uint32_t send = b1 ? pd[0] : pd[1], keep = b1 ? pd[1] : pd[0];
+            pd[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+          dist = nn[u] - 2u * pd[0];
         }
-        sm.idx[r] = gg * GROUP + (int)(k0 & 7u);
-        sm.d0[r] = ORB ? (float)x0 : sqrtf((float)x0);
-        sm.d1[r] = ORB ? x1 : (x1 >= 0.0f ? sqrtf(x1) : -1.0f);
+        uint32_t k0 = ok[u] ? ((dist << 3) | (uint32_t)cand) : 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+#pragma unroll
+        for (int off = 1; off <= 4; off <<= 1) {
+          const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, off);
+          const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, off);
+          const uint32_t hi = max(k0, o0);
+          k0 = min(k0, o0);
+          k1 = min(hi, min(k1, o1));
+        }
+        if (have[u] && cand == 0 && k0 != 0xFFFFFFFFu) {
+          const int r = rr[u];
+          const uint32_t x0 = k0 >> 3;
+          // self check: the group's exact minimum must equal twice the tensor-core value
+          if ((float)x0 != 2.0f * sm.v0[r]) atomicOr(R.err_flag, 1);
+          // second distance: inside the group, or the bound from outside it (exact values both)
+          const float Lr = sm.L[r];
+          float x1 = Lr < INF ? 2.0f * Lr : -1.0f;
+          if (k1 != 0xFFFFFFFFu) {
+            const float x2 = (float)(k1 >> 3);
+            x1 = (x1 < 0.0f || x2 < x1) ? x2 : x1;
+          }
+          sm.idx[r] = gg[u] * GROUP + (int)(k0 & 7u);
+          sm.d0[r] = ORB ? (float)x0 : sqrtf((float)x0);
+          sm.d1[r] = ORB ? x1 : (x1 >= 0.0f ? sqrtf(x1) : -1.0f);
+        }
       }
     }
   }
@@ -1256,8 +1275,8 @@ sift_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcTai
       group_sync<BAR_TAIL, 64>();
       if (sm.flag && !(TT.dbg_skip & 4)) {
         const int q0 = rb * 2 * BM + (int)rank * BM;
-        if (P.fp8) tail_unit<true, 64, 128, BAR_TAIL>(TT.R, TT.C, pairs_tab, prefix_tab, pair, rb, q0, rb * 2 + (int)rank, P.n_rb * 2, false, sm, tid);
-        else tail_unit<false, 64, 128, BAR_TAIL>(TT.R, TT.C, pairs_tab, prefix_tab, pair, rb, q0, rb * 2 + (int)rank, P.n_rb * 2, false, sm, tid);
+        if (P.fp8) tail_unit<true, 64, 128, BAR_TAIL, 1>(TT.R, TT.C, pairs_tab, prefix_tab, pair, rb, q0, rb * 2 + (int)rank, P.n_rb * 2, false, sm, tid);
+        else tail_unit<false, 64, 128, BAR_TAIL, 1>(TT.R, TT.C, pairs_tab, prefix_tab, pair, rb, q0, rb * 2 + (int)rank, P.n_rb * 2, false, sm, tid);
       }
     }
   }
@@ -1876,7 +1895,7 @@ tc_tail_fused_kernel(const RerankParams R, int32_t* __restrict__ knn_idx, float*
 // The match path's tail as one kernel behind the tcgen05 kernel: a block per (256 query rows,
 // frame pair).  The look-back waits only on blocks of the same pair with a smaller index, which the
 // hardware dispatches first.
-template <bool ORB>
+template <bool ORB, int SU>
 __global__ void __launch_bounds__(256)
 tc_tail_compact_kernel(const RerankParams R, const CompactArgs C, const __grid_constant__ InlineTables IT) {
   __shared__ TailSmem<256> sm;
@@ -1886,7 +1905,7 @@ tc_tail_compact_kernel(const RerankParams R, const CompactArgs C, const __grid_c
   const int32_t* prefix_tab = IT.n ? IT.prefix : R.tile_prefix;
   const int pair = blockIdx.y;
   const bool gen_pair = R.q_flags[0] != 0 || pairs_tab[pair].t_flags[0] != 0;
-  tail_unit<ORB, 256, 256, 0>(R, C, pairs_tab, prefix_tab, pair, blockIdx.x, blockIdx.x * 256, blockIdx.x, gridDim.x, gen_pair, sm,
+  tail_unit<ORB, 256, 256, 0, SU>(R, C, pairs_tab, prefix_tab, pair, blockIdx.x, blockIdx.x * 256, blockIdx.x, gridDim.x, gen_pair, sm,
                               threadIdx.x);
 }
 
@@ -2479,14 +2498,25 @@ void launch_tc_tail_compact(const int32_t* q_flags, const uint8_t* q_u8, const i
   static PerDeviceOnce carve_once;
   carve_once.run([] {
     if (getenv("SLAMB200_NO_CARVEOUT")) return true;
-    cudaFuncSetAttribute(tc_tail_compact_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(tc_tail_compact_kernel<true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(tc_tail_compact_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(tc_tail_compact_kernel<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(tc_tail_compact_kernel<true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(tc_tail_compact_kernel<false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     return true;
   });
   dim3 grid((nq + 255) / 256, n_pairs);
-  if (orb) launch_pdl(tc_tail_compact_kernel<true>, grid, dim3(256), 0, s, R, C, IT);
-  else launch_pdl(tc_tail_compact_kernel<false>, grid, dim3(256), 0, s, R, C, IT);
+  // a call of a few pairs is a chain of memory round trips (three survivor rows per lane group in
+  // flight: one pass instead of three); a batch wants the occupancy of the 64-register form
+  if (n_pairs <= TC_INLINE_MAX) {
+    if (orb) launch_pdl(tc_tail_compact_kernel<true, 3>, grid, dim3(256), 0, s, R, C, IT);
+    else launch_pdl(tc_tail_compact_kernel<false, 3>, grid, dim3(256), 0, s, R, C, IT);
+  } else {
+    if (orb) launch_pdl(tc_tail_compact_kernel<true, 1>, grid, dim3(256), 0, s, R, C, IT);
+    else launch_pdl(tc_tail_compact_kernel<false, 1>, grid, dim3(256), 0, s, R, C, IT);
+  }
   COUNT_LAUNCH();
 }

@@ -103,3 +103,20 @@ def test_window_of_equal_frames_forms_agree(tail_ctx):
         assert all(np.array_equal(a, b) for a, b in zip(got3, got)), form
     for k in (0, 47):
         assert np.array_equal(got3[k], c_oracle.match_features(0, q, trains[k], 0.7))
+
+
+def test_lookback_compaction_is_stable_under_load(tail_ctx):
+    """The one-kernel tail orders its output by a look-back over blocks that run concurrently; 40
+    launches of a 40-pair batch (1600 blocks in flight, more than fit on the GPU at once) must give
+    the same lists every time, equal to the two-kernel form's."""
+    ctx = tail_ctx
+    q = synth.sift_like(5000, 61)
+    trains = [synth.sift_train_from_query(q, 3000 + 257 * (i % 7), 62 + i) for i in range(40)]
+    Q = ctx.upload(q)
+    Ts = [ctx.upload(t) for t in trains]
+    ctx.debug_tail_form(1)
+    want = ctx.matchBatch(Q, Ts, MatcherType.SIFT_BF, 0.7)
+    ctx.debug_tail_form(2)
+    for it in range(40):
+        got = ctx.matchBatch(Q, Ts, MatcherType.SIFT_BF, 0.7)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want)), it

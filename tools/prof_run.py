@@ -18,6 +18,15 @@ if which == "sift":
         ctx.matchBatchEnqueue(Q, Ts, MatcherType.SIFT_BF, 0.7, st)
     torch.cuda.synchronize()
     print("ok", [len(m) for m in ctx.batchFetch(st)[0]][:4])
+elif which == "single":
+    # the per-pair drop-in call's kernels: pair table in the parameters, tcgen05 kernel, one tail kernel
+    q = synth.sift_like(10000, 3000)
+    Q = ctx.upload(q)
+    T = ctx.upload(synth.sift_train_from_query(q, 10000, 3001))
+    for _ in range(4):
+        ctx.matchBatchEnqueue(Q, [T], MatcherType.SIFT_BF, 0.7, st)
+    torch.cuda.synchronize()
+    print("ok", len(ctx.batchFetch(st)[0][0]))
 elif which == "orb":
     q, t = synth.orb_pair(10000, 10000, 2001)
     Q, T = ctx.upload(q), ctx.upload(t)
