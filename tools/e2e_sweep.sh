@@ -1,2 +1,7 @@
-for wc in "3 24" "4 18" "5 14" "6 12" "6 8" "7 10"; do set -- $wc; timeout 300 python bench.py --steps 3 --warmup 3 --e2e-steps 8 --e2e-workers $1 --e2e-chunk $2 --no-cpu-baseline --no-extras 2>/dev/null | python -c "
-import json,sys;d=json.loads(sys.stdin.read());print('workers $1 chunk $2 ->', round(d['e2e']['value']), 'pairs/s')"; done
+# e2e A/B on one box: alternates the settings so that the shared host's drift hits both alike
+for rep in 1 2 3; do
+for cfg in "SLAMB200_UPLOAD_DMA=0 SLAMB200_HOST_CHUNK=14" "SLAMB200_UPLOAD_DMA=1 SLAMB200_HOST_CHUNK=14" "SLAMB200_UPLOAD_DMA=0 SLAMB200_HOST_CHUNK=7" "SLAMB200_UPLOAD_DMA=1 SLAMB200_HOST_CHUNK=28"; do
+env $cfg python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline --e2e-steps 20 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); e=d['e2e']; print('$cfg', 'e2e', round(e['value']), 'floor', round(e['host_floor']['pairs_per_s_floor']))"
+done; done
