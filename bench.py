@@ -304,6 +304,12 @@ def run_b200(args, rank, world, local):
     # the contract's W warm-up steps, repeated until at least 0.25 s of the same load has run so
     # that the clock sampler sees the GPU under this kernel even when K steps last milliseconds
     warm_run = 0
+    # the warm-up steps carry events around EVERY kernel class (the tail's and the compaction's
+    # durations come from them); the timed region only around the dominant kernel, whose duration
+    # the roofline line needs live -- an event between two kernels is a boundary the device
+    # drains to, and six of them per step cost a 0.5 ms step of the 8-rank run several per cent
+    ctx.profile_enable(True)
+    ctx.profile_read()
     while True:
         for _ in range(args.warmup):
             step()
@@ -311,8 +317,9 @@ def run_b200(args, rank, world, local):
         torch.cuda.synchronize()
         if time.perf_counter() - t_load0 >= 0.25 or args.warmup == 0:
             break
+    prof_warm = ctx.profile_read()
     barrier()
-    ctx.profile_enable(True)
+    ctx.profile_enable(True, kinds=None if args.events_all else ["sift_tc"])
     ctx.profile_read()
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -372,10 +379,12 @@ def run_b200(args, rank, world, local):
                 "frac_of_burst": achieved / burst, "frac_of_sustained": achieved / sustained,
                 "kernel_ms_per_step": tc_ms / args.steps, "kernel_launches_per_step": tc_n / args.steps,
                 "algorithmic_flop_per_step": FLOP_PER_PAIR * len(pairs),
-                "other_kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()
+                "other_kernels_ms_per_step": {k: v[0] / max(warm_run, 1) for k, v in prof_warm.items()
                                               if k != "sift_tc" and v[1] > 0},
-                "other_kernels_note": "sift_rerank = tc_tail_fused_kernel (slot merge + best-group rerank + "
-                                      "ratio test), finalize = compact_kernel (ordered compaction)",
+                "other_kernels_note": "measured over the warm-up steps (the timed region carries events around the "
+                                      "dominant kernel only); sift_rerank = the tail (slot merge + best-group rerank + "
+                                      "ratio test; with up to 32 pairs per rank also the ordered compaction), "
+                                      "finalize = compact_kernel (ordered compaction)",
                 "kernel_share_of_step": tc_ms / ms_total
                 if world == 1 else None,
                 "traffic": TRAFFIC_BYTES_PER_LAUNCH_N1 if world == 1 else None,
@@ -984,6 +993,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--events-all", action="store_true",
+                    help="developer A/B: events around every kernel class in the timed region too")
     ap.add_argument("--e2e-uploaders", type=int, default=-1,
                     help="narrowing threads inside slamb200_match_batch_host (-1: pack threads + 1)")
     ap.add_argument("--e2e-pack-threads", type=int, default=-1,

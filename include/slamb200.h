@@ -368,6 +368,10 @@ int slamb200_batch_scores_fetch(slamb200_ctx* ctx, int32_t* counts, int32_t* bes
 #define SLAMB200_K_SIFT_DESC 12 /* SIFT base image blur + descriptor kernel */
 #define SLAMB200_K_COUNT 13
 int slamb200_profile_enable(slamb200_ctx* ctx, int on);
+/* The same for a subset of the kernel classes (bit k = SLAMB200_K_*; 0 = off): a timed region that
+ * wants the dominant kernel's duration pays for two events per launch of THAT kernel only -- an
+ * event between two kernels is a boundary the device must drain to. */
+int slamb200_profile_enable_kinds(slamb200_ctx* ctx, unsigned kinds);
 /* Synchronises, then returns the summed device time (ms) and the launch count of each kernel
  * class since the last read; ms and launches have SLAMB200_K_COUNT entries. */
 int slamb200_profile_read(slamb200_ctx* ctx, double* ms, int64_t* launches);

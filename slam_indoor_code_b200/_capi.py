@@ -69,6 +69,7 @@ SYMBOLS = {
     "slamb200_set_match_batch_enqueue": (_i, [_vp, _i, _vp, _vp, _i, _d]),
     "slamb200_set_batch_fetch": (_i, [_vp, _vp, _i, _vp, _vp]),
     "slamb200_profile_enable": (_i, [_vp, _i]),
+    "slamb200_profile_enable_kinds": (_i, [_vp, ctypes.c_uint]),
     "slamb200_profile_read": (_i, [_vp, _vp, _vp]),
 }
 

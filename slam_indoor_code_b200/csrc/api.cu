@@ -98,6 +98,7 @@ struct ProfEvent {
 struct slamb200_ctx {
   int device = 0;
   int profile = 0;
+  unsigned profile_kinds = 0xFFFFFFFFu;   // kernel classes that get events while profile != 0
   std::mutex prof_mu;
   std::vector<ProfEvent> prof;
   cudaMemPool_t pool = nullptr;
@@ -387,7 +388,8 @@ struct ProfScope {
   cudaStream_t s;
   ProfEvent ev;
   bool on;
-  ProfScope(slamb200_ctx* c_, cudaStream_t s_, int kind) : c(c_), s(s_), on(c_->profile != 0) {
+  ProfScope(slamb200_ctx* c_, cudaStream_t s_, int kind)
+      : c(c_), s(s_), on(c_->profile != 0 && ((c_->profile_kinds >> kind) & 1u) != 0) {
     if (!on) return;
     ev.kind = kind;
     if (cudaEventCreate(&ev.a) != cudaSuccess || cudaEventCreate(&ev.b) != cudaSuccess) { on = false; return; }
@@ -404,6 +406,14 @@ struct ProfScope {
 extern "C" int slamb200_profile_enable(slamb200_ctx* c, int on) {
   if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
   c->profile = on ? 1 : 0;
+  c->profile_kinds = 0xFFFFFFFFu;
+  return SLAMB200_OK;
+}
+
+extern "C" int slamb200_profile_enable_kinds(slamb200_ctx* c, unsigned kinds) {
+  if (!c) return fail(SLAMB200_ERR_INVALID, "ctx is NULL");
+  c->profile = kinds ? 1 : 0;
+  c->profile_kinds = kinds;
   return SLAMB200_OK;
 }
 

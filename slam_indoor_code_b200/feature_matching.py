@@ -105,8 +105,16 @@ class Context:
         f.restype = ctypes.c_int
         check(f(self._h, int(form)))
 
-    def profile_enable(self, on=True):
-        check(self._lib.slamb200_profile_enable(self._h, 1 if on else 0))
+    def profile_enable(self, on=True, kinds=None):
+        """Per-kernel-class device times (profile_read).  kinds: names from KERNELS to restrict the
+        events to (a timed region that only wants its dominant kernel's duration)."""
+        if on and kinds is not None:
+            mask = 0
+            for k in kinds:
+                mask |= 1 << self.KERNELS.index(k)
+            check(self._lib.slamb200_profile_enable_kinds(self._h, mask))
+        else:
+            check(self._lib.slamb200_profile_enable(self._h, 1 if on else 0))
 
     def profile_read(self):
         """{kernel: (summed device ms, launches)} since the last read (synchronises)."""
