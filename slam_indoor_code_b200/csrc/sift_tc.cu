@@ -557,7 +557,6 @@ struct CompactArgs {
   slamb200_dmatch* out;       // [pair][cap]
   int cap;
   int32_t* n_out;             // [pair]
-  int dbg_skip;               // timing experiments only (TcTail::dbg_skip)
 };
 
 __device__ __forceinline__ unsigned long long scan_ld(const unsigned long long* p) {
@@ -709,7 +708,7 @@ __device__ __forceinline__ void tail_unit(const RerankParams& R, const CompactAr
       if (survive) sm.list[at + __popc(bal & ((1u << lane) - 1))] = (uint16_t)r;
     }
     group_sync<BAR, NT>();
-    const int n_surv = (C.dbg_skip & 1) ? 0 : sm.n_surv;
+    const int n_surv = sm.n_surv;
     // survivors: eight lanes per row, lane c ending up with candidate c of the row's best group
     // (coalesced 16-byte slices + reduce-scatter, see tc_tail_fused_kernel).  SU rows per lane group
     // and pass, all their loads issued before the first is used: a block of a single-pair call is
@@ -829,7 +828,7 @@ __device__ __forceinline__ void tail_unit(const RerankParams& R, const CompactAr
     }
     const int n = __shfl_sync(0xffffffffu, incl, 31);
     if (lane < ROWS / 32) sm.keep_off[lane] = incl - c;
-    const int base = (C.dbg_skip & 2) ? 0 : scan_lookback(C.scan + (size_t)pair * units_per_pair, C.epoch, unit, n, lane);
+    const int base = scan_lookback(C.scan + (size_t)pair * units_per_pair, C.epoch, unit, n, lane);
     if (lane == 0) {
       sm.base = base;
       if (unit == units_per_pair - 1) C.n_out[pair] = base + n;
@@ -854,8 +853,6 @@ struct TcTail {
   CompactArgs C;              // scan: one word per (pair, row block, CTA of the pair)
   int32_t* seg_done;          // [pair][row block][CTA of the pair]: segments flushed so far; zero
                               // before the first launch, left at zero by every launch
-  int dbg_skip;               // timing experiments (SLAMB200_TAIL_SKIP; results void): 1 no survivors,
-                              // 2 no look-back, 4 no tail work at all
 };
 static_assert(sizeof(TailSmem<128>) <= SMEM_TAIL, "tail scratch does not fit its shared-memory area");
 
@@ -1273,7 +1270,7 @@ sift_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcTai
         sm.flag = mine;
       }
       group_sync<BAR_TAIL, 64>();
-      if (sm.flag && !(TT.dbg_skip & 4)) {
+      if (sm.flag) {
         const int q0 = rb * 2 * BM + (int)rank * BM;
         if (P.fp8) tail_unit<true, 64, 128, BAR_TAIL, 1>(TT.R, TT.C, pairs_tab, prefix_tab, pair, rb, q0, rb * 2 + (int)rank, P.n_rb * 2, false, sm, tid);
         else tail_unit<false, 64, 128, BAR_TAIL, 1>(TT.R, TT.C, pairs_tab, prefix_tab, pair, rb, q0, rb * 2 + (int)rank, P.n_rb * 2, false, sm, tid);
@@ -2386,8 +2383,6 @@ int launch_sift_tc_match(const void* q_tmaps_host_384B, const int32_t* q_flags, 
   R.prune = (ratio >= 0.0 && ratio < 1e300) ? 1 : 0; R.ratio = ratio;
   TT.C.scan = scan; TT.C.epoch = epoch; TT.C.out = out; TT.C.cap = cap; TT.C.n_out = n_out;
   TT.seg_done = seg_done;
-  static const int skip = getenv("SLAMB200_TAIL_SKIP") ? atoi(getenv("SLAMB200_TAIL_SKIP")) : 0;
-  TT.dbg_skip = skip; TT.C.dbg_skip = skip;
   const dim3 grid(2 * n_cta_pairs);
   sift_tc_kernel<false, false, false, true><<<grid, TC_THREADS, SMEM_BYTES_TAIL, s>>>(P, TT, IT);
   COUNT_LAUNCH();
@@ -2491,7 +2486,7 @@ void launch_tc_tail_compact(const int32_t* q_flags, const uint8_t* q_u8, const i
   R.work = nullptr; R.work_v0 = nullptr; R.work_n = nullptr;
   R.prune = (ratio >= 0.0 && ratio < 1e300) ? 1 : 0; R.ratio = ratio;
   CompactArgs C;
-  C.scan = scan; C.epoch = epoch; C.out = out; C.cap = cap; C.n_out = n_out; C.dbg_skip = 0;
+  C.scan = scan; C.epoch = epoch; C.out = out; C.cap = cap; C.n_out = n_out;
   // The tcgen05 kernel in front of this one (and behind it, in a loop of calls) runs with the
   // largest shared-memory carve-out; asking for the same one here spares the SMs a reconfiguration
   // of their L1 / shared split between the two kernels of a call.
