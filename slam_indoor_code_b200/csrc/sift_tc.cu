@@ -557,6 +557,11 @@ struct CompactArgs {
   slamb200_dmatch* out;       // [pair][cap]
   int cap;
   int32_t* n_out;             // [pair]
+  // two-kernel form (COMPACT = false) instead: what compact_kernel consumes
+  int32_t* knn_idx;           // [pair][nq][2]
+  float* knn_dist;            // [pair][nq][2]
+  uint8_t* flags;             // [pair][nq]
+  int32_t* chunk_cnt;         // [pair][units per pair]
 };
 
 __device__ __forceinline__ unsigned long long scan_ld(const unsigned long long* p) {
@@ -613,7 +618,7 @@ __device__ __forceinline__ int scan_lookback(unsigned long long* scan_pair, uint
   return base;
 }
 
-template <bool ORB, int NT, int ROWS, int BAR, int SU>
+template <bool ORB, int NT, int ROWS, int BAR, int SU, bool COMPACT = true>
 __device__ __forceinline__ void tail_unit(const RerankParams& R, const CompactArgs& C, const TcPair* pairs_tab,
                                           const int32_t* prefix_tab, int pair, int rb, int q0, int unit,
                                           int units_per_pair, bool gen_pair, TailSmem<ROWS>& sm, int tid) {
@@ -710,7 +715,10 @@ __device__ __forceinline__ void tail_unit(const RerankParams& R, const CompactAr
     group_sync<BAR, NT>();
     const int n_surv = sm.n_surv;
     // survivors: eight lanes per row, lane c ending up with candidate c of the row's best group
-    // (coalesced 16-byte slices + reduce-scatter, see tc_tail_fused_kernel).  SU rows per lane group
+    // (coalesced 16-byte slices + reduce-scatter: the group's eight train rows are 1 KB of consecutive
+    // bytes, so each load instruction takes ONE 128-byte row per survivor row, lane c its 16-byte slice;
+    // a lane reading its own candidate row touched 32 lines per instruction and the kernel sat on the
+    // L1 tag stage).  SU rows per lane group
     // and pass, all their loads issued before the first is used: a block of a single-pair call is
     // a chain of dependent memory round trips, and SU = 3 turns its three survivor passes into one.
     const int cand = lane & 7;
@@ -818,6 +826,24 @@ __device__ __forceinline__ void tail_unit(const RerankParams& R, const CompactAr
     if (lane == 0) sm.keep_mask[r >> 5] = bal;
   }
   group_sync<BAR, NT>();
+  if (!COMPACT) {
+    // two-kernel form: per-row verdicts and the unit's kept count for compact_kernel
+    for (int r = tid; r < ROWS; r += NT) {
+      const int q = q0 + r;
+      if (q >= R.nq) continue;
+      const size_t o = ((size_t)pair * R.nq + q) * 2;
+      C.knn_idx[o] = sm.idx[r];
+      C.knn_dist[o] = sm.d0[r];
+      C.flags[(size_t)pair * R.nq + q] = (uint8_t)((sm.keep_mask[r >> 5] >> (r & 31)) & 1u);
+    }
+    if (warp == 0) {
+      int c = lane < ROWS / 32 ? __popc(sm.keep_mask[lane]) : 0;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+      if (lane == 0) C.chunk_cnt[pair * units_per_pair + unit] = c;
+    }
+    return;
+  }
   if (warp == 0) {
     const int c = lane < ROWS / 32 ? __popc(sm.keep_mask[lane]) : 0;
     int incl = c;
@@ -1666,227 +1692,24 @@ __global__ void __launch_bounds__(256) orb_rerank_kernel(const RerankParams R) {
   }
 }
 
-// ================= fused tail of the match path =================
+// ================= fused tail of the match path, two-kernel form =================
 // merge -> rerank (best group only) -> ratio test for one block of 256 query rows of one frame
-// pair, in one kernel: the three passes above exchange their intermediate results (work list,
-// partial records) through shared memory instead of HBM, and a single-pair call loses two
-// dependent launches.  Output is what compact_kernel (finalize.cu) consumes: the kept flag, the
-// best index and distance per row, and the block's kept count.  General-float pairs (their
-// records come from the certified rerank) take the plain finalize branch.  The arithmetic of each
-// step is that of sift_merge_kernel / sift_rerank_lite_kernel / orb_rerank_lite_kernel /
-// finalize_rows_kernel; the raw k-NN output keeps the separate kernels.
-template <bool ORB>
+// pair (tail_unit with COMPACT = false).  Output is what compact_kernel (finalize.cu) consumes: the
+// kept flag, the best index and distance per row, and the block's kept count.  General-float
+// pairs (their records come from the certified rerank) take the plain finalize branch.  No block
+// waits for another here, which is why large windows use this form (see tail_unit).
+template <bool ORB, int SU>
 __global__ void __launch_bounds__(256)
-tc_tail_fused_kernel(const RerankParams R, int32_t* __restrict__ knn_idx, float* __restrict__ knn_dist,
-                     uint8_t* __restrict__ flags, int32_t* __restrict__ chunk_cnt) {
-  __shared__ int n_valid_s, n_surv_s;
-  __shared__ uint16_t s_list[256];
-  __shared__ float s_v0[256], s_L[256], s_d0[256], s_d1[256];
-  __shared__ int s_g0[256], s_idx[256];
-  const int pair = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = blockIdx.x * 256 + tid;
+tc_tail_fused_kernel(const RerankParams R, const CompactArgs C, const __grid_constant__ InlineTables IT) {
+  __shared__ TailSmem<256> sm;
   PDL_TRIGGER();
   PDL_WAIT();
-  const TcPair* pr = R.pairs + pair;
-  const float INF = __int_as_float(0x7f800000);
-  int keep = 0;
-  if (R.q_flags[0] != 0 || pr->t_flags[0] != 0) {
-    // general-float pair (block-uniform): finalize its records
-    if (q < R.nq) {
-      uint4 r = make_uint4(ABSENT_KEY, 0xFFFFFFFFu, ABSENT_KEY, 0xFFFFFFFFu);
-      for (int sp = 0; sp < R.n_split; sp++) {
-        const uint4 p = R.part[((size_t)pair * R.n_split + sp) * R.nq + q];
-        if (p.y != 0xFFFFFFFFu) part_top2_insert(r, p.x, p.y);
-        if (p.w != 0xFFFFFFFFu) part_top2_insert(r, p.z, p.w);
-      }
-      const bool has0 = r.y != 0xFFFFFFFFu, has1 = r.w != 0xFFFFFFFFu;
-      const float d0 = __uint_as_float(r.x), d1 = __uint_as_float(r.z);
-      const size_t o = ((size_t)pair * R.nq + q) * 2;
-      knn_idx[o] = has0 ? (int32_t)r.y : -1;
-      knn_dist[o] = has0 ? d0 : 0.f;
-      keep = (has0 && has1 && (double)d0 < __dmul_rn(R.ratio, (double)d1)) ? 1 : 0;
-      flags[(size_t)pair * R.nq + q] = (uint8_t)keep;
-    }
-  } else {
-    if (tid == 0) {
-      // slots the tcgen05 kernel wrote for this (pair, query block): see sift_merge_kernel
-      const int n_tiles = R.tile_prefix[pair + 1] - R.tile_prefix[pair];
-      int nv = 0;
-      if (n_tiles > 0) {
-        const int n_rb = R.nq_pad / 256;
-        const int n_cb = n_tiles / n_rb;
-        const int first = owner_cta(n_tiles, R.n_cta, blockIdx.x * n_cb, R.wide != 0);
-        const int last = owner_cta(n_tiles, R.n_cta, (blockIdx.x + 1) * n_cb - 1, R.wide != 0);
-        nv = last - first + 1;               // one merged record per share
-        if (nv > R.n_slots) nv = R.n_slots;
-      }
-      n_valid_s = nv;
-      n_surv_s = 0;
-    }
-    __syncthreads();
-    const int n_valid = n_valid_s;
-    bool survive = false;
-    float v0 = INF, v1 = INF, s0 = INF;
-    int g0 = 0xFFFF, g1 = 0xFFFF;
-    if (q < R.nq) {
-      for (int sb = 0; sb < n_valid; sb += 4) {
-        uint4 recs[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++)   // independent loads first, then the dependent merge
-          recs[j] = sb + j < n_valid ? R.cand[((size_t)pair * R.n_slots + sb + j) * R.nq_pad + q]
-                                     : make_uint4(0x7f800000u, 0x7f800000u, 0x7f800000u, 0xFFFFFFFFu);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint4 rec = recs[j];
-          const float a = __uint_as_float(rec.x), b = __uint_as_float(rec.y);
-          float sa = __uint_as_float(rec.z);
-          int ia = (int)(rec.w & 0xFFFFu), ib = (int)(rec.w >> 16);
-          if (ORB) {
-            if (a > ORB_PAD_THRESHOLD) ia = 0xFFFF;
-            if (b > ORB_PAD_THRESHOLD) ib = 0xFFFF;
-            if (sa > ORB_PAD_THRESHOLD) sa = INF;
-          }
-          if (ia != 0xFFFF) {
-            if (lt_fi(a, ia, v0, g0)) { v1 = v0; g1 = g0; v0 = a; g0 = ia; s0 = sa; }
-            else if (lt_fi(a, ia, v1, g1)) { v1 = a; g1 = ia; }
-          }
-          if (ib != 0xFFFF) {
-            if (lt_fi(b, ib, v1, g1)) { v1 = b; g1 = ib; }
-          }
-        }
-      }
-      const bool has0 = g0 != 0xFFFF;
-      survive = has0;
-      const float L = fminf(s0, v1);
-      if (R.prune && has0 && L < INF) {
-        const float d0 = ORB ? 2.0f * v0 : sqrtf(2.0f * v0), D1 = ORB ? 2.0f * L : sqrtf(2.0f * L);
-        if (!((double)d0 < __dmul_rn(R.ratio, (double)D1))) survive = false;   // exact pruning
-      }
-      s_v0[tid] = v0; s_L[tid] = L; s_g0[tid] = g0;
-    }
-    {
-      const unsigned bal = __ballot_sync(0xffffffffu, survive);
-      int base = 0;
-      if (lane == 0 && bal) base = atomicAdd(&n_surv_s, __popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (survive) s_list[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)tid;
-    }
-    __syncthreads();
-    const int n_surv = n_surv_s;
-    // Survivors of the block: eight lanes per row (four rows per warp, 32 per pass of the block),
-    // lane c ending up with candidate c of the row's best group.  The group's eight train rows are
-    // 1 KB of consecutive bytes: each load instruction takes ONE 128-byte row per survivor row,
-    // lane c its 16-byte slice c (coalesced: four cache lines per instruction; a lane reading its
-    // own candidate row touched 32 lines per instruction and the kernel was bound by the L1's
-    // tag stage, ncu l1tex 80 %), multiplies it with its slice of the query row, and a
-    // reduce-scatter over the eight lanes (4 + 2 + 1 shuffles) leaves candidate c's dot product
-    // in lane c.  The (distance, column) pair of a candidate fits one 32-bit key -- d^2 < 2^22
-    // for integer-valued rows, Hamming <= 256, three bits for the position inside the group -- so
-    // the top-2 of a group costs three rounds of two shuffles and four min / max.
-    const int cand = lane & 7, sub = lane >> 3;
-    for (int i0 = 0; i0 < n_surv; i0 += 32) {
-      const int i = i0 + warp * 4 + sub;
-      const bool have = i < n_surv;
-      const int r = have ? s_list[i] : 0;
-      const int col0 = s_g0[r] * GROUP;
-      const int col = col0 + cand;
-      const bool ok = have && col < pr->t_n;
-      const int qq = blockIdx.x * 256 + r;
-      uint32_t dist;   // exact integer distance of this lane's candidate: d^2 (SIFT) or Hamming (ORB)
-      if (ORB) {
-        const int cc = ok ? col : 0;
-        const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)cc * 32);
-        const uint4* qp = reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 32);
-        const uint4 t0 = tp[0], t1 = tp[1], q0 = qp[0], q1 = qp[1];
-        dist = (uint32_t)(__popc(q0.x ^ t0.x) + __popc(q0.y ^ t0.y) + __popc(q0.z ^ t0.z) + __popc(q0.w ^ t0.w) +
-                          __popc(q1.x ^ t1.x) + __popc(q1.y ^ t1.y) + __popc(q1.z ^ t1.z) + __popc(q1.w ^ t1.w));
-      } else {
-        // (rows up to the set's 256-row padding exist: a group never leaves the allocation)
-        const uint4* tp = reinterpret_cast<const uint4*>(pr->t_u8 + (size_t)col0 * 128) + cand;
-        const uint4 qv = *(reinterpret_cast<const uint4*>(R.q_u8 + (size_t)qq * 128) + cand);
-        uint4 tv[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) tv[k] = tp[8 * k];
-        const uint32_t nn = (uint32_t)pr->t_nrm2[ok ? col : 0] + (uint32_t)R.q_nrm2[qq];
-        uint32_t pd[8];   // pd[k]: this lane's slice of q . (candidate row k)
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          uint32_t d = __dp4a(qv.x, tv[k].x, 0u);
-          d = __dp4a(qv.y, tv[k].y, d);
-          d = __dp4a(qv.z, tv[k].z, d);
-          pd[k] = __dp4a(qv.w, tv[k].w, d);
-        }
-        const bool b4 = (cand & 4) != 0, b2 = (cand & 2) != 0, b1 = (cand & 1) != 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t send = b4 ? pd[j] : pd[j + 4], keep = b4 ? pd[j + 4] : pd[j];
-          pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          const uint32_t send = b2 ? pd[j] : pd[j + 2], keep = b2 ? pd[j + 2] : pd[j];
-          pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        {
-          const uint32_t send = b1 ? pd[0] : pd[1], keep = b1 ? pd[1] : pd[0];
-          pd[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        }
-        dist = nn - 2u * pd[0];
-      }
-      uint32_t k0 = ok ? ((dist << 3) | (uint32_t)cand) : 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
-#pragma unroll
-      for (int off = 1; off <= 4; off <<= 1) {
-        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, off);
-        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, off);
-        const uint32_t hi = max(k0, o0);
-        k0 = min(k0, o0);
-        k1 = min(hi, min(k1, o1));
-      }
-      if (have && cand == 0) {
-        float d0 = 0.f, d1 = -1.f;   // d1 < 0: no second neighbour
-        int idx = -1;
-        if (k0 != 0xFFFFFFFFu) {
-          const uint32_t x0 = k0 >> 3;
-          // self check: the group's exact minimum must equal twice the tensor-core value
-          if ((float)x0 != 2.0f * s_v0[r]) atomicOr(R.err_flag, 1);
-          idx = s_g0[r] * GROUP + (int)(k0 & 7u);
-          // second distance: inside the group, or the bound from outside it (exact values both)
-          const float Lr = s_L[r];
-          float x1 = Lr < INF ? 2.0f * Lr : -1.0f;
-          if (k1 != 0xFFFFFFFFu) {
-            const float x2 = (float)(k1 >> 3);
-            x1 = (x1 < 0.0f || x2 < x1) ? x2 : x1;
-          }
-          if (ORB) {
-            d0 = (float)x0;
-            d1 = x1;
-          } else {
-            d0 = sqrtf((float)x0);
-            d1 = x1 >= 0.0f ? sqrtf(x1) : -1.0f;
-          }
-        }
-        s_d0[r] = d0; s_d1[r] = d1; s_idx[r] = idx;
-      }
-    }
-    __syncthreads();
-    if (q < R.nq) {
-      int idx = -1;
-      float d0 = 0.f;
-      if (survive) {
-        idx = s_idx[tid];
-        d0 = s_d0[tid];
-        const float d1 = s_d1[tid];
-        keep = (idx >= 0 && d1 >= 0.0f && (double)d0 < __dmul_rn(R.ratio, (double)d1)) ? 1 : 0;
-      }
-      const size_t o = ((size_t)pair * R.nq + q) * 2;
-      knn_idx[o] = idx;
-      knn_dist[o] = d0;
-      flags[(size_t)pair * R.nq + q] = (uint8_t)keep;
-    }
-  }
-  const int n = __syncthreads_count(keep);
-  if (tid == 0) chunk_cnt[pair * gridDim.x + blockIdx.x] = n;
+  const TcPair* pairs_tab = IT.n ? IT.pairs : R.pairs;
+  const int32_t* prefix_tab = IT.n ? IT.prefix : R.tile_prefix;
+  const int pair = blockIdx.y;
+  const bool gen_pair = R.q_flags[0] != 0 || pairs_tab[pair].t_flags[0] != 0;
+  tail_unit<ORB, 256, 256, 0, SU, false>(R, C, pairs_tab, prefix_tab, pair, blockIdx.x, blockIdx.x * 256, blockIdx.x,
+                                         gridDim.x, gen_pair, sm, threadIdx.x);
 }
 
 // The match path's tail as one kernel behind the tcgen05 kernel: a block per (256 query rows,
@@ -2458,9 +2281,16 @@ void launch_tc_tail_fused(const int32_t* q_flags, const uint8_t* q_u8, const int
   R.n_split = n_split; R.part = part; R.err_flag = err_flag;
   R.work = nullptr; R.work_v0 = nullptr; R.work_n = nullptr;
   R.prune = (ratio >= 0.0 && ratio < 1e300) ? 1 : 0; R.ratio = ratio;
+  CompactArgs C;
+  memset(&C, 0, sizeof(C));
+  C.knn_idx = knn_idx; C.knn_dist = knn_dist; C.flags = flags; C.chunk_cnt = chunk_cnt;
+  InlineTables IT;
+  IT.n = 0;
+  // (one survivor row per lane group and pass: with thousands of blocks in flight the occupancy of
+  // the 64-register form hides the latency; two rows in flight measured 3 % slower)
   dim3 grid((nq + 255) / 256, n_pairs);
-  if (orb) launch_pdl(tc_tail_fused_kernel<true>, grid, dim3(256), 0, s, R, knn_idx, knn_dist, flags, chunk_cnt);
-  else launch_pdl(tc_tail_fused_kernel<false>, grid, dim3(256), 0, s, R, knn_idx, knn_dist, flags, chunk_cnt);
+  if (orb) launch_pdl(tc_tail_fused_kernel<true, 1>, grid, dim3(256), 0, s, R, C, IT);
+  else launch_pdl(tc_tail_fused_kernel<false, 1>, grid, dim3(256), 0, s, R, C, IT);
   COUNT_LAUNCH();
 }
 
@@ -2486,6 +2316,7 @@ void launch_tc_tail_compact(const int32_t* q_flags, const uint8_t* q_u8, const i
   R.work = nullptr; R.work_v0 = nullptr; R.work_n = nullptr;
   R.prune = (ratio >= 0.0 && ratio < 1e300) ? 1 : 0; R.ratio = ratio;
   CompactArgs C;
+  memset(&C, 0, sizeof(C));
   C.scan = scan; C.epoch = epoch; C.out = out; C.cap = cap; C.n_out = n_out;
   // The tcgen05 kernel in front of this one (and behind it, in a loop of calls) runs with the
   // largest shared-memory carve-out; asking for the same one here spares the SMs a reconfiguration
